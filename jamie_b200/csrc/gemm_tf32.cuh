@@ -48,9 +48,11 @@ struct alignas(128) GemmProblem {
   int tiles_m, tiles_n, tile_base;
   int round_out;  // round the stored value to tf32 (it feeds another tensor-core GEMM)
   float slope;
-  uint32_t mn_lbo, mn_sbo;  // MN-major descriptor byte offsets (4096 / 1024 for this tiling)
+  uint32_t mn_lbo, mn_sbo;  // MN-major descriptor byte offsets (4096 / 512 for this tiling)
   int accumulate;           // C += result (fp32 atomics-free: one CTA owns the tile)
-  int pad_[3];
+  uint32_t mn_layout;       // UMMA layout type of MN-major operands (1 = SWIZZLE_128B_BASE32B)
+  int pad_[2];
+  long long* dbg;           // optional: per-CTA phase timestamps (bring-up lab only)
 };
 
 struct GemmCtrl {
@@ -91,6 +93,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   if (nstages > GEMM_MAX_STAGES) nstages = GEMM_MAX_STAGES;
   const uint32_t tmem_cols = bn < 32 ? 32u : static_cast<uint32_t>(bn);  // power of two >= 32
 
+  long long* dbg = P.dbg ? P.dbg + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[6] = static_cast<long long>(globaltimer_ns()); }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmA);
     tma_prefetch_desc(&P.tmB);
@@ -109,6 +113,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = ctrl->tmem_base;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -148,17 +153,19 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
         const uint32_t ph = (kb / nstages) & 1;
         mbar_wait(&ctrl->full[s], ph);
         tc_fence_after();
+        if (dbg && kb == 0) dbg[2] = clock64();
         const uint32_t sa = smem_u32(tiles + s * stage_bytes);
         const uint32_t sb = sa + GEMM_A_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-          const uint64_t da = umma_smem_desc_sw128(sa + k * a_step, a_lbo, a_sbo);
-          const uint64_t db = umma_smem_desc_sw128(sb + k * b_step, b_lbo, b_sbo);
+          const uint64_t da = umma_smem_desc(sa + k * a_step, a_lbo, a_sbo, P.a_mn ? P.mn_layout : 2u);
+          const uint64_t db = umma_smem_desc(sb + k * b_step, b_lbo, b_sbo, P.b_mn ? P.mn_layout : 2u);
           umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&ctrl->empty[s]);  // frees the smem slot when these MMAs have read it
       }
       umma_commit(&ctrl->tmem_full);  // accumulator complete
+      if (dbg) dbg[3] = clock64();
     }
     __syncwarp();
   } else {
@@ -167,6 +174,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
     const int row = m0 + q * 32 + lane;
     mbar_wait(&ctrl->tmem_full, 0);
     tc_fence_after();
+    if (dbg && warp == 2 && lane == 0) dbg[4] = clock64();
     const bool row_ok = row < P.M;
     float* crow = P.C + static_cast<size_t>(row_ok ? row : 0) * P.ldc;
     const bool vec_ok = (P.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(P.C) & 15) == 0;
@@ -206,8 +214,10 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
       }
     }
   }
+  if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[7] = static_cast<long long>(globaltimer_ns());
   if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
 }
 
@@ -231,7 +241,7 @@ inline PFN_tmapEncodeTiled tmap_encode_fn() {
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements, 128B swizzle,
 // out-of-bounds box elements read as zero.
 inline int make_tmap_2d(CUtensorMap* tm, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                        uint32_t box_inner, uint32_t box_outer, int dtype_tf32 = 0) {
+                        uint32_t box_inner, uint32_t box_outer, int dtype_tf32 = 1, int swizzle_atom32 = 0) {
   PFN_tmapEncodeTiled fn = tmap_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[2] = {inner, outer};
@@ -240,7 +250,8 @@ inline int make_tmap_2d(CUtensorMap* tm, const float* base, uint64_t inner, uint
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, dtype_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
@@ -254,14 +265,14 @@ inline int pick_bn(int N) {
 // Same for B with N. Returns 0 on success.
 inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
                              float* C, int ldc, int M, int N, int K, int bn, int epi, const float* bias,
-                             float slope, int round_out, int accumulate, int dtype_tf32 = 0) {
+                             float slope, int round_out, int accumulate, int dtype_tf32 = 1) {
   *g = GemmProblem{};
   int rc;
   if (!a_mn) rc = make_tmap_2d(&g->tmA, A, K, M, lda, GEMM_BK, GEMM_BM, dtype_tf32);
-  else rc = make_tmap_2d(&g->tmA, A, M, K, lda, 32, GEMM_BK, dtype_tf32);
+  else rc = make_tmap_2d(&g->tmA, A, M, K, lda, 32, GEMM_BK, dtype_tf32, 1);
   if (rc) return rc;
   if (!b_mn) rc = make_tmap_2d(&g->tmB, B, K, N, ldb, GEMM_BK, bn, dtype_tf32);
-  else rc = make_tmap_2d(&g->tmB, B, N, K, ldb, 32, GEMM_BK, dtype_tf32);
+  else rc = make_tmap_2d(&g->tmB, B, N, K, ldb, 32, GEMM_BK, dtype_tf32, 1);
   if (rc) return rc;
   g->C = C; g->bias = bias;
   g->M = M; g->N = N; g->K = K; g->ldc = ldc;
@@ -270,7 +281,7 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->tiles_n = (N + bn - 1) / bn;
   g->tile_base = 0;
   g->round_out = round_out; g->slope = slope;
-  g->mn_lbo = 4096; g->mn_sbo = 1024;
+  g->mn_lbo = 4096; g->mn_sbo = 512; g->mn_layout = 1;
   g->accumulate = accumulate;
   return 0;
 }

@@ -12,6 +12,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -127,16 +132,20 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 // ---------------------------------------------------------------- UMMA descriptors
-// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
+// Shared-memory matrix descriptor (sm_100 "version 1").
 //   bits [0,14)  start address >> 4       bits [16,30) leading byte offset >> 4
-//   bits [32,46) stride byte offset >> 4  bits [46,48) version = 1   bits [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   bits [32,46) stride byte offset >> 4  bits [46,48) version = 1   bits [61,64) layout type
+//   K-major operands use SWIZZLE_128B (layout 2); MN-major tf32 operands must use SWIZZLE_128B_BASE32B
+//   (layout 1: 32-byte swizzle atoms, 4 K-rows of 128 B per atom) -- the only MN-major layout the tensor core
+//   accepts for 32-bit elements.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;
   return d;
 }
 // Instruction descriptor, kind::tf32, fp32 accumulate, M = 128.

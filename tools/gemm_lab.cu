@@ -47,6 +47,7 @@ struct Case {
   int round_inputs;  // 1: host pre-rounds to tf32 (exact check); 0: raw fp32 inputs
   int tmap_tf32;     // tensor-map dtype TFLOAT32 instead of FLOAT32
   int epi;
+  uint32_t mn_layout = 1;
 };
 
 static int run_case(const Case& c, FILE* out) {
@@ -84,7 +85,7 @@ static int run_case(const Case& c, FILE* out) {
   int rc = jb::gemm_problem_fill(&g, dA, lda, c.a_mn, dB, ldb, c.b_mn, dC, ldc, M, N, K, c.bn, c.epi, dBias, 0.01f, 0,
                                  0, c.tmap_tf32);
   if (rc) { fprintf(out, "tensor map encode failed rc=%d\n", rc); return 1; }
-  g.mn_lbo = c.lbo; g.mn_sbo = c.sbo;
+  g.mn_lbo = c.lbo; g.mn_sbo = c.sbo; g.mn_layout = c.mn_layout;
   int tiles = jb::gemm_table_finalize(&g, 1);
   CK(cudaMemcpy(dT, &g, sizeof(g), cudaMemcpyHostToDevice));
   cudaError_t e = jb::gemm_launch(dT, 1, tiles, 0);
@@ -171,7 +172,7 @@ static int tma_probe(FILE* out) {
   return 0;
 }
 
-static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn, int nprob) {
+static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn, int nprob, int dump_dbg = 0) {
   const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
   float *dA, *dB, *dC;
   jb::GemmProblem* dT;
@@ -184,6 +185,12 @@ static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn,
     if (jb::gemm_problem_fill(&g[i], dA + asz * i, lda, a_mn, dB + bsz * i, ldb, b_mn, dC + csz * i, N, M, N, K, bn, 0,
                               nullptr, 0.f, 0, 0)) return 1;
   int tiles = jb::gemm_table_finalize(g.data(), nprob);
+  long long* dDbg = nullptr;
+  if (dump_dbg) {
+    CK(cudaMalloc(&dDbg, sizeof(long long) * 8 * tiles));
+    CK(cudaMemset(dDbg, 0, sizeof(long long) * 8 * tiles));
+    for (int i = 0; i < nprob; ++i) g[i].dbg = dDbg;
+  }
   CK(cudaMemcpy(dT, g.data(), sizeof(jb::GemmProblem) * nprob, cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -200,6 +207,19 @@ static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn,
   double tf = 2.0 * M * N * K * nprob / (us * 1e-6) / 1e12;
   fprintf(out, "time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%d tiles %d : %.2f us/launch  %.1f TFLOP/s (tf32)\n", nprob, M,
           N, K, a_mn, b_mn, bn, tiles, us, tf);
+  if (dump_dbg) {
+    std::vector<long long> h(8 * tiles);
+    CK(cudaMemcpy(h.data(), dDbg, sizeof(long long) * 8 * tiles, cudaMemcpyDeviceToHost));
+    long long gmin = h[6], gmax = h[7];
+    for (int t = 0; t < tiles; ++t) { if (h[8 * t + 6] < gmin) gmin = h[8 * t + 6]; if (h[8 * t + 7] > gmax) gmax = h[8 * t + 7]; }
+    fprintf(out, "  dbg: kernel span (globaltimer) %lld ns\n", gmax - gmin);
+    for (int t = 0; t < tiles; t += (tiles > 8 ? tiles / 8 : 1)) {
+      long long* d = &h[8 * t];
+      fprintf(out, "  cta %3d: setup %lld  first_full %lld  mma_issued %lld  tmem_full %lld  epi_done %lld (clk) | start +%lld ns, dur %lld ns\n",
+              t, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - gmin, d[7] - d[6]);
+    }
+    cudaFree(dDbg);
+  }
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT);
   return 0;
 }
@@ -233,34 +253,41 @@ int main(int argc, char** argv) {
   } else if (which == 1) {
     // dgrad layout: A K-major, B MN-major.
     const Case cs[] = {
-        {128, 128, 32, 0, 1, 128, 4096, 1024, 1, 0, 0},
-        {512, 512, 1024, 0, 1, 128, 4096, 1024, 1, 0, 0},
-        {300, 2000, 1000, 0, 1, 128, 4096, 1024, 1, 0, 0},
-        {512, 39, 78, 0, 1, 64, 4096, 1024, 1, 0, 0},
-        {512, 32, 512, 0, 1, 32, 4096, 1024, 1, 0, 0},
+        {128, 128, 32, 0, 1, 128, 4096, 512, 1, 1, 0},
+        {512, 512, 1024, 0, 1, 128, 4096, 512, 1, 1, 0},
+        {300, 2000, 1000, 0, 1, 128, 4096, 512, 1, 1, 0},
+        {512, 39, 78, 0, 1, 64, 4096, 512, 1, 1, 0},
+        {512, 32, 512, 0, 1, 32, 4096, 512, 1, 1, 0},
     };
     for (const Case& c : cs)
       if (run_case(c, out) == 2) return 2;
   } else if (which == 2) {
     // wgrad layout: both MN-major.
     const Case cs[] = {
-        {128, 128, 32, 1, 1, 128, 4096, 1024, 1, 0, 0},
-        {1024, 512, 512, 1, 1, 128, 4096, 1024, 1, 0, 0},
-        {2000, 1000, 300, 1, 1, 128, 4096, 1024, 1, 0, 0},
-        {78, 39, 512, 1, 1, 64, 4096, 1024, 1, 0, 0},
-        {512, 32, 512, 1, 1, 32, 4096, 1024, 1, 0, 0},
+        {128, 128, 32, 1, 1, 128, 4096, 512, 1, 1, 0},
+        {1024, 512, 512, 1, 1, 128, 4096, 512, 1, 1, 0},
+        {2000, 1000, 300, 1, 1, 128, 4096, 512, 1, 1, 0},
+        {78, 39, 512, 1, 1, 64, 4096, 512, 1, 1, 0},
+        {512, 32, 512, 1, 1, 32, 4096, 512, 1, 1, 0},
     };
     for (const Case& c : cs)
       if (run_case(c, out) == 2) return 2;
   } else if (which == 3) {
-    // alternative MN descriptor convention (LBO/SBO swapped) in case (1)/(2) mismatch
+    // alternative MN descriptor conventions in case (1)/(2) mismatch
     const Case cs[] = {
-        {128, 128, 32, 0, 1, 128, 1024, 4096, 1, 0, 0},
-        {128, 128, 32, 1, 1, 128, 1024, 4096, 1, 0, 0},
-        {512, 512, 1024, 0, 1, 128, 1024, 4096, 1, 0, 0},
+        {128, 128, 32, 0, 1, 128, 512, 4096, 1, 1, 0, 1},
+        {128, 128, 32, 0, 1, 128, 4096, 1024, 1, 1, 0, 1},
+        {128, 128, 32, 0, 1, 128, 1024, 512, 1, 1, 0, 1},
+        {128, 32, 32, 0, 1, 32, 4096, 512, 1, 1, 0, 1},
+        {128, 32, 8, 0, 1, 32, 4096, 512, 1, 1, 0, 1},
+        {128, 32, 8, 1, 0, 32, 4096, 512, 1, 1, 0, 1},
     };
     for (const Case& c : cs)
       if (run_case(c, out) == 2) return 2;
+  } else if (which == 5) {
+    time_case(out, 512, 1024, 512, 0, 0, 128, 2, 1);
+    time_case(out, 512, 1024, 512, 0, 0, 64, 2, 1);
+    time_case(out, 65536, 1024, 512, 0, 0, 256, 1, 1);
   } else if (which == 4) {
     time_case(out, 512, 1024, 512, 0, 0, 128, 2);
     time_case(out, 512, 1024, 512, 0, 0, 64, 2);
