@@ -1,0 +1,509 @@
+"""``JAMIE``: host-side mirror of the reference class (jamie/jamie.py:29-222, 416-837, 967-972) driving the CUDA engine.
+
+Same constructor arguments, methods, attributes, printed lines and error messages as the reference for the hot path
+(fit_transform -> project_jamie training loop, transform, transform_one, modal_predict, save_model, load_model).
+Everything numeric runs in ``libjamie_b200.so``: the per-step work of the reference loop (batch gather, P/F blocks,
+model forward, the four losses, backward, clip, Adam) is one CUDA-graph launch per optimizer step; the host keeps the
+numpy batch sampler (same draws, same order as the reference, so a seeded run visits the same cells), the epoch
+bookkeeping, early stopping and printing.
+
+Out of scope ("next" rows): estimating F with ``Prime_Dual`` / ``compute_distances``
+(jamie/jamie.py:224-414, 839-890) and the tsne projection branch.  ``use_f_tilde=True`` without a supplied
+``match_result`` therefore falls back to F = 0 with a RuntimeWarning.
+"""
+import os
+import time as _time
+import warnings
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .model import edModelVar
+from .unioncom_shim import UnionCom, init_random_seed
+from .utilities import make_pca, preclass, time_logger
+
+DISTANCE_MODES = [
+    'euclidean', 'l2', 'l1', 'manhattan', 'cityblock', 'braycurtis', 'canberra', 'chebyshev', 'correlation', 'cosine',
+    'dice', 'hamming', 'jaccard', 'kulsinski', 'mahalanobis', 'matching', 'minkowski', 'rogerstanimoto', 'russellrao',
+    'seuclidean', 'sokalmichener', 'sokalsneath', 'sqeuclidean', 'yule', 'wminkowski', 'nan_euclidean', 'haversine',
+    'geodesic', 'spearman', 'pearson',
+]
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class PriorSpec:
+    """Correspondence prior in the most compact form that reproduces the reference's dense-matrix semantics."""
+
+    def __init__(self, P, rows):
+        self.rows = rows
+        self.diag = None      # 1-D mask m: P = diag(m)
+        self.dense = None     # 2-D ndarray
+        if P is None:
+            # jamie/jamie.py:423-428: identity iff the datasets have the same number of rows, else zeros
+            if rows[0] == rows[1]:
+                self.diag = np.ones(rows[0], np.float32)
+        else:
+            if hasattr(P, 'toarray') and not isinstance(P, np.ndarray):   # scipy sparse
+                d = np.asarray(P.diagonal()).ravel() if P.shape[0] == P.shape[1] else None
+                if d is not None and P.count_nonzero() == np.count_nonzero(d):
+                    P = d
+                else:
+                    P = P.toarray()
+            P = np.asarray(P)
+            if P.ndim == 1:
+                assert rows[0] == rows[1] == P.shape[0], 'a 1-D prior is diag(m) and needs equally sized datasets'
+                self.diag = P.astype(np.float32)
+            else:
+                assert P.shape == (rows[0], rows[1]), f'P must be {rows[0]} x {rows[1]}'
+                if P.shape[0] == P.shape[1] and np.count_nonzero(P) == np.count_nonzero(np.diagonal(P)):
+                    self.diag = np.diagonal(P).astype(np.float32)
+                else:
+                    self.dense = P.astype(np.float32)
+        if self.diag is not None and not np.any(self.diag):
+            self.diag = None
+        # jamie/jamie.py:518-534
+        if self.diag is not None and np.all(self.diag == 1):
+            self.sampling_method = 'diag'
+        elif self.diag is not None or (self.dense is not None and np.abs(self.dense).sum() != 0):
+            self.sampling_method = 'hybrid'
+        else:
+            self.sampling_method = 'zeros'
+            self.dense = None
+        self.corr_samples = None
+        if self.sampling_method == 'hybrid':
+            # torch.argwhere(P > 0), of which the reference only ever reads rows 0 and 1 (jamie/jamie.py:525-526, 566)
+            if self.diag is not None:
+                nz = np.flatnonzero(self.diag > 0)[:2]
+                self.corr_samples = np.stack([nz, nz], axis=1)
+            else:
+                self.corr_samples = np.argwhere(self.dense > 0)[:2]
+            if len(self.corr_samples) < 2:
+                raise IndexError('hybrid sampling needs at least two positive entries in P')
+
+    def upload(self, engine):
+        if self.dense is not None:
+            engine.set_prior_dense(self.dense)
+        else:
+            engine.set_prior_diag(self.diag)
+
+    def to_dense(self):
+        if self.dense is not None:
+            return self.dense
+        if self.diag is not None:
+            return np.diag(self.diag)
+        return np.zeros(self.rows, np.float32)
+
+
+def sample_batch(method, rows, cols, batch_size, corr_samples=None):
+    """Batch indices of one optimizer step: jamie/jamie.py:553-579, same numpy draws in the same order."""
+    rep = min(ci for ci in cols) < batch_size
+    if method == 'diag':
+        set_rand = np.random.choice(range(rows[0]), batch_size, replace=rep)
+        return [set_rand, set_rand]
+    if method == 'hybrid':
+        num_corr = len(corr_samples[0])   # == 2: the reference's self.num_corr (jamie/jamie.py:526)
+        corr_sample_num = min(np.sum(np.random.rand(batch_size) < .8), num_corr)
+        non_sample_num = batch_size - corr_sample_num
+        corr_idx = np.random.choice(num_corr, corr_sample_num, replace=rep)
+        out = []
+        for i in range(2):
+            head = np.asarray(corr_samples[i])[corr_idx]
+            out.append(np.concatenate([head, np.random.choice(rows[i], non_sample_num, replace=rep)], axis=0))
+        return out
+    if method == 'zeros':
+        return [np.random.choice(range(rows[i]), batch_size, replace=rep) for i in range(2)]
+    raise Exception(f'Sampling method {method} does not exist')
+
+
+class JAMIE(UnionCom):
+    """
+    Adaptation of https://github.com/caokai1073/UnionCom by caokai1073
+
+    P: Correspondence prior matrix
+    PF_Ratio: Ratio of priors:assumed correspondence; .5 is equal, 1 is only P
+    in_place: Whether to do the calculation in place.  Will save memory but may
+        alter original data
+    """
+
+    def __init__(self, match_result=None, PF_Ratio=None, corr_method='unioncom', dist_method='euclidean',
+                 in_place=False, loss_weights=None, model_pca='pca', model_class=edModelVar, model_lr=1e-3,
+                 dropout=None, pca_dim=2 * [512], batch_step=True, use_f_tilde=True, use_early_stop=True,
+                 min_epochs=2500, min_increment=1e-8, max_steps_without_increment=500, debug=False, log_debug=100,
+                 record_loss=True, enable_memory_logging=False, device='cpu', **kwargs):
+        self.match_result = match_result
+        self.PF_Ratio = PF_Ratio
+        self.corr_method = corr_method
+        self.dist_method = dist_method
+        self.in_place = in_place
+        self.loss_weights = loss_weights
+        self.model_pca = model_pca
+        self.model_class = model_class
+        self.model_lr = model_lr
+        self.dropout = dropout
+        self.pca_dim = pca_dim
+        self.batch_step = batch_step
+        self.use_f_tilde = use_f_tilde
+        self.use_early_stop = use_early_stop
+        self.min_epochs = min_epochs
+        self.min_increment = min_increment
+        self.max_steps_without_increment = max_steps_without_increment
+        self.debug = debug
+        self.log_debug = log_debug
+        self.record_loss = record_loss
+        self.enable_memory_logging = enable_memory_logging
+        # The reference defaults to 'cpu' and warns that its GPU path is incomplete (jamie/jamie.py:88-96).
+        # This implementation has exactly one path, the CUDA engine: any value selects the process's CUDA device.
+        self.device = device
+        defaults = {'project_mode': 'jamie', 'log_pd': 500, 'lr': 1e-3, 'epoch_DNN': 10000, 'log_DNN': 500,
+                    'batch_size': 512}
+        for k, v in defaults.items():
+            if k not in kwargs:
+                kwargs[k] = v
+        super().__init__(**kwargs)
+        self.model = None
+        self.engine = None
+        self.P = None
+        self.F = None
+        self.dataset = None
+        self.dataset_num = 2
+
+    # ------------------------------------------------------------------------------------------------ device
+    def _cuda_index(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError('jamie_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        dev = str(self.device)
+        if dev.startswith('cuda:'):
+            return int(dev.split(':')[1])
+        return int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    # ------------------------------------------------------------------------------------------------ fit
+    def fit_transform(self, dataset=None, P=None):
+        """Fit function with ``nlma`` added"""
+        self.P = P
+        if self.integration_type not in ['MultiOmics']:
+            raise Exception('integration_type error! Enter MultiOmics.')
+        if self.distance_mode not in DISTANCE_MODES:
+            raise Exception('distance_mode error! Enter a correct distance_mode.')
+        if self.project_mode not in ('jamie', 'tsne'):
+            raise Exception("Choose correct project_mode: 'nlma', 'tsne'.")
+        assert self.model_pca in ('pca', 'umap')
+        if self.project_mode == 'tsne':
+            raise NotImplementedError("project_mode='tsne' (UnionCom's legacy projection) is outside this build's scope")
+        if self.model_pca != 'pca':
+            raise NotImplementedError("model_pca='umap' is outside this build's scope")
+
+        time = time_logger(memory_usage=self.enable_memory_logging)
+        init_random_seed(self.manual_seed)
+
+        # Test for dataset type (must all be the same): AnnData inputs carry the matrix in .X
+        self.dataset = dataset
+        self.dataset_annotation = None
+        if not isinstance(self.dataset[0], np.ndarray) and hasattr(self.dataset[0], 'X'):
+            self.dataset = [d.X for d in self.dataset]
+            self.dataset_annotation = dataset
+        if not self.in_place:
+            self.dataset = [d * 1 for d in self.dataset]
+        self.dataset_num = len(self.dataset)
+        self.col = []
+        self.row = []
+        for i in range(self.dataset_num):
+            self.row.append(np.shape(self.dataset[i])[0])
+            self.col.append(np.shape(self.dataset[i])[1])
+        time.log('Distance')
+
+        # Correspondence between samples: supplied, or zeros (use_f_tilde=False, jamie/jamie.py:172-173).
+        # The reference's per-pair linear_sum_assignment (jamie/jamie.py:177-181) only feeds the tsne branch: skipped.
+        if not self.use_f_tilde:
+            self.match_result = None
+            self._F_dense = None
+        elif self.match_result is None:
+            warnings.warn(
+                'Estimating F (Prime_Dual on geodesic distances) is outside this build; continuing with F = 0 as if '
+                'use_f_tilde=False. Pass match_result=[F] to supply a correspondence estimate.', RuntimeWarning)
+            self._F_dense = None
+        else:
+            self._F_dense = np.asarray(self.match_result[0], np.float32)
+        time.log('Correspondence')
+
+        integrated_data = self.project_jamie(None)
+        time.log('Mapping')
+
+        print('-' * 33)
+        print('JAMIE Done!')
+        time.aggregate()
+        print()
+        return integrated_data
+
+    # ------------------------------------------------------------------------------------------------ train
+    def project_jamie(self, W=None):
+        """Perform alignment using TSNE-like backend"""
+        print('-' * 33)
+        print('Train coupled autoencoders')
+        assert self.dataset_num == 2, 'Currently only compatible with 2 modalities.'
+        rank, world = _dist_info()
+        timer = time_logger()
+
+        # ---- preprocessing (jamie/jamie.py:433-469): PCA fit on the host, standardise, keep the inverse
+        pca_list, pca_inv_list = [], []
+        dims_req = self.pca_dim if self.pca_dim is not None else [None] * self.dataset_num
+        for dim, data in zip(dims_req, self.dataset):
+            if dim is not None:
+                if min(*data.shape) < dim:
+                    warnings.warn(
+                        f'PCA dim must be lower than {min(*data.shape)}, found {dim}, '
+                        f'adjusting to compensate.')
+                    dim = min(*data.shape)
+                pca = make_pca(dim)
+                sample = pca.fit_transform(data)
+                pre = preclass(sample, pca=pca)
+            else:
+                pre = preclass(data, axis=0)
+            pca_list.append(pre.transform)
+            pca_inv_list.append(pre.inverse_transform)
+        self.dataset = [f(x) for f, x in zip(pca_list, self.dataset)]
+        self.col = [x.shape[1] for x in self.dataset]
+
+        # ---- model + optimizer state (jamie/jamie.py:471-481)
+        self.model = self.model_class(self.col, self.output_dim, preprocessing=pca_list,
+                                      preprocessing_inverse=pca_inv_list, dropout=self.dropout)
+        # Batch size setup (jamie/jamie.py:510-514); with R data-parallel ranks an epoch is max(row)/(B*R) steps
+        len_dataloader = int(np.max(self.row) / (self.batch_size * world))
+        if len_dataloader == 0:
+            len_dataloader = 1
+            if world == 1:
+                self.batch_size = int(np.max(self.row))
+        self.PF_Ratio = 1 if self.PF_Ratio is None else self.PF_Ratio
+
+        # ---- shard the cells over the data-parallel ranks (contiguous ranges; world == 1: everything)
+        lo = [(r_ * rank) // world for r_ in self.row]
+        hi = [(r_ * (rank + 1)) // world for r_ in self.row]
+        prior_full = PriorSpec(self.P, self.row)
+        self.sampling_method = prior_full.sampling_method
+        self.P = prior_full   # compact prior; .to_dense() materialises the reference's matrix (small n only)
+        if world == 1:
+            prior = prior_full
+            F_local = self._F_dense
+        else:
+            if prior_full.diag is not None:
+                prior = PriorSpec(prior_full.diag[lo[0]:hi[0]], [hi[0] - lo[0], hi[1] - lo[1]])
+            elif prior_full.dense is not None:
+                prior = PriorSpec(prior_full.dense[lo[0]:hi[0], lo[1]:hi[1]], [hi[0] - lo[0], hi[1] - lo[1]])
+            else:
+                prior = PriorSpec(np.zeros((hi[0] - lo[0], hi[1] - lo[1]), np.float32), [hi[0] - lo[0], hi[1] - lo[1]])
+            F_local = None if self._F_dense is None else self._F_dense[lo[0]:hi[0], lo[1]:hi[1]]
+        local_rows = [hi[i] - lo[i] for i in range(2)]
+        self.F = F_local
+
+        dev = self._cuda_index()
+        torch.cuda.set_device(dev)
+        if self.dist_method != 'euclidean':
+            raise NotImplementedError("only dist_method='euclidean' (the reference default) is built")
+        self.engine = Engine(self.col, self.output_dim, self.batch_size, self.model.dropout_p, lr=self.model_lr,
+                             loss_weights=self.loss_weights, pf_ratio=self.PF_Ratio,
+                             seed=(self.manual_seed or 0) * 1000003 + rank, device=dev, world_size=world)
+        eng = self.engine
+        self.model.attach_engine(eng)
+        self.model.push_to_engine()
+        stream = self._stream()
+        for i in range(2):
+            eng.set_dataset(i, np.asarray(self.dataset[i][lo[i]:hi[i]], np.float32), stream)
+        prior.upload(eng)
+        eng.set_f_dense(F_local)
+        if not self.batch_step:
+            eng.set_grad_accumulate(False)
+        if world > 1:
+            import torch.distributed as dist
+            gt = eng.grad_tensor()
+        self.model.train()
+
+        best_running_loss = np.inf
+        streak = 0
+        if self.record_loss:
+            self.loss_history = {}
+        names = ['KL', 'Rec', 'CosSim', 'F']
+        lw = self.loss_weights
+        c = (self.min_epochs / 2) if self.min_epochs > 0 else (self.epoch_DNN / 2)  # Midpoint (jamie/jamie.py:630)
+        timer.log('Setup')
+
+        epoch = 0
+        stop = False
+        t_sample = t_step = 0.0
+        while epoch < self.epoch_DNN and not stop:
+            # Epochs that can be issued without a host decision in between: early stopping cannot trigger before
+            # the streak reaches max_steps_without_increment, and the streak grows by at most one per epoch and only
+            # once epoch > min_epochs (jamie/jamie.py:782-792).
+            safe = max(1, (self.min_epochs + 1 - epoch) if epoch <= self.min_epochs else 0) \
+                + max(0, self.max_steps_without_increment - streak - 1) if self.use_early_stop else self.epoch_DNN
+            n_ep = int(min(self.epoch_DNN - epoch, max(1, safe), max(1, 4096 // len_dataloader)))
+            t0 = _time.perf_counter()
+            idx0 = np.empty((n_ep * len_dataloader, self.batch_size), np.int64)
+            idx1 = np.empty_like(idx0)
+            anneal = np.empty(n_ep * len_dataloader, np.float64)
+            for e_ in range(n_ep):
+                kl_anneal = 1 / (1 + np.exp(-5 * ((epoch + e_) - c) / c))
+                for b_ in range(len_dataloader):
+                    rb = sample_batch(prior.sampling_method, local_rows, self.col, self.batch_size, prior.corr_samples)
+                    idx0[e_ * len_dataloader + b_] = rb[0]
+                    idx1[e_ * len_dataloader + b_] = rb[1]
+                    anneal[e_ * len_dataloader + b_] = kl_anneal
+            t1 = _time.perf_counter()
+            t_sample += t1 - t0
+            eng.upload_plan(idx0, idx1, anneal, stream)
+            nsteps = n_ep * len_dataloader
+            if world == 1 and self.batch_step:
+                eng.train_steps(nsteps, stream)
+            else:
+                for s_ in range(nsteps):
+                    if not self.batch_step:
+                        eng.set_grad_accumulate(s_ % len_dataloader != 0)
+                    eng.step_backward(stream)
+                    last_of_epoch = (s_ + 1) % len_dataloader == 0
+                    if self.batch_step or last_of_epoch:
+                        if world > 1:
+                            dist.all_reduce(gt)
+                        eng.step_update(stream)
+            losses = eng.read_losses(nsteps, stream)          # one device->host read per chunk of epochs
+            if world > 1:
+                lt = torch.from_numpy(losses).cuda()
+                dist.all_reduce(lt)
+                losses = (lt / world).cpu().numpy()
+            t_step += _time.perf_counter() - t1
+
+            for e_ in range(n_ep):
+                blk = losses[e_ * len_dataloader:(e_ + 1) * len_dataloader]
+                tot = blk[:, 4].astype(np.float64)
+                if not np.all(np.isfinite(tot)):
+                    raise FloatingPointError(f'non-finite loss at epoch {epoch + 1}; your lr is likely too high')
+                epoch_loss = float(tot.sum() / len_dataloader)
+                best_batch_loss = float(tot.min())
+                last = blk[-1]
+                # Loss reporting: last batch of the epoch, weighted (jamie/jamie.py:752-761)
+                if self.record_loss:
+                    for k, name in enumerate(names):
+                        self.loss_history.setdefault(name, []).append(float(last[k]) * (lw[k] if lw is not None else 1))
+                if (epoch + 1) % self.log_debug == 0 and self.debug:
+                    if lw is not None:
+                        print(f'Epoch: {epoch + 1:d} - ' + '  '.join(
+                            f'{names[k]}: {last[k] * lw[k]:.4f}' for k in range(4)))
+                    else:
+                        print('  '.join(f'{names[k]}: {last[k]:.4f}' for k in range(4)))
+                if (epoch + 1) % self.log_DNN == 0:
+                    print(f'epoch:[{epoch + 1:d}/{self.epoch_DNN}]: loss:{epoch_loss:4f}')
+                # Early stopping (jamie/jamie.py:777-792)
+                active_loss = best_batch_loss if self.batch_step else epoch_loss
+                if epoch > self.min_epochs:
+                    epsilon = best_running_loss - active_loss
+                    if epsilon > self.min_increment:
+                        best_running_loss = active_loss
+                        streak = 0
+                    else:
+                        streak += 1
+                    if streak >= self.max_steps_without_increment and self.use_early_stop:
+                        stop = True
+                        epoch += 1
+                        assert e_ == n_ep - 1, 'early stop inside a chunk: the chunk bound is wrong'
+                        break
+                epoch += 1
+        self.epochs_run = epoch
+        timer.add('Get subset samples', t_sample, max(1, epoch * len_dataloader))
+        timer.add('Step', t_step, max(1, epoch * len_dataloader))
+
+        # ---- final encode (jamie/jamie.py:794-799): eval mode, z = mu; the n x n `corr` of the reference does not
+        # influence the returned embeddings and is never built
+        self.model.eval()
+        if world > 1:
+            self._average_bn_stats()
+        self.model.pull_from_engine()
+        integrated_data = [eng.encode(i, np.asarray(self.dataset[i], np.float32), stream) for i in range(2)]
+        timer.log('Output')
+        print("Finished Mapping!")
+        if self.debug:
+            timer.aggregate()
+        return integrated_data
+
+    def _average_bn_stats(self):
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        st = self.engine.get_bn_stats()
+        keys = [k for k in st if not k.endswith('num_batches_tracked')]
+        flat = torch.from_numpy(np.concatenate([st[k] for k in keys])).cuda()
+        dist.all_reduce(flat)
+        flat = (flat / world).cpu().numpy()
+        o = 0
+        for k in keys:
+            st[k] = flat[o:o + st[k].size]
+            o += st[k].size
+        self.engine.set_bn_stats(st)
+
+    # ------------------------------------------------------------------------------------------------ inference
+    def _ensure_engine(self):
+        assert self.model is not None, 'Model must be trained before modal prediction.'
+        if self.model.engine() is None:
+            dev = self._cuda_index()
+            torch.cuda.set_device(dev)
+            dims = self.model.input_dims
+            eng = Engine(dims, self.model.output_dim, max(2, int(getattr(self, 'batch_size', 512) or 512)),
+                         self.model.dropout_p, device=dev)
+            self.model.attach_engine(eng)
+            self.model.push_to_engine()
+            self.engine = eng
+        return self.model.engine()
+
+    def modal_predict(self, data, modality, pre_transformed=False):
+        """Predict the opposite modality from dataset ``data`` in modality ``modality``"""
+        assert self.model is not None, 'Model must be trained before modal prediction.'
+        eng = self._ensure_engine()
+        to_modality = (modality + 1) % self.dataset_num
+        if not pre_transformed:
+            data = self.model.preprocessing[modality](data)
+        decoded = eng.predict(modality, to_modality, np.asarray(data, np.float32), self._stream())
+        return np.array(self.model.preprocessing_inverse[to_modality](decoded))
+
+    def transform(self, dataset, corr=None, pre_transformed=False):
+        """Transform data using an already trained model"""
+        eng = self._ensure_engine()
+        if not pre_transformed:
+            dataset = [self.model.preprocessing[i](dataset[i]) for i in range(len(dataset))]
+        return [eng.encode(i, np.asarray(d, np.float32), self._stream()) for i, d in enumerate(dataset)]
+
+    def transform_one(self, data, i, pre_transformed=False):
+        """Transform data using an already trained model"""
+        eng = self._ensure_engine()
+        if not pre_transformed:
+            data = self.model.preprocessing[i](data)
+        return eng.encode(i, np.asarray(data, np.float32), self._stream())
+
+    # ------------------------------------------------------------------------------------------------ metrics
+    def test_closer(self, integrated_data, distance_metric=None):
+        """FOSCTTM (jamie/jamie.py:892-913)"""
+        from .evaluation import foscttm
+        return foscttm(integrated_data[0], integrated_data[1])
+
+    def test_LabelTA(self, integrated_data, datatype, k=None, return_k=False):
+        """Label transfer accuracy (jamie/jamie.py:943-961)"""
+        from .evaluation import label_transfer_accuracy
+        return label_transfer_accuracy(integrated_data, datatype, k=k, return_k=return_k)
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def save_model(self, f):
+        if self.model.engine() is not None:
+            self.model.pull_from_engine()
+        torch.save(self.model, f)
+
+    def load_model(self, f):
+        import jamie  # noqa: F401  (makes jamie.model / jamie.utilities importable for the unpickler)
+        self.model = torch.load(f, weights_only=False)
+        self.dataset_num = self.model.num_modalities
+        self.engine = None
+        self._ensure_engine()

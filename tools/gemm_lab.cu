@@ -48,6 +48,7 @@ struct Case {
   int tmap_tf32;     // tensor-map dtype TFLOAT32 instead of FLOAT32
   int epi;
   uint32_t mn_layout = 1;
+  int ks = 1;
 };
 
 static int run_case(const Case& c, FILE* out) {
@@ -83,12 +84,12 @@ static int run_case(const Case& c, FILE* out) {
   CK(cudaMemcpy(dBias, hBias.data(), N * 4, cudaMemcpyHostToDevice));
   jb::GemmProblem g;
   int rc = jb::gemm_problem_fill(&g, dA, lda, c.a_mn, dB, ldb, c.b_mn, dC, ldc, M, N, K, c.bn, c.epi, dBias, 0.01f, 0,
-                                 0, c.tmap_tf32);
+                                 c.tmap_tf32);
   if (rc) { fprintf(out, "tensor map encode failed rc=%d\n", rc); return 1; }
-  g.mn_lbo = c.lbo; g.mn_sbo = c.sbo; g.mn_layout = c.mn_layout;
+  g.mn_lbo = c.lbo; g.mn_sbo = c.sbo; g.mn_layout = c.mn_layout; g.ks = c.ks;
   int tiles = jb::gemm_table_finalize(&g, 1);
   CK(cudaMemcpy(dT, &g, sizeof(g), cudaMemcpyHostToDevice));
-  cudaError_t e = jb::gemm_launch(dT, 1, tiles, 0);
+  cudaError_t e = jb::gemm_launch<true>(dT, 1, tiles, 0);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     fprintf(out, "M%d N%d K%d a_mn%d b_mn%d bn%d lbo%u sbo%u : LAUNCH ERROR %s\n", M, N, K, c.a_mn, c.b_mn, c.bn, c.lbo,
@@ -114,9 +115,9 @@ static int run_case(const Case& c, FILE* out) {
       max_ref = fmax(max_ref, fabs(acc));
     }
   fprintf(out,
-          "M%-4d N%-4d K%-4d a_mn%d b_mn%d bn%-3d lbo%-4u sbo%-4u rnd%d tmtf32 %d epi%d : max_err %.3e (vs trunc-ref %.3e) "
+          "M%-4d N%-4d K%-4d a_mn%d b_mn%d bn%-3d ks%d sbo%-4u rnd%d tmtf32 %d epi%d : max_err %.3e (vs trunc-ref %.3e) "
           "max_ref %.3e  %s\n",
-          M, N, K, c.a_mn, c.b_mn, c.bn, c.lbo, c.sbo, c.round_inputs, c.tmap_tf32, c.epi, max_err, max_err_tr, max_ref,
+          M, N, K, c.a_mn, c.b_mn, c.bn, c.ks, c.sbo, c.round_inputs, c.tmap_tf32, c.epi, max_err, max_err_tr, max_ref,
           (max_err < 2e-5 * max_ref * (c.round_inputs ? 1 : 200)) ? "OK" : "MISMATCH");
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dBias); cudaFree(dT);
   return 0;
@@ -172,7 +173,8 @@ static int tma_probe(FILE* out) {
   return 0;
 }
 
-static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn, int nprob, int dump_dbg = 0) {
+static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn, int nprob, int dump_dbg = 0,
+                     int ks = 1, int dbg_mode = 0) {
   const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
   float *dA, *dB, *dC;
   jb::GemmProblem* dT;
@@ -183,7 +185,7 @@ static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn,
   std::vector<jb::GemmProblem> g(nprob);
   for (int i = 0; i < nprob; ++i)
     if (jb::gemm_problem_fill(&g[i], dA + asz * i, lda, a_mn, dB + bsz * i, ldb, b_mn, dC + csz * i, N, M, N, K, bn, 0,
-                              nullptr, 0.f, 0, 0)) return 1;
+                              nullptr, 0.f, 0)) return 1;
   int tiles = jb::gemm_table_finalize(g.data(), nprob);
   long long* dDbg = nullptr;
   if (dump_dbg) {
@@ -191,32 +193,30 @@ static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn,
     CK(cudaMemset(dDbg, 0, sizeof(long long) * 8 * tiles));
     for (int i = 0; i < nprob; ++i) g[i].dbg = dDbg;
   }
+  for (int i = 0; i < nprob; ++i) { g[i].ks = ks; g[i].dbg_mode = dbg_mode; }
   CK(cudaMemcpy(dT, g.data(), sizeof(jb::GemmProblem) * nprob, cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 5; ++i) jb::gemm_launch(dT, nprob, tiles, 0);
+  for (int i = 0; i < 5; ++i) jb::gemm_launch<true>(dT, nprob, tiles, 0);
   CK(cudaDeviceSynchronize());
   const int iters = 50;
   cudaEventRecord(e0);
-  for (int i = 0; i < iters; ++i) jb::gemm_launch(dT, nprob, tiles, 0);
+  for (int i = 0; i < iters; ++i) jb::gemm_launch<true>(dT, nprob, tiles, 0);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   double us = ms * 1000.0 / iters;
   double tf = 2.0 * M * N * K * nprob / (us * 1e-6) / 1e12;
-  fprintf(out, "time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%d tiles %d : %.2f us/launch  %.1f TFLOP/s (tf32)\n", nprob, M,
-          N, K, a_mn, b_mn, bn, tiles, us, tf);
+  fprintf(out, "time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%d ks%d mode%d tiles %d : %.2f us/launch  %.1f TFLOP/s (tf32)\n",
+          nprob, M, N, K, a_mn, b_mn, bn, ks, dbg_mode, tiles, us, tf);
   if (dump_dbg) {
     std::vector<long long> h(8 * tiles);
     CK(cudaMemcpy(h.data(), dDbg, sizeof(long long) * 8 * tiles, cudaMemcpyDeviceToHost));
-    long long gmin = h[6], gmax = h[7];
-    for (int t = 0; t < tiles; ++t) { if (h[8 * t + 6] < gmin) gmin = h[8 * t + 6]; if (h[8 * t + 7] > gmax) gmax = h[8 * t + 7]; }
-    fprintf(out, "  dbg: kernel span (globaltimer) %lld ns\n", gmax - gmin);
     for (int t = 0; t < tiles; t += (tiles > 8 ? tiles / 8 : 1)) {
       long long* d = &h[8 * t];
-      fprintf(out, "  cta %3d: setup %lld  first_full %lld  mma_issued %lld  tmem_full %lld  epi_done %lld (clk) | start +%lld ns, dur %lld ns\n",
-              t, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - gmin, d[7] - d[6]);
+      fprintf(out, "  cta %3d: setup %lld  first_full %lld  mma_issued %lld  tmem_full %lld  epi_done %lld (clk)\n",
+              t, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0]);
     }
     cudaFree(dDbg);
   }
@@ -248,8 +248,11 @@ int main(int argc, char** argv) {
         {512, 512, 512, 0, 0, 128, 4096, 1024, 0, 0, 0},
         {512, 512, 512, 0, 0, 128, 4096, 1024, 0, 1, 0},
     };
-    for (const Case& c : base)
-      if (run_case(c, out) == 2) return 2;
+    for (int ks = 1; ks <= 4; ks *= 2)
+      for (Case c : base) {
+        c.ks = ks;
+        if (run_case(c, out) == 2) return 2;
+      }
   } else if (which == 1) {
     // dgrad layout: A K-major, B MN-major.
     const Case cs[] = {
@@ -259,8 +262,11 @@ int main(int argc, char** argv) {
         {512, 39, 78, 0, 1, 64, 4096, 512, 1, 1, 0},
         {512, 32, 512, 0, 1, 32, 4096, 512, 1, 1, 0},
     };
-    for (const Case& c : cs)
-      if (run_case(c, out) == 2) return 2;
+    for (int ks = 1; ks <= 2; ks *= 2)
+      for (Case c : cs) {
+        c.ks = ks;
+        if (run_case(c, out) == 2) return 2;
+      }
   } else if (which == 2) {
     // wgrad layout: both MN-major.
     const Case cs[] = {
@@ -285,9 +291,22 @@ int main(int argc, char** argv) {
     for (const Case& c : cs)
       if (run_case(c, out) == 2) return 2;
   } else if (which == 5) {
-    time_case(out, 512, 1024, 512, 0, 0, 128, 2, 1);
-    time_case(out, 512, 1024, 512, 0, 0, 64, 2, 1);
-    time_case(out, 65536, 1024, 512, 0, 0, 256, 1, 1);
+    for (int mode = 0; mode < 1; ++mode)
+      for (int ks = 1; ks <= 4; ks *= 2) {
+        time_case(out, 512, 1024, 512, 0, 0, 128, 2, 1, ks, mode);
+        time_case(out, 512, 1024, 512, 0, 0, 64, 2, 1, ks, mode);
+      }
+    for (int mode = 3; mode <= 6; mode += 3) {
+      time_case(out, 512, 1024, 512, 0, 0, 128, 2, 1, 1, mode);
+      time_case(out, 512, 1024, 512, 0, 0, 64, 2, 1, 1, mode);
+      time_case(out, 512, 1024, 512, 0, 0, 128, 2, 1, 4, mode);
+    }
+    time_case(out, 1024, 512, 512, 1, 1, 128, 2, 1, 1, 0);
+    time_case(out, 1024, 512, 512, 1, 1, 128, 2, 1, 2, 0);
+    time_case(out, 512, 512, 1024, 0, 1, 128, 2, 1, 2, 0);
+    time_case(out, 65536, 1024, 512, 0, 0, 256, 1, 1, 1, 0);
+    time_case(out, 65536, 1024, 512, 0, 0, 256, 1, 1, 2, 0);
+    time_case(out, 65536, 1024, 512, 0, 0, 128, 1, 1, 2, 0);
   } else if (which == 4) {
     time_case(out, 512, 1024, 512, 0, 0, 128, 2);
     time_case(out, 512, 1024, 512, 0, 0, 64, 2);
