@@ -101,6 +101,23 @@ int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats);
  * accumulate != 0 makes the next backward add into the gradient buffer instead of overwriting it. */
 int jb_set_grad_accumulate(jb_engine* e, int accumulate);
 
+/* One optimizer step whose batch arrives from HOST memory (the reference keeps self.dataset wherever `device` says;
+ * this is the end-to-end form for host-resident data): x0/x1 = the gathered rows data[i][idx_i] ([batch, dims[i]],
+ * packed, ideally pinned), idx0/idx1 = their global cell ids (needed for the P/F blocks), kl_anneal as in
+ * jb_upload_plan. Copies the batch in, runs the step graph, copies the 8 loss scalars out and synchronises. */
+int jb_train_step_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
+                            int batch, double kl_anneal, float out_losses[8], void* stream);
+
+/* Data-parallel form of the host-batch step: copy the batch in and run forward + backward only; the caller then
+ * all-reduces jb_grad_buffer and calls jb_step_update, and reads the losses with jb_read_losses(e, out, 1, stream). */
+int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0,
+                               const long long* idx1, int batch, double kl_anneal, void* stream);
+
+/* Benchmark hook: launch GEMM stage `stage` of the training step (0..5 forward: enc1, enc2, heads, dec1, dec2, dec3;
+ * 6..11 backward in execution order) `iters` times on `stream`, timed with CUDA events on that stream.
+ * Returns the average microseconds per launch and the FLOPs of one launch. */
+int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* flops, void* stream);
+
 /* Per-step results of the steps run since the last jb_upload_plan, in plan order. Synchronises `stream`.
  * out[s*8 + k]: k=0..3 the reference's `losses` list (KL incl. 0.032*anneal, Rec, 32*CosSim, F; unweighted by
  * loss_weights), k=4 weighted total (batch_loss), k=5 pre-clip gradient norm, k=6,7 reserved. */

@@ -97,7 +97,7 @@ struct jb_engine {
   float* data[2]{};
   long long data_n[2]{}, data_ld[2]{};
   float *p_diag = nullptr, *p_dense = nullptr, *f_dense = nullptr;
-  long long pn0 = 0, pn1 = 0;
+  long long pn0 = 0, pn1 = 0, p_diag_n = 0;
   // plan
   int *plan_idx[2]{};
   float* plan_kl = nullptr;
@@ -117,7 +117,9 @@ struct jb_engine {
   GemmStage st_f[6], st_b[6];
   int graph_B = 0;
   bool graph_accum = false;
-  cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr;
+  cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr, g_host = nullptr, g_host_bwd = nullptr;
+  int* h_pin = nullptr;      // pinned staging for the host-batch step (2 x batch indices + 16 floats)
+  int launches_host = 0, launches_host_bwd = 0;
   cudaStream_t cap_stream = nullptr;
   int accumulate = 0;
   bool pending_inject = false;
@@ -378,7 +380,7 @@ jb::Latent make_latent(jb_engine* e) {
   return a;
 }
 
-void record_backward(jb_engine* e, Rec& r, int B) {
+void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   const int L = e->L;
   const float p = e->cfg.dropout;
   const int accum = e->accumulate;
@@ -392,7 +394,7 @@ void record_backward(jb_engine* e, Rec& r, int B) {
     ga.data[i] = e->data[i]; ga.ld_data[i] = e->data_ld[i]; ga.x[i] = e->act[i].x; ga.ldx[i] = e->act[i].ldD;
     ga.D[i] = e->D[i]; ga.idx[i] = e->plan_idx[i];
   }
-  jb::k_gather<<<dim3(B, 2), 128, 0, r.s>>>(ga, e->ctl, B); r.check();
+  if (gather) { jb::k_gather<<<dim3(B, 2), 128, 0, r.s>>>(ga, e->ctl, B); r.check(); }
   jb::CorrArgs ca{};
   ca.p_diag = e->p_diag; ca.p_dense = e->p_dense; ca.f_dense = e->f_dense; ca.n1 = e->pn1;
   ca.idx[0] = e->plan_idx[0]; ca.idx[1] = e->plan_idx[1]; ca.rs_p = e->rs_p; ca.rs_f = e->rs_f;
@@ -496,7 +498,8 @@ int capture(jb_engine* e, int B, int what /*0 full,1 bwd,2 upd*/, cudaGraphExec_
   CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   Rec r{e, e->cap_stream};
   if (what == 0 || what == 1) record_backward(e, r, B);
-  if (what == 0 || what == 2) record_update(e, r, B);
+  if (what == 3 || what == 4) record_backward(e, r, B, false);
+  if (what == 0 || what == 2 || what == 3) record_update(e, r, B);
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
   if (r.err != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail("kernel launch failed during capture: %s", cudaGetErrorString(r.err)); }
   if (ce != cudaSuccess) return fail("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
@@ -510,12 +513,15 @@ int capture(jb_engine* e, int B, int what /*0 full,1 bwd,2 upd*/, cudaGraphExec_
 
 int ensure_graphs(jb_engine* e, int B) {
   const bool acc = e->accumulate != 0;
-  if (e->graph_B == B && e->graph_accum == acc && e->g_full) return 0;
-  if (!e->data[0] || !e->data[1]) return fail("jb_set_dataset must be called for both modalities before stepping");
+  if (e->graph_B == B && e->graph_accum == acc && e->g_upd) return 0;
   if (build_train_tables(e, B, e->accumulate)) return 1;
-  if (capture(e, B, 0, &e->g_full, &e->launches_per_step)) return 1;
-  if (capture(e, B, 1, &e->g_bwd, &e->launches_bwd)) return 1;
+  if (e->data[0] && e->data[1]) {   // the gathering graphs need resident datasets; the host-batch graph does not
+    if (capture(e, B, 0, &e->g_full, &e->launches_per_step)) return 1;
+    if (capture(e, B, 1, &e->g_bwd, &e->launches_bwd)) return 1;
+  }
   if (capture(e, B, 2, &e->g_upd, &e->launches_upd)) return 1;
+  if (capture(e, B, 3, &e->g_host, &e->launches_host)) return 1;
+  if (capture(e, B, 4, &e->g_host_bwd, &e->launches_host_bwd)) return 1;
   e->graph_B = B; e->graph_accum = acc;
   return 0;
 }
@@ -713,6 +719,9 @@ void jb_destroy(jb_engine* e) {
   if (e->g_full) cudaGraphExecDestroy(e->g_full);
   if (e->g_bwd) cudaGraphExecDestroy(e->g_bwd);
   if (e->g_upd) cudaGraphExecDestroy(e->g_upd);
+  if (e->g_host) cudaGraphExecDestroy(e->g_host);
+  if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
+  if (e->h_pin) cudaFreeHost(e->h_pin);
   void* ptrs[] = {e->theta, e->grad, e->adam_m, e->adam_v, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
                   e->arena, e->d_probs, e->ev_a, e->ev_b, e->ev_in, e->ev_out, e->d_ev_probs};
@@ -796,12 +805,15 @@ int jb_set_dataset(jb_engine* e, int mod, const float* X, long long n, long long
                        static_cast<size_t>(e->D[mod]) * 4, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
   e->data_n[mod] = n; e->data_ld[mod] = ldd;
-  if (e->g_full) { cudaGraphExecDestroy(e->g_full); e->g_full = nullptr; e->graph_B = 0; }  // pointers are baked into the graph
+  if (e->g_upd) { cudaGraphExecDestroy(e->g_upd); e->g_upd = nullptr; }  // pointers are baked into the graphs
+  e->graph_B = 0;
   return 0;
 }
 
 static int reset_graphs(jb_engine* e) {
   if (e->g_full) { cudaGraphExecDestroy(e->g_full); e->g_full = nullptr; }
+  if (e->g_bwd) { cudaGraphExecDestroy(e->g_bwd); e->g_bwd = nullptr; }
+  if (e->g_upd) { cudaGraphExecDestroy(e->g_upd); e->g_upd = nullptr; }
   e->graph_B = 0;
   return 0;
 }
@@ -814,6 +826,7 @@ int jb_set_prior_diag(jb_engine* e, const float* m, long long n) {
     CU(cudaMalloc(&e->p_diag, static_cast<size_t>(n) * 4));
     CU(cudaMemcpy(e->p_diag, m, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice));
   }
+  e->p_diag_n = m ? n : 0;
   return reset_graphs(e);
 }
 int jb_set_prior_dense(jb_engine* e, const float* P, long long n0, long long n1) {
@@ -845,7 +858,6 @@ int jb_upload_plan(jb_engine* e, const long long* idx0, const long long* idx1, c
   if (!e || !idx0 || !idx1 || !kl_anneal) return fail("null argument");
   if (batch < 2 || batch > e->Bmax) return fail("batch %d outside [2, %d]", batch, e->Bmax);
   if (nsteps <= 0) return fail("nsteps must be positive");
-  if (!e->data[0] || !e->data[1]) return fail("jb_set_dataset must be called for both modalities first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CU(cudaStreamSynchronize(s));
   if (nsteps > e->plan_cap || batch != e->plan_B) {
@@ -865,7 +877,7 @@ int jb_upload_plan(jb_engine* e, const long long* idx0, const long long* idx1, c
   for (int i = 0; i < 2; ++i) {
     for (size_t k = 0; k < h.size(); ++k) {
       const long long v = src[i][k];
-      if (v < 0 || v >= e->data_n[i]) return fail("batch index %lld out of range for modality %d (n = %lld)", v, i, e->data_n[i]);
+      if (v < 0 || (e->data[i] && v >= e->data_n[i])) return fail("batch index %lld out of range for modality %d (n = %lld)", v, i, e->data_n[i]);
       h[k] = static_cast<int>(v);
     }
     CU(cudaMemcpy(e->plan_idx[i], h.data(), h.size() * 4, cudaMemcpyHostToDevice));
@@ -908,6 +920,7 @@ int jb_train_steps(jb_engine* e, int nsteps, void* stream) {
   if (!e) return fail("null argument");
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
   if (ensure_graphs(e, e->plan_B)) return 1;
+  if (!e->g_full) return fail("jb_set_dataset must be called for both modalities before jb_train_steps");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int k = 0; k < nsteps; ++k) CU(cudaGraphLaunch(e->g_full, s));
   e->launches += static_cast<long long>(nsteps) * e->launches_per_step;
@@ -919,6 +932,7 @@ int jb_step_backward(jb_engine* e, void* stream) {
   if (!e) return fail("null argument");
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
   if (ensure_graphs(e, e->plan_B)) return 1;
+  if (!e->g_bwd) return fail("jb_set_dataset must be called for both modalities before jb_step_backward");
   CU(cudaGraphLaunch(e->g_bwd, static_cast<cudaStream_t>(stream)));
   e->launches += e->launches_bwd;
   for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
@@ -942,6 +956,89 @@ int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats) {
 int jb_set_grad_accumulate(jb_engine* e, int accumulate) {
   if (!e) return fail("null argument");
   e->accumulate = accumulate ? 1 : 0;
+  return 0;
+}
+
+static int hostbatch_common(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
+                           int batch, double kl_anneal, float* out_losses, void* stream) {
+  if (!e || !x0 || !x1 || !idx0 || !idx1) return fail("null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (e->plan_B != batch || e->plan_cap < 1) {   // first call: allocate the one-row plan through the normal path
+    std::vector<long long> z(batch, 0);
+    double k0 = 0;
+    if (jb_upload_plan(e, z.data(), z.data(), &k0, 1, batch, stream)) return 1;
+  }
+  if (ensure_graphs(e, batch)) return 1;
+  if (!e->h_pin) CU(cudaMallocHost(&e->h_pin, (2 * static_cast<size_t>(e->Bmax) + 32) * 4));
+  int* hi = e->h_pin;
+  float* hf = reinterpret_cast<float*>(e->h_pin + 2 * e->Bmax);
+  const long long* src[2] = {idx0, idx1};
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < batch; ++k) {
+      const long long v = src[i][k];
+      long long lim = 1LL << 31;
+      if (e->p_diag) lim = e->p_diag_n;
+      else if (e->p_dense || e->f_dense) lim = i == 0 ? e->pn0 : e->pn1;
+      if (v < 0 || v >= lim) return fail("cell id %lld out of range for the prior (limit %lld)", v, lim);
+      hi[i * e->Bmax + k] = static_cast<int>(v);
+    }
+  hf[0] = static_cast<float>(32 * 1e-3 * kl_anneal);
+  const float* xs[2] = {x0, x1};
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaMemcpyAsync(e->plan_idx[i], hi + i * e->Bmax, static_cast<size_t>(batch) * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(e->act[i].x, static_cast<size_t>(e->act[i].ldD) * 4, xs[i], static_cast<size_t>(e->D[i]) * 4,
+                         static_cast<size_t>(e->D[i]) * 4, batch, cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaMemcpyAsync(e->plan_kl, hf, 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(&e->ctl->cursor, 0, sizeof(long long), s));
+  for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
+  e->plan_steps = 1;
+  e->eval_dirty = true;
+  if (!out_losses) {   // data-parallel form: forward + backward only
+    CU(cudaGraphLaunch(e->g_host_bwd, s));
+    e->launches += e->launches_host_bwd;
+    return 0;
+  }
+  CU(cudaGraphLaunch(e->g_host, s));
+  CU(cudaMemcpyAsync(hf + 8, e->out_loss, 8 * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(out_losses, hf + 8, 8 * 4);
+  e->launches += e->launches_host;
+  return 0;
+}
+int jb_train_step_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
+                            int batch, double kl_anneal, float out_losses[8], void* stream) {
+  if (!out_losses) return fail("null argument");
+  return hostbatch_common(e, x0, x1, idx0, idx1, batch, kl_anneal, out_losses, stream);
+}
+int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
+                               int batch, double kl_anneal, void* stream) {
+  return hostbatch_common(e, x0, x1, idx0, idx1, batch, kl_anneal, nullptr, stream);
+}
+
+int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* flops, void* stream) {
+  if (!e || !avg_us || !flops) return fail("null argument");
+  if (stage < 0 || stage > 11 || iters <= 0) return fail("bad stage / iters");
+  if (!e->plan_B) return fail("jb_upload_plan must be called first");
+  if (ensure_graphs(e, e->plan_B)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const GemmStage& st = stage < 6 ? e->st_f[stage] : e->st_b[stage - 6];
+  double fl = 0;
+  for (int i = st.first; i < st.first + st.count; ++i)
+    fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch<false>(e->d_probs + st.first, st.count, st.tiles, s));
+  CU(cudaEventRecord(a, s));
+  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch<false>(e->d_probs + st.first, st.count, st.tiles, s));
+  CU(cudaEventRecord(b, s));
+  CU(cudaEventSynchronize(b));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  e->launches += iters + 3;
+  *avg_us = ms * 1000.f / static_cast<float>(iters);
+  *flops = fl;
   return 0;
 }
 

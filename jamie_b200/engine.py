@@ -192,6 +192,27 @@ class Engine:
     def step_update(self, stream=0):
         _lib.check(self.lib.jb_step_update(self.h, C.c_void_p(stream)))
 
+    def train_step_hostbatch(self, x0_ptr, x1_ptr, idx0, idx1, kl_anneal, stream=0):
+        """One step with the batch rows coming from (pinned) host memory; returns the 8 loss scalars."""
+        idx0 = np.ascontiguousarray(idx0, dtype=np.int64)
+        idx1 = np.ascontiguousarray(idx1, dtype=np.int64)
+        out = np.empty(8, np.float32)
+        _lib.check(self.lib.jb_train_step_hostbatch(self.h, C.c_void_p(x0_ptr), C.c_void_p(x1_ptr), _ptr(idx0), _ptr(idx1),
+                                                    idx0.size, float(kl_anneal), _ptr(out), C.c_void_p(stream)))
+        return out
+
+    def step_backward_hostbatch(self, x0_ptr, x1_ptr, idx0, idx1, kl_anneal, stream=0):
+        idx0 = np.ascontiguousarray(idx0, dtype=np.int64)
+        idx1 = np.ascontiguousarray(idx1, dtype=np.int64)
+        _lib.check(self.lib.jb_step_backward_hostbatch(self.h, C.c_void_p(x0_ptr), C.c_void_p(x1_ptr), _ptr(idx0),
+                                                       _ptr(idx1), idx0.size, float(kl_anneal), C.c_void_p(stream)))
+
+    def bench_stage(self, stage, iters, stream=0):
+        us = C.c_float()
+        fl = C.c_double()
+        _lib.check(self.lib.jb_bench_stage(self.h, int(stage), int(iters), C.byref(us), C.byref(fl), C.c_void_p(stream)))
+        return float(us.value), float(fl.value)
+
     def set_grad_accumulate(self, flag):
         _lib.check(self.lib.jb_set_grad_accumulate(self.h, int(bool(flag))))
 

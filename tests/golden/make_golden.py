@@ -140,8 +140,31 @@ def build_case(name, spec):
     return out
 
 
+def build_checkpoint():
+    """A checkpoint written by the reference's own save_model (plain reference classes, PCA + standardisation inside)
+    with the predictions the reference makes from it: the cross-loading fixture."""
+    jamie = import_reference()
+    data = synth(90, (60, 45), 77)
+    np.random.seed(42)
+    jm = jamie.JAMIE(output_dim=8, batch_size=32, pca_dim=[20, 14], epoch_DNN=4, min_epochs=2, dropout=0.3,
+                     use_f_tilde=False)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        emb = jm.fit_transform(dataset=[d.copy() for d in data])
+    path = os.path.join(HERE, 'ref_checkpoint.h5')
+    jm.save_model(path)
+    out = {f'data{i}': data[i] for i in range(2)}
+    for i in range(2):
+        out[f'emb{i}'] = emb[i]
+        out[f'pred{i}'] = np.asarray(jm.modal_predict(data[i], i))
+        out[f'tone{i}'] = jm.transform_one(data[i], i)
+    np.savez_compressed(os.path.join(HERE, 'ref_checkpoint_io.npz'), **out)
+    print('checkpoint', os.path.getsize(path) // 1024, 'KiB')
+
+
 def main():
     torch.set_num_threads(4)
+    build_checkpoint()
     for name, spec in CASES.items():
         out = build_case(name, spec)
         path = os.path.join(HERE, f'{name}.npz')

@@ -1,0 +1,46 @@
+"""Data-parallel host logic on CPU: two gloo ranks shard the cells, agree on the epoch length and reduce a flat
+gradient buffer + loss tail exactly as the GPU path does with NCCL."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from jamie_b200.jamie import PriorSpec, _dist_info
+    assert _dist_info() == (rank, world)
+    rows = [1001, 1001]
+    lo = [(r * rank) // world for r in rows]
+    hi = [(r * (rank + 1)) // world for r in rows]
+    m = (np.arange(rows[0]) % 2 == 0).astype(np.float32)
+    prior = PriorSpec(m[lo[0]:hi[0]], [hi[0] - lo[0], hi[1] - lo[1]])
+    # the flat-buffer reduction: sum then divide by world inside the update
+    g = torch.full((16,), float(rank + 1))
+    dist.all_reduce(g)
+    len_dataloader = int(max(rows) / (128 * world))
+    q.put((rank, lo, hi, prior.sampling_method, prior.corr_samples.tolist(), g.tolist(), len_dataloader))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_reduce():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, m0, c0, g0, l0), (r1, lo1, hi1, m1, c1, g1, l1) = res
+    assert lo0 == [0, 0] and hi0 == lo1 and hi1 == [1001, 1001]          # contiguous, disjoint, covering
+    assert m0 == m1 == 'hybrid'
+    assert c0 == [[0, 0], [2, 2]] and c1 == [[0, 0], [2, 2]]                 # shard-local indices (500 is even)
+    assert g0 == g1 == [3.0] * 16
+    assert l0 == l1 == 3

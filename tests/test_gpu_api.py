@@ -1,0 +1,81 @@
+"""End-to-end through the reference-facing Python API (jamie.JAMIE) on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity_util as U
+from tests.golden_util import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def _mmdma_like(n=300, dims=(200, 100), seed=0):
+    rng = np.random.default_rng(seed)
+    t = rng.random(n) * 2 - 1
+    branch = rng.integers(0, 3, n)
+    lat = np.stack([t, t ** 2 * (branch == 0) + t * (branch == 1) - t * (branch == 2), np.sin(3 * t)], 1)
+    data = []
+    for d in dims:
+        W = rng.normal(size=(3, d))
+        data.append(lat @ W + 0.05 * rng.normal(size=(n, d)))
+    return data, branch
+
+
+def test_fit_transform_end_to_end(capsys):
+    from jamie import JAMIE
+    data, labels = _mmdma_like()
+    np.random.seed(42)
+    jm = JAMIE(output_dim=16, batch_size=128, pca_dim=[32, 32], epoch_DNN=400, min_epochs=100, log_DNN=100,
+               use_f_tilde=False, debug=True, log_debug=200)
+    emb = jm.fit_transform(dataset=data)
+    out = capsys.readouterr().out
+    assert 'use random seed: 666' in out and 'Train coupled autoencoders' in out and 'Finished Mapping!' in out
+    assert 'epoch:[400/400]: loss:' in out and 'JAMIE Done!' in out
+    assert emb[0].shape == (300, 16) and emb[1].shape == (300, 16)
+    assert set(jm.loss_history) == {'KL', 'Rec', 'CosSim', 'F'} and len(jm.loss_history['Rec']) == jm.epochs_run
+    assert jm.sampling_method == 'diag'
+    assert np.mean(jm.loss_history['Rec'][-20:]) < 0.5 * np.mean(jm.loss_history['Rec'][:5])
+    fos = jm.test_closer(emb)
+    lta = jm.test_LabelTA(emb, [labels, labels], k=5)
+    assert fos < 0.1 and lta > 0.8, (fos, lta)
+    # fit_transform's return equals transform_one / transform on the training data
+    for i in range(2):
+        np.testing.assert_array_equal(jm.transform_one(data[i], i), emb[i])
+    np.testing.assert_array_equal(jm.transform(data)[1], emb[1])
+    # imputation: held-in correlation per feature is high on this noiseless-ish manifold
+    from jamie_b200.evaluation import imputation_correlation
+    pred1 = jm.modal_predict(data[0], 0)
+    assert pred1.shape == data[1].shape and pred1.dtype == np.float64
+    assert np.nanmean(imputation_correlation(pred1, data[1])) > 0.7
+
+
+def test_save_load_roundtrip(tmp_path):
+    from jamie import JAMIE
+    data, _ = _mmdma_like(n=120, dims=(60, 40), seed=1)
+    jm = JAMIE(output_dim=8, batch_size=64, pca_dim=[16, 16], epoch_DNN=30, min_epochs=10, use_f_tilde=False)
+    jm.fit_transform(dataset=data)
+    f = str(tmp_path / 'model.h5')
+    jm.save_model(f)
+    assert open(f, 'rb').read(4) == b'PK\x03\x04'           # torch zip archive, like the reference's files
+    jm2 = JAMIE()
+    jm2.load_model(f)
+    for i in range(2):
+        np.testing.assert_array_equal(jm2.modal_predict(data[i], i), jm.modal_predict(data[i], i))
+        np.testing.assert_array_equal(jm2.transform_one(data[i], i), jm.transform_one(data[i], i))
+    # the module tree is the reference's
+    keys = list(jm2.model.state_dict().keys())
+    assert keys[0] == 'sigma' and 'encoders.0.0.weight' in keys and 'decoders.1.8.bias' in keys
+    assert 'encoders.0.1.running_mean' in keys and len(keys) == 45 + 24
+
+
+def test_load_reference_checkpoint():
+    """A file written by the reference's own save_model loads here and predicts what the reference predicted."""
+    from jamie import JAMIE
+    io = np.load(os.path.join(GOLDEN_DIR, 'ref_checkpoint_io.npz'))
+    jm = JAMIE()
+    jm.load_model(os.path.join(GOLDEN_DIR, 'ref_checkpoint.h5'))
+    for i in range(2):
+        got = jm.modal_predict(io[f'data{i}'], i)
+        assert U.rel(got, io[f'pred{i}']) < 3e-3
+        assert U.rel(jm.transform_one(io[f'data{i}'], i), io[f'tone{i}']) < 3e-3

@@ -1,0 +1,121 @@
+"""CPU tests of the host-side mirror: initial weights, sampler draws, prior handling, preprocessing, metrics, and the
+epoch bookkeeping helpers -- checked against the reference fixtures and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jamie_oracle as O
+from tests.golden_util import CASES, Golden
+
+
+@pytest.mark.parametrize('name', ['diag_drop', 'rep_F', 'zeros_unequal'])
+def test_initial_weights_equal_reference(name):
+    """Same torch seed + same construction order => bit-identical initial parameters as the reference model."""
+    from jamie_b200.model import edModelVar
+    G = Golden(name)
+    torch.manual_seed(666)
+    m = edModelVar(G.meta['col'], G.kw['output_dim'], dropout=G.kw.get('dropout'))
+    assert [n for n, _ in m.named_parameters()] == G.param_names
+    for got, want in zip(m.packed_parameters(), G.init_params()):
+        np.testing.assert_array_equal(got, want)
+    assert m.dropout_p == G.meta['dropout']
+    for k, v in m.packed_buffers().items():
+        np.testing.assert_array_equal(v, G.buffers('init')[k])
+
+
+def test_layout_matches_oracle_spec():
+    from jamie_b200.layout import bn_spec, param_spec
+    assert param_spec([512, 39], 32) == O.param_spec([512, 39], 32)
+    assert bn_spec([7, 9]) == O.bn_spec([7, 9])
+    assert sum(int(np.prod(s)) for _, s in param_spec([512, 512], 32)) == 4312194
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_sampler_reproduces_reference_draws(name):
+    from jamie_b200.jamie import PriorSpec, sample_batch
+    G = Golden(name)
+    rows, dims, B = G.meta['n'], G.meta['col'], G.meta['batch_size']
+    prior = PriorSpec(G['P'] if G.has('P') else None, rows)
+    assert prior.sampling_method == G.meta['sampling_method']
+    np.random.seed(42)
+    for s in range(G.n_steps):
+        idx = sample_batch(prior.sampling_method, rows, dims, B, prior.corr_samples)
+        data = [G[f'pre{i}'].astype(np.float32) for i in range(2)]
+        for i in range(2):
+            np.testing.assert_array_equal(data[i][idx[i]], G[f's{s}/x{i}'])
+
+
+def test_prior_forms_are_equivalent():
+    from jamie_b200.jamie import PriorSpec
+    import scipy.sparse as sp
+    m = (np.arange(10) % 3 == 0).astype(np.float64)
+    a = PriorSpec(np.diag(m), [10, 10])
+    b = PriorSpec(m, [10, 10])
+    c = PriorSpec(sp.diags(m).tocsr(), [10, 10])
+    for p in (a, b, c):
+        assert p.sampling_method == 'hybrid' and p.dense is None
+        np.testing.assert_array_equal(p.diag, m)
+        np.testing.assert_array_equal(p.corr_samples, [[0, 0], [3, 3]])
+    assert PriorSpec(None, [5, 5]).sampling_method == 'diag'
+    assert PriorSpec(None, [5, 4]).sampling_method == 'zeros'
+    assert PriorSpec(np.zeros((5, 4)), [5, 4]).sampling_method == 'zeros'
+    d = np.zeros((5, 4)); d[1, 2] = 1; d[3, 0] = 2
+    pd = PriorSpec(d, [5, 4])
+    assert pd.sampling_method == 'hybrid' and pd.dense is not None
+    np.testing.assert_array_equal(pd.corr_samples, [[1, 2], [3, 0]])
+    np.testing.assert_array_equal(PriorSpec(m, [10, 10]).to_dense(), np.diag(m))
+
+
+@pytest.mark.parametrize('name', ['diag_drop', 'pca'])
+def test_preclass_matches_reference(name):
+    from jamie_b200.utilities import LinearPCA, preclass
+    G = Golden(name)
+    for i in range(2):
+        raw = G[f'data{i}']
+        if G.kw.get('pca_dim') is not None:
+            pca = LinearPCA(G.kw['pca_dim'][i])
+            sample = pca.fit_transform(raw)
+            # same subspace and sign convention as the reference's sklearn PCA on this (full-SVD) problem
+            np.testing.assert_allclose(np.abs(pca.components_ @ G[f'pca_components{i}'].T), np.eye(len(pca.components_)),
+                                       atol=1e-6)
+            pre = preclass(sample, pca=pca)
+            np.testing.assert_allclose(np.abs(pre.transform(raw)), np.abs(G[f'pre{i}']), rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(pre.inverse_transform(pre.transform(raw)),
+                                       pca.inverse_transform(pca.transform(raw)), rtol=1e-9, atol=1e-9)
+        else:
+            pre = preclass(raw, axis=0)
+            np.testing.assert_allclose(pre.transform(raw), G[f'pre{i}'], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(pre.inverse_transform(pre.transform(raw)), raw, rtol=1e-9, atol=1e-9)
+    const = np.ones((6, 3))
+    assert np.all(preclass(const, axis=0).transform(const) == 0)        # NaN -> 0 rule (jamie/utilities.py:669)
+
+
+def test_constructor_surface_and_validation():
+    from jamie import JAMIE
+    jm = JAMIE(min_epochs=500)
+    assert (jm.batch_size, jm.epoch_DNN, jm.log_DNN, jm.output_dim, jm.manual_seed) == (512, 10000, 500, 32, 666)
+    assert jm.pca_dim == [512, 512] and jm.use_f_tilde and jm.min_epochs == 500 and jm.project_mode == 'jamie'
+    with pytest.raises(TypeError):
+        JAMIE(not_an_argument=1)
+    with pytest.raises(Exception, match='distance_mode error'):
+        JAMIE(distance_mode='nope').fit_transform(dataset=[np.zeros((4, 3)), np.zeros((4, 3))])
+    with pytest.raises(AssertionError, match='Model must be trained'):
+        JAMIE().modal_predict(np.zeros((2, 2)), 0)
+
+
+def test_metrics():
+    from jamie_b200.evaluation import foscttm, imputation_correlation, label_transfer_accuracy
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(50, 4))
+    assert foscttm(a, a) == 0.0
+    assert 0.3 < foscttm(a, rng.normal(size=(50, 4))) < 0.7
+    y = (a[:, 0] > 0).astype(int)
+    assert label_transfer_accuracy([a, a + 0.01 * rng.normal(size=a.shape)], [y, y], k=1) > 0.95
+    r = imputation_correlation(a * 2 + 1, a)
+    np.testing.assert_allclose(r, 1.0)
+
+
+def test_kl_anneal_and_chunk_bound():
+    # anneal midpoint and shape (jamie/jamie.py:630-631)
+    assert abs(O.kl_anneal(250, 500, 10000) - 0.5) < 1e-12
+    assert O.kl_anneal(0, 0, 100) < 0.01 < O.kl_anneal(100, 0, 100)
