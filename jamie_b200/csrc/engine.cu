@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -122,6 +123,7 @@ struct jb_engine {
   int launches_host = 0, launches_host_bwd = 0;
   cudaStream_t cap_stream = nullptr;
   int accumulate = 0;
+  int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
   // eval
   bool eval_dirty = true;
@@ -236,7 +238,7 @@ void carve(jb_engine* e, Carver& c) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>((D + 31) / 32);
+    a.rec_part = c.take<float>((D + 15) / 16);
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
@@ -245,11 +247,19 @@ void carve(jb_engine* e, Carver& c) {
 }
 
 // ------------------------------------------------------------------------------------------- GEMM tables
+// split: error-compensated 3xTF32 (fp32-class accuracy). Used for every forward GEMM and every dgrad of the training
+// step: pre-activation errors flip LeakyReLU' decisions and dX errors propagate down the chain, whereas a wgrad's TF32
+// rounding (~3e-4 relative, unbiased) stays local to that gradient tensor and is left single-pass.
 int add_prob(jb_engine* e, const float* A, int lda, int a_mn, const float* Bm, int ldb, int b_mn, float* C, int ldc, int M,
-             int N, int K, int bn, int epi, const float* bias, int accumulate) {
+             int N, int K, int bn, int epi, const float* bias, int accumulate, int split) {
   GemmProblem g;
-  int rc = jb::gemm_problem_fill(&g, A, lda, a_mn, Bm, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, jb::LRELU, accumulate);
+  if (e->precision_fast) split = 0;
+  int rc = jb::gemm_problem_fill(&g, A, lda, a_mn, Bm, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, jb::LRELU, accumulate, 1,
+                                 split);
   if (rc) return fail("cuTensorMapEncodeTiled failed (%d) for M%d N%d K%d lda%d ldb%d", rc, M, N, K, lda, ldb);
+  g.ks = K >= 128 ? 4 : (K >= 64 ? 2 : 1);   // k-blocks per pipeline stage (tools/gemm_lab mode 5: fewer, fatter stages win)
+  if (split && g.ks > 2) g.ks = 2;           // split stages carry hi and lo tiles: 2 x 2 k-blocks x 24 KB x 2 stages
+  if (const char* ev = getenv("JB_DEBUG_KS")) g.ks = atoi(ev);
   e->h_probs.push_back(g);
   return 0;
 }
@@ -281,35 +291,35 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   // ---- forward
   first = e->h_probs.size();
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.x, a.ldD, 0, W(m.W1), m.W1.ld, 0, a.y1, a.ld2D, B, 2 * D, D, choose_bn(2 * D, 0), jb::EPI_BIAS, W(m.b1), 0)) return 1; }
+    if (add_prob(e, a.x, a.ldD, 0, W(m.W1), m.W1.ld, 0, a.y1, a.ld2D, B, 2 * D, D, choose_bn(2 * D, 0), jb::EPI_BIAS, W(m.b1), 0, 1)) return 1; }
   close_stage(e, e->st_f[0], first);
   first = e->h_probs.size();
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.h1, a.ld2D, 0, W(m.W2), m.W2.ld, 0, a.y2, a.ldD, B, D, 2 * D, choose_bn(D, 0), jb::EPI_BIAS, W(m.b2), 0)) return 1; }
+    if (add_prob(e, a.h1, a.ld2D, 0, W(m.W2), m.W2.ld, 0, a.y2, a.ldD, B, D, 2 * D, choose_bn(D, 0), jb::EPI_BIAS, W(m.b2), 0, 1)) return 1; }
   close_stage(e, e->st_f[1], first);
   first = e->h_probs.size();
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.h2, a.ldD, 0, W(m.Wmv), m.Wmv.ld, 0, a.mulv, a.ldmv, B, 2 * L, D, choose_bn(2 * L, 0), jb::EPI_BIAS, W(m.bmv), 0)) return 1; }
+    if (add_prob(e, a.h2, a.ldD, 0, W(m.Wmv), m.Wmv.ld, 0, a.mulv, a.ldmv, B, 2 * L, D, choose_bn(2 * L, 0), jb::EPI_BIAS, W(m.bmv), 0, 1)) return 1; }
   close_stage(e, e->st_f[2], first);
   first = e->h_probs.size();
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.c, a.LP, 0, W(m.W3), m.W3.ld, 0, a.y3, a.ldD, B, D, L, choose_bn(D, 0), jb::EPI_BIAS, W(m.b3), 0)) return 1; }
+    if (add_prob(e, a.c, a.LP, 0, W(m.W3), m.W3.ld, 0, a.y3, a.ldD, B, D, L, choose_bn(D, 0), jb::EPI_BIAS, W(m.b3), 0, 1)) return 1; }
   close_stage(e, e->st_f[3], first);
   first = e->h_probs.size();
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.g1, a.ldD, 0, W(m.W4), m.W4.ld, 0, a.y4, a.ld2D, B, 2 * D, D, choose_bn(2 * D, 0), jb::EPI_BIAS, W(m.b4), 0)) return 1; }
+    if (add_prob(e, a.g1, a.ldD, 0, W(m.W4), m.W4.ld, 0, a.y4, a.ld2D, B, 2 * D, D, choose_bn(2 * D, 0), jb::EPI_BIAS, W(m.b4), 0, 1)) return 1; }
   close_stage(e, e->st_f[4], first);
   first = e->h_probs.size();
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.g2, a.ld2D, 0, W(m.W5), m.W5.ld, 0, a.xhat, a.ldD, B, D, 2 * D, choose_bn(D, 0), jb::EPI_BIAS, W(m.b5), 0)) return 1; }
+    if (add_prob(e, a.g2, a.ld2D, 0, W(m.W5), m.W5.ld, 0, a.xhat, a.ldD, B, D, 2 * D, choose_bn(D, 0), jb::EPI_BIAS, W(m.b5), 0, 1)) return 1; }
   close_stage(e, e->st_f[5], first);
   // ---- backward: wgrad dW[N_out, N_in] = dY^T X  (A = dY MN-major, B = X MN-major, K = batch)
   //                dgrad dX[B, N_in]     = dY W    (A = dY K-major,  B = W MN-major,  K = N_out)
   auto wgrad = [&](const float* dY, int lddy, const float* X, int ldx, const Seg& s, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, choose_bn(n_in, 0), jb::EPI_STORE, nullptr, accum);
+    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, choose_bn(n_in, 0), jb::EPI_STORE, nullptr, accum, 0);
   };
   auto dgrad = [&](const float* dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in, 0), jb::EPI_STORE, nullptr, 0);
+    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in, 0), jb::EPI_STORE, nullptr, 0, 1);
   };
   first = e->h_probs.size();  // B6: last decoder Linear(2D -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -419,7 +429,10 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    jb::k_bn_fwd<<<pr.l[0].blocks + pr.l[1].blocks, 256, 0, r.s>>>(pr, e->ctl, B, p); r.check();
+    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
+      jb::k_bn_fwd_slab<<<(pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16, jb::SLAB_THREADS, 0, r.s>>>(pr, e->ctl, B, p);
+    else jb::k_bn_fwd<<<pr.l[0].blocks + pr.l[1].blocks, 256, 0, r.s>>>(pr, e->ctl, B, p);
+    r.check();
   };
   // ---- forward
   r.gemm(e->st_f[0]); bnf(0, 0);
@@ -439,9 +452,12 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
     ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
     jb::RecArgs& q = rp.m[i];
     q.xhat = a.xhat; q.ldxh = a.ldD; q.x = a.x; q.ldx = a.ldD; q.dxhat = a.dxhat; q.lddx = a.ldD;
-    q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + 31) / 32;
+    const bool slab = B <= 512;
+    q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + (slab ? 15 : 31)) / (slab ? 16 : 32);
   }
-  jb::k_rec<<<rp.m[0].blocks + rp.m[1].blocks, 256, 0, r.s>>>(rp, B, sc.w[1], accum); r.check();
+  if (B <= 512) jb::k_rec_slab<<<rp.m[0].blocks + rp.m[1].blocks, jb::SLAB_THREADS, 0, r.s>>>(rp, B, sc.w[1], accum);
+  else jb::k_rec<<<rp.m[0].blocks + rp.m[1].blocks, 256, 0, r.s>>>(rp, B, sc.w[1], accum);
+  r.check();
   auto bnb = [&](int which) {
     jb::BnBwdPair pr{};
     for (int i = 0; i < 2; ++i) {
@@ -461,7 +477,10 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    jb::k_bn_bwd<<<pr.l[0].blocks + pr.l[1].blocks, 256, 0, r.s>>>(pr, e->ctl, B, p, accum); r.check();
+    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
+      jb::k_bn_bwd_slab<<<(pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16, jb::SLAB_THREADS, 0, r.s>>>(pr, e->ctl, B, p, accum);
+    else jb::k_bn_bwd<<<pr.l[0].blocks + pr.l[1].blocks, 256, 0, r.s>>>(pr, e->ctl, B, p, accum);
+    r.check();
   };
   r.gemm(e->st_b[0]); bnb(3);
   r.gemm(e->st_b[1]); bnb(2);
@@ -473,12 +492,12 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   jb::FinalArgs fa{};
   fa.rowpart = e->rowpart;
   for (int i = 0; i < 2; ++i) {
-    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = (e->D[i] + 31) / 32;
+    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = (e->D[i] + (B <= 512 ? 15 : 31)) / (B <= 512 ? 16 : 32);
     fa.dmulv[i] = e->act[i].dmulv; fa.dbias_heads[i] = G + e->ms[i].bmv.off; fa.D[i] = e->D[i];
   }
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
   fa.grad_tail = G + e->n_flat;
-  jb::k_latent_final<<<1, 256, 0, r.s>>>(fa, lat, e->ctl, B, L, sc, accum); r.check();
+  jb::k_latent_final<<<1, 1024, 0, r.s>>>(fa, lat, e->ctl, B, L, sc, accum); r.check();
   r.gemm(e->st_b[3]); bnb(1);
   r.gemm(e->st_b[4]); bnb(0);
   r.gemm(e->st_b[5]);
@@ -669,6 +688,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   if (prop.major != 10) return fail("jamie_b200 needs an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
   jb_engine* e = new jb_engine();
   e->cfg = *cfg;
+  if (const char* pv = getenv("JB_PRECISION")) e->precision_fast = strcmp(pv, "tf32") == 0;
   e->D[0] = cfg->dims[0]; e->D[1] = cfg->dims[1]; e->L = cfg->latent; e->LP = r4(cfg->latent); e->Bmax = cfg->max_batch;
   build_layout(e);
   const size_t fb = static_cast<size_t>(e->n_flat + 32) * 4;

@@ -19,6 +19,14 @@
 //                     SWIZZLE_128B_BASE32B (the only MN-major layout for 32-bit operands), LBO 4096, SBO 512,
 //                     +1024 B per K=8 step
 //
+// split = 1 (training GEMMs): error-compensated 3xTF32. The tensor maps are typed FLOAT32 (raw fp32 lands in shared
+// memory) and the tensor core itself truncates every operand to TF32, so the raw tile doubles as the HIGH part
+// hi = trunc(x) for free; the four epilogue warps, idle during the main loop, write the exact remainders
+// lo = x - trunc(x) into a second tile, and each K step issues three MMAs  hi*hi + lo*hi + hi*lo  (lo*lo ~ 2^-22
+// dropped). Products are then exact to ~2^-20, i.e. fp32-class results from the TF32 pipe. Needed because a single
+// TF32 pass perturbs pre-activations by ~5e-4, which flips LeakyReLU' at ~4e-4 of the elements and costs ~2e-2 of
+// relative gradient error (measured, profiles/parity_r1.md) -- far outside the 1e-3 parity tolerance.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> padded smem transpose -> coalesced 128-bit global stores).
 #pragma once
@@ -65,11 +73,13 @@ struct alignas(128) GemmProblem {
   int ks;                   // k-blocks (32 floats of K each) per pipeline stage: 1, 2 or 4
   long long* dbg;           // optional: per-CTA phase timestamps (bring-up lab only)
   int dbg_mode;             // lab only: 1 = TMA only (no MMA), 2 = MMA only (no TMA)
+  int split;                // 1: error-compensated 3xTF32 (fp32-level accuracy), see the header comment
 };
 
 struct GemmCtrl {
   uint64_t full[GEMM_MAX_STAGES];
   uint64_t empty[GEMM_MAX_STAGES];
+  uint64_t ready[GEMM_MAX_STAGES];   // split mode: lo tiles written by the splitter warps
   uint64_t tmem_full;
   uint32_t tmem_base;
 };
@@ -117,7 +127,9 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   const int num_kb = (P.K + GEMM_BK - 1) / GEMM_BK;
   const int kblock_bytes = GEMM_A_STAGE_BYTES + bn * GEMM_BK * 4;  // one k-block: A sub-tile then B sub-tile
   const int ks = P.ks;
-  const int stage_bytes = ks * kblock_bytes;
+  const int split = P.split;
+  const int raw_bytes = ks * kblock_bytes;                 // raw (hi) k-blocks of a stage, contiguous
+  const int stage_bytes = raw_bytes * (split ? 2 : 1);     // split: the lo k-blocks follow the raw ones
   int nstages = GEMM_TILE_SMEM / stage_bytes;
   if (nstages > GEMM_MAX_STAGES) nstages = GEMM_MAX_STAGES;
   const int num_st = (num_kb + ks - 1) / ks;  // pipeline iterations
@@ -132,6 +144,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&ctrl->full[s], 1);
       mbar_init(&ctrl->empty[s], 1);
+      mbar_init(&ctrl->ready[s], 4);   // one arrival per splitter warp
     }
     mbar_init(&ctrl->tmem_full, 1);
     fence_mbar_init();
@@ -192,7 +205,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < num_st; ++it) {
-      if (!(kLab && dbg_mode >= 3)) mbar_wait(&ctrl->full[s], ph);     // lab modes 3/4: no pipeline at all
+      if (!(kLab && dbg_mode >= 3)) mbar_wait(split ? &ctrl->ready[s] : &ctrl->full[s], ph);     // lab modes 3/4: no pipeline at all
       if (!(kLab && dbg_mode == 5)) tc_fence_after();
       if (kLab && dbg && it == 0 && lane == 0) dbg[2] = clock64();
       const int kb0 = it * ks;
@@ -206,10 +219,21 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
             const uint32_t sb = sa + GEMM_A_STAGE_BYTES;                        // never carries out of the 14-bit field
             const uint64_t da0 = da_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
             const uint64_t db0 = db_hi | static_cast<uint64_t>((sb >> 4) & 0x3FFFu);
+            if (split) {
+              const uint32_t lo16 = static_cast<uint32_t>(raw_bytes) >> 4;   // lo tile = raw tile + raw_bytes
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
-              umma_tf32(tmem_d + ((kLab && dbg_mode == 6 && (k & 1)) ? bn : 0), da0 + k * a_step16, db0 + k * b_step16, idesc,
-                        (kb0 | j | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+                const uint64_t da = da0 + k * a_step16, db = db0 + k * b_step16;
+                umma_tf32(tmem_d, da + lo16, db, idesc, (kb0 | j | k) != 0 ? 1u : 0u);   // lo(A) * hi(B)
+                umma_tf32(tmem_d, da, db + lo16, idesc, 1u);                            // hi(A) * lo(B)
+                umma_tf32(tmem_d, da, db, idesc, 1u);                                   // hi(A) * hi(B)
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
+                umma_tf32(tmem_d + ((kLab && dbg_mode == 6 && (k & 1)) ? bn : 0), da0 + k * a_step16, db0 + k * b_step16,
+                          idesc, (kb0 | j | k) != 0 ? 1u : 0u);
+            }
           }
           if (!(kLab && (dbg_mode == 3 || dbg_mode == 5 || dbg_mode == 6))) umma_commit(&ctrl->empty[s]);  // frees the smem slot when these MMAs have read it
         }
@@ -227,6 +251,33 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
     // ------------------------------------------------ epilogue: TMEM -> registers -> smem transpose -> global
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     float* st = epi_stage + q * 32 * GEMM_EPI_PITCH;
+    if (split) {
+      // ---- splitter: lo = x - trunc_tf32(x), elementwise over the raw k-blocks of every stage (layout-agnostic)
+      const int et = (warp - 2) * 32 + lane;   // 0..127
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < num_st; ++it) {
+        mbar_wait(&ctrl->full[s], ph);
+        const int nk = min(ks, num_kb - it * ks);
+        const float4* src = reinterpret_cast<const float4*>(tiles + s * stage_bytes);
+        float4* dst = reinterpret_cast<float4*>(tiles + s * stage_bytes + raw_bytes);
+        const int n4 = (nk * kblock_bytes) >> 4;
+#pragma unroll 4
+        for (int i = et; i < n4; i += 128) {
+          const float4 x = src[i];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          dst[i] = l;
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->ready[s]);
+        if (++s == nstages) { s = 0; ph ^= 1; }
+      }
+    }
     mbar_wait(&ctrl->tmem_full, 0);
     tc_fence_after();
     if (dbg && warp == 2 && lane == 0) dbg[4] = clock64();
@@ -327,8 +378,9 @@ inline int pick_bn(int N) {
 // Same for B with N. Returns 0 on success.
 inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
                              float* C, int ldc, int M, int N, int K, int bn, int epi, const float* bias,
-                             float slope, int accumulate, int dtype_tf32 = 1) {
+                             float slope, int accumulate, int dtype_tf32 = 1, int split = 0) {
   *g = GemmProblem{};
+  if (split) dtype_tf32 = 0;   // raw fp32 in shared memory: the tensor core truncates (hi), the splitter adds lo
   int rc;
   if (!a_mn) rc = make_tmap_2d(&g->tmA, A, K, M, lda, GEMM_BK, GEMM_BM, dtype_tf32);
   else rc = make_tmap_2d(&g->tmA, A, M, K, lda, 32, GEMM_BK, dtype_tf32, 1);
@@ -346,6 +398,7 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->mn_lbo = 4096; g->mn_sbo = 512; g->mn_layout = 1;
   g->accumulate = accumulate;
   g->ks = 2;
+  g->split = split;
   return 0;
 }
 

@@ -346,6 +346,174 @@ __global__ void __launch_bounds__(256) k_bn_bwd(BnBwdPair pr, const Ctl* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ narrow slabs
+// Fast path for B <= 512: a block owns 16 feature columns and all B rows with 1024 threads (64 threads per column,
+// 2 row groups of 4 rows each), so a [512, 1024] layer becomes 128 blocks with 8 (forward) / 16 (backward)
+// independent 4-byte loads in flight per thread instead of a latency-bound walk down the rows.
+constexpr int SLAB_CW = 16;
+constexpr int SLAB_THREADS = 1024;
+constexpr int SLAB_SLOTS = SLAB_THREADS / SLAB_CW;   // 64 threads per column
+constexpr int SLAB_G = 2;                            // row groups (of 4 rows) per thread: B <= 4 * 64 * 2 = 512
+
+// column sums of two per-thread partials over the 64 slots of each column (fixed order), broadcast to all threads
+__device__ __forceinline__ void slab_colsum2(float& a, float& b, float (*sh)[2][SLAB_CW], int warp, int lane) {
+  a += __shfl_xor_sync(0xffffffffu, a, 16);
+  b += __shfl_xor_sync(0xffffffffu, b, 16);
+  if (lane < SLAB_CW) { sh[warp][0][lane] = a; sh[warp][1][lane] = b; }
+  __syncthreads();
+  if (warp == 0 && lane < SLAB_CW) {
+    float x = 0.f, y = 0.f;
+#pragma unroll
+    for (int w = 0; w < SLAB_THREADS / 32; ++w) { x += sh[w][0][lane]; y += sh[w][1][lane]; }
+    sh[0][0][lane] = x; sh[0][1][lane] = y;
+  }
+  __syncthreads();
+  a = sh[0][0][lane & (SLAB_CW - 1)]; b = sh[0][1][lane & (SLAB_CW - 1)];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, const Ctl* __restrict__ ctl, int B, float p) {
+  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
+  const int nb0 = (pr.l[0].N + SLAB_CW - 1) / SLAB_CW;
+  const int which = blockIdx.x >= nb0 ? 1 : 0;
+  const BnFwd& L = pr.l[which];
+  const int cb = blockIdx.x - (which ? nb0 : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = cb * SLAB_CW + (threadIdx.x & (SLAB_CW - 1));
+  const int slot = threadIdx.x / SLAB_CW;
+  const bool cok = c < L.N;
+  const float* Y = L.Y + (cok ? c : 0);
+  const int ldy = L.ldy;
+  float v[4 * SLAB_G];
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      v[4 * t + k] = (cok && r < B) ? __ldg(Y + static_cast<long long>(r) * ldy) : 0.f;
+    }
+  float s = 0.f, dummy = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4 * SLAB_G; ++i) s += v[i];
+  slab_colsum2(s, dummy, sh, warp, lane);
+  const float mean = s / static_cast<float>(B);
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const float d = v[4 * t + k] - mean;
+      q += (r < B) ? d * d : 0.f;
+    }
+  dummy = 0.f;
+  slab_colsum2(q, dummy, sh, warp, lane);
+  const float var = q / static_cast<float>(B);
+  const float invx = 1.0f / sqrtf(var + BN_EPS);
+  if (slot == 0 && cok) {
+    L.mean[c] = mean;
+    L.invstd[c] = invx;
+    const float unb = B > 1 ? var * (static_cast<float>(B) / static_cast<float>(B - 1)) : var;
+    L.run_mean[c] = (1.f - BN_MOM) * L.run_mean[c] + BN_MOM * mean;
+    L.run_var[c] = (1.f - BN_MOM) * L.run_var[c] + BN_MOM * unb;
+  }
+  const float g = cok ? __ldg(L.gamma + c) : 0.f, be = cok ? __ldg(L.beta + c) : 0.f;
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const bool inject = ctl->inject != 0 && L.mask != nullptr;
+  const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
+  const uint2 key = philox_key(ctl);
+  float* H = L.H + (cok ? c : 0);
+  const int ldh = L.ldh;
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t) {
+    const int gq = slot + SLAB_SLOTS * t;
+    uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (p > 0.f && !inject && 4 * gq < B) rnd = rand4(key, L.layer_id, c, gq);
+    const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = gq * 4 + k;
+      if (r < B && cok) {
+        const float a = g * ((v[4 * t + k] - mean) * invx) + be;
+        float o = a > 0.f ? a : LRELU * a;
+        if (p > 0.f) {
+          const bool keep = inject ? (L.mask[static_cast<long long>(r) * L.ldm + c] != 0) : (rr[k] >= thresh);
+          o = keep ? o * scale : 0.f;
+        }
+        H[static_cast<long long>(r) * ldh] = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, const Ctl* __restrict__ ctl, int B, float p,
+                                                               int accum) {
+  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
+  const int nb0 = (pr.l[0].N + SLAB_CW - 1) / SLAB_CW;
+  const int which = blockIdx.x >= nb0 ? 1 : 0;
+  const BnBwd& L = pr.l[which];
+  const int cb = blockIdx.x - (which ? nb0 : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = cb * SLAB_CW + (threadIdx.x & (SLAB_CW - 1));
+  const int slot = threadIdx.x / SLAB_CW;
+  const bool cok = c < L.N;
+  const int cc = cok ? c : 0;
+  const float mean = __ldg(L.mean + cc), inv = __ldg(L.invstd + cc);
+  const float g = __ldg(L.gamma + cc), be = __ldg(L.beta + cc);
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const bool inject = ctl->inject != 0 && L.mask != nullptr;
+  const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
+  const uint2 key = philox_key(ctl);
+  float yh[4 * SLAB_G], da[4 * SLAB_G];
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const bool ok = cok && r < B;
+      yh[4 * t + k] = ok ? __ldg(L.Y + static_cast<long long>(r) * L.ldy + cc) : mean;
+      da[4 * t + k] = ok ? __ldg(L.dH + static_cast<long long>(r) * L.lddh + cc) : 0.f;
+    }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t) {
+    const int gq = slot + SLAB_SLOTS * t;
+    uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (p > 0.f && !inject && 4 * gq < B) rnd = rand4(key, L.layer_id, c, gq);
+    const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = gq * 4 + k;
+      const float h = (yh[4 * t + k] - mean) * inv;
+      const float a = g * h + be;
+      float d = da[4 * t + k];
+      if (p > 0.f && r < B && cok) {
+        const bool keep = inject ? (L.mask[static_cast<long long>(r) * L.ldm + c] != 0) : (rr[k] >= thresh);
+        d = keep ? d * scale : 0.f;
+      }
+      d = a > 0.f ? d : LRELU * d;
+      yh[4 * t + k] = h;
+      da[4 * t + k] = d;
+      s1 += d;
+      s2 += d * h;
+    }
+  }
+  slab_colsum2(s1, s2, sh, warp, lane);
+  if (slot == 0 && cok) {
+    if (accum) { L.dbeta[c] += s1; L.dgamma[c] += s2; }
+    else { L.dbeta[c] = s1; L.dgamma[c] = s2; L.dbias[c] = 0.f; }
+  }
+  const float fb = static_cast<float>(B);
+  const float k0 = inv * g / fb;
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      if (r < B && cok) L.dY[static_cast<long long>(r) * L.lddy + c] = k0 * (fb * da[4 * t + k] - s1 - yh[4 * t + k] * s2);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ reconstruction loss
 // dxhat = w_rec * 2 (xhat - x) / (B D);  per-block partial of sum (xhat - x)^2;  bias gradient of the last decoder
 // Linear = column sums of dxhat   (jamie/jamie.py:637-643).
@@ -369,6 +537,7 @@ __global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int
   const bool cok = c < A.D;
   const float k = w_rec * 2.f / (static_cast<float>(B) * static_cast<float>(A.D));
   float sq = 0.f, cs = 0.f;
+#pragma unroll 8
   for (int r = warp; r < B; r += 8) {
     if (cok) {
       const float d = __ldg(A.xhat + static_cast<long long>(r) * A.ldxh + c) - __ldg(A.x + static_cast<long long>(r) * A.ldx + c);
@@ -383,6 +552,48 @@ __global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int
     if (cok) A.dbias[c] = accum ? A.dbias[c] + cs : cs;
     const float tot = warp_sum(cok ? sq : 0.f);
     if (lane == 0) A.part[cb] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS) k_rec_slab(RecPair pr, int B, float w_rec, int accum) {
+  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
+  const int nb0 = (pr.m[0].D + SLAB_CW - 1) / SLAB_CW;
+  const int which = blockIdx.x >= nb0 ? 1 : 0;
+  const RecArgs& A = pr.m[which];
+  const int cb = blockIdx.x - (which ? nb0 : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = cb * SLAB_CW + (threadIdx.x & (SLAB_CW - 1));
+  const int slot = threadIdx.x / SLAB_CW;
+  const bool cok = c < A.D;
+  const float kk = w_rec * 2.f / (static_cast<float>(B) * static_cast<float>(A.D));
+  float xh[4 * SLAB_G], xx[4 * SLAB_G];
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const bool ok = cok && r < B;
+      xh[4 * t + k] = ok ? __ldg(A.xhat + static_cast<long long>(r) * A.ldxh + c) : 0.f;
+      xx[4 * t + k] = ok ? __ldg(A.x + static_cast<long long>(r) * A.ldx + c) : 0.f;
+    }
+  float sq = 0.f, cs = 0.f;
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const float d = xh[4 * t + k] - xx[4 * t + k];
+      sq += d * d;
+      const float gx = kk * d;
+      cs += gx;
+      if (r < B && cok) A.dxhat[static_cast<long long>(r) * A.lddx + c] = gx;
+    }
+  slab_colsum2(sq, cs, sh, warp, lane);
+  if (warp == 0) {
+    if (lane < SLAB_CW && cok) A.dbias[c] = accum ? A.dbias[c] + cs : cs;
+    float t = (lane < SLAB_CW && cok) ? sq : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) A.part[cb] = t;
   }
 }
 
@@ -427,25 +638,34 @@ __global__ void k_reparam(Latent a, const Ctl* __restrict__ ctl, int B, int L) {
 }
 
 // out[l] (per lane, LAT_MAXT strided) = sum_b M[row, b] * V[b, l], skipping zero entries; also returns the row sum.
+// The row is fetched 512 entries at a time (16 independent loads per lane) before the nonzeros are visited in
+// ascending column order, so the scan is bandwidth- rather than latency-bound and the sum order is fixed.
 __device__ __forceinline__ float row_times(const float* __restrict__ Mrow, const float* __restrict__ V, int B, int LP,
                                            int L, int lane, float (&acc)[LAT_MAXT]) {
 #pragma unroll
   for (int t = 0; t < LAT_MAXT; ++t) acc[t] = 0.f;
   float rs = 0.f;
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    const int b = b0 + lane;
-    const float m = b < B ? __ldg(Mrow + b) : 0.f;
-    unsigned nz = __ballot_sync(0xffffffffu, m != 0.f);
-    while (nz) {
-      const int src = __ffs(nz) - 1;
-      nz &= nz - 1;
-      const float mv = __shfl_sync(0xffffffffu, m, src);
-      rs += mv;
-      const float* v = V + static_cast<long long>(b0 + src) * LP;
+  for (int sup = 0; sup < B; sup += 512) {
+    float m[16];
 #pragma unroll
-      for (int t = 0; t < LAT_MAXT; ++t) {
-        const int l = lane + 32 * t;
-        if (l < L) acc[t] += mv * v[l];
+    for (int i = 0; i < 16; ++i) {
+      const int b = sup + 32 * i + lane;
+      m[i] = b < B ? __ldg(Mrow + b) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      unsigned nz = __ballot_sync(0xffffffffu, m[i] != 0.f);
+      while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const float mv = __shfl_sync(0xffffffffu, m[i], src);
+        rs += mv;
+        const float* v = V + static_cast<long long>(sup + 32 * i + src) * LP;
+#pragma unroll
+        for (int t = 0; t < LAT_MAXT; ++t) {
+          const int l = lane + 32 * t;
+          if (l < L) acc[t] += mv * v[l];
+        }
       }
     }
   }
@@ -588,53 +808,69 @@ struct FinalArgs {
   float* grad_tail;              // 8 floats after the flat gradients (all-reduce piggy-back)
   int D[2];
 };
-__global__ void __launch_bounds__(256) k_latent_final(FinalArgs a, Latent lat, const Ctl* __restrict__ ctl, int B, int L,
-                                                      StepConsts sc, int accum) {
-  __shared__ float red[256];
+__global__ void __launch_bounds__(1024) k_latent_final(FinalArgs a, Latent lat, const Ctl* __restrict__ ctl, int B, int L,
+                                                       StepConsts sc, int accum) {
   __shared__ float tot[14];   // [i*7 + k]: k = 0..5 the rowpart sums, k = 6: sum_r (g.c)[r] * rowsum_i[r]
-  const int tid = threadIdx.x;
-  for (int q = 0; q < 14; ++q) {
-    const int i = q / 7, k = q % 7;
+  __shared__ float colpart[8][128];
+  __shared__ float aux[4];    // [0,1]: sum_l (1 + lv - exp lv) of logvar rows 0/1 (modality 1); [2,3]: sum (xhat - x)^2
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp >= 14 && warp < 16) {
+    const int i = warp - 14;
+    float t1 = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const float lv = a.mulv1[static_cast<long long>(i) * a.ldmv + L + l];
+      t1 += 1.f + lv - expf(lv);
+    }
+    t1 = warp_sum(t1);
+    if (lane == 0) aux[i] = t1;
+  } else if (warp >= 16 && warp < 18) {
+    const int i = warp - 16;
+    float sacc = 0.f;
+    for (int b = lane; b < a.rec_blocks[i]; b += 32) sacc += a.rec_part[i][b];
+    sacc = warp_sum(sacc);
+    if (lane == 0) aux[2 + i] = sacc;
+  }
+  // 14 row reductions, one warp each (fixed order: lane-strided partials, then the shuffle tree)
+  if (warp < 14) {
+    const int i = warp / 7, k = warp % 7;
     float s = 0.f;
-    for (int r = tid; r < B; r += 256) {
+    for (int r = lane; r < B; r += 32) {
       const float* rp = a.rowpart + (static_cast<long long>(i) * B + r) * 8;
       s += k < 6 ? rp[k] : rp[4] * a.rs[i][r];
     }
-    red[tid] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) red[tid] += red[tid + o];
-      __syncthreads();
-    }
-    if (tid == 0) tot[q] = red[0];
-    __syncthreads();
+    s = warp_sum(s);
+    if (lane == 0) tot[warp] = s;
   }
-  // head bias gradients: column sums of dmulv
-  for (int col = tid; col < 4 * L; col += 256) {
-    const int i = col / (2 * L), cidx = col - i * 2 * L;
+  // head bias gradients: column sums of dmulv, 8 row groups x up to 128 columns per pass
+  for (int col0 = 0; col0 < 4 * L; col0 += 128) {
+    const int col = col0 + (tid & 127), grp = tid >> 7;
     float s = 0.f;
-    for (int r = 0; r < B; ++r) s += a.dmulv[i][static_cast<long long>(r) * a.ldmv + cidx];
-    a.dbias_heads[i][cidx] = accum ? a.dbias_heads[i][cidx] + s : s;
+    if (col < 4 * L) {
+      const int i = col / (2 * L), cidx = col - i * 2 * L;
+      const float* src = a.dmulv[i] + cidx;
+#pragma unroll 8
+      for (int r = grp; r < B; r += 8) s += src[static_cast<long long>(r) * a.ldmv];
+    }
+    colpart[grp][tid & 127] = s;
+    __syncthreads();
+    if (tid < 128 && col < 4 * L) {
+      float t = 0.f;
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) t += colpart[gq][tid];
+      const int i = col / (2 * L), cidx = col - i * 2 * L;
+      a.dbias_heads[i][cidx] = accum ? a.dbias_heads[i][cidx] + t : t;
+    }
+    __syncthreads();
   }
+  __syncthreads();
   if (tid == 0) {
     const float fB = static_cast<float>(B), fL = static_cast<float>(L);
     // KL value (jamie/jamie.py:619-628) with logvars = rows 0/1 of modality 1's logvar
     float kl = 0.f;
-    for (int i = 0; i < 2; ++i) {
-      float t1 = 0.f;
-      for (int l = 0; l < L; ++l) {
-        const float lv = a.mulv1[static_cast<long long>(i) * a.ldmv + L + l];
-        t1 += 1.f + lv - expf(lv);
-      }
-      kl += -0.5f * (t1 / fL - tot[i * 7 + 0] / (fB * fL));
-    }
+    for (int i = 0; i < 2; ++i) kl += -0.5f * (aux[i] / fL - tot[i * 7 + 0] / (fB * fL));
     const float l_kl = ctl->kl_base * kl;
     float rec = 0.f;
-    for (int i = 0; i < 2; ++i) {
-      float s = 0.f;
-      for (int b = 0; b < a.rec_blocks[i]; ++b) s += a.rec_part[i][b];
-      rec += s / (fB * static_cast<float>(a.D[i]));
-    }
+    for (int i = 0; i < 2; ++i) rec += aux[2 + i] / (fB * static_cast<float>(a.D[i]));
     const float l_cos = 32.f * (tot[1] + tot[7 + 1]) / (fB * fL);
     const float l_f = tot[2] / (fB * fL);
     // d sigma (combine backward)

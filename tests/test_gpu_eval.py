@@ -23,7 +23,7 @@ def _trained_state(dims, L, seed):
     # non-trivial BN affine
     spec = O.param_spec(dims, L)
     for j, (n, shp) in enumerate(spec):
-        if (n.split('.')[-2] in ('1', '5')) and not n.startswith('fc_'):
+        if n != 'sigma' and (n.split('.')[-2] in ('1', '5')) and not n.startswith('fc_'):
             params[j] = (1 + 0.2 * rng.normal(size=shp)).astype(np.float32) if n.endswith('weight') else \
                 (0.1 * rng.normal(size=shp)).astype(np.float32)
     return params, bufs

@@ -49,6 +49,7 @@ struct Case {
   int epi;
   uint32_t mn_layout = 1;
   int ks = 1;
+  int split = 0;
 };
 
 static int run_case(const Case& c, FILE* out) {
@@ -84,7 +85,7 @@ static int run_case(const Case& c, FILE* out) {
   CK(cudaMemcpy(dBias, hBias.data(), N * 4, cudaMemcpyHostToDevice));
   jb::GemmProblem g;
   int rc = jb::gemm_problem_fill(&g, dA, lda, c.a_mn, dB, ldb, c.b_mn, dC, ldc, M, N, K, c.bn, c.epi, dBias, 0.01f, 0,
-                                 c.tmap_tf32);
+                                 c.tmap_tf32, c.split);
   if (rc) { fprintf(out, "tensor map encode failed rc=%d\n", rc); return 1; }
   g.mn_lbo = c.lbo; g.mn_sbo = c.sbo; g.mn_layout = c.mn_layout; g.ks = c.ks;
   int tiles = jb::gemm_table_finalize(&g, 1);
@@ -118,7 +119,8 @@ static int run_case(const Case& c, FILE* out) {
           "M%-4d N%-4d K%-4d a_mn%d b_mn%d bn%-3d ks%d sbo%-4u rnd%d tmtf32 %d epi%d : max_err %.3e (vs trunc-ref %.3e) "
           "max_ref %.3e  %s\n",
           M, N, K, c.a_mn, c.b_mn, c.bn, c.ks, c.sbo, c.round_inputs, c.tmap_tf32, c.epi, max_err, max_err_tr, max_ref,
-          (max_err < 2e-5 * max_ref * (c.round_inputs ? 1 : 200)) ? "OK" : "MISMATCH");
+          (max_err < 2e-5 * max_ref * ((c.round_inputs || c.split) ? 1 : 200)) ? "OK" : "MISMATCH");
+  if (c.split) fprintf(out, "    split: max_err / max_ref = %.3e\n", max_err / max_ref);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dBias); cudaFree(dT);
   return 0;
 }
@@ -174,7 +176,7 @@ static int tma_probe(FILE* out) {
 }
 
 static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn, int nprob, int dump_dbg = 0,
-                     int ks = 1, int dbg_mode = 0) {
+                     int ks = 1, int dbg_mode = 0, int split = 0) {
   const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
   float *dA, *dB, *dC;
   jb::GemmProblem* dT;
@@ -185,7 +187,7 @@ static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn,
   std::vector<jb::GemmProblem> g(nprob);
   for (int i = 0; i < nprob; ++i)
     if (jb::gemm_problem_fill(&g[i], dA + asz * i, lda, a_mn, dB + bsz * i, ldb, b_mn, dC + csz * i, N, M, N, K, bn, 0,
-                              nullptr, 0.f, 0)) return 1;
+                              nullptr, 0.f, 0, 1, split)) return 1;
   int tiles = jb::gemm_table_finalize(g.data(), nprob);
   long long* dDbg = nullptr;
   if (dump_dbg) {
@@ -208,8 +210,8 @@ static int time_case(FILE* out, int M, int N, int K, int a_mn, int b_mn, int bn,
   cudaEventElapsedTime(&ms, e0, e1);
   double us = ms * 1000.0 / iters;
   double tf = 2.0 * M * N * K * nprob / (us * 1e-6) / 1e12;
-  fprintf(out, "time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%d ks%d mode%d tiles %d : %.2f us/launch  %.1f TFLOP/s (tf32)\n",
-          nprob, M, N, K, a_mn, b_mn, bn, ks, dbg_mode, tiles, us, tf);
+  fprintf(out, "time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%d ks%d mode%d split%d tiles %d : %.2f us/launch  %.1f TFLOP/s (tf32)\n",
+          nprob, M, N, K, a_mn, b_mn, bn, ks, dbg_mode, split, tiles, us, tf);
   if (dump_dbg) {
     std::vector<long long> h(8 * tiles);
     CK(cudaMemcpy(h.data(), dDbg, sizeof(long long) * 8 * tiles, cudaMemcpyDeviceToHost));
@@ -290,6 +292,27 @@ int main(int argc, char** argv) {
     };
     for (const Case& c : cs)
       if (run_case(c, out) == 2) return 2;
+  } else if (which == 7) {
+    // error-compensated 3xTF32 on raw fp32 inputs, all operand layouts, ks 1 and 2
+    const Case cs[] = {
+        {128, 128, 32, 0, 0, 128, 4096, 512, 0, 0, 0}, {512, 1024, 512, 0, 0, 64, 4096, 512, 0, 0, 1},
+        {512, 512, 1024, 0, 1, 64, 4096, 512, 0, 0, 0}, {1024, 512, 512, 1, 1, 64, 4096, 512, 0, 0, 0},
+        {300, 1000, 2000, 0, 0, 64, 4096, 512, 0, 0, 1}, {78, 39, 512, 1, 1, 64, 4096, 512, 0, 0, 0},
+        {512, 39, 78, 0, 1, 64, 4096, 512, 0, 0, 0}, {512, 32, 512, 0, 0, 32, 4096, 512, 0, 0, 1},
+        {2000, 1000, 300, 1, 1, 64, 4096, 512, 0, 0, 0}, {512, 64, 512, 0, 0, 64, 4096, 512, 0, 0, 1},
+    };
+    for (int ks = 1; ks <= 2; ++ks)
+      for (Case c : cs) {
+        c.ks = ks; c.split = 1;
+        if (run_case(c, out) == 2) return 2;
+      }
+    for (int sp = 0; sp < 2; ++sp) {
+      time_case(out, 512, 1024, 512, 0, 0, 64, 2, 1, 2, 0, sp);
+      time_case(out, 512, 512, 1024, 0, 1, 64, 2, 1, 2, 0, sp);
+      time_case(out, 1024, 512, 512, 1, 1, 64, 2, 1, 2, 0, sp);
+      time_case(out, 512, 1024, 512, 0, 0, 128, 2, 1, sp ? 1 : 2, 0, sp);
+      time_case(out, 512, 1024, 512, 0, 0, 32, 2, 1, 2, 0, sp);
+    }
   } else if (which == 5) {
     for (int mode = 0; mode < 1; ++mode)
       for (int ks = 1; ks <= 4; ks *= 2) {
