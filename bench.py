@@ -190,6 +190,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu): no e2e / stage / CPU legs, no JSON line')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -263,6 +264,11 @@ def main():
     losses = eng.read_losses(W + K, stream)
     assert np.all(np.isfinite(losses[:, :6])), 'non-finite losses in the timed region'
     value = BATCH * K * world / (ms * 1e-3)
+
+    if args.profile:
+        print(f'profile run: {ms / K * 1e3:.1f} us/step', flush=True)
+        eng.close()
+        return
 
     # ---------------- end to end with host-resident data
     Ke = max(20, min(K, 300))
