@@ -31,6 +31,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DIMS, LATENT, BATCH, DROPOUT = [512, 512], 32, 512, 0.6
+# launch order of one training step (engine.cu: record_backward / record_update)
+STEP_KERNELS = ['k_begin', 'k_gather', 'k_corr_rowsum', 'k_corr_build', 'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D',
+                'k_bn_fwd', 'gemm F3 heads', 'k_reparam', 'k_combine', 'k_latent_loss', 'gemm F4 dec L->D', 'k_bn_fwd',
+                'gemm F5 dec D->2D', 'k_bn_fwd', 'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 wgrad+dgrad', 'k_bn_bwd',
+                'gemm B5 wgrad+dgrad', 'k_bn_bwd', 'gemm B4 wgrad+dgrad', 'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final',
+                'gemm B3 wgrad+dgrad', 'k_bn_bwd', 'gemm B2 wgrad+dgrad', 'k_bn_bwd', 'gemm B1 wgrad', 'k_gradnorm', 'k_adam',
+                'k_end']
 N_PARAMS = 4312194
 
 
@@ -269,6 +276,14 @@ def main():
         print(f'profile run: {ms / K * 1e3:.1f} us/step', flush=True)
         eng.close()
         return
+    prof = None
+    if world == 1:
+        eng.upload_plan(idx0[:1], idx1[:1], np.full(1, 0.5), stream)
+        us = eng.profile_step(20, stream)
+        names = STEP_KERNELS if len(us) == len(STEP_KERNELS) else [f'launch{k}' for k in range(len(us))]
+        prof = {'sum_us': float(us.sum()), 'launches': [[n, round(float(u), 2)] for n, u in zip(names, us)],
+                'note': 'eager launches with a CUDA event between consecutive kernels (warm L2, no graph, no PDL): '
+                        'shares of the step, not absolutes'}
 
     # ---------------- end to end with host-resident data
     Ke = max(20, min(K, 300))
@@ -339,7 +354,8 @@ def main():
                     'steps': Ke, 'note': 'host gather into pinned memory + jb_train_step_hostbatch (H2D batch, step '
                                          'graph, D2H losses, stream sync) per step'},
             'gpu_launches': int(launches), 'launches_per_step': launches / K,
-            'roofline': roof, 'step_roofline': sroof, 'cpu_baseline': cb, 'clocks': clocks.summary(),
+            'roofline': roof, 'step_roofline': sroof, 'step_profile': prof,
+            'gemm_stages_us': [round(s[0], 2) for s in stages], 'cpu_baseline': cb, 'clocks': clocks.summary(),
             'final_losses': {k: float(v) for k, v in zip(['KL', 'Rec', 'CosSim', 'F', 'total', 'grad_norm'], losses[-1])},
         }
         print(json.dumps(line), flush=True)

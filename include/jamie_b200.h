@@ -118,6 +118,12 @@ int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, c
  * Returns the average microseconds per launch and the FLOPs of one launch. */
 int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* flops, void* stream);
 
+/* Profiling hook: runs `iters` (+1 warm-up) training steps launch by launch (no graph) with a CUDA event between
+ * consecutive launches and returns the average microseconds between the events, i.e. each kernel's in-stream time with
+ * a warm L2. out_us[k] belongs to launch k of the step (same order as the ncu launch list); *n_launches = count.
+ * Consumes plan row 0 every iteration (the cursor is rewound) and takes optimizer steps like jb_train_steps. */
+int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_launches, void* stream);
+
 /* Per-step results of the steps run since the last jb_upload_plan, in plan order. Synchronises `stream`.
  * out[s*8 + k]: k=0..3 the reference's `losses` list (KL incl. 0.032*anneal, Rec, 32*CosSim, F; unweighted by
  * loss_weights), k=4 weighted total (batch_loss), k=5 pre-clip gradient norm, k=6,7 reserved. */

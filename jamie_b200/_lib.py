@@ -62,6 +62,7 @@ SIGNATURES = {
     'jb_train_step_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P, _P]),
     'jb_step_backward_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),
     'jb_bench_stage': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), _P]),
+    'jb_profile_step': (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
     'jb_read_losses': (C.c_int, [_P, _P, C.c_int, _P]),
     'jb_encode': (C.c_int, [_P, C.c_int, _P, _LL, _LL, _P, _LL, C.c_int, _P]),
     'jb_predict': (C.c_int, [_P, C.c_int, C.c_int, _P, _LL, _LL, _P, _LL, C.c_int, _P]),

@@ -62,9 +62,14 @@ struct ModSegs {
   Seg W3, b3, g3, be3, W4, b4, g4, be4, W5, b5;  // decoder: Linear(L,D) BN(D) | Linear(D,2D) BN(2D) | Linear(2D,D)
 };
 
+struct Planes {  // a GEMM operand as TF32 hi / lo planes (same shape and pitch); see gemm_tf32.cuh
+  float *hi = nullptr, *lo = nullptr;
+};
 struct ModActs {  // activations and gradients of one modality (device pointers, pitches in floats)
-  float *x, *y1, *h1, *y2, *h2, *mulv, *y3, *g1, *y4, *g2, *xhat;
-  float *dxhat, *dg2, *dy4, *dg1, *dy3, *dc, *dmulv, *dh2, *dy2, *dh1, *dy1;
+  float *x, *y1, *y2, *mulv, *y3, *y4, *xhat;           // fp32: gathered input and GEMM outputs
+  Planes xp, h1, h2, cp, g1, g2;                         // forward GEMM operands
+  float *dg2, *dg1, *dc, *dmulv, *dh2, *dh1;             // fp32: dgrad outputs (+ dmulv from the latent backward)
+  Planes dxhat, dy4, dy3, dmp, dy2, dy1;                 // backward GEMM operands
   float *z, *c, *S, *g, *eps, *inj_eps, *den, *rs;
   float *bn_mean[4], *bn_inv[4];  // enc1, enc2, dec1, dec2
   unsigned char* inj_mask[4];
@@ -88,6 +93,7 @@ struct jb_engine {
   std::vector<PackMap> packmap;
   long long n_packed = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
+  float *theta_hi = nullptr, *theta_lo = nullptr;   // TF32 planes of theta (same layout), rewritten by every Adam step
   // BatchNorm running statistics: 8 layers in packed order (enc0.1, enc0.5, enc1.1, enc1.5, dec0.1, dec0.5, dec1.1, dec1.5)
   float* bn_run = nullptr;
   long long bn_off[8]{};
@@ -125,6 +131,7 @@ struct jb_engine {
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
+  bool use_pdl = true;       // programmatic dependent launch between the kernels of the step graph (JB_PDL=0 disables)
   // eval
   bool eval_dirty = true;
   int eval_chunk = 8192;
@@ -222,15 +229,17 @@ void carve(jb_engine* e, Carver& c) {
     ModActs& a = e->act[i];
     const int D = e->D[i];
     a.ldD = r4(D); a.ld2D = r4(2 * D); a.ldmv = r4(2 * e->L); a.LP = e->LP;
-    a.x = c.take<float>(B * a.ldD); a.y1 = c.take<float>(B * a.ld2D); a.h1 = c.take<float>(B * a.ld2D);
-    a.y2 = c.take<float>(B * a.ldD); a.h2 = c.take<float>(B * a.ldD); a.mulv = c.take<float>(B * a.ldmv);
-    a.y3 = c.take<float>(B * a.ldD); a.g1 = c.take<float>(B * a.ldD); a.y4 = c.take<float>(B * a.ld2D);
-    a.g2 = c.take<float>(B * a.ld2D); a.xhat = c.take<float>(B * a.ldD);
-    a.dxhat = c.take<float>(B * a.ldD); a.dg2 = c.take<float>(B * a.ld2D); a.dy4 = c.take<float>(B * a.ld2D);
-    a.dg1 = c.take<float>(B * a.ldD); a.dy3 = c.take<float>(B * a.ldD); a.dc = c.take<float>(B * a.LP);
-    a.dmulv = c.take<float>(B * a.ldmv); a.dh2 = c.take<float>(B * a.ldD); a.dy2 = c.take<float>(B * a.ldD);
-    a.dh1 = c.take<float>(B * a.ld2D); a.dy1 = c.take<float>(B * a.ld2D);
-    a.z = c.take<float>(B * a.LP); a.c = c.take<float>(B * a.LP); a.S = c.take<float>(B * a.LP);
+    auto planes = [&](Planes& p, size_t n) { p.hi = c.take<float>(n); p.lo = c.take<float>(n); };
+    a.x = c.take<float>(B * a.ldD); planes(a.xp, B * a.ldD);
+    a.y1 = c.take<float>(B * a.ld2D); planes(a.h1, B * a.ld2D);
+    a.y2 = c.take<float>(B * a.ldD); planes(a.h2, B * a.ldD); a.mulv = c.take<float>(B * a.ldmv);
+    a.y3 = c.take<float>(B * a.ldD); planes(a.g1, B * a.ldD); a.y4 = c.take<float>(B * a.ld2D);
+    planes(a.g2, B * a.ld2D); a.xhat = c.take<float>(B * a.ldD);
+    planes(a.dxhat, B * a.ldD); a.dg2 = c.take<float>(B * a.ld2D); planes(a.dy4, B * a.ld2D);
+    a.dg1 = c.take<float>(B * a.ldD); planes(a.dy3, B * a.ldD); a.dc = c.take<float>(B * a.LP);
+    a.dmulv = c.take<float>(B * a.ldmv); planes(a.dmp, B * a.ldmv); a.dh2 = c.take<float>(B * a.ldD); planes(a.dy2, B * a.ldD);
+    a.dh1 = c.take<float>(B * a.ld2D); planes(a.dy1, B * a.ld2D);
+    a.z = c.take<float>(B * a.LP); a.c = c.take<float>(B * a.LP); planes(a.cp, B * a.LP); a.S = c.take<float>(B * a.LP);
     a.g = c.take<float>(B * a.LP); a.eps = c.take<float>(B * a.LP); a.inj_eps = c.take<float>(B * a.LP);
     a.den = c.take<float>(B); a.rs = c.take<float>(B);
     const int w[4] = {2 * D, D, D, 2 * D};
@@ -247,27 +256,22 @@ void carve(jb_engine* e, Carver& c) {
 }
 
 // ------------------------------------------------------------------------------------------- GEMM tables
-// split: error-compensated 3xTF32 (fp32-class accuracy). Used for every forward GEMM and every dgrad of the training
-// step: pre-activation errors flip LeakyReLU' decisions and dX errors propagate down the chain, whereas a wgrad's TF32
-// rounding (~3e-4 relative, unbiased) stays local to that gradient tensor and is left single-pass.
-int add_prob(jb_engine* e, const float* A, int lda, int a_mn, const float* Bm, int ldb, int b_mn, float* C, int ldc, int M,
-             int N, int K, int bn, int epi, const float* bias, int accumulate, int split) {
+// Forward GEMMs and dgrads run the error-compensated 3xTF32 mode on hi/lo planes (fp32-class accuracy): pre-activation
+// errors flip LeakyReLU' decisions and dX errors propagate down the chain. A wgrad's TF32 rounding (~3e-4 relative,
+// unbiased) stays local to that gradient tensor, so wgrads are single-pass on the hi planes.
+int add_prob(jb_engine* e, Planes A, int lda, int a_mn, Planes Bm, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
+             int bn, int epi, const float* bias, int accumulate, int split) {
   GemmProblem g;
   if (e->precision_fast) split = 0;
-  int rc = jb::gemm_problem_fill(&g, A, lda, a_mn, Bm, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, jb::LRELU, accumulate, 1,
-                                 split);
+  int rc = jb::gemm_problem_fill(&g, A.hi, lda, a_mn, Bm.hi, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, jb::LRELU, accumulate, 0,
+                                 split ? A.lo : nullptr, split ? Bm.lo : nullptr);
   if (rc) return fail("cuTensorMapEncodeTiled failed (%d) for M%d N%d K%d lda%d ldb%d", rc, M, N, K, lda, ldb);
-  g.ks = K >= 128 ? 4 : (K >= 64 ? 2 : 1);   // k-blocks per pipeline stage (tools/gemm_lab mode 5: fewer, fatter stages win)
-  if (split && g.ks > 2) g.ks = 2;           // split stages carry hi and lo tiles: 2 x 2 k-blocks x 24 KB x 2 stages
-  if (const char* ev = getenv("JB_DEBUG_KS")) g.ks = atoi(ev);
   e->h_probs.push_back(g);
   return 0;
 }
-int choose_bn(int N, int tiles_m_total_hint) {
-  (void)tiles_m_total_hint;
+int choose_bn(int N) {
   if (N <= 32) return 32;
-  if (N <= 64) return 64;
-  return 64;  // more CTAs beat wider tiles at these problem sizes (measured in tools/gemm_lab, mode 5)
+  return 64;  // more CTAs beat wider tiles at these problem sizes
 }
 void close_stage(jb_engine* e, GemmStage& st, int first) {
   st.first = first;
@@ -286,40 +290,38 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   float* G = e->grad;
   const int L = e->L;
   int first;
-  auto W = [&](const Seg& s) { return T + s.off; };
+  auto W = [&](const Seg& s) { return Planes{e->theta_hi + s.off, e->theta_lo + s.off}; };
+  auto bias = [&](const Seg& s) { return T + s.off; };
   auto dW = [&](const Seg& s) { return G + s.off; };
-  // ---- forward
-  first = e->h_probs.size();
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.x, a.ldD, 0, W(m.W1), m.W1.ld, 0, a.y1, a.ld2D, B, 2 * D, D, choose_bn(2 * D, 0), jb::EPI_BIAS, W(m.b1), 0, 1)) return 1; }
-  close_stage(e, e->st_f[0], first);
-  first = e->h_probs.size();
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.h1, a.ld2D, 0, W(m.W2), m.W2.ld, 0, a.y2, a.ldD, B, D, 2 * D, choose_bn(D, 0), jb::EPI_BIAS, W(m.b2), 0, 1)) return 1; }
-  close_stage(e, e->st_f[1], first);
-  first = e->h_probs.size();
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.h2, a.ldD, 0, W(m.Wmv), m.Wmv.ld, 0, a.mulv, a.ldmv, B, 2 * L, D, choose_bn(2 * L, 0), jb::EPI_BIAS, W(m.bmv), 0, 1)) return 1; }
-  close_stage(e, e->st_f[2], first);
-  first = e->h_probs.size();
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.c, a.LP, 0, W(m.W3), m.W3.ld, 0, a.y3, a.ldD, B, D, L, choose_bn(D, 0), jb::EPI_BIAS, W(m.b3), 0, 1)) return 1; }
-  close_stage(e, e->st_f[3], first);
-  first = e->h_probs.size();
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.g1, a.ldD, 0, W(m.W4), m.W4.ld, 0, a.y4, a.ld2D, B, 2 * D, D, choose_bn(2 * D, 0), jb::EPI_BIAS, W(m.b4), 0, 1)) return 1; }
-  close_stage(e, e->st_f[4], first);
-  first = e->h_probs.size();
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (add_prob(e, a.g2, a.ld2D, 0, W(m.W5), m.W5.ld, 0, a.xhat, a.ldD, B, D, 2 * D, choose_bn(D, 0), jb::EPI_BIAS, W(m.b5), 0, 1)) return 1; }
-  close_stage(e, e->st_f[5], first);
-  // ---- backward: wgrad dW[N_out, N_in] = dY^T X  (A = dY MN-major, B = X MN-major, K = batch)
-  //                dgrad dX[B, N_in]     = dY W    (A = dY K-major,  B = W MN-major,  K = N_out)
-  auto wgrad = [&](const float* dY, int lddy, const float* X, int ldx, const Seg& s, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, choose_bn(n_in, 0), jb::EPI_STORE, nullptr, accum, 0);
+  // ---- forward:  Y[B, N_out] = X W^T + b   (A = X planes K-major, B = W planes K-major)
+  auto fwd = [&](GemmStage& st, auto pick) {
+    const int f0 = static_cast<int>(e->h_probs.size());
+    for (int i = 0; i < 2; ++i) if (pick(i)) return 1;
+    close_stage(e, st, f0);
+    return 0;
   };
-  auto dgrad = [&](const float* dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in, 0), jb::EPI_STORE, nullptr, 0, 1);
+  auto lin = [&](Planes X, int ldx, const Seg& w, const Seg& b, float* Y, int ldy, int n_out, int n_in) {
+    return add_prob(e, X, ldx, 0, W(w), w.ld, 0, Y, ldy, B, n_out, n_in, choose_bn(n_out), jb::EPI_BIAS, bias(b), 0, 1);
+  };
+  if (fwd(e->st_f[0], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.xp, a.ldD, m.W1, m.b1, a.y1, a.ld2D, 2 * D, D); })) return 1;
+  if (fwd(e->st_f[1], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.h1, a.ld2D, m.W2, m.b2, a.y2, a.ldD, D, 2 * D); })) return 1;
+  if (fwd(e->st_f[2], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.h2, a.ldD, m.Wmv, m.bmv, a.mulv, a.ldmv, 2 * L, D); })) return 1;
+  if (fwd(e->st_f[3], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.cp, a.LP, m.W3, m.b3, a.y3, a.ldD, D, L); })) return 1;
+  if (fwd(e->st_f[4], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D); })) return 1;
+  if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D); })) return 1;
+  // ---- backward: wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass)
+  //                dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out)
+  auto wgrad = [&](Planes dY, int lddy, Planes X, int ldx, const Seg& s, int n_out, int n_in) {
+    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, choose_bn(n_in), jb::EPI_STORE, nullptr, accum, 0);
+  };
+  auto dgrad = [&](Planes dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
+    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in), jb::EPI_STORE, nullptr, 0, 1);
   };
   first = e->h_probs.size();  // B6: last decoder Linear(2D -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -333,13 +335,13 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   close_stage(e, e->st_b[1], first);
   first = e->h_probs.size();  // B4: decoder Linear(L -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dy3, a.ldD, a.c, a.LP, m.W3, D, L)) return 1;
+    if (wgrad(a.dy3, a.ldD, a.cp, a.LP, m.W3, D, L)) return 1;
     if (dgrad(a.dy3, a.ldD, m.W3, a.dc, a.LP, D, L)) return 1; }
   close_stage(e, e->st_b[2], first);
   first = e->h_probs.size();  // B3: heads Linear(D -> 2L)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dmulv, a.ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D)) return 1;
-    if (dgrad(a.dmulv, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
+    if (wgrad(a.dmp, a.ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D)) return 1;
+    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
   close_stage(e, e->st_b[3], first);
   first = e->h_probs.size();  // B2: encoder Linear(2D -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -348,7 +350,7 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   close_stage(e, e->st_b[4], first);
   first = e->h_probs.size();  // B1: encoder Linear(D -> 2D): no input gradient
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dy1, a.ld2D, a.x, a.ldD, m.W1, 2 * D, D)) return 1; }
+    if (wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D)) return 1; }
   close_stage(e, e->st_b[5], first);
   if (e->d_probs) cudaFree(e->d_probs);
   CU(cudaMalloc(&e->d_probs, e->h_probs.size() * sizeof(GemmProblem)));
@@ -359,12 +361,35 @@ int build_train_tables(jb_engine* e, int B, int accum) {
 // ------------------------------------------------------------------------------------------- step recording
 struct Rec {  // launches kernels on a stream and counts them
   jb_engine* e; cudaStream_t s; int n = 0; cudaError_t err = cudaSuccess;
-  void check() { if (err == cudaSuccess) err = cudaGetLastError(); ++n; }
+  cudaEvent_t* ev = nullptr;        // profiling: ev[k] is recorded after launch k - 1 (ev[0] before the first launch)
+  const char** names = nullptr;
+  void mark(const char* name) {
+    if (ev && n < 63) { names[n] = name; cudaEventRecord(ev[n + 1], s); }
+  }
   void gemm(const GemmStage& st) {
-    if (err == cudaSuccess) err = jb::gemm_launch<false>(e->d_probs + st.first, st.count, st.tiles, s);
+    if (err == cudaSuccess) err = jb::gemm_launch(e->d_probs + st.first, st.count, st.tiles, s, e->use_pdl);
+    mark("gemm");
     ++n;
   }
 };
+
+// Every kernel of the step starts with griddepcontrol.launch_dependents + griddepcontrol.wait (kernels.cuh), so with
+// programmatic stream serialization the next kernel's launch latency and prologue overlap this kernel's execution while
+// all data dependencies (transitively) still see completed, flushed predecessors.
+template <typename... KP, typename... A>
+void launchk(Rec& r, void (*kern)(KP...), dim3 grid, dim3 block, A... args) {
+  if (r.err != cudaSuccess) { ++r.n; return; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = r.s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = r.e->use_pdl ? 1 : 0;
+  r.err = cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+  r.mark(nullptr);
+  ++r.n;
+}
 
 jb::StepConsts make_consts(const jb_engine* e, int B) {
   jb::StepConsts sc{};
@@ -383,6 +408,7 @@ jb::Latent make_latent(jb_engine* e) {
     ModActs& m = e->act[i];
     a.mulv[i] = m.mulv; a.eps[i] = m.eps; a.inj_eps[i] = m.inj_eps; a.z[i] = m.z; a.c[i] = m.c; a.S[i] = m.S;
     a.g[i] = m.g; a.den[i] = m.den; a.rs[i] = m.rs; a.dc_dec[i] = m.dc; a.dmulv[i] = m.dmulv;
+    a.ch[i] = m.cp.hi; a.cl[i] = m.cp.lo; a.dmh[i] = m.dmp.hi; a.dml[i] = m.dmp.lo;
   }
   a.ldmv = e->act[0].ldmv; a.r = e->lat_r; a.rowpart = e->rowpart;
   a.corr = e->corr; a.corr_t = e->corr_t; a.fblk = e->fblk; a.fblk_t = e->fblk_t;
@@ -398,19 +424,21 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   float* T = e->theta;
   float* G = e->grad;
   // control + inputs
-  jb::k_begin<<<1, 1, 0, r.s>>>(e->ctl, e->plan_kl, sc); r.check();
+  launchk(r, jb::k_begin, dim3(1), dim3(1), e->ctl, e->plan_kl, sc);
   jb::GatherArgs ga{};
   for (int i = 0; i < 2; ++i) {
     ga.data[i] = e->data[i]; ga.ld_data[i] = e->data_ld[i]; ga.x[i] = e->act[i].x; ga.ldx[i] = e->act[i].ldD;
+    ga.xh[i] = e->act[i].xp.hi; ga.xl[i] = e->act[i].xp.lo;
     ga.D[i] = e->D[i]; ga.idx[i] = e->plan_idx[i];
   }
-  if (gather) { jb::k_gather<<<dim3(B, 2), 128, 0, r.s>>>(ga, e->ctl, B); r.check(); }
+  if (gather) launchk(r, jb::k_gather, dim3(B, 2), dim3(128), ga, e->ctl, B);
+  else launchk(r, jb::k_split_x, dim3(B, 2), dim3(128), ga, B);   // host batch: x was copied in, make its operand planes
   jb::CorrArgs ca{};
   ca.p_diag = e->p_diag; ca.p_dense = e->p_dense; ca.f_dense = e->f_dense; ca.n1 = e->pn1;
   ca.idx[0] = e->plan_idx[0]; ca.idx[1] = e->plan_idx[1]; ca.rs_p = e->rs_p; ca.rs_f = e->rs_f;
   ca.corr = e->corr; ca.corr_t = e->corr_t; ca.fblk = e->fblk; ca.fblk_t = e->fblk_t; ca.pf_ratio = e->cfg.pf_ratio;
-  jb::k_corr_rowsum<<<B, 128, 0, r.s>>>(ca, e->ctl, B); r.check();
-  jb::k_corr_build<<<dim3((B + 31) / 32, (B + 31) / 32), dim3(32, 8), 0, r.s>>>(ca, e->ctl, B); r.check();
+  launchk(r, jb::k_corr_rowsum, dim3(B), dim3(128), ca, e->ctl, B);
+  launchk(r, jb::k_corr_build, dim3((B + 31) / 32, (B + 31) / 32), dim3(32, 8), ca, e->ctl, B);
 
   auto bnf = [&](int k, int which /*0 enc1,1 enc2,2 dec1,3 dec2*/) {
     (void)k;
@@ -420,29 +448,28 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       jb::BnFwd& l = pr.l[i];
       const int bnidx = which < 2 ? (2 * i + which) : (4 + 2 * i + (which - 2));
       switch (which) {
-        case 0: l.Y = a.y1; l.ldy = a.ld2D; l.H = a.h1; l.ldh = a.ld2D; l.gamma = T + m.g1.off; l.beta = T + m.be1.off; l.N = 2 * D; break;
-        case 1: l.Y = a.y2; l.ldy = a.ldD; l.H = a.h2; l.ldh = a.ldD; l.gamma = T + m.g2.off; l.beta = T + m.be2.off; l.N = D; break;
-        case 2: l.Y = a.y3; l.ldy = a.ldD; l.H = a.g1; l.ldh = a.ldD; l.gamma = T + m.g3.off; l.beta = T + m.be3.off; l.N = D; break;
-        default: l.Y = a.y4; l.ldy = a.ld2D; l.H = a.g2; l.ldh = a.ld2D; l.gamma = T + m.g4.off; l.beta = T + m.be4.off; l.N = 2 * D; break;
+        case 0: l.Y = a.y1; l.ldy = a.ld2D; l.Hh = a.h1.hi; l.Hl = a.h1.lo; l.ldh = a.ld2D; l.gamma = T + m.g1.off; l.beta = T + m.be1.off; l.N = 2 * D; break;
+        case 1: l.Y = a.y2; l.ldy = a.ldD; l.Hh = a.h2.hi; l.Hl = a.h2.lo; l.ldh = a.ldD; l.gamma = T + m.g2.off; l.beta = T + m.be2.off; l.N = D; break;
+        case 2: l.Y = a.y3; l.ldy = a.ldD; l.Hh = a.g1.hi; l.Hl = a.g1.lo; l.ldh = a.ldD; l.gamma = T + m.g3.off; l.beta = T + m.be3.off; l.N = D; break;
+        default: l.Y = a.y4; l.ldy = a.ld2D; l.Hh = a.g2.hi; l.Hl = a.g2.lo; l.ldh = a.ld2D; l.gamma = T + m.g4.off; l.beta = T + m.be4.off; l.N = 2 * D; break;
       }
       l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
       l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
     if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
-      jb::k_bn_fwd_slab<<<(pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16, jb::SLAB_THREADS, 0, r.s>>>(pr, e->ctl, B, p);
-    else jb::k_bn_fwd<<<pr.l[0].blocks + pr.l[1].blocks, 256, 0, r.s>>>(pr, e->ctl, B, p);
-    r.check();
+      launchk(r, jb::k_bn_fwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p);
+    else launchk(r, jb::k_bn_fwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p);
   };
   // ---- forward
   r.gemm(e->st_f[0]); bnf(0, 0);
   r.gemm(e->st_f[1]); bnf(1, 1);
   r.gemm(e->st_f[2]);
   jb::Latent lat = make_latent(e);
-  jb::k_reparam<<<(2 * B * L + 255) / 256, 256, 0, r.s>>>(lat, e->ctl, B, L); r.check();
+  launchk(r, jb::k_reparam, dim3((2 * B * L + 255) / 256), dim3(256), lat, e->ctl, B, L);
   const int wblocks = (2 * B * 32 + 255) / 256;
-  jb::k_combine<<<wblocks, 256, 0, r.s>>>(lat, B, L); r.check();
-  jb::k_latent_loss<<<wblocks, 256, 0, r.s>>>(lat, B, L); r.check();
+  launchk(r, jb::k_combine, dim3(wblocks), dim3(256), lat, B, L);
+  launchk(r, jb::k_latent_loss, dim3(wblocks), dim3(256), lat, B, L);
   r.gemm(e->st_f[3]); bnf(2, 2);
   r.gemm(e->st_f[4]); bnf(3, 3);
   r.gemm(e->st_f[5]);
@@ -451,13 +478,12 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
     jb::RecArgs& q = rp.m[i];
-    q.xhat = a.xhat; q.ldxh = a.ldD; q.x = a.x; q.ldx = a.ldD; q.dxhat = a.dxhat; q.lddx = a.ldD;
+    q.xhat = a.xhat; q.ldxh = a.ldD; q.x = a.x; q.ldx = a.ldD; q.dxh = a.dxhat.hi; q.dxl = a.dxhat.lo; q.lddx = a.ldD;
     const bool slab = B <= 512;
     q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + (slab ? 15 : 31)) / (slab ? 16 : 32);
   }
-  if (B <= 512) jb::k_rec_slab<<<rp.m[0].blocks + rp.m[1].blocks, jb::SLAB_THREADS, 0, r.s>>>(rp, B, sc.w[1], accum);
-  else jb::k_rec<<<rp.m[0].blocks + rp.m[1].blocks, 256, 0, r.s>>>(rp, B, sc.w[1], accum);
-  r.check();
+  if (B <= 512) launchk(r, jb::k_rec_slab, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(jb::SLAB_THREADS), rp, B, sc.w[1], accum);
+  else launchk(r, jb::k_rec, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(256), rp, B, sc.w[1], accum);
   auto bnb = [&](int which) {
     jb::BnBwdPair pr{};
     for (int i = 0; i < 2; ++i) {
@@ -465,30 +491,29 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       jb::BnBwd& l = pr.l[i];
       const int bnidx = which < 2 ? (2 * i + which) : (4 + 2 * i + (which - 2));
       switch (which) {
-        case 0: l.dH = a.dh1; l.lddh = a.ld2D; l.Y = a.y1; l.ldy = a.ld2D; l.dY = a.dy1; l.lddy = a.ld2D; l.N = 2 * D;
+        case 0: l.dH = a.dh1; l.lddh = a.ld2D; l.Y = a.y1; l.ldy = a.ld2D; l.dYh = a.dy1.hi; l.dYl = a.dy1.lo; l.lddy = a.ld2D; l.N = 2 * D;
                 l.gamma = T + m.g1.off; l.beta = T + m.be1.off; l.dgamma = G + m.g1.off; l.dbeta = G + m.be1.off; l.dbias = G + m.b1.off; break;
-        case 1: l.dH = a.dh2; l.lddh = a.ldD; l.Y = a.y2; l.ldy = a.ldD; l.dY = a.dy2; l.lddy = a.ldD; l.N = D;
+        case 1: l.dH = a.dh2; l.lddh = a.ldD; l.Y = a.y2; l.ldy = a.ldD; l.dYh = a.dy2.hi; l.dYl = a.dy2.lo; l.lddy = a.ldD; l.N = D;
                 l.gamma = T + m.g2.off; l.beta = T + m.be2.off; l.dgamma = G + m.g2.off; l.dbeta = G + m.be2.off; l.dbias = G + m.b2.off; break;
-        case 2: l.dH = a.dg1; l.lddh = a.ldD; l.Y = a.y3; l.ldy = a.ldD; l.dY = a.dy3; l.lddy = a.ldD; l.N = D;
+        case 2: l.dH = a.dg1; l.lddh = a.ldD; l.Y = a.y3; l.ldy = a.ldD; l.dYh = a.dy3.hi; l.dYl = a.dy3.lo; l.lddy = a.ldD; l.N = D;
                 l.gamma = T + m.g3.off; l.beta = T + m.be3.off; l.dgamma = G + m.g3.off; l.dbeta = G + m.be3.off; l.dbias = G + m.b3.off; break;
-        default: l.dH = a.dg2; l.lddh = a.ld2D; l.Y = a.y4; l.ldy = a.ld2D; l.dY = a.dy4; l.lddy = a.ld2D; l.N = 2 * D;
+        default: l.dH = a.dg2; l.lddh = a.ld2D; l.Y = a.y4; l.ldy = a.ld2D; l.dYh = a.dy4.hi; l.dYl = a.dy4.lo; l.lddy = a.ld2D; l.N = 2 * D;
                 l.gamma = T + m.g4.off; l.beta = T + m.be4.off; l.dgamma = G + m.g4.off; l.dbeta = G + m.be4.off; l.dbias = G + m.b4.off; break;
       }
       l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
     if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
-      jb::k_bn_bwd_slab<<<(pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16, jb::SLAB_THREADS, 0, r.s>>>(pr, e->ctl, B, p, accum);
-    else jb::k_bn_bwd<<<pr.l[0].blocks + pr.l[1].blocks, 256, 0, r.s>>>(pr, e->ctl, B, p, accum);
-    r.check();
+      launchk(r, jb::k_bn_bwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p, accum);
+    else launchk(r, jb::k_bn_bwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p, accum);
   };
   r.gemm(e->st_b[0]); bnb(3);
   r.gemm(e->st_b[1]); bnb(2);
   r.gemm(e->st_b[2]);
   const float k_cos = sc.w[2] * 32.f * 2.f / (static_cast<float>(B) * static_cast<float>(L));
   const float k_f = sc.w[3] * 2.f / (static_cast<float>(B) * static_cast<float>(L));
-  jb::k_latent_bwd_c<<<wblocks, 256, 0, r.s>>>(lat, B, L, k_cos, k_f); r.check();
-  jb::k_latent_bwd_z<<<wblocks, 256, 0, r.s>>>(lat, e->ctl, B, L, k_cos); r.check();
+  launchk(r, jb::k_latent_bwd_c, dim3(wblocks), dim3(256), lat, B, L, k_cos, k_f);
+  launchk(r, jb::k_latent_bwd_z, dim3(wblocks), dim3(256), lat, e->ctl, B, L, k_cos);
   jb::FinalArgs fa{};
   fa.rowpart = e->rowpart;
   for (int i = 0; i < 2; ++i) {
@@ -497,7 +522,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   }
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
   fa.grad_tail = G + e->n_flat;
-  jb::k_latent_final<<<1, 1024, 0, r.s>>>(fa, lat, e->ctl, B, L, sc, accum); r.check();
+  launchk(r, jb::k_latent_final, dim3(1), dim3(1024), fa, lat, e->ctl, B, L, sc, accum);
   r.gemm(e->st_b[3]); bnb(1);
   r.gemm(e->st_b[4]); bnb(0);
   r.gemm(e->st_b[5]);
@@ -506,10 +531,9 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
 void record_update(jb_engine* e, Rec& r, int B) {
   const jb::StepConsts sc = make_consts(e, B);
   const long long n4 = e->n_flat / 4;
-  jb::k_gradnorm<<<jb::NORM_BLOCKS, 256, 0, r.s>>>(e->grad, n4, e->norm_part); r.check();
-  jb::k_adam<<<jb::NORM_BLOCKS * 2, 256, 0, r.s>>>(e->theta, e->grad, e->adam_m, e->adam_v, n4, e->norm_part,
-                                                   jb::NORM_BLOCKS, e->ctl, sc, e->out_loss); r.check();
-  jb::k_end<<<1, 1, 0, r.s>>>(e->ctl); r.check();
+  launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, n4, e->norm_part);
+  launchk(r, jb::k_adam, jb::NORM_BLOCKS * 2, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
+  launchk(r, jb::k_end, dim3(1), dim3(1), e->ctl);
 }
 
 int capture(jb_engine* e, int B, int what /*0 full,1 bwd,2 upd*/, cudaGraphExec_t* out, int* nlaunch) {
@@ -606,7 +630,7 @@ int run_chain(jb_engine* e, int from, int to, const float* in, int ld_in, int ro
   }
   CU(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, s));
   for (size_t k = 0; k < tab.size(); ++k) {
-    CU(jb::gemm_launch<false>(d_tab + k, 1, tab[k].tiles_m * tab[k].tiles_n, s));
+    CU(jb::gemm_launch(d_tab + k, 1, tab[k].tiles_m * tab[k].tiles_n, s));
     ++e->launches;
   }
   return 0;
@@ -698,7 +722,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
     return 0;
   };
   if (alloc0(&e->theta, fb) || alloc0(&e->grad, fb) || alloc0(&e->adam_m, fb) || alloc0(&e->adam_v, fb) ||
-      alloc0(&e->theta_eval, fb) || alloc0(&e->bn_run, e->n_bn * 4)) { jb_destroy(e); return 1; }
+      alloc0(&e->theta_eval, fb) || alloc0(&e->theta_hi, fb) || alloc0(&e->theta_lo, fb) ||
+      alloc0(&e->bn_run, e->n_bn * 4)) { jb_destroy(e); return 1; }
   {  // BatchNorm defaults: running_mean 0, running_var 1; gamma = 1 is set through jb_set_params
     std::vector<float> h(e->n_bn, 0.f);
     for (int k = 0; k < 8; ++k)
@@ -718,7 +743,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMemcpy(e->ctl, &c0, sizeof c0, cudaMemcpyHostToDevice));
   CU(cudaMalloc(&e->norm_part, jb::NORM_BLOCKS * sizeof(double)));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
-  CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
+  if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
   // eval workspaces: two slots of chunk activations
   {
     const int Dm = e->D[0] > e->D[1] ? e->D[0] : e->D[1];
@@ -742,7 +768,7 @@ void jb_destroy(jb_engine* e) {
   if (e->g_host) cudaGraphExecDestroy(e->g_host);
   if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
   if (e->h_pin) cudaFreeHost(e->h_pin);
-  void* ptrs[] = {e->theta, e->grad, e->adam_m, e->adam_v, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
+  void* ptrs[] = {e->theta, e->grad, e->adam_m, e->adam_v, e->theta_eval, e->theta_hi, e->theta_lo, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
                   e->arena, e->d_probs, e->ev_a, e->ev_b, e->ev_in, e->ev_out, e->d_ev_probs};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -759,7 +785,12 @@ int jb_set_params(jb_engine* e, const float* packed, long long n) {
   if (n != e->n_packed) return fail("expected %lld parameters, got %lld", e->n_packed, n);
   CU(cudaDeviceSynchronize());
   e->eval_dirty = true;
-  return copy_packed(e, e->theta, const_cast<float*>(packed), true);
+  if (copy_packed(e, e->theta, const_cast<float*>(packed), true)) return 1;
+  jb::k_split_flat<<<296, 256>>>(e->theta, e->theta_hi, e->theta_lo, e->n_flat);   // operand planes of the training GEMMs
+  ++e->launches;
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return 0;
 }
 int jb_get_params(jb_engine* e, float* packed, long long n) {
   if (!e || !packed) return fail("null argument");
@@ -1048,9 +1079,9 @@ int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* fl
     fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch<false>(e->d_probs + st.first, st.count, st.tiles, s));
+  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.tiles, s));
   CU(cudaEventRecord(a, s));
-  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch<false>(e->d_probs + st.first, st.count, st.tiles, s));
+  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.tiles, s));
   CU(cudaEventRecord(b, s));
   CU(cudaEventSynchronize(b));
   float ms = 0;
@@ -1059,6 +1090,48 @@ int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* fl
   e->launches += iters + 3;
   *avg_us = ms * 1000.f / static_cast<float>(iters);
   *flops = fl;
+  return 0;
+}
+
+int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_launches, void* stream) {
+  if (!e || !out_us || !n_launches || iters <= 0) return fail("bad argument");
+  if (!e->plan_B) return fail("jb_upload_plan must be called first");
+  if (ensure_graphs(e, e->plan_B)) return 1;
+  if (!e->data[0] || !e->data[1]) return fail("jb_set_dataset must be called for both modalities first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev[65];
+  const char* names[64] = {};
+  for (auto& x : ev) CU(cudaEventCreate(&x));
+  std::vector<double> acc(64, 0.0);
+  int n = 0;
+  const bool pdl = e->use_pdl;
+  e->use_pdl = false;   // events between launches serialise the stream anyway
+  for (int it = 0; it < iters + 1; ++it) {
+    // rewind the plan cursor so that the profile can run any number of iterations
+    CU(cudaMemsetAsync(&e->ctl->cursor, 0, sizeof(long long), s));
+    jb::k_spin<<<1, 1, 0, s>>>(400000);   // 0.4 ms head start: the host enqueues the whole step behind it
+    Rec r{e, s};
+    r.ev = ev; r.names = names;
+    CU(cudaEventRecord(ev[0], s));
+    record_backward(e, r, e->plan_B);
+    record_update(e, r, e->plan_B);
+    CU(cudaStreamSynchronize(s));
+    if (r.err != cudaSuccess) return fail("launch failed while profiling: %s", cudaGetErrorString(r.err));
+    n = r.n < 64 ? r.n : 64;
+    if (it == 0) continue;   // warm-up
+    for (int k = 0; k < n; ++k) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      acc[k] += ms * 1e3;
+    }
+  }
+  e->use_pdl = pdl;
+  for (auto& x : ev) cudaEventDestroy(x);
+  for (int k = 0; k < 8; ++k) e->nbt[k] += iters + 1;
+  e->launches += static_cast<long long>(iters + 1) * (n + 1);
+  e->eval_dirty = true;
+  *n_launches = n;
+  for (int k = 0; k < n && k < cap; ++k) out_us[k] = static_cast<float>(acc[k] / iters);
   return 0;
 }
 
@@ -1096,7 +1169,7 @@ struct DevBuf {  // scoped device allocation
 int launch_one(jb_engine* e, GemmProblem& g, GemmProblem* d_slot, cudaStream_t s) {
   jb::gemm_table_finalize(&g, 1);
   CU(cudaMemcpyAsync(d_slot, &g, sizeof g, cudaMemcpyHostToDevice, s));
-  CU(jb::gemm_launch<false>(d_slot, 1, g.tiles_m * g.tiles_n, s));
+  CU(jb::gemm_launch(d_slot, 1, g.tiles_m * g.tiles_n, s));
   ++e->launches;
   return 0;
 }
@@ -1135,15 +1208,14 @@ int jb_pca_project(jb_engine* e, const float* X, long long n, long long d, const
       src = x_raw.p;
     }
     jb::k_split_tf32<<<static_cast<unsigned>(rows), 256, 0, s>>>(src, d, rows, static_cast<int>(d), 0, d_mean.p, 1.f, 0.f, x_hi.p, x_lo.p, ldd); ++e->launches;
-    const float* As[3] = {x_hi.p, x_hi.p, x_lo.p};
-    const float* Bs[3] = {c_hi.p, c_lo.p, c_hi.p};
-    for (int pass = 0; pass < 3; ++pass) {
-      GemmProblem g;
-      const int bn = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
-      int rc = jb::gemm_problem_fill(&g, As[pass], static_cast<int>(ldd), 0, Bs[pass], static_cast<int>(ldd), 0, z.p, ldk,
-                                     static_cast<int>(rows), k, static_cast<int>(d), bn, jb::EPI_STORE, nullptr, 0.f, pass > 0);
+    {
+      GemmProblem g;   // one 3xTF32 launch on the hi/lo planes
+      const int bn = k <= 32 ? 32 : 64;
+      int rc = jb::gemm_problem_fill(&g, x_hi.p, static_cast<int>(ldd), 0, c_hi.p, static_cast<int>(ldd), 0, z.p, ldk,
+                                     static_cast<int>(rows), k, static_cast<int>(d), bn, jb::EPI_STORE, nullptr, 0.f, 0, 0,
+                                     x_lo.p, c_lo.p);
       if (rc) return fail("PCA tensor map encode failed (%d)", rc);
-      if (launch_one(e, g, e->d_ev_probs + pass, s)) return 1;
+      if (launch_one(e, g, e->d_ev_probs, s)) return 1;
     }
     float* dst = on_device ? out + r0 * k : out_dev.p;
     jb::k_standardise<<<static_cast<unsigned>(rows), 128, 0, s>>>(z.p, ldk, rows, k, m, sdev, dst, k); ++e->launches;
@@ -1178,15 +1250,13 @@ int jb_pca_inverse(jb_engine* e, const float* Z, long long n, int k, const float
       src = z_raw.p;
     }
     jb::k_split_tf32<<<static_cast<unsigned>(rows), 128, 0, s>>>(src, k, rows, k, 1, nullptr, sdev, m, z_hi.p, z_lo.p, ldk); ++e->launches;
-    const float* As[3] = {z_hi.p, z_hi.p, z_lo.p};
-    const float* Bs[3] = {c_hi.p, c_lo.p, c_hi.p};
-    for (int pass = 0; pass < 3; ++pass) {
+    {
       GemmProblem g;   // out[rows, d] = A[rows, k] * comp[k, d]: B is logically [N = d, K = k] stored [k][d] -> MN-major
-      int rc = jb::gemm_problem_fill(&g, As[pass], ldk, 0, Bs[pass], static_cast<int>(ldd), 1, o.p, static_cast<int>(ldd),
-                                     static_cast<int>(rows), static_cast<int>(d), k, 128, pass == 0 ? jb::EPI_BIAS : jb::EPI_STORE,
-                                     d_mean.p, 0.f, pass > 0);
+      int rc = jb::gemm_problem_fill(&g, z_hi.p, ldk, 0, c_hi.p, static_cast<int>(ldd), 1, o.p, static_cast<int>(ldd),
+                                     static_cast<int>(rows), static_cast<int>(d), k, 64, jb::EPI_BIAS, d_mean.p, 0.f, 0, 0,
+                                     z_lo.p, c_lo.p);
       if (rc) return fail("PCA tensor map encode failed (%d)", rc);
-      if (launch_one(e, g, e->d_ev_probs + pass, s)) return 1;
+      if (launch_one(e, g, e->d_ev_probs, s)) return 1;
     }
     CU(cudaMemcpy2DAsync(out + r0 * d, static_cast<size_t>(d) * 4, o.p, static_cast<size_t>(ldd) * 4, static_cast<size_t>(d) * 4,
                          rows, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -1200,24 +1270,27 @@ long long jb_debug_read(jb_engine* e, const char* name, float* out, long long ca
   if (!e || !name || !out) { fail("null argument"); return -1; }
   cudaDeviceSynchronize();
   const int B = e->graph_B ? e->graph_B : e->plan_B;
-  struct Tap { const char* n; const float* p; long long rows, cols, ld; };
+  struct Tap { const char* n; const float* p; long long rows, cols, ld; const float* lo = nullptr; };
   std::vector<Tap> taps;
   char nm[2][24][16];
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i];
     const int D = e->D[i], L = e->L;
-    const struct { const char* base; const float* p; int cols, ld; } t[] = {
-        {"x", a.x, D, a.ldD}, {"y1_", a.y1, 2 * D, a.ld2D}, {"h1_", a.h1, 2 * D, a.ld2D}, {"y2_", a.y2, D, a.ldD},
-        {"h2_", a.h2, D, a.ldD}, {"mulv", a.mulv, 2 * L, a.ldmv}, {"z", a.z, L, a.LP}, {"c", a.c, L, a.LP},
-        {"eps", a.eps, L, a.LP}, {"g1_", a.g1, D, a.ldD}, {"g2_", a.g2, 2 * D, a.ld2D}, {"xhat", a.xhat, D, a.ldD},
-        {"dxhat", a.dxhat, D, a.ldD}, {"dg2_", a.dg2, 2 * D, a.ld2D}, {"dy4_", a.dy4, 2 * D, a.ld2D},
-        {"dg1_", a.dg1, D, a.ldD}, {"dy3_", a.dy3, D, a.ldD}, {"dc", a.dc, L, a.LP}, {"dmulv", a.dmulv, 2 * L, a.ldmv},
-        {"dh2_", a.dh2, D, a.ldD}, {"dy2_", a.dy2, D, a.ldD}, {"dh1_", a.dh1, 2 * D, a.ld2D}, {"dy1_", a.dy1, 2 * D, a.ld2D},
-        {"S", a.S, L, a.LP}};
+    // tensors that only exist as operand planes are returned as hi + lo
+    const struct { const char* base; const float* p; int cols, ld; const float* lo; } t[] = {
+        {"x", a.x, D, a.ldD, nullptr}, {"y1_", a.y1, 2 * D, a.ld2D, nullptr}, {"h1_", a.h1.hi, 2 * D, a.ld2D, a.h1.lo},
+        {"y2_", a.y2, D, a.ldD, nullptr}, {"h2_", a.h2.hi, D, a.ldD, a.h2.lo}, {"mulv", a.mulv, 2 * L, a.ldmv, nullptr},
+        {"z", a.z, L, a.LP, nullptr}, {"c", a.c, L, a.LP, nullptr}, {"eps", a.eps, L, a.LP, nullptr},
+        {"g1_", a.g1.hi, D, a.ldD, a.g1.lo}, {"g2_", a.g2.hi, 2 * D, a.ld2D, a.g2.lo}, {"xhat", a.xhat, D, a.ldD, nullptr},
+        {"dxhat", a.dxhat.hi, D, a.ldD, a.dxhat.lo}, {"dg2_", a.dg2, 2 * D, a.ld2D, nullptr},
+        {"dy4_", a.dy4.hi, 2 * D, a.ld2D, a.dy4.lo}, {"dg1_", a.dg1, D, a.ldD, nullptr}, {"dy3_", a.dy3.hi, D, a.ldD, a.dy3.lo},
+        {"dc", a.dc, L, a.LP, nullptr}, {"dmulv", a.dmulv, 2 * L, a.ldmv, nullptr}, {"dh2_", a.dh2, D, a.ldD, nullptr},
+        {"dy2_", a.dy2.hi, D, a.ldD, a.dy2.lo}, {"dh1_", a.dh1, 2 * D, a.ld2D, nullptr},
+        {"dy1_", a.dy1.hi, 2 * D, a.ld2D, a.dy1.lo}, {"S", a.S, L, a.LP, nullptr}};
     int k = 0;
     for (const auto& q : t) {
       snprintf(nm[i][k], sizeof nm[i][k], "%s%d", q.base, i);
-      taps.push_back({nm[i][k], q.p, B, q.cols, q.ld});
+      taps.push_back({nm[i][k], q.p, B, q.cols, q.ld, q.lo});
       ++k;
     }
   }
@@ -1232,6 +1305,13 @@ long long jb_debug_read(jb_engine* e, const char* name, float* out, long long ca
       cudaError_t ce = cudaMemcpy2D(out, static_cast<size_t>(t.cols) * 4, t.p, static_cast<size_t>(t.ld) * 4,
                                     static_cast<size_t>(t.cols) * 4, t.rows, cudaMemcpyDeviceToHost);
       if (ce != cudaSuccess) { fail("debug read failed: %s", cudaGetErrorString(ce)); return -1; }
+      if (t.lo) {
+        std::vector<float> lo(static_cast<size_t>(need));
+        ce = cudaMemcpy2D(lo.data(), static_cast<size_t>(t.cols) * 4, t.lo, static_cast<size_t>(t.ld) * 4,
+                          static_cast<size_t>(t.cols) * 4, t.rows, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { fail("debug read failed: %s", cudaGetErrorString(ce)); return -1; }
+        for (long long q = 0; q < need; ++q) out[q] += lo[static_cast<size_t>(q)];
+      }
       return need;
     }
   }

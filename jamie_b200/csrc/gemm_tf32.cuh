@@ -9,23 +9,28 @@
 // without materialising transposed copies. One launch covers a whole table of problems (both
 // modalities, wgrad + dgrad of a stage, ...): blockIdx.x is a global tile id.
 //
-// Numerics: operands are fp32 in global memory; the tensor maps are typed TFLOAT32 so TMA rounds
-// (round-to-nearest) to TF32 on the way into shared memory (verified on B200: a FLOAT32 map leaves the low
-// mantissa bits and the tensor core then truncates, which biases every product low). Accumulation is fp32.
+// Numerics: accumulation is fp32 in TMEM. Two operand modes:
+//   split = 0 (wgrad, inference): one TF32 pass. Operands are either fp32 arrays read through TFLOAT32 tensor maps
+//       (TMA rounds to nearest on the way into shared memory; a FLOAT32 map would leave the low mantissa bits and the
+//       tensor core then truncates, which biases every product low -- verified on B200) or planes that already hold
+//       TF32-representable values.
+//   split = 1 (forward and dgrad of the training step): error-compensated 3xTF32 on PRE-SPLIT operands. Every producer
+//       kernel of the step (gather, BatchNorm slabs, latent kernels, Adam) writes its result x as two planes
+//       hi = rna_tf32(x), lo = rna_tf32(x - hi), so |x - hi - lo| <= 2^-23 |x| and both planes are exactly
+//       representable (the tensor core's truncation is then a no-op and nothing is biased). Per 8-wide K step the MMA
+//       warp issues TWO instructions:  D[:, 0:2bn] += A_hi * [B_hi ; B_lo]^T   (B_hi and B_lo tiles are adjacent in
+//       shared memory, so one N = 2 bn instruction reads A_hi once) and  D[:, 0:bn] += A_lo * B_hi^T. The epilogue adds
+//       the two column groups. Only lo*lo (<= 2^-22 relative, unbiased) is dropped: fp32-class products from the TF32
+//       pipe. Needed because a single TF32 pass perturbs pre-activations by ~5e-4, which flips LeakyReLU' at ~4e-4 of
+//       the elements and costs ~2e-2 of relative gradient error -- far outside the 1e-3 parity tolerance.
 //
 // Shared-memory layouts (verified on B200 with tools/gemm_lab.cu):
 //   K-major operand : TMA SWIZZLE_128B, box {32 k, rows};  UMMA layout SWIZZLE_128B, SBO 1024, +32 B per K=8 step
 //   MN-major operand: TMA SWIZZLE_128B_ATOM_32B, boxes {32 rows, 32 k} (4 KB each);  UMMA layout
 //                     SWIZZLE_128B_BASE32B (the only MN-major layout for 32-bit operands), LBO 4096, SBO 512,
 //                     +1024 B per K=8 step
-//
-// split = 1 (training GEMMs): error-compensated 3xTF32. The tensor maps are typed FLOAT32 (raw fp32 lands in shared
-// memory) and the tensor core itself truncates every operand to TF32, so the raw tile doubles as the HIGH part
-// hi = trunc(x) for free; the four epilogue warps, idle during the main loop, write the exact remainders
-// lo = x - trunc(x) into a second tile, and each K step issues three MMAs  hi*hi + lo*hi + hi*lo  (lo*lo ~ 2^-22
-// dropped). Products are then exact to ~2^-20, i.e. fp32-class results from the TF32 pipe. Needed because a single
-// TF32 pass perturbs pre-activations by ~5e-4, which flips LeakyReLU' at ~4e-4 of the elements and costs ~2e-2 of
-// relative gradient error (measured, profiles/parity_r1.md) -- far outside the 1e-3 parity tolerance.
+// One k-block (32 floats of K) in shared memory: [A_hi 16 KB][A_lo 16 KB][B_hi bn*128 B][B_lo bn*128 B] (split) or
+// [A][B]; the ring holds as many k-blocks as fit in 192 KB (4 for split bn = 64, 8 for single-pass).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> padded smem transpose -> coalesced 128-bit global stores).
@@ -49,6 +54,7 @@ constexpr int GEMM_EPI_PITCH = 36;                         // floats; 144 B rows
 constexpr int GEMM_EPI_SMEM = 4 * 32 * GEMM_EPI_PITCH * 4; // 18 KB: one 32x32 transpose buffer per epilogue warp
 constexpr int GEMM_SMEM_BYTES = GEMM_TILE_SMEM + GEMM_CTRL_SMEM + GEMM_EPI_SMEM + 1024;  // + alignment slack
 constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_DRAIN_KB = 2;       // split: k-blocks accumulated in TMEM between two drains (8 accumulation steps)
 
 enum GemmEpilogue : int {
   EPI_STORE = 0,       // C = acc
@@ -57,38 +63,33 @@ enum GemmEpilogue : int {
 };
 
 struct alignas(128) GemmProblem {
-  CUtensorMap tmA;  // 128 B each
+  CUtensorMap tmA;     // 128 B each; split: the hi planes
   CUtensorMap tmB;
+  CUtensorMap tmA_lo;  // split only
+  CUtensorMap tmB_lo;
   float* C;
   const float* bias;
   int M, N, K, ldc;
-  int bn;          // N tile = UMMA N (32, 64, 128 or 256)
+  int bn;          // N tile (32, 64 or 128); split problems issue UMMA N = 2 bn
   int a_mn, b_mn;  // 0 = K-major operand, 1 = MN-major operand
   int epi;
   int tiles_m, tiles_n, tile_base;
   int accumulate;  // C += result (one CTA owns the tile: no atomics)
   float slope;
-  uint32_t mn_lbo, mn_sbo;  // MN-major descriptor byte offsets (4096 / 512 for this tiling)
-  uint32_t mn_layout;       // UMMA layout type of MN-major operands (1 = SWIZZLE_128B_BASE32B)
-  int ks;                   // k-blocks (32 floats of K each) per pipeline stage: 1, 2 or 4
-  long long* dbg;           // optional: per-CTA phase timestamps (bring-up lab only)
-  int dbg_mode;             // lab only: 1 = TMA only (no MMA), 2 = MMA only (no TMA)
-  int split;                // 1: error-compensated 3xTF32 (fp32-level accuracy), see the header comment
+  int split;       // 1: error-compensated 3xTF32 on pre-split hi/lo planes, see the header comment
 };
 
 struct GemmCtrl {
   uint64_t full[GEMM_MAX_STAGES];
   uint64_t empty[GEMM_MAX_STAGES];
-  uint64_t ready[GEMM_MAX_STAGES];   // split mode: lo tiles written by the splitter warps
   uint64_t tmem_full;
+  uint64_t acc_full[2];    // split: a k-block's worth of hi*hi products is complete in accumulator buffer b
+  uint64_t acc_empty[2];   // split: the epilogue warps have drained buffer b (4 arrivals)
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
-// kLab = true adds the bring-up instrumentation (phase timestamps, TMA-only / MMA-only modes); the product
-// instantiation (kLab = false) carries none of it.
-template <bool kLab>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   extern __shared__ uint8_t smem_raw[];
@@ -120,33 +121,31 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   float* const pC = P.C;
   const float* const pbias = P.bias;
   const float slope = P.slope;
-  const uint32_t mn_lbo = P.mn_lbo, mn_sbo = P.mn_sbo, mn_layout = P.mn_layout;
-  const int dbg_mode = kLab ? P.dbg_mode : 0;
-  const CUtensorMap* const tmA = &P.tmA;
-  const CUtensorMap* const tmB = &P.tmB;
-  const int num_kb = (P.K + GEMM_BK - 1) / GEMM_BK;
-  const int kblock_bytes = GEMM_A_STAGE_BYTES + bn * GEMM_BK * 4;  // one k-block: A sub-tile then B sub-tile
-  const int ks = P.ks;
   const int split = P.split;
-  const int raw_bytes = ks * kblock_bytes;                 // raw (hi) k-blocks of a stage, contiguous
-  const int stage_bytes = raw_bytes * (split ? 2 : 1);     // split: the lo k-blocks follow the raw ones
-  int nstages = GEMM_TILE_SMEM / stage_bytes;
+  const int num_kb = (P.K + GEMM_BK - 1) / GEMM_BK;
+  const int b_bytes = bn * GEMM_BK * 4;
+  const int kb_bytes = (GEMM_A_STAGE_BYTES + b_bytes) * (split ? 2 : 1);   // one ring slot = one k-block
+  int nstages = GEMM_TILE_SMEM / kb_bytes;
   if (nstages > GEMM_MAX_STAGES) nstages = GEMM_MAX_STAGES;
-  const int num_st = (num_kb + ks - 1) / ks;  // pipeline iterations
-  uint32_t tmem_cols = bn < 32 ? 32u : static_cast<uint32_t>(bn);  // power of two >= 32
-  if (kLab && dbg_mode == 6) tmem_cols *= 2;  // lab: two independent accumulators
+  // split: [big0 | small0 | big1 | small1], bn columns each (see the MMA issuer); bn in {32, 64}: a power of two >= 32
+  const uint32_t tmem_cols = static_cast<uint32_t>(split ? 4 * bn : bn);
+  // offsets inside a ring slot
+  const int off_alo = GEMM_A_STAGE_BYTES;                        // split only
+  const int off_b = split ? 2 * GEMM_A_STAGE_BYTES : GEMM_A_STAGE_BYTES;
 
-  long long* dbg = (kLab && P.dbg) ? P.dbg + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
-  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tmA);
-    tma_prefetch_desc(tmB);
+    tma_prefetch_desc(&P.tmA);
+    tma_prefetch_desc(&P.tmB);
+    if (split) { tma_prefetch_desc(&P.tmA_lo); tma_prefetch_desc(&P.tmB_lo); }
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&ctrl->full[s], 1);
       mbar_init(&ctrl->empty[s], 1);
-      mbar_init(&ctrl->ready[s], 4);   // one arrival per splitter warp
     }
     mbar_init(&ctrl->tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctrl->acc_full[b], 1);
+      mbar_init(&ctrl->acc_empty[b], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -157,36 +156,43 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = ctrl->tmem_base;
-  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  // Everything above touched only this kernel's own parameters (the problem table and tensor maps are written by the
+  // host, never by a kernel of the step): with programmatic dependent launch it overlaps the previous kernel's tail.
+  grid_dep_wait();
+  grid_dep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (whole warp loops, one elected lane issues)
+    const CUtensorMap* const tmA = &P.tmA;
+    const CUtensorMap* const tmB = &P.tmB;
+    const CUtensorMap* const tmAl = &P.tmA_lo;
+    const CUtensorMap* const tmBl = &P.tmB_lo;
     int s = 0;          // ring slot and its phase parity, advanced incrementally (no integer divisions in the loop)
     uint32_t ph = 0;
-    for (int it = 0; it < ((kLab && dbg_mode >= 3) ? 0 : num_st); ++it) {
+    for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&ctrl->empty[s], ph ^ 1);
-      const int kb0 = it * ks;
-      const int nk = min(ks, num_kb - kb0);
       if (elect_one()) {
-        if (kLab && dbg_mode == 2) {
-          mbar_arrive(&ctrl->full[s]);
+        uint64_t* bar = &ctrl->full[s];
+        mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kb_bytes));
+        uint8_t* sa = tiles + s * kb_bytes;
+        uint8_t* sb = sa + off_b;
+        const int k0 = kb * GEMM_BK;
+        if (!a_mn) {
+          tma_load_2d(sa, tmA, bar, k0, m0);  // box {32 k, 128 rows}
+          if (split) tma_load_2d(sa + off_alo, tmAl, bar, k0, m0);
         } else {
-          mbar_arrive_expect_tx(&ctrl->full[s], static_cast<uint32_t>(nk * kblock_bytes));
-          for (int j = 0; j < nk; ++j) {
-            uint8_t* sa = tiles + s * stage_bytes + j * kblock_bytes;
-            uint8_t* sb = sa + GEMM_A_STAGE_BYTES;
-            const int k0 = (kb0 + j) * GEMM_BK;
-            if (!a_mn) {
-              tma_load_2d(sa, tmA, &ctrl->full[s], k0, m0);  // box {32 k, 128 rows}
-            } else {
-              for (int i = 0; i < GEMM_BM / 32; ++i)  // box {32 rows(contiguous), 32 k}
-                tma_load_2d(sa + i * 4096, tmA, &ctrl->full[s], m0 + 32 * i, k0);
-            }
-            if (!b_mn) {
-              tma_load_2d(sb, tmB, &ctrl->full[s], k0, n0);  // box {32 k, bn rows}
-            } else {
-              for (int i = 0; i < bn / 32; ++i) tma_load_2d(sb + i * 4096, tmB, &ctrl->full[s], n0 + 32 * i, k0);
-            }
+          for (int i = 0; i < GEMM_BM / 32; ++i) {  // box {32 rows(contiguous), 32 k}
+            tma_load_2d(sa + i * 4096, tmA, bar, m0 + 32 * i, k0);
+            if (split) tma_load_2d(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0);
+          }
+        }
+        if (!b_mn) {
+          tma_load_2d(sb, tmB, bar, k0, n0);  // box {32 k, bn rows}
+          if (split) tma_load_2d(sb + b_bytes, tmBl, bar, k0, n0);
+        } else {
+          for (int i = 0; i < bn / 32; ++i) {
+            tma_load_2d(sb + i * 4096, tmB, bar, n0 + 32 * i, k0);
+            if (split) tma_load_2d(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0);
           }
         }
       }
@@ -196,99 +202,125 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (whole warp loops, one elected lane issues)
     const uint32_t idesc = umma_idesc_tf32(GEMM_BM, bn, a_mn, b_mn);
+    const uint32_t idesc2 = umma_idesc_tf32(GEMM_BM, 2 * bn, a_mn, b_mn);   // A_hi x [B_hi ; B_lo]
     const uint32_t a_step16 = a_mn ? 64u : 2u;  // descriptor start-address units (16 B) per UMMA_K step
     const uint32_t b_step16 = b_mn ? 64u : 2u;
     // descriptor bits that do not change across the k loop (everything but the start address)
-    const uint64_t da_hi = umma_smem_desc(0u, a_mn ? mn_lbo : 16u, a_mn ? mn_sbo : 1024u, a_mn ? mn_layout : 2u);
-    const uint64_t db_hi = umma_smem_desc(0u, b_mn ? mn_lbo : 16u, b_mn ? mn_sbo : 1024u, b_mn ? mn_layout : 2u);
+    const uint64_t da_hi = umma_smem_desc(0u, a_mn ? 4096u : 16u, a_mn ? 512u : 1024u, a_mn ? 1u : 2u);
+    const uint64_t db_hi = umma_smem_desc(0u, b_mn ? 4096u : 16u, b_mn ? 512u : 1024u, b_mn ? 1u : 2u);
     const uint32_t tiles_u32 = smem_u32(tiles);
+    const uint32_t alo16 = static_cast<uint32_t>(off_alo) >> 4;
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < num_st; ++it) {
-      if (!(kLab && dbg_mode >= 3)) mbar_wait(split ? &ctrl->ready[s] : &ctrl->full[s], ph);     // lab modes 3/4: no pipeline at all
-      if (!(kLab && dbg_mode == 5)) tc_fence_after();
-      if (kLab && dbg && it == 0 && lane == 0) dbg[2] = clock64();
-      const int kb0 = it * ks;
-      const int nk = min(ks, num_kb - kb0);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&ctrl->full[s], ph);
+      const int chunk = kb / GEMM_DRAIN_KB;
+      const bool chunk_start = kb % GEMM_DRAIN_KB == 0;
+      if (split && chunk_start && chunk >= 2) mbar_wait(&ctrl->acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);   // buffer drained
+      tc_fence_after();
       if (elect_one()) {
-        if (kLab && dbg_mode == 1) {
-          mbar_arrive(&ctrl->empty[s]);
-        } else {
-          for (int j = 0; j < nk; ++j) {
-            const uint32_t sa = tiles_u32 + s * stage_bytes + j * kblock_bytes;  // 1024-aligned: (addr >> 4) + k*step
-            const uint32_t sb = sa + GEMM_A_STAGE_BYTES;                        // never carries out of the 14-bit field
-            const uint64_t da0 = da_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
-            const uint64_t db0 = db_hi | static_cast<uint64_t>((sb >> 4) & 0x3FFFu);
-            if (split) {
-              const uint32_t lo16 = static_cast<uint32_t>(raw_bytes) >> 4;   // lo tile = raw tile + raw_bytes
+        const uint32_t sa = tiles_u32 + s * kb_bytes;   // 1024-aligned: (addr >> 4) + k*step never carries out of
+        const uint32_t sb = sa + off_b;                 // the 14-bit start-address field
+        const uint64_t da0 = da_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
+        const uint64_t db0 = db_hi | static_cast<uint64_t>((sb >> 4) & 0x3FFFu);
+        if (split) {
+          // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+          // accumulation steps (measured: 2.4e-6 relative at K = 512, 9e-6 at K = 2000). So the dominant hi*hi sum is
+          // accumulated in TMEM for a chunk of GEMM_DRAIN_KB k-blocks (8 steps) only: "big" buffer b = chunk & 1 is
+          // overwritten at the start of every chunk and drained by the epilogue warps, which keep the running sum in
+          // registers with round-to-nearest fp32 adds (measured: 1.1-1.8e-7 relative for K = 32 .. 2000). The
+          // correction terms (2^-11 smaller, truncation irrelevant) accumulate over the whole K in the "small" buffer
+          // next to it.
+          const uint32_t big = tmem_d + static_cast<uint32_t>((chunk & 1) * 2 * bn), small = big + static_cast<uint32_t>(bn);
+          const uint32_t blo16 = static_cast<uint32_t>(b_bytes) >> 4;
 #pragma unroll
-              for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-                const uint64_t da = da0 + k * a_step16, db = db0 + k * b_step16;
-                umma_tf32(tmem_d, da + lo16, db, idesc, (kb0 | j | k) != 0 ? 1u : 0u);   // lo(A) * hi(B)
-                umma_tf32(tmem_d, da, db + lo16, idesc, 1u);                            // hi(A) * lo(B)
-                umma_tf32(tmem_d, da, db, idesc, 1u);                                   // hi(A) * hi(B)
-              }
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+            const uint64_t da = da0 + k * a_step16, db = db0 + k * b_step16;
+            if (k == 0 && chunk_start && chunk >= 2) {
+              umma_tf32(big, da, db, idesc, 0u);                          // hi(A) * hi(B): restart the big buffer
+              umma_tf32(small, da, db + blo16, idesc, 1u);                // hi(A) * lo(B)
             } else {
-#pragma unroll
-              for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
-                umma_tf32(tmem_d + ((kLab && dbg_mode == 6 && (k & 1)) ? bn : 0), da0 + k * a_step16, db0 + k * b_step16,
-                          idesc, (kb0 | j | k) != 0 ? 1u : 0u);
+              // hi(A) * [hi(B) ; lo(B)] -> big | small in one N = 2 bn instruction (first use of a buffer: overwrite)
+              umma_tf32(big, da, db, idesc2, (k != 0 || !chunk_start) ? 1u : 0u);
             }
+            umma_tf32(small, da + alo16, db, idesc, 1u);                  // lo(A) * hi(B)
           }
-          if (!(kLab && (dbg_mode == 3 || dbg_mode == 5 || dbg_mode == 6))) umma_commit(&ctrl->empty[s]);  // frees the smem slot when these MMAs have read it
+          umma_commit(&ctrl->empty[s]);             // frees the ring slot when these MMAs have read it
+          if (kb % GEMM_DRAIN_KB == GEMM_DRAIN_KB - 1 || kb == num_kb - 1)
+            umma_commit(&ctrl->acc_full[chunk & 1]);   // ... and hands the big buffer to the epilogue warps
+        } else {
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
+            umma_tf32(tmem_d, da0 + k * a_step16, db0 + k * b_step16, idesc, (kb | k) != 0 ? 1u : 0u);
         }
+        if (!split) umma_commit(&ctrl->empty[s]);  // frees the ring slot when these MMAs have read it
       }
       __syncwarp();
       if (++s == nstages) { s = 0; ph ^= 1; }
     }
-    if (elect_one()) {
-      if (kLab && dbg_mode == 1) mbar_arrive(&ctrl->tmem_full);
-      else umma_commit(&ctrl->tmem_full);  // accumulator complete
-      if (kLab && dbg) dbg[3] = clock64();
-    }
+    if (!split && elect_one()) umma_commit(&ctrl->tmem_full);  // accumulator complete
     __syncwarp();
   } else {
     // ------------------------------------------------ epilogue: TMEM -> registers -> smem transpose -> global
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     float* st = epi_stage + q * 32 * GEMM_EPI_PITCH;
+    float run[2][32];   // split: running sum of the drained big buffers (bn <= 64 columns of this thread's row)
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
     if (split) {
-      // ---- splitter: lo = x - trunc_tf32(x), elementwise over the raw k-blocks of every stage (layout-agnostic)
-      const int et = (warp - 2) * 32 + lane;   // 0..127
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < num_st; ++it) {
-        mbar_wait(&ctrl->full[s], ph);
-        const int nk = min(ks, num_kb - it * ks);
-        const float4* src = reinterpret_cast<const float4*>(tiles + s * stage_bytes);
-        float4* dst = reinterpret_cast<float4*>(tiles + s * stage_bytes + raw_bytes);
-        const int n4 = (nk * kblock_bytes) >> 4;
-#pragma unroll 4
-        for (int i = et; i < n4; i += 128) {
-          const float4 x = src[i];
-          float4 l;
-          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          dst[i] = l;
-        }
-        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { run[0][j] = 0.f; run[1][j] = 0.f; }
+      const int num_chunks = (num_kb + GEMM_DRAIN_KB - 1) / GEMM_DRAIN_KB;
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&ctrl->acc_full[c & 1], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t big = lane_base + static_cast<uint32_t>((c & 1) * 2 * bn);
+        float v[32], w[32];
+        tmem_ld_32x32(big, v);
+        if (bn > 32) tmem_ld_32x32(big + 32u, w);
+        tmem_ld_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->ready[s]);
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        if (lane == 0) mbar_arrive(&ctrl->acc_empty[c & 1]);   // values are in registers: the buffer may be overwritten
+#pragma unroll
+        for (int j = 0; j < 32; ++j) run[0][j] += v[j];
+        if (bn > 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[1][j] += w[j];
+        }
       }
+      // the last acc_full commit covers every MMA of the tile: the small buffers are final as well
+    } else {
+      mbar_wait(&ctrl->tmem_full, 0);
+      tc_fence_after();
     }
-    mbar_wait(&ctrl->tmem_full, 0);
-    tc_fence_after();
-    if (dbg && warp == 2 && lane == 0) dbg[4] = clock64();
     const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
     const int rsub = lane >> 3, ch = lane & 7;  // read-back mapping: 4 rows x 8 float4 per pass
     for (int c0 = 0; c0 < bn; c0 += 32) {
       const int nbase = n0 + c0;
       if (nbase >= pN) break;  // warp-uniform
       float v[32];
-      tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), v);
-      tmem_ld_wait();
+      const uint32_t taddr = lane_base + static_cast<uint32_t>(c0);
+      if (split) {
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(bn), v);   // small0: correction terms of the even k-blocks
+        tmem_ld_wait();
+        if (num_kb > GEMM_DRAIN_KB) {   // more than one chunk: buffer 1 was used
+          float w[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(3 * bn), w);   // small1: odd k-blocks
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
+        if (c0 == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += run[0][j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += run[1][j];
+        }
+      } else {
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+      }
       if (epi != EPI_STORE) {
         const float bl = (nbase + lane < pN) ? __ldg(pbias + nbase + lane) : 0.f;  // one coalesced load, then shuffles
 #pragma unroll
@@ -327,7 +359,6 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
       __syncwarp();
     }
   }
-  if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
@@ -375,19 +406,26 @@ inline int pick_bn(int N) {
 }
 
 // Fill one problem entry. A is logically [M,K]: K-major => memory [M][lda]; MN-major => memory [K][lda].
-// Same for B with N. Returns 0 on success.
+// Same for B with N. split: A/B are the hi planes and A_lo/B_lo the lo planes (same shape and pitch).
+// dtype_tf32: single-pass problems on raw fp32 arrays let TMA round to TF32 on load. Returns 0 on success.
 inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
                              float* C, int ldc, int M, int N, int K, int bn, int epi, const float* bias,
-                             float slope, int accumulate, int dtype_tf32 = 1, int split = 0) {
+                             float slope, int accumulate, int dtype_tf32 = 1, const float* A_lo = nullptr,
+                             const float* B_lo = nullptr) {
   *g = GemmProblem{};
-  if (split) dtype_tf32 = 0;   // raw fp32 in shared memory: the tensor core truncates (hi), the splitter adds lo
+  const int split = (A_lo && B_lo) ? 1 : 0;
+  if (split) dtype_tf32 = 0;   // the planes are already TF32-representable
+  auto mk = [&](CUtensorMap* tm, const float* base, int rows, int ld, int mn, int box_rows) {
+    if (!mn) return make_tmap_2d(tm, base, K, rows, ld, GEMM_BK, box_rows, dtype_tf32);
+    return make_tmap_2d(tm, base, rows, K, ld, 32, GEMM_BK, dtype_tf32, 1);
+  };
   int rc;
-  if (!a_mn) rc = make_tmap_2d(&g->tmA, A, K, M, lda, GEMM_BK, GEMM_BM, dtype_tf32);
-  else rc = make_tmap_2d(&g->tmA, A, M, K, lda, 32, GEMM_BK, dtype_tf32, 1);
-  if (rc) return rc;
-  if (!b_mn) rc = make_tmap_2d(&g->tmB, B, K, N, ldb, GEMM_BK, bn, dtype_tf32);
-  else rc = make_tmap_2d(&g->tmB, B, N, K, ldb, 32, GEMM_BK, dtype_tf32, 1);
-  if (rc) return rc;
+  if ((rc = mk(&g->tmA, A, M, lda, a_mn, GEMM_BM))) return rc;
+  if ((rc = mk(&g->tmB, B, N, ldb, b_mn, bn))) return rc;
+  if (split) {
+    if ((rc = mk(&g->tmA_lo, A_lo, M, lda, a_mn, GEMM_BM))) return rc;
+    if ((rc = mk(&g->tmB_lo, B_lo, N, ldb, b_mn, bn))) return rc;
+  }
   g->C = C; g->bias = bias;
   g->M = M; g->N = N; g->K = K; g->ldc = ldc;
   g->bn = bn; g->a_mn = a_mn; g->b_mn = b_mn; g->epi = epi;
@@ -395,10 +433,9 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->tiles_n = (N + bn - 1) / bn;
   g->tile_base = 0;
   g->slope = slope;
-  g->mn_lbo = 4096; g->mn_sbo = 512; g->mn_layout = 1;
   g->accumulate = accumulate;
-  g->ks = 2;
   g->split = split;
+  if (split && bn > 64) return -2;   // the split epilogue keeps bn <= 64 running sums in registers
   return 0;
 }
 
@@ -412,17 +449,27 @@ inline int gemm_table_finalize(GemmProblem* g, int n) {
   return base;
 }
 
-template <bool kLab = false>
-inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_tiles, cudaStream_t st) {
+// use_pdl: launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself), so that its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream.
+inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_tiles, cudaStream_t st, bool use_pdl = false) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel<kLab>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tf32_grouped_kernel<kLab><<<total_tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(dev_table, nprobs);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(total_tiles);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs);
 }
 
 }  // namespace jb

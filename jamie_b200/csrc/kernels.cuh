@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "ptx.cuh"
 
 namespace jb {
 
@@ -55,6 +56,13 @@ __device__ __forceinline__ uint2 philox_key(const Ctl* ctl) {
   return make_uint2(static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32));
 }
 
+// First statement of every kernel of the step: let the next kernel of the stream start launching, then wait until
+// every earlier kernel has completed and flushed (both are no-ops without programmatic stream serialization).
+__device__ __forceinline__ void pdl_prologue() {
+  grid_dep_launch();
+  grid_dep_wait();
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -64,6 +72,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------ k_begin
 // One thread: advance the plan cursor and derive this step's scalars.
 __global__ void k_begin(Ctl* ctl, const float* __restrict__ plan_kl, StepConsts sc) {
+  pdl_prologue();
   const long long row = ctl->cursor++;
   const long long t = ++ctl->adam_t;
   ctl->row = static_cast<int>(row);
@@ -75,7 +84,14 @@ __global__ void k_begin(Ctl* ctl, const float* __restrict__ plan_kl, StepConsts 
   ctl->inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   ctl->stream_id = static_cast<unsigned long long>(t);
 }
-__global__ void k_end(Ctl* ctl) { ctl->inject = 0; }
+__global__ void k_end(Ctl* ctl) {
+  pdl_prologue(); ctl->inject = 0; }
+
+// busy-wait (profiling only): gives the host a head start so a whole step is enqueued behind it
+__global__ void k_spin(long long ns) {
+  const uint64_t t0 = globaltimer_ns();
+  while (globaltimer_ns() - t0 < static_cast<uint64_t>(ns)) {}
+}
 
 // ------------------------------------------------------------------------------------------------ gather
 // x_i[b, :] = data_i[idx_i[row][b], :]   (jamie/jamie.py:583).  grid (B, 2), 128 threads.
@@ -83,24 +99,51 @@ struct GatherArgs {
   const float* data[2];
   long long ld_data[2];
   float* x[2];
+  float* xh[2];       // TF32 hi / lo planes of x (operands of the first encoder GEMM), same pitch as x
+  float* xl[2];
   int ldx[2];
   int D[2];
   const int* idx[2];  // plan index arrays [nsteps][B]
 };
 __global__ void k_gather(GatherArgs a, const Ctl* __restrict__ ctl, int B) {
+  pdl_prologue();
   const int i = blockIdx.y, b = blockIdx.x;
   const int src = a.idx[i][static_cast<long long>(ctl->row) * B + b];
   const float* s = a.data[i] + static_cast<long long>(src) * a.ld_data[i];
-  float* d = a.x[i] + static_cast<long long>(b) * a.ldx[i];
+  const long long o = static_cast<long long>(b) * a.ldx[i];
+  float* d = a.x[i] + o;
+  float* dh = a.xh[i] + o;
+  float* dl = a.xl[i] + o;
   const int D = a.D[i];
+  int j0 = 0;
   if ((a.ld_data[i] & 3) == 0 && (reinterpret_cast<uintptr_t>(a.data[i]) & 15) == 0) {
     const int nv = D >> 2;
-    for (int j = threadIdx.x; j < nv; j += blockDim.x)
-      reinterpret_cast<float4*>(d)[j] = __ldg(reinterpret_cast<const float4*>(s) + j);
-    for (int j = (nv << 2) + threadIdx.x; j < D; j += blockDim.x) d[j] = __ldg(s + j);
-  } else {
-    for (int j = threadIdx.x; j < D; j += blockDim.x) d[j] = __ldg(s + j);
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(s) + j);
+      float4 h, l;
+      tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+      reinterpret_cast<float4*>(d)[j] = v;
+      reinterpret_cast<float4*>(dh)[j] = h;
+      reinterpret_cast<float4*>(dl)[j] = l;
+    }
+    j0 = nv << 2;
   }
+  for (int j = j0 + threadIdx.x; j < D; j += blockDim.x) {
+    const float v = __ldg(s + j);
+    d[j] = v;
+    tf32_split(v, dh[j], dl[j]);
+  }
+}
+// Host-batch step: x arrives by H2D copy; this produces its operand planes. grid (B, 2), 128 threads.
+__global__ void k_split_x(GatherArgs a, int B) {
+  pdl_prologue();
+  const int i = blockIdx.y, b = blockIdx.x;
+  const long long o = static_cast<long long>(b) * a.ldx[i];
+  const float* s = a.x[i] + o;
+  float* dh = a.xh[i] + o;
+  float* dl = a.xl[i] + o;
+  for (int j = threadIdx.x; j < a.D[i]; j += blockDim.x) tf32_split(s[j], dh[j], dl[j]);
+  (void)B;
 }
 
 // ------------------------------------------------------------------------------------------------ P / F blocks
@@ -127,6 +170,7 @@ __device__ __forceinline__ float corr_p_entry(const CorrArgs& a, int i0, int i1)
 }
 // one block per block-row a: row sums (fixed-order tree)
 __global__ void k_corr_rowsum(CorrArgs a, const Ctl* __restrict__ ctl, int B) {
+  pdl_prologue();
   __shared__ float sp[128], sf[128];
   const long long base = static_cast<long long>(ctl->row) * B;
   const int ra = blockIdx.x;
@@ -150,6 +194,7 @@ __global__ void k_corr_rowsum(CorrArgs a, const Ctl* __restrict__ ctl, int B) {
 }
 // 32x32 tiles, block (32, 8): writes corr, corr^T, F block and its transpose with coalesced stores.
 __global__ void k_corr_build(CorrArgs a, const Ctl* __restrict__ ctl, int B) {
+  pdl_prologue();
   __shared__ float tc[32][33], tf[32][33];
   const long long base = static_cast<long long>(ctl->row) * B;
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
@@ -186,7 +231,7 @@ __global__ void k_corr_build(CorrArgs a, const Ctl* __restrict__ ctl, int B) {
 // statistics are block-local; 8 warps stride over rows in groups of 4 (one Philox call = 4 rows of one column).
 struct BnFwd {
   const float* Y; int ldy;
-  float* H; int ldh;
+  float* Hh; float* Hl; int ldh;      // output as TF32 hi / lo planes (the next GEMM's operand; h itself is never needed)
   const float* gamma; const float* beta;
   float* mean; float* invstd;         // saved for backward
   float* run_mean; float* run_var;    // running statistics (momentum 0.1, unbiased variance)
@@ -217,6 +262,7 @@ __device__ __forceinline__ uint4 rand4(uint2 key, unsigned layer_id, int col, in
 }
 
 __global__ void __launch_bounds__(256) k_bn_fwd(BnFwdPair pr, const Ctl* __restrict__ ctl, int B, float p) {
+  pdl_prologue();
   __shared__ float sh[8][2][32];
   const int which = blockIdx.x >= pr.l[0].blocks ? 1 : 0;
   const BnFwd& L = pr.l[which];
@@ -269,7 +315,7 @@ __global__ void __launch_bounds__(256) k_bn_fwd(BnFwdPair pr, const Ctl* __restr
           const bool keep = inject ? (L.mask[static_cast<long long>(r) * L.ldm + c] != 0) : (rr[k] >= thresh);
           o = keep ? o * scale : 0.f;
         }
-        L.H[static_cast<long long>(r) * L.ldh + c] = o;
+        tf32_split(o, L.Hh[static_cast<long long>(r) * L.ldh + c], L.Hl[static_cast<long long>(r) * L.ldh + c]);
       }
     }
   }
@@ -280,7 +326,7 @@ __global__ void __launch_bounds__(256) k_bn_fwd(BnFwdPair pr, const Ctl* __restr
 struct BnBwd {
   const float* dH; int lddh;
   const float* Y; int ldy;
-  float* dY; int lddy;
+  float* dYh; float* dYl; int lddy;   // dY as TF32 hi / lo planes (dgrad reads both, wgrad the hi plane)
   const float* gamma; const float* beta;
   const float* mean; const float* invstd;
   float* dgamma; float* dbeta; float* dbias;
@@ -292,6 +338,7 @@ struct BnBwd {
 struct BnBwdPair { BnBwd l[2]; };
 
 __global__ void __launch_bounds__(256) k_bn_bwd(BnBwdPair pr, const Ctl* __restrict__ ctl, int B, float p, int accum) {
+  pdl_prologue();
   __shared__ float sh[8][2][32];
   const int which = blockIdx.x >= pr.l[0].blocks ? 1 : 0;
   const BnBwd& L = pr.l[which];
@@ -331,7 +378,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd(BnBwdPair pr, const Ctl* __restr
             s2 += da * yh;
           } else {
             const float fb = static_cast<float>(B);
-            L.dY[static_cast<long long>(r) * L.lddy + c] = (inv * g / fb) * (fb * da - s1 - yh * s2);
+            const long long o = static_cast<long long>(r) * L.lddy + c;
+            tf32_split((inv * g / fb) * (fb * da - s1 - yh * s2), L.dYh[o], L.dYl[o]);
           }
         }
       }
@@ -373,6 +421,7 @@ __device__ __forceinline__ void slab_colsum2(float& a, float& b, float (*sh)[2][
 }
 
 __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, const Ctl* __restrict__ ctl, int B, float p) {
+  pdl_prologue();
   __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
   const int nb0 = (pr.l[0].N + SLAB_CW - 1) / SLAB_CW;
   const int which = blockIdx.x >= nb0 ? 1 : 0;
@@ -422,7 +471,8 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, cons
   const bool inject = ctl->inject != 0 && L.mask != nullptr;
   const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
   const uint2 key = philox_key(ctl);
-  float* H = L.H + (cok ? c : 0);
+  float* Hh = L.Hh + (cok ? c : 0);
+  float* Hl = L.Hl + (cok ? c : 0);
   const int ldh = L.ldh;
 #pragma unroll
   for (int t = 0; t < SLAB_G; ++t) {
@@ -440,7 +490,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, cons
           const bool keep = inject ? (L.mask[static_cast<long long>(r) * L.ldm + c] != 0) : (rr[k] >= thresh);
           o = keep ? o * scale : 0.f;
         }
-        H[static_cast<long long>(r) * ldh] = o;
+        tf32_split(o, Hh[static_cast<long long>(r) * ldh], Hl[static_cast<long long>(r) * ldh]);
       }
     }
   }
@@ -448,6 +498,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, cons
 
 __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, const Ctl* __restrict__ ctl, int B, float p,
                                                                int accum) {
+  pdl_prologue();
   __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
   const int nb0 = (pr.l[0].N + SLAB_CW - 1) / SLAB_CW;
   const int which = blockIdx.x >= nb0 ? 1 : 0;
@@ -510,7 +561,10 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, cons
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int r = 4 * (slot + SLAB_SLOTS * t) + k;
-      if (r < B && cok) L.dY[static_cast<long long>(r) * L.lddy + c] = k0 * (fb * da[4 * t + k] - s1 - yh[4 * t + k] * s2);
+      if (r < B && cok) {
+        const long long o = static_cast<long long>(r) * L.lddy + c;
+        tf32_split(k0 * (fb * da[4 * t + k] - s1 - yh[4 * t + k] * s2), L.dYh[o], L.dYl[o]);
+      }
     }
 }
 
@@ -520,7 +574,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, cons
 struct RecArgs {
   const float* xhat; int ldxh;
   const float* x; int ldx;
-  float* dxhat; int lddx;
+  float* dxh; float* dxl; int lddx;   // d loss / d xhat as TF32 hi / lo planes
   float* dbias;
   float* part;   // [blocks] partial sums of squares
   int D;
@@ -528,6 +582,7 @@ struct RecArgs {
 };
 struct RecPair { RecArgs m[2]; };
 __global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int accum) {
+  pdl_prologue();
   __shared__ float sh[8][2][32];
   const int which = blockIdx.x >= pr.m[0].blocks ? 1 : 0;
   const RecArgs& A = pr.m[which];
@@ -544,7 +599,7 @@ __global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int
       sq += d * d;
       const float gx = k * d;
       cs += gx;
-      A.dxhat[static_cast<long long>(r) * A.lddx + c] = gx;
+      tf32_split(gx, A.dxh[static_cast<long long>(r) * A.lddx + c], A.dxl[static_cast<long long>(r) * A.lddx + c]);
     }
   }
   block_colsum2(sq, cs, sh, warp, lane);
@@ -556,6 +611,7 @@ __global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int
 }
 
 __global__ void __launch_bounds__(SLAB_THREADS) k_rec_slab(RecPair pr, int B, float w_rec, int accum) {
+  pdl_prologue();
   __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
   const int nb0 = (pr.m[0].D + SLAB_CW - 1) / SLAB_CW;
   const int which = blockIdx.x >= nb0 ? 1 : 0;
@@ -586,7 +642,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_rec_slab(RecPair pr, int B, fl
       sq += d * d;
       const float gx = kk * d;
       cs += gx;
-      if (r < B && cok) A.dxhat[static_cast<long long>(r) * A.lddx + c] = gx;
+      if (r < B && cok) tf32_split(gx, A.dxh[static_cast<long long>(r) * A.lddx + c], A.dxl[static_cast<long long>(r) * A.lddx + c]);
     }
   slab_colsum2(sq, cs, sh, warp, lane);
   if (warp == 0) {
@@ -604,6 +660,8 @@ struct Latent {
   float* eps[2];                    // [B, LP]
   const float* inj_eps[2];
   float* z[2]; float* c[2]; float* S[2]; float* g[2];   // [B, LP]
+  float* ch[2]; float* cl[2];       // TF32 hi / lo planes of c (first decoder GEMM operand)
+  float* dmh[2]; float* dml[2];     // TF32 hi / lo planes of dmulv (heads dgrad / wgrad operand)
   float* den[2]; float* rs[2];      // [B]
   float* r;                         // [B, LP] F-loss residual c0 - F c1
   const float* dc_dec[2];           // [B, LP] decoder dgrad wrt c
@@ -618,6 +676,7 @@ constexpr int LAT_MAXT = 4;  // latent width up to 128
 
 // eps (injected or Philox Box-Muller) and z = mu + (exp(logvar/2) + 1e-7) eps   (jamie/model.py:230-240)
 __global__ void k_reparam(Latent a, const Ctl* __restrict__ ctl, int B, int L) {
+  pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 2 * B * L) return;
   const int i = t / (B * L), rem = t - i * B * L, b = rem / L, l = rem - b * L;
@@ -675,6 +734,7 @@ __device__ __forceinline__ float row_times(const float* __restrict__ Mrow, const
 // combine (jamie/model.py:245-259): c_i = (s_i z_i + s_j C_i z_j) / (s_i + s_j rowsum(C_i)), C_0 = corr, C_1 = corr^T.
 // One warp per (modality, row).
 __global__ void k_combine(Latent a, int B, int L) {
+  pdl_prologue();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= 2 * B) return;
   const int i = w / B, row = w - i * B, j = 1 - i;
@@ -690,7 +750,9 @@ __global__ void k_combine(Latent a, int B, int L) {
     if (l < L) {
       const long long o = static_cast<long long>(row) * a.LP + l;
       a.S[i][o] = acc[t];
-      a.c[i][o] = (si * a.z[i][o] + sj * acc[t]) / den;
+      const float cv = (si * a.z[i][o] + sj * acc[t]) / den;
+      a.c[i][o] = cv;
+      tf32_split(cv, a.ch[i][o], a.cl[i][o]);
     }
   }
 }
@@ -699,6 +761,7 @@ __global__ void k_combine(Latent a, int B, int L) {
 //   0: sum_l mu^2   1: sum_l (z - c)^2   2: sum_l r^2 (i = 0)   3: sum_l g z   4: sum_l g c   5: sum_l g S
 // F residual r = c0 - F c1 (jamie/jamie.py:663-665).
 __global__ void k_latent_loss(Latent a, int B, int L) {
+  pdl_prologue();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= 2 * B) return;
   const int i = w / B, row = w - i * B;
@@ -734,6 +797,7 @@ __global__ void k_latent_loss(Latent a, int B, int L) {
 
 // g_i = d(loss)/dc_i / den_i with d/dc_i = decoder dgrad - k_cos (z_i - c_i) + F term.
 __global__ void k_latent_bwd_c(Latent a, int B, int L, float k_cos, float k_f) {
+  pdl_prologue();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= 2 * B) return;
   const int i = w / B, row = w - i * B;
@@ -769,6 +833,7 @@ __global__ void k_latent_bwd_c(Latent a, int B, int L, float k_cos, float k_f) {
 // (jamie/jamie.py:619-632 with the reference's logvar quirk: only rows 0 and 1 of modality 1's logvar get KL
 // gradient, each scaled by the broadcast over the batch).
 __global__ void k_latent_bwd_z(Latent a, const Ctl* __restrict__ ctl, int B, int L, float k_cos) {
+  pdl_prologue();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= 2 * B) return;
   const int i = w / B, row = w - i * B, j = 1 - i;
@@ -791,6 +856,8 @@ __global__ void k_latent_bwd_z(Latent a, const Ctl* __restrict__ ctl, int B, int
       if (i == 1 && row < 2) dlv += kkl * -0.5f * (1.f - expf(lv)) / static_cast<float>(L);
       a.dmulv[i][om + l] = dmu;
       a.dmulv[i][om + L + l] = dlv;
+      tf32_split(dmu, a.dmh[i][om + l], a.dml[i][om + l]);
+      tf32_split(dlv, a.dmh[i][om + L + l], a.dml[i][om + L + l]);
     }
   }
 }
@@ -810,6 +877,7 @@ struct FinalArgs {
 };
 __global__ void __launch_bounds__(1024) k_latent_final(FinalArgs a, Latent lat, const Ctl* __restrict__ ctl, int B, int L,
                                                        StepConsts sc, int accum) {
+  pdl_prologue();
   __shared__ float tot[14];   // [i*7 + k]: k = 0..5 the rowpart sums, k = 6: sum_r (g.c)[r] * rowsum_i[r]
   __shared__ float colpart[8][128];
   __shared__ float aux[4];    // [0,1]: sum_l (1 + lv - exp lv) of logvar rows 0/1 (modality 1); [2,3]: sum (xhat - x)^2
@@ -890,6 +958,7 @@ __global__ void __launch_bounds__(1024) k_latent_final(FinalArgs a, Latent lat, 
 // ------------------------------------------------------------------------------------------------ clip + Adam
 // Phase 1: per-block partial of sum g^2 over the padded flat buffer (padding is zero).
 __global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, long long n4, double* __restrict__ part) {
+  pdl_prologue();
   __shared__ double red[256];
   double s = 0.0;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -908,10 +977,12 @@ __global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, l
 }
 // Phase 2: every block re-reduces the partials in the same order (identical clip coefficient everywhere), then
 // g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
-__global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* __restrict__ theta_hi,
+                                              float* __restrict__ theta_lo, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n4, const double* __restrict__ part,
                                               int nparts, const Ctl* __restrict__ ctl, StepConsts sc,
                                               float* __restrict__ out_loss) {
+  pdl_prologue();
   __shared__ double red[256];
   __shared__ float s_coef;
   double s = 0.0;
@@ -951,7 +1022,16 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, const f
       tp[k] = tp[k] - step * (mp[k] / denom);
     }
     m4[i] = mm; v4[i] = vv; t4[i] = tt;
+    float4 th, tl;   // the updated weights as GEMM operand planes for the next step
+    tf32_split(tt.x, th.x, tl.x); tf32_split(tt.y, th.y, tl.y); tf32_split(tt.z, th.z, tl.z); tf32_split(tt.w, th.w, tl.w);
+    reinterpret_cast<float4*>(theta_hi)[i] = th;
+    reinterpret_cast<float4*>(theta_lo)[i] = tl;
   }
+}
+// theta -> (theta_hi, theta_lo) over the whole flat buffer (after jb_set_params)
+__global__ void k_split_flat(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    tf32_split(src[i], hi[i], lo[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ eval-mode folding
@@ -978,9 +1058,9 @@ __global__ void k_copy2d(const float* __restrict__ src, long long lds, float* __
 }
 
 // ------------------------------------------------------------------------------------------------ PCA helpers
-// Error-compensated TF32 split: v = hi + lo with hi = rna_tf32(v) and lo = v - hi (exact in fp32). Three tensor-core
-// passes hi*hi + hi*lo + lo*hi then reproduce the fp32 product to ~2^-21 relative (used for the PCA projection,
-// which the reference computes in float64 before casting to float32).
+// Error-compensated TF32 split (tf32_split) of a [rows, cols] matrix with a fused pre-transform; the split GEMM then
+// reproduces the fp32 product to ~2^-22 relative (used for the PCA projection, which the reference computes in
+// float64 before casting to float32).
 //   mode 0: v = x - colmean[c]      (centre before projecting, jamie/utilities.py:663)
 //   mode 1: v = x * s + m           (un-standardise before the inverse projection, jamie/utilities.py:674-675)
 //   mode 2: v = x
@@ -993,11 +1073,7 @@ __global__ void k_split_tf32(const float* __restrict__ src, long long lds, long 
     float v = src[r * lds + c];
     if (mode == 0) v -= colmean[c];
     else if (mode == 1) v = v * s + m;
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    const float h = __uint_as_float(u);
-    hi[r * ldd + c] = h;
-    lo[r * ldd + c] = v - h;
+    tf32_split(v, hi[r * ldd + c], lo[r * ldd + c]);
   }
 }
 // out = (z - m) / s with NaN -> 0 (jamie/utilities.py:664-669), written with the caller's pitch

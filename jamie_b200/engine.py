@@ -213,6 +213,13 @@ class Engine:
         _lib.check(self.lib.jb_bench_stage(self.h, int(stage), int(iters), C.byref(us), C.byref(fl), C.c_void_p(stream)))
         return float(us.value), float(fl.value)
 
+    def profile_step(self, iters=20, stream=0):
+        """Average in-stream microseconds of every launch of one training step (jb_profile_step)."""
+        out = np.zeros(64, np.float32)
+        n = C.c_int()
+        _lib.check(self.lib.jb_profile_step(self.h, int(iters), _ptr(out), 64, C.byref(n), C.c_void_p(stream)))
+        return out[:n.value].copy()
+
     def set_grad_accumulate(self, flag):
         _lib.check(self.lib.jb_set_grad_accumulate(self.h, int(bool(flag))))
 
