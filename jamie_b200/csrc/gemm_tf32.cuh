@@ -91,7 +91,7 @@ struct GemmCtrl {
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
+gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int cm, int cn) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle (TMA and UMMA descriptors agree on it).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,9 +110,21 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   const GemmProblem& P = probs[p];
   // Everything the pipelines need is read ONCE into registers: the inline-asm barriers below carry "memory"
   // clobbers, so any P.field left inside a loop would be re-fetched from global memory on every iteration.
+  // Clusters of cm x cn CTAs (launch attribute) cover cm row tiles x cn column tiles of one problem: the cn CTAs of a
+  // cluster row share their A tile and the cm CTAs of a cluster column share their B tile, each CTA fetching 1/cn of
+  // A and 1/cm of B from L2 and multicasting it to its mates (every problem of the launch has tiles_m % cm == 0 and
+  // tiles_n % cn == 0, so tile_base is a multiple of the cluster size and blockIdx.x % cs is the cluster rank).
+  const int cs = cm * cn;
   const int t = blockIdx.x - P.tile_base;
   const int tiles_n = P.tiles_n;
-  const int tm = t / tiles_n, tn = t % tiles_n;
+  const int crank = t % cs, cq = t / cs;
+  const int mi = crank / cn, ni = crank - mi * cn;
+  const int qn_count = tiles_n / cn;
+  const int tm = (cq / qn_count) * cm + mi, tn = (cq % qn_count) * cn + ni;
+  const uint16_t mask_a = static_cast<uint16_t>(((1u << cn) - 1u) << (mi * cn));   // my cluster row (shares A)
+  uint16_t mask_b = 0;                                                             // my cluster column (shares B)
+  for (int j = 0; j < cm; ++j) mask_b |= static_cast<uint16_t>(1u << (j * cn + ni));
+  const uint16_t mask_ab = mask_a | mask_b;
   const int m0 = tm * GEMM_BM;
   const int bn = P.bn;
   const int n0 = tn * bn;
@@ -139,7 +151,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
     if (split) { tma_prefetch_desc(&P.tmA_lo); tma_prefetch_desc(&P.tmB_lo); }
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&ctrl->full[s], 1);
-      mbar_init(&ctrl->empty[s], 1);
+      mbar_init(&ctrl->empty[s], static_cast<uint32_t>(cn + cm - 1));   // one release per CTA that reads what I multicast
     }
     mbar_init(&ctrl->tmem_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -154,6 +166,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // every mate's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_d = ctrl->tmem_base;
   // Everything above touched only this kernel's own parameters (the problem table and tensor maps are written by the
@@ -177,22 +190,50 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
         uint8_t* sa = tiles + s * kb_bytes;
         uint8_t* sb = sa + off_b;
         const int k0 = kb * GEMM_BK;
-        if (!a_mn) {
-          tma_load_2d(sa, tmA, bar, k0, m0);  // box {32 k, 128 rows}
-          if (split) tma_load_2d(sa + off_alo, tmAl, bar, k0, m0);
-        } else {
-          for (int i = 0; i < GEMM_BM / 32; ++i) {  // box {32 rows(contiguous), 32 k}
-            tma_load_2d(sa + i * 4096, tmA, bar, m0 + 32 * i, k0);
-            if (split) tma_load_2d(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0);
+        if (cs == 1) {
+          if (!a_mn) {
+            tma_load_2d(sa, tmA, bar, k0, m0);  // box {32 k, 128 rows}
+            if (split) tma_load_2d(sa + off_alo, tmAl, bar, k0, m0);
+          } else {
+            for (int i = 0; i < GEMM_BM / 32; ++i) {  // box {32 rows(contiguous), 32 k}
+              tma_load_2d(sa + i * 4096, tmA, bar, m0 + 32 * i, k0);
+              if (split) tma_load_2d(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0);
+            }
           }
-        }
-        if (!b_mn) {
-          tma_load_2d(sb, tmB, bar, k0, n0);  // box {32 k, bn rows}
-          if (split) tma_load_2d(sb + b_bytes, tmBl, bar, k0, n0);
+          if (!b_mn) {
+            tma_load_2d(sb, tmB, bar, k0, n0);  // box {32 k, bn rows}
+            if (split) tma_load_2d(sb + b_bytes, tmBl, bar, k0, n0);
+          } else {
+            for (int i = 0; i < bn / 32; ++i) {
+              tma_load_2d(sb + i * 4096, tmB, bar, n0 + 32 * i, k0);
+              if (split) tma_load_2d(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0);
+            }
+          }
         } else {
-          for (int i = 0; i < bn / 32; ++i) {
-            tma_load_2d(sb + i * 4096, tmB, bar, n0 + 32 * i, k0);
-            if (split) tma_load_2d(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0);
+          // my 1/cn of the A tile -> the cn CTAs of my cluster row; my 1/cm of the B tile -> the cm CTAs of my column.
+          // (128 B per row of a K-major box / 4 KB per MN-major box: pieces start on 1 KB boundaries, so the 128-byte
+          // swizzle pattern of a piece is the same as inside one whole-tile box.)
+          if (!a_mn) {
+            const int pr = GEMM_BM / cn;   // K-major maps of clustered problems have box {32 k, 128 / cn rows}
+            tma_load_2d_mc(sa + ni * pr * 128, tmA, bar, k0, m0 + ni * pr, mask_a);
+            if (split) tma_load_2d_mc(sa + off_alo + ni * pr * 128, tmAl, bar, k0, m0 + ni * pr, mask_a);
+          } else {
+            const int nb = (GEMM_BM / 32) / cn;
+            for (int i = ni * nb; i < (ni + 1) * nb; ++i) {
+              tma_load_2d_mc(sa + i * 4096, tmA, bar, m0 + 32 * i, k0, mask_a);
+              if (split) tma_load_2d_mc(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0, mask_a);
+            }
+          }
+          if (!b_mn) {
+            const int pr = bn / cm;        // box {32 k, bn / cm rows}
+            tma_load_2d_mc(sb + mi * pr * 128, tmB, bar, k0, n0 + mi * pr, mask_b);
+            if (split) tma_load_2d_mc(sb + b_bytes + mi * pr * 128, tmBl, bar, k0, n0 + mi * pr, mask_b);
+          } else {
+            const int nb = (bn / 32) / cm;
+            for (int i = mi * nb; i < (mi + 1) * nb; ++i) {
+              tma_load_2d_mc(sb + i * 4096, tmB, bar, n0 + 32 * i, k0, mask_b);
+              if (split) tma_load_2d_mc(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0, mask_b);
+            }
           }
         }
       }
@@ -245,7 +286,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
             }
             umma_tf32(small, da + alo16, db, idesc, 1u);                  // lo(A) * hi(B)
           }
-          umma_commit(&ctrl->empty[s]);             // frees the ring slot when these MMAs have read it
+          // frees the ring slot (here and at every mate that multicasts into it) when these MMAs have read it
+          if (cs == 1) umma_commit(&ctrl->empty[s]); else umma_commit_mc(&ctrl->empty[s], mask_ab);
           if (kb % GEMM_DRAIN_KB == GEMM_DRAIN_KB - 1 || kb == num_kb - 1)
             umma_commit(&ctrl->acc_full[chunk & 1]);   // ... and hands the big buffer to the epilogue warps
         } else {
@@ -253,7 +295,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
             umma_tf32(tmem_d, da0 + k * a_step16, db0 + k * b_step16, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (!split) umma_commit(&ctrl->empty[s]);  // frees the ring slot when these MMAs have read it
+        if (!split) { if (cs == 1) umma_commit(&ctrl->empty[s]); else umma_commit_mc(&ctrl->empty[s], mask_ab); }
       }
       __syncwarp();
       if (++s == nstages) { s = 0; ph ^= 1; }
@@ -362,6 +404,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+  // no CTA may exit while a mate can still signal its barriers (the last slot releases are multicast to it)
+  if (cs > 1) cluster_sync_all();
 }
 
 // =========================================================================== host side
@@ -411,7 +455,7 @@ inline int pick_bn(int N) {
 inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
                              float* C, int ldc, int M, int N, int K, int bn, int epi, const float* bias,
                              float slope, int accumulate, int dtype_tf32 = 1, const float* A_lo = nullptr,
-                             const float* B_lo = nullptr) {
+                             const float* B_lo = nullptr, int cm = 1, int cn = 1) {
   *g = GemmProblem{};
   const int split = (A_lo && B_lo) ? 1 : 0;
   if (split) dtype_tf32 = 0;   // the planes are already TF32-representable
@@ -420,11 +464,13 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
     return make_tmap_2d(tm, base, rows, K, ld, 32, GEMM_BK, dtype_tf32, 1);
   };
   int rc;
-  if ((rc = mk(&g->tmA, A, M, lda, a_mn, GEMM_BM))) return rc;
-  if ((rc = mk(&g->tmB, B, N, ldb, b_mn, bn))) return rc;
+  // clustered launches: a CTA fetches 1/cn of the A tile and 1/cm of the B tile (K-major boxes shrink; MN-major tiles
+  // are already made of 32-row boxes)
+  if ((rc = mk(&g->tmA, A, M, lda, a_mn, GEMM_BM / cn))) return rc;
+  if ((rc = mk(&g->tmB, B, N, ldb, b_mn, bn / cm))) return rc;
   if (split) {
-    if ((rc = mk(&g->tmA_lo, A_lo, M, lda, a_mn, GEMM_BM))) return rc;
-    if ((rc = mk(&g->tmB_lo, B_lo, N, ldb, b_mn, bn))) return rc;
+    if ((rc = mk(&g->tmA_lo, A_lo, M, lda, a_mn, GEMM_BM / cn))) return rc;
+    if ((rc = mk(&g->tmB_lo, B_lo, N, ldb, b_mn, bn / cm))) return rc;
   }
   g->C = C; g->bias = bias;
   g->M = M; g->N = N; g->K = K; g->ldc = ldc;
@@ -436,7 +482,22 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->accumulate = accumulate;
   g->split = split;
   if (split && bn > 64) return -2;   // the split epilogue keeps bn <= 64 running sums in registers
+  if (cm * cn > 1) {
+    if (g->tiles_m % cm || g->tiles_n % cn || (GEMM_BM / 32) % cn || (b_mn && (bn / 32) % cm) || bn % (8 * cm)) return -3;
+  }
   return 0;
+}
+
+// Largest cluster shape (cm x cn, at most 2 x 4) that every problem of a stage supports: tiles_m % cm == 0,
+// tiles_n % cn == 0, and an MN-major B tile must split into whole 32-row boxes.
+struct GemmShapeInfo { int tiles_m, tiles_n, bn, b_mn; };
+inline void gemm_pick_cluster(const GemmShapeInfo* p, int n, int* cm, int* cn) {
+  int m = 2, c = 4;
+  for (int i = 0; i < n; ++i) {
+    while (c > 1 && p[i].tiles_n % c) c >>= 1;
+    if (p[i].tiles_m % 2 || (p[i].b_mn && (p[i].bn / 32) % 2)) m = 1;
+  }
+  *cm = m; *cn = c;
 }
 
 // Assign tile ranges; returns the total tile count (= grid size).
@@ -451,7 +512,8 @@ inline int gemm_table_finalize(GemmProblem* g, int n) {
 
 // use_pdl: launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself), so that its
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream.
-inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_tiles, cudaStream_t st, bool use_pdl = false) {
+inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_tiles, cudaStream_t st, bool use_pdl = false,
+                               int cm = 1, int cn = 1) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -464,12 +526,23 @@ inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int tot
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (use_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cm * cn > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = static_cast<unsigned>(cm * cn);
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, cm, cn);
 }
 
 }  // namespace jb
