@@ -78,11 +78,8 @@ struct ModActs {  // activations and gradients of one modality (device pointers,
 };
 
 struct GemmStage {
-  int first = 0, count = 0, tiles = 0;
-  int cm = 1, cn = 1;   // cluster shape of the launch (operand multicast, gemm_tf32.cuh)
-};
-struct ProbSpec {   // one GEMM of a stage, before its tensor maps are encoded
-  Planes A, Bm; int lda, a_mn, ldb, b_mn; float* C; int ldc, M, N, K, bn, epi; const float* bias; int accumulate, split;
+  int first = 0, count = 0, ctas = 0;
+  int ck = 1;   // split-K factor = cluster size of the launch (gemm_tf32.cuh)
 };
 
 }  // namespace
@@ -125,7 +122,6 @@ struct jb_engine {
   // GEMM tables (device) for the training step at batch size graph_B
   jb::GemmProblem* d_probs = nullptr;
   std::vector<jb::GemmProblem> h_probs;
-  std::vector<ProbSpec> pending;   // problems of the stage being built
   GemmStage st_f[6], st_b[6];
   int graph_B = 0;
   bool graph_accum = false;
@@ -137,7 +133,8 @@ struct jb_engine {
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
   bool use_pdl = true;       // programmatic dependent launch between the kernels of the step graph (JB_PDL=0 disables)
-  bool use_cluster = false;  // thread-block clusters with operand multicast in the training GEMMs (JB_CLUSTER=1 enables; measured: no gain)
+  bool use_splitk = true;    // split-K clusters for stages with few tiles (JB_SPLITK=0 disables)
+  int num_sms = 148;
   // eval
   bool eval_dirty = true;
   int eval_chunk = 8192;
@@ -267,46 +264,28 @@ void carve(jb_engine* e, Carver& c) {
 // unbiased) stays local to that gradient tensor, so wgrads are single-pass on the hi planes.
 int add_prob(jb_engine* e, Planes A, int lda, int a_mn, Planes Bm, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
              int bn, int epi, const float* bias, int accumulate, int split) {
+  GemmProblem g;
   if (e->precision_fast) split = 0;
-  e->pending.push_back(ProbSpec{A, Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, accumulate, split});
+  int rc = jb::gemm_problem_fill(&g, A.hi, lda, a_mn, Bm.hi, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, jb::LRELU, accumulate, 0,
+                                 split ? A.lo : nullptr, split ? Bm.lo : nullptr);
+  if (rc) return fail("cuTensorMapEncodeTiled failed (%d) for M%d N%d K%d lda%d ldb%d", rc, M, N, K, lda, ldb);
+  e->h_probs.push_back(g);
   return 0;
 }
 int choose_bn(int N) {
   if (N <= 32) return 32;
   return 64;  // more CTAs beat wider tiles at these problem sizes
 }
-// Encodes the pending problems of one stage with the largest cluster shape all of them support.
-int close_stage(jb_engine* e, GemmStage& st) {
-  const int first = static_cast<int>(e->h_probs.size());
-  std::vector<jb::GemmShapeInfo> info;
-  for (const ProbSpec& q : e->pending)
-    info.push_back({(q.M + jb::GEMM_BM - 1) / jb::GEMM_BM, (q.N + q.bn - 1) / q.bn, q.bn, q.b_mn});
-  int cm = 1, cn = 1;
-  if (e->use_cluster) jb::gemm_pick_cluster(info.data(), static_cast<int>(info.size()), &cm, &cn);
-  for (const ProbSpec& q : e->pending) {
-    GemmProblem g;
-    int rc = jb::gemm_problem_fill(&g, q.A.hi, q.lda, q.a_mn, q.Bm.hi, q.ldb, q.b_mn, q.C, q.ldc, q.M, q.N, q.K, q.bn, q.epi,
-                                   q.bias, jb::LRELU, q.accumulate, 0, q.split ? q.A.lo : nullptr, q.split ? q.Bm.lo : nullptr,
-                                   cm, cn);
-    if (rc) return fail("cuTensorMapEncodeTiled failed (%d) for M%d N%d K%d lda%d ldb%d cluster %dx%d", rc, q.M, q.N, q.K, q.lda, q.ldb, cm, cn);
-    e->h_probs.push_back(g);
-  }
-  e->pending.clear();
+// Closes the stage made of h_probs[first ..]: picks its split-K factor and assigns CTA ranges.
+void close_stage(jb_engine* e, GemmStage& st, int first) {
   st.first = first;
   st.count = static_cast<int>(e->h_probs.size()) - first;
-  st.cm = cm; st.cn = cn;
-  int base = 0;
-  for (int i = first; i < first + st.count; ++i) {
-    e->h_probs[i].tile_base = base;
-    base += e->h_probs[i].tiles_m * e->h_probs[i].tiles_n;
-  }
-  st.tiles = base;
-  return 0;
+  st.ck = e->use_splitk ? jb::gemm_pick_splitk(e->h_probs.data() + first, st.count, e->num_sms) : 1;
+  st.ctas = jb::gemm_table_finalize(e->h_probs.data() + first, st.count, st.ck);
 }
 
 int build_train_tables(jb_engine* e, int B, int accum) {
   e->h_probs.clear();
-  e->pending.clear();
   float* T = e->theta;
   float* G = e->grad;
   const int L = e->L;
@@ -315,8 +294,10 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   auto dW = [&](const Seg& s) { return G + s.off; };
   // ---- forward:  Y[B, N_out] = X W^T + b   (A = X planes K-major, B = W planes K-major)
   auto fwd = [&](GemmStage& st, auto pick) {
+    const int f0 = static_cast<int>(e->h_probs.size());
     for (int i = 0; i < 2; ++i) if (pick(i)) return 1;
-    return close_stage(e, st);
+    close_stage(e, st, f0);
+    return 0;
   };
   auto lin = [&](Planes X, int ldx, const Seg& w, const Seg& b, float* Y, int ldy, int n_out, int n_in) {
     return add_prob(e, X, ldx, 0, W(w), w.ld, 0, Y, ldy, B, n_out, n_in, choose_bn(n_out), jb::EPI_BIAS, bias(b), 0, 1);
@@ -333,43 +314,49 @@ int build_train_tables(jb_engine* e, int B, int accum) {
         return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D); })) return 1;
   if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
         return lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D); })) return 1;
-  // ---- backward: wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass)
-  //                dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out)
+  // ---- backward: dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out): one stage
+  //                per layer on the critical path;
+  //                wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass): nothing
+  //                downstream of a wgrad but the optimizer, so all twelve run as ONE launch at the end of the backward pass.
   auto wgrad = [&](Planes dY, int lddy, Planes X, int ldx, const Seg& s, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, choose_bn(n_in), jb::EPI_STORE, nullptr, accum, 0);
+    const int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : 128);   // single pass: 128-wide tiles halve the CTA count
+    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, bn, jb::EPI_STORE, nullptr, accum, 0);
   };
   auto dgrad = [&](Planes dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
     return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in), jb::EPI_STORE, nullptr, 0, 1);
   };
-  // B6: last decoder Linear(2D -> D)
+  int first = static_cast<int>(e->h_probs.size());   // B6: last decoder Linear(2D -> D)
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, D, 2 * D)) return 1; }
+  close_stage(e, e->st_b[0], first);
+  first = static_cast<int>(e->h_probs.size());       // B5: decoder Linear(D -> 2D)
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 2 * D, D)) return 1; }
+  close_stage(e, e->st_b[1], first);
+  first = static_cast<int>(e->h_probs.size());       // B4: decoder Linear(L -> D)
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dy3, a.ldD, m.W3, a.dc, a.LP, D, L)) return 1; }
+  close_stage(e, e->st_b[2], first);
+  first = static_cast<int>(e->h_probs.size());       // B3: heads Linear(D -> 2L)
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
+  close_stage(e, e->st_b[3], first);
+  first = static_cast<int>(e->h_probs.size());       // B2: encoder Linear(2D -> D); Linear(D -> 2D) needs no input gradient
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
+  close_stage(e, e->st_b[4], first);
+  first = static_cast<int>(e->h_probs.size());       // all weight gradients (largest problems first)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     if (wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D)) return 1;
-    if (dgrad(a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, D, 2 * D)) return 1; }
-  if (close_stage(e, e->st_b[0])) return 1;
-  // B5: decoder Linear(D -> 2D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     if (wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D)) return 1;
-    if (dgrad(a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 2 * D, D)) return 1; }
-  if (close_stage(e, e->st_b[1])) return 1;
-  // B4: decoder Linear(L -> D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dy3, a.ldD, a.cp, a.LP, m.W3, D, L)) return 1;
-    if (dgrad(a.dy3, a.ldD, m.W3, a.dc, a.LP, D, L)) return 1; }
-  if (close_stage(e, e->st_b[2])) return 1;
-  // B3: heads Linear(D -> 2L)
+    if (wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D)) return 1;
+    if (wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D)) return 1; }
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     if (wgrad(a.dmp, a.ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D)) return 1;
-    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
-  if (close_stage(e, e->st_b[3])) return 1;
-  // B2: encoder Linear(2D -> D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D)) return 1;
-    if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
-  if (close_stage(e, e->st_b[4])) return 1;
-  // B1: encoder Linear(D -> 2D): no input gradient
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D)) return 1; }
-  if (close_stage(e, e->st_b[5])) return 1;
+    if (wgrad(a.dy3, a.ldD, a.cp, a.LP, m.W3, D, L)) return 1; }
+  close_stage(e, e->st_b[5], first);
+  e->st_b[5].ck = 1;   // several waves of CTAs: no split-K
+  e->st_b[5].ctas = jb::gemm_table_finalize(e->h_probs.data() + first, e->st_b[5].count, 1);
   if (e->d_probs) cudaFree(e->d_probs);
   CU(cudaMalloc(&e->d_probs, e->h_probs.size() * sizeof(GemmProblem)));
   CU(cudaMemcpy(e->d_probs, e->h_probs.data(), e->h_probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice));
@@ -385,7 +372,7 @@ struct Rec {  // launches kernels on a stream and counts them
     if (ev && n < 63) { names[n] = name; cudaEventRecord(ev[n + 1], s); }
   }
   void gemm(const GemmStage& st) {
-    if (err == cudaSuccess) err = jb::gemm_launch(e->d_probs + st.first, st.count, st.tiles, s, e->use_pdl, st.cm, st.cn);
+    if (err == cudaSuccess) err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl, st.ck);
     mark("gemm");
     ++n;
   }
@@ -763,7 +750,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_CLUSTER")) e->use_cluster = atoi(pv) != 0;
+  if (const char* pv = getenv("JB_SPLITK")) e->use_splitk = atoi(pv) != 0;
+  e->num_sms = prop.multiProcessorCount;
   // eval workspaces: two slots of chunk activations
   {
     const int Dm = e->D[0] > e->D[1] ? e->D[0] : e->D[1];
@@ -1098,9 +1086,9 @@ int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* fl
     fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.tiles, s, false, st.cm, st.cn));
+  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck));
   CU(cudaEventRecord(a, s));
-  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.tiles, s, false, st.cm, st.cn));
+  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck));
   CU(cudaEventRecord(b, s));
   CU(cudaEventSynchronize(b));
   float ms = 0;

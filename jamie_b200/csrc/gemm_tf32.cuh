@@ -34,6 +34,12 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> padded smem transpose -> coalesced 128-bit global stores).
+//
+// Split-K (ck = 2 or 4, a launch attribute): measured on B200, a CTA ingests its operand k-blocks at ~100 GB/s whatever
+// the grid size (profiles/gemm_r1_s2_multicast_lab.md), so a stage is as slow as its busiest CTA. Stages with few tiles
+// (K = 1024 layers: 64 tiles; heads and latent dgrads: 8 tiles) therefore launch a cluster of ck CTAs per tile, each
+// accumulating 1/ck of K, and reduce-scatter the partial tiles through distributed shared memory: the rows of epilogue
+// warp q are finished by rank q * ck / 4, which adds the deposits in ascending rank order (deterministic).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -91,7 +97,7 @@ struct GemmCtrl {
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int cm, int cn) {
+gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle (TMA and UMMA descriptors agree on it).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,21 +116,14 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   const GemmProblem& P = probs[p];
   // Everything the pipelines need is read ONCE into registers: the inline-asm barriers below carry "memory"
   // clobbers, so any P.field left inside a loop would be re-fetched from global memory on every iteration.
-  // Clusters of cm x cn CTAs (launch attribute) cover cm row tiles x cn column tiles of one problem: the cn CTAs of a
-  // cluster row share their A tile and the cm CTAs of a cluster column share their B tile, each CTA fetching 1/cn of
-  // A and 1/cm of B from L2 and multicasting it to its mates (every problem of the launch has tiles_m % cm == 0 and
-  // tiles_n % cn == 0, so tile_base is a multiple of the cluster size and blockIdx.x % cs is the cluster rank).
-  const int cs = cm * cn;
-  const int t = blockIdx.x - P.tile_base;
+  // Split-K: a cluster of ck CTAs (launch attribute) owns one output tile; rank r accumulates its share of the
+  // k-blocks and the partial tiles are reduced through distributed shared memory (see the epilogue). tile_base counts
+  // CTAs, a multiple of ck for every problem, so blockIdx.x % ck is the cluster rank.
+  const int cta = blockIdx.x - P.tile_base;
+  const int crank = cta % ck;
+  const int t = cta / ck;
   const int tiles_n = P.tiles_n;
-  const int crank = t % cs, cq = t / cs;
-  const int mi = crank / cn, ni = crank - mi * cn;
-  const int qn_count = tiles_n / cn;
-  const int tm = (cq / qn_count) * cm + mi, tn = (cq % qn_count) * cn + ni;
-  const uint16_t mask_a = static_cast<uint16_t>(((1u << cn) - 1u) << (mi * cn));   // my cluster row (shares A)
-  uint16_t mask_b = 0;                                                             // my cluster column (shares B)
-  for (int j = 0; j < cm; ++j) mask_b |= static_cast<uint16_t>(1u << (j * cn + ni));
-  const uint16_t mask_ab = mask_a | mask_b;
+  const int tm = t / tiles_n, tn = t % tiles_n;
   const int m0 = tm * GEMM_BM;
   const int bn = P.bn;
   const int n0 = tn * bn;
@@ -134,7 +133,9 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   const float* const pbias = P.bias;
   const float slope = P.slope;
   const int split = P.split;
-  const int num_kb = (P.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_total = (P.K + GEMM_BK - 1) / GEMM_BK;   // the host guarantees kb_total >= ck
+  const int kb_begin = crank * (kb_total / ck) + (crank < kb_total % ck ? crank : kb_total % ck);
+  const int num_kb = kb_total / ck + (crank < kb_total % ck ? 1 : 0);
   const int b_bytes = bn * GEMM_BK * 4;
   const int kb_bytes = (GEMM_A_STAGE_BYTES + b_bytes) * (split ? 2 : 1);   // one ring slot = one k-block
   int nstages = GEMM_TILE_SMEM / kb_bytes;
@@ -151,7 +152,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     if (split) { tma_prefetch_desc(&P.tmA_lo); tma_prefetch_desc(&P.tmB_lo); }
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&ctrl->full[s], 1);
-      mbar_init(&ctrl->empty[s], static_cast<uint32_t>(cn + cm - 1));   // one release per CTA that reads what I multicast
+      mbar_init(&ctrl->empty[s], 1);
     }
     mbar_init(&ctrl->tmem_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -166,13 +167,15 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   }
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();   // every mate's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_d = ctrl->tmem_base;
   // Everything above touched only this kernel's own parameters (the problem table and tensor maps are written by the
   // host, never by a kernel of the step): with programmatic dependent launch it overlaps the previous kernel's tail.
   grid_dep_wait();
   grid_dep_launch();
+
+  // running sum of the drained big buffers (split): bn <= 64 columns of this thread's row; epilogue warps only
+  float run[2][32];
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (whole warp loops, one elected lane issues)
@@ -189,51 +192,23 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
         mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kb_bytes));
         uint8_t* sa = tiles + s * kb_bytes;
         uint8_t* sb = sa + off_b;
-        const int k0 = kb * GEMM_BK;
-        if (cs == 1) {
-          if (!a_mn) {
-            tma_load_2d(sa, tmA, bar, k0, m0);  // box {32 k, 128 rows}
-            if (split) tma_load_2d(sa + off_alo, tmAl, bar, k0, m0);
-          } else {
-            for (int i = 0; i < GEMM_BM / 32; ++i) {  // box {32 rows(contiguous), 32 k}
-              tma_load_2d(sa + i * 4096, tmA, bar, m0 + 32 * i, k0);
-              if (split) tma_load_2d(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0);
-            }
-          }
-          if (!b_mn) {
-            tma_load_2d(sb, tmB, bar, k0, n0);  // box {32 k, bn rows}
-            if (split) tma_load_2d(sb + b_bytes, tmBl, bar, k0, n0);
-          } else {
-            for (int i = 0; i < bn / 32; ++i) {
-              tma_load_2d(sb + i * 4096, tmB, bar, n0 + 32 * i, k0);
-              if (split) tma_load_2d(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0);
-            }
-          }
+        const int k0 = (kb_begin + kb) * GEMM_BK;
+        if (!a_mn) {
+          tma_load_2d(sa, tmA, bar, k0, m0);  // box {32 k, 128 rows}
+          if (split) tma_load_2d(sa + off_alo, tmAl, bar, k0, m0);
         } else {
-          // my 1/cn of the A tile -> the cn CTAs of my cluster row; my 1/cm of the B tile -> the cm CTAs of my column.
-          // (128 B per row of a K-major box / 4 KB per MN-major box: pieces start on 1 KB boundaries, so the 128-byte
-          // swizzle pattern of a piece is the same as inside one whole-tile box.)
-          if (!a_mn) {
-            const int pr = GEMM_BM / cn;   // K-major maps of clustered problems have box {32 k, 128 / cn rows}
-            tma_load_2d_mc(sa + ni * pr * 128, tmA, bar, k0, m0 + ni * pr, mask_a);
-            if (split) tma_load_2d_mc(sa + off_alo + ni * pr * 128, tmAl, bar, k0, m0 + ni * pr, mask_a);
-          } else {
-            const int nb = (GEMM_BM / 32) / cn;
-            for (int i = ni * nb; i < (ni + 1) * nb; ++i) {
-              tma_load_2d_mc(sa + i * 4096, tmA, bar, m0 + 32 * i, k0, mask_a);
-              if (split) tma_load_2d_mc(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0, mask_a);
-            }
+          for (int i = 0; i < GEMM_BM / 32; ++i) {  // box {32 rows(contiguous), 32 k}
+            tma_load_2d(sa + i * 4096, tmA, bar, m0 + 32 * i, k0);
+            if (split) tma_load_2d(sa + off_alo + i * 4096, tmAl, bar, m0 + 32 * i, k0);
           }
-          if (!b_mn) {
-            const int pr = bn / cm;        // box {32 k, bn / cm rows}
-            tma_load_2d_mc(sb + mi * pr * 128, tmB, bar, k0, n0 + mi * pr, mask_b);
-            if (split) tma_load_2d_mc(sb + b_bytes + mi * pr * 128, tmBl, bar, k0, n0 + mi * pr, mask_b);
-          } else {
-            const int nb = (bn / 32) / cm;
-            for (int i = mi * nb; i < (mi + 1) * nb; ++i) {
-              tma_load_2d_mc(sb + i * 4096, tmB, bar, n0 + 32 * i, k0, mask_b);
-              if (split) tma_load_2d_mc(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0, mask_b);
-            }
+        }
+        if (!b_mn) {
+          tma_load_2d(sb, tmB, bar, k0, n0);  // box {32 k, bn rows}
+          if (split) tma_load_2d(sb + b_bytes, tmBl, bar, k0, n0);
+        } else {
+          for (int i = 0; i < bn / 32; ++i) {
+            tma_load_2d(sb + i * 4096, tmB, bar, n0 + 32 * i, k0);
+            if (split) tma_load_2d(sb + b_bytes + i * 4096, tmBl, bar, n0 + 32 * i, k0);
           }
         }
       }
@@ -286,8 +261,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
             }
             umma_tf32(small, da + alo16, db, idesc, 1u);                  // lo(A) * hi(B)
           }
-          // frees the ring slot (here and at every mate that multicasts into it) when these MMAs have read it
-          if (cs == 1) umma_commit(&ctrl->empty[s]); else umma_commit_mc(&ctrl->empty[s], mask_ab);
+          umma_commit(&ctrl->empty[s]);             // frees the ring slot when these MMAs have read it
           if (kb % GEMM_DRAIN_KB == GEMM_DRAIN_KB - 1 || kb == num_kb - 1)
             umma_commit(&ctrl->acc_full[chunk & 1]);   // ... and hands the big buffer to the epilogue warps
         } else {
@@ -295,7 +269,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
             umma_tf32(tmem_d, da0 + k * a_step16, db0 + k * b_step16, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (!split) { if (cs == 1) umma_commit(&ctrl->empty[s]); else umma_commit_mc(&ctrl->empty[s], mask_ab); }
+        if (!split) umma_commit(&ctrl->empty[s]);  // frees the ring slot when these MMAs have read it
       }
       __syncwarp();
       if (++s == nstages) { s = 0; ph ^= 1; }
@@ -303,10 +277,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     if (!split && elect_one()) umma_commit(&ctrl->tmem_full);  // accumulator complete
     __syncwarp();
   } else {
-    // ------------------------------------------------ epilogue: TMEM -> registers -> smem transpose -> global
+    // ------------------------------------------------ epilogue warps, phase 1: wait for (and, split, drain) the MMAs
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    float* st = epi_stage + q * 32 * GEMM_EPI_PITCH;
-    float run[2][32];   // split: running sum of the drained big buffers (bn <= 64 columns of this thread's row)
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
     if (split) {
 #pragma unroll
@@ -335,19 +307,26 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
       mbar_wait(&ctrl->tmem_full, 0);
       tc_fence_after();
     }
-    const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
-    const int rsub = lane >> 3, ch = lane & 7;  // read-back mapping: 4 rows x 8 float4 per pass
-    for (int c0 = 0; c0 < bn; c0 += 32) {
-      const int nbase = n0 + c0;
-      if (nbase >= pN) break;  // warp-uniform
-      float v[32];
+  }
+
+  // Split-K, barrier A: every CTA of the cluster has finished reading its operand ring (the epilogue warps arrive after
+  // the last MMA has completed), so a mate may now deposit its partial tile into it.
+  if (ck > 1) cluster_sync_all();
+
+  if (warp >= 2) {
+    // ------------------------------------------------ epilogue warps, phase 2: TMEM -> registers -> (reduce) -> global
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
+    float* st = epi_stage + q * 32 * GEMM_EPI_PITCH;
+    // this thread's row of the CTA's partial tile, columns [c0, c0 + 32)
+    auto load_chunk = [&](int c0, float (&v)[32]) {
       const uint32_t taddr = lane_base + static_cast<uint32_t>(c0);
       if (split) {
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(bn), v);   // small0: correction terms of the even k-blocks
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(bn), v);   // small0: correction terms of the even chunks
         tmem_ld_wait();
         if (num_kb > GEMM_DRAIN_KB) {   // more than one chunk: buffer 1 was used
           float w[32];
-          tmem_ld_32x32(taddr + static_cast<uint32_t>(3 * bn), w);   // small1: odd k-blocks
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(3 * bn), w);   // small1: odd chunks
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += w[j];
@@ -363,49 +342,89 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
       }
-      if (epi != EPI_STORE) {
-        const float bl = (nbase + lane < pN) ? __ldg(pbias + nbase + lane) : 0.f;  // one coalesced load, then shuffles
+    };
+    // Split-K reduce-scatter: the 32-row slab of epilogue warp q is finished by cluster rank owner = q * ck / 4; the
+    // other ranks deposit their partial slab in the owner's (now idle) operand ring: slot (sender rank, skipping the
+    // owner), rows padded to bn + 4 floats (conflict-free 128-bit accesses on both sides).
+    const int owner = (q * ck) >> 2;
+    const int pitch = bn + 4;
+    const int slab_floats = 32 * pitch;
+    const int ql = q - ((owner * 4) / ck);                 // slab index among the slabs this owner finishes
+    const int slabs_per_owner = 4 / ck;
+    if (ck > 1 && owner != crank) {
+      const int slot = crank < owner ? crank : crank - 1;
+      float* dst_local = reinterpret_cast<float*>(tiles) + (slot * slabs_per_owner + ql) * slab_floats + lane * pitch;
+      const uint32_t dst = mapa_shared(smem_u32(dst_local), static_cast<uint32_t>(owner));
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        if (n0 + c0 >= pN) break;  // warp-uniform
+        float v[32];
+        load_chunk(c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
-          if (epi == EPI_BIAS_LRELU) x = leaky(x, slope);
-          v[j] = x;
-        }
+        for (int j = 0; j < 8; ++j)
+          st_shared_cluster_f4(dst + static_cast<uint32_t>((c0 + 4 * j) * 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
+    }
+    if (ck > 1) cluster_sync_all();   // barrier B: the deposits are visible to their owners
+    if (ck == 1 || owner == crank) {
+      const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
+      const int rsub = lane >> 3, ch = lane & 7;  // read-back mapping: 4 rows x 8 float4 per pass
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        const int nbase = n0 + c0;
+        if (nbase >= pN) break;  // warp-uniform
+        float v[32];
+        load_chunk(c0, v);
+        for (int sl = 0; sl < ck - 1; ++sl) {   // fixed order: ascending sender rank
+          const float* src = reinterpret_cast<const float*>(tiles) + (sl * slabs_per_owner + ql) * slab_floats + lane * pitch + c0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * j) =
-            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + rsub;
-        const int grow = m0 + q * 32 + r;
-        const int n = nbase + ch * 4;
-        float4 x = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
-        if (grow < pM && n < pN) {
-          float* dst = pC + static_cast<size_t>(grow) * ldc + n;
-          if (vec_ok && n + 4 <= pN) {
-            if (accumulate) {
-              const float4 o = *reinterpret_cast<const float4*>(dst);
-              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
-            }
-            *reinterpret_cast<float4*>(dst) = x;
-          } else {
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            for (int j = 0; j < 4; ++j)
-              if (n + j < pN) dst[j] = accumulate ? dst[j] + xs[j] : xs[j];
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(src + 4 * j);
+            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
           }
         }
+        if (epi != EPI_STORE) {
+          const float bl = (nbase + lane < pN) ? __ldg(pbias + nbase + lane) : 0.f;  // one coalesced load, then shuffles
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
+            if (epi == EPI_BIAS_LRELU) x = leaky(x, slope);
+            v[j] = x;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * j) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;
+          const int grow = m0 + q * 32 + r;
+          const int n = nbase + ch * 4;
+          float4 x = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
+          if (grow < pM && n < pN) {
+            float* dst = pC + static_cast<size_t>(grow) * ldc + n;
+            if (vec_ok && n + 4 <= pN) {
+              if (accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+              }
+              *reinterpret_cast<float4*>(dst) = x;
+            } else {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+              for (int j = 0; j < 4; ++j)
+                if (n + j < pN) dst[j] = accumulate ? dst[j] + xs[j] : xs[j];
+            }
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
+  } else if (ck > 1) {
+    cluster_sync_all();   // barrier B (producer and MMA warps only take part in the cluster barriers)
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
-  // no CTA may exit while a mate can still signal its barriers (the last slot releases are multicast to it)
-  if (cs > 1) cluster_sync_all();
 }
 
 // =========================================================================== host side
@@ -455,7 +474,7 @@ inline int pick_bn(int N) {
 inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
                              float* C, int ldc, int M, int N, int K, int bn, int epi, const float* bias,
                              float slope, int accumulate, int dtype_tf32 = 1, const float* A_lo = nullptr,
-                             const float* B_lo = nullptr, int cm = 1, int cn = 1) {
+                             const float* B_lo = nullptr) {
   *g = GemmProblem{};
   const int split = (A_lo && B_lo) ? 1 : 0;
   if (split) dtype_tf32 = 0;   // the planes are already TF32-representable
@@ -464,13 +483,11 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
     return make_tmap_2d(tm, base, rows, K, ld, 32, GEMM_BK, dtype_tf32, 1);
   };
   int rc;
-  // clustered launches: a CTA fetches 1/cn of the A tile and 1/cm of the B tile (K-major boxes shrink; MN-major tiles
-  // are already made of 32-row boxes)
-  if ((rc = mk(&g->tmA, A, M, lda, a_mn, GEMM_BM / cn))) return rc;
-  if ((rc = mk(&g->tmB, B, N, ldb, b_mn, bn / cm))) return rc;
+  if ((rc = mk(&g->tmA, A, M, lda, a_mn, GEMM_BM))) return rc;
+  if ((rc = mk(&g->tmB, B, N, ldb, b_mn, bn))) return rc;
   if (split) {
-    if ((rc = mk(&g->tmA_lo, A_lo, M, lda, a_mn, GEMM_BM / cn))) return rc;
-    if ((rc = mk(&g->tmB_lo, B_lo, N, ldb, b_mn, bn / cm))) return rc;
+    if ((rc = mk(&g->tmA_lo, A_lo, M, lda, a_mn, GEMM_BM))) return rc;
+    if ((rc = mk(&g->tmB_lo, B_lo, N, ldb, b_mn, bn))) return rc;
   }
   g->C = C; g->bias = bias;
   g->M = M; g->N = N; g->K = K; g->ldc = ldc;
@@ -482,38 +499,38 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->accumulate = accumulate;
   g->split = split;
   if (split && bn > 64) return -2;   // the split epilogue keeps bn <= 64 running sums in registers
-  if (cm * cn > 1) {
-    if (g->tiles_m % cm || g->tiles_n % cn || (GEMM_BM / 32) % cn || (b_mn && (bn / 32) % cm) || bn % (8 * cm)) return -3;
-  }
   return 0;
 }
 
-// Largest cluster shape (cm x cn, at most 2 x 4) that every problem of a stage supports: tiles_m % cm == 0,
-// tiles_n % cn == 0, and an MN-major B tile must split into whole 32-row boxes.
-struct GemmShapeInfo { int tiles_m, tiles_n, bn, b_mn; };
-inline void gemm_pick_cluster(const GemmShapeInfo* p, int n, int* cm, int* cn) {
-  int m = 2, c = 4;
+// Split-K factor of a stage: the largest ck in {4, 2, 1} that keeps the launch within one wave of `sms` CTAs and leaves
+// every cluster rank at least `min_kb_per_rank` k-blocks.
+inline int gemm_pick_splitk(const GemmProblem* g, int n, int sms = 148, int min_kb_per_rank = 4) {
+  int tiles = 0, min_kb = 1 << 30;
   for (int i = 0; i < n; ++i) {
-    while (c > 1 && p[i].tiles_n % c) c >>= 1;
-    if (p[i].tiles_m % 2 || (p[i].b_mn && (p[i].bn / 32) % 2)) m = 1;
+    tiles += g[i].tiles_m * g[i].tiles_n;
+    const int kb = (g[i].K + GEMM_BK - 1) / GEMM_BK;
+    if (kb < min_kb) min_kb = kb;
   }
-  *cm = m; *cn = c;
+  for (int ck = 4; ck > 1; ck >>= 1)
+    if (tiles * ck <= sms && min_kb >= min_kb_per_rank * ck) return ck;
+  return 1;
 }
 
-// Assign tile ranges; returns the total tile count (= grid size).
-inline int gemm_table_finalize(GemmProblem* g, int n) {
+// Assign CTA ranges (ck CTAs per tile); returns the grid size.
+inline int gemm_table_finalize(GemmProblem* g, int n, int ck = 1) {
   int base = 0;
   for (int i = 0; i < n; ++i) {
     g[i].tile_base = base;
-    base += g[i].tiles_m * g[i].tiles_n;
+    base += g[i].tiles_m * g[i].tiles_n * ck;
   }
   return base;
 }
 
 // use_pdl: launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself), so that its
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream.
-inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_tiles, cudaStream_t st, bool use_pdl = false,
-                               int cm = 1, int cn = 1) {
+// total_ctas = gemm_table_finalize(..., ck). ck > 1 launches clusters of ck CTAs (split-K, see the kernel).
+inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_ctas, cudaStream_t st, bool use_pdl = false,
+                               int ck = 1) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -522,7 +539,7 @@ inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int tot
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(total_tiles);
+  cfg.gridDim = dim3(total_ctas);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
   cfg.stream = st;
@@ -533,16 +550,16 @@ inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int tot
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (cm * cn > 1) {
+  if (ck > 1) {
     at[na].id = cudaLaunchAttributeClusterDimension;
-    at[na].val.clusterDim.x = static_cast<unsigned>(cm * cn);
+    at[na].val.clusterDim.x = static_cast<unsigned>(ck);
     at[na].val.clusterDim.y = 1;
     at[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, cm, cn);
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck);
 }
 
 }  // namespace jb

@@ -36,7 +36,7 @@ static float frand() {  // uniform (-1, 1)
 
 struct Case {
   int M, N, K, a_mn, b_mn, bn, split, epi, accumulate;
-  int cm = 1, cn = 1;   // cluster shape (operand multicast)
+  int ck = 1;           // split-K cluster size
 };
 
 static int run_case(const Case& c) {
@@ -66,13 +66,13 @@ static int run_case(const Case& c) {
   CK(cudaMemcpy(dbias, bias.data(), N * 4, cudaMemcpyHostToDevice));
   jb::GemmProblem g;
   int rc = jb::gemm_problem_fill(&g, dA, lda, c.a_mn, dB, ldb, c.b_mn, dC, ldc, M, N, K, c.bn, c.epi, dbias, 0.01f, c.accumulate,
-                                 1, c.split ? dAl : nullptr, c.split ? dBl : nullptr, c.cm, c.cn);
+                                 1, c.split ? dAl : nullptr, c.split ? dBl : nullptr);
   if (rc) { printf("tensor map encode failed %d\n", rc); return 1; }
-  const int tiles = jb::gemm_table_finalize(&g, 1);
+  const int tiles = jb::gemm_table_finalize(&g, 1, c.ck);
   jb::GemmProblem* dg;
   CK(cudaMalloc(&dg, sizeof g));
   CK(cudaMemcpy(dg, &g, sizeof g, cudaMemcpyHostToDevice));
-  CK(jb::gemm_launch(dg, 1, tiles, 0, false, c.cm, c.cn));
+  CK(jb::gemm_launch(dg, 1, tiles, 0, false, c.ck));
   CK(cudaDeviceSynchronize());
   std::vector<float> C(C0.size());
   CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
@@ -89,14 +89,14 @@ static int run_case(const Case& c) {
     }
   const double rel = sqrt(err2 / (ref2 + 1e-30));
   const double tol = c.split ? 5e-7 : 6e-4;
-  printf("%s M%-4d N%-4d K%-4d a_mn%d b_mn%d bn%-3d split%d epi%d acc%d cl%dx%d : rel %.3e max %.3e %s\n", rel < tol ? "ok  " : "FAIL",
-         M, N, K, c.a_mn, c.b_mn, c.bn, c.split, c.epi, c.accumulate, c.cm, c.cn, rel, emax, rel < tol ? "" : "<<<<<<");
+  printf("%s M%-4d N%-4d K%-4d a_mn%d b_mn%d bn%-3d split%d epi%d acc%d ck%d : rel %.3e max %.3e %s\n", rel < tol ? "ok  " : "FAIL",
+         M, N, K, c.a_mn, c.b_mn, c.bn, c.split, c.epi, c.accumulate, c.ck, rel, emax, rel < tol ? "" : "<<<<<<");
   cudaFree(dA); cudaFree(dAl); cudaFree(dB); cudaFree(dBl); cudaFree(dC); cudaFree(dbias); cudaFree(dg);
   return rel < tol ? 0 : 2;
 }
 
 // nprob identical problems in one launch (the two modalities of a stage), L2-warm, back-to-back
-static int time_case(int nprob, int M, int N, int K, int a_mn, int b_mn, int bn, int split, bool pdl, int cm = 1, int cn = 1) {
+static int time_case(int nprob, int M, int N, int K, int a_mn, int b_mn, int bn, int split, bool pdl, int ck = 1) {
   const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
   std::vector<jb::GemmProblem> g(nprob);
   std::vector<float*> bufs;
@@ -109,27 +109,27 @@ static int time_case(int nprob, int M, int N, int K, int a_mn, int b_mn, int bn,
     CK(cudaMemset(dB, 0, static_cast<size_t>(N) * K * 4)); CK(cudaMemset(dBl, 0, static_cast<size_t>(N) * K * 4));
     bufs.insert(bufs.end(), {dA, dAl, dB, dBl, dC});
     if (jb::gemm_problem_fill(&g[i], dA, lda, a_mn, dB, ldb, b_mn, dC, N, M, N, K, bn, jb::EPI_STORE, nullptr, 0.f, 0, 1,
-                              split ? dAl : nullptr, split ? dBl : nullptr, cm, cn)) { printf("encode failed\n"); return 1; }
+                              split ? dAl : nullptr, split ? dBl : nullptr)) { printf("encode failed\n"); return 1; }
   }
-  const int tiles = jb::gemm_table_finalize(g.data(), nprob);
+  const int tiles = jb::gemm_table_finalize(g.data(), nprob, ck);
   jb::GemmProblem* dg;
   CK(cudaMalloc(&dg, nprob * sizeof(jb::GemmProblem)));
   CK(cudaMemcpy(dg, g.data(), nprob * sizeof(jb::GemmProblem), cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 5; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, cm, cn));
+  for (int i = 0; i < 5; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, ck));
   const int iters = 200;
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, cm, cn));
+  for (int i = 0; i < iters; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, ck));
   CK(cudaEventRecord(e1));
   CK(cudaEventSynchronize(e1));
   float ms;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   const double us = ms * 1e3 / iters;
   const double tf = 2.0 * nprob * M * N * K / (us * 1e-6) / 1e12;
-  const double mb = static_cast<double>(tiles) * ((K + 31) / 32) * (128.0 / cn + static_cast<double>(bn) / cm) * 128 * (split ? 2 : 1) / 1e6;
-  printf("time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%-3d split%d pdl%d cl%dx%d tiles %-3d : %6.2f us/launch  %6.1f TFLOP/s (algorithmic)  L2->SM %.1f MB = %.2f TB/s\n",
-         nprob, M, N, K, a_mn, b_mn, bn, split, pdl ? 1 : 0, cm, cn, tiles, us, tf, mb, mb / us);
+  const double mb = static_cast<double>(tiles / ck) * ((K + 31) / 32) * (128 + bn) * 128 * (split ? 2 : 1) / 1e6;
+  printf("time: %d x [M%d N%d K%d] a_mn%d b_mn%d bn%-3d split%d pdl%d ck%d ctas %-3d : %6.2f us/launch  %6.1f TFLOP/s (algorithmic)  L2->SM %.1f MB = %.2f TB/s\n",
+         nprob, M, N, K, a_mn, b_mn, bn, split, pdl ? 1 : 0, ck, tiles, us, tf, mb, mb / us);
   for (float* p : bufs) cudaFree(p);
   cudaFree(dg);
   return 0;
@@ -152,14 +152,13 @@ int main(int argc, char** argv) {
         {300, 1000, 2000, 0, 0, 64, 1, jb::EPI_BIAS, 0}, {300, 78, 39, 0, 1, 64, 1, jb::EPI_STORE, 0},
         {700, 64, 1302, 0, 0, 64, 1, jb::EPI_STORE, 0}, {700, 1302, 64, 0, 1, 64, 1, jb::EPI_BIAS, 0},
         {130, 39, 300, 1, 1, 64, 1, jb::EPI_STORE, 1},  {100, 130, 70, 1, 0, 64, 1, jb::EPI_STORE, 0},
-        // clusters with operand multicast: 1x2, 1x4, 2x1, 2x2, 2x4, every major combination, ragged edges
-        {512, 1024, 512, 0, 0, 64, 1, jb::EPI_BIAS, 0, 1, 4},  {512, 1024, 512, 0, 0, 64, 1, jb::EPI_BIAS, 0, 2, 4},
-        {512, 512, 1024, 0, 0, 64, 1, jb::EPI_BIAS, 0, 2, 2},  {512, 1024, 512, 0, 1, 64, 1, jb::EPI_STORE, 0, 2, 4},
-        {1024, 512, 512, 1, 1, 64, 0, jb::EPI_STORE, 1, 2, 4}, {1024, 512, 512, 1, 1, 64, 0, jb::EPI_STORE, 0, 1, 2},
-        {300, 1000, 2000, 0, 0, 64, 1, jb::EPI_BIAS, 0, 1, 4}, {300, 1000, 200, 0, 0, 64, 1, jb::EPI_BIAS, 0, 1, 4},
-        {200, 250, 72, 0, 1, 64, 0, jb::EPI_STORE, 0, 2, 4},   {250, 500, 300, 1, 1, 64, 1, jb::EPI_STORE, 1, 2, 4},
-        {256, 120, 96, 1, 0, 32, 1, jb::EPI_BIAS_LRELU, 0, 2, 4}, {512, 512, 32, 0, 0, 64, 1, jb::EPI_BIAS, 0, 2, 4},
-        {64, 512, 512, 1, 1, 64, 0, jb::EPI_STORE, 0, 1, 4},   {512, 512, 64, 0, 1, 64, 1, jb::EPI_STORE, 0, 2, 1},
+        // split-K clusters with the DSMEM reduce-scatter: ck = 2, 4; both numeric modes; ragged edges; uneven k-block shares
+        {512, 512, 1024, 0, 0, 64, 1, jb::EPI_BIAS, 0, 2},   {512, 64, 512, 0, 0, 64, 1, jb::EPI_BIAS, 0, 4},
+        {512, 32, 512, 0, 1, 32, 1, jb::EPI_STORE, 0, 4},    {512, 512, 1024, 0, 1, 64, 1, jb::EPI_STORE, 0, 2},
+        {300, 1000, 2000, 0, 0, 64, 1, jb::EPI_BIAS, 0, 2},  {300, 78, 200, 0, 1, 64, 1, jb::EPI_STORE, 0, 4},
+        {700, 64, 1302, 0, 0, 64, 1, jb::EPI_BIAS_LRELU, 0, 4}, {130, 39, 300, 1, 1, 64, 1, jb::EPI_STORE, 1, 2},
+        {64, 512, 512, 1, 1, 64, 0, jb::EPI_STORE, 0, 4},    {1024, 512, 512, 1, 1, 128, 0, jb::EPI_STORE, 1, 2},
+        {256, 128, 160, 0, 0, 64, 0, jb::EPI_BIAS, 0, 4},    {100, 130, 70, 1, 0, 32, 1, jb::EPI_STORE, 0, 2},
     };
     for (const Case& c : cases) bad += run_case(c) != 0;
     printf("check: %d failing case(s)\n", bad);
@@ -174,15 +173,13 @@ int main(int argc, char** argv) {
       time_case(2, 512, 64, 512, 0, 0, 64, 1, pdl);      // heads
       time_case(2, 512, 512, 32, 0, 0, 64, 1, pdl);      // first decoder layer
       time_case(2, 512, 1024, 512, 0, 0, 64, 0, pdl);    // single pass for comparison
-      // the same with clusters (operand multicast)
-      time_case(2, 512, 1024, 512, 0, 0, 64, 1, pdl, 1, 4);
-      time_case(2, 512, 1024, 512, 0, 0, 64, 1, pdl, 2, 2);
-      time_case(2, 512, 1024, 512, 0, 0, 64, 1, pdl, 2, 4);
-      time_case(2, 512, 512, 1024, 0, 0, 64, 1, pdl, 2, 4);
-      time_case(2, 512, 512, 1024, 0, 0, 32, 1, pdl, 2, 4);
-      time_case(2, 512, 1024, 512, 0, 1, 64, 1, pdl, 2, 4);
-      time_case(2, 1024, 512, 512, 1, 1, 64, 0, pdl, 2, 4);
-      time_case(2, 512, 1024, 512, 0, 0, 64, 0, pdl, 2, 4);
+      time_case(2, 1024, 512, 512, 1, 1, 128, 0, pdl);   // wgrad, 128-wide tiles
+      // split-K
+      time_case(2, 512, 512, 1024, 0, 0, 64, 1, pdl, 2);
+      time_case(2, 512, 512, 1024, 0, 1, 64, 1, pdl, 2);
+      time_case(2, 512, 64, 512, 0, 0, 64, 1, pdl, 4);
+      time_case(2, 512, 32, 512, 0, 1, 32, 1, pdl, 4);
+      time_case(2, 512, 64, 512, 0, 0, 64, 1, pdl, 2);
     }
   }
   return bad ? 1 : 0;
