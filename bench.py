@@ -32,12 +32,12 @@ sys.path.insert(0, ROOT)
 
 DIMS, LATENT, BATCH, DROPOUT = [512, 512], 32, 512, 0.6
 # launch order of one training step (engine.cu: record_backward / record_update)
-STEP_KERNELS = ['k_begin', 'k_gather', 'k_corr_rowsum', 'k_corr_build', 'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D',
-                'k_bn_fwd', 'gemm F3 heads', 'k_reparam', 'k_combine', 'k_latent_loss', 'gemm F4 dec L->D', 'k_bn_fwd',
-                'gemm F5 dec D->2D', 'k_bn_fwd', 'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 wgrad+dgrad', 'k_bn_bwd',
-                'gemm B5 wgrad+dgrad', 'k_bn_bwd', 'gemm B4 wgrad+dgrad', 'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final',
-                'gemm B3 wgrad+dgrad', 'k_bn_bwd', 'gemm B2 wgrad+dgrad', 'k_bn_bwd', 'gemm B1 wgrad', 'k_gradnorm', 'k_adam',
-                'k_end']
+STEP_KERNELS = ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
+                'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D', 'k_bn_fwd', 'gemm F3 heads', 'k_reparam',
+                'k_combine(+latent loss)', 'gemm F4 dec L->D', 'k_bn_fwd', 'gemm F5 dec D->2D', 'k_bn_fwd',
+                'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 dgrad', 'k_bn_bwd', 'gemm B5 dgrad', 'k_bn_bwd', 'gemm B4 dgrad',
+                'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final', 'gemm B3 dgrad', 'k_bn_bwd', 'gemm B2 dgrad',
+                'k_bn_bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam']
 N_PARAMS = 4312194
 
 
@@ -176,6 +176,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        return t.get(kernel_key)
+    except Exception:
+        return None
+
+
+def predict_leg(eng, torch, peaks, stream, rows_dev=1 << 20, rows_host=1 << 17):
+    """modal_predict (BASELINE metric 2): modality 0 -> 1 on pre-transformed [N, 512] fp32 rows.
+    value: rows resident in HBM, CUDA events; e2e: pinned host buffers in and out through jb_predict."""
+    g = torch.Generator(device='cuda').manual_seed(2)
+    x = torch.randn((rows_dev, DIMS[0]), generator=g, device='cuda', dtype=torch.float32)
+    out = torch.empty((rows_dev, DIMS[1]), device='cuda', dtype=torch.float32)
+    l0 = eng.launch_count()
+    eng.predict_into(0, 1, x.data_ptr(), 1 << 16, DIMS[0], out.data_ptr(), DIMS[1], 1, stream)   # warm-up, folds BN
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.predict_into(0, 1, x.data_ptr(), rows_dev, DIMS[0], out.data_ptr(), DIMS[1], 1, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert bool(torch.isfinite(out[::4097]).all())
+    del x, out
+    hx = torch.randn((rows_host, DIMS[0]), dtype=torch.float32).pin_memory()
+    ho = torch.empty((rows_host, DIMS[1]), dtype=torch.float32).pin_memory()
+    eng.predict_into(0, 1, hx.data_ptr(), rows_host, DIMS[0], ho.data_ptr(), DIMS[1], 0, stream)
+    t0 = time.perf_counter()
+    eng.predict_into(0, 1, hx.data_ptr(), rows_host, DIMS[0], ho.data_ptr(), DIMS[1], 0, stream)
+    dt = time.perf_counter() - t0
+    flops_row = 2.0 * (2 * DIMS[0] * DIMS[0] * 2 + DIMS[0] * LATENT + LATENT * DIMS[1] + 2 * DIMS[1] * DIMS[1] * 2)
+    v = rows_dev / (ms * 1e-3)
+    return {'metric': 'modal_predict cells/sec', 'value': v, 'unit': 'cells/s', 'rows': rows_dev, 'ms': ms,
+            'e2e': {'value': rows_host / dt, 'unit': 'cells/s', 'rows': rows_host,
+                    'h2d_bytes': rows_host * DIMS[0] * 4, 'd2h_bytes': rows_host * DIMS[1] * 4},
+            'roofline': {'bound': 'tensor', 'achieved': v * flops_row / 1e12, 'peak': peaks['bf16_tflops_sustained'],
+                         'unit': 'TFLOP/s', 'frac': v * flops_row / 1e12 / peaks['bf16_tflops_sustained'],
+                         'flops_per_row': flops_row,
+                         'note': 'BatchNorm folded, single-pass TF32 (hardware rate = half the bf16 peak in the denominator)'},
+            'gpu_launches': eng.launch_count() - l0}
+
+
 def workload_config(n_gpus):
     if n_gpus == 1:
         wl = 'BASELINE configs[1]: synthetic 50k-cell pair, post-PCA widths [512,512], output_dim 32, batch 512, ' \
@@ -197,6 +241,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-predict', action='store_true')
     ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu): no e2e / stage / CPU legs, no JSON line')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -321,6 +366,12 @@ def main():
     h2d = sum(BATCH * d * 4 for d in DIMS) + 2 * BATCH * 4 + 4
     d2h = 8 * 4
 
+    pred = predict_leg(eng, torch, peaks, stream) if not args.no_predict else None
+    if pred is not None and world > 1:      # rows/s of the whole job: every rank imputes its own shard, no collective
+        t = torch.tensor([pred['ms'], pred['rows'] / pred['e2e']['value']], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pred['value'] = world * pred['rows'] / (float(t[0]) * 1e-3)
+        pred['e2e']['value'] = world * pred['e2e']['rows'] / float(t[1])
     line = None
     if rank == 0:
         # ---------------- dominant kernel alone (CUDA events on the launching stream)
@@ -343,6 +394,7 @@ def main():
                  'note': 'algorithmic bytes of a whole step = r/w of fp32 params + Adam m, v (6*4*4312194) + gathered '
                          'inputs; SURVEY.md section 8d: the step roofline is 16.1 us'}
         cb = None
+        roof['traffic'] = ncu_traffic('gemm_stage_%d' % st)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline()
         line = {
@@ -355,7 +407,7 @@ def main():
                                          'graph, D2H losses, stream sync) per step'},
             'gpu_launches': int(launches), 'launches_per_step': launches / K,
             'roofline': roof, 'step_roofline': sroof, 'step_profile': prof,
-            'gemm_stages_us': [round(s[0], 2) for s in stages], 'cpu_baseline': cb, 'clocks': clocks.summary(),
+            'gemm_stages_us': [round(s[0], 2) for s in stages], 'modal_predict': pred, 'cpu_baseline': cb, 'clocks': clocks.summary(),
             'final_losses': {k: float(v) for k, v in zip(['KL', 'Rec', 'CosSim', 'F', 'total', 'grad_norm'], losses[-1])},
         }
         print(json.dumps(line), flush=True)

@@ -128,7 +128,9 @@ struct jb_engine {
   cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr, g_host = nullptr, g_host_bwd = nullptr;
   int* h_pin = nullptr;      // pinned staging for the host-batch step (2 x batch indices + 16 floats)
   int launches_host = 0, launches_host_bwd = 0;
-  cudaStream_t cap_stream = nullptr;
+  cudaStream_t cap_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
@@ -366,13 +368,18 @@ int build_train_tables(jb_engine* e, int B, int accum) {
 // ------------------------------------------------------------------------------------------- step recording
 struct Rec {  // launches kernels on a stream and counts them
   jb_engine* e; cudaStream_t s; int n = 0; cudaError_t err = cudaSuccess;
+  // Capture only: a second stream forked off the step's stream so that kernels nothing upstream depends on (the P / F
+  // block build) run beside the encoder instead of in front of it. Null: everything is launched in order on s.
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool no_pdl_next = false;   // the next launch has a cross-stream dependency: plain (full) serialization
   cudaEvent_t* ev = nullptr;        // profiling: ev[k] is recorded after launch k - 1 (ev[0] before the first launch)
   const char** names = nullptr;
   void mark(const char* name) {
     if (ev && n < 63) { names[n] = name; cudaEventRecord(ev[n + 1], s); }
   }
   void gemm(const GemmStage& st) {
-    if (err == cudaSuccess) err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl, st.ck);
+    if (err == cudaSuccess)
+      err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl, st.ck, e->h_probs.data() + st.first);
     mark("gemm");
     ++n;
   }
@@ -390,7 +397,8 @@ void launchk(Rec& r, void (*kern)(KP...), dim3 grid, dim3 block, A... args) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = r.e->use_pdl ? 1 : 0;
+  cfg.numAttrs = (r.e->use_pdl && !r.no_pdl_next) ? 1 : 0;
+  r.no_pdl_next = false;
   r.err = cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
   r.mark(nullptr);
   ++r.n;
@@ -428,22 +436,35 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   const jb::StepConsts sc = make_consts(e, B);
   float* T = e->theta;
   float* G = e->grad;
-  // control + inputs
-  launchk(r, jb::k_begin, dim3(1), dim3(1), e->ctl, e->plan_kl, sc);
+  // inputs (the first kernel also derives the step's control scalars)
   jb::GatherArgs ga{};
   for (int i = 0; i < 2; ++i) {
     ga.data[i] = e->data[i]; ga.ld_data[i] = e->data_ld[i]; ga.x[i] = e->act[i].x; ga.ldx[i] = e->act[i].ldD;
     ga.xh[i] = e->act[i].xp.hi; ga.xl[i] = e->act[i].xp.lo;
     ga.D[i] = e->D[i]; ga.idx[i] = e->plan_idx[i];
   }
-  if (gather) launchk(r, jb::k_gather, dim3(B, 2), dim3(128), ga, e->ctl, B);
-  else launchk(r, jb::k_split_x, dim3(B, 2), dim3(128), ga, B);   // host batch: x was copied in, make its operand planes
+  if (gather) launchk(r, jb::k_gather, dim3(B, 2), dim3(128), ga, e->ctl, e->plan_kl, sc, B);
+  else launchk(r, jb::k_split_x, dim3(B, 2), dim3(128), ga, e->ctl, e->plan_kl, sc, B);   // host batch: x was copied in
+  // P / F blocks: needed first by k_combine, so on the side stream they overlap the encoder
   jb::CorrArgs ca{};
   ca.p_diag = e->p_diag; ca.p_dense = e->p_dense; ca.f_dense = e->f_dense; ca.n1 = e->pn1;
   ca.idx[0] = e->plan_idx[0]; ca.idx[1] = e->plan_idx[1]; ca.rs_p = e->rs_p; ca.rs_f = e->rs_f;
   ca.corr = e->corr; ca.corr_t = e->corr_t; ca.fblk = e->fblk; ca.fblk_t = e->fblk_t; ca.pf_ratio = e->cfg.pf_ratio;
-  launchk(r, jb::k_corr_rowsum, dim3(B), dim3(128), ca, e->ctl, B);
-  launchk(r, jb::k_corr_build, dim3((B + 31) / 32, (B + 31) / 32), dim3(32, 8), ca, e->ctl, B);
+  {
+    cudaStream_t main_s = r.s;
+    const bool fork = r.side != nullptr && r.err == cudaSuccess;
+    if (fork) {
+      if ((r.err = cudaEventRecord(r.ev_fork, main_s)) == cudaSuccess) r.err = cudaStreamWaitEvent(r.side, r.ev_fork, 0);
+      r.s = r.side;
+      r.no_pdl_next = true;
+    }
+    launchk(r, jb::k_corr_rowsum, dim3(B), dim3(128), ca, e->ctl, B);
+    launchk(r, jb::k_corr_build, dim3((B + 31) / 32, (B + 31) / 32), dim3(32, 8), ca, e->ctl, B);
+    if (fork) {
+      if (r.err == cudaSuccess) r.err = cudaEventRecord(r.ev_join, r.side);
+      r.s = main_s;
+    }
+  }
 
   auto bnf = [&](int k, int which /*0 enc1,1 enc2,2 dec1,3 dec2*/) {
     (void)k;
@@ -473,8 +494,13 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   jb::Latent lat = make_latent(e);
   launchk(r, jb::k_reparam, dim3((2 * B * L + 255) / 256), dim3(256), lat, e->ctl, B, L);
   const int wblocks = (2 * B * 32 + 255) / 256;
-  launchk(r, jb::k_combine, dim3(wblocks), dim3(256), lat, B, L);
-  launchk(r, jb::k_latent_loss, dim3(wblocks), dim3(256), lat, B, L);
+  if (r.side && r.err == cudaSuccess) {   // join: the P / F blocks are complete
+    r.err = cudaStreamWaitEvent(r.s, r.ev_join, 0);
+    r.no_pdl_next = true;
+  }
+  const int fuse_loss = lat.f_present ? 0 : 1;   // without F the loss partials need nothing of another row
+  launchk(r, jb::k_combine, dim3(wblocks), dim3(256), lat, B, L, fuse_loss);
+  if (!fuse_loss) launchk(r, jb::k_latent_loss, dim3(wblocks), dim3(256), lat, B, L);
   r.gemm(e->st_f[3]); bnf(2, 2);
   r.gemm(e->st_f[4]); bnf(3, 3);
   r.gemm(e->st_f[5]);
@@ -527,7 +553,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   }
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
   fa.grad_tail = G + e->n_flat;
-  launchk(r, jb::k_latent_final, dim3(1), dim3(1024), fa, lat, e->ctl, B, L, sc, accum);
+  launchk(r, jb::k_latent_final, dim3(1 + (4 * L + jb::SLAB_CW - 1) / jb::SLAB_CW), dim3(jb::SLAB_THREADS), fa, e->ctl, B, L, sc, accum);
   r.gemm(e->st_b[3]); bnb(1);
   r.gemm(e->st_b[4]); bnb(0);
   r.gemm(e->st_b[5]);
@@ -538,13 +564,13 @@ void record_update(jb_engine* e, Rec& r, int B) {
   const long long n4 = e->n_flat / 4;
   launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, n4, e->norm_part);
   launchk(r, jb::k_adam, jb::NORM_BLOCKS * 2, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
-  launchk(r, jb::k_end, dim3(1), dim3(1), e->ctl);
 }
 
 int capture(jb_engine* e, int B, int what /*0 full,1 bwd,2 upd*/, cudaGraphExec_t* out, int* nlaunch) {
   cudaGraph_t g = nullptr;
   CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   Rec r{e, e->cap_stream};
+  if (e->use_side) { r.side = e->side_stream; r.ev_fork = e->ev_fork; r.ev_join = e->ev_join; }
   if (what == 0 || what == 1) record_backward(e, r, B);
   if (what == 3 || what == 4) record_backward(e, r, B, false);
   if (what == 0 || what == 2 || what == 3) record_update(e, r, B);
@@ -748,6 +774,10 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMemcpy(e->ctl, &c0, sizeof c0, cudaMemcpyHostToDevice));
   CU(cudaMalloc(&e->norm_part, jb::NORM_BLOCKS * sizeof(double)));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
   if (const char* pv = getenv("JB_SPLITK")) e->use_splitk = atoi(pv) != 0;
@@ -780,6 +810,9 @@ void jb_destroy(jb_engine* e) {
                   e->arena, e->d_probs, e->ev_a, e->ev_b, e->ev_in, e->ev_out, e->d_ev_probs};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (int k = 0; k < 2; ++k) if (e->ev_stream[k]) cudaStreamDestroy(e->ev_stream[k]);
   delete e;
 }
@@ -1086,9 +1119,9 @@ int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* fl
     fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck));
+  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first));
   CU(cudaEventRecord(a, s));
-  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck));
+  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first));
   CU(cudaEventRecord(b, s));
   CU(cudaEventSynchronize(b));
   float ms = 0;

@@ -85,6 +85,11 @@ struct alignas(128) GemmProblem {
   int split;       // 1: error-compensated 3xTF32 on pre-split hi/lo planes, see the header comment
 };
 
+// First CTA of every problem of a launch, passed BY VALUE (constant bank): the CTA -> problem lookup costs no dependent
+// global loads (the wgrad launch has 12 problems).
+constexpr int GEMM_MAX_PROBS = 16;
+struct GemmBases { int base[GEMM_MAX_PROBS]; };
+
 struct GemmCtrl {
   uint64_t full[GEMM_MAX_STAGES];
   uint64_t empty[GEMM_MAX_STAGES];
@@ -97,7 +102,7 @@ struct GemmCtrl {
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck) {
+gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck, const GemmBases bases) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle (TMA and UMMA descriptors agree on it).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,7 +116,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   int p = 0;
   {
     const int tile = blockIdx.x;
-    while (p + 1 < nprobs && tile >= probs[p + 1].tile_base) ++p;
+    while (p + 1 < nprobs && tile >= bases.base[p + 1]) ++p;
   }
   const GemmProblem& P = probs[p];
   // Everything the pipelines need is read ONCE into registers: the inline-asm barriers below carry "memory"
@@ -119,7 +124,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   // Split-K: a cluster of ck CTAs (launch attribute) owns one output tile; rank r accumulates its share of the
   // k-blocks and the partial tiles are reduced through distributed shared memory (see the epilogue). tile_base counts
   // CTAs, a multiple of ck for every problem, so blockIdx.x % ck is the cluster rank.
-  const int cta = blockIdx.x - P.tile_base;
+  const int cta = blockIdx.x - bases.base[p];
   const int crank = cta % ck;
   const int t = cta / ck;
   const int tiles_n = P.tiles_n;
@@ -529,8 +534,12 @@ inline int gemm_table_finalize(GemmProblem* g, int n, int ck = 1) {
 // use_pdl: launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself), so that its
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream.
 // total_ctas = gemm_table_finalize(..., ck). ck > 1 launches clusters of ck CTAs (split-K, see the kernel).
+// host_table: the host copy of the same table entries (tile_base of every problem), or null for a single problem.
 inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_ctas, cudaStream_t st, bool use_pdl = false,
-                               int ck = 1) {
+                               int ck = 1, const GemmProblem* host_table = nullptr) {
+  if (nprobs > GEMM_MAX_PROBS || (nprobs > 1 && !host_table)) return cudaErrorInvalidValue;
+  GemmBases bases{};
+  for (int i = 0; i < nprobs; ++i) bases.base[i] = host_table ? host_table[i].tile_base : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -559,7 +568,7 @@ inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int tot
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck);
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck, bases);
 }
 
 }  // namespace jb

@@ -69,12 +69,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// ------------------------------------------------------------------------------------------------ k_begin
-// One thread: advance the plan cursor and derive this step's scalars.
-__global__ void k_begin(Ctl* ctl, const float* __restrict__ plan_kl, StepConsts sc) {
-  pdl_prologue();
-  const long long row = ctl->cursor++;
-  const long long t = ++ctl->adam_t;
+// ------------------------------------------------------------------------------------------------ step control
+// The first kernel of a step (k_gather / k_split_x) derives the step's scalars: every block reads the plan cursor
+// (nobody writes it while that kernel runs) and one thread publishes the derived values for the later kernels. The
+// cursor and the Adam step count advance later in the step (k_reparam); the injection flag is cleared by k_adam.
+__device__ __forceinline__ void step_begin(Ctl* ctl, const float* __restrict__ plan_kl, const StepConsts& sc) {
+  const long long row = ctl->cursor;
+  const long long t = ctl->adam_t + 1;
   ctl->row = static_cast<int>(row);
   ctl->kl_base = plan_kl[row];
   ctl->kl_coef = sc.w[0] * plan_kl[row];
@@ -84,8 +85,6 @@ __global__ void k_begin(Ctl* ctl, const float* __restrict__ plan_kl, StepConsts 
   ctl->inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   ctl->stream_id = static_cast<unsigned long long>(t);
 }
-__global__ void k_end(Ctl* ctl) {
-  pdl_prologue(); ctl->inject = 0; }
 
 // busy-wait (profiling only): gives the host a head start so a whole step is enqueued behind it
 __global__ void k_spin(long long ns) {
@@ -105,10 +104,12 @@ struct GatherArgs {
   int D[2];
   const int* idx[2];  // plan index arrays [nsteps][B]
 };
-__global__ void k_gather(GatherArgs a, const Ctl* __restrict__ ctl, int B) {
+__global__ void k_gather(GatherArgs a, Ctl* ctl, const float* __restrict__ plan_kl, StepConsts sc, int B) {
   pdl_prologue();
   const int i = blockIdx.y, b = blockIdx.x;
-  const int src = a.idx[i][static_cast<long long>(ctl->row) * B + b];
+  const long long row = ctl->cursor;
+  if (i == 0 && b == 0 && threadIdx.x == 0) step_begin(ctl, plan_kl, sc);
+  const int src = a.idx[i][row * B + b];
   const float* s = a.data[i] + static_cast<long long>(src) * a.ld_data[i];
   const long long o = static_cast<long long>(b) * a.ldx[i];
   float* d = a.x[i] + o;
@@ -135,9 +136,10 @@ __global__ void k_gather(GatherArgs a, const Ctl* __restrict__ ctl, int B) {
   }
 }
 // Host-batch step: x arrives by H2D copy; this produces its operand planes. grid (B, 2), 128 threads.
-__global__ void k_split_x(GatherArgs a, int B) {
+__global__ void k_split_x(GatherArgs a, Ctl* ctl, const float* __restrict__ plan_kl, StepConsts sc, int B) {
   pdl_prologue();
   const int i = blockIdx.y, b = blockIdx.x;
+  if (i == 0 && b == 0 && threadIdx.x == 0) step_begin(ctl, plan_kl, sc);
   const long long o = static_cast<long long>(b) * a.ldx[i];
   const float* s = a.x[i] + o;
   float* dh = a.xh[i] + o;
@@ -675,9 +677,10 @@ struct Latent {
 constexpr int LAT_MAXT = 4;  // latent width up to 128
 
 // eps (injected or Philox Box-Muller) and z = mu + (exp(logvar/2) + 1e-7) eps   (jamie/model.py:230-240)
-__global__ void k_reparam(Latent a, const Ctl* __restrict__ ctl, int B, int L) {
+__global__ void k_reparam(Latent a, Ctl* ctl, int B, int L) {
   pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) { ctl->cursor += 1; ctl->adam_t += 1; }   // this step's scalars were derived by the first kernel
   if (t >= 2 * B * L) return;
   const int i = t / (B * L), rem = t - i * B * L, b = rem / L, l = rem - b * L;
   float e;
@@ -733,7 +736,9 @@ __device__ __forceinline__ float row_times(const float* __restrict__ Mrow, const
 
 // combine (jamie/model.py:245-259): c_i = (s_i z_i + s_j C_i z_j) / (s_i + s_j rowsum(C_i)), C_0 = corr, C_1 = corr^T.
 // One warp per (modality, row).
-__global__ void k_combine(Latent a, int B, int L) {
+// fuse_loss (F absent: the F residual is r = c0, nothing of another row is needed): also emits the row partial sums of
+// k_latent_loss, which is then not launched.
+__global__ void k_combine(Latent a, int B, int L, int fuse_loss) {
   pdl_prologue();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= 2 * B) return;
@@ -744,15 +749,31 @@ __global__ void k_combine(Latent a, int B, int L) {
   const float rs = row_times(Ci, a.z[j], B, a.LP, L, lane, acc);
   const float den = si + sj * rs;
   if (lane == 0) { a.den[i][row] = den; a.rs[i][row] = rs; }
+  float smu = 0.f, scs = 0.f, sr = 0.f;
 #pragma unroll
   for (int t = 0; t < LAT_MAXT; ++t) {
     const int l = lane + 32 * t;
     if (l < L) {
       const long long o = static_cast<long long>(row) * a.LP + l;
       a.S[i][o] = acc[t];
-      const float cv = (si * a.z[i][o] + sj * acc[t]) / den;
+      const float zv = a.z[i][o];
+      const float cv = (si * zv + sj * acc[t]) / den;
       a.c[i][o] = cv;
       tf32_split(cv, a.ch[i][o], a.cl[i][o]);
+      if (fuse_loss) {
+        const float mu = a.mulv[i][static_cast<long long>(row) * a.ldmv + l];
+        smu += mu * mu;
+        const float d = zv - cv;
+        scs += d * d;
+        if (i == 0) { a.r[o] = cv; sr += cv * cv; }
+      }
+    }
+  }
+  if (fuse_loss) {
+    smu = warp_sum(smu); scs = warp_sum(scs); sr = warp_sum(sr);
+    if (lane == 0) {
+      float* rp = a.rowpart + (static_cast<long long>(i) * B + row) * 8;
+      rp[0] = smu; rp[1] = scs; rp[2] = sr;
     }
   }
 }
@@ -875,13 +896,30 @@ struct FinalArgs {
   float* grad_tail;              // 8 floats after the flat gradients (all-reduce piggy-back)
   int D[2];
 };
-__global__ void __launch_bounds__(1024) k_latent_final(FinalArgs a, Latent lat, const Ctl* __restrict__ ctl, int B, int L,
-                                                       StepConsts sc, int accum) {
+// grid 1 + ceil(4L / 16) blocks of 1024 threads: block 0 reduces the loss scalars and d sigma; block 1 + k owns 16 of
+// the 4L head-bias columns (both modalities: mu bias | var bias) with 64 row slots per column.
+__global__ void __launch_bounds__(SLAB_THREADS) k_latent_final(FinalArgs a, const Ctl* __restrict__ ctl, int B, int L,
+                                                               StepConsts sc, int accum) {
   pdl_prologue();
   __shared__ float tot[14];   // [i*7 + k]: k = 0..5 the rowpart sums, k = 6: sum_r (g.c)[r] * rowsum_i[r]
-  __shared__ float colpart[8][128];
   __shared__ float aux[4];    // [0,1]: sum_l (1 + lv - exp lv) of logvar rows 0/1 (modality 1); [2,3]: sum (xhat - x)^2
+  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (blockIdx.x > 0) {
+    // head bias gradients: column sums of dmulv over the batch (fixed order)
+    const int col = (blockIdx.x - 1) * SLAB_CW + (tid & (SLAB_CW - 1));
+    const int slot = tid / SLAB_CW;
+    const bool cok = col < 4 * L;
+    const int i = cok ? col / (2 * L) : 0, cidx = cok ? col - i * 2 * L : 0;
+    const float* src = a.dmulv[i] + cidx;
+    float s = 0.f, dummy = 0.f;
+    if (cok)
+#pragma unroll 8
+      for (int r = slot; r < B; r += SLAB_SLOTS) s += __ldg(src + static_cast<long long>(r) * a.ldmv);
+    slab_colsum2(s, dummy, sh, warp, lane);
+    if (slot == 0 && cok) a.dbias_heads[i][cidx] = accum ? a.dbias_heads[i][cidx] + s : s;
+    return;
+  }
   if (warp >= 14 && warp < 16) {
     const int i = warp - 14;
     float t1 = 0.f;
@@ -909,27 +947,6 @@ __global__ void __launch_bounds__(1024) k_latent_final(FinalArgs a, Latent lat, 
     s = warp_sum(s);
     if (lane == 0) tot[warp] = s;
   }
-  // head bias gradients: column sums of dmulv, 8 row groups x up to 128 columns per pass
-  for (int col0 = 0; col0 < 4 * L; col0 += 128) {
-    const int col = col0 + (tid & 127), grp = tid >> 7;
-    float s = 0.f;
-    if (col < 4 * L) {
-      const int i = col / (2 * L), cidx = col - i * 2 * L;
-      const float* src = a.dmulv[i] + cidx;
-#pragma unroll 8
-      for (int r = grp; r < B; r += 8) s += src[static_cast<long long>(r) * a.ldmv];
-    }
-    colpart[grp][tid & 127] = s;
-    __syncthreads();
-    if (tid < 128 && col < 4 * L) {
-      float t = 0.f;
-#pragma unroll
-      for (int gq = 0; gq < 8; ++gq) t += colpart[gq][tid];
-      const int i = col / (2 * L), cidx = col - i * 2 * L;
-      a.dbias_heads[i][cidx] = accum ? a.dbias_heads[i][cidx] + t : t;
-    }
-    __syncthreads();
-  }
   __syncthreads();
   if (tid == 0) {
     const float fB = static_cast<float>(B), fL = static_cast<float>(L);
@@ -952,7 +969,6 @@ __global__ void __launch_bounds__(1024) k_latent_final(FinalArgs a, Latent lat, 
     o[0] = l_kl; o[1] = rec; o[2] = l_cos; o[3] = l_f; o[4] = total; o[6] = 0.f; o[7] = 0.f;
     a.grad_tail[0] = l_kl; a.grad_tail[1] = rec; a.grad_tail[2] = l_cos; a.grad_tail[3] = l_f; a.grad_tail[4] = total;
   }
-  (void)lat;
 }
 
 // ------------------------------------------------------------------------------------------------ clip + Adam
@@ -980,7 +996,7 @@ __global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, l
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* __restrict__ theta_hi,
                                               float* __restrict__ theta_lo, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n4, const double* __restrict__ part,
-                                              int nparts, const Ctl* __restrict__ ctl, StepConsts sc,
+                                              int nparts, Ctl* ctl, StepConsts sc,
                                               float* __restrict__ out_loss) {
   pdl_prologue();
   __shared__ double red[256];
@@ -997,7 +1013,10 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
     const double norm = sqrt(red[0]) * static_cast<double>(sc.grad_scale);
     const double coef = fmin(1.0, static_cast<double>(sc.max_norm) / (norm + 1e-6));
     s_coef = static_cast<float>(coef) * sc.grad_scale;
-    if (blockIdx.x == 0) out_loss[static_cast<long long>(ctl->row) * 8 + 5] = static_cast<float>(norm);
+    if (blockIdx.x == 0) {
+      out_loss[static_cast<long long>(ctl->row) * 8 + 5] = static_cast<float>(norm);
+      ctl->inject = 0;   // injected eps / masks serve exactly one step
+    }
   }
   __syncthreads();
   const float coef = s_coef;

@@ -117,10 +117,10 @@ static int time_case(int nprob, int M, int N, int K, int a_mn, int b_mn, int bn,
   CK(cudaMemcpy(dg, g.data(), nprob * sizeof(jb::GemmProblem), cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 5; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, ck));
+  for (int i = 0; i < 5; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, ck, g.data()));
   const int iters = 200;
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, ck));
+  for (int i = 0; i < iters; ++i) CK(jb::gemm_launch(dg, nprob, tiles, 0, pdl, ck, g.data()));
   CK(cudaEventRecord(e1));
   CK(cudaEventSynchronize(e1));
   float ms;
