@@ -32,12 +32,21 @@ sys.path.insert(0, ROOT)
 
 DIMS, LATENT, BATCH, DROPOUT = [512, 512], 32, 512, 0.6
 # launch order of one training step (engine.cu: record_backward / record_update)
-STEP_KERNELS = ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
-                'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D', 'k_bn_fwd', 'gemm F3 heads', 'k_reparam',
-                'k_combine(+latent loss)', 'gemm F4 dec L->D', 'k_bn_fwd', 'gemm F5 dec D->2D', 'k_bn_fwd',
-                'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 dgrad', 'k_bn_bwd', 'gemm B5 dgrad', 'k_bn_bwd', 'gemm B4 dgrad',
-                'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final', 'gemm B3 dgrad', 'k_bn_bwd', 'gemm B2 dgrad',
-                'k_bn_bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam']
+STEP_KERNELS = {
+    # fused epilogues (B <= 512): BatchNorm / LeakyReLU / Dropout forward and backward and the reconstruction loss live in
+    # the GEMM epilogues
+    22: ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
+         'gemm F1 enc D->2D +BN', 'gemm F2 enc 2D->D +BN', 'gemm F3 heads', 'k_reparam', 'k_combine(+latent loss)',
+         'gemm F4 dec L->D +BN', 'gemm F5 dec D->2D +BN', 'gemm F6 dec 2D->D +rec loss', 'gemm B6 dgrad +BN bwd',
+         'gemm B5 dgrad +BN bwd', 'gemm B4 dgrad', 'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final',
+         'gemm B3 dgrad +BN bwd', 'gemm B2 dgrad +BN bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam'],
+    31: ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
+         'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D', 'k_bn_fwd', 'gemm F3 heads', 'k_reparam',
+         'k_combine(+latent loss)', 'gemm F4 dec L->D', 'k_bn_fwd', 'gemm F5 dec D->2D', 'k_bn_fwd',
+         'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 dgrad', 'k_bn_bwd', 'gemm B5 dgrad', 'k_bn_bwd', 'gemm B4 dgrad',
+         'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final', 'gemm B3 dgrad', 'k_bn_bwd', 'gemm B2 dgrad',
+         'k_bn_bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam'],
+}
 N_PARAMS = 4312194
 
 
@@ -325,7 +334,7 @@ def main():
     if world == 1:
         eng.upload_plan(idx0[:1], idx1[:1], np.full(1, 0.5), stream)
         us = eng.profile_step(20, stream)
-        names = STEP_KERNELS if len(us) == len(STEP_KERNELS) else [f'launch{k}' for k in range(len(us))]
+        names = STEP_KERNELS.get(len(us), [f'launch{k}' for k in range(len(us))])
         prof = {'sum_us': float(us.sum()), 'launches': [[n, round(float(u), 2)] for n, u in zip(names, us)],
                 'note': 'eager launches with a CUDA event between consecutive kernels (warm L2, no graph, no PDL): '
                         'shares of the step, not absolutes'}

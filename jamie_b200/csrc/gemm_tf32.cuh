@@ -46,6 +46,7 @@
 #include <cstdint>
 #include <cstdio>
 #include "ptx.cuh"
+#include "kernels.cuh"
 
 namespace jb {
 
@@ -66,6 +67,27 @@ enum GemmEpilogue : int {
   EPI_STORE = 0,       // C = acc
   EPI_BIAS = 1,        // C = acc + bias[n]
   EPI_BIAS_LRELU = 2,  // C = leaky_relu(acc + bias[n], slope)      (inference, BatchNorm folded)
+  // Fused training epilogues (B <= 512: the M tiles of one column block form a thread-block cluster that exchanges
+  // per-column statistics through distributed shared memory, so BatchNorm needs no kernel of its own):
+  EPI_BN_FWD = 3,      // Y = acc + bias -> BatchNorm (batch stats, running-stat update) -> LeakyReLU -> Dropout -> hi / lo planes
+  EPI_BN_BWD = 4,      // dH = acc -> through Dropout, LeakyReLU, BatchNorm -> dY hi / lo planes, dgamma, dbeta
+  EPI_REC = 5,         // xhat = acc + bias -> dxhat = k (xhat - x) hi / lo planes, sum (xhat - x)^2, bias gradient
+};
+
+// Arguments of the fused training epilogues (see the kernel).
+struct GemmFused {
+  float* out_hi; float* out_lo; int ld_out;    // the planes the next GEMM reads
+  const float* aux; int ld_aux;                // BN_BWD: saved pre-BN Y;  REC: x
+  const float* gamma; const float* beta;
+  float* mean; float* invstd;                  // BN_FWD writes, BN_BWD reads
+  float* run_mean; float* run_var;
+  float* dgamma; float* dbeta; float* dbias;   // BN_BWD (dbias = 0);  REC: dbias = column sums of dxhat
+  float* part;                                 // REC: [4 * cm] per-slab partial sums of (xhat - x)^2
+  const unsigned char* mask; int ldm;          // injected keep-mask or null
+  unsigned layer_id;
+  float drop_p;
+  float scale_k;                               // REC: w_rec * 2 / (B D)
+  int store_c;                                 // also store the fp32 result C (Y / xhat)
 };
 
 struct alignas(128) GemmProblem {
@@ -83,6 +105,8 @@ struct alignas(128) GemmProblem {
   int accumulate;  // C += result (one CTA owns the tile: no atomics)
   float slope;
   int split;       // 1: error-compensated 3xTF32 on pre-split hi/lo planes, see the header comment
+  int cm;          // M tiles per cluster (fused epilogues: all M tiles of a column block, padded to a power of two); else 1
+  GemmFused f;
 };
 
 // First CTA of every problem of a launch, passed BY VALUE (constant bank): the CTA -> problem lookup costs no dependent
@@ -102,7 +126,8 @@ struct GemmCtrl {
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck, const GemmBases bases) {
+gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck, const GemmBases bases,
+                         const Ctl* __restrict__ ctl) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle (TMA and UMMA descriptors agree on it).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,11 +149,19 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   // Split-K: a cluster of ck CTAs (launch attribute) owns one output tile; rank r accumulates its share of the
   // k-blocks and the partial tiles are reduced through distributed shared memory (see the epilogue). tile_base counts
   // CTAs, a multiple of ck for every problem, so blockIdx.x % ck is the cluster rank.
+  // Fused epilogues: the cluster additionally spans the cm M tiles of one column block (cluster = cm x ck CTAs, the
+  // split-K ranks of a tile adjacent), so per-column statistics over the whole batch are exchanged through DSMEM.
+  const int cm = P.cm;
+  const int csize = cm * ck;                // cluster size of the launch (identical for every problem of a launch)
   const int cta = blockIdx.x - bases.base[p];
-  const int crank = cta % ck;
-  const int t = cta / ck;
+  const int cr = cta % csize;               // == %cluster_ctarank (problem bases are multiples of csize)
+  const int crank = cr % ck;                // split-K rank
+  const int tmc = cr / ck;                  // M tile within the cluster
+  const int kbase = tmc * ck;               // cluster rank of split-K rank 0 of this tile
   const int tiles_n = P.tiles_n;
-  const int tm = t / tiles_n, tn = t % tiles_n;
+  int tm, tn;
+  if (cm > 1) { tn = cta / csize; tm = tmc; }
+  else { const int t = cta / ck; tm = t / tiles_n; tn = t % tiles_n; }
   const int m0 = tm * GEMM_BM;
   const int bn = P.bn;
   const int n0 = tn * bn;
@@ -316,7 +349,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
 
   // Split-K, barrier A: every CTA of the cluster has finished reading its operand ring (the epilogue warps arrive after
   // the last MMA has completed), so a mate may now deposit its partial tile into it.
-  if (ck > 1) cluster_sync_all();
+  if (csize > 1) cluster_sync_all();
 
   if (warp >= 2) {
     // ------------------------------------------------ epilogue warps, phase 2: TMEM -> registers -> (reduce) -> global
@@ -359,7 +392,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     if (ck > 1 && owner != crank) {
       const int slot = crank < owner ? crank : crank - 1;
       float* dst_local = reinterpret_cast<float*>(tiles) + (slot * slabs_per_owner + ql) * slab_floats + lane * pitch;
-      const uint32_t dst = mapa_shared(smem_u32(dst_local), static_cast<uint32_t>(owner));
+      const uint32_t dst = mapa_shared(smem_u32(dst_local), static_cast<uint32_t>(kbase + owner));
       for (int c0 = 0; c0 < bn; c0 += 32) {
         if (n0 + c0 >= pN) break;  // warp-uniform
         float v[32];
@@ -370,7 +403,275 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
       }
     }
     if (ck > 1) cluster_sync_all();   // barrier B: the deposits are visible to their owners
-    if (ck == 1 || owner == crank) {
+    const bool is_owner = ck == 1 || owner == crank;
+    // this thread's row of the FINISHED tile (all split-K partials added in ascending rank order), columns [c0, c0 + 32)
+    auto final_chunk = [&](int c0, float (&v)[32]) {
+      load_chunk(c0, v);
+      for (int sl = 0; sl < ck - 1; ++sl) {
+        const float* src = reinterpret_cast<const float*>(tiles) + (sl * slabs_per_owner + ql) * slab_floats + lane * pitch + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(src + 4 * j);
+          v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+        }
+      }
+    };
+    if (epi >= EPI_BN_FWD) {
+      // ------------------------------------------------ fused training epilogues
+      const GemmFused F = P.f;
+      float* const stats = reinterpret_cast<float*>(tiles + 64 * 1024);   // [16 slabs][2][64 columns]
+      float* const stash = reinterpret_cast<float*>(tiles + 96 * 1024);   // [2 planes][64 columns][128 rows]
+      const int tid_e = q * 32 + lane;           // row inside the CTA tile
+      const int grow = m0 + tid_e;
+      const bool rok = grow < pM;
+      const int slab = tmc * 4 + q;              // 32-row slab of the batch this warp finishes (rows 32 slab ..)
+      const int nslabs = 4 * cm;
+      const int n_w = pM - (m0 + q * 32) < 0 ? 0 : (pM - (m0 + q * 32) > 32 ? 32 : pM - (m0 + q * 32));
+      const float fM = static_cast<float>(pM);
+      const float drop_p = F.drop_p;
+      const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+      const bool inject = epi != EPI_REC && ctl->inject != 0 && F.mask != nullptr;
+      const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(fminf(drop_p * 4294967296.0f, 4294967040.0f)) : 0u;
+      const uint2 key = epi != EPI_REC ? philox_key(ctl) : make_uint2(0u, 0u);
+      const int rsub = lane >> 3, ch = lane & 7;
+      // bit j: element (grow, nbase + j) is kept by the dropout; one Philox call yields 4 columns of this row
+      auto keep_bits = [&](int nbase) -> uint32_t {
+        if (!(drop_p > 0.f)) return 0xffffffffu;
+        uint32_t bits = 0u;
+        if (inject) {
+          if (rok) {
+            const unsigned char* mrow = F.mask + static_cast<long long>(grow) * F.ldm + nbase;
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < pN && mrow[j] != 0) bits |= 1u << j;
+          }
+        } else {
+#pragma unroll
+          for (int cg = 0; cg < 8; ++cg) {
+            const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(grow), static_cast<uint32_t>((nbase >> 2) + cg),
+                                                  F.layer_id, 0x4A4Eu), key);
+            bits |= (r.x >= thresh ? 1u : 0u) << (4 * cg) | (r.y >= thresh ? 1u : 0u) << (4 * cg + 1) |
+                    (r.z >= thresh ? 1u : 0u) << (4 * cg + 2) | (r.w >= thresh ? 1u : 0u) << (4 * cg + 3);
+          }
+        }
+        return bits;
+      };
+      // x[j] = element (this row, column j) -> st (transposed access), then lane = column: sum over the 32 rows
+      auto to_stage = [&](const float (&x)[32]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        __syncwarp();
+      };
+      auto colsum = [&](const float (&x)[32]) -> float {
+        to_stage(x);
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) s += st[r * GEMM_EPI_PITCH + lane];
+        __syncwarp();
+        return s;
+      };
+      // coalesced store of this warp's 32 x 32 block (row = thread) to base[grow, nbase ..]
+      auto store_rows = [&](const float (&x)[32], float* base, int ld, int nbase) {
+        const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+        to_stage(x);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;
+          const int gr = m0 + q * 32 + r;
+          const int n = nbase + ch * 4;
+          const float4 xx = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
+          if (gr < pM && n < pN) {
+            float* dst = base + static_cast<size_t>(gr) * ld + n;
+            if (vec && n + 4 <= pN) *reinterpret_cast<float4*>(dst) = xx;
+            else {
+              const float xs[4] = {xx.x, xx.y, xx.z, xx.w};
+              for (int j = 0; j < 4; ++j) if (n + j < pN) dst[j] = xs[j];
+            }
+          }
+        }
+        __syncwarp();
+      };
+      auto store_planes = [&](float (&x)[32], int nbase) {   // x -> hi / lo planes; x is destroyed
+        float h[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = tf32_rna(x[j]);
+        store_rows(h, F.out_hi, F.ld_out, nbase);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = tf32_rna(x[j] - h[j]);
+        store_rows(h, F.out_lo, F.ld_out, nbase);
+      };
+      // this row of an fp32 [M, ld] matrix, columns [nbase, nbase + 32) (zeros outside the matrix)
+      auto load_row = [&](const float* base, int ld, int nbase, float (&x)[32]) {
+        const float* src = base + static_cast<long long>(rok ? grow : 0) * ld + nbase;
+        if (rok && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && nbase + 32 <= pN) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(src) + j);
+            x[4 * j] = t4.x; x[4 * j + 1] = t4.y; x[4 * j + 2] = t4.z; x[4 * j + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (rok && nbase + j < pN) ? __ldg(src + j) : 0.f;
+        }
+      };
+      // all-gather of this slab's two per-column statistics into every CTA of the cluster
+      auto publish = [&](int c0, float a, float b) {
+        float* loc = stats + slab * 128 + c0 + lane;
+        if (csize == 1) { loc[0] = a; loc[64] = b; }
+        else {
+          const uint32_t la = smem_u32(loc);
+          for (int rr = 0; rr < csize; ++rr) {
+            const uint32_t ra = mapa_shared(la, static_cast<uint32_t>(rr));
+            st_shared_cluster_f32(ra, a);
+            st_shared_cluster_f32(ra + 256u, b);
+          }
+        }
+      };
+
+      // -------- phase 1: finish the tile, local statistics, stash what phase 2 needs
+      float sq_thread = 0.f;
+      if (is_owner) {
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+          const int nbase = n0 + c0;
+          if (nbase >= pN) break;  // warp-uniform
+          const int col = nbase + lane;
+          const bool cok = col < pN;
+          float v[32];
+          final_chunk(c0, v);
+          if (epi != EPI_BN_BWD) {
+            const float bl = cok ? __ldg(pbias + col) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+            if (F.store_c) store_rows(v, pC, ldc, nbase);
+          }
+          if (epi == EPI_BN_FWD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (!rok) v[j] = 0.f;
+              stash[(c0 + j) * 128 + tid_e] = v[j];
+            }
+            // per-slab mean and sum of squared deviations (merged exactly across slabs in phase 2)
+            to_stage(v);
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) s += st[r * GEMM_EPI_PITCH + lane];   // rows >= n_w hold zeros
+            const float mw = n_w > 0 ? s / static_cast<float>(n_w) : 0.f;
+            float m2 = 0.f;
+            for (int r = 0; r < n_w; ++r) { const float d = st[r * GEMM_EPI_PITCH + lane] - mw; m2 += d * d; }
+            __syncwarp();
+            publish(c0, mw, m2);
+          } else if (epi == EPI_BN_BWD) {
+            const float cmean = cok ? __ldg(F.mean + col) : 0.f, cinv = cok ? __ldg(F.invstd + col) : 0.f;
+            const float cg = cok ? __ldg(F.gamma + col) : 0.f, cb = cok ? __ldg(F.beta + col) : 0.f;
+            float y[32];
+            load_row(F.aux, F.ld_aux, nbase, y);
+            const uint32_t bits = keep_bits(nbase);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float xh = (y[j] - __shfl_sync(0xffffffffu, cmean, j)) * __shfl_sync(0xffffffffu, cinv, j);
+              const float a = __shfl_sync(0xffffffffu, cg, j) * xh + __shfl_sync(0xffffffffu, cb, j);
+              float d = v[j];
+              if (drop_p > 0.f) d = (bits >> j & 1u) ? d * dscale : 0.f;
+              d = a > 0.f ? d : LRELU * d;
+              if (!rok || nbase + j >= pN) { d = 0.f; xh = 0.f; }
+              v[j] = d; y[j] = xh;
+              stash[(c0 + j) * 128 + tid_e] = d;
+              stash[(64 + c0 + j) * 128 + tid_e] = xh;
+            }
+            const float s1 = colsum(v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] *= v[j];
+            const float s2 = colsum(y);
+            publish(c0, s1, s2);
+          } else {   // EPI_REC
+            float x[32];
+            load_row(F.aux, F.ld_aux, nbase, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = (rok && nbase + j < pN) ? v[j] - x[j] : 0.f;
+              sq_thread += d * d;
+              v[j] = F.scale_k * d;
+            }
+            const float s1 = colsum(v);
+            publish(c0, s1, 0.f);
+            store_planes(v, nbase);
+          }
+        }
+        if (epi == EPI_REC) {
+          sq_thread = warp_sum(sq_thread);
+          if (lane == 0) F.part[tn * nslabs + slab] = sq_thread;
+        }
+      }
+      // -------- the statistics of every slab of the batch are in this CTA's shared memory
+      if (csize > 1) cluster_sync_all(); else epilogue_bar_sync();
+      // -------- phase 2
+      if (is_owner) {
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+          const int nbase = n0 + c0;
+          if (nbase >= pN) break;  // warp-uniform
+          const int col = nbase + lane;
+          const bool cok = col < pN;
+          const float* sc = stats + c0 + lane;
+          if (epi == EPI_BN_FWD) {
+            float msum = 0.f;
+            for (int k = 0; k < nslabs; ++k) {
+              const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
+              msum += static_cast<float>(nk) * sc[k * 128];
+            }
+            const float mean = msum / fM;
+            float m2 = 0.f;
+            for (int k = 0; k < nslabs; ++k) {
+              const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
+              const float d = sc[k * 128] - mean;
+              m2 += sc[k * 128 + 64] + static_cast<float>(nk) * d * d;
+            }
+            const float var = m2 / fM;
+            const float inv = 1.0f / sqrtf(var + BN_EPS);
+            if (slab == 0 && cok) {
+              F.mean[col] = mean;
+              F.invstd[col] = inv;
+              const float unb = pM > 1 ? var * (fM / (fM - 1.f)) : var;
+              F.run_mean[col] = (1.f - BN_MOM) * F.run_mean[col] + BN_MOM * mean;
+              F.run_var[col] = (1.f - BN_MOM) * F.run_var[col] + BN_MOM * unb;
+            }
+            const float g = cok ? __ldg(F.gamma + col) : 0.f, be = cok ? __ldg(F.beta + col) : 0.f;
+            const uint32_t bits = keep_bits(nbase);
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float y = stash[(c0 + j) * 128 + tid_e];
+              const float a = __shfl_sync(0xffffffffu, g, j) *
+                              ((y - __shfl_sync(0xffffffffu, mean, j)) * __shfl_sync(0xffffffffu, inv, j)) +
+                              __shfl_sync(0xffffffffu, be, j);
+              float oo = a > 0.f ? a : LRELU * a;
+              if (drop_p > 0.f) oo = (bits >> j & 1u) ? oo * dscale : 0.f;
+              o[j] = oo;
+            }
+            store_planes(o, nbase);
+          } else if (epi == EPI_BN_BWD) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int k = 0; k < nslabs; ++k) { s1 += sc[k * 128]; s2 += sc[k * 128 + 64]; }
+            if (slab == 0 && cok) {
+              if (accumulate) { F.dbeta[col] += s1; F.dgamma[col] += s2; }
+              else { F.dbeta[col] = s1; F.dgamma[col] = s2; F.dbias[col] = 0.f; }
+            }
+            const float k0 = cok ? __ldg(F.invstd + col) * __ldg(F.gamma + col) / fM : 0.f;
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float da = stash[(c0 + j) * 128 + tid_e], xh = stash[(64 + c0 + j) * 128 + tid_e];
+              o[j] = __shfl_sync(0xffffffffu, k0, j) *
+                     (fM * da - __shfl_sync(0xffffffffu, s1, j) - xh * __shfl_sync(0xffffffffu, s2, j));
+            }
+            store_planes(o, nbase);
+          } else if (slab == 0) {   // EPI_REC: bias gradient of the last decoder layer
+            float s1 = 0.f;
+            for (int k = 0; k < nslabs; ++k) s1 += sc[k * 128];
+            if (cok) F.dbias[col] = accumulate ? F.dbias[col] + s1 : s1;
+          }
+        }
+      }
+    } else if (is_owner) {
       const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
       const int rsub = lane >> 3, ch = lane & 7;  // read-back mapping: 4 rows x 8 float4 per pass
       for (int c0 = 0; c0 < bn; c0 += 32) {
@@ -424,8 +725,9 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
         __syncwarp();
       }
     }
-  } else if (ck > 1) {
-    cluster_sync_all();   // barrier B (producer and MMA warps only take part in the cluster barriers)
+  } else {   // producer and MMA warps only take part in the cluster barriers
+    if (ck > 1) cluster_sync_all();                         // barrier B
+    if (epi >= EPI_BN_FWD && csize > 1) cluster_sync_all();  // statistics exchange of the fused epilogues
   }
   tc_fence_before();
   __syncthreads();
@@ -503,21 +805,34 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->slope = slope;
   g->accumulate = accumulate;
   g->split = split;
+  g->cm = 1;
   if (split && bn > 64) return -2;   // the split epilogue keeps bn <= 64 running sums in registers
   return 0;
 }
 
+// Switches a filled problem to one of the fused training epilogues. Needs M <= 512 (at most 4 M tiles -> one cluster
+// per column block) and bn <= 64 (stash / statistics sizing). Returns 0 on success.
+inline int gemm_problem_set_fused(GemmProblem* g, int epi, const GemmFused& f) {
+  if (g->tiles_m > 4 || g->bn > 64 || epi < EPI_BN_FWD) return -3;
+  g->epi = epi;
+  g->f = f;
+  g->cm = g->tiles_m <= 1 ? 1 : (g->tiles_m == 2 ? 2 : 4);   // 3 tiles: a fourth, empty one keeps the cluster a power of two
+  return 0;
+}
+inline int gemm_problem_ctas(const GemmProblem& g, int ck) { return (g.cm > 1 ? g.cm : g.tiles_m) * g.tiles_n * ck; }
+
 // Split-K factor of a stage: the largest ck in {4, 2, 1} that keeps the launch within one wave of `sms` CTAs and leaves
 // every cluster rank at least `min_kb_per_rank` k-blocks.
 inline int gemm_pick_splitk(const GemmProblem* g, int n, int sms = 148, int min_kb_per_rank = 4) {
-  int tiles = 0, min_kb = 1 << 30;
+  int tiles = 0, min_kb = 1 << 30, cm = 1;
   for (int i = 0; i < n; ++i) {
-    tiles += g[i].tiles_m * g[i].tiles_n;
+    tiles += gemm_problem_ctas(g[i], 1);
     const int kb = (g[i].K + GEMM_BK - 1) / GEMM_BK;
     if (kb < min_kb) min_kb = kb;
+    if (g[i].cm > cm) cm = g[i].cm;
   }
   for (int ck = 4; ck > 1; ck >>= 1)
-    if (tiles * ck <= sms && min_kb >= min_kb_per_rank * ck) return ck;
+    if (cm * ck <= 8 && tiles * ck <= sms && min_kb >= min_kb_per_rank * ck) return ck;   // portable cluster size: 8
   return 1;
 }
 
@@ -526,7 +841,7 @@ inline int gemm_table_finalize(GemmProblem* g, int n, int ck = 1) {
   int base = 0;
   for (int i = 0; i < n; ++i) {
     g[i].tile_base = base;
-    base += g[i].tiles_m * g[i].tiles_n * ck;
+    base += gemm_problem_ctas(g[i], ck);
   }
   return base;
 }
@@ -535,11 +850,18 @@ inline int gemm_table_finalize(GemmProblem* g, int n, int ck = 1) {
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream.
 // total_ctas = gemm_table_finalize(..., ck). ck > 1 launches clusters of ck CTAs (split-K, see the kernel).
 // host_table: the host copy of the same table entries (tile_base of every problem), or null for a single problem.
+// ctl: the step's control block (fused training epilogues only). Every problem of a launch has the same cm.
 inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_ctas, cudaStream_t st, bool use_pdl = false,
-                               int ck = 1, const GemmProblem* host_table = nullptr) {
+                               int ck = 1, const GemmProblem* host_table = nullptr, const Ctl* ctl = nullptr) {
   if (nprobs > GEMM_MAX_PROBS || (nprobs > 1 && !host_table)) return cudaErrorInvalidValue;
   GemmBases bases{};
-  for (int i = 0; i < nprobs; ++i) bases.base[i] = host_table ? host_table[i].tile_base : 0;
+  int cm = host_table ? host_table[0].cm : 1;
+  for (int i = 0; i < nprobs; ++i) {
+    bases.base[i] = host_table ? host_table[i].tile_base : 0;
+    if (host_table && host_table[i].cm != cm) return cudaErrorInvalidValue;
+    if (host_table && host_table[i].epi >= EPI_BN_FWD && !ctl) return cudaErrorInvalidValue;
+  }
+  const int csize = cm * ck;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -559,16 +881,16 @@ inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int tot
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (ck > 1) {
+  if (csize > 1) {
     at[na].id = cudaLaunchAttributeClusterDimension;
-    at[na].val.clusterDim.x = static_cast<unsigned>(ck);
+    at[na].val.clusterDim.x = static_cast<unsigned>(csize);
     at[na].val.clusterDim.y = 1;
     at[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck, bases);
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck, bases, ctl);
 }
 
 }  // namespace jb
