@@ -79,7 +79,8 @@ struct ModActs {  // activations and gradients of one modality (device pointers,
 
 struct GemmStage {
   int first = 0, count = 0, ctas = 0;
-  int ck = 1;   // split-K factor = cluster size of the launch (gemm_tf32.cuh)
+  int ck = 1;   // split-K factor of the launch (gemm_tf32.cuh); the cluster is cm x ck CTAs
+  bool fused = false;   // BatchNorm / loss epilogue fused into this stage's GEMM
 };
 
 }  // namespace
@@ -132,7 +133,8 @@ struct jb_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
   bool use_fuse = true;      // BatchNorm / reconstruction-loss kernels fused into the GEMM epilogues for B <= 512 (JB_FUSE=0 disables)
-  bool fused = false;        // the current tables use the fused epilogues
+  int wgrad_bn = 128;        // widest N tile of the batched wgrad launch (JB_WGRAD_BN=256)
+  bool fuse_over_splitk = false;   // JB_FUSE_SPLITK=1: fuse even where the 4-tile cluster leaves no room for split-K
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
@@ -254,7 +256,7 @@ void carve(jb_engine* e, Carver& c) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>((D + 15) / 16 + ((D + 63) / 64) * 16);   // slab kernel: D/16 blocks; fused epilogue: 16 slabs per column block
+    a.rec_part = c.take<float>((D + 15) / 16 + ((D + 31) / 32) * 32);   // slab kernel: D/16 blocks; fused epilogue: 16 slabs x 2 chunks per column block
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
@@ -301,6 +303,18 @@ void close_stage(jb_engine* e, GemmStage& st, int first) {
     st.ck >>= 1;
     st.ctas = jb::gemm_table_finalize(g, st.count, st.ck);
   }
+  st.fused = g[0].epi >= jb::EPI_BN_FWD;
+  if (st.fused && !e->fuse_over_splitk && e->use_splitk) {
+    // The fused epilogue's cluster spans the M tiles of a column block; with split-K on top it may no longer fit in one
+    // wave (8-CTA clusters). Where plain split-K would have been picked and is lost, keep the stand-alone kernels.
+    std::vector<GemmProblem> plain(g, g + st.count);
+    for (auto& q : plain) jb::gemm_problem_unfuse(&q);
+    if (jb::gemm_pick_splitk(plain.data(), st.count, e->num_sms) > st.ck) {
+      for (int i = 0; i < st.count; ++i) jb::gemm_problem_unfuse(&g[i]);
+      close_stage(e, st, first);
+      return;
+    }
+  }
   if (getenv("JB_DEBUG_STAGES"))
     fprintf(stderr, "stage first %d count %d: M %d N %d K %d epi %d cm %d ck %d ctas %d\n", first, st.count, g[0].M, g[0].N, g[0].K,
             g[0].epi, g[0].cm, st.ck, st.ctas);
@@ -322,7 +336,6 @@ int build_train_tables(jb_engine* e, int B, int accum) {
     return 0;
   };
   const bool fuse = e->use_fuse && B <= 512;
-  e->fused = fuse;
   // BatchNorm layer `which` (0 enc1, 1 enc2, 2 dec1, 3 dec2) of modality i: the fields both fused epilogues share
   auto bn_layer = [&](int i, int which, jb::GemmFused& f) {
     ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -389,7 +402,9 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   //                wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass): nothing
   //                downstream of a wgrad but the optimizer, so all twelve run as ONE launch at the end of the backward pass.
   auto wgrad = [&](Planes dY, int lddy, Planes X, int ldx, const Seg& s, int n_out, int n_in) {
-    const int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : 128);   // single pass: 128-wide tiles halve the CTA count
+    // single pass: wide tiles cut the CTA count and the operand bytes per output (256-wide: the twelve wgrads of the
+    // headline shapes fit in one wave of 140 CTAs)
+    const int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
     return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, bn, jb::EPI_STORE, nullptr, accum, 0);
   };
   auto dgrad = [&](Planes dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
@@ -551,7 +566,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    if (e->fused) return;   // done by the epilogue of the GEMM just launched
+    { const int stage_of[4] = {0, 1, 3, 4}; if (e->st_f[stage_of[which]].fused) return; }   // done by the GEMM's epilogue
     if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
       launchk(r, jb::k_bn_fwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p);
     else launchk(r, jb::k_bn_fwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p);
@@ -582,7 +597,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
     const bool slab = B <= 512;
     q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + (slab ? 15 : 31)) / (slab ? 16 : 32);
   }
-  if (e->fused) {}   // reconstruction loss and its gradient: epilogue of the last decoder GEMM
+  if (e->st_f[5].fused) {}   // reconstruction loss and its gradient: epilogue of the last decoder GEMM
   else if (B <= 512) launchk(r, jb::k_rec_slab, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(jb::SLAB_THREADS), rp, B, sc.w[1], accum);
   else launchk(r, jb::k_rec, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(256), rp, B, sc.w[1], accum);
   auto bnb = [&](int which) {
@@ -604,7 +619,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    if (e->fused) return;
+    { const int stage_of[4] = {4, 3, 1, 0}; if (e->st_b[stage_of[which]].fused) return; }
     if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
       launchk(r, jb::k_bn_bwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p, accum);
     else launchk(r, jb::k_bn_bwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p, accum);
@@ -620,9 +635,9 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   fa.rowpart = e->rowpart;
   for (int i = 0; i < 2; ++i) {
     fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = (e->D[i] + (B <= 512 ? 15 : 31)) / (B <= 512 ? 16 : 32);
-    if (e->fused) {   // one partial per 32-row slab of every column block of the last decoder GEMM
+    if (e->st_f[5].fused) {   // one partial per 32-row slab and 32-column chunk of every column block of the last decoder GEMM
       const GemmProblem& gp = e->h_probs[e->st_f[5].first + i];
-      fa.rec_blocks[i] = gp.tiles_n * 4 * gp.cm;
+      fa.rec_blocks[i] = gp.tiles_n * 4 * gp.cm * 2;
     }
     fa.dmulv[i] = e->act[i].dmulv; fa.dbias_heads[i] = G + e->ms[i].bmv.off; fa.D[i] = e->D[i];
   }
@@ -854,6 +869,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
   if (const char* pv = getenv("JB_FUSE")) e->use_fuse = atoi(pv) != 0;
+  if (const char* pv = getenv("JB_FUSE_SPLITK")) e->fuse_over_splitk = atoi(pv) != 0;
+  if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
   if (const char* pv = getenv("JB_SPLITK")) e->use_splitk = atoi(pv) != 0;

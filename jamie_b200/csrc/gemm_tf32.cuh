@@ -88,6 +88,7 @@ struct GemmFused {
   float drop_p;
   float scale_k;                               // REC: w_rec * 2 / (B D)
   int store_c;                                 // also store the fp32 result C (Y / xhat)
+  int orig_epi, orig_accumulate;               // the problem's plain epilogue (gemm_problem_unfuse)
 };
 
 struct alignas(128) GemmProblem {
@@ -351,7 +352,14 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   // the last MMA has completed), so a mate may now deposit its partial tile into it.
   if (csize > 1) cluster_sync_all();
 
-  if (warp >= 2) {
+  const bool fused = epi >= EPI_BN_FWD;
+  // Fused epilogues: the finished accumulator tile is staged column-major (pitch 129: conflict-free for row-per-lane
+  // writes and column-per-lane reads) and the per-slab column statistics of the whole cluster are gathered here.
+  constexpr int STASH_PITCH = 129;
+  float* const stats = reinterpret_cast<float*>(tiles + 64 * 1024);   // [16 slabs][2][64 columns]
+  float* const stash = reinterpret_cast<float*>(tiles + 96 * 1024);   // [64 columns][STASH_PITCH]
+
+  if (warp >= 2 && warp < 6) {
     // ------------------------------------------------ epilogue warps, phase 2: TMEM -> registers -> (reduce) -> global
     const int q = warp & 3;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
@@ -404,272 +412,23 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     }
     if (ck > 1) cluster_sync_all();   // barrier B: the deposits are visible to their owners
     const bool is_owner = ck == 1 || owner == crank;
-    // this thread's row of the FINISHED tile (all split-K partials added in ascending rank order), columns [c0, c0 + 32)
-    auto final_chunk = [&](int c0, float (&v)[32]) {
-      load_chunk(c0, v);
-      for (int sl = 0; sl < ck - 1; ++sl) {
-        const float* src = reinterpret_cast<const float*>(tiles) + (sl * slabs_per_owner + ql) * slab_floats + lane * pitch + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(src + 4 * j);
-          v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-        }
-      }
-    };
-    if (epi >= EPI_BN_FWD) {
-      // ------------------------------------------------ fused training epilogues
-      const GemmFused F = P.f;
-      float* const stats = reinterpret_cast<float*>(tiles + 64 * 1024);   // [16 slabs][2][64 columns]
-      float* const stash = reinterpret_cast<float*>(tiles + 96 * 1024);   // [2 planes][64 columns][128 rows]
-      const int tid_e = q * 32 + lane;           // row inside the CTA tile
-      const int grow = m0 + tid_e;
-      const bool rok = grow < pM;
-      const int slab = tmc * 4 + q;              // 32-row slab of the batch this warp finishes (rows 32 slab ..)
-      const int nslabs = 4 * cm;
-      const int n_w = pM - (m0 + q * 32) < 0 ? 0 : (pM - (m0 + q * 32) > 32 ? 32 : pM - (m0 + q * 32));
-      const float fM = static_cast<float>(pM);
-      const float drop_p = F.drop_p;
-      const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-      const bool inject = epi != EPI_REC && ctl->inject != 0 && F.mask != nullptr;
-      const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(fminf(drop_p * 4294967296.0f, 4294967040.0f)) : 0u;
-      const uint2 key = epi != EPI_REC ? philox_key(ctl) : make_uint2(0u, 0u);
-      const int rsub = lane >> 3, ch = lane & 7;
-      // bit j: element (grow, nbase + j) is kept by the dropout; one Philox call yields 4 columns of this row
-      auto keep_bits = [&](int nbase) -> uint32_t {
-        if (!(drop_p > 0.f)) return 0xffffffffu;
-        uint32_t bits = 0u;
-        if (inject) {
-          if (rok) {
-            const unsigned char* mrow = F.mask + static_cast<long long>(grow) * F.ldm + nbase;
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < pN && mrow[j] != 0) bits |= 1u << j;
-          }
-        } else {
-#pragma unroll
-          for (int cg = 0; cg < 8; ++cg) {
-            const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(grow), static_cast<uint32_t>((nbase >> 2) + cg),
-                                                  F.layer_id, 0x4A4Eu), key);
-            bits |= (r.x >= thresh ? 1u : 0u) << (4 * cg) | (r.y >= thresh ? 1u : 0u) << (4 * cg + 1) |
-                    (r.z >= thresh ? 1u : 0u) << (4 * cg + 2) | (r.w >= thresh ? 1u : 0u) << (4 * cg + 3);
-          }
-        }
-        return bits;
-      };
-      // x[j] = element (this row, column j) -> st (transposed access), then lane = column: sum over the 32 rows
-      auto to_stage = [&](const float (&x)[32]) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        __syncwarp();
-      };
-      auto colsum = [&](const float (&x)[32]) -> float {
-        to_stage(x);
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) s += st[r * GEMM_EPI_PITCH + lane];
-        __syncwarp();
-        return s;
-      };
-      // coalesced store of this warp's 32 x 32 block (row = thread) to base[grow, nbase ..]
-      auto store_rows = [&](const float (&x)[32], float* base, int ld, int nbase) {
-        const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
-        to_stage(x);
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rsub;
-          const int gr = m0 + q * 32 + r;
-          const int n = nbase + ch * 4;
-          const float4 xx = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
-          if (gr < pM && n < pN) {
-            float* dst = base + static_cast<size_t>(gr) * ld + n;
-            if (vec && n + 4 <= pN) *reinterpret_cast<float4*>(dst) = xx;
-            else {
-              const float xs[4] = {xx.x, xx.y, xx.z, xx.w};
-              for (int j = 0; j < 4; ++j) if (n + j < pN) dst[j] = xs[j];
-            }
-          }
-        }
-        __syncwarp();
-      };
-      auto store_planes = [&](float (&x)[32], int nbase) {   // x -> hi / lo planes; x is destroyed
-        float h[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = tf32_rna(x[j]);
-        store_rows(h, F.out_hi, F.ld_out, nbase);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = tf32_rna(x[j] - h[j]);
-        store_rows(h, F.out_lo, F.ld_out, nbase);
-      };
-      // this row of an fp32 [M, ld] matrix, columns [nbase, nbase + 32) (zeros outside the matrix)
-      auto load_row = [&](const float* base, int ld, int nbase, float (&x)[32]) {
-        const float* src = base + static_cast<long long>(rok ? grow : 0) * ld + nbase;
-        if (rok && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && nbase + 32 <= pN) {
+    if (is_owner && fused) {
+      // fused epilogues, phase 0: the finished tile (all split-K partials added in ascending rank order) -> stash
+      const int tid_e = q * 32 + lane;
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        if (n0 + c0 >= pN) break;  // warp-uniform
+        float v[32];
+        load_chunk(c0, v);
+        for (int sl = 0; sl < ck - 1; ++sl) {
+          const float* src = reinterpret_cast<const float*>(tiles) + (sl * slabs_per_owner + ql) * slab_floats + lane * pitch + c0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(src) + j);
-            x[4 * j] = t4.x; x[4 * j + 1] = t4.y; x[4 * j + 2] = t4.z; x[4 * j + 3] = t4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (rok && nbase + j < pN) ? __ldg(src + j) : 0.f;
-        }
-      };
-      // all-gather of this slab's two per-column statistics into every CTA of the cluster
-      auto publish = [&](int c0, float a, float b) {
-        float* loc = stats + slab * 128 + c0 + lane;
-        if (csize == 1) { loc[0] = a; loc[64] = b; }
-        else {
-          const uint32_t la = smem_u32(loc);
-          for (int rr = 0; rr < csize; ++rr) {
-            const uint32_t ra = mapa_shared(la, static_cast<uint32_t>(rr));
-            st_shared_cluster_f32(ra, a);
-            st_shared_cluster_f32(ra + 256u, b);
+            const float4 x = *reinterpret_cast<const float4*>(src + 4 * j);
+            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
           }
         }
-      };
-
-      // -------- phase 1: finish the tile, local statistics, stash what phase 2 needs
-      float sq_thread = 0.f;
-      if (is_owner) {
-        for (int c0 = 0; c0 < bn; c0 += 32) {
-          const int nbase = n0 + c0;
-          if (nbase >= pN) break;  // warp-uniform
-          const int col = nbase + lane;
-          const bool cok = col < pN;
-          float v[32];
-          final_chunk(c0, v);
-          if (epi != EPI_BN_BWD) {
-            const float bl = cok ? __ldg(pbias + col) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
-            if (F.store_c) store_rows(v, pC, ldc, nbase);
-          }
-          if (epi == EPI_BN_FWD) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (!rok) v[j] = 0.f;
-              stash[(c0 + j) * 128 + tid_e] = v[j];
-            }
-            // per-slab mean and sum of squared deviations (merged exactly across slabs in phase 2)
-            to_stage(v);
-            float s = 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) s += st[r * GEMM_EPI_PITCH + lane];   // rows >= n_w hold zeros
-            const float mw = n_w > 0 ? s / static_cast<float>(n_w) : 0.f;
-            float m2 = 0.f;
-            for (int r = 0; r < n_w; ++r) { const float d = st[r * GEMM_EPI_PITCH + lane] - mw; m2 += d * d; }
-            __syncwarp();
-            publish(c0, mw, m2);
-          } else if (epi == EPI_BN_BWD) {
-            const float cmean = cok ? __ldg(F.mean + col) : 0.f, cinv = cok ? __ldg(F.invstd + col) : 0.f;
-            const float cg = cok ? __ldg(F.gamma + col) : 0.f, cb = cok ? __ldg(F.beta + col) : 0.f;
-            float y[32];
-            load_row(F.aux, F.ld_aux, nbase, y);
-            const uint32_t bits = keep_bits(nbase);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float xh = (y[j] - __shfl_sync(0xffffffffu, cmean, j)) * __shfl_sync(0xffffffffu, cinv, j);
-              const float a = __shfl_sync(0xffffffffu, cg, j) * xh + __shfl_sync(0xffffffffu, cb, j);
-              float d = v[j];
-              if (drop_p > 0.f) d = (bits >> j & 1u) ? d * dscale : 0.f;
-              d = a > 0.f ? d : LRELU * d;
-              if (!rok || nbase + j >= pN) { d = 0.f; xh = 0.f; }
-              v[j] = d; y[j] = xh;
-              stash[(c0 + j) * 128 + tid_e] = d;
-              stash[(64 + c0 + j) * 128 + tid_e] = xh;
-            }
-            const float s1 = colsum(v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] *= v[j];
-            const float s2 = colsum(y);
-            publish(c0, s1, s2);
-          } else {   // EPI_REC
-            float x[32];
-            load_row(F.aux, F.ld_aux, nbase, x);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float d = (rok && nbase + j < pN) ? v[j] - x[j] : 0.f;
-              sq_thread += d * d;
-              v[j] = F.scale_k * d;
-            }
-            const float s1 = colsum(v);
-            publish(c0, s1, 0.f);
-            store_planes(v, nbase);
-          }
-        }
-        if (epi == EPI_REC) {
-          sq_thread = warp_sum(sq_thread);
-          if (lane == 0) F.part[tn * nslabs + slab] = sq_thread;
-        }
-      }
-      // -------- the statistics of every slab of the batch are in this CTA's shared memory
-      if (csize > 1) cluster_sync_all(); else epilogue_bar_sync();
-      // -------- phase 2
-      if (is_owner) {
-        for (int c0 = 0; c0 < bn; c0 += 32) {
-          const int nbase = n0 + c0;
-          if (nbase >= pN) break;  // warp-uniform
-          const int col = nbase + lane;
-          const bool cok = col < pN;
-          const float* sc = stats + c0 + lane;
-          if (epi == EPI_BN_FWD) {
-            float msum = 0.f;
-            for (int k = 0; k < nslabs; ++k) {
-              const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
-              msum += static_cast<float>(nk) * sc[k * 128];
-            }
-            const float mean = msum / fM;
-            float m2 = 0.f;
-            for (int k = 0; k < nslabs; ++k) {
-              const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
-              const float d = sc[k * 128] - mean;
-              m2 += sc[k * 128 + 64] + static_cast<float>(nk) * d * d;
-            }
-            const float var = m2 / fM;
-            const float inv = 1.0f / sqrtf(var + BN_EPS);
-            if (slab == 0 && cok) {
-              F.mean[col] = mean;
-              F.invstd[col] = inv;
-              const float unb = pM > 1 ? var * (fM / (fM - 1.f)) : var;
-              F.run_mean[col] = (1.f - BN_MOM) * F.run_mean[col] + BN_MOM * mean;
-              F.run_var[col] = (1.f - BN_MOM) * F.run_var[col] + BN_MOM * unb;
-            }
-            const float g = cok ? __ldg(F.gamma + col) : 0.f, be = cok ? __ldg(F.beta + col) : 0.f;
-            const uint32_t bits = keep_bits(nbase);
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float y = stash[(c0 + j) * 128 + tid_e];
-              const float a = __shfl_sync(0xffffffffu, g, j) *
-                              ((y - __shfl_sync(0xffffffffu, mean, j)) * __shfl_sync(0xffffffffu, inv, j)) +
-                              __shfl_sync(0xffffffffu, be, j);
-              float oo = a > 0.f ? a : LRELU * a;
-              if (drop_p > 0.f) oo = (bits >> j & 1u) ? oo * dscale : 0.f;
-              o[j] = oo;
-            }
-            store_planes(o, nbase);
-          } else if (epi == EPI_BN_BWD) {
-            float s1 = 0.f, s2 = 0.f;
-            for (int k = 0; k < nslabs; ++k) { s1 += sc[k * 128]; s2 += sc[k * 128 + 64]; }
-            if (slab == 0 && cok) {
-              if (accumulate) { F.dbeta[col] += s1; F.dgamma[col] += s2; }
-              else { F.dbeta[col] = s1; F.dgamma[col] = s2; F.dbias[col] = 0.f; }
-            }
-            const float k0 = cok ? __ldg(F.invstd + col) * __ldg(F.gamma + col) / fM : 0.f;
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float da = stash[(c0 + j) * 128 + tid_e], xh = stash[(64 + c0 + j) * 128 + tid_e];
-              o[j] = __shfl_sync(0xffffffffu, k0, j) *
-                     (fM * da - __shfl_sync(0xffffffffu, s1, j) - xh * __shfl_sync(0xffffffffu, s2, j));
-            }
-            store_planes(o, nbase);
-          } else if (slab == 0) {   // EPI_REC: bias gradient of the last decoder layer
-            float s1 = 0.f;
-            for (int k = 0; k < nslabs; ++k) s1 += sc[k * 128];
-            if (cok) F.dbias[col] = accumulate ? F.dbias[col] + s1 : s1;
-          }
-        }
+        for (int j = 0; j < 32; ++j) stash[(c0 + j) * STASH_PITCH + tid_e] = v[j];
       }
     } else if (is_owner) {
       const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
@@ -725,9 +484,205 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
         __syncwarp();
       }
     }
-  } else {   // producer and MMA warps only take part in the cluster barriers
+  } else {   // the other warps only take part in the cluster barrier
     if (ck > 1) cluster_sync_all();                         // barrier B
-    if (epi >= EPI_BN_FWD && csize > 1) cluster_sync_all();  // statistics exchange of the fused epilogues
+  }
+
+  if (fused) {
+    // ------------------------------------------------ fused training epilogues: all 8 warps, thread = one column of one
+    // 32-row slab (warp & 3 = slab of the tile, warp >> 2 = 32-column chunk), so per-column quantities are scalars and
+    // every global access is coalesced along the row.
+    __syncthreads();   // the stash is complete
+    const GemmFused F = P.f;
+    const int hs = warp & 3, hc = warp >> 2;
+    const int c0 = hc * 32;
+    const int nbase = n0 + c0;
+    const bool own = ck == 1 || ((hs * ck) >> 2) == crank;
+    const bool work = own && c0 < bn && nbase < pN;          // warp-uniform
+    const int col = nbase + lane;
+    const bool cok = work && col < pN;
+    const int slab = tmc * 4 + hs;                           // 32-row slab of the batch
+    const int nslabs = 4 * cm;
+    const int row0 = m0 + hs * 32;
+    const int n_w = pM - row0 < 0 ? 0 : (pM - row0 > 32 ? 32 : pM - row0);
+    const float fM = static_cast<float>(pM);
+    const float drop_p = F.drop_p;
+    const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const bool bn_epi = epi != EPI_REC;
+    const bool inject = bn_epi && ctl->inject != 0 && F.mask != nullptr;
+    const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(fminf(drop_p * 4294967296.0f, 4294967040.0f)) : 0u;
+    const uint2 key = bn_epi ? philox_key(ctl) : make_uint2(0u, 0u);
+    const float* sp = stash + (c0 + lane) * STASH_PITCH + hs * 32;   // this thread's column, rows of its slab
+    float* sc = stats + c0 + lane;
+    // keep decisions of rows 4 g .. 4 g + 3 of this column: same Philox stream as the stand-alone slab kernels
+    auto keep4 = [&](int g, bool (&keep)[4]) {
+      if (!(drop_p > 0.f)) { keep[0] = keep[1] = keep[2] = keep[3] = true; return; }
+      if (inject) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = 4 * g + k;
+          keep[k] = cok && r < n_w && F.mask[static_cast<long long>(row0 + r) * F.ldm + col] != 0;
+        }
+      } else {
+        const uint4 rnd = rand4(key, F.layer_id, col, (row0 >> 2) + g);
+        keep[0] = rnd.x >= thresh; keep[1] = rnd.y >= thresh; keep[2] = rnd.z >= thresh; keep[3] = rnd.w >= thresh;
+      }
+    };
+    // all-gather of this slab's two per-column statistics into every CTA of the cluster
+    auto publish = [&](float a, float b) {
+      float* loc = sc + slab * 128;
+      if (csize == 1) { loc[0] = a; loc[64] = b; }
+      else {
+        const uint32_t la = smem_u32(loc);
+        for (int rr = 0; rr < csize; ++rr) {
+          const uint32_t ra = mapa_shared(la, static_cast<uint32_t>(rr));
+          st_shared_cluster_f32(ra, a);
+          st_shared_cluster_f32(ra + 256u, b);
+        }
+      }
+    };
+    float val[32];   // BN_FWD: y;  BN_BWD: d loss / d (BatchNorm output)
+    float xh[32];    // BN_BWD: normalised pre-activation
+    // -------- phase 1: local statistics of the slab
+    if (work) {
+      if (epi == EPI_BN_FWD) {
+        const float bl = cok ? __ldg(pbias + col) : 0.f;
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float y = r < n_w ? sp[r] + bl : 0.f;
+          val[r] = y;
+          s += y;
+        }
+        // per-slab mean and sum of squared deviations (merged exactly across slabs in phase 2)
+        const float mw = n_w > 0 ? s / static_cast<float>(n_w) : 0.f;
+        float m2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) { const float d = val[r] - mw; m2 += r < n_w ? d * d : 0.f; }
+        publish(mw, m2);
+      } else if (epi == EPI_BN_BWD) {
+        const float cmean = cok ? __ldg(F.mean + col) : 0.f, cinv = cok ? __ldg(F.invstd + col) : 0.f;
+        const float cg = cok ? __ldg(F.gamma + col) : 0.f, cb = cok ? __ldg(F.beta + col) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          xh[r] = (cok && r < n_w) ? __ldg(F.aux + static_cast<long long>(row0 + r) * F.ld_aux + col) : cmean;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          bool keep[4];
+          keep4(g, keep);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = 4 * g + k;
+            const float h = (xh[r] - cmean) * cinv;
+            const float a = cg * h + cb;
+            float d = sp[r];
+            if (drop_p > 0.f) d = keep[k] ? d * dscale : 0.f;
+            d = a > 0.f ? d : LRELU * d;
+            if (!(cok && r < n_w)) d = 0.f;
+            val[r] = d; xh[r] = h;
+            s1 += d; s2 += d * h;
+          }
+        }
+        publish(s1, s2);
+      } else {   // EPI_REC
+        const float bl = cok ? __ldg(pbias + col) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          xh[r] = (cok && r < n_w) ? __ldg(F.aux + static_cast<long long>(row0 + r) * F.ld_aux + col) : 0.f;
+        float s1 = 0.f, sq = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const bool ok = cok && r < n_w;
+          const float xo = sp[r] + bl;
+          const float d = ok ? xo - xh[r] : 0.f;
+          sq += d * d;
+          const float gx = F.scale_k * d;
+          s1 += gx;
+          if (ok) {
+            const long long row = row0 + r;
+            if (F.store_c) pC[row * ldc + col] = xo;
+            const float hi = tf32_rna(gx);
+            F.out_hi[row * F.ld_out + col] = hi;
+            F.out_lo[row * F.ld_out + col] = tf32_rna(gx - hi);
+          }
+        }
+        publish(s1, 0.f);
+        sq = warp_sum(sq);
+        if (lane == 0) F.part[(tn * nslabs + slab) * 2 + hc] = sq;
+      }
+    }
+    // -------- the statistics of every slab of the batch are in this CTA's shared memory
+    if (csize > 1) cluster_sync_all(); else __syncthreads();
+    // -------- phase 2
+    if (work) {
+      if (epi == EPI_BN_FWD) {
+        float msum = 0.f;
+        for (int k = 0; k < nslabs; ++k) {
+          const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
+          msum += static_cast<float>(nk) * sc[k * 128];
+        }
+        const float mean = msum / fM;
+        float m2 = 0.f;
+        for (int k = 0; k < nslabs; ++k) {
+          const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
+          const float d = sc[k * 128] - mean;
+          m2 += sc[k * 128 + 64] + static_cast<float>(nk) * d * d;
+        }
+        const float var = m2 / fM;
+        const float inv = 1.0f / sqrtf(var + BN_EPS);
+        if (slab == 0 && cok) {
+          F.mean[col] = mean;
+          F.invstd[col] = inv;
+          const float unb = pM > 1 ? var * (fM / (fM - 1.f)) : var;
+          F.run_mean[col] = (1.f - BN_MOM) * F.run_mean[col] + BN_MOM * mean;
+          F.run_var[col] = (1.f - BN_MOM) * F.run_var[col] + BN_MOM * unb;
+        }
+        const float g = cok ? __ldg(F.gamma + col) : 0.f, be = cok ? __ldg(F.beta + col) : 0.f;
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) {
+          bool keep[4];
+          keep4(gq, keep);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = 4 * gq + k;
+            const float y = val[r];
+            const float a = g * ((y - mean) * inv) + be;
+            float o = a > 0.f ? a : LRELU * a;
+            if (drop_p > 0.f) o = keep[k] ? o * dscale : 0.f;
+            if (cok && r < n_w) {
+              const long long row = row0 + r;
+              if (F.store_c) pC[row * ldc + col] = y;
+              const float hi = tf32_rna(o);
+              F.out_hi[row * F.ld_out + col] = hi;
+              F.out_lo[row * F.ld_out + col] = tf32_rna(o - hi);
+            }
+          }
+        }
+      } else if (epi == EPI_BN_BWD) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k < nslabs; ++k) { s1 += sc[k * 128]; s2 += sc[k * 128 + 64]; }
+        if (slab == 0 && cok) {
+          if (accumulate) { F.dbeta[col] += s1; F.dgamma[col] += s2; }
+          else { F.dbeta[col] = s1; F.dgamma[col] = s2; F.dbias[col] = 0.f; }
+        }
+        const float k0 = cok ? __ldg(F.invstd + col) * __ldg(F.gamma + col) / fM : 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          if (cok && r < n_w) {
+            const long long row = row0 + r;
+            const float dy = k0 * (fM * val[r] - s1 - xh[r] * s2);
+            const float hi = tf32_rna(dy);
+            F.out_hi[row * F.ld_out + col] = hi;
+            F.out_lo[row * F.ld_out + col] = tf32_rna(dy - hi);
+          }
+        }
+      } else if (slab == 0) {   // EPI_REC: bias gradient of the last decoder layer
+        float s1 = 0.f;
+        for (int k = 0; k < nslabs; ++k) s1 += sc[k * 128];
+        if (cok) F.dbias[col] = accumulate ? F.dbias[col] + s1 : s1;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -814,10 +769,16 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
 // per column block) and bn <= 64 (stash / statistics sizing). Returns 0 on success.
 inline int gemm_problem_set_fused(GemmProblem* g, int epi, const GemmFused& f) {
   if (g->tiles_m > 4 || g->bn > 64 || epi < EPI_BN_FWD) return -3;
+  const int oe = g->epi, oa = g->accumulate;
   g->epi = epi;
   g->f = f;
+  g->f.orig_epi = oe; g->f.orig_accumulate = oa;
   g->cm = g->tiles_m <= 1 ? 1 : (g->tiles_m == 2 ? 2 : 4);   // 3 tiles: a fourth, empty one keeps the cluster a power of two
   return 0;
+}
+inline void gemm_problem_unfuse(GemmProblem* g) {
+  if (g->epi < EPI_BN_FWD) return;
+  g->epi = g->f.orig_epi; g->accumulate = g->f.orig_accumulate; g->cm = 1;
 }
 inline int gemm_problem_ctas(const GemmProblem& g, int ck) { return (g.cm > 1 ? g.cm : g.tiles_m) * g.tiles_n * ck; }
 

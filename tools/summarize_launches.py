@@ -1,4 +1,4 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list into one training step (k_begin .. k_end).
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list into one training step (k_gather .. k_adam).
 Usage: python tools/summarize_launches.py gpurun_out/launches.csv > profiles/launches_rNN.md"""
 import csv
 import sys
@@ -17,11 +17,11 @@ def main(path):
         if len(row) > vi and row[ni] == 'gpu__time_duration.sum':
             name = row[ki].replace('void ', '').split('(')[0].replace('jb::', '')
             seq.append((name, float(row[vi].replace(',', '')) / 1000.0, row[gi], row[bi]))
-    starts = [i for i, s in enumerate(seq) if 'k_begin' in s[0]]
+    starts = [i for i, s in enumerate(seq) if 'k_gather' in s[0] or 'k_begin' in s[0]]
     if len(starts) < 2:
         print('no complete step found')
         return
-    s, e = starts[0], starts[1]
+    s, e = starts[-2], starts[-1]   # a late, warm step
     step = seq[s:e]
     tot = sum(x[1] for x in step)
     print(f'# One optimizer step, kernel by kernel ({path})\n')
