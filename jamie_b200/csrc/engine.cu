@@ -79,8 +79,7 @@ struct ModActs {  // activations and gradients of one modality (device pointers,
 
 struct GemmStage {
   int first = 0, count = 0, ctas = 0;
-  int ck = 1;   // split-K factor of the launch (gemm_tf32.cuh); the cluster is cm x ck CTAs
-  bool fused = false;   // BatchNorm / loss epilogue fused into this stage's GEMM
+  int ck = 1;   // split-K factor = cluster size of the launch (gemm_tf32.cuh)
 };
 
 }  // namespace
@@ -132,9 +131,7 @@ struct jb_engine {
   cudaStream_t cap_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
-  bool use_fuse = true;      // BatchNorm / reconstruction-loss kernels fused into the GEMM epilogues for B <= 512 (JB_FUSE=0 disables)
-  int wgrad_bn = 128;        // widest N tile of the batched wgrad launch (JB_WGRAD_BN=256)
-  bool fuse_over_splitk = false;   // JB_FUSE_SPLITK=1: fuse even where the 4-tile cluster leaves no room for split-K
+  int wgrad_bn = 256;        // widest N tile of the batched wgrad launch
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
@@ -256,7 +253,7 @@ void carve(jb_engine* e, Carver& c) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>((D + 15) / 16 + ((D + 31) / 32) * 32);   // slab kernel: D/16 blocks; fused epilogue: 16 slabs x 2 chunks per column block
+    a.rec_part = c.take<float>((D + 15) / 16);
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
@@ -286,38 +283,8 @@ int choose_bn(int N) {
 void close_stage(jb_engine* e, GemmStage& st, int first) {
   st.first = first;
   st.count = static_cast<int>(e->h_probs.size()) - first;
-  GemmProblem* g = e->h_probs.data() + first;
-  st.ck = e->use_splitk ? jb::gemm_pick_splitk(g, st.count, e->num_sms) : 1;
-  st.ctas = jb::gemm_table_finalize(g, st.count, st.ck);
-  // a cluster launch that cannot be co-scheduled in one wave loses more than split-K gains: halve ck until it fits
-  while (st.ck > 1 && g[0].cm * st.ck > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(st.ctas); cfg.blockDim = dim3(jb::GEMM_THREADS); cfg.dynamicSmemBytes = jb::GEMM_SMEM_BYTES;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = static_cast<unsigned>(g[0].cm * st.ck); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, jb::gemm_tf32_grouped_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); break; }
-    if (nclusters * g[0].cm * st.ck >= st.ctas) break;
-    st.ck >>= 1;
-    st.ctas = jb::gemm_table_finalize(g, st.count, st.ck);
-  }
-  st.fused = g[0].epi >= jb::EPI_BN_FWD;
-  if (st.fused && !e->fuse_over_splitk && e->use_splitk) {
-    // The fused epilogue's cluster spans the M tiles of a column block; with split-K on top it may no longer fit in one
-    // wave (8-CTA clusters). Where plain split-K would have been picked and is lost, keep the stand-alone kernels.
-    std::vector<GemmProblem> plain(g, g + st.count);
-    for (auto& q : plain) jb::gemm_problem_unfuse(&q);
-    if (jb::gemm_pick_splitk(plain.data(), st.count, e->num_sms) > st.ck) {
-      for (int i = 0; i < st.count; ++i) jb::gemm_problem_unfuse(&g[i]);
-      close_stage(e, st, first);
-      return;
-    }
-  }
-  if (getenv("JB_DEBUG_STAGES"))
-    fprintf(stderr, "stage first %d count %d: M %d N %d K %d epi %d cm %d ck %d ctas %d\n", first, st.count, g[0].M, g[0].N, g[0].K,
-            g[0].epi, g[0].cm, st.ck, st.ctas);
+  st.ck = e->use_splitk ? jb::gemm_pick_splitk(e->h_probs.data() + first, st.count, e->num_sms) : 1;
+  st.ctas = jb::gemm_table_finalize(e->h_probs.data() + first, st.count, st.ck);
 }
 
 int build_train_tables(jb_engine* e, int B, int accum) {
@@ -335,75 +302,29 @@ int build_train_tables(jb_engine* e, int B, int accum) {
     close_stage(e, st, f0);
     return 0;
   };
-  const bool fuse = e->use_fuse && B <= 512;
-  // BatchNorm layer `which` (0 enc1, 1 enc2, 2 dec1, 3 dec2) of modality i: the fields both fused epilogues share
-  auto bn_layer = [&](int i, int which, jb::GemmFused& f) {
-    ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    const int bnidx = which < 2 ? (2 * i + which) : (4 + 2 * i + (which - 2));
-    const Seg* gs[4] = {&m.g1, &m.g2, &m.g3, &m.g4};
-    const Seg* es[4] = {&m.be1, &m.be2, &m.be3, &m.be4};
-    const Seg* bs[4] = {&m.b1, &m.b2, &m.b3, &m.b4};
-    const int N = (which == 0 || which == 3) ? 2 * D : D;
-    f.gamma = T + gs[which]->off; f.beta = T + es[which]->off;
-    f.mean = a.bn_mean[which]; f.invstd = a.bn_inv[which];
-    f.run_mean = e->bn_run + e->bn_off[bnidx]; f.run_var = f.run_mean + e->bn_w[bnidx];
-    f.dgamma = G + gs[which]->off; f.dbeta = G + es[which]->off; f.dbias = G + bs[which]->off;
-    f.mask = a.inj_mask[which]; f.ldm = N; f.layer_id = static_cast<unsigned>(bnidx); f.drop_p = e->cfg.dropout;
-  };
-  auto fuse_fwd = [&](int i, int which) {   // the forward GEMM just added feeds BatchNorm layer `which`
-    if (!fuse) return 0;
-    ModActs& a = e->act[i];
-    jb::GemmFused f{};
-    bn_layer(i, which, f);
-    Planes H[4] = {a.h1, a.h2, a.g1, a.g2};
-    const int ld[4] = {a.ld2D, a.ldD, a.ldD, a.ld2D};
-    f.out_hi = H[which].hi; f.out_lo = H[which].lo; f.ld_out = ld[which]; f.store_c = 1;
-    if (jb::gemm_problem_set_fused(&e->h_probs.back(), jb::EPI_BN_FWD, f)) return fail("fused BatchNorm epilogue: unsupported tile shape");
-    return 0;
-  };
-  auto fuse_bwd = [&](int i, int which) {   // the dgrad just added produces dH of BatchNorm layer `which`
-    if (!fuse) return 0;
-    ModActs& a = e->act[i];
-    jb::GemmFused f{};
-    bn_layer(i, which, f);
-    Planes dY[4] = {a.dy1, a.dy2, a.dy3, a.dy4};
-    const float* Y[4] = {a.y1, a.y2, a.y3, a.y4};
-    const int ld[4] = {a.ld2D, a.ldD, a.ldD, a.ld2D};
-    f.out_hi = dY[which].hi; f.out_lo = dY[which].lo; f.ld_out = ld[which]; f.aux = Y[which]; f.ld_aux = ld[which];
-    if (jb::gemm_problem_set_fused(&e->h_probs.back(), jb::EPI_BN_BWD, f)) return fail("fused BatchNorm epilogue: unsupported tile shape");
-    e->h_probs.back().accumulate = accum;
-    return 0;
-  };
   auto lin = [&](Planes X, int ldx, const Seg& w, const Seg& b, float* Y, int ldy, int n_out, int n_in) {
     return add_prob(e, X, ldx, 0, W(w), w.ld, 0, Y, ldy, B, n_out, n_in, choose_bn(n_out), jb::EPI_BIAS, bias(b), 0, 1);
   };
   if (fwd(e->st_f[0], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.xp, a.ldD, m.W1, m.b1, a.y1, a.ld2D, 2 * D, D) || fuse_fwd(i, 0); })) return 1;
+        return lin(a.xp, a.ldD, m.W1, m.b1, a.y1, a.ld2D, 2 * D, D); })) return 1;
   if (fwd(e->st_f[1], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.h1, a.ld2D, m.W2, m.b2, a.y2, a.ldD, D, 2 * D) || fuse_fwd(i, 1); })) return 1;
+        return lin(a.h1, a.ld2D, m.W2, m.b2, a.y2, a.ldD, D, 2 * D); })) return 1;
   if (fwd(e->st_f[2], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
         return lin(a.h2, a.ldD, m.Wmv, m.bmv, a.mulv, a.ldmv, 2 * L, D); })) return 1;
   if (fwd(e->st_f[3], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.cp, a.LP, m.W3, m.b3, a.y3, a.ldD, D, L) || fuse_fwd(i, 2); })) return 1;
+        return lin(a.cp, a.LP, m.W3, m.b3, a.y3, a.ldD, D, L); })) return 1;
   if (fwd(e->st_f[4], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D) || fuse_fwd(i, 3); })) return 1;
+        return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D); })) return 1;
   if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        if (lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D)) return 1;
-        if (!fuse) return 0;
-        jb::GemmFused f{};   // reconstruction loss, d loss / d xhat and the bias gradient in the epilogue
-        f.out_hi = a.dxhat.hi; f.out_lo = a.dxhat.lo; f.ld_out = a.ldD; f.aux = a.x; f.ld_aux = a.ldD;
-        f.dbias = G + m.b5.off; f.part = a.rec_part; f.store_c = 1;
-        f.scale_k = e->cfg.loss_w[1] * 2.f / (static_cast<float>(B) * static_cast<float>(D));
-        if (jb::gemm_problem_set_fused(&e->h_probs.back(), jb::EPI_REC, f)) return fail("fused reconstruction epilogue: unsupported tile shape");
-        e->h_probs.back().accumulate = accum;
-        return 0; })) return 1;
+        return lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D); })) return 1;
   // ---- backward: dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out): one stage
   //                per layer on the critical path;
   //                wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass): nothing
   //                downstream of a wgrad but the optimizer, so all twelve run as ONE launch at the end of the backward pass.
   auto wgrad = [&](Planes dY, int lddy, Planes X, int ldx, const Seg& s, int n_out, int n_in) {
-    // single pass: wide tiles cut the CTA count and the operand bytes per output (256-wide: the twelve wgrads of the
-    // headline shapes fit in one wave of 140 CTAs)
+    // single pass: wide tiles cut the CTA count and the operand bytes per output; with 256-wide tiles the twelve wgrads
+    // of the headline shapes are ONE wave of 140 CTAs instead of 272 CTAs in two (profiles/README.md; JB_WGRAD_BN=128
+    // restores the narrower tiles)
     const int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
     return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, bn, jb::EPI_STORE, nullptr, accum, 0);
   };
@@ -412,11 +333,11 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   };
   int first = static_cast<int>(e->h_probs.size());   // B6: last decoder Linear(2D -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, D, 2 * D) || fuse_bwd(i, 3)) return 1; }
+    if (dgrad(a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, D, 2 * D)) return 1; }
   close_stage(e, e->st_b[0], first);
   first = static_cast<int>(e->h_probs.size());       // B5: decoder Linear(D -> 2D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 2 * D, D) || fuse_bwd(i, 2)) return 1; }
+    if (dgrad(a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 2 * D, D)) return 1; }
   close_stage(e, e->st_b[1], first);
   first = static_cast<int>(e->h_probs.size());       // B4: decoder Linear(L -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -424,11 +345,11 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   close_stage(e, e->st_b[2], first);
   first = static_cast<int>(e->h_probs.size());       // B3: heads Linear(D -> 2L)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D) || fuse_bwd(i, 1)) return 1; }
+    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
   close_stage(e, e->st_b[3], first);
   first = static_cast<int>(e->h_probs.size());       // B2: encoder Linear(2D -> D); Linear(D -> 2D) needs no input gradient
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D) || fuse_bwd(i, 0)) return 1; }
+    if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
   close_stage(e, e->st_b[4], first);
   first = static_cast<int>(e->h_probs.size());       // all weight gradients (largest problems first)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -462,7 +383,7 @@ struct Rec {  // launches kernels on a stream and counts them
   }
   void gemm(const GemmStage& st) {
     if (err == cudaSuccess)
-      err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl, st.ck, e->h_probs.data() + st.first, e->ctl);
+      err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl, st.ck, e->h_probs.data() + st.first);
     mark("gemm");
     ++n;
   }
@@ -566,7 +487,6 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    { const int stage_of[4] = {0, 1, 3, 4}; if (e->st_f[stage_of[which]].fused) return; }   // done by the GEMM's epilogue
     if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
       launchk(r, jb::k_bn_fwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p);
     else launchk(r, jb::k_bn_fwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p);
@@ -597,8 +517,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
     const bool slab = B <= 512;
     q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + (slab ? 15 : 31)) / (slab ? 16 : 32);
   }
-  if (e->st_f[5].fused) {}   // reconstruction loss and its gradient: epilogue of the last decoder GEMM
-  else if (B <= 512) launchk(r, jb::k_rec_slab, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(jb::SLAB_THREADS), rp, B, sc.w[1], accum);
+  if (B <= 512) launchk(r, jb::k_rec_slab, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(jb::SLAB_THREADS), rp, B, sc.w[1], accum);
   else launchk(r, jb::k_rec, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(256), rp, B, sc.w[1], accum);
   auto bnb = [&](int which) {
     jb::BnBwdPair pr{};
@@ -619,7 +538,6 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    { const int stage_of[4] = {4, 3, 1, 0}; if (e->st_b[stage_of[which]].fused) return; }
     if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
       launchk(r, jb::k_bn_bwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p, accum);
     else launchk(r, jb::k_bn_bwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p, accum);
@@ -635,10 +553,6 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   fa.rowpart = e->rowpart;
   for (int i = 0; i < 2; ++i) {
     fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = (e->D[i] + (B <= 512 ? 15 : 31)) / (B <= 512 ? 16 : 32);
-    if (e->st_f[5].fused) {   // one partial per 32-row slab and 32-column chunk of every column block of the last decoder GEMM
-      const GemmProblem& gp = e->h_probs[e->st_f[5].first + i];
-      fa.rec_blocks[i] = gp.tiles_n * 4 * gp.cm * 2;
-    }
     fa.dmulv[i] = e->act[i].dmulv; fa.dbias_heads[i] = G + e->ms[i].bmv.off; fa.D[i] = e->D[i];
   }
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
@@ -868,8 +782,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_FUSE")) e->use_fuse = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_FUSE_SPLITK")) e->fuse_over_splitk = atoi(pv) != 0;
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
@@ -1212,9 +1124,9 @@ int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* fl
     fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first, e->ctl));
+  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first));
   CU(cudaEventRecord(a, s));
-  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first, e->ctl));
+  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first));
   CU(cudaEventRecord(b, s));
   CU(cudaEventSynchronize(b));
   float ms = 0;

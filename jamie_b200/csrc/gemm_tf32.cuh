@@ -46,7 +46,6 @@
 #include <cstdint>
 #include <cstdio>
 #include "ptx.cuh"
-#include "kernels.cuh"
 
 namespace jb {
 
@@ -67,28 +66,6 @@ enum GemmEpilogue : int {
   EPI_STORE = 0,       // C = acc
   EPI_BIAS = 1,        // C = acc + bias[n]
   EPI_BIAS_LRELU = 2,  // C = leaky_relu(acc + bias[n], slope)      (inference, BatchNorm folded)
-  // Fused training epilogues (B <= 512: the M tiles of one column block form a thread-block cluster that exchanges
-  // per-column statistics through distributed shared memory, so BatchNorm needs no kernel of its own):
-  EPI_BN_FWD = 3,      // Y = acc + bias -> BatchNorm (batch stats, running-stat update) -> LeakyReLU -> Dropout -> hi / lo planes
-  EPI_BN_BWD = 4,      // dH = acc -> through Dropout, LeakyReLU, BatchNorm -> dY hi / lo planes, dgamma, dbeta
-  EPI_REC = 5,         // xhat = acc + bias -> dxhat = k (xhat - x) hi / lo planes, sum (xhat - x)^2, bias gradient
-};
-
-// Arguments of the fused training epilogues (see the kernel).
-struct GemmFused {
-  float* out_hi; float* out_lo; int ld_out;    // the planes the next GEMM reads
-  const float* aux; int ld_aux;                // BN_BWD: saved pre-BN Y;  REC: x
-  const float* gamma; const float* beta;
-  float* mean; float* invstd;                  // BN_FWD writes, BN_BWD reads
-  float* run_mean; float* run_var;
-  float* dgamma; float* dbeta; float* dbias;   // BN_BWD (dbias = 0);  REC: dbias = column sums of dxhat
-  float* part;                                 // REC: [4 * cm] per-slab partial sums of (xhat - x)^2
-  const unsigned char* mask; int ldm;          // injected keep-mask or null
-  unsigned layer_id;
-  float drop_p;
-  float scale_k;                               // REC: w_rec * 2 / (B D)
-  int store_c;                                 // also store the fp32 result C (Y / xhat)
-  int orig_epi, orig_accumulate;               // the problem's plain epilogue (gemm_problem_unfuse)
 };
 
 struct alignas(128) GemmProblem {
@@ -106,8 +83,6 @@ struct alignas(128) GemmProblem {
   int accumulate;  // C += result (one CTA owns the tile: no atomics)
   float slope;
   int split;       // 1: error-compensated 3xTF32 on pre-split hi/lo planes, see the header comment
-  int cm;          // M tiles per cluster (fused epilogues: all M tiles of a column block, padded to a power of two); else 1
-  GemmFused f;
 };
 
 // First CTA of every problem of a launch, passed BY VALUE (constant bank): the CTA -> problem lookup costs no dependent
@@ -127,8 +102,7 @@ struct GemmCtrl {
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck, const GemmBases bases,
-                         const Ctl* __restrict__ ctl) {
+gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int ck, const GemmBases bases) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle (TMA and UMMA descriptors agree on it).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -150,19 +124,11 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   // Split-K: a cluster of ck CTAs (launch attribute) owns one output tile; rank r accumulates its share of the
   // k-blocks and the partial tiles are reduced through distributed shared memory (see the epilogue). tile_base counts
   // CTAs, a multiple of ck for every problem, so blockIdx.x % ck is the cluster rank.
-  // Fused epilogues: the cluster additionally spans the cm M tiles of one column block (cluster = cm x ck CTAs, the
-  // split-K ranks of a tile adjacent), so per-column statistics over the whole batch are exchanged through DSMEM.
-  const int cm = P.cm;
-  const int csize = cm * ck;                // cluster size of the launch (identical for every problem of a launch)
   const int cta = blockIdx.x - bases.base[p];
-  const int cr = cta % csize;               // == %cluster_ctarank (problem bases are multiples of csize)
-  const int crank = cr % ck;                // split-K rank
-  const int tmc = cr / ck;                  // M tile within the cluster
-  const int kbase = tmc * ck;               // cluster rank of split-K rank 0 of this tile
+  const int crank = cta % ck;
+  const int t = cta / ck;
   const int tiles_n = P.tiles_n;
-  int tm, tn;
-  if (cm > 1) { tn = cta / csize; tm = tmc; }
-  else { const int t = cta / ck; tm = t / tiles_n; tn = t % tiles_n; }
+  const int tm = t / tiles_n, tn = t % tiles_n;
   const int m0 = tm * GEMM_BM;
   const int bn = P.bn;
   const int n0 = tn * bn;
@@ -350,16 +316,9 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
 
   // Split-K, barrier A: every CTA of the cluster has finished reading its operand ring (the epilogue warps arrive after
   // the last MMA has completed), so a mate may now deposit its partial tile into it.
-  if (csize > 1) cluster_sync_all();
+  if (ck > 1) cluster_sync_all();
 
-  const bool fused = epi >= EPI_BN_FWD;
-  // Fused epilogues: the finished accumulator tile is staged column-major (pitch 129: conflict-free for row-per-lane
-  // writes and column-per-lane reads) and the per-slab column statistics of the whole cluster are gathered here.
-  constexpr int STASH_PITCH = 129;
-  float* const stats = reinterpret_cast<float*>(tiles + 64 * 1024);   // [16 slabs][2][64 columns]
-  float* const stash = reinterpret_cast<float*>(tiles + 96 * 1024);   // [64 columns][STASH_PITCH]
-
-  if (warp >= 2 && warp < 6) {
+  if (warp >= 2) {
     // ------------------------------------------------ epilogue warps, phase 2: TMEM -> registers -> (reduce) -> global
     const int q = warp & 3;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
@@ -400,7 +359,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     if (ck > 1 && owner != crank) {
       const int slot = crank < owner ? crank : crank - 1;
       float* dst_local = reinterpret_cast<float*>(tiles) + (slot * slabs_per_owner + ql) * slab_floats + lane * pitch;
-      const uint32_t dst = mapa_shared(smem_u32(dst_local), static_cast<uint32_t>(kbase + owner));
+      const uint32_t dst = mapa_shared(smem_u32(dst_local), static_cast<uint32_t>(owner));
       for (int c0 = 0; c0 < bn; c0 += 32) {
         if (n0 + c0 >= pN) break;  // warp-uniform
         float v[32];
@@ -411,26 +370,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
       }
     }
     if (ck > 1) cluster_sync_all();   // barrier B: the deposits are visible to their owners
-    const bool is_owner = ck == 1 || owner == crank;
-    if (is_owner && fused) {
-      // fused epilogues, phase 0: the finished tile (all split-K partials added in ascending rank order) -> stash
-      const int tid_e = q * 32 + lane;
-      for (int c0 = 0; c0 < bn; c0 += 32) {
-        if (n0 + c0 >= pN) break;  // warp-uniform
-        float v[32];
-        load_chunk(c0, v);
-        for (int sl = 0; sl < ck - 1; ++sl) {
-          const float* src = reinterpret_cast<const float*>(tiles) + (sl * slabs_per_owner + ql) * slab_floats + lane * pitch + c0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(src + 4 * j);
-            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stash[(c0 + j) * STASH_PITCH + tid_e] = v[j];
-      }
-    } else if (is_owner) {
+    if (ck == 1 || owner == crank) {
       const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
       const int rsub = lane >> 3, ch = lane & 7;  // read-back mapping: 4 rows x 8 float4 per pass
       for (int c0 = 0; c0 < bn; c0 += 32) {
@@ -484,205 +424,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
         __syncwarp();
       }
     }
-  } else {   // the other warps only take part in the cluster barrier
-    if (ck > 1) cluster_sync_all();                         // barrier B
-  }
-
-  if (fused) {
-    // ------------------------------------------------ fused training epilogues: all 8 warps, thread = one column of one
-    // 32-row slab (warp & 3 = slab of the tile, warp >> 2 = 32-column chunk), so per-column quantities are scalars and
-    // every global access is coalesced along the row.
-    __syncthreads();   // the stash is complete
-    const GemmFused F = P.f;
-    const int hs = warp & 3, hc = warp >> 2;
-    const int c0 = hc * 32;
-    const int nbase = n0 + c0;
-    const bool own = ck == 1 || ((hs * ck) >> 2) == crank;
-    const bool work = own && c0 < bn && nbase < pN;          // warp-uniform
-    const int col = nbase + lane;
-    const bool cok = work && col < pN;
-    const int slab = tmc * 4 + hs;                           // 32-row slab of the batch
-    const int nslabs = 4 * cm;
-    const int row0 = m0 + hs * 32;
-    const int n_w = pM - row0 < 0 ? 0 : (pM - row0 > 32 ? 32 : pM - row0);
-    const float fM = static_cast<float>(pM);
-    const float drop_p = F.drop_p;
-    const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const bool bn_epi = epi != EPI_REC;
-    const bool inject = bn_epi && ctl->inject != 0 && F.mask != nullptr;
-    const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(fminf(drop_p * 4294967296.0f, 4294967040.0f)) : 0u;
-    const uint2 key = bn_epi ? philox_key(ctl) : make_uint2(0u, 0u);
-    const float* sp = stash + (c0 + lane) * STASH_PITCH + hs * 32;   // this thread's column, rows of its slab
-    float* sc = stats + c0 + lane;
-    // keep decisions of rows 4 g .. 4 g + 3 of this column: same Philox stream as the stand-alone slab kernels
-    auto keep4 = [&](int g, bool (&keep)[4]) {
-      if (!(drop_p > 0.f)) { keep[0] = keep[1] = keep[2] = keep[3] = true; return; }
-      if (inject) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = 4 * g + k;
-          keep[k] = cok && r < n_w && F.mask[static_cast<long long>(row0 + r) * F.ldm + col] != 0;
-        }
-      } else {
-        const uint4 rnd = rand4(key, F.layer_id, col, (row0 >> 2) + g);
-        keep[0] = rnd.x >= thresh; keep[1] = rnd.y >= thresh; keep[2] = rnd.z >= thresh; keep[3] = rnd.w >= thresh;
-      }
-    };
-    // all-gather of this slab's two per-column statistics into every CTA of the cluster
-    auto publish = [&](float a, float b) {
-      float* loc = sc + slab * 128;
-      if (csize == 1) { loc[0] = a; loc[64] = b; }
-      else {
-        const uint32_t la = smem_u32(loc);
-        for (int rr = 0; rr < csize; ++rr) {
-          const uint32_t ra = mapa_shared(la, static_cast<uint32_t>(rr));
-          st_shared_cluster_f32(ra, a);
-          st_shared_cluster_f32(ra + 256u, b);
-        }
-      }
-    };
-    float val[32];   // BN_FWD: y;  BN_BWD: d loss / d (BatchNorm output)
-    float xh[32];    // BN_BWD: normalised pre-activation
-    // -------- phase 1: local statistics of the slab
-    if (work) {
-      if (epi == EPI_BN_FWD) {
-        const float bl = cok ? __ldg(pbias + col) : 0.f;
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float y = r < n_w ? sp[r] + bl : 0.f;
-          val[r] = y;
-          s += y;
-        }
-        // per-slab mean and sum of squared deviations (merged exactly across slabs in phase 2)
-        const float mw = n_w > 0 ? s / static_cast<float>(n_w) : 0.f;
-        float m2 = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) { const float d = val[r] - mw; m2 += r < n_w ? d * d : 0.f; }
-        publish(mw, m2);
-      } else if (epi == EPI_BN_BWD) {
-        const float cmean = cok ? __ldg(F.mean + col) : 0.f, cinv = cok ? __ldg(F.invstd + col) : 0.f;
-        const float cg = cok ? __ldg(F.gamma + col) : 0.f, cb = cok ? __ldg(F.beta + col) : 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          xh[r] = (cok && r < n_w) ? __ldg(F.aux + static_cast<long long>(row0 + r) * F.ld_aux + col) : cmean;
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          bool keep[4];
-          keep4(g, keep);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = 4 * g + k;
-            const float h = (xh[r] - cmean) * cinv;
-            const float a = cg * h + cb;
-            float d = sp[r];
-            if (drop_p > 0.f) d = keep[k] ? d * dscale : 0.f;
-            d = a > 0.f ? d : LRELU * d;
-            if (!(cok && r < n_w)) d = 0.f;
-            val[r] = d; xh[r] = h;
-            s1 += d; s2 += d * h;
-          }
-        }
-        publish(s1, s2);
-      } else {   // EPI_REC
-        const float bl = cok ? __ldg(pbias + col) : 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          xh[r] = (cok && r < n_w) ? __ldg(F.aux + static_cast<long long>(row0 + r) * F.ld_aux + col) : 0.f;
-        float s1 = 0.f, sq = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const bool ok = cok && r < n_w;
-          const float xo = sp[r] + bl;
-          const float d = ok ? xo - xh[r] : 0.f;
-          sq += d * d;
-          const float gx = F.scale_k * d;
-          s1 += gx;
-          if (ok) {
-            const long long row = row0 + r;
-            if (F.store_c) pC[row * ldc + col] = xo;
-            const float hi = tf32_rna(gx);
-            F.out_hi[row * F.ld_out + col] = hi;
-            F.out_lo[row * F.ld_out + col] = tf32_rna(gx - hi);
-          }
-        }
-        publish(s1, 0.f);
-        sq = warp_sum(sq);
-        if (lane == 0) F.part[(tn * nslabs + slab) * 2 + hc] = sq;
-      }
-    }
-    // -------- the statistics of every slab of the batch are in this CTA's shared memory
-    if (csize > 1) cluster_sync_all(); else __syncthreads();
-    // -------- phase 2
-    if (work) {
-      if (epi == EPI_BN_FWD) {
-        float msum = 0.f;
-        for (int k = 0; k < nslabs; ++k) {
-          const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
-          msum += static_cast<float>(nk) * sc[k * 128];
-        }
-        const float mean = msum / fM;
-        float m2 = 0.f;
-        for (int k = 0; k < nslabs; ++k) {
-          const int nk = pM - 32 * k < 0 ? 0 : (pM - 32 * k > 32 ? 32 : pM - 32 * k);
-          const float d = sc[k * 128] - mean;
-          m2 += sc[k * 128 + 64] + static_cast<float>(nk) * d * d;
-        }
-        const float var = m2 / fM;
-        const float inv = 1.0f / sqrtf(var + BN_EPS);
-        if (slab == 0 && cok) {
-          F.mean[col] = mean;
-          F.invstd[col] = inv;
-          const float unb = pM > 1 ? var * (fM / (fM - 1.f)) : var;
-          F.run_mean[col] = (1.f - BN_MOM) * F.run_mean[col] + BN_MOM * mean;
-          F.run_var[col] = (1.f - BN_MOM) * F.run_var[col] + BN_MOM * unb;
-        }
-        const float g = cok ? __ldg(F.gamma + col) : 0.f, be = cok ? __ldg(F.beta + col) : 0.f;
-#pragma unroll
-        for (int gq = 0; gq < 8; ++gq) {
-          bool keep[4];
-          keep4(gq, keep);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = 4 * gq + k;
-            const float y = val[r];
-            const float a = g * ((y - mean) * inv) + be;
-            float o = a > 0.f ? a : LRELU * a;
-            if (drop_p > 0.f) o = keep[k] ? o * dscale : 0.f;
-            if (cok && r < n_w) {
-              const long long row = row0 + r;
-              if (F.store_c) pC[row * ldc + col] = y;
-              const float hi = tf32_rna(o);
-              F.out_hi[row * F.ld_out + col] = hi;
-              F.out_lo[row * F.ld_out + col] = tf32_rna(o - hi);
-            }
-          }
-        }
-      } else if (epi == EPI_BN_BWD) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int k = 0; k < nslabs; ++k) { s1 += sc[k * 128]; s2 += sc[k * 128 + 64]; }
-        if (slab == 0 && cok) {
-          if (accumulate) { F.dbeta[col] += s1; F.dgamma[col] += s2; }
-          else { F.dbeta[col] = s1; F.dgamma[col] = s2; F.dbias[col] = 0.f; }
-        }
-        const float k0 = cok ? __ldg(F.invstd + col) * __ldg(F.gamma + col) / fM : 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          if (cok && r < n_w) {
-            const long long row = row0 + r;
-            const float dy = k0 * (fM * val[r] - s1 - xh[r] * s2);
-            const float hi = tf32_rna(dy);
-            F.out_hi[row * F.ld_out + col] = hi;
-            F.out_lo[row * F.ld_out + col] = tf32_rna(dy - hi);
-          }
-        }
-      } else if (slab == 0) {   // EPI_REC: bias gradient of the last decoder layer
-        float s1 = 0.f;
-        for (int k = 0; k < nslabs; ++k) s1 += sc[k * 128];
-        if (cok) F.dbias[col] = accumulate ? F.dbias[col] + s1 : s1;
-      }
-    }
+  } else if (ck > 1) {
+    cluster_sync_all();   // barrier B (producer and MMA warps only take part in the cluster barriers)
   }
   tc_fence_before();
   __syncthreads();
@@ -760,40 +503,21 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->slope = slope;
   g->accumulate = accumulate;
   g->split = split;
-  g->cm = 1;
   if (split && bn > 64) return -2;   // the split epilogue keeps bn <= 64 running sums in registers
   return 0;
 }
 
-// Switches a filled problem to one of the fused training epilogues. Needs M <= 512 (at most 4 M tiles -> one cluster
-// per column block) and bn <= 64 (stash / statistics sizing). Returns 0 on success.
-inline int gemm_problem_set_fused(GemmProblem* g, int epi, const GemmFused& f) {
-  if (g->tiles_m > 4 || g->bn > 64 || epi < EPI_BN_FWD) return -3;
-  const int oe = g->epi, oa = g->accumulate;
-  g->epi = epi;
-  g->f = f;
-  g->f.orig_epi = oe; g->f.orig_accumulate = oa;
-  g->cm = g->tiles_m <= 1 ? 1 : (g->tiles_m == 2 ? 2 : 4);   // 3 tiles: a fourth, empty one keeps the cluster a power of two
-  return 0;
-}
-inline void gemm_problem_unfuse(GemmProblem* g) {
-  if (g->epi < EPI_BN_FWD) return;
-  g->epi = g->f.orig_epi; g->accumulate = g->f.orig_accumulate; g->cm = 1;
-}
-inline int gemm_problem_ctas(const GemmProblem& g, int ck) { return (g.cm > 1 ? g.cm : g.tiles_m) * g.tiles_n * ck; }
-
 // Split-K factor of a stage: the largest ck in {4, 2, 1} that keeps the launch within one wave of `sms` CTAs and leaves
 // every cluster rank at least `min_kb_per_rank` k-blocks.
 inline int gemm_pick_splitk(const GemmProblem* g, int n, int sms = 148, int min_kb_per_rank = 4) {
-  int tiles = 0, min_kb = 1 << 30, cm = 1;
+  int tiles = 0, min_kb = 1 << 30;
   for (int i = 0; i < n; ++i) {
-    tiles += gemm_problem_ctas(g[i], 1);
+    tiles += g[i].tiles_m * g[i].tiles_n;
     const int kb = (g[i].K + GEMM_BK - 1) / GEMM_BK;
     if (kb < min_kb) min_kb = kb;
-    if (g[i].cm > cm) cm = g[i].cm;
   }
   for (int ck = 4; ck > 1; ck >>= 1)
-    if (cm * ck <= 8 && tiles * ck <= sms && min_kb >= min_kb_per_rank * ck) return ck;   // portable cluster size: 8
+    if (tiles * ck <= sms && min_kb >= min_kb_per_rank * ck) return ck;
   return 1;
 }
 
@@ -802,7 +526,7 @@ inline int gemm_table_finalize(GemmProblem* g, int n, int ck = 1) {
   int base = 0;
   for (int i = 0; i < n; ++i) {
     g[i].tile_base = base;
-    base += gemm_problem_ctas(g[i], ck);
+    base += g[i].tiles_m * g[i].tiles_n * ck;
   }
   return base;
 }
@@ -811,18 +535,11 @@ inline int gemm_table_finalize(GemmProblem* g, int n, int ck = 1) {
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream.
 // total_ctas = gemm_table_finalize(..., ck). ck > 1 launches clusters of ck CTAs (split-K, see the kernel).
 // host_table: the host copy of the same table entries (tile_base of every problem), or null for a single problem.
-// ctl: the step's control block (fused training epilogues only). Every problem of a launch has the same cm.
 inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int total_ctas, cudaStream_t st, bool use_pdl = false,
-                               int ck = 1, const GemmProblem* host_table = nullptr, const Ctl* ctl = nullptr) {
+                               int ck = 1, const GemmProblem* host_table = nullptr) {
   if (nprobs > GEMM_MAX_PROBS || (nprobs > 1 && !host_table)) return cudaErrorInvalidValue;
   GemmBases bases{};
-  int cm = host_table ? host_table[0].cm : 1;
-  for (int i = 0; i < nprobs; ++i) {
-    bases.base[i] = host_table ? host_table[i].tile_base : 0;
-    if (host_table && host_table[i].cm != cm) return cudaErrorInvalidValue;
-    if (host_table && host_table[i].epi >= EPI_BN_FWD && !ctl) return cudaErrorInvalidValue;
-  }
-  const int csize = cm * ck;
+  for (int i = 0; i < nprobs; ++i) bases.base[i] = host_table ? host_table[i].tile_base : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -842,16 +559,16 @@ inline cudaError_t gemm_launch(const GemmProblem* dev_table, int nprobs, int tot
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (csize > 1) {
+  if (ck > 1) {
     at[na].id = cudaLaunchAttributeClusterDimension;
-    at[na].val.clusterDim.x = static_cast<unsigned>(csize);
+    at[na].val.clusterDim.x = static_cast<unsigned>(ck);
     at[na].val.clusterDim.y = 1;
     at[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck, bases, ctl);
+  return cudaLaunchKernelEx(&cfg, gemm_tf32_grouped_kernel, dev_table, nprobs, ck, bases);
 }
 
 }  // namespace jb

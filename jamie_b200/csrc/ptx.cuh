@@ -62,12 +62,6 @@ __device__ __forceinline__ void st_shared_cluster_f4(uint32_t addr, float a, flo
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__device__ __forceinline__ void st_shared_cluster_f32(uint32_t addr, float a) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
-}
-// Named barrier over the four epilogue warps of a CTA (barrier id 1, 128 threads).
-__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -236,51 +236,3 @@ def test_split_step_equals_fused_step():
         eng.close()
     np.testing.assert_array_equal(res[0][0], res[1][0])
     np.testing.assert_array_equal(res[0][1], res[1][1])
-
-
-@pytest.mark.parametrize('dims,L,B,p', [([512, 39], 32, 512, 0.6), ([200, 100], 16, 300, 0.5), ([96, 64], 8, 64, 0.3),
-                                        ([160, 72], 8, 200, 0.0)])
-def test_fused_epilogues_match_separate_kernels(dims, L, B, p, monkeypatch):
-    """BatchNorm / dropout / reconstruction loss in the GEMM epilogues (cluster statistics exchange, 1 - 4 M tiles,
-    ragged widths) == the stand-alone slab kernels: one step on injected randomness (losses, gradients, Adam step, BN
-    running statistics), then one step on the engine's own Philox stream (same counters in both paths)."""
-    n = 2 * B
-    data = U.synth_pair(n, dims, seed=3)
-    params = U.torch_like_init(dims, L, seed=4)
-    rng = np.random.default_rng(9)
-    idx = np.stack([rng.choice(n, B, replace=False) for _ in range(2)])
-    eps, masks = U.draw_randomness(B, dims, L, p, seed=12)
-    res = []
-    for fuse in ('0', '1'):
-        monkeypatch.setenv('JB_FUSE', fuse)
-        eng = _engine(dims, L, B, p, seed=77)
-        eng.set_params(params)
-        for i in range(2):
-            eng.set_dataset(i, data[i])
-        eng.set_prior_diag(np.ones(n, np.float32))
-        eng.set_f_dense(None)
-        eng.upload_plan(idx, idx, np.array([0.4, 0.4]))
-        eng.inject(eps, masks)
-        eng.train_steps(1)
-        first = (eng.read_losses(1)[0].copy(), eng.get_grads(), eng.get_params(), eng.get_bn_stats())
-        n_before = eng.launch_count()
-        eng.train_steps(1)
-        res.append(first + (eng.launch_count() - n_before, eng.read_losses(2)[1].copy(), eng.get_grads()))
-        eng.close()
-    (l0, g0, p0, b0, n0, m0, h0), (l1, g1, p1, b1, n1, m1, h1) = res
-    assert n1 < n0          # the fused step really launches fewer kernels
-    np.testing.assert_allclose(l1[:6], l0[:6], rtol=2e-5, atol=1e-7)
-    for (nm, _), a, b in zip(O.param_spec(dims, L), g1, g0):
-        if nm in U.PRE_BN_BIAS:
-            assert np.abs(a).max() == 0
-            continue
-        assert U.rel(a, b) < 5e-5, nm
-    for a, b in zip(p1, p0):     # first Adam step moves every element by ~lr whatever its gradient: compare loosely
-        np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
-        assert np.mean(np.abs(a - b) > 2e-6) < 1e-3
-    for k in b0:
-        np.testing.assert_allclose(b1[k], b0[k], rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(m1[:5], m0[:5], rtol=1e-3, atol=1e-6)     # second step, own RNG stream: same masks and eps
-    for (nm, _), a, b in zip(O.param_spec(dims, L), h1, h0):
-        if nm not in U.PRE_BN_BIAS:
-            assert U.rel(a, b) < 5e-3, nm

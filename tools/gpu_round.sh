@@ -6,11 +6,6 @@ out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1
-if [ $? -ne 0 ]; then
-  echo "smoke failed with the fused epilogues; retrying with JB_FUSE=0"; tail -8 $out/smoke_$tag.log
-  export JB_FUSE=0
-  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_${tag}_nofuse.log 2>&1 || { tail -20 $out/smoke_${tag}_nofuse.log; }
-fi
 tail -2 $out/smoke_$tag.log
 timeout 900 python -m pytest tests -m gpu -q > $out/pytest_$tag.log 2>&1; echo "pytest exit $?"; tail -40 $out/pytest_$tag.log
 timeout 600 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit $?"; tail -3 $out/bench_$tag.err; cat $out/bench_$tag.json
