@@ -60,8 +60,16 @@ def main():
     if not ks:
         print('no kernel records captured')
         return
-    per = len(ks) // args.steps
-    mid = ks[per * (args.steps // 2): per * (args.steps // 2 + 1)]
+    # a step starts at its k_gather; with the pipelined update the previous step's Adam chunks run inside the next step
+    starts = [i for i, e in enumerate(ks) if 'k_gather' in e['name']]
+    if len(starts) < 3:
+        print('fewer than 3 steps captured')
+        return
+    a = starts[len(starts) // 2]
+    b = starts[len(starts) // 2 + 1]
+    first_adam = next((i for i in range(a - 8, a) if i >= 0 and 'k_adam' in ks[i]['name']), a)
+    mid = ks[min(a, first_adam):b]
+    per = b - a
     t0 = mid[0]['ts']
     rows, prev_end = [], t0
     for e in mid:
