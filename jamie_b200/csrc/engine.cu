@@ -114,8 +114,7 @@ struct jb_engine {
   jb::Ctl* ctl = nullptr;
   double* norm_part = nullptr;
   jb::AdamSnap* snap = nullptr;
-  // flat-buffer ranges of the optimizer update: everything, and the six forward-order chunks of the pipelined update
-  jb::AdamRanges adam_all{}, adam_chunk[6]{};
+  jb::AdamRanges adam_all{};   // the whole flat buffer as one optimizer range
   // workspaces
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -129,14 +128,6 @@ struct jb_engine {
   int graph_B = 0;
   bool graph_accum = false;
   cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr, g_host = nullptr, g_host_bwd = nullptr;
-  // Pipelined multi-step form of jb_train_steps: g_first = backward + norm; g_pipe = [previous step's Adam in six chunks on
-  // a second stream] beside [this step's backward + norm], each forward GEMM waiting for its layer's chunk; g_flush = Adam.
-  cudaGraphExec_t g_first = nullptr, g_pipe = nullptr, g_flush = nullptr;
-  int launches_first = 0, launches_pipe = 0, launches_flush = 0;
-  cudaStream_t adam_stream = nullptr;
-  cudaEvent_t ev_pipe_fork = nullptr, ev_chunk[6]{};
-  bool use_pipe = true;      // JB_PIPE=0: every step is one self-contained graph
-  bool pipe_pdl = true;      // keep programmatic dependent launch on the GEMMs that also wait for an Adam chunk
   int* h_pin = nullptr;      // pinned staging for the host-batch step (2 x batch indices + 16 floats)
   int launches_host = 0, launches_host_bwd = 0;
   cudaStream_t cap_stream = nullptr, side_stream = nullptr;
@@ -210,16 +201,6 @@ void build_layout(jb_engine* e) {
   // optimizer ranges (float4 indices; every tensor starts on a 32-float boundary)
   e->adam_all = jb::AdamRanges{};
   e->adam_all.begin4[0] = 0; e->adam_all.end4[0] = e->n_flat / 4; e->adam_all.n = 1;
-  for (int c = 0; c < 6; ++c) {
-    jb::AdamRanges rg{};
-    for (int i = 0; i < 2; ++i) {
-      const ModSegs& m = e->ms[i];
-      const long long starts[7] = {m.W1.off, m.W2.off, m.Wmv.off, m.W3.off, m.W4.off, m.W5.off, i == 0 ? e->ms[1].W1.off : e->n_flat};
-      rg.begin4[rg.n] = starts[c] / 4; rg.end4[rg.n] = starts[c + 1] / 4; ++rg.n;
-    }
-    if (c == 0) { rg.begin4[rg.n] = 0; rg.end4[rg.n] = e->ms[0].W1.off / 4; ++rg.n; }   // sigma
-    e->adam_chunk[c] = rg;
-  }
   // BatchNorm running stats
   const int widths[8] = {2 * e->D[0], e->D[0], 2 * e->D[1], e->D[1], e->D[0], 2 * e->D[0], e->D[1], 2 * e->D[1]};
   long long off = 0;
@@ -400,7 +381,7 @@ struct Rec {  // launches kernels on a stream and counts them
   // block build) run beside the encoder instead of in front of it. Null: everything is launched in order on s.
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool no_pdl_next = false;   // the next launch has a cross-stream dependency: plain (full) serialization
-  const cudaEvent_t* chunk_ev = nullptr;   // pipelined update: forward GEMM k waits for chunk_ev[k] (its layer's weights)
+
   cudaEvent_t* ev = nullptr;        // profiling: ev[k] is recorded after launch k - 1 (ev[0] before the first launch)
   const char** names = nullptr;
   void mark(const char* name) {
@@ -517,15 +498,10 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       launchk(r, jb::k_bn_fwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p);
     else launchk(r, jb::k_bn_fwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p);
   };
-  // ---- forward (pipelined update: a layer's GEMM starts once the previous step's Adam has rewritten its weights)
-  auto wait_chunk = [&](int k) {
-    if (!r.chunk_ev || r.err != cudaSuccess) return;
-    r.err = cudaStreamWaitEvent(r.s, r.chunk_ev[k], 0);
-    if (!e->pipe_pdl) r.no_pdl_next = true;
-  };
-  wait_chunk(0); r.gemm(e->st_f[0]); bnf(0, 0);
-  wait_chunk(1); r.gemm(e->st_f[1]); bnf(1, 1);
-  wait_chunk(2); r.gemm(e->st_f[2]);
+  // ---- forward
+  r.gemm(e->st_f[0]); bnf(0, 0);
+  r.gemm(e->st_f[1]); bnf(1, 1);
+  r.gemm(e->st_f[2]);
   jb::Latent lat = make_latent(e);
   launchk(r, jb::k_reparam, dim3((2 * B * L + 255) / 256), dim3(256), lat, e->ctl, B, L);
   const int wblocks = (2 * B * 32 + 255) / 256;
@@ -536,9 +512,9 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   const int fuse_loss = lat.f_present ? 0 : 1;   // without F the loss partials need nothing of another row
   launchk(r, jb::k_combine, dim3(wblocks), dim3(256), lat, B, L, fuse_loss);
   if (!fuse_loss) launchk(r, jb::k_latent_loss, dim3(wblocks), dim3(256), lat, B, L);
-  wait_chunk(3); r.gemm(e->st_f[3]); bnf(2, 2);
-  wait_chunk(4); r.gemm(e->st_f[4]); bnf(3, 3);
-  wait_chunk(5); r.gemm(e->st_f[5]);
+  r.gemm(e->st_f[3]); bnf(2, 2);
+  r.gemm(e->st_f[4]); bnf(3, 3);
+  r.gemm(e->st_f[5]);
   // ---- losses + backward
   jb::RecPair rp{};
   for (int i = 0; i < 2; ++i) {
@@ -612,28 +588,14 @@ void record_update(jb_engine* e, Rec& r, int B) {
   record_adam(e, r, B, e->adam_all);
 }
 
-int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd, 5 pipelined, 6 bwd + norm, 7 adam*/,
-            cudaGraphExec_t* out, int* nlaunch) {
+int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd*/, cudaGraphExec_t* out, int* nlaunch) {
   cudaGraph_t g = nullptr;
   CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   Rec r{e, e->cap_stream};
   if (e->use_side) { r.side = e->side_stream; r.ev_fork = e->ev_fork; r.ev_join = e->ev_join; }
-  if (what == 5) {   // pipelined step: the previous step's update in forward order on a second stream
-    if ((r.err = cudaEventRecord(e->ev_pipe_fork, e->cap_stream)) == cudaSuccess) r.err = cudaStreamWaitEvent(e->adam_stream, e->ev_pipe_fork, 0);
-    r.s = e->adam_stream;
-    for (int c = 0; c < 6; ++c) {
-      if (c == 0) r.no_pdl_next = true;
-      record_adam(e, r, B, e->adam_chunk[c]);
-      if (r.err == cudaSuccess) r.err = cudaEventRecord(e->ev_chunk[c], e->adam_stream);
-    }
-    r.s = e->cap_stream;
-    r.chunk_ev = e->ev_chunk;
-  }
-  if (what == 0 || what == 1 || what == 5 || what == 6) record_backward(e, r, B);
+  if (what == 0 || what == 1) record_backward(e, r, B);
   if (what == 3 || what == 4) record_backward(e, r, B, false);
   if (what == 0 || what == 2 || what == 3) record_update(e, r, B);
-  if (what == 5 || what == 6) record_norm(e, r, B);
-  if (what == 7) record_adam(e, r, B, e->adam_all);
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
   if (r.err != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail("kernel launch failed during capture: %s", cudaGetErrorString(r.err)); }
   if (ce != cudaSuccess) return fail("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
@@ -652,16 +614,6 @@ int ensure_graphs(jb_engine* e, int B) {
   if (e->data[0] && e->data[1]) {   // the gathering graphs need resident datasets; the host-batch graph does not
     if (capture(e, B, 0, &e->g_full, &e->launches_per_step)) return 1;
     if (capture(e, B, 1, &e->g_bwd, &e->launches_bwd)) return 1;
-    if (e->g_pipe) { cudaGraphExecDestroy(e->g_pipe); e->g_pipe = nullptr; }
-    if (e->use_pipe) {
-      if (capture(e, B, 6, &e->g_first, &e->launches_first) || capture(e, B, 7, &e->g_flush, &e->launches_flush)) return 1;
-      if (capture(e, B, 5, &e->g_pipe, &e->launches_pipe) && e->pipe_pdl) {
-        // a programmatic edge next to a cross-stream edge was refused: plain serialization on those launches
-        cudaGetLastError();
-        e->pipe_pdl = false;
-        if (capture(e, B, 5, &e->g_pipe, &e->launches_pipe)) { cudaGetLastError(); e->g_pipe = nullptr; }
-      }
-    }
   }
   if (capture(e, B, 2, &e->g_upd, &e->launches_upd)) return 1;
   if (capture(e, B, 3, &e->g_host, &e->launches_host)) return 1;
@@ -708,7 +660,7 @@ int run_chain(jb_engine* e, int from, int to, const float* in, int ld_in, int ro
   auto add = [&](const float* A, int lda, const Seg& Wt, const Seg& bt, int n_rows_w, float* C, int ldc, int N, int K, int epi) {
     GemmProblem g;
     (void)n_rows_w;
-    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N >= 256 ? 256 : 128));   // single pass: wide tiles, fewer operand bytes per output
     int rc = jb::gemm_problem_fill(&g, A, lda, 0, T + Wt.off, Wt.ld, 0, C, ldc, rows, N, K, bn, epi, T + bt.off, jb::LRELU, 0);
     if (rc) return fail("eval tensor map encode failed (%d)", rc);
     jb::gemm_table_finalize(&g, 1);
@@ -731,7 +683,9 @@ int run_chain(jb_engine* e, int from, int to, const float* in, int ld_in, int ro
   }
   CU(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, s));
   for (size_t k = 0; k < tab.size(); ++k) {
-    CU(jb::gemm_launch(d_tab + k, 1, tab[k].tiles_m * tab[k].tiles_n, s));
+    // programmatic dependent launch inside the chain: GEMM k + 1 sets up while GEMM k drains (the kernel waits for its
+    // predecessor before touching memory)
+    CU(jb::gemm_launch(d_tab + k, 1, tab[k].tiles_m * tab[k].tiles_n, s, k > 0));
     ++e->launches;
   }
   return 0;
@@ -845,18 +799,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMalloc(&e->norm_part, jb::NORM_BLOCKS * sizeof(double)));
   CU(cudaMalloc(&e->snap, sizeof(jb::AdamSnap)));
   CU(cudaMemset(e->snap, 0, sizeof(jb::AdamSnap)));
-  CU(cudaStreamCreateWithFlags(&e->adam_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&e->ev_pipe_fork, cudaEventDisableTiming));
-  for (auto& ev : e->ev_chunk) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  if (const char* pv = getenv("JB_PIPE")) e->use_pipe = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_PIPE_PDL")) e->pipe_pdl = atoi(pv) != 0;
-  CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
-  CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
   if (const char* pv = getenv("JB_SPLITK")) e->use_splitk = atoi(pv) != 0;
   e->num_sms = prop.multiProcessorCount;
@@ -882,12 +824,6 @@ void jb_destroy(jb_engine* e) {
   if (e->g_upd) cudaGraphExecDestroy(e->g_upd);
   if (e->g_host) cudaGraphExecDestroy(e->g_host);
   if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
-  if (e->g_first) cudaGraphExecDestroy(e->g_first);
-  if (e->g_pipe) cudaGraphExecDestroy(e->g_pipe);
-  if (e->g_flush) cudaGraphExecDestroy(e->g_flush);
-  if (e->adam_stream) cudaStreamDestroy(e->adam_stream);
-  if (e->ev_pipe_fork) cudaEventDestroy(e->ev_pipe_fork);
-  for (auto& ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
   if (e->snap) cudaFree(e->snap);
   if (e->h_pin) cudaFreeHost(e->h_pin);
   void* ptrs[] = {e->theta, e->grad, e->adam_m, e->adam_v, e->theta_eval, e->theta_hi, e->theta_lo, e->bn_run, e->data[0], e->data[1], e->p_diag,
@@ -1098,16 +1034,8 @@ int jb_train_steps(jb_engine* e, int nsteps, void* stream) {
   if (ensure_graphs(e, e->plan_B)) return 1;
   if (!e->g_full) return fail("jb_set_dataset must be called for both modalities before jb_train_steps");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (e->g_pipe && nsteps >= 2) {
-    // same result as nsteps self-contained steps: update k runs beside forward k + 1, the last one after the loop
-    CU(cudaGraphLaunch(e->g_first, s));
-    for (int k = 1; k < nsteps; ++k) CU(cudaGraphLaunch(e->g_pipe, s));
-    CU(cudaGraphLaunch(e->g_flush, s));
-    e->launches += e->launches_first + static_cast<long long>(nsteps - 1) * e->launches_pipe + e->launches_flush;
-  } else {
-    for (int k = 0; k < nsteps; ++k) CU(cudaGraphLaunch(e->g_full, s));
-    e->launches += static_cast<long long>(nsteps) * e->launches_per_step;
-  }
+  for (int k = 0; k < nsteps; ++k) CU(cudaGraphLaunch(e->g_full, s));
+  e->launches += static_cast<long long>(nsteps) * e->launches_per_step;
   for (int k = 0; k < 8; ++k) e->nbt[k] += nsteps;
   e->eval_dirty = true;
   return 0;
