@@ -244,6 +244,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-predict', action='store_true')
+    ap.add_argument('--predict-only', action='store_true', help='modal_predict leg alone (tuning runs)')
     ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu): no e2e / stage / CPU legs, no JSON line')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -283,6 +284,11 @@ def main():
     idx0, idx1 = make_plan(n, W + K, rng, cs)
     eng.upload_plan(idx0, idx1, np.full(W + K, 0.5), stream)
     gt = eng.grad_tensor() if world > 1 else None
+    if args.predict_only:
+        p = predict_leg(eng, torch, peaks, stream)
+        print(json.dumps({k: p[k] for k in ('value', 'ms', 'e2e', 'gpu_launches')}), flush=True)
+        eng.close()
+        return
 
     def run_steps(k):
         if world == 1:
