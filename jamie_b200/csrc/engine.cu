@@ -134,6 +134,7 @@ struct jb_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
   int wgrad_bn = 256;        // widest N tile of the batched wgrad launch
+  int slab_cw = 16;          // columns per block of the BatchNorm / reconstruction slab kernels: 16 (1024 threads) or 8 (512)
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
   bool pending_inject = false;
@@ -259,7 +260,7 @@ void carve(jb_engine* e, Carver& c) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>((D + 15) / 16);
+    a.rec_part = c.take<float>((D + 7) / 8);
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
@@ -495,8 +496,12 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
-      launchk(r, jb::k_bn_fwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p);
+    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN")) {
+      const int cw = e->slab_cw;
+      const dim3 grid((pr.l[0].N + cw - 1) / cw + (pr.l[1].N + cw - 1) / cw);
+      if (cw == 8) launchk(r, jb::k_bn_fwd_slab<8, 512>, grid, dim3(512), pr, e->ctl, B, p);
+      else launchk(r, jb::k_bn_fwd_slab<16, 1024>, grid, dim3(1024), pr, e->ctl, B, p);
+    }
     else launchk(r, jb::k_bn_fwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p);
   };
   // ---- forward
@@ -523,9 +528,11 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
     jb::RecArgs& q = rp.m[i];
     q.xhat = a.xhat; q.ldxh = a.ldD; q.x = a.x; q.ldx = a.ldD; q.dxh = a.dxhat.hi; q.dxl = a.dxhat.lo; q.lddx = a.ldD;
     const bool slab = B <= 512;
-    q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + (slab ? 15 : 31)) / (slab ? 16 : 32);
+    const int cw = slab ? e->slab_cw : 32;
+    q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + cw - 1) / cw;
   }
-  if (B <= 512) launchk(r, jb::k_rec_slab, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(jb::SLAB_THREADS), rp, B, sc.w[1], accum);
+  if (B <= 512 && e->slab_cw == 8) launchk(r, jb::k_rec_slab<8, 512>, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(512), rp, B, sc.w[1], accum);
+  else if (B <= 512) launchk(r, jb::k_rec_slab<16, 1024>, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(1024), rp, B, sc.w[1], accum);
   else launchk(r, jb::k_rec, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(256), rp, B, sc.w[1], accum);
   auto bnb = [&](int which) {
     jb::BnBwdPair pr{};
@@ -546,8 +553,12 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
       l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
       l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
     }
-    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN"))
-      launchk(r, jb::k_bn_bwd_slab, dim3((pr.l[0].N + 15) / 16 + (pr.l[1].N + 15) / 16), dim3(jb::SLAB_THREADS), pr, e->ctl, B, p, accum);
+    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN")) {
+      const int cw = e->slab_cw;
+      const dim3 grid((pr.l[0].N + cw - 1) / cw + (pr.l[1].N + cw - 1) / cw);
+      if (cw == 8) launchk(r, jb::k_bn_bwd_slab<8, 512>, grid, dim3(512), pr, e->ctl, B, p, accum);
+      else launchk(r, jb::k_bn_bwd_slab<16, 1024>, grid, dim3(1024), pr, e->ctl, B, p, accum);
+    }
     else launchk(r, jb::k_bn_bwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p, accum);
   };
   r.gemm(e->st_b[0]); bnb(3);
@@ -560,7 +571,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   jb::FinalArgs fa{};
   fa.rowpart = e->rowpart;
   for (int i = 0; i < 2; ++i) {
-    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = (e->D[i] + (B <= 512 ? 15 : 31)) / (B <= 512 ? 16 : 32);
+    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = rp.m[i].blocks;
     fa.dmulv[i] = e->act[i].dmulv; fa.dbias_heads[i] = G + e->ms[i].bmv.off; fa.D[i] = e->D[i];
   }
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
@@ -806,6 +817,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
+  if (const char* pv = getenv("JB_SLAB_CW")) e->slab_cw = atoi(pv) == 8 ? 8 : 16;
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
   if (const char* pv = getenv("JB_SPLITK")) e->use_splitk = atoi(pv) != 0;

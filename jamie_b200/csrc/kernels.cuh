@@ -405,33 +405,39 @@ constexpr int SLAB_THREADS = 1024;
 constexpr int SLAB_SLOTS = SLAB_THREADS / SLAB_CW;   // 64 threads per column
 constexpr int SLAB_G = 2;                            // row groups (of 4 rows) per thread: B <= 4 * 64 * 2 = 512
 
-// column sums of two per-thread partials over the 64 slots of each column (fixed order), broadcast to all threads
-__device__ __forceinline__ void slab_colsum2(float& a, float& b, float (*sh)[2][SLAB_CW], int warp, int lane) {
-  a += __shfl_xor_sync(0xffffffffu, a, 16);
-  b += __shfl_xor_sync(0xffffffffu, b, 16);
-  if (lane < SLAB_CW) { sh[warp][0][lane] = a; sh[warp][1][lane] = b; }
+// column sums of two per-thread partials over the 64 slots of each column (fixed order), broadcast to all threads.
+// CW columns per block (16 or 8), THREADS = 64 CW threads: thread t owns column t % CW, slot t / CW.
+template <int CW, int THREADS>
+__device__ __forceinline__ void slab_colsum2(float& a, float& b, float (*sh)[2][CW], int warp, int lane) {
+#pragma unroll
+  for (int o = 16; o >= CW; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane < CW) { sh[warp][0][lane] = a; sh[warp][1][lane] = b; }
   __syncthreads();
-  if (warp == 0 && lane < SLAB_CW) {
+  if (warp == 0 && lane < CW) {
     float x = 0.f, y = 0.f;
 #pragma unroll
-    for (int w = 0; w < SLAB_THREADS / 32; ++w) { x += sh[w][0][lane]; y += sh[w][1][lane]; }
+    for (int w = 0; w < THREADS / 32; ++w) { x += sh[w][0][lane]; y += sh[w][1][lane]; }
     sh[0][0][lane] = x; sh[0][1][lane] = y;
   }
   __syncthreads();
-  a = sh[0][0][lane & (SLAB_CW - 1)]; b = sh[0][1][lane & (SLAB_CW - 1)];
+  a = sh[0][0][lane & (CW - 1)]; b = sh[0][1][lane & (CW - 1)];
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, const Ctl* __restrict__ ctl, int B, float p) {
+template <int CW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bn_fwd_slab(BnFwdPair pr, const Ctl* __restrict__ ctl, int B, float p) {
   pdl_prologue();
-  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
-  const int nb0 = (pr.l[0].N + SLAB_CW - 1) / SLAB_CW;
+  __shared__ float sh[THREADS / 32][2][CW];
+  const int nb0 = (pr.l[0].N + CW - 1) / CW;
   const int which = blockIdx.x >= nb0 ? 1 : 0;
   const BnFwd& L = pr.l[which];
   const int cb = blockIdx.x - (which ? nb0 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = cb * SLAB_CW + (threadIdx.x & (SLAB_CW - 1));
-  const int slot = threadIdx.x / SLAB_CW;
+  const int c = cb * CW + (threadIdx.x & (CW - 1));
+  const int slot = threadIdx.x / CW;
   const bool cok = c < L.N;
   const float* Y = L.Y + (cok ? c : 0);
   const int ldy = L.ldy;
@@ -440,25 +446,25 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, cons
   for (int t = 0; t < SLAB_G; ++t)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
       v[4 * t + k] = (cok && r < B) ? __ldg(Y + static_cast<long long>(r) * ldy) : 0.f;
     }
   float s = 0.f, dummy = 0.f;
 #pragma unroll
   for (int i = 0; i < 4 * SLAB_G; ++i) s += v[i];
-  slab_colsum2(s, dummy, sh, warp, lane);
+  slab_colsum2<CW, THREADS>(s, dummy, sh, warp, lane);
   const float mean = s / static_cast<float>(B);
   float q = 0.f;
 #pragma unroll
   for (int t = 0; t < SLAB_G; ++t)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
       const float d = v[4 * t + k] - mean;
       q += (r < B) ? d * d : 0.f;
     }
   dummy = 0.f;
-  slab_colsum2(q, dummy, sh, warp, lane);
+  slab_colsum2<CW, THREADS>(q, dummy, sh, warp, lane);
   const float var = q / static_cast<float>(B);
   const float invx = 1.0f / sqrtf(var + BN_EPS);
   if (slot == 0 && cok) {
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, cons
   const int ldh = L.ldh;
 #pragma unroll
   for (int t = 0; t < SLAB_G; ++t) {
-    const int gq = slot + SLAB_SLOTS * t;
+    const int gq = slot + (THREADS / CW) * t;
     uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     if (p > 0.f && !inject && 4 * gq < B) rnd = rand4(key, L.layer_id, c, gq);
     const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
@@ -498,17 +504,18 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_fwd_slab(BnFwdPair pr, cons
   }
 }
 
-__global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, const Ctl* __restrict__ ctl, int B, float p,
+template <int CW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bn_bwd_slab(BnBwdPair pr, const Ctl* __restrict__ ctl, int B, float p,
                                                                int accum) {
   pdl_prologue();
-  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
-  const int nb0 = (pr.l[0].N + SLAB_CW - 1) / SLAB_CW;
+  __shared__ float sh[THREADS / 32][2][CW];
+  const int nb0 = (pr.l[0].N + CW - 1) / CW;
   const int which = blockIdx.x >= nb0 ? 1 : 0;
   const BnBwd& L = pr.l[which];
   const int cb = blockIdx.x - (which ? nb0 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = cb * SLAB_CW + (threadIdx.x & (SLAB_CW - 1));
-  const int slot = threadIdx.x / SLAB_CW;
+  const int c = cb * CW + (threadIdx.x & (CW - 1));
+  const int slot = threadIdx.x / CW;
   const bool cok = c < L.N;
   const int cc = cok ? c : 0;
   const float mean = __ldg(L.mean + cc), inv = __ldg(L.invstd + cc);
@@ -522,7 +529,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, cons
   for (int t = 0; t < SLAB_G; ++t)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
       const bool ok = cok && r < B;
       yh[4 * t + k] = ok ? __ldg(L.Y + static_cast<long long>(r) * L.ldy + cc) : mean;
       da[4 * t + k] = ok ? __ldg(L.dH + static_cast<long long>(r) * L.lddh + cc) : 0.f;
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, cons
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int t = 0; t < SLAB_G; ++t) {
-    const int gq = slot + SLAB_SLOTS * t;
+    const int gq = slot + (THREADS / CW) * t;
     uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     if (p > 0.f && !inject && 4 * gq < B) rnd = rand4(key, L.layer_id, c, gq);
     const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, cons
       s2 += d * h;
     }
   }
-  slab_colsum2(s1, s2, sh, warp, lane);
+  slab_colsum2<CW, THREADS>(s1, s2, sh, warp, lane);
   if (slot == 0 && cok) {
     if (accum) { L.dbeta[c] += s1; L.dgamma[c] += s2; }
     else { L.dbeta[c] = s1; L.dgamma[c] = s2; L.dbias[c] = 0.f; }
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_bn_bwd_slab(BnBwdPair pr, cons
   for (int t = 0; t < SLAB_G; ++t)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
       if (r < B && cok) {
         const long long o = static_cast<long long>(r) * L.lddy + c;
         tf32_split(k0 * (fb * da[4 * t + k] - s1 - yh[4 * t + k] * s2), L.dYh[o], L.dYl[o]);
@@ -612,16 +619,17 @@ __global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int
   }
 }
 
-__global__ void __launch_bounds__(SLAB_THREADS) k_rec_slab(RecPair pr, int B, float w_rec, int accum) {
+template <int CW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_rec_slab(RecPair pr, int B, float w_rec, int accum) {
   pdl_prologue();
-  __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
-  const int nb0 = (pr.m[0].D + SLAB_CW - 1) / SLAB_CW;
+  __shared__ float sh[THREADS / 32][2][CW];
+  const int nb0 = (pr.m[0].D + CW - 1) / CW;
   const int which = blockIdx.x >= nb0 ? 1 : 0;
   const RecArgs& A = pr.m[which];
   const int cb = blockIdx.x - (which ? nb0 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = cb * SLAB_CW + (threadIdx.x & (SLAB_CW - 1));
-  const int slot = threadIdx.x / SLAB_CW;
+  const int c = cb * CW + (threadIdx.x & (CW - 1));
+  const int slot = threadIdx.x / CW;
   const bool cok = c < A.D;
   const float kk = w_rec * 2.f / (static_cast<float>(B) * static_cast<float>(A.D));
   float xh[4 * SLAB_G], xx[4 * SLAB_G];
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_rec_slab(RecPair pr, int B, fl
   for (int t = 0; t < SLAB_G; ++t)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
       const bool ok = cok && r < B;
       xh[4 * t + k] = ok ? __ldg(A.xhat + static_cast<long long>(r) * A.ldxh + c) : 0.f;
       xx[4 * t + k] = ok ? __ldg(A.x + static_cast<long long>(r) * A.ldx + c) : 0.f;
@@ -639,17 +647,17 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_rec_slab(RecPair pr, int B, fl
   for (int t = 0; t < SLAB_G; ++t)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (slot + SLAB_SLOTS * t) + k;
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
       const float d = xh[4 * t + k] - xx[4 * t + k];
       sq += d * d;
       const float gx = kk * d;
       cs += gx;
       if (r < B && cok) tf32_split(gx, A.dxh[static_cast<long long>(r) * A.lddx + c], A.dxl[static_cast<long long>(r) * A.lddx + c]);
     }
-  slab_colsum2(sq, cs, sh, warp, lane);
+  slab_colsum2<CW, THREADS>(sq, cs, sh, warp, lane);
   if (warp == 0) {
-    if (lane < SLAB_CW && cok) A.dbias[c] = accum ? A.dbias[c] + cs : cs;
-    float t = (lane < SLAB_CW && cok) ? sq : 0.f;
+    if (lane < CW && cok) A.dbias[c] = accum ? A.dbias[c] + cs : cs;
+    float t = (lane < CW && cok) ? sq : 0.f;
     t = warp_sum(t);
     if (lane == 0) A.part[cb] = t;
   }
@@ -916,7 +924,7 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_latent_final(FinalArgs a, cons
     if (cok)
 #pragma unroll 8
       for (int r = slot; r < B; r += SLAB_SLOTS) s += __ldg(src + static_cast<long long>(r) * a.ldmv);
-    slab_colsum2(s, dummy, sh, warp, lane);
+    slab_colsum2<SLAB_CW, SLAB_THREADS>(s, dummy, sh, warp, lane);
     if (slot == 0 && cok) a.dbias_heads[i][cidx] = accum ? a.dbias_heads[i][cidx] + s : s;
     return;
   }

@@ -14,8 +14,8 @@ if [ "$2" != "quick" ]; then
   timeout 300 python bench.py --impl reference --steps 40 --warmup 3 > $out/bench_ref_$tag.json 2>&1; cat $out/bench_ref_$tag.json
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
     python bench.py --profile --steps 6 --warmup 8 > $out/ncu_launch_$tag.log 2>&1; tail -2 $out/ncu_launch_$tag.log
-  # full captures: the batched wgrad launch (12th GEMM of a step), the first encoder GEMM (3xTF32), Adam
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 35 -c 2 -f -o $out/gemm_$tag \
+  # full captures: the batched wgrad launch (12th GEMM of a step), the first two encoder GEMMs (3xTF32; the second with split-K), Adam
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 35 -c 3 -f -o $out/gemm_$tag \
     python bench.py --profile --steps 3 --warmup 3 > $out/ncu_gemm_$tag.log 2>&1; tail -2 $out/ncu_gemm_$tag.log
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_adam -s 3 -c 1 -f -o $out/adam_$tag \
     python bench.py --profile --steps 3 --warmup 3 > $out/ncu_adam_$tag.log 2>&1; tail -2 $out/ncu_adam_$tag.log

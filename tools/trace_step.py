@@ -60,15 +60,14 @@ def main():
     if not ks:
         print('no kernel records captured')
         return
-    # a step starts at its k_gather; with the pipelined update the previous step's Adam chunks run inside the next step
+    # a step starts at its k_gather
     starts = [i for i, e in enumerate(ks) if 'k_gather' in e['name']]
     if len(starts) < 3:
         print('fewer than 3 steps captured')
         return
     a = starts[len(starts) // 2]
     b = starts[len(starts) // 2 + 1]
-    first_adam = next((i for i in range(a - 8, a) if i >= 0 and 'k_adam' in ks[i]['name']), a)
-    mid = ks[min(a, first_adam):b]
+    mid = ks[a:b]
     per = b - a
     t0 = mid[0]['ts']
     rows, prev_end = [], t0
