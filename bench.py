@@ -343,26 +343,39 @@ def main():
     host = [d.cpu().pin_memory() for d in data] if n <= 200_000 else \
         [d[:200_000].cpu().pin_memory() for d in data]
     nh = host[0].shape[0]
-    hb = [torch.empty((BATCH, d), dtype=torch.float32).pin_memory() for d in DIMS]
+    hb = [[torch.empty((BATCH, d), dtype=torch.float32).pin_memory() for d in DIMS] for _ in range(2)]   # two host slots
     i0e, i1e = make_plan(nh, Ke + 5, rng, cs if nz.max() < nh else np.stack([np.flatnonzero(mask[:nh])[:2]] * 2, 1))
     ti = [torch.from_numpy(i0e), torch.from_numpy(i1e)]
 
-    def e2e_step(s):
-        for i in range(2):
-            torch.index_select(host[i], 0, ti[i][s], out=hb[i])      # the reference's dataset[i][random_batch[i]]
-        if world == 1:
-            return eng.train_step_hostbatch(hb[0].data_ptr(), hb[1].data_ptr(), i0e[s], i1e[s], 0.5, stream)
-        eng.step_backward_hostbatch(hb[0].data_ptr(), hb[1].data_ptr(), i0e[s], i1e[s], 0.5, stream)
-        dist.all_reduce(gt)
-        eng.step_update(stream)
-        return eng.read_losses(1, stream)[0]
+    def e2e_run(first, count):
+        """The reference's loop shape (jamie/jamie.py:549-742) with host-resident data: gather the batch rows on the host,
+        hand them to the engine, read the step's losses back. N = 1: the engine's asynchronous host-batch API keeps two
+        steps in flight, so the host gather of batch k + 1 overlaps step k; N > 1: backward, all-reduce, update."""
+        out, pending = None, 0
+        for s in range(first, first + count):
+            b = hb[s & 1]
+            for i in range(2):
+                torch.index_select(host[i], 0, ti[i][s], out=b[i])      # the reference's dataset[i][random_batch[i]]
+            if world == 1:
+                eng.hostbatch_submit(b[0].data_ptr(), b[1].data_ptr(), i0e[s], i1e[s], 0.5, stream)
+                pending += 1
+                if pending == 2:
+                    out = eng.hostbatch_wait()
+                    pending -= 1
+            else:
+                eng.step_backward_hostbatch(b[0].data_ptr(), b[1].data_ptr(), i0e[s], i1e[s], 0.5, stream)
+                dist.all_reduce(gt)
+                eng.step_update(stream)
+                out = eng.read_losses(2, stream)[s & 1]
+        while pending:
+            out = eng.hostbatch_wait()
+            pending -= 1
+        return out
 
-    for s in range(5):
-        e2e_step(s)
+    e2e_run(0, 5)
     sync_all()
     t0 = time.perf_counter()
-    for s in range(5, 5 + Ke):
-        out = e2e_step(s)
+    out = e2e_run(5, Ke)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -411,8 +424,9 @@ def main():
             'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
             'config': workload_config(world),
             'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': Ke, 'note': 'host gather into pinned memory + jb_train_step_hostbatch (H2D batch, step '
-                                         'graph, D2H losses, stream sync) per step'},
+                    'steps': Ke, 'note': 'per step: host gather of the batch rows into pinned memory, H2D of rows + cell ids, '
+                                         'step graph, D2H of the 8 loss scalars; jb_hostbatch_submit / jb_hostbatch_wait keep '
+                                         'two steps in flight (N = 1)'},
             'gpu_launches': int(launches), 'launches_per_step': launches / K,
             'roofline': roof, 'step_roofline': sroof, 'step_profile': prof,
             'gemm_stages_us': [round(s[0], 2) for s in stages], 'modal_predict': pred, 'cpu_baseline': cb, 'clocks': clocks.summary(),

@@ -113,6 +113,15 @@ int jb_train_step_hostbatch(jb_engine* e, const float* x0, const float* x1, cons
 int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0,
                                const long long* idx1, int batch, double kl_anneal, void* stream);
 
+/* Asynchronous form of jb_train_step_hostbatch for a host loop that prepares batch k + 1 (the reference's
+ * dataset[i][random_batch[i]] gather, jamie/jamie.py:583) while step k runs: submit enqueues the copies on an internal
+ * copy stream and the step on `stream` and returns at once; wait blocks until the OLDEST submitted step has finished and
+ * returns its 8 loss scalars. At most two steps may be in flight; x0 / x1 must stay valid (pinned) until the step's
+ * jb_hostbatch_wait has returned. */
+int jb_hostbatch_submit(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1, int batch,
+                        double kl_anneal, void* stream);
+int jb_hostbatch_wait(jb_engine* e, float out_losses[8]);
+
 /* Benchmark hook: launch GEMM stage `stage` of the training step (0..5 forward: enc1, enc2, heads, dec1, dec2, dec3;
  * 6..11 backward in execution order) `iters` times on `stream`, timed with CUDA events on that stream.
  * Returns the average microseconds per launch and the FLOPs of one launch. */

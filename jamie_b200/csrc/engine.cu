@@ -67,6 +67,7 @@ struct Planes {  // a GEMM operand as TF32 hi / lo planes (same shape and pitch)
 };
 struct ModActs {  // activations and gradients of one modality (device pointers, pitches in floats)
   float *x, *y1, *y2, *mulv, *y3, *y4, *xhat;           // fp32: gathered input and GEMM outputs
+  float* x_stage[2];                                     // host-batch steps: two H2D landing buffers for x
   Planes xp, h1, h2, cp, g1, g2;                         // forward GEMM operands
   float *dg2, *dg1, *dc, *dmulv, *dh2, *dh1;             // fp32: dgrad outputs (+ dmulv from the latent backward)
   Planes dxhat, dy4, dy3, dmp, dy2, dy1;                 // backward GEMM operands
@@ -83,6 +84,14 @@ struct GemmStage {
 };
 
 }  // namespace
+
+struct HostPin {
+  long long cursor_val[2];   // {0, 1}: plan row of a slot, copied into the control block before the step graph
+  int slot_val[2];           // {0, 1}
+  float kl[2];
+  float losses[2][8];
+  int idx[1];                // [slot][modality][Bmax]
+};
 
 struct jb_engine {
   jb_config cfg{};
@@ -128,7 +137,12 @@ struct jb_engine {
   int graph_B = 0;
   bool graph_accum = false;
   cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr, g_host = nullptr, g_host_bwd = nullptr;
-  int* h_pin = nullptr;      // pinned staging for the host-batch step (2 x batch indices + 16 floats)
+  // Host-batch steps (data resident on the host): two slots so that the copies of batch k + 1 run while step k computes.
+  struct HostPin* h_pin = nullptr;   // pinned: constants, per-slot kl / losses / indices
+  cudaStream_t h2d_stream = nullptr;
+  cudaEvent_t ev_h2d[2]{}, ev_slot_free[2]{}, ev_loss[2]{};
+  bool slot_used[2]{};
+  int hb_slot = 0, hb_oldest = 0, hb_outstanding = 0;
   int launches_host = 0, launches_host_bwd = 0;
   cudaStream_t cap_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -244,6 +258,7 @@ void carve(jb_engine* e, Carver& c) {
     a.ldD = r4(D); a.ld2D = r4(2 * D); a.ldmv = r4(2 * e->L); a.LP = e->LP;
     auto planes = [&](Planes& p, size_t n) { p.hi = c.take<float>(n); p.lo = c.take<float>(n); };
     a.x = c.take<float>(B * a.ldD); planes(a.xp, B * a.ldD);
+    a.x_stage[0] = c.take<float>(B * a.ldD); a.x_stage[1] = c.take<float>(B * a.ldD);
     a.y1 = c.take<float>(B * a.ld2D); planes(a.h1, B * a.ld2D);
     a.y2 = c.take<float>(B * a.ldD); planes(a.h2, B * a.ldD); a.mulv = c.take<float>(B * a.ldmv);
     a.y3 = c.take<float>(B * a.ldD); planes(a.g1, B * a.ldD); a.y4 = c.take<float>(B * a.ld2D);
@@ -455,6 +470,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
     ga.data[i] = e->data[i]; ga.ld_data[i] = e->data_ld[i]; ga.x[i] = e->act[i].x; ga.ldx[i] = e->act[i].ldD;
     ga.xh[i] = e->act[i].xp.hi; ga.xl[i] = e->act[i].xp.lo;
     ga.D[i] = e->D[i]; ga.idx[i] = e->plan_idx[i];
+    ga.stage[0][i] = e->act[i].x_stage[0]; ga.stage[1][i] = e->act[i].x_stage[1];
   }
   if (gather) launchk(r, jb::k_gather, dim3(B, 2), dim3(128), ga, e->ctl, e->plan_kl, sc, B);
   else launchk(r, jb::k_split_x, dim3(B, 2), dim3(128), ga, e->ctl, e->plan_kl, sc, B);   // host batch: x was copied in
@@ -851,6 +867,12 @@ void jb_destroy(jb_engine* e) {
   if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
   if (e->snap) cudaFree(e->snap);
   if (e->h_pin) cudaFreeHost(e->h_pin);
+  if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
+  for (int k = 0; k < 2; ++k) {
+    if (e->ev_h2d[k]) cudaEventDestroy(e->ev_h2d[k]);
+    if (e->ev_slot_free[k]) cudaEventDestroy(e->ev_slot_free[k]);
+    if (e->ev_loss[k]) cudaEventDestroy(e->ev_loss[k]);
+  }
   void* ptrs[] = {e->theta, e->grad, e->adam_m, e->adam_v, e->theta_eval, e->theta_hi, e->theta_lo, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
                   e->arena, e->d_probs, e->ev_a, e->ev_b, e->ev_in, e->ev_out, e->d_ev_probs};
@@ -1096,19 +1118,35 @@ int jb_set_grad_accumulate(jb_engine* e, int accumulate) {
   return 0;
 }
 
-static int hostbatch_common(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
-                           int batch, double kl_anneal, float* out_losses, void* stream) {
+// Enqueues one host-batch step in slot e->hb_slot: index / kl / row copies on the copy stream, then (after an event) the
+// control-block pokes, the step graph and the loss read-back on the caller's stream. Nothing here blocks the host.
+static int hostbatch_submit(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
+                            int batch, double kl_anneal, bool with_update, void* stream) {
   if (!e || !x0 || !x1 || !idx0 || !idx1) return fail("null argument");
+  if (with_update && e->hb_outstanding >= 2) return fail("two host-batch steps are in flight: call jb_hostbatch_wait first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (e->plan_B != batch || e->plan_cap < 1) {   // first call: allocate the one-row plan through the normal path
-    std::vector<long long> z(batch, 0);
-    double k0 = 0;
-    if (jb_upload_plan(e, z.data(), z.data(), &k0, 1, batch, stream)) return 1;
+  if (e->plan_B != batch || e->plan_cap < 2) {   // first call: allocate a two-row plan (one row per slot) through the normal path
+    std::vector<long long> z(2 * static_cast<size_t>(batch), 0);
+    double k0[2] = {0, 0};
+    if (jb_upload_plan(e, z.data(), z.data(), k0, 2, batch, stream)) return 1;
   }
   if (ensure_graphs(e, batch)) return 1;
-  if (!e->h_pin) CU(cudaMallocHost(&e->h_pin, (2 * static_cast<size_t>(e->Bmax) + 32) * 4));
-  int* hi = e->h_pin;
-  float* hf = reinterpret_cast<float*>(e->h_pin + 2 * e->Bmax);
+  if (!e->h_pin) {
+    CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_pin), sizeof(HostPin) + 4 * static_cast<size_t>(e->Bmax) * sizeof(int)));
+    e->h_pin->cursor_val[0] = 0; e->h_pin->cursor_val[1] = 1;
+    e->h_pin->slot_val[0] = 0; e->h_pin->slot_val[1] = 1;
+    CU(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ev_slot_free[k], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ev_loss[k], cudaEventDisableTiming));
+    }
+  }
+  const int slot = e->hb_slot;
+  HostPin* hp = e->h_pin;
+  // the slot's pinned index / kl area is reused: its previous copies (two submits ago) must have been consumed
+  if (e->slot_used[slot]) CU(cudaEventSynchronize(e->ev_h2d[slot]));
+  int* hi = hp->idx + static_cast<size_t>(slot) * 2 * e->Bmax;
   const long long* src[2] = {idx0, idx1};
   for (int i = 0; i < 2; ++i)
     for (int k = 0; k < batch; ++k) {
@@ -1119,38 +1157,65 @@ static int hostbatch_common(jb_engine* e, const float* x0, const float* x1, cons
       if (v < 0 || v >= lim) return fail("cell id %lld out of range for the prior (limit %lld)", v, lim);
       hi[i * e->Bmax + k] = static_cast<int>(v);
     }
-  hf[0] = static_cast<float>(32 * 1e-3 * kl_anneal);
+  hp->kl[slot] = static_cast<float>(32 * 1e-3 * kl_anneal);
+  // copy stream: wait until the step that last used this slot's device buffers has run, then bring the batch in
+  cudaStream_t cs = e->h2d_stream;
+  if (e->slot_used[slot]) CU(cudaStreamWaitEvent(cs, e->ev_slot_free[slot], 0));
   const float* xs[2] = {x0, x1};
   for (int i = 0; i < 2; ++i) {
-    CU(cudaMemcpyAsync(e->plan_idx[i], hi + i * e->Bmax, static_cast<size_t>(batch) * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpy2DAsync(e->act[i].x, static_cast<size_t>(e->act[i].ldD) * 4, xs[i], static_cast<size_t>(e->D[i]) * 4,
-                         static_cast<size_t>(e->D[i]) * 4, batch, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->plan_idx[i] + static_cast<size_t>(slot) * batch, hi + i * e->Bmax, static_cast<size_t>(batch) * 4,
+                       cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpy2DAsync(e->act[i].x_stage[slot], static_cast<size_t>(e->act[i].ldD) * 4, xs[i], static_cast<size_t>(e->D[i]) * 4,
+                         static_cast<size_t>(e->D[i]) * 4, batch, cudaMemcpyHostToDevice, cs));
   }
-  CU(cudaMemcpyAsync(e->plan_kl, hf, 4, cudaMemcpyHostToDevice, s));
-  CU(cudaMemsetAsync(&e->ctl->cursor, 0, sizeof(long long), s));
+  CU(cudaMemcpyAsync(e->plan_kl + slot, &hp->kl[slot], 4, cudaMemcpyHostToDevice, cs));
+  CU(cudaEventRecord(e->ev_h2d[slot], cs));
+  // compute stream
+  CU(cudaStreamWaitEvent(s, e->ev_h2d[slot], 0));
+  CU(cudaMemcpyAsync(&e->ctl->cursor, &hp->cursor_val[slot], sizeof(long long), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(&e->ctl->host_slot, &hp->slot_val[slot], sizeof(int), cudaMemcpyHostToDevice, s));
   for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
-  e->plan_steps = 1;
+  if (e->plan_steps < 2) e->plan_steps = 2;
   e->eval_dirty = true;
-  if (!out_losses) {   // data-parallel form: forward + backward only
+  if (!with_update) {   // data-parallel form: forward + backward only
     CU(cudaGraphLaunch(e->g_host_bwd, s));
     e->launches += e->launches_host_bwd;
-    return 0;
+  } else {
+    CU(cudaGraphLaunch(e->g_host, s));
+    CU(cudaMemcpyAsync(hp->losses[slot], e->out_loss + static_cast<size_t>(slot) * 8, 8 * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(e->ev_loss[slot], s));
+    e->launches += e->launches_host;
+    ++e->hb_outstanding;
   }
-  CU(cudaGraphLaunch(e->g_host, s));
-  CU(cudaMemcpyAsync(hf + 8, e->out_loss, 8 * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  memcpy(out_losses, hf + 8, 8 * 4);
-  e->launches += e->launches_host;
+  CU(cudaEventRecord(e->ev_slot_free[slot], s));
+  e->slot_used[slot] = true;
+  e->hb_slot ^= 1;
+  return 0;
+}
+int jb_hostbatch_submit(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1, int batch,
+                        double kl_anneal, void* stream) {
+  return hostbatch_submit(e, x0, x1, idx0, idx1, batch, kl_anneal, true, stream);
+}
+int jb_hostbatch_wait(jb_engine* e, float out_losses[8]) {
+  if (!e || !out_losses) return fail("null argument");
+  if (e->hb_outstanding <= 0) return fail("no host-batch step in flight");
+  const int slot = e->hb_oldest;
+  CU(cudaEventSynchronize(e->ev_loss[slot]));
+  memcpy(out_losses, e->h_pin->losses[slot], 8 * 4);
+  e->hb_oldest ^= 1;
+  --e->hb_outstanding;
   return 0;
 }
 int jb_train_step_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
                             int batch, double kl_anneal, float out_losses[8], void* stream) {
   if (!out_losses) return fail("null argument");
-  return hostbatch_common(e, x0, x1, idx0, idx1, batch, kl_anneal, out_losses, stream);
+  if (e && e->hb_outstanding > 0) return fail("asynchronous host-batch steps are in flight: call jb_hostbatch_wait first");
+  if (hostbatch_submit(e, x0, x1, idx0, idx1, batch, kl_anneal, true, stream)) return 1;
+  return jb_hostbatch_wait(e, out_losses);
 }
 int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
                                int batch, double kl_anneal, void* stream) {
-  return hostbatch_common(e, x0, x1, idx0, idx1, batch, kl_anneal, nullptr, stream);
+  return hostbatch_submit(e, x0, x1, idx0, idx1, batch, kl_anneal, false, stream);
 }
 
 int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* flops, void* stream) {

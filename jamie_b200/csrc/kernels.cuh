@@ -27,6 +27,7 @@ struct Ctl {
   float kl_base;      // 0.032 * anneal(epoch) (the reference's KL scale, before loss_weights)
   unsigned long long seed;
   unsigned long long stream_id;  // philox counter word: distinct per step
+  int host_slot;      // host-batch steps: which of the two device staging buffers holds this step's rows
 };
 
 struct StepConsts {
@@ -103,6 +104,7 @@ struct GatherArgs {
   int ldx[2];
   int D[2];
   const int* idx[2];  // plan index arrays [nsteps][B]
+  const float* stage[2][2];  // host-batch steps: [slot][modality] staging buffers the H2D copies land in (pitch ldx)
 };
 __global__ void k_gather(GatherArgs a, Ctl* ctl, const float* __restrict__ plan_kl, StepConsts sc, int B) {
   pdl_prologue();
@@ -135,16 +137,22 @@ __global__ void k_gather(GatherArgs a, Ctl* ctl, const float* __restrict__ plan_
     tf32_split(v, dh[j], dl[j]);
   }
 }
-// Host-batch step: x arrives by H2D copy; this produces its operand planes. grid (B, 2), 128 threads.
+// Host-batch step: the rows arrived by H2D copy in staging slot ctl->host_slot; this writes x and its operand planes.
+// grid (B, 2), 128 threads.
 __global__ void k_split_x(GatherArgs a, Ctl* ctl, const float* __restrict__ plan_kl, StepConsts sc, int B) {
   pdl_prologue();
   const int i = blockIdx.y, b = blockIdx.x;
   if (i == 0 && b == 0 && threadIdx.x == 0) step_begin(ctl, plan_kl, sc);
   const long long o = static_cast<long long>(b) * a.ldx[i];
-  const float* s = a.x[i] + o;
+  const float* s = a.stage[ctl->host_slot != 0 ? 1 : 0][i] + o;
+  float* d = a.x[i] + o;
   float* dh = a.xh[i] + o;
   float* dl = a.xl[i] + o;
-  for (int j = threadIdx.x; j < a.D[i]; j += blockDim.x) tf32_split(s[j], dh[j], dl[j]);
+  for (int j = threadIdx.x; j < a.D[i]; j += blockDim.x) {
+    const float v = s[j];
+    d[j] = v;
+    tf32_split(v, dh[j], dl[j]);
+  }
   (void)B;
 }
 

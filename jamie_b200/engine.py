@@ -201,6 +201,19 @@ class Engine:
                                                     idx0.size, float(kl_anneal), _ptr(out), C.c_void_p(stream)))
         return out
 
+    def hostbatch_submit(self, x0_ptr, x1_ptr, idx0, idx1, kl_anneal, stream=0):
+        """Asynchronous train_step_hostbatch: returns at once; at most two steps in flight (jb_hostbatch_submit)."""
+        idx0 = np.ascontiguousarray(idx0, dtype=np.int64)
+        idx1 = np.ascontiguousarray(idx1, dtype=np.int64)
+        _lib.check(self.lib.jb_hostbatch_submit(self.h, C.c_void_p(x0_ptr), C.c_void_p(x1_ptr), _ptr(idx0), _ptr(idx1),
+                                                idx0.size, float(kl_anneal), C.c_void_p(stream)))
+
+    def hostbatch_wait(self):
+        """The 8 loss scalars of the oldest step submitted with hostbatch_submit (blocks until it has finished)."""
+        out = np.empty(8, np.float32)
+        _lib.check(self.lib.jb_hostbatch_wait(self.h, _ptr(out)))
+        return out
+
     def step_backward_hostbatch(self, x0_ptr, x1_ptr, idx0, idx1, kl_anneal, stream=0):
         idx0 = np.ascontiguousarray(idx0, dtype=np.int64)
         idx1 = np.ascontiguousarray(idx1, dtype=np.int64)

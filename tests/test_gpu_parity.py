@@ -236,3 +236,56 @@ def test_split_step_equals_fused_step():
         eng.close()
     np.testing.assert_array_equal(res[0][0], res[1][0])
     np.testing.assert_array_equal(res[0][1], res[1][1])
+
+
+def test_hostbatch_async_equals_sync_and_resident():
+    """Host-resident data: the asynchronous two-slot API (jb_hostbatch_submit / jb_hostbatch_wait), the synchronous
+    jb_train_step_hostbatch and the device-resident plan path run the same steps: identical losses and parameters
+    (same Philox counters: the step index, not the slot, keys the streams)."""
+    import torch
+    dims, L, B, p, n, steps = [96, 64], 8, 64, 0.4, 256, 5
+    data = U.synth_pair(n, dims, seed=21)
+    params = U.torch_like_init(dims, L, seed=22)
+    rng = np.random.default_rng(23)
+    idx = np.stack([rng.choice(n, B, replace=False) for _ in range(steps)])
+    m = (np.arange(n) % 3 != 0).astype(np.float32)
+    host = [torch.from_numpy(d).pin_memory() for d in data]
+    res = []
+    for mode in ('resident', 'sync', 'async'):
+        eng = _engine(dims, L, B, p, seed=5)
+        eng.set_params(params)
+        eng.set_prior_diag(m)
+        eng.set_f_dense(None)
+        if mode == 'resident':
+            for i in range(2):
+                eng.set_dataset(i, data[i])
+            eng.upload_plan(idx, idx, np.full(steps, 0.3))
+            eng.train_steps(steps)
+            losses = eng.read_losses(steps)[:, :6].copy()
+        else:
+            bufs = [[torch.empty((B, d), dtype=torch.float32).pin_memory() for d in dims] for _ in range(2)]
+            losses, pending = [], 0
+            for s in range(steps):
+                b = bufs[s & 1]
+                for i in range(2):
+                    torch.index_select(host[i], 0, torch.from_numpy(idx[s]), out=b[i])
+                if mode == 'sync':
+                    losses.append(eng.train_step_hostbatch(b[0].data_ptr(), b[1].data_ptr(), idx[s], idx[s], 0.3)[:6])
+                else:
+                    eng.hostbatch_submit(b[0].data_ptr(), b[1].data_ptr(), idx[s], idx[s], 0.3)
+                    pending += 1
+                    if pending == 2:
+                        losses.append(eng.hostbatch_wait()[:6])
+                        pending -= 1
+            while pending:
+                losses.append(eng.hostbatch_wait()[:6])
+                pending -= 1
+            losses = np.stack(losses)
+        res.append((losses, np.concatenate([t.ravel() for t in eng.get_params()])))
+        eng.close()
+    for other in res[1:]:
+        np.testing.assert_array_equal(other[0], res[0][0])
+        np.testing.assert_array_equal(other[1], res[0][1])
+    with pytest.raises(RuntimeError, match='no host-batch step in flight'):
+        eng = _engine(dims, L, B, p)
+        eng.hostbatch_wait()
