@@ -229,7 +229,8 @@ def workload_config(n_gpus):
         n = 50_000
     else:
         wl = f'BASELINE configs[3]: synthetic 1M-cell pair sharded over {n_gpus} ranks, widths [512,512], output_dim 32, ' \
-             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, one flat-gradient all-reduce/step'
+             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, flat-gradient all-reduce in two buckets/step '
+             f'(the first overlapped with the encoder backward)'
         n = 1_000_000
     return {'workload': wl, 'cells': n, 'widths': DIMS, 'output_dim': LATENT, 'batch_per_rank': BATCH,
             'parallelism': f'dp{n_gpus}', 'l2_policy': 'parameter + Adam state (69 MB) and gathered rows are re-read '
@@ -284,6 +285,7 @@ def main():
     idx0, idx1 = make_plan(n, W + K, rng, cs)
     eng.upload_plan(idx0, idx1, np.full(W + K, 0.5), stream)
     gt = eng.grad_tensor() if world > 1 else None
+    buckets = [eng.grad_bucket_tensor(0), eng.grad_bucket_tensor(1)] if world > 1 else None
     if args.predict_only:
         p = predict_leg(eng, torch, peaks, stream)
         print(json.dumps({k: p[k] for k in ('value', 'ms', 'e2e', 'gpu_launches')}), flush=True)
@@ -294,10 +296,8 @@ def main():
         if world == 1:
             eng.train_steps(k, stream)
         else:
-            for _ in range(k):
-                eng.step_backward(stream)
-                dist.all_reduce(gt)
-                eng.step_update(stream)
+            for _ in range(k):      # backward part 0 | all-reduce(bucket 0) beside backward part 1 | all-reduce(bucket 1) | update
+                eng.dp_step(dist, buckets, stream)
 
     def sync_all():
         if world > 1:

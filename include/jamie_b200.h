@@ -97,6 +97,12 @@ int jb_train_steps(jb_engine* e, int nsteps, void* stream);
 int jb_step_backward(jb_engine* e, void* stream);
 int jb_step_update(jb_engine* e, void* stream);
 int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats);
+/* The same data-parallel step with the exchange overlapped (world_size > 1): part 0 runs the forward pass and the backward
+ * pass down to the latent layer and completes gradient bucket 0 (heads + decoders + the loss scalars), part 1 runs the
+ * encoder backward and completes bucket 1 (sigma + encoders). The caller all-reduces bucket 0 on a second stream while
+ * part 1 runs, then bucket 1, then calls jb_step_update. The two buckets tile the buffer of jb_grad_buffer. */
+int jb_step_backward_part(jb_engine* e, int part, void* stream);
+int jb_grad_bucket(jb_engine* e, int part, float** dev_ptr, long long* n_floats);
 /* batch_step=False (jamie/jamie.py:744-749): accumulate gradients over several jb_step_backward calls.
  * accumulate != 0 makes the next backward add into the gradient buffer instead of overwriting it. */
 int jb_set_grad_accumulate(jb_engine* e, int accumulate);

@@ -100,6 +100,7 @@ struct jb_engine {
   ModSegs ms[2];
   Seg sigma;
   long long n_flat = 0;  // padded float count (multiple of 4)
+  long long n_enc = 0;   // floats [0, n_enc): sigma + both encoders; [n_enc, n_flat): heads + decoders
   std::vector<PackMap> packmap;
   long long n_packed = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
@@ -133,7 +134,9 @@ struct jb_engine {
   // GEMM tables (device) for the training step at batch size graph_B
   jb::GemmProblem* d_probs = nullptr;
   std::vector<jb::GemmProblem> h_probs;
-  GemmStage st_f[6], st_b[6];
+  GemmStage st_f[6], st_b[7];   // st_b[5]: all wgrads, or (data-parallel) heads + decoder wgrads with st_b[6] = encoder wgrads
+  cudaGraphExec_t g_bwd_part[2]{};   // data-parallel step in two halves (see build_layout)
+  int launches_bwd_part[2]{};
   int graph_B = 0;
   bool graph_accum = false;
   cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr, g_host = nullptr, g_host_bwd = nullptr;
@@ -182,11 +185,19 @@ void build_layout(jb_engine* e) {
   const int L = e->L;
   e->n_flat = 0;
   add_seg(e, e->sigma, 1, 2);
+  // Encoder tensors of both modalities first, then heads + decoders: the gradients of the second part are complete
+  // half-way through the backward pass, so the data-parallel step can all-reduce that bucket while the encoder backward
+  // still runs (jb_step_backward_part / jb_grad_bucket).
   for (int i = 0; i < 2; ++i) {
     const int D = e->D[i];
     ModSegs& m = e->ms[i];
     add_seg(e, m.W1, 2 * D, D); add_seg(e, m.b1, 1, 2 * D); add_seg(e, m.g1, 1, 2 * D); add_seg(e, m.be1, 1, 2 * D);
     add_seg(e, m.W2, D, 2 * D); add_seg(e, m.b2, 1, D); add_seg(e, m.g2, 1, D); add_seg(e, m.be2, 1, D);
+  }
+  e->n_enc = e->n_flat;
+  for (int i = 0; i < 2; ++i) {
+    const int D = e->D[i];
+    ModSegs& m = e->ms[i];
     add_seg(e, m.Wmv, 2 * L, D); add_seg(e, m.bmv, 1, 2 * L);
     add_seg(e, m.W3, D, L); add_seg(e, m.b3, 1, D); add_seg(e, m.g3, 1, D); add_seg(e, m.be3, 1, D);
     add_seg(e, m.W4, 2 * D, D); add_seg(e, m.b4, 1, 2 * D); add_seg(e, m.g4, 1, 2 * D); add_seg(e, m.be4, 1, 2 * D);
@@ -373,18 +384,26 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
   close_stage(e, e->st_b[4], first);
-  first = static_cast<int>(e->h_probs.size());       // all weight gradients (largest problems first)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D)) return 1;
-    if (wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D)) return 1;
-    if (wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D)) return 1;
-    if (wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D)) return 1; }
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (wgrad(a.dmp, a.ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D)) return 1;
-    if (wgrad(a.dy3, a.ldD, a.cp, a.LP, m.W3, D, L)) return 1; }
-  close_stage(e, e->st_b[5], first);
-  e->st_b[5].ck = 1;   // several waves of CTAs: no split-K
-  e->st_b[5].ctas = jb::gemm_table_finalize(e->h_probs.data() + first, e->st_b[5].count, 1);
+  // weight gradients (largest problems first). One rank: all twelve in one launch at the end. Data-parallel: the heads +
+  // decoder wgrads right after the latent backward (their gradient bucket is all-reduced while the encoder backward runs),
+  // the encoder wgrads at the end.
+  const bool split_w = e->cfg.world_size > 1;
+  auto wgrad_stage = [&](GemmStage& st, bool dec, bool enc) {
+    const int f0 = static_cast<int>(e->h_probs.size());
+    for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+      if (dec && (wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D) || wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D))) return 1;
+      if (enc && (wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D) || wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D))) return 1; }
+    if (dec)
+      for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        if (wgrad(a.dmp, a.ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D) || wgrad(a.dy3, a.ldD, a.cp, a.LP, m.W3, D, L)) return 1; }
+    close_stage(e, st, f0);
+    st.ck = 1;   // wide tiles, about one wave of CTAs: no split-K
+    st.ctas = jb::gemm_table_finalize(e->h_probs.data() + f0, st.count, 1);
+    return 0;
+  };
+  e->st_b[6] = GemmStage{};
+  if (split_w) { if (wgrad_stage(e->st_b[5], true, false) || wgrad_stage(e->st_b[6], false, true)) return 1; }
+  else if (wgrad_stage(e->st_b[5], true, true)) return 1;
   if (e->d_probs) cudaFree(e->d_probs);
   CU(cudaMalloc(&e->d_probs, e->h_probs.size() * sizeof(GemmProblem)));
   CU(cudaMemcpy(e->d_probs, e->h_probs.data(), e->h_probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice));
@@ -398,6 +417,7 @@ struct Rec {  // launches kernels on a stream and counts them
   // block build) run beside the encoder instead of in front of it. Null: everything is launched in order on s.
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool no_pdl_next = false;   // the next launch has a cross-stream dependency: plain (full) serialization
+  bool mute = false;          // recording the other half of a two-part backward: launches are skipped
 
   cudaEvent_t* ev = nullptr;        // profiling: ev[k] is recorded after launch k - 1 (ev[0] before the first launch)
   const char** names = nullptr;
@@ -405,6 +425,7 @@ struct Rec {  // launches kernels on a stream and counts them
     if (ev && n < 63) { names[n] = name; cudaEventRecord(ev[n + 1], s); }
   }
   void gemm(const GemmStage& st) {
+    if (mute) return;
     if (err == cudaSuccess)
       err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl && !no_pdl_next, st.ck, e->h_probs.data() + st.first);
     no_pdl_next = false;
@@ -418,6 +439,7 @@ struct Rec {  // launches kernels on a stream and counts them
 // all data dependencies (transitively) still see completed, flushed predecessors.
 template <typename... KP, typename... A>
 void launchk(Rec& r, void (*kern)(KP...), dim3 grid, dim3 block, A... args) {
+  if (r.mute) return;
   if (r.err != cudaSuccess) { ++r.n; return; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = r.s;
@@ -457,8 +479,11 @@ jb::Latent make_latent(jb_engine* e) {
   return a;
 }
 
-void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
+// part < 0: the whole forward + backward. Data-parallel halves: part 0 = everything up to the heads + decoder wgrads,
+// part 1 = encoder backward and encoder wgrads.
+void record_backward(jb_engine* e, Rec& r, int B, bool gather = true, int part = -1) {
   const int L = e->L;
+  r.mute = part == 1;
   const float p = e->cfg.dropout;
   const int accum = e->accumulate;
   const jb::StepConsts sc = make_consts(e, B);
@@ -481,7 +506,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   ca.corr = e->corr; ca.corr_t = e->corr_t; ca.fblk = e->fblk; ca.fblk_t = e->fblk_t; ca.pf_ratio = e->cfg.pf_ratio;
   {
     cudaStream_t main_s = r.s;
-    const bool fork = r.side != nullptr && r.err == cudaSuccess;
+    const bool fork = r.side != nullptr && r.err == cudaSuccess && !r.mute;
     if (fork) {
       if ((r.err = cudaEventRecord(r.ev_fork, main_s)) == cudaSuccess) r.err = cudaStreamWaitEvent(r.side, r.ev_fork, 0);
       r.s = r.side;
@@ -527,7 +552,7 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   jb::Latent lat = make_latent(e);
   launchk(r, jb::k_reparam, dim3((2 * B * L + 255) / 256), dim3(256), lat, e->ctl, B, L);
   const int wblocks = (2 * B * 32 + 255) / 256;
-  if (r.side && r.err == cudaSuccess) {   // join: the P / F blocks are complete
+  if (r.side && r.err == cudaSuccess && !r.mute) {   // join: the P / F blocks are complete
     r.err = cudaStreamWaitEvent(r.s, r.ev_join, 0);
     r.no_pdl_next = true;
   }
@@ -593,9 +618,13 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true) {
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
   fa.grad_tail = G + e->n_flat;
   launchk(r, jb::k_latent_final, dim3(1 + (4 * L + jb::SLAB_CW - 1) / jb::SLAB_CW), dim3(jb::SLAB_THREADS), fa, e->ctl, B, L, sc, accum);
+  const bool split_w = e->st_b[6].count > 0;
+  if (split_w) r.gemm(e->st_b[5]);   // heads + decoder wgrads: that gradient bucket is now complete
+  r.mute = part == 0;
   r.gemm(e->st_b[3]); bnb(1);
   r.gemm(e->st_b[4]); bnb(0);
-  r.gemm(e->st_b[5]);
+  r.gemm(split_w ? e->st_b[6] : e->st_b[5]);
+  r.mute = false;
 }
 
 void record_norm(jb_engine* e, Rec& r, int B) {
@@ -616,12 +645,14 @@ void record_update(jb_engine* e, Rec& r, int B) {
   record_adam(e, r, B, e->adam_all);
 }
 
-int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd*/, cudaGraphExec_t* out, int* nlaunch) {
+int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd, 5 / 6 bwd halves*/, cudaGraphExec_t* out,
+            int* nlaunch) {
   cudaGraph_t g = nullptr;
   CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   Rec r{e, e->cap_stream};
   if (e->use_side) { r.side = e->side_stream; r.ev_fork = e->ev_fork; r.ev_join = e->ev_join; }
   if (what == 0 || what == 1) record_backward(e, r, B);
+  if (what == 5 || what == 6) record_backward(e, r, B, true, what - 5);
   if (what == 3 || what == 4) record_backward(e, r, B, false);
   if (what == 0 || what == 2 || what == 3) record_update(e, r, B);
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
@@ -642,6 +673,9 @@ int ensure_graphs(jb_engine* e, int B) {
   if (e->data[0] && e->data[1]) {   // the gathering graphs need resident datasets; the host-batch graph does not
     if (capture(e, B, 0, &e->g_full, &e->launches_per_step)) return 1;
     if (capture(e, B, 1, &e->g_bwd, &e->launches_bwd)) return 1;
+    if (e->st_b[6].count > 0)
+      for (int h = 0; h < 2; ++h)
+        if (capture(e, B, 5 + h, &e->g_bwd_part[h], &e->launches_bwd_part[h])) return 1;
   }
   if (capture(e, B, 2, &e->g_upd, &e->launches_upd)) return 1;
   if (capture(e, B, 3, &e->g_host, &e->launches_host)) return 1;
@@ -865,6 +899,7 @@ void jb_destroy(jb_engine* e) {
   if (e->g_upd) cudaGraphExecDestroy(e->g_upd);
   if (e->g_host) cudaGraphExecDestroy(e->g_host);
   if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
+  for (auto& g : e->g_bwd_part) if (g) cudaGraphExecDestroy(g);
   if (e->snap) cudaFree(e->snap);
   if (e->h_pin) cudaFreeHost(e->h_pin);
   if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
@@ -1096,6 +1131,26 @@ int jb_step_backward(jb_engine* e, void* stream) {
   e->launches += e->launches_bwd;
   for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
   e->eval_dirty = true;
+  return 0;
+}
+int jb_step_backward_part(jb_engine* e, int part, void* stream) {
+  if (!e) return fail("null argument");
+  if (part < 0 || part > 1) return fail("part must be 0 or 1");
+  if (!e->plan_B) return fail("jb_upload_plan must be called first");
+  if (ensure_graphs(e, e->plan_B)) return 1;
+  if (!e->g_bwd_part[part]) return fail("the two-part backward needs world_size > 1 and both datasets");
+  CU(cudaGraphLaunch(e->g_bwd_part[part], static_cast<cudaStream_t>(stream)));
+  e->launches += e->launches_bwd_part[part];
+  if (part == 0) for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
+  e->eval_dirty = true;
+  return 0;
+}
+int jb_grad_bucket(jb_engine* e, int part, float** dev_ptr, long long* n_floats) {
+  if (!e || !dev_ptr || !n_floats) return fail("null argument");
+  if (part < 0 || part > 1) return fail("part must be 0 or 1");
+  // part 0 finishes the heads + decoder gradients (and the loss scalars behind the buffer), part 1 the rest
+  *dev_ptr = part == 0 ? e->grad + e->n_enc : e->grad;
+  *n_floats = part == 0 ? e->n_flat + 8 - e->n_enc : e->n_enc;
   return 0;
 }
 int jb_step_update(jb_engine* e, void* stream) {

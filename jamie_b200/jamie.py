@@ -325,6 +325,7 @@ class JAMIE(UnionCom):
         if world > 1:
             import torch.distributed as dist
             gt = eng.grad_tensor()
+            buckets = [eng.grad_bucket_tensor(0), eng.grad_bucket_tensor(1)]
         self.model.train()
 
         best_running_loss = np.inf
@@ -363,6 +364,9 @@ class JAMIE(UnionCom):
             nsteps = n_ep * len_dataloader
             if world == 1 and self.batch_step:
                 eng.train_steps(nsteps, stream)
+            elif self.batch_step:
+                for s_ in range(nsteps):      # gradient exchange overlapped with the encoder backward
+                    eng.dp_step(dist, buckets, stream)
             else:
                 for s_ in range(nsteps):
                     if not self.batch_step:
