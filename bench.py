@@ -229,7 +229,7 @@ def workload_config(n_gpus):
         n = 50_000
     else:
         wl = f'BASELINE configs[3]: synthetic 1M-cell pair sharded over {n_gpus} ranks, widths [512,512], output_dim 32, ' \
-             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, flat-gradient all-reduce in two buckets/step '
+             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, flat-gradient all-reduce in two buckets/step ' \
              f'(the first overlapped with the encoder backward)'
         n = 1_000_000
     return {'workload': wl, 'cells': n, 'widths': DIMS, 'output_dim': LATENT, 'batch_per_rank': BATCH,
