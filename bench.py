@@ -41,6 +41,9 @@ STEP_KERNELS = {
          'k_bn_bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam'],
 }
 N_PARAMS = 4312194
+# N > 1: 'single' = backward | one all-reduce of the flat gradient buffer | update (default: measured fastest at N = 2 and
+# N = 8, profiles/README.md); 'overlap' = Engine.dp_step with bucket 0 all-reduced beside the encoder backward
+DP_MODE = os.environ.get('JB_DP_MODE', 'single')
 
 
 def load_peaks():
@@ -229,8 +232,7 @@ def workload_config(n_gpus):
         n = 50_000
     else:
         wl = f'BASELINE configs[3]: synthetic 1M-cell pair sharded over {n_gpus} ranks, widths [512,512], output_dim 32, ' \
-             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, flat-gradient all-reduce in two buckets/step ' \
-             f'(the first overlapped with the encoder backward)'
+             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, one flat-gradient all-reduce/step'
         n = 1_000_000
     return {'workload': wl, 'cells': n, 'widths': DIMS, 'output_dim': LATENT, 'batch_per_rank': BATCH,
             'parallelism': f'dp{n_gpus}', 'l2_policy': 'parameter + Adam state (69 MB) and gathered rows are re-read '
@@ -260,6 +262,8 @@ def main():
         args.gpus = world
     torch.cuda.set_device(local)
     if world > 1:
+        # 17 MB all-reduce per step: measured on 8 B200 375.7 us/step with NVLS off vs 392.5 us/step with NCCL's default
+        os.environ.setdefault('NCCL_NVLS_ENABLE', '0')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from jamie_b200.engine import Engine
     peaks = load_peaks()
@@ -296,8 +300,14 @@ def main():
         if world == 1:
             eng.train_steps(k, stream)
         else:
-            for _ in range(k):      # backward part 0 | all-reduce(bucket 0) beside backward part 1 | all-reduce(bucket 1) | update
-                eng.dp_step(dist, buckets, stream)
+            if DP_MODE == 'single':
+                for _ in range(k):  # backward | one all-reduce of the flat gradient buffer | update
+                    eng.step_backward(stream)
+                    dist.all_reduce(gt)
+                    eng.step_update(stream)
+            else:                   # backward part 0 | all-reduce(bucket 0) beside backward part 1 | all-reduce(bucket 1) | update
+                for _ in range(k):
+                    eng.dp_step(dist, buckets, stream, overlap=DP_MODE == 'overlap')
 
     def sync_all():
         if world > 1:

@@ -136,6 +136,7 @@ struct jb_engine {
   std::vector<jb::GemmProblem> h_probs;
   GemmStage st_f[6], st_b[7];   // st_b[5]: all wgrads, or (data-parallel) heads + decoder wgrads with st_b[6] = encoder wgrads
   cudaGraphExec_t g_bwd_part[2]{};   // data-parallel step in two halves (see build_layout)
+  bool dp_split = false;             // set by the first jb_step_backward_part: wgrads in two launches
   int launches_bwd_part[2]{};
   int graph_B = 0;
   bool graph_accum = false;
@@ -384,10 +385,10 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
   close_stage(e, e->st_b[4], first);
-  // weight gradients (largest problems first). One rank: all twelve in one launch at the end. Data-parallel: the heads +
-  // decoder wgrads right after the latent backward (their gradient bucket is all-reduced while the encoder backward runs),
-  // the encoder wgrads at the end.
-  const bool split_w = e->cfg.world_size > 1;
+  // weight gradients (largest problems first): all twelve in one launch at the end. Two-part data-parallel backward
+  // (jb_step_backward_part): the heads + decoder wgrads right after the latent backward (their gradient bucket is
+  // all-reduced while the encoder backward runs), the encoder wgrads at the end.
+  const bool split_w = e->dp_split;
   auto wgrad_stage = [&](GemmStage& st, bool dec, bool enc) {
     const int f0 = static_cast<int>(e->h_probs.size());
     for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -1137,8 +1138,10 @@ int jb_step_backward_part(jb_engine* e, int part, void* stream) {
   if (!e) return fail("null argument");
   if (part < 0 || part > 1) return fail("part must be 0 or 1");
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
+  if (e->cfg.world_size <= 1) return fail("the two-part backward is the data-parallel form: it needs world_size > 1");
+  if (!e->dp_split) { e->dp_split = true; reset_graphs(e); }   // rebuild the tables with the wgrads in two launches
   if (ensure_graphs(e, e->plan_B)) return 1;
-  if (!e->g_bwd_part[part]) return fail("the two-part backward needs world_size > 1 and both datasets");
+  if (!e->g_bwd_part[part]) return fail("jb_set_dataset must be called for both modalities before jb_step_backward_part");
   CU(cudaGraphLaunch(e->g_bwd_part[part], static_cast<cudaStream_t>(stream)));
   e->launches += e->launches_bwd_part[part];
   if (part == 0) for (int k = 0; k < 8; ++k) e->nbt[k] += 1;

@@ -246,14 +246,20 @@ class Engine:
     def step_backward_part(self, part, stream=0):
         _lib.check(self.lib.jb_step_backward_part(self.h, int(part), C.c_void_p(stream)))
 
-    def dp_step(self, dist, buckets, stream=0):
-        """One data-parallel optimizer step with the gradient exchange overlapped: bucket 0 (heads + decoders) is
-        all-reduced on the process group's stream while the encoder backward still runs. `buckets` =
-        [grad_bucket_tensor(0), grad_bucket_tensor(1)]; `stream` must be torch's current stream."""
-        self.step_backward_part(0, stream)
-        w0 = dist.all_reduce(buckets[0], async_op=True)
-        self.step_backward_part(1, stream)
-        w1 = dist.all_reduce(buckets[1], async_op=True)
+    def dp_step(self, dist, buckets, stream=0, overlap=True):
+        """One data-parallel optimizer step. overlap: gradient bucket 0 (heads + decoders) is all-reduced on the process
+        group's stream while the encoder backward still runs, then bucket 1; otherwise one backward graph and both
+        buckets after it. `buckets` = [grad_bucket_tensor(0), grad_bucket_tensor(1)]; `stream` must be torch's current
+        stream."""
+        if not overlap:
+            self.step_backward(stream)
+            w1 = dist.all_reduce(buckets[1], async_op=True)     # the two buckets tile the buffer: two calls, no copy
+            w0 = dist.all_reduce(buckets[0], async_op=True)
+        else:
+            self.step_backward_part(0, stream)
+            w0 = dist.all_reduce(buckets[0], async_op=True)
+            self.step_backward_part(1, stream)
+            w1 = dist.all_reduce(buckets[1], async_op=True)
         w0.wait()
         w1.wait()
         self.step_update(stream)

@@ -364,8 +364,8 @@ class JAMIE(UnionCom):
             nsteps = n_ep * len_dataloader
             if world == 1 and self.batch_step:
                 eng.train_steps(nsteps, stream)
-            elif self.batch_step:
-                for s_ in range(nsteps):      # gradient exchange overlapped with the encoder backward
+            elif self.batch_step and os.environ.get('JB_DP_MODE', 'single') == 'overlap':
+                for s_ in range(nsteps):      # gradient exchange overlapped with the encoder backward (opt-in)
                     eng.dp_step(dist, buckets, stream)
             else:
                 for s_ in range(nsteps):
