@@ -123,8 +123,6 @@ struct jb_engine {
   int plan_cap = 0, plan_steps = 0, plan_B = 0;
   jb::Ctl* ctl = nullptr;
   double* norm_part = nullptr;
-  jb::AdamSnap* snap = nullptr;
-  jb::AdamRanges adam_all{};   // the whole flat buffer as one optimizer range
   // workspaces
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -226,9 +224,6 @@ void build_layout(jb_engine* e) {
     whole(m.W3); whole(m.b3); whole(m.g3); whole(m.be3); whole(m.W4); whole(m.b4); whole(m.g4); whole(m.be4);
     whole(m.W5); whole(m.b5);
   }
-  // optimizer ranges (float4 indices; every tensor starts on a 32-float boundary)
-  e->adam_all = jb::AdamRanges{};
-  e->adam_all.begin4[0] = 0; e->adam_all.end4[0] = e->n_flat / 4; e->adam_all.n = 1;
   // BatchNorm running stats
   const int widths[8] = {2 * e->D[0], e->D[0], 2 * e->D[1], e->D[1], e->D[0], 2 * e->D[0], e->D[1], 2 * e->D[1]};
   long long off = 0;
@@ -628,22 +623,11 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true, int part =
   r.mute = false;
 }
 
-void record_norm(jb_engine* e, Rec& r, int B) {
-  const jb::StepConsts sc = make_consts(e, B);
-  launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, e->n_flat / 4, e->norm_part, e->ctl, sc, e->out_loss, e->snap);
-}
-void record_adam(jb_engine* e, Rec& r, int B, const jb::AdamRanges& rg) {
-  const jb::StepConsts sc = make_consts(e, B);
-  long long total = 0;
-  for (int k = 0; k < rg.n; ++k) total += rg.end4[k] - rg.begin4[k];
-  long long blocks = (total + 511) / 512;   // two float4 per thread
-  if (blocks > jb::NORM_BLOCKS * 2) blocks = jb::NORM_BLOCKS * 2;
-  if (blocks < 1) blocks = 1;
-  launchk(r, jb::k_adam, dim3(static_cast<unsigned>(blocks)), dim3(256), e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, rg, e->snap, sc);
-}
 void record_update(jb_engine* e, Rec& r, int B) {
-  record_norm(e, r, B);
-  record_adam(e, r, B, e->adam_all);
+  const jb::StepConsts sc = make_consts(e, B);
+  const long long n4 = e->n_flat / 4;
+  launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, n4, e->norm_part);
+  launchk(r, jb::k_adam, jb::NORM_BLOCKS * 2, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
 }
 
 int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd, 5 / 6 bwd halves*/, cudaGraphExec_t* out,
@@ -860,8 +844,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   c0.seed = cfg->seed;
   CU(cudaMemcpy(e->ctl, &c0, sizeof c0, cudaMemcpyHostToDevice));
   CU(cudaMalloc(&e->norm_part, jb::NORM_BLOCKS * sizeof(double)));
-  CU(cudaMalloc(&e->snap, sizeof(jb::AdamSnap)));
-  CU(cudaMemset(e->snap, 0, sizeof(jb::AdamSnap)));
   CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -901,7 +883,6 @@ void jb_destroy(jb_engine* e) {
   if (e->g_host) cudaGraphExecDestroy(e->g_host);
   if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
   for (auto& g : e->g_bwd_part) if (g) cudaGraphExecDestroy(g);
-  if (e->snap) cudaFree(e->snap);
   if (e->h_pin) cudaFreeHost(e->h_pin);
   if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
   for (int k = 0; k < 2; ++k) {

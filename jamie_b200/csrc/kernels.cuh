@@ -73,7 +73,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------ step control
 // The first kernel of a step (k_gather / k_split_x) derives the step's scalars: every block reads the plan cursor
 // (nobody writes it while that kernel runs) and one thread publishes the derived values for the later kernels. The
-// cursor and the Adam step count advance later in the step (k_reparam); the injection flag is cleared by k_gradnorm.
+// cursor and the Adam step count advance later in the step (k_reparam); the injection flag is cleared by k_adam.
 __device__ __forceinline__ void step_begin(Ctl* ctl, const float* __restrict__ plan_kl, const StepConsts& sc) {
   const long long row = ctl->cursor;
   const long long t = ctl->adam_t + 1;
@@ -988,24 +988,10 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_latent_final(FinalArgs a, cons
 }
 
 // ------------------------------------------------------------------------------------------------ clip + Adam
-// What the optimizer update of a step needs, frozen by k_gradnorm when the step's gradient norm is known: the update
-// kernels read this snapshot instead of the step control block, so they may run beside the NEXT step's forward pass
-// (whose first kernel rewrites the control block).
-struct AdamSnap {
-  float coef;           // grad_scale * clip coefficient
-  float step_size;      // lr / (1 - beta1^t)
-  float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
-  unsigned ticket;      // blocks of the running k_gradnorm that have stored their partial
-};
-
-// Per-block partials of sum g^2 over the padded flat buffer (padding is zero); the LAST block to finish re-reduces all
-// partials in a fixed order (the result does not depend on which block that is), derives the clip coefficient
-// (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), jamie/jamie.py:739) and freezes the snapshot.
-__global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, long long n4, double* part, Ctl* ctl,
-                                                  StepConsts sc, float* __restrict__ out_loss, AdamSnap* snap) {
+// Phase 1: per-block partial of sum g^2 over the padded flat buffer (padding is zero).
+__global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, long long n4, double* __restrict__ part) {
   pdl_prologue();
   __shared__ double red[256];
-  __shared__ bool last;
   double s = 0.0;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
@@ -1019,16 +1005,29 @@ __global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, l
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    part[blockIdx.x] = red[0];
-    __threadfence();
-    last = atomicAdd(&snap->ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  s = 0.0;
-  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 256) s += __ldcg(part + i);
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+// Phase 2: every block re-reduces the partials in the same order (identical clip coefficient everywhere), then
+// g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* __restrict__ theta_hi,
+                                              float* __restrict__ theta_lo, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, long long n4, const double* __restrict__ part,
+                                              int nparts, Ctl* ctl, StepConsts sc,
+                                              float* __restrict__ out_loss) {
+  pdl_prologue();
+  __shared__ double red[256];
+  __shared__ float s_coef;
+  float4* t4 = reinterpret_cast<float4*>(theta);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  // the first element's operands are requested before the norm is reduced: the HBM latency hides behind the reduction
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), mm = gg, vv = gg, tt = gg;
+  if (i < n4) { gg = __ldg(g4 + i); mm = m4[i]; vv = v4[i]; tt = t4[i]; }
+  double s = 0.0;
+  for (int k = threadIdx.x; k < nparts; k += 256) s += part[k];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -1038,58 +1037,38 @@ __global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, l
   if (threadIdx.x == 0) {
     const double norm = sqrt(red[0]) * static_cast<double>(sc.grad_scale);
     const double coef = fmin(1.0, static_cast<double>(sc.max_norm) / (norm + 1e-6));
-    snap->coef = static_cast<float>(coef) * sc.grad_scale;
-    snap->step_size = ctl->step_size;
-    snap->inv_bc2_sqrt = ctl->inv_bc2_sqrt;
-    snap->ticket = 0u;
-    out_loss[static_cast<long long>(ctl->row) * 8 + 5] = static_cast<float>(norm);
-    ctl->inject = 0;   // injected eps / masks serve exactly one step
+    s_coef = static_cast<float>(coef) * sc.grad_scale;
+    if (blockIdx.x == 0) {
+      out_loss[static_cast<long long>(ctl->row) * 8 + 5] = static_cast<float>(norm);
+      ctl->inject = 0;   // injected eps / masks serve exactly one step
+    }
   }
-}
-
-// g *= coef;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741) over up to four ranges of
-// the flat buffer (float4 indices); also rewrites the TF32 hi / lo operand planes of the updated weights.
-struct AdamRanges {
-  long long begin4[4], end4[4];
-  int n;
-};
-__global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* __restrict__ theta_hi,
-                                              float* __restrict__ theta_lo, const float* __restrict__ g, float* __restrict__ m,
-                                              float* __restrict__ v, AdamRanges rg, const AdamSnap* __restrict__ snap,
-                                              StepConsts sc) {
-  pdl_prologue();
-  const float coef = snap->coef;
+  __syncthreads();
+  const float coef = s_coef;
   const float b1 = sc.beta1, b2 = sc.beta2, eps = sc.adam_eps;
-  const float step = snap->step_size, ibc2 = snap->inv_bc2_sqrt;
-  float4* t4 = reinterpret_cast<float4*>(theta);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  float4* m4 = reinterpret_cast<float4*>(m);
-  float4* v4 = reinterpret_cast<float4*>(v);
-  long long total = 0;
-  for (int k = 0; k < rg.n; ++k) total += rg.end4[k] - rg.begin4[k];
-  for (long long j = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; j < total; j += static_cast<long long>(gridDim.x) * 256) {
-    long long i = j;
-    int k = 0;
-    while (k + 1 < rg.n && i >= rg.end4[k] - rg.begin4[k]) { i -= rg.end4[k] - rg.begin4[k]; ++k; }
-    i += rg.begin4[k];
-    const float4 gg = __ldg(g4 + i);
-    float4 mm = m4[i], vv = v4[i], tt = t4[i];
+  const float step = ctl->step_size, ibc2 = ctl->inv_bc2_sqrt;
+  while (i < n4) {
+    const long long nx = i + stride;
+    float4 gn = gg, mn = mm, vn = vv, tn = tt;
+    if (nx < n4) { gn = __ldg(g4 + nx); mn = m4[nx]; vn = v4[nx]; tn = t4[nx]; }   // next element in flight
     const float gx[4] = {gg.x * coef, gg.y * coef, gg.z * coef, gg.w * coef};
     float* mp = reinterpret_cast<float*>(&mm);
     float* vp = reinterpret_cast<float*>(&vv);
     float* tp = reinterpret_cast<float*>(&tt);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      mp[q] = mp[q] + (gx[q] - mp[q]) * (1.f - b1);
-      vp[q] = vp[q] * b2 + gx[q] * gx[q] * (1.f - b2);
-      const float denom = sqrtf(vp[q]) * ibc2 + eps;
-      tp[q] = tp[q] - step * (mp[q] / denom);
+    for (int k = 0; k < 4; ++k) {
+      mp[k] = mp[k] + (gx[k] - mp[k]) * (1.f - b1);
+      vp[k] = vp[k] * b2 + gx[k] * gx[k] * (1.f - b2);
+      const float denom = sqrtf(vp[k]) * ibc2 + eps;
+      tp[k] = tp[k] - step * (mp[k] / denom);
     }
     m4[i] = mm; v4[i] = vv; t4[i] = tt;
     float4 th, tl;   // the updated weights as GEMM operand planes for the next step
     tf32_split(tt.x, th.x, tl.x); tf32_split(tt.y, th.y, tl.y); tf32_split(tt.z, th.z, tl.z); tf32_split(tt.w, th.w, tl.w);
     reinterpret_cast<float4*>(theta_hi)[i] = th;
     reinterpret_cast<float4*>(theta_lo)[i] = tl;
+    gg = gn; mm = mn; vv = vn; tt = tn;
+    i = nx;
   }
 }
 // theta -> (theta_hi, theta_lo) over the whole flat buffer (after jb_set_params)
