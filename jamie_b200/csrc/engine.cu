@@ -106,8 +106,7 @@ struct jb_engine {
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
   float *theta_hi = nullptr, *theta_lo = nullptr;   // TF32 planes of theta (same layout), rewritten by every Adam step
   float* state_slab = nullptr;   // one allocation: theta | adam_m | adam_v | theta_hi | theta_lo
-  size_t slab_bytes = 0, persist_bytes = 0, window_max = 0;
-  bool l2_persist = true;        // JB_L2_PERSIST=0: no persisting-L2 window for the optimizer state
+  size_t slab_bytes = 0;
   // BatchNorm running statistics: 8 layers in packed order (enc0.1, enc0.5, enc1.1, enc1.5, dec0.1, dec0.5, dec1.1, dec1.5)
   float* bn_run = nullptr;
   long long bn_off[8]{};
@@ -417,7 +416,7 @@ struct Rec {  // launches kernels on a stream and counts them
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool no_pdl_next = false;   // the next launch has a cross-stream dependency: plain (full) serialization
   bool mute = false;          // recording the other half of a two-part backward: launches are skipped
-  bool persist_next = false;  // the next launch gets the persisting-L2 window over the optimizer state
+
 
   cudaEvent_t* ev = nullptr;        // profiling: ev[k] is recorded after launch k - 1 (ev[0] before the first launch)
   const char** names = nullptr;
@@ -443,24 +442,13 @@ void launchk(Rec& r, void (*kern)(KP...), dim3 grid, dim3 block, A... args) {
   if (r.err != cudaSuccess) { ++r.n; return; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = r.s;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[1];
   int na = 0;
   if (r.e->use_pdl && !r.no_pdl_next) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (r.persist_next && r.e->l2_persist) {   // this kernel sweeps the optimizer state: keep it in the persisting part of L2
-    size_t bytes = r.e->slab_bytes < r.e->window_max ? r.e->slab_bytes : r.e->window_max;
-    at[na].id = cudaLaunchAttributeAccessPolicyWindow;
-    at[na].val.accessPolicyWindow.base_ptr = r.e->state_slab;
-    at[na].val.accessPolicyWindow.num_bytes = bytes;
-    at[na].val.accessPolicyWindow.hitRatio = bytes > 0 ? static_cast<float>(r.e->persist_bytes < bytes ? static_cast<double>(r.e->persist_bytes) / bytes : 1.0) : 0.f;
-    at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    ++na;
-  }
-  r.persist_next = false;
   cfg.attrs = at;
   cfg.numAttrs = na;
   r.no_pdl_next = false;
@@ -646,7 +634,6 @@ void record_update(jb_engine* e, Rec& r, int B) {
   const jb::StepConsts sc = make_consts(e, B);
   const long long n4 = e->n_flat / 4;
   launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, n4, e->norm_part);
-  r.persist_next = true;
   launchk(r, jb::k_adam, jb::NORM_BLOCKS * 2, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
 }
 
@@ -843,23 +830,14 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
     CU(cudaMemset(*p, 0, bytes));
     return 0;
   };
-  // theta, the Adam moments and the operand planes live in ONE slab (fb is a multiple of 128 B) so that a single L2
-  // access-policy window can cover the optimizer state (see persist_window)
+  // theta, the Adam moments and the operand planes live in ONE slab (fb is a multiple of 128 B). A persisting-L2
+  // access-policy window over it for k_adam was measured on B200: 268.8 vs 266.5 us/step without (the set-aside L2 is
+  // missed by the activations), so none is set.
   e->slab_bytes = 5 * fb;
   if (alloc0(&e->state_slab, e->slab_bytes) || alloc0(&e->grad, fb) || alloc0(&e->theta_eval, fb) ||
       alloc0(&e->bn_run, e->n_bn * 4)) { jb_destroy(e); return 1; }
   e->theta = e->state_slab; e->adam_m = e->theta + fb / 4; e->adam_v = e->adam_m + fb / 4;
   e->theta_hi = e->adam_v + fb / 4; e->theta_lo = e->theta_hi + fb / 4;
-  if (const char* pv = getenv("JB_L2_PERSIST")) e->l2_persist = atoi(pv) != 0;
-  if (e->l2_persist) {
-    // Keep the optimizer state (theta, m, v: 52 MB at the headline shapes; with the planes 86 MB) resident in the
-    // persisting part of L2 across steps: the Adam sweep then reads it from L2 instead of HBM.
-    size_t want = e->slab_bytes < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? e->slab_bytes : static_cast<size_t>(prop.persistingL2CacheMaxSize);
-    if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); e->l2_persist = false; }
-    e->persist_bytes = want;
-    e->window_max = static_cast<size_t>(prop.accessPolicyMaxWindowSize);
-    if (getenv("JB_DEBUG_STAGES")) fprintf(stderr, "L2 persist: slab %zu B, set-aside %zu B, max window %zu B\n", e->slab_bytes, want, e->window_max);
-  }
   {  // BatchNorm defaults: running_mean 0, running_var 1; gamma = 1 is set through jb_set_params
     std::vector<float> h(e->n_bn, 0.f);
     for (int k = 0; k < 8; ++k)
@@ -911,7 +889,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
 void jb_destroy(jb_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
-  if (e->l2_persist) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
   if (e->g_full) cudaGraphExecDestroy(e->g_full);
   if (e->g_bwd) cudaGraphExecDestroy(e->g_bwd);
   if (e->g_upd) cudaGraphExecDestroy(e->g_upd);
