@@ -152,7 +152,6 @@ struct jb_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
   int wgrad_bn = 256;        // widest N tile of the batched wgrad launch
-  bool wide_split = true;    // 128-column 3xTF32 tiles where the stage still splits K (JB_WIDE_SPLIT=0: always 64)
   int slab_cw = 16;          // columns per block of the BatchNorm / reconstruction slab kernels: 16 (1024 threads) or 8 (512)
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
@@ -307,26 +306,9 @@ int add_prob(jb_engine* e, Planes A, int lda, int a_mn, Planes Bm, int ldb, int 
   e->h_probs.push_back(g);
   return 0;
 }
-// N tiles of the two 3xTF32 problems of a forward / dgrad stage (outputs [B, N_i], contraction K_i). Default 64 columns
-// (more CTAs beat wider tiles at these sizes). Wide = 128 columns when the stage then still splits K over a cluster and a
-// CTA accumulates at most 16 k-blocks (the wide tile does not drain its accumulators, gemm_tf32.cuh): a 128 x 128 tile with
-// half the K moves 512 KB of operands into a CTA instead of 768 KB for 128 x 64 with the whole K.
-void choose_bns(const jb_engine* e, int B, const int N[2], const int K[2], int bn[2]) {
-  for (int i = 0; i < 2; ++i) bn[i] = N[i] <= 32 ? 32 : 64;
-  if (!e->wide_split || !e->use_splitk || e->precision_fast) return;
-  int wide[2], tiles = 0, min_kb = 1 << 30, max_kb = 0;
-  for (int i = 0; i < 2; ++i) {
-    wide[i] = N[i] >= 256 ? 128 : bn[i];
-    tiles += ((B + 127) / 128) * ((N[i] + wide[i] - 1) / wide[i]);
-    const int kb = (K[i] + 31) / 32;
-    min_kb = kb < min_kb ? kb : min_kb;
-    max_kb = kb > max_kb ? kb : max_kb;
-  }
-  if (wide[0] != 128 && wide[1] != 128) return;
-  int ck = 1;
-  for (int c = 4; c > 1; c >>= 1)
-    if (tiles * c <= e->num_sms && min_kb >= 4 * c) { ck = c; break; }
-  if (ck >= 2 && (max_kb + ck - 1) / ck <= 16) { bn[0] = wide[0]; bn[1] = wide[1]; }
+int choose_bn(int N) {
+  if (N <= 32) return 32;
+  return 64;  // more CTAs beat wider tiles at these problem sizes
 }
 // Closes the stage made of h_probs[first ..]: picks its split-K factor and assigns CTA ranges.
 void close_stage(jb_engine* e, GemmStage& st, int first) {
@@ -351,30 +333,21 @@ int build_train_tables(jb_engine* e, int B, int accum) {
     close_stage(e, st, f0);
     return 0;
   };
-  // widths by code, so that a stage's tile widths can be chosen from BOTH modalities' shapes: 0 D, 1 2D, 2 L, 3 2L
-  auto width = [&](int code, int i) { return code == 0 ? e->D[i] : (code == 1 ? 2 * e->D[i] : (code == 2 ? L : 2 * L)); };
-  auto stage_bn = [&](int i, int n_code, int k_code) {
-    const int N[2] = {width(n_code, 0), width(n_code, 1)}, K[2] = {width(k_code, 0), width(k_code, 1)};
-    int bn[2];
-    choose_bns(e, B, N, K, bn);
-    return bn[i];
+  auto lin = [&](Planes X, int ldx, const Seg& w, const Seg& b, float* Y, int ldy, int n_out, int n_in) {
+    return add_prob(e, X, ldx, 0, W(w), w.ld, 0, Y, ldy, B, n_out, n_in, choose_bn(n_out), jb::EPI_BIAS, bias(b), 0, 1);
   };
-  auto lin = [&](int i, Planes X, int ldx, const Seg& w, const Seg& b, float* Y, int ldy, int n_code, int k_code) {
-    return add_prob(e, X, ldx, 0, W(w), w.ld, 0, Y, ldy, B, width(n_code, i), width(k_code, i), stage_bn(i, n_code, k_code),
-                    jb::EPI_BIAS, bias(b), 0, 1);
-  };
-  if (fwd(e->st_f[0], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-        return lin(i, a.xp, a.ldD, m.W1, m.b1, a.y1, a.ld2D, 1, 0); })) return 1;
-  if (fwd(e->st_f[1], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-        return lin(i, a.h1, a.ld2D, m.W2, m.b2, a.y2, a.ldD, 0, 1); })) return 1;
-  if (fwd(e->st_f[2], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-        return lin(i, a.h2, a.ldD, m.Wmv, m.bmv, a.mulv, a.ldmv, 3, 0); })) return 1;
-  if (fwd(e->st_f[3], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-        return lin(i, a.cp, a.LP, m.W3, m.b3, a.y3, a.ldD, 0, 2); })) return 1;
-  if (fwd(e->st_f[4], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-        return lin(i, a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 1, 0); })) return 1;
-  if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-        return lin(i, a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, 0, 1); })) return 1;
+  if (fwd(e->st_f[0], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.xp, a.ldD, m.W1, m.b1, a.y1, a.ld2D, 2 * D, D); })) return 1;
+  if (fwd(e->st_f[1], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.h1, a.ld2D, m.W2, m.b2, a.y2, a.ldD, D, 2 * D); })) return 1;
+  if (fwd(e->st_f[2], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.h2, a.ldD, m.Wmv, m.bmv, a.mulv, a.ldmv, 2 * L, D); })) return 1;
+  if (fwd(e->st_f[3], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.cp, a.LP, m.W3, m.b3, a.y3, a.ldD, D, L); })) return 1;
+  if (fwd(e->st_f[4], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D); })) return 1;
+  if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+        return lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D); })) return 1;
   // ---- backward: dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out): one stage
   //                per layer on the critical path;
   //                wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass): nothing
@@ -386,29 +359,28 @@ int build_train_tables(jb_engine* e, int B, int accum) {
     const int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
     return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, bn, jb::EPI_STORE, nullptr, accum, 0);
   };
-  auto dgrad = [&](int i, Planes dY, int lddy, const Seg& s, float* dX, int lddx, int out_code, int in_code) {
-    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, width(in_code, i), width(out_code, i), stage_bn(i, in_code, out_code),
-                    jb::EPI_STORE, nullptr, 0, 1);
+  auto dgrad = [&](Planes dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
+    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in), jb::EPI_STORE, nullptr, 0, 1);
   };
   int first = static_cast<int>(e->h_probs.size());   // B6: last decoder Linear(2D -> D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-    if (dgrad(i, a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, 0, 1)) return 1; }
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, D, 2 * D)) return 1; }
   close_stage(e, e->st_b[0], first);
   first = static_cast<int>(e->h_probs.size());       // B5: decoder Linear(D -> 2D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-    if (dgrad(i, a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 1, 0)) return 1; }
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 2 * D, D)) return 1; }
   close_stage(e, e->st_b[1], first);
   first = static_cast<int>(e->h_probs.size());       // B4: decoder Linear(L -> D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-    if (dgrad(i, a.dy3, a.ldD, m.W3, a.dc, a.LP, 0, 2)) return 1; }
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dy3, a.ldD, m.W3, a.dc, a.LP, D, L)) return 1; }
   close_stage(e, e->st_b[2], first);
   first = static_cast<int>(e->h_probs.size());       // B3: heads Linear(D -> 2L)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-    if (dgrad(i, a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 3, 0)) return 1; }
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
   close_stage(e, e->st_b[3], first);
   first = static_cast<int>(e->h_probs.size());       // B2: encoder Linear(2D -> D); Linear(D -> 2D) needs no input gradient
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-    if (dgrad(i, a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, 0, 1)) return 1; }
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
   close_stage(e, e->st_b[4], first);
   // weight gradients (largest problems first): all twelve in one launch at the end. Two-part data-parallel backward
   // (jb_step_backward_part): the heads + decoder wgrads right after the latent backward (their gradient bucket is
@@ -890,7 +862,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
-  if (const char* pv = getenv("JB_WIDE_SPLIT")) e->wide_split = atoi(pv) != 0;
   if (const char* pv = getenv("JB_SLAB_CW")) e->slab_cw = atoi(pv) == 8 ? 8 : 16;
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;

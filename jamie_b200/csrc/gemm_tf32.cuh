@@ -145,11 +145,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
   const int kb_bytes = (GEMM_A_STAGE_BYTES + b_bytes) * (split ? 2 : 1);   // one ring slot = one k-block
   int nstages = GEMM_TILE_SMEM / kb_bytes;
   if (nstages > GEMM_MAX_STAGES) nstages = GEMM_MAX_STAGES;
-  // split, bn <= 64: [big0 | small0 | big1 | small1], bn columns each, the big buffers drained every GEMM_DRAIN_KB
-  // k-blocks (see the MMA issuer). split, bn = 128 (wide tiles, always combined with split-K so that a CTA accumulates
-  // few k-blocks): [big | small] accumulated in TMEM over the CTA's whole K share, no drain.
-  const bool nodrain = split && bn > 64;
-  const uint32_t tmem_cols = static_cast<uint32_t>(split ? (nodrain ? 2 * bn : 4 * bn) : bn);
+  // split: [big0 | small0 | big1 | small1], bn columns each (see the MMA issuer); bn in {32, 64}: a power of two >= 32
+  const uint32_t tmem_cols = static_cast<uint32_t>(split ? 4 * bn : bn);
   // offsets inside a ring slot
   const int off_alo = GEMM_A_STAGE_BYTES;                        // split only
   const int off_b = split ? 2 * GEMM_A_STAGE_BYTES : GEMM_A_STAGE_BYTES;
@@ -240,25 +237,14 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
       mbar_wait(&ctrl->full[s], ph);
       const int chunk = kb / GEMM_DRAIN_KB;
       const bool chunk_start = kb % GEMM_DRAIN_KB == 0;
-      if (split && !nodrain && chunk_start && chunk >= 2) mbar_wait(&ctrl->acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);   // buffer drained
+      if (split && chunk_start && chunk >= 2) mbar_wait(&ctrl->acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);   // buffer drained
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = tiles_u32 + s * kb_bytes;   // 1024-aligned: (addr >> 4) + k*step never carries out of
         const uint32_t sb = sa + off_b;                 // the 14-bit start-address field
         const uint64_t da0 = da_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
         const uint64_t db0 = db_hi | static_cast<uint64_t>((sb >> 4) & 0x3FFFu);
-        if (nodrain) {
-          // wide tile: hi(A) * [hi(B) ; lo(B)] -> big | small (one N = 2 bn = 256 instruction), lo(A) * hi(B) -> small
-          const uint32_t blo16 = static_cast<uint32_t>(b_bytes) >> 4;
-          (void)blo16;
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-            const uint64_t da = da0 + k * a_step16, db = db0 + k * b_step16;
-            umma_tf32(tmem_d, da, db, idesc2, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32(tmem_d + static_cast<uint32_t>(bn), da + alo16, db, idesc, 1u);
-          }
-          umma_commit(&ctrl->empty[s]);
-        } else if (split) {
+        if (split) {
           // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
           // accumulation steps (measured: 2.4e-6 relative at K = 512, 9e-6 at K = 2000). So the dominant hi*hi sum is
           // accumulated in TMEM for a chunk of GEMM_DRAIN_KB k-blocks (8 steps) only: "big" buffer b = chunk & 1 is
@@ -293,13 +279,13 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
       __syncwarp();
       if (++s == nstages) { s = 0; ph ^= 1; }
     }
-    if ((!split || nodrain) && elect_one()) umma_commit(&ctrl->tmem_full);  // accumulator complete
+    if (!split && elect_one()) umma_commit(&ctrl->tmem_full);  // accumulator complete
     __syncwarp();
   } else {
     // ------------------------------------------------ epilogue warps, phase 1: wait for (and, split, drain) the MMAs
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
-    if (split && !nodrain) {
+    if (split) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) { run[0][j] = 0.f; run[1][j] = 0.f; }
       const int num_chunks = (num_kb + GEMM_DRAIN_KB - 1) / GEMM_DRAIN_KB;
@@ -340,14 +326,7 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     // this thread's row of the CTA's partial tile, columns [c0, c0 + 32)
     auto load_chunk = [&](int c0, float (&v)[32]) {
       const uint32_t taddr = lane_base + static_cast<uint32_t>(c0);
-      if (nodrain) {
-        float w[32];
-        tmem_ld_32x32(taddr, v);                               // big: hi * hi
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(bn), w);   // small: hi * lo + lo * hi
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
-      } else if (split) {
+      if (split) {
         tmem_ld_32x32(taddr + static_cast<uint32_t>(bn), v);   // small0: correction terms of the even chunks
         tmem_ld_wait();
         if (num_kb > GEMM_DRAIN_KB) {   // more than one chunk: buffer 1 was used
@@ -524,7 +503,7 @@ inline int gemm_problem_fill(GemmProblem* g, const float* A, int lda, int a_mn, 
   g->slope = slope;
   g->accumulate = accumulate;
   g->split = split;
-  if (split && bn > 128) return -2;   // split tiles: bn <= 64 (drained accumulators) or 128 (no drain, used with split-K)
+  if (split && bn > 64) return -2;   // the split epilogue keeps bn <= 64 running sums in registers
   return 0;
 }
 

@@ -159,10 +159,6 @@ int main(int argc, char** argv) {
         {700, 64, 1302, 0, 0, 64, 1, jb::EPI_BIAS_LRELU, 0, 4}, {130, 39, 300, 1, 1, 64, 1, jb::EPI_STORE, 1, 2},
         {64, 512, 512, 1, 1, 64, 0, jb::EPI_STORE, 0, 4},    {1024, 512, 512, 1, 1, 128, 0, jb::EPI_STORE, 1, 2},
         {256, 128, 160, 0, 0, 64, 0, jb::EPI_BIAS, 0, 4},    {100, 130, 70, 1, 0, 32, 1, jb::EPI_STORE, 0, 2},
-        // wide 3xTF32 tiles (128 columns, accumulators not drained) with split-K
-        {512, 1024, 512, 0, 0, 128, 1, jb::EPI_BIAS, 0, 2},  {512, 512, 1024, 0, 0, 128, 1, jb::EPI_BIAS, 0, 4},
-        {512, 1024, 512, 0, 1, 128, 1, jb::EPI_STORE, 0, 2}, {512, 512, 1024, 0, 1, 128, 1, jb::EPI_STORE, 0, 4},
-        {300, 1000, 1000, 0, 0, 128, 1, jb::EPI_BIAS, 0, 2}, {256, 300, 160, 0, 1, 128, 1, jb::EPI_STORE, 0, 1},
         // 256-wide single-pass tiles (wgrad launch in one wave)
         {1024, 512, 512, 1, 1, 256, 0, jb::EPI_STORE, 1},    {512, 1024, 512, 1, 1, 256, 0, jb::EPI_STORE, 0},
         {300, 700, 130, 0, 0, 256, 0, jb::EPI_BIAS, 0},      {200, 300, 72, 0, 1, 256, 0, jb::EPI_STORE, 0},
@@ -185,10 +181,6 @@ int main(int argc, char** argv) {
       time_case(8, 1024, 512, 512, 1, 1, 128, 0, pdl);   // the eight big wgrads of a step, 256 CTAs
       time_case(8, 1024, 512, 512, 1, 1, 256, 0, pdl);   // ... in one wave of 128 CTAs
       // split-K
-      time_case(2, 512, 1024, 512, 0, 0, 128, 1, pdl, 2);   // wide tiles: 128 x 128, half the K per CTA
-      time_case(2, 512, 512, 1024, 0, 0, 128, 1, pdl, 4);
-      time_case(2, 512, 1024, 512, 0, 1, 128, 1, pdl, 2);
-      time_case(2, 512, 512, 1024, 0, 1, 128, 1, pdl, 4);
       time_case(2, 512, 512, 1024, 0, 0, 64, 1, pdl, 2);
       time_case(2, 512, 512, 1024, 0, 1, 64, 1, pdl, 2);
       time_case(2, 512, 64, 512, 0, 0, 64, 1, pdl, 4);
