@@ -1017,17 +1017,8 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
   pdl_prologue();
   __shared__ double red[256];
   __shared__ float s_coef;
-  float4* t4 = reinterpret_cast<float4*>(theta);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  float4* m4 = reinterpret_cast<float4*>(m);
-  float4* v4 = reinterpret_cast<float4*>(v);
-  // the first element's operands are requested before the norm is reduced: the HBM latency hides behind the reduction
-  const long long stride = static_cast<long long>(gridDim.x) * 256;
-  long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  float4 gg = make_float4(0.f, 0.f, 0.f, 0.f), mm = gg, vv = gg, tt = gg;
-  if (i < n4) { gg = __ldg(g4 + i); mm = m4[i]; vv = v4[i]; tt = t4[i]; }
   double s = 0.0;
-  for (int k = threadIdx.x; k < nparts; k += 256) s += part[k];
+  for (int i = threadIdx.x; i < nparts; i += 256) s += part[i];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -1047,10 +1038,13 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
   const float coef = s_coef;
   const float b1 = sc.beta1, b2 = sc.beta2, eps = sc.adam_eps;
   const float step = ctl->step_size, ibc2 = ctl->inv_bc2_sqrt;
-  while (i < n4) {
-    const long long nx = i + stride;
-    float4 gn = gg, mn = mm, vn = vv, tn = tt;
-    if (nx < n4) { gn = __ldg(g4 + nx); mn = m4[nx]; vn = v4[nx]; tn = t4[nx]; }   // next element in flight
+  float4* t4 = reinterpret_cast<float4*>(theta);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    const float4 gg = __ldg(g4 + i);
+    float4 mm = m4[i], vv = v4[i], tt = t4[i];
     const float gx[4] = {gg.x * coef, gg.y * coef, gg.z * coef, gg.w * coef};
     float* mp = reinterpret_cast<float*>(&mm);
     float* vp = reinterpret_cast<float*>(&vv);
@@ -1067,8 +1061,6 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
     tf32_split(tt.x, th.x, tl.x); tf32_split(tt.y, th.y, tl.y); tf32_split(tt.z, th.z, tl.z); tf32_split(tt.w, th.w, tl.w);
     reinterpret_cast<float4*>(theta_hi)[i] = th;
     reinterpret_cast<float4*>(theta_lo)[i] = tl;
-    gg = gn; mm = mn; vv = vn; tt = tn;
-    i = nx;
   }
 }
 // theta -> (theta_hi, theta_lo) over the whole flat buffer (after jb_set_params)
