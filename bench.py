@@ -253,6 +253,17 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: anything libraries print on the way (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0))
@@ -292,7 +303,7 @@ def main():
     buckets = [eng.grad_bucket_tensor(0), eng.grad_bucket_tensor(1)] if world > 1 else None
     if args.predict_only:
         p = predict_leg(eng, torch, peaks, stream)
-        print(json.dumps({k: p[k] for k in ('value', 'ms', 'e2e', 'gpu_launches')}), flush=True)
+        emit({k: p[k] for k in ('value', 'ms', 'e2e', 'gpu_launches')})
         eng.close()
         return
 
@@ -442,7 +453,7 @@ def main():
             'gemm_stages_us': [round(s[0], 2) for s in stages], 'modal_predict': pred, 'cpu_baseline': cb, 'clocks': clocks.summary(),
             'final_losses': {k: float(v) for k, v in zip(['KL', 'Rec', 'CosSim', 'F', 'total', 'grad_norm'], losses[-1])},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
