@@ -23,6 +23,7 @@
 
 #include "../../include/jamie_b200.h"
 #include "gemm_tf32.cuh"
+#include "gemm_persistent.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -163,6 +164,7 @@ struct jb_engine {
   bool eval_dirty = true;
   int eval_chunk = 8192;     // rows per pass of the folded chain (JB_EVAL_CHUNK); activations of a chunk stay in L2
   int eval_bn256_min = 256;  // layers at least this wide use 256-column tiles (JB_EVAL_BN256_MIN)
+  bool eval_persist = true;  // inference chain on the persistent GEMM (JB_EVAL_PERSIST=0: one tile per CTA)
   float *ev_a = nullptr, *ev_b = nullptr, *ev_in = nullptr, *ev_out = nullptr;
   jb::GemmProblem* d_ev_probs = nullptr;
   int ev_probs_cap = 0;
@@ -739,7 +741,8 @@ int run_chain(jb_engine* e, int from, int to, const float* in, int ld_in, int ro
   for (size_t k = 0; k < tab.size(); ++k) {
     // programmatic dependent launch inside the chain: GEMM k + 1 sets up while GEMM k drains (the kernel waits for its
     // predecessor before touching memory)
-    CU(jb::gemm_launch(d_tab + k, 1, tab[k].tiles_m * tab[k].tiles_n, s, k > 0));
+    if (e->eval_persist) CU(jb::gemm_launch_persistent(d_tab + k, tab[k], e->num_sms, s, k > 0));
+    else CU(jb::gemm_launch(d_tab + k, 1, tab[k].tiles_m * tab[k].tiles_n, s, k > 0));
     ++e->launches;
   }
   return 0;
@@ -872,6 +875,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   e->eval_chunk = 128 * e->num_sms;
   if (const char* pv = getenv("JB_EVAL_CHUNK")) { if (atoi(pv) >= 128) e->eval_chunk = atoi(pv); }
   if (const char* pv = getenv("JB_EVAL_BN256_MIN")) e->eval_bn256_min = atoi(pv);
+  if (const char* pv = getenv("JB_EVAL_PERSIST")) e->eval_persist = atoi(pv) != 0;
   // eval workspaces: two slots of chunk activations
   {
     const int Dm = e->D[0] > e->D[1] ? e->D[0] : e->D[1];
