@@ -29,7 +29,7 @@ def _trained_state(dims, L, seed):
     return params, bufs
 
 
-@pytest.mark.parametrize('dims,L,n', [([512, 512], 32, 128 * 148 + 8192 + 37), ([512, 39], 32, 300), ([40, 12], 6, 1), ([72, 40], 8, 129)])
+@pytest.mark.parametrize('dims,L,n', [([512, 512], 32, 2 * 128 * 148 + 8192 + 37), ([512, 39], 32, 300), ([40, 12], 6, 1), ([72, 40], 8, 129)])
 def test_encode_predict_vs_oracle(dims, L, n):
     from jamie_b200.engine import Engine
     import torch

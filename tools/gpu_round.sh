@@ -17,6 +17,8 @@ if [ "$2" != "quick" ]; then
   # full captures: the batched wgrad launch (12th GEMM of a step), the first two encoder GEMMs (3xTF32; the second with split-K), Adam
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 35 -c 3 -f -o $out/gemm_$tag \
     python bench.py --profile --steps 3 --warmup 3 > $out/ncu_gemm_$tag.log 2>&1; tail -2 $out/ncu_gemm_$tag.log
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:persistent -s 12 -c 2 -f -o $out/predict_$tag \
+    python bench.py --predict-only > $out/ncu_predict_$tag.log 2>&1; tail -2 $out/ncu_predict_$tag.log
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_adam -s 3 -c 1 -f -o $out/adam_$tag \
     python bench.py --profile --steps 3 --warmup 3 > $out/ncu_adam_$tag.log 2>&1; tail -2 $out/ncu_adam_$tag.log
 fi
