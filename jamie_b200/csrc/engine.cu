@@ -719,6 +719,7 @@ int run_chain(jb_engine* e, int from, int to, const float* in, int ld_in, int ro
     int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N >= e->eval_bn256_min ? 256 : 128));   // single pass: wide tiles, fewer operand bytes per output
     int rc = jb::gemm_problem_fill(&g, A, lda, 0, T + Wt.off, Wt.ld, 0, C, ldc, rows, N, K, bn, epi, T + bt.off, jb::LRELU, 0);
     if (rc) return fail("eval tensor map encode failed (%d)", rc);
+    if (e->eval_persist && (rc = jb::gemm_problem_set_store_map(&g))) return fail("eval output tensor map encode failed (%d)", rc);
     jb::gemm_table_finalize(&g, 1);
     tab.push_back(g);
     return 0;

@@ -5,9 +5,10 @@
 // One CTA per SM walks the output tiles (tile = blockIdx.x, += gridDim.x; the N tiles of one M tile are adjacent, so
 // neighbouring SMs share the A rows in L2). The operand ring, the barriers and the TMEM allocation live for the whole
 // kernel, and the accumulator is double-buffered in TMEM (2 x bn columns): while the four epilogue warps drain tile i
-// (tcgen05.ld -> bias / LeakyReLU -> padded smem transpose -> coalesced 128-bit stores) the TMA and MMA warps already run
-// the main loop of tile i + 1. Compared with the one-tile-per-CTA kernel of the training step this removes the per-tile
-// prologue (barrier init, TMEM allocation, pipeline fill) and the exposed epilogue from every tile but the last.
+// (tcgen05.ld -> bias / LeakyReLU -> swizzled 32 x 32 block in shared memory -> one TMA store, which also clips the
+// ragged edges) the TMA and MMA warps already run the main loop of tile i + 1. Compared with the one-tile-per-CTA kernel
+// of the training step this removes the per-tile prologue (barrier init, TMEM allocation, pipeline fill) and the exposed
+// epilogue from every tile but the last.
 #pragma once
 #include "gemm_tf32.cuh"
 
@@ -35,8 +36,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
   const int tiles_n = P.tiles_n;
   const int total_tiles = P.tiles_m * tiles_n;
   const int bn = P.bn;
-  const int pM = P.M, pN = P.N, ldc = P.ldc, epi = P.epi;
-  float* const pC = P.C;
+  const int pM = P.M, pN = P.N, epi = P.epi;
   const float* const pbias = P.bias;
   const float slope = P.slope;
   const int num_kb = (P.K + GEMM_BK - 1) / GEMM_BK;
@@ -122,11 +122,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
       }
     }
   } else if (warp < 6) {
-    // ------------------------------------------------ epilogue warps: TMEM -> registers -> smem transpose -> global
+    // ------------------------------------------------ epilogue warps: TMEM -> registers -> swizzled smem block -> TMA store
     const int q = warp & 3;   // TMEM lane quadrant this warp may access
-    float* st = epi_stage + q * 32 * GEMM_EPI_PITCH;
-    const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
-    const int rsub = lane >> 3, ch = lane & 7;   // read-back mapping: 4 rows x 8 float4 per pass
+    // 32 rows x 128 B per warp in the SWIZZLE_128B pattern the output tensor map expects: the 16-byte unit j of row r
+    // lives at unit j ^ (r & 7), so the row-per-lane 128-bit writes are bank-conflict free
+    uint8_t* const stw = reinterpret_cast<uint8_t*>(epi_stage) + q * 4096;
+    const CUtensorMap* const tmC = &P.tmC;
+    if (lane == 0) tma_prefetch_desc(tmC);
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int buf = j & 1;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctrl->acc_empty[buf]);
         }
-        if (nbase >= pN) continue;   // warp-uniform (the accumulator columns beyond N are never stored)
+        if (nbase >= pN || m0 + q * 32 >= pM) continue;   // warp-uniform: nothing of this block lies inside C
         if (epi != EPI_STORE) {
           const float bl = (nbase + lane < pN) ? __ldg(pbias + nbase + lane) : 0.f;
 #pragma unroll
@@ -154,39 +156,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
             v[i] = x;
           }
         }
+        if (lane == 0) tma_store_wait_read();   // the previous store of this warp has read the staging block
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          *reinterpret_cast<float4*>(stw + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rsub;
-          const int grow = m0 + q * 32 + r;
-          const int n = nbase + ch * 4;
-          const float4 x = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
-          if (grow < pM && n < pN) {
-            float* dst = pC + static_cast<size_t>(grow) * ldc + n;
-            if (vec_ok && n + 4 <= pN) *reinterpret_cast<float4*>(dst) = x;
-            else {
-              const float xs[4] = {x.x, x.y, x.z, x.w};
-              for (int i = 0; i < 4; ++i)
-                if (n + i < pN) dst[i] = xs[i];
-            }
-          }
+        if (lane == 0) {
+          tma_store_2d(tmC, stw, nbase, m0 + q * 32);   // rows / columns beyond C are clipped by the tensor map
+          tma_store_commit();
         }
-        __syncwarp();
       }
     }
+    if (lane == 0) tma_store_wait_all();   // global writes complete before the kernel ends
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
 }
 
-// One problem (filled by gemm_problem_fill with K-major operands, no split), one CTA per SM at most.
+// Output tensor map of a filled problem (C [M, N] fp32, pitch ldc): 32 x 32 boxes in the 128-byte swizzle.
+inline int gemm_problem_set_store_map(GemmProblem* g) {
+  PFN_tmapEncodeTiled fn = tmap_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->N), static_cast<cuuint64_t>(g->M)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(g->ldc) * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&g->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g->C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+// One problem (filled by gemm_problem_fill with K-major operands, no split, + gemm_problem_set_store_map), one CTA per
+// SM at most.
 inline cudaError_t gemm_launch_persistent(const GemmProblem* dev_prob, const GemmProblem& host_prob, int sms, cudaStream_t st,
                                           bool use_pdl) {
   if (host_prob.a_mn || host_prob.b_mn || host_prob.split || host_prob.accumulate || host_prob.bn > 256) return cudaErrorInvalidValue;
+  if ((host_prob.ldc & 3) != 0 || (reinterpret_cast<uintptr_t>(host_prob.C) & 15) != 0) return cudaErrorInvalidValue;   // TMA store
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);

@@ -73,6 +73,7 @@ struct alignas(128) GemmProblem {
   CUtensorMap tmB;
   CUtensorMap tmA_lo;  // split only
   CUtensorMap tmB_lo;
+  CUtensorMap tmC;     // persistent inference GEMM only: 32 x 32 output boxes, SWIZZLE_128B (TMA store epilogue)
   float* C;
   const float* bias;
   int M, N, K, ldc;
