@@ -153,6 +153,7 @@ struct jb_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
   int wgrad_bn = 256;        // widest N tile of the batched wgrad launch
+  int adam_blocks = 888;     // grid of k_adam: 6 blocks of 256 threads per SM (JB_ADAM_BLOCKS; 592: +2.7 us/step)
   int slab_cw = 16;          // columns per block of the BatchNorm / reconstruction slab kernels: 16 (1024 threads) or 8 (512)
   int accumulate = 0;
   int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
@@ -636,7 +637,7 @@ void record_update(jb_engine* e, Rec& r, int B) {
   const jb::StepConsts sc = make_consts(e, B);
   const long long n4 = e->n_flat / 4;
   launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, n4, e->norm_part);
-  launchk(r, jb::k_adam, jb::NORM_BLOCKS * 2, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
+  launchk(r, jb::k_adam, e->adam_blocks, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
 }
 
 int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd, 5 / 6 bwd halves*/, cudaGraphExec_t* out,
@@ -869,6 +870,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
+  if (const char* pv = getenv("JB_ADAM_BLOCKS")) { if (atoi(pv) > 0) e->adam_blocks = atoi(pv); }
   if (const char* pv = getenv("JB_SLAB_CW")) e->slab_cw = atoi(pv) == 8 ? 8 : 16;
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;

@@ -12,7 +12,7 @@ namespace jb {
 constexpr float BN_EPS = 1e-5f;
 constexpr float BN_MOM = 0.1f;
 constexpr float LRELU = 0.01f;
-constexpr int NORM_BLOCKS = 296;  // 2 x 148 SMs
+constexpr int NORM_BLOCKS = 592;  // 4 x 148 SMs: blocks (and partials) of k_gradnorm
 
 // ------------------------------------------------------------------------------------------------ step control
 // Device-resident per-step scalars so that one captured CUDA graph serves every step.
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(256) k_gradnorm(const float* __restrict__ g, l
 }
 // Phase 2: every block re-reduces the partials in the same order (identical clip coefficient everywhere), then
 // g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
-__global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* __restrict__ theta_hi,
+__global__ void __launch_bounds__(256, 6) k_adam(float* __restrict__ theta, float* __restrict__ theta_hi,
                                               float* __restrict__ theta_lo, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n4, const double* __restrict__ part,
                                               int nparts, Ctl* ctl, StepConsts sc,
