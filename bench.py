@@ -33,10 +33,10 @@ sys.path.insert(0, ROOT)
 DIMS, LATENT, BATCH, DROPOUT = [512, 512], 32, 512, 0.6
 # launch order of one training step (engine.cu: record_backward / record_update)
 STEP_KERNELS = {
-    30: ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
+    31: ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
          'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D', 'k_bn_fwd', 'gemm F3 heads', 'k_reparam',
          'k_combine(+latent loss)', 'gemm F4 dec L->D', 'k_bn_fwd', 'gemm F5 dec D->2D', 'k_bn_fwd',
-         'gemm F6 dec 2D->D (+rec loss)', 'gemm B6 dgrad', 'k_bn_bwd', 'gemm B5 dgrad', 'k_bn_bwd', 'gemm B4 dgrad',
+         'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 dgrad', 'k_bn_bwd', 'gemm B5 dgrad', 'k_bn_bwd', 'gemm B4 dgrad',
          'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final', 'gemm B3 dgrad', 'k_bn_bwd', 'gemm B2 dgrad',
          'k_bn_bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam'],
 }

@@ -287,7 +287,7 @@ void carve(jb_engine* e, Carver& c) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>(((B + 127) / 128) * ((D + 31) / 32) * 4);   // one partial per 32-row slab of every tile of the last decoder GEMM
+    a.rec_part = c.take<float>((D + 7) / 8);
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
@@ -350,13 +350,7 @@ int build_train_tables(jb_engine* e, int B, int accum) {
   if (fwd(e->st_f[4], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
         return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D); })) return 1;
   if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        if (lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D)) return 1;
-        GemmProblem& g = e->h_probs.back();   // reconstruction loss and d loss / d xhat in this GEMM's epilogue
-        g.epi = jb::EPI_REC;
-        g.rec.x = a.x; g.rec.ldx = a.ldD; g.rec.out_hi = a.dxhat.hi; g.rec.out_lo = a.dxhat.lo; g.rec.ld_out = a.ldD;
-        g.rec.part = a.rec_part;
-        g.rec.scale_k = e->cfg.loss_w[1] * 2.f / (static_cast<float>(B) * static_cast<float>(D));
-        return 0; })) return 1;
+        return lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D); })) return 1;
   // ---- backward: dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out): one stage
   //                per layer on the critical path;
   //                wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass): nothing
@@ -574,7 +568,19 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true, int part =
   r.gemm(e->st_f[3]); bnf(2, 2);
   r.gemm(e->st_f[4]); bnf(3, 3);
   r.gemm(e->st_f[5]);
-  // ---- losses + backward (the reconstruction loss and its gradient come out of the last decoder GEMM's epilogue)
+  // ---- losses + backward
+  jb::RecPair rp{};
+  for (int i = 0; i < 2; ++i) {
+    ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
+    jb::RecArgs& q = rp.m[i];
+    q.xhat = a.xhat; q.ldxh = a.ldD; q.x = a.x; q.ldx = a.ldD; q.dxh = a.dxhat.hi; q.dxl = a.dxhat.lo; q.lddx = a.ldD;
+    const bool slab = B <= 512;
+    const int cw = slab ? e->slab_cw : 32;
+    q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + cw - 1) / cw;
+  }
+  if (B <= 512 && e->slab_cw == 8) launchk(r, jb::k_rec_slab<8, 512>, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(512), rp, B, sc.w[1], accum);
+  else if (B <= 512) launchk(r, jb::k_rec_slab<16, 1024>, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(1024), rp, B, sc.w[1], accum);
+  else launchk(r, jb::k_rec, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(256), rp, B, sc.w[1], accum);
   auto bnb = [&](int which) {
     jb::BnBwdPair pr{};
     for (int i = 0; i < 2; ++i) {
@@ -612,17 +618,12 @@ void record_backward(jb_engine* e, Rec& r, int B, bool gather = true, int part =
   jb::FinalArgs fa{};
   fa.rowpart = e->rowpart;
   for (int i = 0; i < 2; ++i) {
-    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part;
-    { const GemmProblem& gp = e->h_probs[e->st_f[5].first + i]; fa.rec_blocks[i] = gp.tiles_m * gp.tiles_n * 4; }
-    fa.dxh[i] = e->act[i].dxhat.hi; fa.dxl[i] = e->act[i].dxhat.lo; fa.lddx[i] = e->act[i].ldD;
-    fa.dbias_out[i] = G + e->ms[i].b5.off;
+    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = rp.m[i].blocks;
     fa.dmulv[i] = e->act[i].dmulv; fa.dbias_heads[i] = G + e->ms[i].bmv.off; fa.D[i] = e->D[i];
   }
   fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
   fa.grad_tail = G + e->n_flat;
-  fa.head_blocks = (4 * L + jb::SLAB_CW - 1) / jb::SLAB_CW;
-  launchk(r, jb::k_latent_final, dim3(1 + fa.head_blocks + (e->D[0] + jb::SLAB_CW - 1) / jb::SLAB_CW + (e->D[1] + jb::SLAB_CW - 1) / jb::SLAB_CW),
-          dim3(jb::SLAB_THREADS), fa, e->ctl, B, L, sc, accum);
+  launchk(r, jb::k_latent_final, dim3(1 + (4 * L + jb::SLAB_CW - 1) / jb::SLAB_CW), dim3(jb::SLAB_THREADS), fa, e->ctl, B, L, sc, accum);
   const bool split_w = e->st_b[6].count > 0;
   if (split_w) r.gemm(e->st_b[5]);   // heads + decoder wgrads: that gradient bucket is now complete
   r.mute = part == 0;

@@ -46,7 +46,6 @@
 #include <cstdint>
 #include <cstdio>
 #include "ptx.cuh"
-#include "kernels.cuh"
 
 namespace jb {
 
@@ -67,16 +66,6 @@ enum GemmEpilogue : int {
   EPI_STORE = 0,       // C = acc
   EPI_BIAS = 1,        // C = acc + bias[n]
   EPI_BIAS_LRELU = 2,  // C = leaky_relu(acc + bias[n], slope)      (inference, BatchNorm folded)
-  // last decoder layer of the training step: C = xhat = acc + bias, and in the same pass the reconstruction loss
-  // (jamie/jamie.py:637-643): d = xhat - x, per-warp partials of sum d^2, d loss / d xhat = k d as TF32 hi / lo planes
-  EPI_REC = 3,
-};
-
-struct GemmRec {   // EPI_REC arguments
-  const float* x; int ldx;              // the step's input rows [M, N]
-  float* out_hi; float* out_lo; int ld_out;
-  float* part;                          // [tiles_m * tiles_n * 4] partial sums of d^2, one per 32-row slab of a tile
-  float scale_k;                        // w_rec * 2 / (B D)
 };
 
 struct alignas(128) GemmProblem {
@@ -95,7 +84,6 @@ struct alignas(128) GemmProblem {
   int accumulate;  // C += result (one CTA owns the tile: no atomics)
   float slope;
   int split;       // 1: error-compensated 3xTF32 on pre-split hi/lo planes, see the header comment
-  GemmRec rec;
 };
 
 // First CTA of every problem of a launch, passed BY VALUE (constant bank): the CTA -> problem lookup costs no dependent
@@ -384,39 +372,8 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
     }
     if (ck > 1) cluster_sync_all();   // barrier B: the deposits are visible to their owners
     if (ck == 1 || owner == crank) {
+      const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
       const int rsub = lane >> 3, ch = lane & 7;  // read-back mapping: 4 rows x 8 float4 per pass
-      // this warp's 32 x 32 block (row = thread) -> base[grow, nbase ..] through the padded transpose, coalesced
-      auto store_block = [&](const float (&x)[32], float* base, int ld, int nbase, int acc) {
-        const bool vec_ok = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * j) =
-              make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rsub;
-          const int grow = m0 + q * 32 + r;
-          const int n = nbase + ch * 4;
-          float4 y = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
-          if (grow < pM && n < pN) {
-            float* dst = base + static_cast<size_t>(grow) * ld + n;
-            if (vec_ok && n + 4 <= pN) {
-              if (acc) {
-                const float4 o = *reinterpret_cast<const float4*>(dst);
-                y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w;
-              }
-              *reinterpret_cast<float4*>(dst) = y;
-            } else {
-              const float ys[4] = {y.x, y.y, y.z, y.w};
-              for (int j = 0; j < 4; ++j)
-                if (n + j < pN) dst[j] = acc ? dst[j] + ys[j] : ys[j];
-            }
-          }
-        }
-        __syncwarp();
-      };
-      float sq = 0.f;   // EPI_REC: this thread's share of sum (xhat - x)^2
       for (int c0 = 0; c0 < bn; c0 += 32) {
         const int nbase = n0 + c0;
         if (nbase >= pN) break;  // warp-uniform
@@ -439,39 +396,33 @@ gemm_tf32_grouped_kernel(const GemmProblem* __restrict__ probs, int nprobs, int 
             v[j] = x;
           }
         }
-        store_block(v, pC, ldc, nbase, accumulate);
-        if (epi == EPI_REC) {
-          // reconstruction loss in the same pass: this thread's row of x, d = xhat - x, k d as operand planes
-          const GemmRec R = P.rec;
-          const int grow = m0 + q * 32 + lane;
-          const bool rok = grow < pM;
-          const float* xr = R.x + static_cast<size_t>(rok ? grow : 0) * R.ldx + nbase;
-          float xv[32];
-          if (rok && (R.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(R.x) & 15) == 0 && nbase + 32 <= pN) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr) + j);
-              xv[4 * j] = t4.x; xv[4 * j + 1] = t4.y; xv[4 * j + 2] = t4.z; xv[4 * j + 3] = t4.w;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * GEMM_EPI_PITCH + 4 * j) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;
+          const int grow = m0 + q * 32 + r;
+          const int n = nbase + ch * 4;
+          float4 x = *reinterpret_cast<const float4*>(st + r * GEMM_EPI_PITCH + ch * 4);
+          if (grow < pM && n < pN) {
+            float* dst = pC + static_cast<size_t>(grow) * ldc + n;
+            if (vec_ok && n + 4 <= pN) {
+              if (accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+              }
+              *reinterpret_cast<float4*>(dst) = x;
+            } else {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+              for (int j = 0; j < 4; ++j)
+                if (n + j < pN) dst[j] = accumulate ? dst[j] + xs[j] : xs[j];
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) xv[j] = (rok && nbase + j < pN) ? __ldg(xr + j) : 0.f;
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = (rok && nbase + j < pN) ? v[j] - xv[j] : 0.f;
-            sq += d * d;
-            const float gx = R.scale_k * d;
-            v[j] = tf32_rna(gx);
-            xv[j] = tf32_rna(gx - v[j]);
-          }
-          store_block(v, R.out_hi, R.ld_out, nbase, 0);
-          store_block(xv, R.out_lo, R.ld_out, nbase, 0);
         }
-      }
-      if (epi == EPI_REC) {
-        sq = warp_sum(sq);
-        if (lane == 0) P.rec.part[(tm * tiles_n + tn) * 4 + q] = sq;
+        __syncwarp();
       }
     }
   } else if (ck > 1) {

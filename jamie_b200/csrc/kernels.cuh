@@ -585,6 +585,92 @@ __global__ void __launch_bounds__(THREADS) k_bn_bwd_slab(BnBwdPair pr, const Ctl
     }
 }
 
+// ------------------------------------------------------------------------------------------------ reconstruction loss
+// dxhat = w_rec * 2 (xhat - x) / (B D);  per-block partial of sum (xhat - x)^2;  bias gradient of the last decoder
+// Linear = column sums of dxhat   (jamie/jamie.py:637-643).
+struct RecArgs {
+  const float* xhat; int ldxh;
+  const float* x; int ldx;
+  float* dxh; float* dxl; int lddx;   // d loss / d xhat as TF32 hi / lo planes
+  float* dbias;
+  float* part;   // [blocks] partial sums of squares
+  int D;
+  int blocks;
+};
+struct RecPair { RecArgs m[2]; };
+__global__ void __launch_bounds__(256) k_rec(RecPair pr, int B, float w_rec, int accum) {
+  pdl_prologue();
+  __shared__ float sh[8][2][32];
+  const int which = blockIdx.x >= pr.m[0].blocks ? 1 : 0;
+  const RecArgs& A = pr.m[which];
+  const int cb = blockIdx.x - (which ? pr.m[0].blocks : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = cb * 32 + lane;
+  const bool cok = c < A.D;
+  const float k = w_rec * 2.f / (static_cast<float>(B) * static_cast<float>(A.D));
+  float sq = 0.f, cs = 0.f;
+#pragma unroll 8
+  for (int r = warp; r < B; r += 8) {
+    if (cok) {
+      const float d = __ldg(A.xhat + static_cast<long long>(r) * A.ldxh + c) - __ldg(A.x + static_cast<long long>(r) * A.ldx + c);
+      sq += d * d;
+      const float gx = k * d;
+      cs += gx;
+      tf32_split(gx, A.dxh[static_cast<long long>(r) * A.lddx + c], A.dxl[static_cast<long long>(r) * A.lddx + c]);
+    }
+  }
+  block_colsum2(sq, cs, sh, warp, lane);
+  if (warp == 0) {
+    if (cok) A.dbias[c] = accum ? A.dbias[c] + cs : cs;
+    const float tot = warp_sum(cok ? sq : 0.f);
+    if (lane == 0) A.part[cb] = tot;
+  }
+}
+
+template <int CW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_rec_slab(RecPair pr, int B, float w_rec, int accum) {
+  pdl_prologue();
+  __shared__ float sh[THREADS / 32][2][CW];
+  const int nb0 = (pr.m[0].D + CW - 1) / CW;
+  const int which = blockIdx.x >= nb0 ? 1 : 0;
+  const RecArgs& A = pr.m[which];
+  const int cb = blockIdx.x - (which ? nb0 : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = cb * CW + (threadIdx.x & (CW - 1));
+  const int slot = threadIdx.x / CW;
+  const bool cok = c < A.D;
+  const float kk = w_rec * 2.f / (static_cast<float>(B) * static_cast<float>(A.D));
+  float xh[4 * SLAB_G], xx[4 * SLAB_G];
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
+      const bool ok = cok && r < B;
+      xh[4 * t + k] = ok ? __ldg(A.xhat + static_cast<long long>(r) * A.ldxh + c) : 0.f;
+      xx[4 * t + k] = ok ? __ldg(A.x + static_cast<long long>(r) * A.ldx + c) : 0.f;
+    }
+  float sq = 0.f, cs = 0.f;
+#pragma unroll
+  for (int t = 0; t < SLAB_G; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (slot + (THREADS / CW) * t) + k;
+      const float d = xh[4 * t + k] - xx[4 * t + k];
+      sq += d * d;
+      const float gx = kk * d;
+      cs += gx;
+      if (r < B && cok) tf32_split(gx, A.dxh[static_cast<long long>(r) * A.lddx + c], A.dxl[static_cast<long long>(r) * A.lddx + c]);
+    }
+  slab_colsum2<CW, THREADS>(sq, cs, sh, warp, lane);
+  if (warp == 0) {
+    if (lane < CW && cok) A.dbias[c] = accum ? A.dbias[c] + cs : cs;
+    float t = (lane < CW && cok) ? sq : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) A.part[cb] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ latent stage
 struct Latent {
   // per modality
@@ -825,15 +911,9 @@ struct FinalArgs {
   float* out_loss;               // [nsteps][8]
   float* grad_tail;              // 8 floats after the flat gradients (all-reduce piggy-back)
   int D[2];
-  // bias gradient of the last decoder Linear = column sums of d loss / d xhat (written as hi / lo planes by the epilogue of
-  // that layer's GEMM, gemm_tf32.cuh: EPI_REC)
-  const float* dxh[2]; const float* dxl[2]; int lddx[2];
-  float* dbias_out[2];
-  int head_blocks;               // blocks 1 .. head_blocks own the head-bias columns, the following ones dbias_out
 };
-// grid 1 + ceil(4L / 16) + ceil(D0 / 16) + ceil(D1 / 16) blocks of 1024 threads: block 0 reduces the loss scalars and
-// d sigma; the next ceil(4L / 16) blocks own 16 of the 4L head-bias columns each (both modalities: mu bias | var bias)
-// with 64 row slots per column; the rest own 16 columns of the last decoder layer's bias gradient.
+// grid 1 + ceil(4L / 16) blocks of 1024 threads: block 0 reduces the loss scalars and d sigma; block 1 + k owns 16 of
+// the 4L head-bias columns (both modalities: mu bias | var bias) with 64 row slots per column.
 __global__ void __launch_bounds__(SLAB_THREADS) k_latent_final(FinalArgs a, const Ctl* __restrict__ ctl, int B, int L,
                                                                StepConsts sc, int accum) {
   pdl_prologue();
@@ -841,26 +921,6 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_latent_final(FinalArgs a, cons
   __shared__ float aux[4];    // [0,1]: sum_l (1 + lv - exp lv) of logvar rows 0/1 (modality 1); [2,3]: sum (xhat - x)^2
   __shared__ float sh[SLAB_THREADS / 32][2][SLAB_CW];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (static_cast<int>(blockIdx.x) > a.head_blocks) {
-    // bias gradient of the last decoder layer: column sums of dxhat = hi + lo over the batch (fixed order)
-    int cb = static_cast<int>(blockIdx.x) - 1 - a.head_blocks;
-    const int nb0 = (a.D[0] + SLAB_CW - 1) / SLAB_CW;
-    const int i = cb >= nb0 ? 1 : 0;
-    cb -= i ? nb0 : 0;
-    const int col = cb * SLAB_CW + (tid & (SLAB_CW - 1));
-    const int slot = tid / SLAB_CW;
-    const bool cok = col < a.D[i];
-    float s = 0.f, dummy = 0.f;
-    if (cok)
-#pragma unroll 4
-      for (int r = slot; r < B; r += SLAB_SLOTS) {
-        const long long o = static_cast<long long>(r) * a.lddx[i] + col;
-        s += __ldg(a.dxh[i] + o) + __ldg(a.dxl[i] + o);
-      }
-    slab_colsum2<SLAB_CW, SLAB_THREADS>(s, dummy, sh, warp, lane);
-    if (slot == 0 && cok) a.dbias_out[i][col] = accum ? a.dbias_out[i][col] + s : s;
-    return;
-  }
   if (blockIdx.x > 0) {
     // head bias gradients: column sums of dmulv over the batch (fixed order)
     const int col = (blockIdx.x - 1) * SLAB_CW + (tid & (SLAB_CW - 1));
