@@ -153,6 +153,7 @@ struct jb_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
   int wgrad_bn = 256;        // widest N tile of the batched wgrad launch
+  int dgrad_split = 1;       // dgrads in 3xTF32 (1) or one TF32 pass on the hi planes (JB_DGRAD_SPLIT=0: exploration)
   int adam_blocks = 888;     // grid of k_adam: 6 blocks of 256 threads per SM (JB_ADAM_BLOCKS; 592: +2.7 us/step)
   int slab_cw = 16;          // columns per block of the BatchNorm / reconstruction slab kernels: 16 (1024 threads) or 8 (512)
   int accumulate = 0;
@@ -363,7 +364,7 @@ int build_train_tables(jb_engine* e, int B, int accum) {
     return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, bn, jb::EPI_STORE, nullptr, accum, 0);
   };
   auto dgrad = [&](Planes dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in), jb::EPI_STORE, nullptr, 0, 1);
+    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in), jb::EPI_STORE, nullptr, 0, e->dgrad_split);
   };
   int first = static_cast<int>(e->h_probs.size());   // B6: last decoder Linear(2D -> D)
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -870,6 +871,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
+  if (const char* pv = getenv("JB_DGRAD_SPLIT")) e->dgrad_split = atoi(pv) != 0;
   if (const char* pv = getenv("JB_ADAM_BLOCKS")) { if (atoi(pv) > 0) e->adam_blocks = atoi(pv); }
   if (const char* pv = getenv("JB_SLAB_CW")) e->slab_cw = atoi(pv) == 8 ? 8 : 16;
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
