@@ -190,7 +190,7 @@ def ncu_traffic(kernel_key):
         return None
 
 
-def predict_leg(eng, torch, peaks, stream, rows_dev=1 << 20, rows_host=1 << 19):
+def predict_leg(eng, torch, peaks, stream, rows_dev=1 << 20, rows_host=1 << 18):
     """modal_predict (BASELINE metric 2): modality 0 -> 1 on pre-transformed [N, 512] fp32 rows.
     value: rows resident in HBM, CUDA events; e2e: pinned host buffers in and out through jb_predict."""
     g = torch.Generator(device='cuda').manual_seed(2)
