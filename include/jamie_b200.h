@@ -115,7 +115,8 @@ int jb_train_step_hostbatch(jb_engine* e, const float* x0, const float* x1, cons
                             int batch, double kl_anneal, float out_losses[8], void* stream);
 
 /* Data-parallel form of the host-batch step: copy the batch in and run forward + backward only; the caller then
- * all-reduces jb_grad_buffer and calls jb_step_update, and reads the losses with jb_read_losses(e, out, 1, stream). */
+ * all-reduces jb_grad_buffer and calls jb_step_update. Host-batch steps alternate between two plan rows (slots): the
+ * k-th host-batch step (k = 0, 1, ...) leaves its losses in row k & 1 of jb_read_losses(e, out, 2, stream). */
 int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, const long long* idx0,
                                const long long* idx1, int batch, double kl_anneal, void* stream);
 
