@@ -139,3 +139,38 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e'] == {'value': d['value'], 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'].startswith('BASELINE configs[1]')
+
+
+def test_fast_sampler_distribution_and_reference_default():
+    """sampler='fast' / 'auto' above 16k cells: an O(batch) draw with the reference's distribution (distinct indices in
+    range, hybrid head from the matched pairs); the default path below that size stays the reference's numpy stream."""
+    from jamie_b200.jamie import sample_batch
+    rows, cols, B = [100_000, 90_000], [512, 512], 512
+    rng = np.random.default_rng(7)
+    cs = [np.array([11, 22]), np.array([33, 44])]
+    np.random.seed(3)
+    for method in ('diag', 'zeros', 'hybrid'):
+        rb = sample_batch(method, rows, cols, B, cs, fast_rng=rng)
+        assert len(rb) == 2 and all(len(r) == B for r in rb)
+        for i in range(2):
+            tail = rb[i] if method != 'hybrid' else rb[i][np.isin(rb[i], cs[i], invert=True)]
+            assert tail.min() >= 0 and tail.max() < rows[0 if method == 'diag' else i]
+            assert len(np.unique(tail)) == len(tail)
+        if method == 'diag':
+            assert rb[0] is rb[1]
+        if method == 'hybrid':
+            k = B - len(rb[0][np.isin(rb[0], cs[0], invert=True)])
+            assert k <= 2 and set(rb[0][:k]) <= set(cs[0]) and set(rb[1][:k]) <= set(cs[1])
+    # uniformity: mean of many draws is close to (n - 1) / 2
+    draws = np.concatenate([sample_batch('zeros', rows, cols, B, fast_rng=rng)[0] for _ in range(200)])
+    assert abs(draws.mean() / (rows[0] - 1) - 0.5) < 0.01
+    # replacement sampling (narrow modality) and the default path keep the legacy global generator
+    np.random.seed(5)
+    a = sample_batch('diag', [300, 300], [39, 512], B, fast_rng=rng)[0]
+    np.random.seed(5)
+    b = np.random.choice(300, B, replace=True)
+    np.testing.assert_array_equal(a, b)
+    np.random.seed(6)
+    c = sample_batch('zeros', [400, 300], cols, 128)
+    np.random.seed(6)
+    np.testing.assert_array_equal(c[0], np.random.choice(range(400), 128, replace=False))
