@@ -365,26 +365,34 @@ class JAMIE(UnionCom):
         epoch = 0
         stop = False
         t_sample = t_step = 0.0
-        while epoch < self.epoch_DNN and not stop:
-            # Epochs that can be issued without a host decision in between: early stopping cannot trigger before
-            # the streak reaches max_steps_without_increment, and the streak grows by at most one per epoch and only
-            # once epoch > min_epochs (jamie/jamie.py:782-792).
-            safe = max(1, (self.min_epochs + 1 - epoch) if epoch <= self.min_epochs else 0) \
-                + max(0, self.max_steps_without_increment - streak - 1) if self.use_early_stop else self.epoch_DNN
-            n_ep = int(min(self.epoch_DNN - epoch, max(1, safe), max(1, 4096 // len_dataloader)))
+
+        def build_chunk(first_epoch, streak_bound):
+            """Sampling plan of the next chunk of epochs, starting at `first_epoch`, given an upper bound of the
+            early-stopping streak at that point. Epochs that can be issued without a host decision in between: early
+            stopping cannot trigger before the streak reaches max_steps_without_increment, and the streak grows by at
+            most one per epoch and only once epoch > min_epochs (jamie/jamie.py:782-792)."""
+            nonlocal t_sample
+            safe = max(1, (self.min_epochs + 1 - first_epoch) if first_epoch <= self.min_epochs else 0) \
+                + max(0, self.max_steps_without_increment - streak_bound - 1) if self.use_early_stop else self.epoch_DNN
+            n = int(min(self.epoch_DNN - first_epoch, max(1, safe), max(1, 4096 // len_dataloader)))
             t0 = _time.perf_counter()
-            idx0 = np.empty((n_ep * len_dataloader, self.batch_size), np.int64)
-            idx1 = np.empty_like(idx0)
-            anneal = np.empty(n_ep * len_dataloader, np.float64)
-            for e_ in range(n_ep):
-                kl_anneal = 1 / (1 + np.exp(-5 * ((epoch + e_) - c) / c))
+            i0 = np.empty((n * len_dataloader, self.batch_size), np.int64)
+            i1 = np.empty_like(i0)
+            ann = np.empty(n * len_dataloader, np.float64)
+            for e_ in range(n):
+                kl_anneal = 1 / (1 + np.exp(-5 * ((first_epoch + e_) - c) / c))
                 for b_ in range(len_dataloader):
                     rb = sample_batch(prior.sampling_method, local_rows, self.col, self.batch_size, prior.corr_samples, fast_rng)
-                    idx0[e_ * len_dataloader + b_] = rb[0]
-                    idx1[e_ * len_dataloader + b_] = rb[1]
-                    anneal[e_ * len_dataloader + b_] = kl_anneal
+                    i0[e_ * len_dataloader + b_] = rb[0]
+                    i1[e_ * len_dataloader + b_] = rb[1]
+                    ann[e_ * len_dataloader + b_] = kl_anneal
+            t_sample += _time.perf_counter() - t0
+            return n, i0, i1, ann
+
+        chunk = build_chunk(0, 0) if self.epoch_DNN > 0 else None
+        while chunk is not None and not stop:
+            n_ep, idx0, idx1, anneal = chunk
             t1 = _time.perf_counter()
-            t_sample += t1 - t0
             eng.upload_plan(idx0, idx1, anneal, stream)
             nsteps = n_ep * len_dataloader
             if world == 1 and self.batch_step:
@@ -402,6 +410,11 @@ class JAMIE(UnionCom):
                         if world > 1:
                             dist.all_reduce(gt)
                         eng.step_update(stream)
+            # The steps above are only enqueued: the next chunk's plan is sampled on the host while the GPU runs them.
+            # Its size uses the largest streak this chunk can end with, so it never crosses an early-stop decision.
+            t_enq = _time.perf_counter()
+            chunk = build_chunk(epoch + n_ep, streak + n_ep) if epoch + n_ep < self.epoch_DNN else None
+            t1 += _time.perf_counter() - t_enq                # sampling time is booked under 'Get subset samples'
             losses = eng.read_losses(nsteps, stream)          # one device->host read per chunk of epochs
             if world > 1:
                 lt = torch.from_numpy(losses).cuda()
