@@ -139,6 +139,17 @@ def sample_batch(method, rows, cols, batch_size, corr_samples=None, fast_rng=Non
     raise Exception(f'Sampling method {method} does not exist')
 
 
+def chunk_epochs(first_epoch, streak_bound, min_epochs, max_steps_without_increment, use_early_stop, epoch_DNN,
+                 len_dataloader, max_steps=4096):
+    """How many epochs can be enqueued from `first_epoch` on without a host decision in between, given an upper bound of
+    the early-stopping streak at that point: early stopping (jamie/jamie.py:777-792) is only evaluated once
+    epoch > min_epochs, the streak then grows by at most one per epoch, and training stops when it reaches
+    max_steps_without_increment -- so the earliest possible stop is always the LAST epoch of the chunk."""
+    safe = max(1, (min_epochs + 1 - first_epoch) if first_epoch <= min_epochs else 0) \
+        + max(0, max_steps_without_increment - streak_bound - 1) if use_early_stop else epoch_DNN
+    return int(min(epoch_DNN - first_epoch, max(1, safe), max(1, max_steps // len_dataloader)))
+
+
 class JAMIE(UnionCom):
     """
     Adaptation of https://github.com/caokai1073/UnionCom by caokai1073
@@ -368,13 +379,10 @@ class JAMIE(UnionCom):
 
         def build_chunk(first_epoch, streak_bound):
             """Sampling plan of the next chunk of epochs, starting at `first_epoch`, given an upper bound of the
-            early-stopping streak at that point. Epochs that can be issued without a host decision in between: early
-            stopping cannot trigger before the streak reaches max_steps_without_increment, and the streak grows by at
-            most one per epoch and only once epoch > min_epochs (jamie/jamie.py:782-792)."""
+            early-stopping streak at that point (chunk_epochs)."""
             nonlocal t_sample
-            safe = max(1, (self.min_epochs + 1 - first_epoch) if first_epoch <= self.min_epochs else 0) \
-                + max(0, self.max_steps_without_increment - streak_bound - 1) if self.use_early_stop else self.epoch_DNN
-            n = int(min(self.epoch_DNN - first_epoch, max(1, safe), max(1, 4096 // len_dataloader)))
+            n = chunk_epochs(first_epoch, streak_bound, self.min_epochs, self.max_steps_without_increment,
+                             self.use_early_stop, self.epoch_DNN, len_dataloader)
             t0 = _time.perf_counter()
             i0 = np.empty((n * len_dataloader, self.batch_size), np.int64)
             i1 = np.empty_like(i0)

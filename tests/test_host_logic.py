@@ -174,3 +174,50 @@ def test_fast_sampler_distribution_and_reference_default():
     c = sample_batch('zeros', [400, 300], cols, 128)
     np.random.seed(6)
     np.testing.assert_array_equal(c[0], np.random.choice(range(400), 128, replace=False))
+
+
+def test_chunked_early_stopping_matches_the_epoch_by_epoch_rule():
+    """The fit loop enqueues chunks of epochs and samples the next chunk while the GPU runs (its size bounded by the
+    largest streak the running chunk can end with): whatever the loss sequence, early stopping fires at the same epoch as
+    the reference's epoch-by-epoch rule (jamie/jamie.py:777-792) and always on the last epoch of a chunk."""
+    from jamie_b200.jamie import chunk_epochs
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        epoch_DNN = int(rng.integers(1, 400))
+        min_epochs = int(rng.integers(0, 200))
+        msi = int(rng.integers(1, 40))
+        ldl = int(rng.integers(1, 300))
+        use_es = bool(rng.integers(0, 4))
+        losses = np.minimum.accumulate(rng.random(epoch_DNN) + 1.0) if trial % 3 else rng.random(epoch_DNN)
+        losses = losses + (rng.random(epoch_DNN) < 0.5) * 0.05        # plateaus and regressions
+
+        def rule(epoch, best, streak):          # one epoch of the reference's early-stop bookkeeping
+            stop = False
+            if epoch > min_epochs:
+                if best - losses[epoch] > 1e-8:
+                    best, streak = losses[epoch], 0
+                else:
+                    streak += 1
+                stop = streak >= msi and use_es
+            return best, streak, stop
+        # reference: epoch by epoch
+        best, streak, want = np.inf, 0, epoch_DNN
+        for ep in range(epoch_DNN):
+            best, streak, stop = rule(ep, best, streak)
+            if stop:
+                want = ep + 1
+                break
+        # chunked + pipelined, as in JAMIE.project_jamie
+        best, streak, epoch, stop = np.inf, 0, 0, False
+        n = chunk_epochs(0, 0, min_epochs, msi, use_es, epoch_DNN, ldl)
+        while n is not None and not stop:
+            assert 1 <= n <= epoch_DNN - epoch and n * ldl <= max(4096, ldl)
+            nxt = chunk_epochs(epoch + n, streak + n, min_epochs, msi, use_es, epoch_DNN, ldl) if epoch + n < epoch_DNN else None
+            for e_ in range(n):
+                best, streak, stop = rule(epoch, best, streak)
+                epoch += 1
+                if stop:
+                    assert e_ == n - 1, 'early stop inside a chunk'
+                    break
+            n = nxt
+        assert epoch == want, (trial, epoch, want)
