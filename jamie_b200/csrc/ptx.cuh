@@ -121,6 +121,50 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// generic-proxy writes (st.global / st.shared of any thread, once visible to this thread) -> visible to the async proxy
+// (TMA loads issued afterwards by this thread), all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---------------------------------------------------------------- grid-wide barrier (persistent kernels, all CTAs co-resident)
+// One monotonically increasing counter in global memory (never reset inside a launch; the host zeroes it before the
+// launch): every CTA adds 1 per barrier and waits until the count reaches `target` = barriers so far * CTAs.
+// Release / acquire at gpu scope; the bracketing __syncthreads make the whole CTA's writes part of the release and the
+// whole CTA a reader of the acquire. The proxy fences order generic global writes before later TMA (async proxy) reads.
+// A protocol bug traps (launch error) instead of hanging the box.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  fence_proxy_async_global();   // this thread's generic global writes -> async proxy (a later TMA load of any CTA)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // release: cumulative over the CTA's writes ordered before it by the bar.sync above
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int v, spins = 0;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (++spins > (1u << 24)) __trap();
+    } while (static_cast<int>(v - target) < 0);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire (also invalidates this SM's L1)
+  }
+  __syncthreads();
+}
+// the first version measured on B200: 1.66 us per barrier (tools/hgemm_lab bar); kept for A/B
+__device__ __forceinline__ void grid_barrier_v0(unsigned int* counter, unsigned int target) {
+  fence_proxy_async_all();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int v, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (++spins > (1u << 24)) __trap();
+    } while (static_cast<int>(v - target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+  fence_proxy_async_all();
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
