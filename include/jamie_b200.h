@@ -9,7 +9,7 @@
  *     The Python wrapper raises RuntimeError / AssertionError with the reference's own messages where it has one.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). All device work of a call is
  *     enqueued on it; calls do not synchronise the host unless stated.
- *   - the handle owns parameters, Adam moments, BatchNorm statistics, datasets, workspaces and CUDA graphs; the
+ *   - the handle owns parameters, Adam moments, BatchNorm statistics, datasets and workspaces; the
  *     caller owns every buffer it passes in. A handle is bound to one device and is not thread-safe.
  *   - "packed" parameter order = edModelVar.named_parameters() order (jamie/model.py:147-220):
  *       sigma[2]; encoders.{0,1}.{0.weight,0.bias,1.weight,1.bias,4.weight,4.bias,5.weight,5.bias};
@@ -89,22 +89,18 @@ int jb_inject_randomness(jb_engine* e, const float* eps0, const float* eps1, con
                          void* stream);
 
 /* Run `nsteps` full optimizer steps from the plan cursor: gather, P/F blocks, forward, 4 losses, backward,
- * clip_grad_norm_, Adam, zero_grad (jamie/jamie.py:549-742 with batch_step=True). Asynchronous; one CUDA-graph
- * launch per step, no host synchronisation. */
+ * clip_grad_norm_, Adam, zero_grad (jamie/jamie.py:549-742 with batch_step=True). Asynchronous; ONE launch of the
+ * persistent step kernel for all `nsteps` steps (csrc/stepk.cuh), no host synchronisation. */
 int jb_train_steps(jb_engine* e, int nsteps, void* stream);
 /* Data-parallel split of one step: backward leaves the summed-loss gradients in the flat buffer returned by
  * jb_grad_buffer (the caller all-reduces it, e.g. NCCL sum), update divides by world_size, clips and applies Adam. */
 int jb_step_backward(jb_engine* e, void* stream);
 int jb_step_update(jb_engine* e, void* stream);
 int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats);
-/* The same data-parallel step with the exchange overlapped (world_size > 1): part 0 runs the forward pass and the backward
- * pass down to the latent layer and completes gradient bucket 0 (heads + decoders + the loss scalars), part 1 runs the
- * encoder backward and completes bucket 1 (sigma + encoders). The caller all-reduces bucket 0 on a second stream while
- * part 1 runs, then bucket 1, then calls jb_step_update. The two buckets tile the buffer of jb_grad_buffer. */
-int jb_step_backward_part(jb_engine* e, int part, void* stream);
-int jb_grad_bucket(jb_engine* e, int part, float** dev_ptr, long long* n_floats);
-/* batch_step=False (jamie/jamie.py:744-749): accumulate gradients over several jb_step_backward calls.
- * accumulate != 0 makes the next backward add into the gradient buffer instead of overwriting it. */
+/* batch_step=False (jamie/jamie.py:744-749): accumulate gradients over several jb_step_backward calls, one
+ * jb_step_update per epoch. accumulate != 0 makes the following backward passes add into the gradient buffer instead of
+ * overwriting it (a device-side flag: no rebuild, no synchronisation). The optimizer step count (Adam bias correction)
+ * advances per jb_step_update, the Philox stream per backward pass. */
 int jb_set_grad_accumulate(jb_engine* e, int accumulate);
 
 /* One optimizer step whose batch arrives from HOST memory (the reference keeps self.dataset wherever `device` says;
@@ -129,15 +125,19 @@ int jb_hostbatch_submit(jb_engine* e, const float* x0, const float* x1, const lo
                         double kl_anneal, void* stream);
 int jb_hostbatch_wait(jb_engine* e, float out_losses[8]);
 
-/* Benchmark hook: launch GEMM stage `stage` of the training step (0..5 forward: enc1, enc2, heads, dec1, dec2, dec3;
- * 6..11 backward in execution order) `iters` times on `stream`, timed with CUDA events on that stream.
- * Returns the average microseconds per launch and the FLOPs of one launch. */
-int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* flops, void* stream);
+/* Phases of the step kernel (csrc/stepk.cuh: StepPhase), in execution order. */
+int jb_num_phases(void);
+const char* jb_phase_name(int phase);
 
-/* Profiling hook: runs `iters` (+1 warm-up) training steps launch by launch (no graph) with a CUDA event between
- * consecutive launches and returns the average microseconds between the events, i.e. each kernel's in-stream time with
- * a warm L2. out_us[k] belongs to launch k of the step (same order as the ncu launch list); *n_launches = count.
- * Consumes plan row 0 every iteration (the cursor is rewound) and takes optimizer steps like jb_train_steps. */
+/* Benchmark hook: `iters` launches of the step kernel restricted to ONE phase, timed with CUDA events on `stream`.
+ * Returns the average microseconds per launch (kernel set-up included: an upper bound of the phase's share of a step)
+ * and, for GEMM phases, the FLOPs of one launch (0 otherwise). */
+int jb_bench_stage(jb_engine* e, int phase, int iters, float* avg_us, double* flops, void* stream);
+
+/* Profiling hook: runs `iters` (+1 warm-up) training steps in ONE launch of the persistent step kernel while CTA 0 records
+ * the GPU global timer at every phase boundary; out_us[p] = average microseconds of phase p inside the kernel (its grid
+ * barrier included), *n_launches = jb_num_phases(). Rewinds the plan cursor first (needs >= 2 plan rows) and takes
+ * optimizer steps like jb_train_steps. */
 int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_launches, void* stream);
 
 /* Per-step results of the steps run since the last jb_upload_plan, in plan order. Synchronises `stream`.
@@ -170,7 +170,7 @@ int jb_pca_inverse(jb_engine* e, const float* Z, long long n, int k, const float
  * Names: "x0","y1_0","h1_0","y2_0","h2_0","mulv0","z0","c0","xhat0", ... (see csrc/engine.cu: tap table),
  * "corr", "fblk", "grad" (padded flat), "theta". Returns the number of floats written, or -1. */
 long long jb_debug_read(jb_engine* e, const char* name, float* out, long long cap);
-/* number of kernel launches issued by the handle so far (graph nodes counted per replay) */
+/* number of kernel launches issued by the handle so far */
 long long jb_launch_count(const jb_engine* e);
 
 #ifdef __cplusplus

@@ -58,13 +58,13 @@ SIGNATURES = {
     'jb_step_backward': (C.c_int, [_P, _P]),
     'jb_step_update': (C.c_int, [_P, _P]),
     'jb_grad_buffer': (C.c_int, [_P, C.POINTER(_P), C.POINTER(_LL)]),
-    'jb_step_backward_part': (C.c_int, [_P, C.c_int, _P]),
-    'jb_grad_bucket': (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_LL)]),
     'jb_set_grad_accumulate': (C.c_int, [_P, C.c_int]),
     'jb_train_step_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P, _P]),
     'jb_step_backward_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),
     'jb_hostbatch_submit': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),
     'jb_hostbatch_wait': (C.c_int, [_P, _P]),
+    'jb_num_phases': (C.c_int, []),
+    'jb_phase_name': (C.c_char_p, [C.c_int]),
     'jb_bench_stage': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), _P]),
     'jb_profile_step': (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
     'jb_read_losses': (C.c_int, [_P, _P, C.c_int, _P]),

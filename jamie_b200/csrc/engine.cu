@@ -1,16 +1,21 @@
 // jamie_b200 engine: device state of one JAMIE model (both modalities' encoder/decoder MLPs, Adam moments, BatchNorm
 // statistics, resident datasets) and the C ABI declared in include/jamie_b200.h.
 //
-// Memory layout (all fp32, one cudaMalloc arena each):
-//   theta / grad / adam_m / adam_v : one flat buffer each with the SAME padded layout. Every tensor starts on a
-//       128-byte boundary and 2-D weights use a row pitch rounded up to 4 floats so that TMA can address them
-//       directly (tensor maps need 16-byte aligned bases and pitches). Padding stays zero forever (zero gradient ->
-//       zero Adam update), so clip-norm and Adam run over the whole buffer with 128-bit accesses.
+// Memory layout:
+//   theta / grad / adam_m / adam_v (fp32) : one flat buffer each with the SAME padded layout. Every tensor starts on a
+//       128-byte boundary and 2-D weights use a row pitch rounded up to 8 elements so that TMA can address them directly
+//       in fp32 and in fp16 (tensor maps need 16-byte aligned bases and pitches). Padding stays zero forever (zero
+//       gradient -> zero Adam update), so clip-norm and Adam run over the whole buffer with 128-bit accesses.
 //       fc_mus.i / fc_vars.i are stored as ONE [2L, D] matrix per modality (mu rows, then logvar rows): one heads GEMM.
-//   activations: [B, pitch] row-major per layer and modality, pitch = width rounded up to 4 floats.
-// One training step = one CUDA graph (built once per batch size) of ~35 kernels; every step-varying scalar (plan row,
-// KL anneal, Adam bias corrections, Philox stream) lives in a device-side control block.
+//   theta_hi / theta_lo (fp16)            : the GEMM operand planes of theta (hgemm.cuh), same element offsets,
+//       rewritten by every Adam step.
+//   activations: [B, pitch] row-major per layer and modality, pitch = width rounded up to 8 elements; GEMM outputs are
+//       fp32 (with room for split-K partial sums), GEMM inputs are fp16 hi / lo planes.
+// One training step = the phases of ONE persistent cooperative kernel (stepk.cuh); every step-varying scalar (plan row,
+// KL anneal, Adam bias corrections, Philox stream) derives from a device-side control block, so jb_train_steps(n) is a
+// single launch for n optimizer steps.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -25,6 +30,8 @@
 #include "gemm_tf32.cuh"
 #include "gemm_persistent.cuh"
 #include "kernels.cuh"
+#include "hgemm.cuh"
+#include "stepk.cuh"
 
 namespace {
 
@@ -45,6 +52,7 @@ int fail(const char* fmt, ...) {
   } while (0)
 
 inline int r4(int x) { return (x + 3) & ~3; }
+inline int r8(int x) { return (x + 7) & ~7; }
 inline long long r32(long long x) { return (x + 31) & ~31LL; }
 
 struct Seg {  // one tensor of the padded flat layout
@@ -63,31 +71,26 @@ struct ModSegs {
   Seg W3, b3, g3, be3, W4, b4, g4, be4, W5, b5;  // decoder: Linear(L,D) BN(D) | Linear(D,2D) BN(2D) | Linear(2D,D)
 };
 
-struct Planes {  // a GEMM operand as TF32 hi / lo planes (same shape and pitch); see gemm_tf32.cuh
-  float *hi = nullptr, *lo = nullptr;
-};
-struct ModActs {  // activations and gradients of one modality (device pointers, pitches in floats)
-  float *x, *y1, *y2, *mulv, *y3, *y4, *xhat;           // fp32: gathered input and GEMM outputs
+using jb::HPlanes;
+struct ModActs {  // activations and gradients of one modality (device pointers; pitches in elements)
+  float* x; HPlanes xp;
   float* x_stage[2];                                     // host-batch steps: two H2D landing buffers for x
-  Planes xp, h1, h2, cp, g1, g2;                         // forward GEMM operands
-  float *dg2, *dg1, *dc, *dmulv, *dh2, *dh1;             // fp32: dgrad outputs (+ dmulv from the latent backward)
-  Planes dxhat, dy4, dy3, dmp, dy2, dy1;                 // backward GEMM operands
+  HPlanes h1, h2, cp, g1, g2;                            // forward GEMM operands
+  HPlanes dxhat, dy4, dy3, dmp, dy2, dy1;                // backward GEMM operands
+  float* dmulv;
   float *z, *c, *S, *g, *eps, *inj_eps, *den, *rs;
   float *bn_mean[4], *bn_inv[4];  // enc1, enc2, dec1, dec2
   unsigned char* inj_mask[4];
   float* rec_part;
-  int ldD, ld2D, ldmv, LP;
-};
-
-struct GemmStage {
-  int first = 0, count = 0, ctas = 0;
-  int ck = 1;   // split-K factor = cluster size of the launch (gemm_tf32.cuh)
+  // GEMM outputs (fp32, split-K partial sums; carved per table build)
+  jb::Parts y1, y2, mulv, y3, y4, xhat, dg2, dg1, dc, dh2, dh1;
+  int ldD, ld2D;
 };
 
 }  // namespace
 
 struct HostPin {
-  long long cursor_val[2];   // {0, 1}: plan row of a slot, copied into the control block before the step graph
+  long long cursor_val[2];   // {0, 1}: plan row of a slot, copied into the control block before the step
   int slot_val[2];           // {0, 1}
   float kl[2];
   float losses[2][8];
@@ -96,17 +99,16 @@ struct HostPin {
 
 struct jb_engine {
   jb_config cfg{};
-  int D[2]{}, L = 0, LP = 0, Bmax = 0;
+  int D[2]{}, L = 0, LP = 0, ldmv = 0, Bmax = 0;
   // flat parameter layout
   ModSegs ms[2];
   Seg sigma;
-  long long n_flat = 0;  // padded float count (multiple of 4)
-  long long n_enc = 0;   // floats [0, n_enc): sigma + both encoders; [n_enc, n_flat): heads + decoders
+  long long n_flat = 0;  // padded float count (multiple of 32)
   std::vector<PackMap> packmap;
   long long n_packed = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
-  float *theta_hi = nullptr, *theta_lo = nullptr;   // TF32 planes of theta (same layout), rewritten by every Adam step
-  float* state_slab = nullptr;   // one allocation: theta | adam_m | adam_v | theta_hi | theta_lo
+  __half *theta_hi = nullptr, *theta_lo = nullptr;   // fp16 operand planes of theta (same element offsets)
+  float* state_slab = nullptr;   // one allocation: theta | adam_m | adam_v | theta_hi, theta_lo
   size_t slab_bytes = 0;
   // BatchNorm running statistics: 8 layers in packed order (enc0.1, enc0.5, enc1.1, enc1.5, dec0.1, dec0.5, dec1.1, dec1.5)
   float* bn_run = nullptr;
@@ -120,47 +122,40 @@ struct jb_engine {
   float *p_diag = nullptr, *p_dense = nullptr, *f_dense = nullptr;
   long long pn0 = 0, pn1 = 0, p_diag_n = 0;
   // plan
-  int *plan_idx[2]{};
+  int* plan_idx[2]{};
   float* plan_kl = nullptr;
   float* out_loss = nullptr;
   int plan_cap = 0, plan_steps = 0, plan_B = 0;
   jb::Ctl* ctl = nullptr;
   double* norm_part = nullptr;
+  unsigned int* bar = nullptr;          // grid barrier counter of k_step
+  unsigned long long* d_ts = nullptr;   // phase timestamps (profiling)
   // workspaces
   char* arena = nullptr;
   size_t arena_bytes = 0;
+  char* parts_arena = nullptr;          // GEMM outputs with their split-K partials (depends on the batch size)
   ModActs act[2]{};
-  float *corr = nullptr, *corr_t = nullptr, *fblk = nullptr, *fblk_t = nullptr, *rs_p = nullptr, *rs_f = nullptr;
+  float *corr = nullptr, *corr_t = nullptr, *fblk = nullptr, *fblk_t = nullptr;
   float *lat_r = nullptr, *rowpart = nullptr;
-  // GEMM tables (device) for the training step at batch size graph_B
-  jb::GemmProblem* d_probs = nullptr;
-  std::vector<jb::GemmProblem> h_probs;
-  GemmStage st_f[6], st_b[7];   // st_b[5]: all wgrads, or (data-parallel) heads + decoder wgrads with st_b[6] = encoder wgrads
-  cudaGraphExec_t g_bwd_part[2]{};   // data-parallel step in two halves (see build_layout)
-  bool dp_split = false;             // set by the first jb_step_backward_part: wgrads in two launches
-  int launches_bwd_part[2]{};
-  int graph_B = 0;
-  bool graph_accum = false;
-  cudaGraphExec_t g_full = nullptr, g_bwd = nullptr, g_upd = nullptr, g_host = nullptr, g_host_bwd = nullptr;
+  // step tables at batch size step_B
+  std::vector<jb::HgProblem> h_probs;
+  jb::HgProblem* d_probs = nullptr;
+  jb::StepCtx h_ctx{};
+  jb::StepCtx* d_ctx = nullptr;
+  int step_B = 0;
+  int grid = 148;            // CTAs of k_step: one per SM
+  int accumulate = 0, accumulate_dev = 0;
+  int wgrad_mode = jb::HG_MEDIUM;
+  int wgrad_bn = 256;
+  int max_ksplit = 8;
+  float gs = 1.f;
   // Host-batch steps (data resident on the host): two slots so that the copies of batch k + 1 run while step k computes.
   struct HostPin* h_pin = nullptr;   // pinned: constants, per-slot kl / losses / indices
   cudaStream_t h2d_stream = nullptr;
   cudaEvent_t ev_h2d[2]{}, ev_slot_free[2]{}, ev_loss[2]{};
   bool slot_used[2]{};
   int hb_slot = 0, hb_oldest = 0, hb_outstanding = 0;
-  int launches_host = 0, launches_host_bwd = 0;
-  cudaStream_t cap_stream = nullptr, side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool use_side = true;      // P / F block build on a forked branch of the step graph (JB_SIDE=0 disables)
-  int wgrad_bn = 256;        // widest N tile of the batched wgrad launch
-  int dgrad_split = 1;       // dgrads in 3xTF32 (1) or one TF32 pass on the hi planes (JB_DGRAD_SPLIT=0: exploration)
-  int adam_blocks = 888;     // grid of k_adam: 6 blocks of 256 threads per SM (JB_ADAM_BLOCKS; 592: +2.7 us/step)
-  int slab_cw = 16;          // columns per block of the BatchNorm / reconstruction slab kernels: 16 (1024 threads) or 8 (512)
-  int accumulate = 0;
-  int precision_fast = 0;    // JB_PRECISION=tf32: single-pass TF32 everywhere (no parity claim)
-  bool pending_inject = false;
-  bool use_pdl = true;       // programmatic dependent launch between the kernels of the step graph (JB_PDL=0 disables)
-  bool use_splitk = true;    // split-K clusters for stages with few tiles (JB_SPLITK=0 disables)
+  int precision_fast = 0;    // JB_PRECISION=f16: single-pass fp16 everywhere (no parity claim)
   int num_sms = 148;
   // eval
   bool eval_dirty = true;
@@ -173,7 +168,6 @@ struct jb_engine {
   cudaStream_t ev_stream[2]{};
   cudaEvent_t ev_done[2]{}, ev_free[2]{};
   long long launches = 0;
-  int launches_per_step = 0, launches_bwd = 0, launches_upd = 0;
 };
 
 namespace {
@@ -182,7 +176,7 @@ using jb::GemmProblem;
 
 // ------------------------------------------------------------------------------------------- layout
 void add_seg(jb_engine* e, Seg& s, int rows, int cols) {
-  s.rows = rows; s.cols = cols; s.ld = rows > 1 ? r4(cols) : cols;
+  s.rows = rows; s.cols = cols; s.ld = rows > 1 ? r8(cols) : cols;
   s.off = e->n_flat;
   e->n_flat = r32(e->n_flat + (rows > 1 ? s.span() : cols));
 }
@@ -190,16 +184,12 @@ void build_layout(jb_engine* e) {
   const int L = e->L;
   e->n_flat = 0;
   add_seg(e, e->sigma, 1, 2);
-  // Encoder tensors of both modalities first, then heads + decoders: the gradients of the second part are complete
-  // half-way through the backward pass, so the data-parallel step can all-reduce that bucket while the encoder backward
-  // still runs (jb_step_backward_part / jb_grad_bucket).
   for (int i = 0; i < 2; ++i) {
     const int D = e->D[i];
     ModSegs& m = e->ms[i];
     add_seg(e, m.W1, 2 * D, D); add_seg(e, m.b1, 1, 2 * D); add_seg(e, m.g1, 1, 2 * D); add_seg(e, m.be1, 1, 2 * D);
     add_seg(e, m.W2, D, 2 * D); add_seg(e, m.b2, 1, D); add_seg(e, m.g2, 1, D); add_seg(e, m.be2, 1, D);
   }
-  e->n_enc = e->n_flat;
   for (int i = 0; i < 2; ++i) {
     const int D = e->D[i];
     ModSegs& m = e->ms[i];
@@ -268,415 +258,221 @@ void carve(jb_engine* e, Carver& c) {
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i];
     const int D = e->D[i];
-    a.ldD = r4(D); a.ld2D = r4(2 * D); a.ldmv = r4(2 * e->L); a.LP = e->LP;
-    auto planes = [&](Planes& p, size_t n) { p.hi = c.take<float>(n); p.lo = c.take<float>(n); };
+    a.ldD = r8(D); a.ld2D = r8(2 * D);
+    auto planes = [&](HPlanes& p, size_t n) { p.hi = c.take<__half>(n); p.lo = c.take<__half>(n); };
     a.x = c.take<float>(B * a.ldD); planes(a.xp, B * a.ldD);
     a.x_stage[0] = c.take<float>(B * a.ldD); a.x_stage[1] = c.take<float>(B * a.ldD);
-    a.y1 = c.take<float>(B * a.ld2D); planes(a.h1, B * a.ld2D);
-    a.y2 = c.take<float>(B * a.ldD); planes(a.h2, B * a.ldD); a.mulv = c.take<float>(B * a.ldmv);
-    a.y3 = c.take<float>(B * a.ldD); planes(a.g1, B * a.ldD); a.y4 = c.take<float>(B * a.ld2D);
-    planes(a.g2, B * a.ld2D); a.xhat = c.take<float>(B * a.ldD);
-    planes(a.dxhat, B * a.ldD); a.dg2 = c.take<float>(B * a.ld2D); planes(a.dy4, B * a.ld2D);
-    a.dg1 = c.take<float>(B * a.ldD); planes(a.dy3, B * a.ldD); a.dc = c.take<float>(B * a.LP);
-    a.dmulv = c.take<float>(B * a.ldmv); planes(a.dmp, B * a.ldmv); a.dh2 = c.take<float>(B * a.ldD); planes(a.dy2, B * a.ldD);
-    a.dh1 = c.take<float>(B * a.ld2D); planes(a.dy1, B * a.ld2D);
-    a.z = c.take<float>(B * a.LP); a.c = c.take<float>(B * a.LP); planes(a.cp, B * a.LP); a.S = c.take<float>(B * a.LP);
-    a.g = c.take<float>(B * a.LP); a.eps = c.take<float>(B * a.LP); a.inj_eps = c.take<float>(B * a.LP);
+    planes(a.h1, B * a.ld2D); planes(a.h2, B * a.ldD); planes(a.g1, B * a.ldD); planes(a.g2, B * a.ld2D);
+    planes(a.dxhat, B * a.ldD); planes(a.dy4, B * a.ld2D); planes(a.dy3, B * a.ldD);
+    a.dmulv = c.take<float>(B * e->ldmv); planes(a.dmp, B * e->ldmv); planes(a.dy2, B * a.ldD); planes(a.dy1, B * a.ld2D);
+    a.z = c.take<float>(B * e->LP); a.c = c.take<float>(B * e->LP); planes(a.cp, B * e->LP); a.S = c.take<float>(B * e->LP);
+    a.g = c.take<float>(B * e->LP); a.eps = c.take<float>(B * e->LP); a.inj_eps = c.take<float>(B * e->LP);
     a.den = c.take<float>(B); a.rs = c.take<float>(B);
     const int w[4] = {2 * D, D, D, 2 * D};
     for (int k = 0; k < 4; ++k) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>((D + 7) / 8);
+    a.rec_part = c.take<float>((D + jb::SK_CW - 1) / jb::SK_CW);
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
-  e->rs_p = c.take<float>(B); e->rs_f = c.take<float>(B);
   e->lat_r = c.take<float>(B * e->LP); e->rowpart = c.take<float>(2 * B * 8);
 }
 
-// ------------------------------------------------------------------------------------------- GEMM tables
-// Forward GEMMs and dgrads run the error-compensated 3xTF32 mode on hi/lo planes (fp32-class accuracy): pre-activation
-// errors flip LeakyReLU' decisions and dX errors propagate down the chain. A wgrad's TF32 rounding (~3e-4 relative,
-// unbiased) stays local to that gradient tensor, so wgrads are single-pass on the hi planes.
-int add_prob(jb_engine* e, Planes A, int lda, int a_mn, Planes Bm, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
-             int bn, int epi, const float* bias, int accumulate, int split) {
-  GemmProblem g;
-  if (e->precision_fast) split = 0;
-  int rc = jb::gemm_problem_fill(&g, A.hi, lda, a_mn, Bm.hi, ldb, b_mn, C, ldc, M, N, K, bn, epi, bias, jb::LRELU, accumulate, 0,
-                                 split ? A.lo : nullptr, split ? Bm.lo : nullptr);
-  if (rc) return fail("cuTensorMapEncodeTiled failed (%d) for M%d N%d K%d lda%d ldb%d", rc, M, N, K, lda, ldb);
-  e->h_probs.push_back(g);
-  return 0;
-}
-int choose_bn(int N) {
-  if (N <= 32) return 32;
-  return 64;  // more CTAs beat wider tiles at these problem sizes
-}
-// Closes the stage made of h_probs[first ..]: picks its split-K factor and assigns CTA ranges.
-void close_stage(jb_engine* e, GemmStage& st, int first) {
-  st.first = first;
-  st.count = static_cast<int>(e->h_probs.size()) - first;
-  st.ck = e->use_splitk ? jb::gemm_pick_splitk(e->h_probs.data() + first, st.count, e->num_sms) : 1;
-  st.ctas = jb::gemm_table_finalize(e->h_probs.data() + first, st.count, st.ck);
-}
-
-int build_train_tables(jb_engine* e, int B, int accum) {
-  e->h_probs.clear();
-  float* T = e->theta;
-  float* G = e->grad;
-  const int L = e->L;
-  auto W = [&](const Seg& s) { return Planes{e->theta_hi + s.off, e->theta_lo + s.off}; };
-  auto bias = [&](const Seg& s) { return T + s.off; };
-  auto dW = [&](const Seg& s) { return G + s.off; };
-  // ---- forward:  Y[B, N_out] = X W^T + b   (A = X planes K-major, B = W planes K-major)
-  auto fwd = [&](GemmStage& st, auto pick) {
-    const int f0 = static_cast<int>(e->h_probs.size());
-    for (int i = 0; i < 2; ++i) if (pick(i)) return 1;
-    close_stage(e, st, f0);
-    return 0;
-  };
-  auto lin = [&](Planes X, int ldx, const Seg& w, const Seg& b, float* Y, int ldy, int n_out, int n_in) {
-    return add_prob(e, X, ldx, 0, W(w), w.ld, 0, Y, ldy, B, n_out, n_in, choose_bn(n_out), jb::EPI_BIAS, bias(b), 0, 1);
-  };
-  if (fwd(e->st_f[0], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.xp, a.ldD, m.W1, m.b1, a.y1, a.ld2D, 2 * D, D); })) return 1;
-  if (fwd(e->st_f[1], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.h1, a.ld2D, m.W2, m.b2, a.y2, a.ldD, D, 2 * D); })) return 1;
-  if (fwd(e->st_f[2], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.h2, a.ldD, m.Wmv, m.bmv, a.mulv, a.ldmv, 2 * L, D); })) return 1;
-  if (fwd(e->st_f[3], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.cp, a.LP, m.W3, m.b3, a.y3, a.ldD, D, L); })) return 1;
-  if (fwd(e->st_f[4], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.g1, a.ldD, m.W4, m.b4, a.y4, a.ld2D, 2 * D, D); })) return 1;
-  if (fwd(e->st_f[5], [&](int i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        return lin(a.g2, a.ld2D, m.W5, m.b5, a.xhat, a.ldD, D, 2 * D); })) return 1;
-  // ---- backward: dgrad dX[B, N_in]     = dY W    (A = dY planes K-major, B = W planes MN-major, K = N_out): one stage
-  //                per layer on the critical path;
-  //                wgrad dW[N_out, N_in] = dY^T X  (A = dY hi MN-major, B = X hi MN-major, K = batch, single pass): nothing
-  //                downstream of a wgrad but the optimizer, so all twelve run as ONE launch at the end of the backward pass.
-  auto wgrad = [&](Planes dY, int lddy, Planes X, int ldx, const Seg& s, int n_out, int n_in) {
-    // single pass: wide tiles cut the CTA count and the operand bytes per output; with 256-wide tiles the twelve wgrads
-    // of the headline shapes are ONE wave of 140 CTAs instead of 272 CTAs in two (profiles/README.md; JB_WGRAD_BN=128
-    // restores the narrower tiles)
-    const int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
-    return add_prob(e, dY, lddy, 1, X, ldx, 1, dW(s), s.ld, n_out, n_in, B, bn, jb::EPI_STORE, nullptr, accum, 0);
-  };
-  auto dgrad = [&](Planes dY, int lddy, const Seg& s, float* dX, int lddx, int n_out, int n_in) {
-    return add_prob(e, dY, lddy, 0, W(s), s.ld, 1, dX, lddx, B, n_in, n_out, choose_bn(n_in), jb::EPI_STORE, nullptr, 0, e->dgrad_split);
-  };
-  int first = static_cast<int>(e->h_probs.size());   // B6: last decoder Linear(2D -> D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dxhat, a.ldD, m.W5, a.dg2, a.ld2D, D, 2 * D)) return 1; }
-  close_stage(e, e->st_b[0], first);
-  first = static_cast<int>(e->h_probs.size());       // B5: decoder Linear(D -> 2D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dy4, a.ld2D, m.W4, a.dg1, a.ldD, 2 * D, D)) return 1; }
-  close_stage(e, e->st_b[1], first);
-  first = static_cast<int>(e->h_probs.size());       // B4: decoder Linear(L -> D)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dy3, a.ldD, m.W3, a.dc, a.LP, D, L)) return 1; }
-  close_stage(e, e->st_b[2], first);
-  first = static_cast<int>(e->h_probs.size());       // B3: heads Linear(D -> 2L)
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dmp, a.ldmv, m.Wmv, a.dh2, a.ldD, 2 * L, D)) return 1; }
-  close_stage(e, e->st_b[3], first);
-  first = static_cast<int>(e->h_probs.size());       // B2: encoder Linear(2D -> D); Linear(D -> 2D) needs no input gradient
-  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    if (dgrad(a.dy2, a.ldD, m.W2, a.dh1, a.ld2D, D, 2 * D)) return 1; }
-  close_stage(e, e->st_b[4], first);
-  // weight gradients (largest problems first): all twelve in one launch at the end. Two-part data-parallel backward
-  // (jb_step_backward_part): the heads + decoder wgrads right after the latent backward (their gradient bucket is
-  // all-reduced while the encoder backward runs), the encoder wgrads at the end.
-  const bool split_w = e->dp_split;
-  auto wgrad_stage = [&](GemmStage& st, bool dec, bool enc) {
-    const int f0 = static_cast<int>(e->h_probs.size());
-    for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-      if (dec && (wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D) || wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D))) return 1;
-      if (enc && (wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D) || wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D))) return 1; }
-    if (dec)
-      for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-        if (wgrad(a.dmp, a.ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D) || wgrad(a.dy3, a.ldD, a.cp, a.LP, m.W3, D, L)) return 1; }
-    close_stage(e, st, f0);
-    st.ck = 1;   // wide tiles, about one wave of CTAs: no split-K
-    st.ctas = jb::gemm_table_finalize(e->h_probs.data() + f0, st.count, 1);
-    return 0;
-  };
-  e->st_b[6] = GemmStage{};
-  if (split_w) { if (wgrad_stage(e->st_b[5], true, false) || wgrad_stage(e->st_b[6], false, true)) return 1; }
-  else if (wgrad_stage(e->st_b[5], true, true)) return 1;
-  if (e->d_probs) cudaFree(e->d_probs);
-  CU(cudaMalloc(&e->d_probs, e->h_probs.size() * sizeof(GemmProblem)));
-  CU(cudaMemcpy(e->d_probs, e->h_probs.data(), e->h_probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice));
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------- step recording
-struct Rec {  // launches kernels on a stream and counts them
-  jb_engine* e; cudaStream_t s; int n = 0; cudaError_t err = cudaSuccess;
-  // Capture only: a second stream forked off the step's stream so that kernels nothing upstream depends on (the P / F
-  // block build) run beside the encoder instead of in front of it. Null: everything is launched in order on s.
-  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool no_pdl_next = false;   // the next launch has a cross-stream dependency: plain (full) serialization
-  bool mute = false;          // recording the other half of a two-part backward: launches are skipped
-
-
-  cudaEvent_t* ev = nullptr;        // profiling: ev[k] is recorded after launch k - 1 (ev[0] before the first launch)
-  const char** names = nullptr;
-  void mark(const char* name) {
-    if (ev && n < 63) { names[n] = name; cudaEventRecord(ev[n + 1], s); }
-  }
-  void gemm(const GemmStage& st) {
-    if (mute) return;
-    if (err == cudaSuccess)
-      err = jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, e->use_pdl && !no_pdl_next, st.ck, e->h_probs.data() + st.first);
-    no_pdl_next = false;
-    mark("gemm");
-    ++n;
-  }
+// ------------------------------------------------------------------------------------------- step tables
+// Forward GEMMs and dgrads run the fp32-class 3-pass mode on the fp16 hi / lo planes (HG_PRECISE): pre-activation errors
+// flip LeakyReLU' decisions and dX errors propagate down the chain. Weight gradients run three passes without the
+// accumulator drains (HG_MEDIUM, ~1e-6): their rounding stays local to the gradient tensor, but a single pass (3e-4 at
+// the headline shape, up to 1.2e-3 at small ones, measured in round 1) would eat the whole 1e-3 parity budget.
+struct StageSpec {   // one problem of a GEMM phase before its split-K factor is known
+  HPlanes A; int lda, a_mn; HPlanes Bm; int ldb, b_mn;
+  jb::Parts* out;    // activation output (partials carved later) or null ...
+  float* C;          // ... for weight gradients, which go straight into the gradient buffer
+  int ldc, M, N, K, bn, mode, epi;
+  const float* bias;
+  float out_scale;
+  int acc_dynamic;
 };
 
-// Every kernel of the step starts with griddepcontrol.launch_dependents + griddepcontrol.wait (kernels.cuh), so with
-// programmatic stream serialization the next kernel's launch latency and prologue overlap this kernel's execution while
-// all data dependencies (transitively) still see completed, flushed predecessors.
-template <typename... KP, typename... A>
-void launchk(Rec& r, void (*kern)(KP...), dim3 grid, dim3 block, A... args) {
-  if (r.mute) return;
-  if (r.err != cudaSuccess) { ++r.n; return; }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = r.s;
-  cudaLaunchAttribute at[1];
-  int na = 0;
-  if (r.e->use_pdl && !r.no_pdl_next) {
-    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
+int build_step(jb_engine* e, int B) {
+  const int L = e->L;
+  float* T = e->theta;
+  float* G = e->grad;
+  auto W = [&](const Seg& s) { return HPlanes{e->theta_hi + s.off, e->theta_lo + s.off}; };
+  auto bias = [&](const Seg& s) { return T + s.off; };
+  // loss scale of the backward pass: d xhat = gs * 2 w (xhat - x) / (B D) is O(xhat - x)
+  {
+    const int Dm = e->D[0] > e->D[1] ? e->D[0] : e->D[1];
+    float wmax = 1.f;
+    for (int k = 0; k < 4; ++k) wmax = fmaxf(wmax, fabsf(e->cfg.loss_w[k]));
+    const int ex = static_cast<int>(ceil(log2(static_cast<double>(B) * Dm))) - static_cast<int>(ceil(log2(static_cast<double>(wmax))));
+    e->gs = ldexpf(1.f, ex < 0 ? 0 : (ex > 30 ? 30 : ex));
+    if (const char* pv = getenv("JB_LOSS_SCALE_LOG2")) e->gs = ldexpf(1.f, atoi(pv));
   }
-  cfg.attrs = at;
-  cfg.numAttrs = na;
-  r.no_pdl_next = false;
-  r.err = cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
-  r.mark(nullptr);
-  ++r.n;
-}
-
-jb::StepConsts make_consts(const jb_engine* e, int B) {
-  jb::StepConsts sc{};
+  const float inv_gs = 1.f / e->gs;
+  const int fmode = e->precision_fast ? jb::HG_SINGLE : jb::HG_PRECISE;
+  const int wmode = e->precision_fast ? jb::HG_SINGLE : e->wgrad_mode;
+  std::vector<std::vector<StageSpec>> st(jb::SK_NUM_GEMM);
+  auto fbn = [&](int N) { return N <= 32 ? 32 : 64; };
+  for (int i = 0; i < 2; ++i) {
+    ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    auto fwd = [&](int stage, HPlanes X, int ldx, const Seg& w, const Seg& b, jb::Parts* out, int ldy, int n_out, int n_in) {
+      st[stage].push_back(StageSpec{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode, jb::EPI_BIAS, bias(b), 1.f, 0});
+    };
+    fwd(0, a.xp, a.ldD, m.W1, m.b1, &a.y1, a.ld2D, 2 * D, D);
+    fwd(1, a.h1, a.ld2D, m.W2, m.b2, &a.y2, a.ldD, D, 2 * D);
+    fwd(2, a.h2, a.ldD, m.Wmv, m.bmv, &a.mulv, e->ldmv, 2 * L, D);
+    fwd(3, a.cp, e->LP, m.W3, m.b3, &a.y3, a.ldD, D, L);
+    fwd(4, a.g1, a.ldD, m.W4, m.b4, &a.y4, a.ld2D, 2 * D, D);
+    fwd(5, a.g2, a.ld2D, m.W5, m.b5, &a.xhat, a.ldD, D, 2 * D);
+    // dgrad dX[B, N_in] = dY W   (A = dY planes K-major, B = W planes MN-major, K = N_out)
+    auto dgrad = [&](int stage, HPlanes dY, int lddy, const Seg& s, jb::Parts* out, int lddx, int n_out, int n_in) {
+      st[stage].push_back(StageSpec{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0});
+    };
+    dgrad(6, a.dxhat, a.ldD, m.W5, &a.dg2, a.ld2D, D, 2 * D);
+    dgrad(7, a.dy4, a.ld2D, m.W4, &a.dg1, a.ldD, 2 * D, D);
+    dgrad(8, a.dy3, a.ldD, m.W3, &a.dc, e->LP, D, L);
+    dgrad(9, a.dmp, e->ldmv, m.Wmv, &a.dh2, a.ldD, 2 * L, D);
+    dgrad(10, a.dy2, a.ldD, m.W2, &a.dh1, a.ld2D, D, 2 * D);
+  }
+  // wgrad dW[N_out, N_in] = dY^T X / gs  (A = dY planes MN-major, B = X planes MN-major, K = batch); largest first
+  auto wgrad = [&](HPlanes dY, int lddy, HPlanes X, int ldx, const Seg& s, int n_out, int n_in) {
+    int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
+    st[11].push_back(StageSpec{dY, lddy, 1, X, ldx, 1, nullptr, G + s.off, s.ld, n_out, n_in, B, bn, wmode, jb::EPI_STORE, nullptr, inv_gs, 1});
+  };
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D); wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D);
+    wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D); wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D); }
+  for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
+    wgrad(a.dmp, e->ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D); wgrad(a.dy3, a.ldD, a.cp, e->LP, m.W3, D, L); }
+  // split-K factor per problem: fill the grid, at least two k-blocks per partial
+  size_t parts_bytes = 0;
+  std::vector<std::vector<int>> ks(jb::SK_NUM_GEMM);
+  for (int g = 0; g < jb::SK_NUM_GEMM; ++g) {
+    int tiles = 0;
+    for (const StageSpec& s : st[g]) tiles += ((s.M + jb::HG_BM - 1) / jb::HG_BM) * ((s.N + s.bn - 1) / s.bn);
+    for (const StageSpec& s : st[g]) {
+      int k = 1;
+      if (s.out != nullptr) {
+        const int kb = (s.K + jb::HG_BK - 1) / jb::HG_BK;
+        k = e->grid / (tiles > 0 ? tiles : 1);
+        if (k > kb / 2) k = kb / 2;
+        if (k > e->max_ksplit) k = e->max_ksplit;
+        if (k < 1) k = 1;
+        parts_bytes = ((parts_bytes + 255) & ~size_t(255)) + static_cast<size_t>(k) * s.M * s.ldc * 4;
+      }
+      ks[g].push_back(k);
+    }
+  }
+  if (e->parts_arena) { cudaFree(e->parts_arena); e->parts_arena = nullptr; }
+  CU(cudaMalloc(&e->parts_arena, parts_bytes + 256));
+  CU(cudaMemset(e->parts_arena, 0, parts_bytes + 256));
+  Carver pc(e->parts_arena);
+  e->h_probs.clear();
+  jb::StepCtx& cx = e->h_ctx;
+  cx = jb::StepCtx{};
+  for (int g = 0; g < jb::SK_NUM_GEMM; ++g) {
+    const int first = static_cast<int>(e->h_probs.size());
+    if (st[g].size() > static_cast<size_t>(jb::HG_MAX_PROBS)) return fail("too many problems in a GEMM phase");
+    for (size_t q = 0; q < st[g].size(); ++q) {
+      const StageSpec& s = st[g][q];
+      const int k = ks[g][q];
+      float* C = s.C;
+      long long pstride = 0;
+      if (s.out != nullptr) {
+        pstride = static_cast<long long>(s.M) * s.ldc;
+        C = pc.take<float>(static_cast<size_t>(k) * pstride);
+        *s.out = jb::Parts{C, pstride, k};
+      }
+      jb::HgProblem hp;
+      int rc = jb::hg_problem_fill(&hp, s.A, s.lda, s.a_mn, s.Bm, s.ldb, s.b_mn, C, s.ldc, s.M, s.N, s.K, s.bn, s.mode, s.epi, s.bias, k,
+                                   pstride, 0, s.out_scale, jb::LRELU);
+      if (rc) return fail("hgemm problem fill failed (%d) for M%d N%d K%d lda%d ldb%d bn%d mode%d", rc, s.M, s.N, s.K, s.lda, s.ldb, s.bn, s.mode);
+      if (hp.ksplit != k && s.out != nullptr) s.out->n = hp.ksplit;
+      if (s.acc_dynamic) hp.acc_flag = &e->ctl->accum;
+      e->h_probs.push_back(hp);
+    }
+    cx.gph[g] = jb::hg_phase_finalize(e->h_probs.data(), first, static_cast<int>(st[g].size()));
+  }
+  if (e->d_probs) { cudaFree(e->d_probs); e->d_probs = nullptr; }
+  CU(cudaMalloc(&e->d_probs, e->h_probs.size() * sizeof(jb::HgProblem)));
+  CU(cudaMemcpy(e->d_probs, e->h_probs.data(), e->h_probs.size() * sizeof(jb::HgProblem), cudaMemcpyHostToDevice));
+  // ---- the rest of the step context
+  cx.B = B; cx.L = L; cx.LP = e->LP; cx.ldmv = e->ldmv;
+  for (int i = 0; i < 2; ++i) {
+    ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
+    jb::ModCtx& M = cx.m[i];
+    M.data = e->data[i]; M.ld_data = e->data_ld[i]; M.stage[0] = a.x_stage[0]; M.stage[1] = a.x_stage[1];
+    M.idx = e->plan_idx[i]; M.x = a.x; M.xh = a.xp.hi; M.xl = a.xp.lo;
+    M.mulv = a.mulv; M.eps = a.eps; M.z = a.z; M.c = a.c; M.S = a.S; M.g = a.g; M.den = a.den; M.rs = a.rs;
+    M.inj_eps = a.inj_eps; M.ch = a.cp.hi; M.cl = a.cp.lo; M.dc = a.dc; M.dmulv = a.dmulv; M.dmh = a.dmp.hi; M.dml = a.dmp.lo;
+    M.xhat = a.xhat; M.dxh = a.dxhat.hi; M.dxl = a.dxhat.lo; M.db5 = G + m.b5.off; M.rec_part = a.rec_part;
+    M.dbias_heads = G + m.bmv.off; M.D = e->D[i]; M.ldD = a.ldD;
+    const int D = e->D[i];
+    const struct { jb::Parts Y; HPlanes H; const Seg *g, *be, *b; jb::Parts dH; HPlanes dY; int N, ld; } bl[4] = {
+        {a.y1, a.h1, &m.g1, &m.be1, &m.b1, a.dh1, a.dy1, 2 * D, a.ld2D},
+        {a.y2, a.h2, &m.g2, &m.be2, &m.b2, a.dh2, a.dy2, D, a.ldD},
+        {a.y3, a.g1, &m.g3, &m.be3, &m.b3, a.dg1, a.dy3, D, a.ldD},
+        {a.y4, a.g2, &m.g4, &m.be4, &m.b4, a.dg2, a.dy4, 2 * D, a.ld2D}};
+    for (int k = 0; k < 4; ++k) {
+      jb::BnLayer& l = cx.bn[k][i];
+      const int bnidx = k < 2 ? (2 * i + k) : (4 + 2 * i + (k - 2));
+      l.Y = bl[k].Y; l.Hh = bl[k].H.hi; l.Hl = bl[k].H.lo;
+      l.gamma = T + bl[k].g->off; l.beta = T + bl[k].be->off;
+      l.mean = a.bn_mean[k]; l.invstd = a.bn_inv[k];
+      l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
+      l.mask = a.inj_mask[k];
+      l.dH = bl[k].dH; l.dYh = bl[k].dY.hi; l.dYl = bl[k].dY.lo;
+      l.dgamma = G + bl[k].g->off; l.dbeta = G + bl[k].be->off; l.dbias = G + bl[k].b->off;
+      l.N = bl[k].N; l.ld = bl[k].ld; l.layer_id = static_cast<unsigned>(bnidx);
+    }
+  }
+  cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
+  cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
+  cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;
+  cx.lat_r = e->lat_r; cx.rowpart = e->rowpart;
+  cx.theta = e->theta; cx.grad = e->grad; cx.adam_m = e->adam_m; cx.adam_v = e->adam_v;
+  cx.theta_hi = e->theta_hi; cx.theta_lo = e->theta_lo; cx.n_flat = e->n_flat;
+  cx.sigma = T + e->sigma.off; cx.dsigma = G + e->sigma.off; cx.norm_part = e->norm_part;
+  cx.plan_kl = e->plan_kl; cx.out_loss = e->out_loss; cx.ctl = e->ctl;
+  jb::StepConsts& sc = cx.sc;
   sc.lr = e->cfg.lr; sc.beta1 = e->cfg.beta1; sc.beta2 = e->cfg.beta2; sc.adam_eps = e->cfg.adam_eps;
   sc.max_norm = e->cfg.max_grad_norm;
   for (int k = 0; k < 4; ++k) sc.w[k] = e->cfg.loss_w[k];
   sc.pf_ratio = e->cfg.pf_ratio; sc.dropout = e->cfg.dropout;
   sc.grad_scale = 1.0f / static_cast<float>(e->cfg.world_size > 0 ? e->cfg.world_size : 1);
-  sc.B = B; sc.L = e->L; sc.D[0] = e->D[0]; sc.D[1] = e->D[1];
-  return sc;
-}
-
-jb::Latent make_latent(jb_engine* e) {
-  jb::Latent a{};
-  for (int i = 0; i < 2; ++i) {
-    ModActs& m = e->act[i];
-    a.mulv[i] = m.mulv; a.eps[i] = m.eps; a.inj_eps[i] = m.inj_eps; a.z[i] = m.z; a.c[i] = m.c; a.S[i] = m.S;
-    a.g[i] = m.g; a.den[i] = m.den; a.rs[i] = m.rs; a.dc_dec[i] = m.dc; a.dmulv[i] = m.dmulv;
-    a.ch[i] = m.cp.hi; a.cl[i] = m.cp.lo; a.dmh[i] = m.dmp.hi; a.dml[i] = m.dmp.lo;
-  }
-  a.ldmv = e->act[0].ldmv; a.r = e->lat_r; a.rowpart = e->rowpart;
-  a.corr = e->corr; a.corr_t = e->corr_t; a.fblk = e->fblk; a.fblk_t = e->fblk_t;
-  a.sigma = e->theta + e->sigma.off; a.LP = e->LP; a.f_present = e->f_dense != nullptr;
-  return a;
-}
-
-// part < 0: the whole forward + backward. Data-parallel halves: part 0 = everything up to the heads + decoder wgrads,
-// part 1 = encoder backward and encoder wgrads.
-void record_backward(jb_engine* e, Rec& r, int B, bool gather = true, int part = -1) {
-  const int L = e->L;
-  r.mute = part == 1;
-  const float p = e->cfg.dropout;
-  const int accum = e->accumulate;
-  const jb::StepConsts sc = make_consts(e, B);
-  float* T = e->theta;
-  float* G = e->grad;
-  // inputs (the first kernel also derives the step's control scalars)
-  jb::GatherArgs ga{};
-  for (int i = 0; i < 2; ++i) {
-    ga.data[i] = e->data[i]; ga.ld_data[i] = e->data_ld[i]; ga.x[i] = e->act[i].x; ga.ldx[i] = e->act[i].ldD;
-    ga.xh[i] = e->act[i].xp.hi; ga.xl[i] = e->act[i].xp.lo;
-    ga.D[i] = e->D[i]; ga.idx[i] = e->plan_idx[i];
-    ga.stage[0][i] = e->act[i].x_stage[0]; ga.stage[1][i] = e->act[i].x_stage[1];
-  }
-  if (gather) launchk(r, jb::k_gather, dim3(B, 2), dim3(128), ga, e->ctl, e->plan_kl, sc, B);
-  else launchk(r, jb::k_split_x, dim3(B, 2), dim3(128), ga, e->ctl, e->plan_kl, sc, B);   // host batch: x was copied in
-  // P / F blocks: needed first by k_combine, so on the side stream they overlap the encoder
-  jb::CorrArgs ca{};
-  ca.p_diag = e->p_diag; ca.p_dense = e->p_dense; ca.f_dense = e->f_dense; ca.n1 = e->pn1;
-  ca.idx[0] = e->plan_idx[0]; ca.idx[1] = e->plan_idx[1]; ca.rs_p = e->rs_p; ca.rs_f = e->rs_f;
-  ca.corr = e->corr; ca.corr_t = e->corr_t; ca.fblk = e->fblk; ca.fblk_t = e->fblk_t; ca.pf_ratio = e->cfg.pf_ratio;
-  {
-    cudaStream_t main_s = r.s;
-    const bool fork = r.side != nullptr && r.err == cudaSuccess && !r.mute;
-    if (fork) {
-      if ((r.err = cudaEventRecord(r.ev_fork, main_s)) == cudaSuccess) r.err = cudaStreamWaitEvent(r.side, r.ev_fork, 0);
-      r.s = r.side;
-      r.no_pdl_next = true;
-    }
-    launchk(r, jb::k_corr_rowsum, dim3(B), dim3(128), ca, e->ctl, B);
-    launchk(r, jb::k_corr_build, dim3((B + 31) / 32, (B + 31) / 32), dim3(32, 8), ca, e->ctl, B);
-    if (fork) {
-      if (r.err == cudaSuccess) r.err = cudaEventRecord(r.ev_join, r.side);
-      r.s = main_s;
-    }
-  }
-
-  auto bnf = [&](int k, int which /*0 enc1,1 enc2,2 dec1,3 dec2*/) {
-    (void)k;
-    jb::BnFwdPair pr{};
-    for (int i = 0; i < 2; ++i) {
-      ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-      jb::BnFwd& l = pr.l[i];
-      const int bnidx = which < 2 ? (2 * i + which) : (4 + 2 * i + (which - 2));
-      switch (which) {
-        case 0: l.Y = a.y1; l.ldy = a.ld2D; l.Hh = a.h1.hi; l.Hl = a.h1.lo; l.ldh = a.ld2D; l.gamma = T + m.g1.off; l.beta = T + m.be1.off; l.N = 2 * D; break;
-        case 1: l.Y = a.y2; l.ldy = a.ldD; l.Hh = a.h2.hi; l.Hl = a.h2.lo; l.ldh = a.ldD; l.gamma = T + m.g2.off; l.beta = T + m.be2.off; l.N = D; break;
-        case 2: l.Y = a.y3; l.ldy = a.ldD; l.Hh = a.g1.hi; l.Hl = a.g1.lo; l.ldh = a.ldD; l.gamma = T + m.g3.off; l.beta = T + m.be3.off; l.N = D; break;
-        default: l.Y = a.y4; l.ldy = a.ld2D; l.Hh = a.g2.hi; l.Hl = a.g2.lo; l.ldh = a.ld2D; l.gamma = T + m.g4.off; l.beta = T + m.be4.off; l.N = 2 * D; break;
-      }
-      l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
-      l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
-      l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
-    }
-    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN")) {
-      const int cw = e->slab_cw;
-      const dim3 grid((pr.l[0].N + cw - 1) / cw + (pr.l[1].N + cw - 1) / cw);
-      if (cw == 8) launchk(r, jb::k_bn_fwd_slab<8, 512>, grid, dim3(512), pr, e->ctl, B, p);
-      else launchk(r, jb::k_bn_fwd_slab<16, 1024>, grid, dim3(1024), pr, e->ctl, B, p);
-    }
-    else launchk(r, jb::k_bn_fwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p);
-  };
-  // ---- forward
-  r.gemm(e->st_f[0]); bnf(0, 0);
-  r.gemm(e->st_f[1]); bnf(1, 1);
-  r.gemm(e->st_f[2]);
-  jb::Latent lat = make_latent(e);
-  launchk(r, jb::k_reparam, dim3((2 * B * L + 255) / 256), dim3(256), lat, e->ctl, B, L);
-  const int wblocks = (2 * B * 32 + 255) / 256;
-  if (r.side && r.err == cudaSuccess && !r.mute) {   // join: the P / F blocks are complete
-    r.err = cudaStreamWaitEvent(r.s, r.ev_join, 0);
-    r.no_pdl_next = true;
-  }
-  const int fuse_loss = lat.f_present ? 0 : 1;   // without F the loss partials need nothing of another row
-  launchk(r, jb::k_combine, dim3(wblocks), dim3(256), lat, B, L, fuse_loss);
-  if (!fuse_loss) launchk(r, jb::k_latent_loss, dim3(wblocks), dim3(256), lat, B, L);
-  r.gemm(e->st_f[3]); bnf(2, 2);
-  r.gemm(e->st_f[4]); bnf(3, 3);
-  r.gemm(e->st_f[5]);
-  // ---- losses + backward
-  jb::RecPair rp{};
-  for (int i = 0; i < 2; ++i) {
-    ModActs& a = e->act[i]; ModSegs& m = e->ms[i];
-    jb::RecArgs& q = rp.m[i];
-    q.xhat = a.xhat; q.ldxh = a.ldD; q.x = a.x; q.ldx = a.ldD; q.dxh = a.dxhat.hi; q.dxl = a.dxhat.lo; q.lddx = a.ldD;
-    const bool slab = B <= 512;
-    const int cw = slab ? e->slab_cw : 32;
-    q.dbias = G + m.b5.off; q.part = a.rec_part; q.D = e->D[i]; q.blocks = (e->D[i] + cw - 1) / cw;
-  }
-  if (B <= 512 && e->slab_cw == 8) launchk(r, jb::k_rec_slab<8, 512>, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(512), rp, B, sc.w[1], accum);
-  else if (B <= 512) launchk(r, jb::k_rec_slab<16, 1024>, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(1024), rp, B, sc.w[1], accum);
-  else launchk(r, jb::k_rec, dim3(rp.m[0].blocks + rp.m[1].blocks), dim3(256), rp, B, sc.w[1], accum);
-  auto bnb = [&](int which) {
-    jb::BnBwdPair pr{};
-    for (int i = 0; i < 2; ++i) {
-      ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-      jb::BnBwd& l = pr.l[i];
-      const int bnidx = which < 2 ? (2 * i + which) : (4 + 2 * i + (which - 2));
-      switch (which) {
-        case 0: l.dH = a.dh1; l.lddh = a.ld2D; l.Y = a.y1; l.ldy = a.ld2D; l.dYh = a.dy1.hi; l.dYl = a.dy1.lo; l.lddy = a.ld2D; l.N = 2 * D;
-                l.gamma = T + m.g1.off; l.beta = T + m.be1.off; l.dgamma = G + m.g1.off; l.dbeta = G + m.be1.off; l.dbias = G + m.b1.off; break;
-        case 1: l.dH = a.dh2; l.lddh = a.ldD; l.Y = a.y2; l.ldy = a.ldD; l.dYh = a.dy2.hi; l.dYl = a.dy2.lo; l.lddy = a.ldD; l.N = D;
-                l.gamma = T + m.g2.off; l.beta = T + m.be2.off; l.dgamma = G + m.g2.off; l.dbeta = G + m.be2.off; l.dbias = G + m.b2.off; break;
-        case 2: l.dH = a.dg1; l.lddh = a.ldD; l.Y = a.y3; l.ldy = a.ldD; l.dYh = a.dy3.hi; l.dYl = a.dy3.lo; l.lddy = a.ldD; l.N = D;
-                l.gamma = T + m.g3.off; l.beta = T + m.be3.off; l.dgamma = G + m.g3.off; l.dbeta = G + m.be3.off; l.dbias = G + m.b3.off; break;
-        default: l.dH = a.dg2; l.lddh = a.ld2D; l.Y = a.y4; l.ldy = a.ld2D; l.dYh = a.dy4.hi; l.dYl = a.dy4.lo; l.lddy = a.ld2D; l.N = 2 * D;
-                l.gamma = T + m.g4.off; l.beta = T + m.be4.off; l.dgamma = G + m.g4.off; l.dbeta = G + m.be4.off; l.dbias = G + m.b4.off; break;
-      }
-      l.mean = a.bn_mean[which]; l.invstd = a.bn_inv[which];
-      l.mask = a.inj_mask[which]; l.ldm = l.N; l.layer_id = static_cast<unsigned>(bnidx); l.blocks = (l.N + 31) / 32;
-    }
-    if (B <= 512 && !getenv("JB_DEBUG_GENERIC_BN")) {
-      const int cw = e->slab_cw;
-      const dim3 grid((pr.l[0].N + cw - 1) / cw + (pr.l[1].N + cw - 1) / cw);
-      if (cw == 8) launchk(r, jb::k_bn_bwd_slab<8, 512>, grid, dim3(512), pr, e->ctl, B, p, accum);
-      else launchk(r, jb::k_bn_bwd_slab<16, 1024>, grid, dim3(1024), pr, e->ctl, B, p, accum);
-    }
-    else launchk(r, jb::k_bn_bwd, dim3(pr.l[0].blocks + pr.l[1].blocks), dim3(256), pr, e->ctl, B, p, accum);
-  };
-  r.gemm(e->st_b[0]); bnb(3);
-  r.gemm(e->st_b[1]); bnb(2);
-  r.gemm(e->st_b[2]);
-  const float k_cos = sc.w[2] * 32.f * 2.f / (static_cast<float>(B) * static_cast<float>(L));
-  const float k_f = sc.w[3] * 2.f / (static_cast<float>(B) * static_cast<float>(L));
-  launchk(r, jb::k_latent_bwd_c, dim3(wblocks), dim3(256), lat, B, L, k_cos, k_f);
-  launchk(r, jb::k_latent_bwd_z, dim3(wblocks), dim3(256), lat, e->ctl, B, L, k_cos);
-  jb::FinalArgs fa{};
-  fa.rowpart = e->rowpart;
-  for (int i = 0; i < 2; ++i) {
-    fa.rs[i] = e->act[i].rs; fa.rec_part[i] = e->act[i].rec_part; fa.rec_blocks[i] = rp.m[i].blocks;
-    fa.dmulv[i] = e->act[i].dmulv; fa.dbias_heads[i] = G + e->ms[i].bmv.off; fa.D[i] = e->D[i];
-  }
-  fa.mulv1 = e->act[1].mulv; fa.ldmv = e->act[0].ldmv; fa.dsigma = G + e->sigma.off; fa.out_loss = e->out_loss;
-  fa.grad_tail = G + e->n_flat;
-  launchk(r, jb::k_latent_final, dim3(1 + (4 * L + jb::SLAB_CW - 1) / jb::SLAB_CW), dim3(jb::SLAB_THREADS), fa, e->ctl, B, L, sc, accum);
-  const bool split_w = e->st_b[6].count > 0;
-  if (split_w) r.gemm(e->st_b[5]);   // heads + decoder wgrads: that gradient bucket is now complete
-  r.mute = part == 0;
-  r.gemm(e->st_b[3]); bnb(1);
-  r.gemm(e->st_b[4]); bnb(0);
-  r.gemm(split_w ? e->st_b[6] : e->st_b[5]);
-  r.mute = false;
-}
-
-void record_update(jb_engine* e, Rec& r, int B) {
-  const jb::StepConsts sc = make_consts(e, B);
-  const long long n4 = e->n_flat / 4;
-  launchk(r, jb::k_gradnorm, dim3(jb::NORM_BLOCKS), dim3(256), e->grad, n4, e->norm_part);
-  launchk(r, jb::k_adam, e->adam_blocks, 256, e->theta, e->theta_hi, e->theta_lo, e->grad, e->adam_m, e->adam_v, n4, e->norm_part, jb::NORM_BLOCKS, e->ctl, sc, e->out_loss);
-}
-
-int capture(jb_engine* e, int B, int what /*0 full, 1 bwd, 2 upd, 3 host, 4 host bwd, 5 / 6 bwd halves*/, cudaGraphExec_t* out,
-            int* nlaunch) {
-  cudaGraph_t g = nullptr;
-  CU(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
-  Rec r{e, e->cap_stream};
-  if (e->use_side) { r.side = e->side_stream; r.ev_fork = e->ev_fork; r.ev_join = e->ev_join; }
-  if (what == 0 || what == 1) record_backward(e, r, B);
-  if (what == 5 || what == 6) record_backward(e, r, B, true, what - 5);
-  if (what == 3 || what == 4) record_backward(e, r, B, false);
-  if (what == 0 || what == 2 || what == 3) record_update(e, r, B);
-  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
-  if (r.err != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail("kernel launch failed during capture: %s", cudaGetErrorString(r.err)); }
-  if (ce != cudaSuccess) return fail("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
-  if (*out) { cudaGraphExecDestroy(*out); *out = nullptr; }
-  ce = cudaGraphInstantiate(out, g, 0);
-  cudaGraphDestroy(g);
-  if (ce != cudaSuccess) return fail("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
-  *nlaunch = r.n;
+  sc.B = B; sc.L = L; sc.D[0] = e->D[0]; sc.D[1] = e->D[1];
+  cx.gs = e->gs; cx.inv_gs = inv_gs;
+  cx.probs = e->d_probs;
+  CU(cudaMemcpy(e->d_ctx, &cx, sizeof cx, cudaMemcpyHostToDevice));
+  e->step_B = B;
   return 0;
 }
 
-int ensure_graphs(jb_engine* e, int B) {
-  const bool acc = e->accumulate != 0;
-  if (e->graph_B == B && e->graph_accum == acc && e->g_upd) return 0;
-  if (build_train_tables(e, B, e->accumulate)) return 1;
-  if (e->data[0] && e->data[1]) {   // the gathering graphs need resident datasets; the host-batch graph does not
-    if (capture(e, B, 0, &e->g_full, &e->launches_per_step)) return 1;
-    if (capture(e, B, 1, &e->g_bwd, &e->launches_bwd)) return 1;
-    if (e->st_b[6].count > 0)
-      for (int h = 0; h < 2; ++h)
-        if (capture(e, B, 5 + h, &e->g_bwd_part[h], &e->launches_bwd_part[h])) return 1;
+int ensure_step(jb_engine* e, int B) {
+  if (e->step_B == B) return 0;
+  CU(cudaDeviceSynchronize());
+  return build_step(e, B);
+}
+
+// One launch of the step kernel: phases [lo, hi) of nsteps consecutive steps, then the control-block update.
+int launch_step(jb_engine* e, int lo, int hi, int nsteps, int use_stage, cudaStream_t s, unsigned long long* ts = nullptr) {
+  if (e->accumulate != e->accumulate_dev) {
+    jb::k_set_accum<<<1, 1, 0, s>>>(e->ctl, e->accumulate);
+    e->accumulate_dev = e->accumulate;
+    ++e->launches;
   }
-  if (capture(e, B, 2, &e->g_upd, &e->launches_upd)) return 1;
-  if (capture(e, B, 3, &e->g_host, &e->launches_host)) return 1;
-  if (capture(e, B, 4, &e->g_host_bwd, &e->launches_host_bwd)) return 1;
-  e->graph_B = B; e->graph_accum = acc;
+  CU(cudaMemsetAsync(e->bar, 0, sizeof(unsigned int), s));
+  const jb::StepCtx* cxp = e->d_ctx;
+  int row_bias = lo > jb::PH_GATHER ? -1 : 0;
+  unsigned int* bar = e->bar;
+  void* args[] = {&cxp, &lo, &hi, &nsteps, &bar, &use_stage, &row_bias, &ts};
+  CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
+  const int fwd = lo == jb::PH_GATHER ? nsteps : 0, upd = hi == jb::PH_COUNT ? nsteps : 0;
+  jb::k_ctl_advance<<<1, 1, 0, s>>>(e->ctl, fwd, upd, fwd > 0 ? 1 : 0);
+  CU(cudaGetLastError());
+  e->launches += 2;
   return 0;
 }
 
@@ -810,13 +606,14 @@ int eval_common(jb_engine* e, int from, int to, const float* X, long long n, lon
   return 0;
 }
 
+
 }  // namespace
 
 // =============================================================================================== C ABI
 extern "C" {
 
 const char* jb_last_error(void) { return g_err.c_str(); }
-int jb_version(void) { return 100; }
+int jb_version(void) { return 200; }
 
 int jb_create(const jb_config* cfg, jb_engine** out) {
   if (!cfg || !out) return fail("null argument");
@@ -828,10 +625,12 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail("jamie_b200 needs an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
+  if (!prop.cooperativeLaunch) return fail("the device does not support cooperative launches");
   jb_engine* e = new jb_engine();
   e->cfg = *cfg;
-  if (const char* pv = getenv("JB_PRECISION")) e->precision_fast = strcmp(pv, "tf32") == 0;
-  e->D[0] = cfg->dims[0]; e->D[1] = cfg->dims[1]; e->L = cfg->latent; e->LP = r4(cfg->latent); e->Bmax = cfg->max_batch;
+  if (const char* pv = getenv("JB_PRECISION")) e->precision_fast = strcmp(pv, "f16") == 0 || strcmp(pv, "tf32") == 0;
+  e->D[0] = cfg->dims[0]; e->D[1] = cfg->dims[1]; e->L = cfg->latent; e->LP = r8(cfg->latent); e->ldmv = r8(2 * cfg->latent);
+  e->Bmax = cfg->max_batch;
   build_layout(e);
   const size_t fb = static_cast<size_t>(e->n_flat + 32) * 4;
   auto alloc0 = [&](float** p, size_t bytes) -> int {
@@ -839,14 +638,12 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
     CU(cudaMemset(*p, 0, bytes));
     return 0;
   };
-  // theta, the Adam moments and the operand planes live in ONE slab (fb is a multiple of 128 B). A persisting-L2
-  // access-policy window over it for k_adam was measured on B200: 268.8 vs 266.5 us/step without (the set-aside L2 is
-  // missed by the activations), so none is set.
-  e->slab_bytes = 5 * fb;
+  // theta, the Adam moments (fp32) and the fp16 operand planes live in ONE slab (fb is a multiple of 128 B)
+  e->slab_bytes = 4 * fb;
   if (alloc0(&e->state_slab, e->slab_bytes) || alloc0(&e->grad, fb) || alloc0(&e->theta_eval, fb) ||
       alloc0(&e->bn_run, e->n_bn * 4)) { jb_destroy(e); return 1; }
   e->theta = e->state_slab; e->adam_m = e->theta + fb / 4; e->adam_v = e->adam_m + fb / 4;
-  e->theta_hi = e->adam_v + fb / 4; e->theta_lo = e->theta_hi + fb / 4;
+  e->theta_hi = reinterpret_cast<__half*>(e->adam_v + fb / 4); e->theta_lo = e->theta_hi + fb / 4;
   {  // BatchNorm defaults: running_mean 0, running_var 1; gamma = 1 is set through jb_set_params
     std::vector<float> h(e->n_bn, 0.f);
     for (int k = 0; k < 8; ++k)
@@ -864,20 +661,23 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   jb::Ctl c0{};
   c0.seed = cfg->seed;
   CU(cudaMemcpy(e->ctl, &c0, sizeof c0, cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&e->norm_part, jb::NORM_BLOCKS * sizeof(double)));
-  CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  if (const char* pv = getenv("JB_SIDE")) e->use_side = atoi(pv) != 0;
+  CU(cudaMalloc(&e->norm_part, jb::SK_MAX_CTAS * sizeof(double)));
+  CU(cudaMalloc(&e->bar, 128));
+  CU(cudaMemset(e->bar, 0, 128));
+  CU(cudaMalloc(&e->d_ctx, sizeof(jb::StepCtx)));
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
-  if (const char* pv = getenv("JB_DGRAD_SPLIT")) e->dgrad_split = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_ADAM_BLOCKS")) { if (atoi(pv) > 0) e->adam_blocks = atoi(pv); }
-  if (const char* pv = getenv("JB_SLAB_CW")) e->slab_cw = atoi(pv) == 8 ? 8 : 16;
+  if (const char* pv = getenv("JB_WGRAD_MODE")) e->wgrad_mode = strcmp(pv, "single") == 0 ? jb::HG_SINGLE : jb::HG_MEDIUM;
+  if (const char* pv = getenv("JB_MAX_KSPLIT")) { if (atoi(pv) >= 1) e->max_ksplit = atoi(pv); }
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
-  if (const char* pv = getenv("JB_PDL")) e->use_pdl = atoi(pv) != 0;
-  if (const char* pv = getenv("JB_SPLITK")) e->use_splitk = atoi(pv) != 0;
+  CU(cudaFuncSetAttribute(jb::k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::HG_SMEM_BYTES));
   e->num_sms = prop.multiProcessorCount;
+  {  // the step kernel is cooperative: one CTA per SM must be co-resident
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb::k_step, jb::SK_THREADS, jb::HG_SMEM_BYTES));
+    if (per_sm < 1) { jb_destroy(e); return fail("the step kernel does not fit on an SM (shared memory / registers)"); }
+    e->grid = e->num_sms < jb::SK_MAX_CTAS ? e->num_sms : jb::SK_MAX_CTAS;
+    if (const char* pv = getenv("JB_STEP_CTAS")) { if (atoi(pv) >= 1 && atoi(pv) <= e->grid) e->grid = atoi(pv); }
+  }
   // rows per pass of the folded chain: one 128-row M tile per SM, so every GEMM of the chain is a whole number of waves
   // (measured on B200, 1M rows 512 -> 512: 8192 rows 59.1, 9472 rows 66.7, 18944 rows 69.0 M rows/s)
   e->eval_chunk = 128 * e->num_sms;
@@ -901,12 +701,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
 void jb_destroy(jb_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
-  if (e->g_full) cudaGraphExecDestroy(e->g_full);
-  if (e->g_bwd) cudaGraphExecDestroy(e->g_bwd);
-  if (e->g_upd) cudaGraphExecDestroy(e->g_upd);
-  if (e->g_host) cudaGraphExecDestroy(e->g_host);
-  if (e->g_host_bwd) cudaGraphExecDestroy(e->g_host_bwd);
-  for (auto& g : e->g_bwd_part) if (g) cudaGraphExecDestroy(g);
   if (e->h_pin) cudaFreeHost(e->h_pin);
   if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
   for (int k = 0; k < 2; ++k) {
@@ -916,12 +710,9 @@ void jb_destroy(jb_engine* e) {
   }
   void* ptrs[] = {e->state_slab, e->grad, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
-                  e->arena, e->d_probs, e->ev_a, e->ev_b, e->ev_in, e->ev_out, e->d_ev_probs};
+                  e->arena, e->parts_arena, e->d_probs, e->d_ctx, e->bar, e->d_ts, e->ev_a, e->ev_b, e->ev_in, e->ev_out,
+                  e->d_ev_probs};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
-  if (e->side_stream) cudaStreamDestroy(e->side_stream);
-  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (int k = 0; k < 2; ++k) if (e->ev_stream[k]) cudaStreamDestroy(e->ev_stream[k]);
   delete e;
 }
@@ -935,7 +726,7 @@ int jb_set_params(jb_engine* e, const float* packed, long long n) {
   CU(cudaDeviceSynchronize());
   e->eval_dirty = true;
   if (copy_packed(e, e->theta, const_cast<float*>(packed), true)) return 1;
-  jb::k_split_flat<<<296, 256>>>(e->theta, e->theta_hi, e->theta_lo, e->n_flat);   // operand planes of the training GEMMs
+  jb::k_hsplit_flat<<<296, 256>>>(e->theta, e->theta_hi, e->theta_lo, e->n_flat);   // operand planes of the training GEMMs
   ++e->launches;
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
@@ -1005,18 +796,10 @@ int jb_set_dataset(jb_engine* e, int mod, const float* X, long long n, long long
                        static_cast<size_t>(e->D[mod]) * 4, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
   e->data_n[mod] = n; e->data_ld[mod] = ldd;
-  if (e->g_upd) { cudaGraphExecDestroy(e->g_upd); e->g_upd = nullptr; }  // pointers are baked into the graphs
-  e->graph_B = 0;
+  e->step_B = 0;   // pointers are baked into the step context
   return 0;
 }
 
-static int reset_graphs(jb_engine* e) {
-  if (e->g_full) { cudaGraphExecDestroy(e->g_full); e->g_full = nullptr; }
-  if (e->g_bwd) { cudaGraphExecDestroy(e->g_bwd); e->g_bwd = nullptr; }
-  if (e->g_upd) { cudaGraphExecDestroy(e->g_upd); e->g_upd = nullptr; }
-  e->graph_B = 0;
-  return 0;
-}
 int jb_set_prior_diag(jb_engine* e, const float* m, long long n) {
   if (!e) return fail("null argument");
   CU(cudaDeviceSynchronize());
@@ -1027,7 +810,8 @@ int jb_set_prior_diag(jb_engine* e, const float* m, long long n) {
     CU(cudaMemcpy(e->p_diag, m, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice));
   }
   e->p_diag_n = m ? n : 0;
-  return reset_graphs(e);
+  e->step_B = 0;
+  return 0;
 }
 int jb_set_prior_dense(jb_engine* e, const float* P, long long n0, long long n1) {
   if (!e || !P) return fail("null argument");
@@ -1038,7 +822,8 @@ int jb_set_prior_dense(jb_engine* e, const float* P, long long n0, long long n1)
   CU(cudaMalloc(&e->p_dense, static_cast<size_t>(n0) * n1 * 4));
   CU(cudaMemcpy(e->p_dense, P, static_cast<size_t>(n0) * n1 * 4, cudaMemcpyHostToDevice));
   e->pn0 = n0; e->pn1 = n1;
-  return reset_graphs(e);
+  e->step_B = 0;
+  return 0;
 }
 int jb_set_f_dense(jb_engine* e, const float* F, long long n0, long long n1) {
   if (!e) return fail("null argument");
@@ -1050,7 +835,8 @@ int jb_set_f_dense(jb_engine* e, const float* F, long long n0, long long n1) {
     CU(cudaMemcpy(e->f_dense, F, static_cast<size_t>(n0) * n1 * 4, cudaMemcpyHostToDevice));
     e->pn0 = n0; e->pn1 = n1;
   }
-  return reset_graphs(e);
+  e->step_B = 0;
+  return 0;
 }
 
 int jb_upload_plan(jb_engine* e, const long long* idx0, const long long* idx1, const double* kl_anneal, int nsteps, int batch,
@@ -1070,7 +856,7 @@ int jb_upload_plan(jb_engine* e, const long long* idx0, const long long* idx1, c
     CU(cudaMalloc(&e->plan_kl, static_cast<size_t>(cap) * 4));
     CU(cudaMalloc(&e->out_loss, static_cast<size_t>(cap) * 8 * 4));
     e->plan_cap = cap; e->plan_B = batch;
-    reset_graphs(e);  // plan pointers are baked into the graph
+    e->step_B = 0;  // plan pointers are baked into the step context
   }
   std::vector<int> h(static_cast<size_t>(nsteps) * batch);
   const long long* src[2] = {idx0, idx1};
@@ -1118,12 +904,11 @@ int jb_inject_randomness(jb_engine* e, const float* eps0, const float* eps1, con
 
 int jb_train_steps(jb_engine* e, int nsteps, void* stream) {
   if (!e) return fail("null argument");
+  if (nsteps <= 0) return 0;
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
-  if (ensure_graphs(e, e->plan_B)) return 1;
-  if (!e->g_full) return fail("jb_set_dataset must be called for both modalities before jb_train_steps");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (int k = 0; k < nsteps; ++k) CU(cudaGraphLaunch(e->g_full, s));
-  e->launches += static_cast<long long>(nsteps) * e->launches_per_step;
+  if (!e->data[0] || !e->data[1]) return fail("jb_set_dataset must be called for both modalities before jb_train_steps");
+  if (ensure_step(e, e->plan_B)) return 1;
+  if (launch_step(e, jb::PH_GATHER, jb::PH_COUNT, nsteps, 0, static_cast<cudaStream_t>(stream))) return 1;
   for (int k = 0; k < 8; ++k) e->nbt[k] += nsteps;
   e->eval_dirty = true;
   return 0;
@@ -1131,58 +916,34 @@ int jb_train_steps(jb_engine* e, int nsteps, void* stream) {
 int jb_step_backward(jb_engine* e, void* stream) {
   if (!e) return fail("null argument");
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
-  if (ensure_graphs(e, e->plan_B)) return 1;
-  if (!e->g_bwd) return fail("jb_set_dataset must be called for both modalities before jb_step_backward");
-  CU(cudaGraphLaunch(e->g_bwd, static_cast<cudaStream_t>(stream)));
-  e->launches += e->launches_bwd;
+  if (!e->data[0] || !e->data[1]) return fail("jb_set_dataset must be called for both modalities before jb_step_backward");
+  if (ensure_step(e, e->plan_B)) return 1;
+  if (launch_step(e, jb::PH_GATHER, jb::PH_NORM, 1, 0, static_cast<cudaStream_t>(stream))) return 1;
   for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
   e->eval_dirty = true;
   return 0;
 }
-int jb_step_backward_part(jb_engine* e, int part, void* stream) {
-  if (!e) return fail("null argument");
-  if (part < 0 || part > 1) return fail("part must be 0 or 1");
-  if (!e->plan_B) return fail("jb_upload_plan must be called first");
-  if (e->cfg.world_size <= 1) return fail("the two-part backward is the data-parallel form: it needs world_size > 1");
-  if (!e->dp_split) { e->dp_split = true; reset_graphs(e); }   // rebuild the tables with the wgrads in two launches
-  if (ensure_graphs(e, e->plan_B)) return 1;
-  if (!e->g_bwd_part[part]) return fail("jb_set_dataset must be called for both modalities before jb_step_backward_part");
-  CU(cudaGraphLaunch(e->g_bwd_part[part], static_cast<cudaStream_t>(stream)));
-  e->launches += e->launches_bwd_part[part];
-  if (part == 0) for (int k = 0; k < 8; ++k) e->nbt[k] += 1;
-  e->eval_dirty = true;
-  return 0;
-}
-int jb_grad_bucket(jb_engine* e, int part, float** dev_ptr, long long* n_floats) {
-  if (!e || !dev_ptr || !n_floats) return fail("null argument");
-  if (part < 0 || part > 1) return fail("part must be 0 or 1");
-  // part 0 finishes the heads + decoder gradients (and the loss scalars behind the buffer), part 1 the rest
-  *dev_ptr = part == 0 ? e->grad + e->n_enc : e->grad;
-  *n_floats = part == 0 ? e->n_flat + 8 - e->n_enc : e->n_enc;
-  return 0;
-}
 int jb_step_update(jb_engine* e, void* stream) {
   if (!e) return fail("null argument");
-  if (!e->g_upd) return fail("jb_step_backward must run before jb_step_update");
-  CU(cudaGraphLaunch(e->g_upd, static_cast<cudaStream_t>(stream)));
-  e->launches += e->launches_upd;
+  if (!e->step_B) return fail("jb_step_backward must run before jb_step_update");
+  if (launch_step(e, jb::PH_NORM, jb::PH_COUNT, 1, 0, static_cast<cudaStream_t>(stream))) return 1;
   e->eval_dirty = true;
   return 0;
 }
 int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats) {
   if (!e || !dev_ptr || !n_floats) return fail("null argument");
   *dev_ptr = e->grad;
-  *n_floats = e->n_flat + 8;  // flat gradients + the loss scalars appended by the loss kernel
+  *n_floats = e->n_flat + 8;  // flat gradients + the loss scalars appended by the loss phase
   return 0;
 }
 int jb_set_grad_accumulate(jb_engine* e, int accumulate) {
   if (!e) return fail("null argument");
-  e->accumulate = accumulate ? 1 : 0;
+  e->accumulate = accumulate ? 1 : 0;   // reaches the device control block with the next launch (no re-build, no sync)
   return 0;
 }
 
 // Enqueues one host-batch step in slot e->hb_slot: index / kl / row copies on the copy stream, then (after an event) the
-// control-block pokes, the step graph and the loss read-back on the caller's stream. Nothing here blocks the host.
+// control-block pokes, the step kernel and the loss read-back on the caller's stream. Nothing here blocks the host.
 static int hostbatch_submit(jb_engine* e, const float* x0, const float* x1, const long long* idx0, const long long* idx1,
                             int batch, double kl_anneal, bool with_update, void* stream) {
   if (!e || !x0 || !x1 || !idx0 || !idx1) return fail("null argument");
@@ -1193,7 +954,7 @@ static int hostbatch_submit(jb_engine* e, const float* x0, const float* x1, cons
     double k0[2] = {0, 0};
     if (jb_upload_plan(e, z.data(), z.data(), k0, 2, batch, stream)) return 1;
   }
-  if (ensure_graphs(e, batch)) return 1;
+  if (ensure_step(e, batch)) return 1;
   if (!e->h_pin) {
     CU(cudaMallocHost(reinterpret_cast<void**>(&e->h_pin), sizeof(HostPin) + 4 * static_cast<size_t>(e->Bmax) * sizeof(int)));
     e->h_pin->cursor_val[0] = 0; e->h_pin->cursor_val[1] = 1;
@@ -1241,13 +1002,11 @@ static int hostbatch_submit(jb_engine* e, const float* x0, const float* x1, cons
   if (e->plan_steps < 2) e->plan_steps = 2;
   e->eval_dirty = true;
   if (!with_update) {   // data-parallel form: forward + backward only
-    CU(cudaGraphLaunch(e->g_host_bwd, s));
-    e->launches += e->launches_host_bwd;
+    if (launch_step(e, jb::PH_GATHER, jb::PH_NORM, 1, 1, s)) return 1;
   } else {
-    CU(cudaGraphLaunch(e->g_host, s));
+    if (launch_step(e, jb::PH_GATHER, jb::PH_COUNT, 1, 1, s)) return 1;
     CU(cudaMemcpyAsync(hp->losses[slot], e->out_loss + static_cast<size_t>(slot) * 8, 8 * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(e->ev_loss[slot], s));
-    e->launches += e->launches_host;
     ++e->hb_outstanding;
   }
   CU(cudaEventRecord(e->ev_slot_free[slot], s));
@@ -1281,21 +1040,42 @@ int jb_step_backward_hostbatch(jb_engine* e, const float* x0, const float* x1, c
   return hostbatch_submit(e, x0, x1, idx0, idx1, batch, kl_anneal, false, stream);
 }
 
-int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* flops, void* stream) {
+int jb_num_phases(void) { return jb::PH_COUNT; }
+const char* jb_phase_name(int ph) {
+  static const char* names[jb::PH_COUNT] = {
+      "gather+corr", "gemm enc1", "bn1", "gemm enc2", "bn2", "gemm heads", "reparam", "combine", "latloss", "gemm dec1", "bn3",
+      "gemm dec2", "bn4", "gemm dec3", "rec", "dgrad W5", "bnb4", "dgrad W4", "bnb3", "dgrad W3", "latbc", "latbz",
+      "dgrad heads+final", "bnb2", "dgrad W2", "bnb1", "wgrad x12", "gradnorm", "adam"};
+  return ph >= 0 && ph < jb::PH_COUNT ? names[ph] : "";
+}
+
+// Times ONE phase alone: `iters` launches of k_step over [phase, phase + 1) on `stream` (CUDA events on that stream; each
+// launch includes the kernel's setup, so this is an upper bound of the phase's share of a step). flops: GEMM phases only.
+int jb_bench_stage(jb_engine* e, int phase, int iters, float* avg_us, double* flops, void* stream) {
   if (!e || !avg_us || !flops) return fail("null argument");
-  if (stage < 0 || stage > 11 || iters <= 0) return fail("bad stage / iters");
+  if (phase < 0 || phase >= jb::PH_COUNT || iters <= 0) return fail("bad phase / iters");
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
-  if (ensure_graphs(e, e->plan_B)) return 1;
+  if (ensure_step(e, e->plan_B)) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const GemmStage& st = stage < 6 ? e->st_f[stage] : e->st_b[stage - 6];
   double fl = 0;
-  for (int i = st.first; i < st.first + st.count; ++i)
-    fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
+  const int gi = jb::gemm_index(phase);
+  if (gi >= 0) {
+    const jb::HgPhase& ph = e->h_ctx.gph[gi];
+    for (int i = ph.first; i < ph.first + ph.count; ++i)
+      fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
+  }
+  const jb::StepCtx* cxp = e->d_ctx;
+  int lo = phase, hi = phase + 1, one = 1, zero = 0;
+  unsigned int* bar = e->bar;
+  unsigned long long* ts = nullptr;
+  void* args[] = {&cxp, &lo, &hi, &one, &bar, &zero, &zero, &ts};
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first));
+  for (int i = 0; i < 3; ++i)
+    CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
   CU(cudaEventRecord(a, s));
-  for (int i = 0; i < iters; ++i) CU(jb::gemm_launch(e->d_probs + st.first, st.count, st.ctas, s, false, st.ck, e->h_probs.data() + st.first));
+  for (int i = 0; i < iters; ++i)
+    CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
   CU(cudaEventRecord(b, s));
   CU(cudaEventSynchronize(b));
   float ms = 0;
@@ -1307,45 +1087,36 @@ int jb_bench_stage(jb_engine* e, int stage, int iters, float* avg_us, double* fl
   return 0;
 }
 
+// In-kernel phase timeline: runs `iters` (+1 warm-up) training steps in ONE launch with CTA 0 recording the global timer at
+// every phase boundary; out_us[p] = average microseconds of phase p INSIDE the persistent kernel (barrier included).
+// Consumes plan row 0 for every step (the cursor is rewound) and takes optimizer steps like jb_train_steps.
 int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_launches, void* stream) {
   if (!e || !out_us || !n_launches || iters <= 0) return fail("bad argument");
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
-  if (ensure_graphs(e, e->plan_B)) return 1;
   if (!e->data[0] || !e->data[1]) return fail("jb_set_dataset must be called for both modalities first");
+  if (iters + 1 > e->plan_steps) iters = e->plan_steps - 1;
+  if (iters < 1) return fail("the plan needs at least two rows for a profile");
+  if (ensure_step(e, e->plan_B)) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaEvent_t ev[65];
-  const char* names[64] = {};
-  for (auto& x : ev) CU(cudaEventCreate(&x));
-  std::vector<double> acc(64, 0.0);
-  int n = 0;
-  const bool pdl = e->use_pdl;
-  e->use_pdl = false;   // events between launches serialise the stream anyway
-  for (int it = 0; it < iters + 1; ++it) {
-    // rewind the plan cursor so that the profile can run any number of iterations
-    CU(cudaMemsetAsync(&e->ctl->cursor, 0, sizeof(long long), s));
-    jb::k_spin<<<1, 1, 0, s>>>(400000);   // 0.4 ms head start: the host enqueues the whole step behind it
-    Rec r{e, s};
-    r.ev = ev; r.names = names;
-    CU(cudaEventRecord(ev[0], s));
-    record_backward(e, r, e->plan_B);
-    record_update(e, r, e->plan_B);
-    CU(cudaStreamSynchronize(s));
-    if (r.err != cudaSuccess) return fail("launch failed while profiling: %s", cudaGetErrorString(r.err));
-    n = r.n < 64 ? r.n : 64;
-    if (it == 0) continue;   // warm-up
-    for (int k = 0; k < n; ++k) {
-      float ms = 0;
-      CU(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
-      acc[k] += ms * 1e3;
+  const size_t nts = 1 + static_cast<size_t>(iters + 1) * jb::PH_COUNT;
+  if (e->d_ts) { cudaFree(e->d_ts); e->d_ts = nullptr; }
+  CU(cudaMalloc(&e->d_ts, nts * 8));
+  CU(cudaMemsetAsync(e->d_ts, 0, nts * 8, s));
+  CU(cudaMemsetAsync(&e->ctl->cursor, 0, sizeof(long long), s));
+  if (launch_step(e, jb::PH_GATHER, jb::PH_COUNT, iters + 1, 0, s, e->d_ts)) return 1;
+  std::vector<unsigned long long> ts(nts);
+  CU(cudaMemcpyAsync(ts.data(), e->d_ts, nts * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  std::vector<double> acc(jb::PH_COUNT, 0.0);
+  for (int it = 1; it <= iters; ++it)
+    for (int p = 0; p < jb::PH_COUNT; ++p) {
+      const size_t k = 1 + static_cast<size_t>(it) * jb::PH_COUNT + p;
+      acc[p] += static_cast<double>(ts[k] - ts[k - 1]) * 1e-3;
     }
-  }
-  e->use_pdl = pdl;
-  for (auto& x : ev) cudaEventDestroy(x);
   for (int k = 0; k < 8; ++k) e->nbt[k] += iters + 1;
-  e->launches += static_cast<long long>(iters + 1) * (n + 1);
   e->eval_dirty = true;
-  *n_launches = n;
-  for (int k = 0; k < n && k < cap; ++k) out_us[k] = static_cast<float>(acc[k] / iters);
+  *n_launches = jb::PH_COUNT;
+  for (int p = 0; p < jb::PH_COUNT && p < cap; ++p) out_us[p] = static_cast<float>(acc[p] / iters);
   return 0;
 }
 
@@ -1483,51 +1254,67 @@ int jb_pca_inverse(jb_engine* e, const float* Z, long long n, int k, const float
 long long jb_debug_read(jb_engine* e, const char* name, float* out, long long cap) {
   if (!e || !name || !out) { fail("null argument"); return -1; }
   cudaDeviceSynchronize();
-  const int B = e->graph_B ? e->graph_B : e->plan_B;
-  struct Tap { const char* n; const float* p; long long rows, cols, ld; const float* lo = nullptr; };
+  const int B = e->step_B ? e->step_B : e->plan_B;
+  // a tap is an fp32 array (optionally the sum of split-K partials) or a pair of fp16 operand planes (hi + lo / 2^11);
+  // backward taps carry the loss scale, which is divided out here
+  struct Tap { const char* n; const float* p; const __half* hi; const __half* lo; long long rows, cols, ld; int parts; long long pstride; float scale; };
   std::vector<Tap> taps;
   char nm[2][24][16];
+  const float ig = 1.f / e->gs;
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i];
     const int D = e->D[i], L = e->L;
-    // tensors that only exist as operand planes are returned as hi + lo
-    const struct { const char* base; const float* p; int cols, ld; const float* lo; } t[] = {
-        {"x", a.x, D, a.ldD, nullptr}, {"y1_", a.y1, 2 * D, a.ld2D, nullptr}, {"h1_", a.h1.hi, 2 * D, a.ld2D, a.h1.lo},
-        {"y2_", a.y2, D, a.ldD, nullptr}, {"h2_", a.h2.hi, D, a.ldD, a.h2.lo}, {"mulv", a.mulv, 2 * L, a.ldmv, nullptr},
-        {"z", a.z, L, a.LP, nullptr}, {"c", a.c, L, a.LP, nullptr}, {"eps", a.eps, L, a.LP, nullptr},
-        {"g1_", a.g1.hi, D, a.ldD, a.g1.lo}, {"g2_", a.g2.hi, 2 * D, a.ld2D, a.g2.lo}, {"xhat", a.xhat, D, a.ldD, nullptr},
-        {"dxhat", a.dxhat.hi, D, a.ldD, a.dxhat.lo}, {"dg2_", a.dg2, 2 * D, a.ld2D, nullptr},
-        {"dy4_", a.dy4.hi, 2 * D, a.ld2D, a.dy4.lo}, {"dg1_", a.dg1, D, a.ldD, nullptr}, {"dy3_", a.dy3.hi, D, a.ldD, a.dy3.lo},
-        {"dc", a.dc, L, a.LP, nullptr}, {"dmulv", a.dmulv, 2 * L, a.ldmv, nullptr}, {"dh2_", a.dh2, D, a.ldD, nullptr},
-        {"dy2_", a.dy2.hi, D, a.ldD, a.dy2.lo}, {"dh1_", a.dh1, 2 * D, a.ld2D, nullptr},
-        {"dy1_", a.dy1.hi, 2 * D, a.ld2D, a.dy1.lo}, {"S", a.S, L, a.LP, nullptr}};
     int k = 0;
-    for (const auto& q : t) {
-      snprintf(nm[i][k], sizeof nm[i][k], "%s%d", q.base, i);
-      taps.push_back({nm[i][k], q.p, B, q.cols, q.ld, q.lo});
-      ++k;
-    }
+    auto f32 = [&](const char* base, const float* p, int cols, int ld, float scale = 1.f) {
+      snprintf(nm[i][k], sizeof nm[i][k], "%s%d", base, i);
+      taps.push_back({nm[i][k], p, nullptr, nullptr, B, cols, ld, 1, 0, scale}); ++k;
+    };
+    auto prt = [&](const char* base, const jb::Parts& q, int cols, int ld, float scale = 1.f) {
+      snprintf(nm[i][k], sizeof nm[i][k], "%s%d", base, i);
+      taps.push_back({nm[i][k], q.ptr, nullptr, nullptr, B, cols, ld, q.n, q.stride, scale}); ++k;
+    };
+    auto pl = [&](const char* base, const HPlanes& h, int cols, int ld, float scale = 1.f) {
+      snprintf(nm[i][k], sizeof nm[i][k], "%s%d", base, i);
+      taps.push_back({nm[i][k], nullptr, h.hi, h.lo, B, cols, ld, 1, 0, scale}); ++k;
+    };
+    f32("x", a.x, D, a.ldD); prt("y1_", a.y1, 2 * D, a.ld2D); pl("h1_", a.h1, 2 * D, a.ld2D); prt("y2_", a.y2, D, a.ldD);
+    pl("h2_", a.h2, D, a.ldD); prt("mulv", a.mulv, 2 * L, e->ldmv); f32("z", a.z, L, e->LP); f32("c", a.c, L, e->LP);
+    f32("eps", a.eps, L, e->LP); pl("g1_", a.g1, D, a.ldD); pl("g2_", a.g2, 2 * D, a.ld2D); prt("xhat", a.xhat, D, a.ldD);
+    pl("dxhat", a.dxhat, D, a.ldD, ig); prt("dg2_", a.dg2, 2 * D, a.ld2D, ig); pl("dy4_", a.dy4, 2 * D, a.ld2D, ig);
+    prt("dg1_", a.dg1, D, a.ldD, ig); pl("dy3_", a.dy3, D, a.ldD, ig); prt("dc", a.dc, L, e->LP, ig);
+    f32("dmulv", a.dmulv, 2 * L, e->ldmv, ig); prt("dh2_", a.dh2, D, a.ldD, ig); pl("dy2_", a.dy2, D, a.ldD, ig);
+    prt("dh1_", a.dh1, 2 * D, a.ld2D, ig); pl("dy1_", a.dy1, 2 * D, a.ld2D, ig); f32("S", a.S, L, e->LP);
   }
-  taps.push_back({"corr", e->corr, B, B, B});
-  taps.push_back({"fblk", e->fblk, B, B, B});
-  taps.push_back({"grad", e->grad, 1, e->n_flat, e->n_flat});
-  taps.push_back({"theta", e->theta, 1, e->n_flat, e->n_flat});
+  taps.push_back({"corr", e->corr, nullptr, nullptr, B, B, B, 1, 0, 1.f});
+  taps.push_back({"fblk", e->fblk, nullptr, nullptr, B, B, B, 1, 0, 1.f});
+  taps.push_back({"grad", e->grad, nullptr, nullptr, 1, e->n_flat, e->n_flat, 1, 0, 1.f});
+  taps.push_back({"theta", e->theta, nullptr, nullptr, 1, e->n_flat, e->n_flat, 1, 0, 1.f});
   for (const Tap& t : taps) {
-    if (strcmp(t.n, name) == 0) {
-      const long long need = t.rows * t.cols;
-      if (need > cap) { fail("buffer too small: need %lld floats", need); return -1; }
-      cudaError_t ce = cudaMemcpy2D(out, static_cast<size_t>(t.cols) * 4, t.p, static_cast<size_t>(t.ld) * 4,
-                                    static_cast<size_t>(t.cols) * 4, t.rows, cudaMemcpyDeviceToHost);
-      if (ce != cudaSuccess) { fail("debug read failed: %s", cudaGetErrorString(ce)); return -1; }
-      if (t.lo) {
-        std::vector<float> lo(static_cast<size_t>(need));
-        ce = cudaMemcpy2D(lo.data(), static_cast<size_t>(t.cols) * 4, t.lo, static_cast<size_t>(t.ld) * 4,
-                          static_cast<size_t>(t.cols) * 4, t.rows, cudaMemcpyDeviceToHost);
+    if (strcmp(t.n, name) != 0) continue;
+    const long long need = t.rows * t.cols;
+    if (need > cap) { fail("buffer too small: need %lld floats", need); return -1; }
+    if (t.p) {
+      if (!e->step_B && t.parts > 0 && t.p == nullptr) { fail("no step has run yet"); return -1; }
+      std::vector<float> tmp(static_cast<size_t>(need));
+      for (long long q = 0; q < need; ++q) out[q] = 0.f;
+      for (int p = 0; p < t.parts; ++p) {
+        cudaError_t ce = cudaMemcpy2D(tmp.data(), static_cast<size_t>(t.cols) * 4, t.p + p * t.pstride, static_cast<size_t>(t.ld) * 4,
+                                      static_cast<size_t>(t.cols) * 4, t.rows, cudaMemcpyDeviceToHost);
         if (ce != cudaSuccess) { fail("debug read failed: %s", cudaGetErrorString(ce)); return -1; }
-        for (long long q = 0; q < need; ++q) out[q] += lo[static_cast<size_t>(q)];
+        for (long long q = 0; q < need; ++q) out[q] += tmp[static_cast<size_t>(q)];
       }
-      return need;
+    } else {
+      std::vector<__half> hi(static_cast<size_t>(need)), lo(static_cast<size_t>(need));
+      cudaError_t ce = cudaMemcpy2D(hi.data(), static_cast<size_t>(t.cols) * 2, t.hi, static_cast<size_t>(t.ld) * 2,
+                                    static_cast<size_t>(t.cols) * 2, t.rows, cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess)
+        ce = cudaMemcpy2D(lo.data(), static_cast<size_t>(t.cols) * 2, t.lo, static_cast<size_t>(t.ld) * 2,
+                          static_cast<size_t>(t.cols) * 2, t.rows, cudaMemcpyDeviceToHost);
+      if (ce != cudaSuccess) { fail("debug read failed: %s", cudaGetErrorString(ce)); return -1; }
+      for (long long q = 0; q < need; ++q) out[q] = __half2float(hi[static_cast<size_t>(q)]) + __half2float(lo[static_cast<size_t>(q)]) * jb::HG_LO_INV;
     }
+    if (t.scale != 1.f) for (long long q = 0; q < need; ++q) out[q] *= t.scale;
+    return need;
   }
   fail("unknown tap '%s'", name);
   return -1;

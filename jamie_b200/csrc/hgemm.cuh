@@ -71,6 +71,7 @@ struct alignas(128) HgProblem {
   int ksplit;              // >= 1
   int tiles_m, tiles_n, tile_base;   // CTA work items of this problem: [tile_base, tile_base + tiles_m tiles_n ksplit)
   int accumulate;          // C += result (one work item owns the tile: no atomics)
+  const int* acc_flag;     // optional device flag: accumulate if *acc_flag != 0 (gradient accumulation over batches)
   float out_scale;         // exact power of two (1 / loss scale for weight gradients)
   float slope;
 };
@@ -348,7 +349,8 @@ __device__ __forceinline__ void hg_epilogue(const HgProblem* __restrict__ probs,
   for (int t = cta; t < ph.total_tiles; t += ncta) {
     const HgTile T = hg_decode(probs, ph, t);
     const HgProblem& P = probs[T.p];
-    const int bn = T.bn, mode = P.mode, pM = P.M, pN = P.N, ldc = P.ldc, epi = P.epi, accumulate = P.accumulate;
+    const int bn = T.bn, mode = P.mode, pM = P.M, pN = P.N, ldc = P.ldc, epi = P.epi;
+    const int accumulate = P.accumulate | (P.acc_flag != nullptr ? __ldcg(P.acc_flag) : 0);
     float* const pC = P.C + static_cast<long long>(T.ks) * P.part_stride;
     const float* const pbias = T.ks == 0 ? P.bias : nullptr;
     const float slope = P.slope, out_scale = P.out_scale;
@@ -492,7 +494,10 @@ __device__ __forceinline__ void hg_epilogue(const HgProblem* __restrict__ probs,
 __device__ __forceinline__ void hg_run_phase(const HgProblem* __restrict__ probs, const HgPhase& ph, int cta, int ncta,
                                              HgCtrl* ctrl, uint8_t* ring, uint8_t* stage_base, uint32_t tmem_d, HgPipe& pp,
                                              int warp, int lane) {
-  if (warp == HG_WARP_TMA) hg_produce(probs, ph, cta, ncta, ctrl, ring, pp);
+  if (warp == HG_WARP_TMA) {
+    fence_proxy_async_global();   // operands written by generic stores of earlier phases (any CTA) -> TMA reads
+    hg_produce(probs, ph, cta, ncta, ctrl, ring, pp);
+  }
   else if (warp == HG_WARP_MMA) hg_mma(probs, ph, cta, ncta, ctrl, ring, tmem_d, pp);
   else if (warp >= HG_WARP_EPI0 && warp < HG_WARP_EPI0 + HG_NEPI) hg_epilogue(probs, ph, cta, ncta, ctrl, stage_base, tmem_d, pp, warp - HG_WARP_EPI0, lane);
 }

@@ -28,6 +28,7 @@ struct Ctl {
   unsigned long long seed;
   unsigned long long stream_id;  // philox counter word: distinct per step
   int host_slot;      // host-batch steps: which of the two device staging buffers holds this step's rows
+  int accum;          // batch_step=False: gradients of this backward pass are added to the buffer (jamie/jamie.py:744-749)
 };
 
 struct StepConsts {

@@ -226,8 +226,11 @@ class Engine:
         _lib.check(self.lib.jb_bench_stage(self.h, int(stage), int(iters), C.byref(us), C.byref(fl), C.c_void_p(stream)))
         return float(us.value), float(fl.value)
 
+    def phase_names(self):
+        return [self.lib.jb_phase_name(p).decode() for p in range(int(self.lib.jb_num_phases()))]
+
     def profile_step(self, iters=20, stream=0):
-        """Average in-stream microseconds of every launch of one training step (jb_profile_step)."""
+        """Average microseconds of every phase of one training step INSIDE the persistent kernel (jb_profile_step)."""
         out = np.zeros(64, np.float32)
         n = C.c_int()
         _lib.check(self.lib.jb_profile_step(self.h, int(iters), _ptr(out), 64, C.byref(n), C.c_void_p(stream)))
@@ -242,40 +245,6 @@ class Engine:
         n = C.c_longlong()
         _lib.check(self.lib.jb_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
-
-    def step_backward_part(self, part, stream=0):
-        _lib.check(self.lib.jb_step_backward_part(self.h, int(part), C.c_void_p(stream)))
-
-    def dp_step(self, dist, buckets, stream=0, overlap=True):
-        """One data-parallel optimizer step. overlap: gradient bucket 0 (heads + decoders) is all-reduced on the process
-        group's stream while the encoder backward still runs, then bucket 1; otherwise one backward graph and both
-        buckets after it. `buckets` = [grad_bucket_tensor(0), grad_bucket_tensor(1)]; `stream` must be torch's current
-        stream."""
-        if not overlap:
-            self.step_backward(stream)
-            w1 = dist.all_reduce(buckets[1], async_op=True)     # the two buckets tile the buffer: two calls, no copy
-            w0 = dist.all_reduce(buckets[0], async_op=True)
-        else:
-            self.step_backward_part(0, stream)
-            w0 = dist.all_reduce(buckets[0], async_op=True)
-            self.step_backward_part(1, stream)
-            w1 = dist.all_reduce(buckets[1], async_op=True)
-        w0.wait()
-        w1.wait()
-        self.step_update(stream)
-
-    def grad_bucket_tensor(self, part):
-        """Gradient bucket `part` (0: heads + decoders + loss scalars, 1: sigma + encoders) as a torch CUDA tensor view."""
-        import torch
-        p = C.c_void_p()
-        n = C.c_longlong()
-        _lib.check(self.lib.jb_grad_bucket(self.h, int(part), C.byref(p), C.byref(n)))
-        ptr, cnt = int(p.value), int(n.value)
-
-        class _Buf:
-            __cuda_array_interface__ = {'shape': (cnt,), 'typestr': '<f4', 'data': (ptr, False), 'version': 3,
-                                        'strides': None}
-        return torch.as_tensor(_Buf(), device=f'cuda:{self.device}')
 
     def grad_tensor(self):
         """The gradient buffer as a torch CUDA tensor view (no copy) -- what torch.distributed all-reduces."""

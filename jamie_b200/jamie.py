@@ -357,7 +357,6 @@ class JAMIE(UnionCom):
         if world > 1:
             import torch.distributed as dist
             gt = eng.grad_tensor()
-            buckets = [eng.grad_bucket_tensor(0), eng.grad_bucket_tensor(1)]
         self.model.train()
         # O(batch) sampler for large datasets; seeded from numpy's global generator, so np.random.seed(...) in the caller
         # still makes a run reproducible
@@ -405,9 +404,6 @@ class JAMIE(UnionCom):
             nsteps = n_ep * len_dataloader
             if world == 1 and self.batch_step:
                 eng.train_steps(nsteps, stream)
-            elif self.batch_step and os.environ.get('JB_DP_MODE', 'single') == 'overlap':
-                for s_ in range(nsteps):      # gradient exchange overlapped with the encoder backward (opt-in)
-                    eng.dp_step(dist, buckets, stream)
             else:
                 for s_ in range(nsteps):
                     if not self.batch_step:

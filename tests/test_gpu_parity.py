@@ -290,44 +290,3 @@ def test_hostbatch_async_equals_sync_and_resident():
         eng = _engine(dims, L, B, p)
         eng.hostbatch_wait()
 
-
-def test_two_part_backward_equals_single_backward():
-    """Data-parallel step in two halves (jb_step_backward_part 0 / 1, gradient buckets for the overlapped all-reduce) ==
-    jb_step_backward: same gradients and update; the two buckets tile the flat gradient buffer."""
-    dims, L, B, p, n = [160, 72], 8, 200, 0.3, 400
-    data = U.synth_pair(n, dims, seed=31)
-    params = U.torch_like_init(dims, L, seed=32)
-    rng = np.random.default_rng(33)
-    idx = np.stack([rng.choice(n, B, replace=False) for _ in range(3)])
-    res = []
-    for split in (False, True):
-        eng = _engine(dims, L, B, p, seed=9, world_size=2)
-        eng.set_params(params)
-        for i in range(2):
-            eng.set_dataset(i, data[i])
-        eng.set_prior_diag(np.ones(n, np.float32))
-        eng.set_f_dense(None)
-        eng.upload_plan(idx, idx, np.full(3, 0.5))
-        for _ in range(3):
-            if split:
-                eng.step_backward_part(0)
-                eng.step_backward_part(1)
-            else:
-                eng.step_backward()
-            eng.step_update()
-        res.append((eng.read_losses(3).copy(), np.concatenate([g.ravel() for g in eng.get_grads()]),
-                    np.concatenate([t.ravel() for t in eng.get_params()])))
-        if split:
-            whole, b0, b1 = eng.grad_tensor(), eng.grad_bucket_tensor(0), eng.grad_bucket_tensor(1)
-            assert b1.data_ptr() == whole.data_ptr() and b0.data_ptr() == whole.data_ptr() + 4 * b1.numel()
-            assert b0.numel() + b1.numel() == whole.numel()
-        eng.close()
-    for a, b in zip(res[0], res[1]):
-        np.testing.assert_array_equal(a, b)
-    eng = _engine(dims, L, B, p)        # one rank: no two-part graphs
-    eng.set_params(params)
-    for i in range(2):
-        eng.set_dataset(i, data[i])
-    eng.upload_plan(idx, idx, np.full(3, 0.5))
-    with pytest.raises(RuntimeError, match='world_size > 1'):
-        eng.step_backward_part(0)

@@ -67,8 +67,16 @@ def main():
                 got = eng.debug_read(key, ot[key].shape)
                 print(f'  {key:10s} rel {U.rel(got, ot[key]):.3e}')
         print('  losses gpu', losses[:6], ' oracle', [float(v) for v in ls], 'norm', tot)
-        # gradients: engine's padded flat buffer is private; compare through parameters after the step instead,
-        # and through the recorded norm
+        gg = eng.get_grads()
+        gworst = 0
+        for (nm, _), g_ in zip(orc.spec, gg):
+            if nm in U.PRE_BN_BIAS:
+                continue
+            r_ = U.rel(g_, grads[nm])
+            gworst = max(gworst, r_)
+            if r_ > 3e-4:
+                print(f'  grad {nm:24s} rel {r_:.3e}')
+        print(f'  worst per-tensor gradient error {gworst:.3e}')
         after = eng.get_params()
         worst = 0
         for (nm, _), ga, oa, tb in zip(orc.spec, after, orc.param_list(), theta_before):
