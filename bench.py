@@ -3,21 +3,30 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json): N = 1 -> configs[1], synthetic scRNA+scATAC-like pair, 50k cells, post-PCA widths [512, 512],
-output_dim 32, batch 512, 50 % partially matched P (diag mask -> 'hybrid' sampler), dropout 0.6, F = 0.
-N > 1 -> configs[3], 1M cells sharded over the ranks, batch 512 per rank (weak scaling), one NCCL all-reduce of the
-flat gradient buffer per step.  Data are synthetic standardised fp32 rows of the named shape; weights are the
-reference's random init (torch seed 666).  A "step" is one optimizer step over one batch.
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on, at EVERY N): synthetic 1M-cell pair,
+post-PCA widths [512, 512], output_dim 32, batch 512 per rank, 50 % partially matched P (diag mask -> 'hybrid' sampler),
+dropout 0.6, F = 0; the cells are sharded over the ranks (weak scaling: per-rank batch fixed), one all-reduce of the flat
+gradient buffer per step for N > 1. Data are synthetic standardised fp32 rows of the named shape; weights are the
+reference's random init (torch seed 666). A "step" is one optimizer step over one batch.
 
-  value : cells/s, whole job, data and sampling plan resident in HBM, K CUDA-graph steps timed with CUDA events
+  value : cells/s, whole job, data and sampling plan resident in HBM; the K steps are ONE launch of the persistent step
+          kernel (N = 1) timed with CUDA events
   e2e   : cells/s through the C ABI with HOST data: per step the batch is gathered on the host into pinned memory,
-          copied to the device inside jb_train_step_hostbatch, and the loss scalars are read back
-  roofline     : the dominant kernel (largest TF32 GEMM stage) timed alone with CUDA events, vs the measured tensor peak
-  step_roofline: compulsory HBM bytes of one step (fp32 param + Adam moments r/w + gathered inputs) / step time
-  cpu_baseline : the numpy oracle (a port of the reference's algorithm) timed on this box's host cores
-`--impl reference` times the oracle port alone (the reference is Python and /root/reference is absent on the GPU box).
+          copied to the device inside jb_hostbatch_submit, and the loss scalars are read back
+  e2e_fit_transform : wall clock of the user-facing call, JAMIE(...).fit_transform on host numpy arrays (standardise,
+          upload, sampler, training chunks, loss read-back, final encode, download)
+  roofline      : the step kernel (k_step: the whole step is one kernel) against the measured HBM peak with the
+          compulsory bytes of a step (fp32 param + Adam moments r/w + gathered inputs); DRAM traffic from
+          the committed `ncu --set full` capture
+  gemm_roofline : all GEMM phases together (algorithmic FLOPs / in-kernel phase time) against the measured tensor peak
+  step_profile  : microseconds per phase INSIDE the persistent kernel (GPU global timer at the phase boundaries)
+  cpu_baseline  : the reference itself (oracle/_ref = a copy of /root/reference/jamie made by build()) timed on this
+          box's host cores; falls back to the numpy oracle port when the copy is absent
+`--impl reference` times the reference alone (all host cores; rank 0 only under torchrun).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -31,19 +40,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DIMS, LATENT, BATCH, DROPOUT = [512, 512], 32, 512, 0.6
-# launch order of one training step (engine.cu: record_backward / record_update)
-STEP_KERNELS = {
-    31: ['k_gather(+step ctl)', 'k_corr_rowsum (side branch in the graph)', 'k_corr_build (side branch in the graph)',
-         'gemm F1 enc D->2D', 'k_bn_fwd', 'gemm F2 enc 2D->D', 'k_bn_fwd', 'gemm F3 heads', 'k_reparam',
-         'k_combine(+latent loss)', 'gemm F4 dec L->D', 'k_bn_fwd', 'gemm F5 dec D->2D', 'k_bn_fwd',
-         'gemm F6 dec 2D->D', 'k_rec', 'gemm B6 dgrad', 'k_bn_bwd', 'gemm B5 dgrad', 'k_bn_bwd', 'gemm B4 dgrad',
-         'k_latent_bwd_c', 'k_latent_bwd_z', 'k_latent_final', 'gemm B3 dgrad', 'k_bn_bwd', 'gemm B2 dgrad',
-         'k_bn_bwd', 'gemm wgrad x12', 'k_gradnorm', 'k_adam'],
-}
+N_CELLS = 1_000_000
 N_PARAMS = 4312194
-# N > 1: 'single' = backward | one all-reduce of the flat gradient buffer | update (default: measured fastest at N = 2 and
-# N = 8, profiles/README.md); 'overlap' = Engine.dp_step with bucket 0 all-reduced beside the encoder backward
-DP_MODE = os.environ.get('JB_DP_MODE', 'single')
+ALG_BYTES_PER_STEP = 6 * 4 * N_PARAMS + 4 * BATCH * sum(DIMS)      # 105.6 MB
+ALG_FLOPS_PER_STEP = 12.11e9
 
 
 def load_peaks():
@@ -122,11 +122,57 @@ def init_params():
     return m.packed_parameters(), m.packed_buffers()
 
 
-def cpu_baseline(seconds=12.0, max_steps=200):
-    """Oracle port of one reference optimizer step (sampling, gather, P block, fwd, losses, bwd, clip, Adam)."""
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_reference(steps, warmup, n=4096):
+    """The UNMODIFIED reference (oracle/_ref, or /root/reference in the build container) on this box's host cores, timed
+    as BASELINE.md section 3 prescribes: its own project_jamie loop on synthetic data of the benchmark's shape with n
+    capped (its per-step cost does not depend on n, its set-up is O(n^2)), use_f_tilde=False, and the per-batch laps of its
+    own time_logger ('Get subset samples' ... 'Step') summed over `steps` optimizer steps after `warmup`."""
+    import torch
+    from oracle import ref_harness as RH
+    torch.set_num_threads(os.cpu_count() or 1)
+    jamie = RH.import_reference()
+    import jamie.jamie as JJ
+    loggers = []
+    base = JJ.time_logger
+
+    class Spy(base):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            loggers.append(self)
+
+    JJ.time_logger = Spy
+    rng = np.random.default_rng(0)
+    data = [rng.standard_normal((n, d)) for d in DIMS]
+    m = (rng.random(n) < 0.5).astype(np.float64)
+    per_epoch = max(1, n // BATCH)
+    epochs = -(-(steps + warmup) // per_epoch)
+    np.random.seed(42)
+    try:
+        jm = jamie.JAMIE(output_dim=LATENT, batch_size=BATCH, pca_dim=None, dropout=DROPOUT, use_f_tilde=False,
+                         epoch_DNN=epochs, min_epochs=10 * epochs, log_DNN=10 ** 9, use_early_stop=False)
+        with contextlib.redirect_stdout(io.StringIO()):
+            jm.fit_transform(dataset=data, P=np.diag(m))
+    finally:
+        JJ.time_logger = base
+    hist = max((lg.history for lg in loggers), key=lambda h: len(h.get('Step', [])))
+    labels = [k for k in hist if k not in ('Setup', 'Output')]
+    avail = len(hist['Step'])
+    w = min(warmup, max(0, avail - steps))
+    k = min(steps, avail - w)
+    total = sum(float(np.sum(hist[lb][w:w + k])) for lb in labels if len(hist[lb]) >= w + k)
+    return {'value': BATCH * k / total, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'reference',
+            'threads': torch.get_num_threads(), 'ms_per_step': 1e3 * total / k,
+            'sample': f'{k} optimizer steps (after {w} warm-up) of the reference\'s own project_jamie loop, batch {BATCH}, widths '
+                      f'{DIMS}, output_dim {LATENT}, dropout {DROPOUT}, n = {n} cells, torch {torch.__version__} CPU; sum of '
+                      f'its time_logger laps {labels}, {total:.1f} s'}
+
+
+def cpu_port(seconds=12.0, max_steps=200):
+    """Fallback when the reference copy is absent: the numpy oracle port of one reference optimizer step."""
     from oracle import jamie_oracle as O
     rng = np.random.default_rng(0)
-    n = 8192      # the reference's per-step cost does not depend on n (BASELINE.md section 3)
+    n = 8192
     data = [rng.standard_normal((n, d)).astype(np.float32) for d in DIMS]
     m = (rng.random(n) < 0.5).astype(np.float32)
     nz = np.flatnonzero(m)[:2]
@@ -160,13 +206,24 @@ def cpu_baseline(seconds=12.0, max_steps=200):
                       f'(numpy fp32 oracle, BLAS on all host cores), {dt:.1f} s', 'ms_per_step': 1e3 * dt / steps}
 
 
+def cpu_baseline(steps=60, warmup=10):
+    from oracle import ref_harness as RH
+    if RH.reference_available():
+        try:
+            return cpu_reference(steps, warmup)
+        except Exception as ex:   # a broken copy must not take the GPU numbers down with it
+            cb = cpu_port()
+            cb['note'] = f'reference copy failed to run ({type(ex).__name__}: {ex}); oracle port timed instead'
+            return cb
+    return cpu_port()
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    from oracle import jamie_oracle as O  # noqa: F401
-    t_budget = max(5.0, min(120.0, 0.15 * (args.steps + args.warmup)))
-    cb = cpu_baseline(seconds=t_budget, max_steps=max(args.steps, 3))
+    steps = max(3, min(args.steps, 200))
+    cb = cpu_baseline(steps=steps, warmup=max(3, min(args.warmup, 20)))
     line = {
         'impl': 'reference', 'metric': 'train cells/sec (fwd+bwd+Adam)', 'value': cb['value'], 'unit': 'cells/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'],
@@ -175,8 +232,6 @@ def run_reference(args):
         'cpu_baseline': cb,
         'e2e': {'value': cb['value'], 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-        'note': 'oracle port of the reference step on the host cores: the reference is pure Python/torch and cannot '
-                'travel to the GPU box',
     }
     print(json.dumps(line), flush=True)
 
@@ -190,9 +245,10 @@ def ncu_traffic(kernel_key):
         return None
 
 
-def predict_leg(eng, torch, peaks, stream, rows_dev=1 << 20, rows_host=1 << 18):
-    """modal_predict (BASELINE metric 2): modality 0 -> 1 on pre-transformed [N, 512] fp32 rows.
-    value: rows resident in HBM, CUDA events; e2e: pinned host buffers in and out through jb_predict."""
+def predict_leg(eng, torch, peaks, stream, rows_dev=1_250_000, rows_host=1 << 18):
+    """modal_predict (BASELINE metric 2, configs[4]: 10M cells over 8 GPUs = 1.25M rows per rank): modality 0 -> 1 on
+    pre-transformed [N, 512] fp32 rows. value: rows resident in HBM, CUDA events; e2e: pinned host buffers in and out
+    through jb_predict."""
     g = torch.Generator(device='cuda').manual_seed(2)
     x = torch.randn((rows_dev, DIMS[0]), generator=g, device='cuda', dtype=torch.float32)
     out = torch.empty((rows_dev, DIMS[1]), device='cuda', dtype=torch.float32)
@@ -220,23 +276,49 @@ def predict_leg(eng, torch, peaks, stream, rows_dev=1 << 20, rows_host=1 << 18):
                     'h2d_bytes': rows_host * DIMS[0] * 4, 'd2h_bytes': rows_host * DIMS[1] * 4},
             'roofline': {'bound': 'tensor', 'achieved': v * flops_row / 1e12, 'peak': peaks['bf16_tflops_sustained'],
                          'unit': 'TFLOP/s', 'frac': v * flops_row / 1e12 / peaks['bf16_tflops_sustained'],
-                         'flops_per_row': flops_row,
-                         'note': 'BatchNorm folded, single-pass TF32 (hardware rate = half the bf16 peak in the denominator)'},
+                         'flops_per_row': flops_row},
             'gpu_launches': eng.launch_count() - l0}
 
 
+def fit_transform_leg(torch, n=100_000, epochs=3):
+    """Wall clock of the user-facing call: JAMIE(...).fit_transform(dataset=[X0, X1], P=mask) on host numpy arrays that
+    already have the post-PCA width (pca_dim=None: per-feature standardisation only), then the embeddings come back as
+    numpy. Everything a user waits for is inside: standardise, engine creation, upload, batch sampler, training chunks,
+    loss read-back, final encode of all cells, download."""
+    from jamie import JAMIE
+    rng = np.random.default_rng(7)
+    data = [rng.standard_normal((n, d)).astype(np.float32) for d in DIMS]
+    mask = (rng.random(n) < 0.5).astype(np.float32)
+    np.random.seed(0)
+    out = {}
+    for tag, ep in (('warm', 1), ('timed', epochs)):
+        jm = JAMIE(output_dim=LATENT, batch_size=BATCH, pca_dim=None, dropout=DROPOUT, use_f_tilde=False, epoch_DNN=ep,
+                   min_epochs=10 * ep, log_DNN=10 ** 9, use_early_stop=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            emb = jm.fit_transform(dataset=data, P=mask)
+        dt = time.perf_counter() - t0
+        steps = ep * (n // BATCH)
+        out[tag] = (dt, steps)
+        assert emb[0].shape == (n, LATENT) and np.all(np.isfinite(emb[0][::997]))
+        jm.engine.close()
+    dt, steps = out['timed']
+    dt_w, steps_w = out['warm']
+    per_step = (dt - dt_w) / max(1, steps - steps_w)
+    return {'value': BATCH * steps / dt, 'unit': 'cells/s', 'seconds': dt, 'optimizer_steps': steps, 'cells': n, 'epochs': epochs,
+            'marginal_us_per_step': 1e6 * per_step,
+            'note': 'wall clock of JAMIE.fit_transform on host numpy data (pca_dim=None), incl. standardise, upload, sampler, '
+                    'training, final encode, download; marginal_us_per_step = (T(3 epochs) - T(1 epoch)) / extra steps'}
+
+
 def workload_config(n_gpus):
-    if n_gpus == 1:
-        wl = 'BASELINE configs[1]: synthetic 50k-cell pair, post-PCA widths [512,512], output_dim 32, batch 512, ' \
-             '50% partially matched diagonal P (hybrid sampler), dropout 0.6, F=0'
-        n = 50_000
-    else:
-        wl = f'BASELINE configs[3]: synthetic 1M-cell pair sharded over {n_gpus} ranks, widths [512,512], output_dim 32, ' \
-             f'batch 512 per rank, 50% partially matched diagonal P, dropout 0.6, F=0, one flat-gradient all-reduce/step'
-        n = 1_000_000
-    return {'workload': wl, 'cells': n, 'widths': DIMS, 'output_dim': LATENT, 'batch_per_rank': BATCH,
-            'parallelism': f'dp{n_gpus}', 'l2_policy': 'parameter + Adam state (69 MB) and gathered rows are re-read '
-            'every step by design; inputs are gathered from a dataset larger than L2 (N>1) / re-sampled rows (N=1)'}
+    wl = f'BASELINE configs[3]: synthetic 1M-cell pair sharded over {n_gpus} rank(s), widths [512,512], output_dim 32, ' \
+         f'batch 512 per rank, 50% partially matched diagonal P (hybrid sampler), dropout 0.6, F=0' + \
+         (', one flat-gradient all-reduce/step' if n_gpus > 1 else '')
+    return {'workload': wl, 'cells': N_CELLS, 'widths': DIMS, 'output_dim': LATENT, 'batch_per_rank': BATCH,
+            'parallelism': f'dp{n_gpus}', 'l2_policy': 'inputs larger than L2: every step gathers 2 x 512 random rows from a '
+            '4.1 GB (N=1) resident dataset; parameters + Adam state (69 MB) are re-read every step by design'}
 
 
 def main():
@@ -247,6 +329,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-predict', action='store_true')
+    ap.add_argument('--no-fit', action='store_true')
     ap.add_argument('--predict-only', action='store_true', help='modal_predict leg alone (tuning runs)')
     ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu): no e2e / stage / CPU legs, no JSON line')
     args = ap.parse_args()
@@ -280,8 +363,7 @@ def main():
     peaks = load_peaks()
     K, W = args.steps, max(args.warmup, 3)
 
-    n_total = workload_config(args.gpus)['cells']
-    n = n_total // world
+    n = N_CELLS // world
     g = torch.Generator(device='cuda').manual_seed(1234 + rank)
     data = [torch.randn((n, d), generator=g, device='cuda', dtype=torch.float32) for d in DIMS]
     rng = np.random.default_rng(100 + rank)
@@ -300,7 +382,6 @@ def main():
     idx0, idx1 = make_plan(n, W + K, rng, cs)
     eng.upload_plan(idx0, idx1, np.full(W + K, 0.5), stream)
     gt = eng.grad_tensor() if world > 1 else None
-    buckets = [eng.grad_bucket_tensor(0), eng.grad_bucket_tensor(1)] if world > 1 else None
     if args.predict_only:
         p = predict_leg(eng, torch, peaks, stream)
         emit({k: p[k] for k in ('value', 'ms', 'e2e', 'gpu_launches')})
@@ -309,16 +390,12 @@ def main():
 
     def run_steps(k):
         if world == 1:
-            eng.train_steps(k, stream)
+            eng.train_steps(k, stream)          # ONE launch of the persistent step kernel for k optimizer steps
         else:
-            if DP_MODE == 'single':
-                for _ in range(k):  # backward | one all-reduce of the flat gradient buffer | update
-                    eng.step_backward(stream)
-                    dist.all_reduce(gt)
-                    eng.step_update(stream)
-            else:                   # backward part 0 | all-reduce(bucket 0) beside backward part 1 | all-reduce(bucket 1) | update
-                for _ in range(k):
-                    eng.dp_step(dist, buckets, stream, overlap=DP_MODE == 'overlap')
+            for _ in range(k):                  # backward | one all-reduce of the flat gradient buffer | update
+                eng.step_backward(stream)
+                dist.all_reduce(gt)
+                eng.step_update(stream)
 
     def sync_all():
         if world > 1:
@@ -352,18 +429,16 @@ def main():
         return
     prof = None
     if world == 1:
-        eng.upload_plan(idx0[:1], idx1[:1], np.full(1, 0.5), stream)
-        us = eng.profile_step(20, stream)
-        names = STEP_KERNELS.get(len(us), [f'launch{k}' for k in range(len(us))])
-        prof = {'sum_us': float(us.sum()), 'launches': [[n, round(float(u), 2)] for n, u in zip(names, us)],
-                'note': 'eager launches with a CUDA event between consecutive kernels (warm L2, no graph, no PDL): '
-                        'shares of the step, not absolutes'}
+        eng.upload_plan(idx0[:64], idx1[:64], np.full(64, 0.5), stream)
+        us = eng.profile_step(48, stream)
+        prof = {'sum_us': float(us.sum()), 'phases': [[nm, round(float(u), 2)] for nm, u in zip(eng.phase_names(), us)],
+                'note': 'microseconds per phase inside the persistent kernel (GPU global timer at the phase boundaries, grid '
+                        'barrier included), averaged over 48 consecutive steps of one launch'}
 
     # ---------------- end to end with host-resident data
     Ke = max(20, min(K, 300))
-    host = [d.cpu().pin_memory() for d in data] if n <= 200_000 else \
-        [d[:200_000].cpu().pin_memory() for d in data]
-    nh = host[0].shape[0]
+    nh = min(n, 200_000)
+    host = [d[:nh].cpu().pin_memory() for d in data]
     hb = [[torch.empty((BATCH, d), dtype=torch.float32).pin_memory() for d in DIMS] for _ in range(2)]   # two host slots
     i0e, i1e = make_plan(nh, Ke + 5, rng, cs if nz.max() < nh else np.stack([np.flatnonzero(mask[:nh])[:2]] * 2, 1))
     ti = [torch.from_numpy(i0e), torch.from_numpy(i1e)]
@@ -407,6 +482,7 @@ def main():
     e2e_value = BATCH * Ke * world / dt
     h2d = sum(BATCH * d * 4 for d in DIMS) + 2 * BATCH * 4 + 4
     d2h = 8 * 4
+    del host
 
     pred = predict_leg(eng, torch, peaks, stream) if not args.no_predict else None
     if pred is not None and world > 1:      # rows/s of the whole job: every rank imputes its own shard, no collective
@@ -416,48 +492,54 @@ def main():
         pred['e2e']['value'] = world * pred['e2e']['rows'] / float(t[1])
     line = None
     if rank == 0:
-        # ---------------- dominant kernel alone (CUDA events on the launching stream)
-        stages = []
-        for st in range(12):
-            us, fl = eng.bench_stage(st, 200, stream)
-            stages.append((us, fl, st))
-        tot_gemm_us = sum(s[0] for s in stages)
-        us, fl, st = max(stages)
-        tf = fl / (us * 1e-6) / 1e12
         step_us = ms * 1e3 / K
-        alg_bytes = 6 * 4 * N_PARAMS + 4 * BATCH * sum(DIMS)
-        roof = {'bound': 'tensor', 'kernel': f'gemm_tf32_grouped_kernel (stage {st})', 'achieved': tf,
-                'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops'],
-                'traffic': None, 'us_per_launch': us, 'flops_per_launch': fl, 'peak_source': peaks['source'],
-                'note': 'kernel computes in TF32 (hardware rate = half the bf16 peak used as denominator); '
-                        f'all 12 GEMM stages alone sum to {tot_gemm_us:.1f} us of the {step_us:.1f} us step'}
-        sroof = {'bound': 'hbm', 'achieved': alg_bytes / (step_us * 1e-6) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                 'frac': alg_bytes / (step_us * 1e-6) / 1e9 / peaks['hbm_gbs'], 'bytes_per_step': alg_bytes,
-                 'note': 'algorithmic bytes of a whole step = r/w of fp32 params + Adam m, v (6*4*4312194) + gathered '
-                         'inputs; SURVEY.md section 8d: the step roofline is 16.1 us'}
+        roof = {'bound': 'hbm', 'kernel': 'k_step (the whole optimizer step is one persistent kernel)',
+                'achieved': ALG_BYTES_PER_STEP / (step_us * 1e-6) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': ALG_BYTES_PER_STEP / (step_us * 1e-6) / 1e9 / peaks['hbm_gbs'], 'traffic': ncu_traffic('k_step_per_step'),
+                'us_per_step': step_us, 'bytes_per_step': ALG_BYTES_PER_STEP, 'peak_source': peaks['source'],
+                'note': 'algorithmic bytes of a step = r/w of fp32 params + Adam m, v (6*4*4312194) + gathered inputs '
+                        '(SURVEY.md 8d: the step roofline is 16.1 us); traffic = DRAM bytes per step from the committed ncu capture'}
+        groof = None
+        if prof is not None:
+            gem = [(nm, u) for nm, u in prof['phases'] if nm.startswith('gemm') or nm.startswith('dgrad') or nm.startswith('wgrad')]
+            gus = sum(u for _, u in gem)
+            groof = {'bound': 'tensor', 'achieved': ALG_FLOPS_PER_STEP / (gus * 1e-6) / 1e12, 'peak': peaks['bf16_tflops_sustained'],
+                     'unit': 'TFLOP/s', 'frac': ALG_FLOPS_PER_STEP / (gus * 1e-6) / 1e12 / peaks['bf16_tflops_sustained'],
+                     'gemm_phases_us': round(gus, 2), 'flops_per_step': ALG_FLOPS_PER_STEP,
+                     'note': 'all 12 GEMM phases of a step together: algorithmic FLOPs (one fp32-class product per MAC; the '
+                             'kernel issues three fp16 tensor-core passes per product) over their in-kernel time'}
+        fit = None
+        if world == 1 and not args.no_fit:
+            eng.close()
+            del data
+            torch.cuda.empty_cache()
+            fit = fit_transform_leg(torch)
         cb = None
-        roof['traffic'] = ncu_traffic('gemm_stage_%d' % st)
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:   # last: importing the reference replaces the `jamie` package in sys.modules
             cb = cpu_baseline()
         line = {
             'metric': 'train cells/sec (fwd+bwd+Adam)', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
             'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'f16x2 (fp16 hi/lo split operands, fp32 accumulate: fp32-class products)', 'data': 'synthetic',
             'config': workload_config(world),
             'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': Ke, 'note': 'per step: host gather of the batch rows into pinned memory, H2D of rows + cell ids, '
-                                         'step graph, D2H of the 8 loss scalars; jb_hostbatch_submit / jb_hostbatch_wait keep '
+                                         'step kernel, D2H of the 8 loss scalars; jb_hostbatch_submit / jb_hostbatch_wait keep '
                                          'two steps in flight (N = 1)'},
+            'e2e_fit_transform': fit,
             'gpu_launches': int(launches), 'launches_per_step': launches / K,
-            'roofline': roof, 'step_roofline': sroof, 'step_profile': prof,
-            'gemm_stages_us': [round(s[0], 2) for s in stages], 'modal_predict': pred, 'cpu_baseline': cb, 'clocks': clocks.summary(),
+            'roofline': roof, 'gemm_roofline': groof, 'step_profile': prof,
+            'modal_predict': pred, 'cpu_baseline': cb, 'clocks': clocks.summary(),
             'final_losses': {k: float(v) for k, v in zip(['KL', 'Rec', 'CosSim', 'F', 'total', 'grad_norm'], losses[-1])},
         }
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
+    try:
+        eng.close()
+    except Exception:
+        pass
 
 
 if __name__ == '__main__':

@@ -1257,6 +1257,7 @@ long long jb_debug_read(jb_engine* e, const char* name, float* out, long long ca
   const int B = e->step_B ? e->step_B : e->plan_B;
   // a tap is an fp32 array (optionally the sum of split-K partials) or a pair of fp16 operand planes (hi + lo / 2^11);
   // backward taps carry the loss scale, which is divided out here
+  // (parts that the consuming phase reduces in place hold the sum in partial 0: read with parts = 1)
   struct Tap { const char* n; const float* p; const __half* hi; const __half* lo; long long rows, cols, ld; int parts; long long pstride; float scale; };
   std::vector<Tap> taps;
   char nm[2][24][16];
@@ -1269,9 +1270,9 @@ long long jb_debug_read(jb_engine* e, const char* name, float* out, long long ca
       snprintf(nm[i][k], sizeof nm[i][k], "%s%d", base, i);
       taps.push_back({nm[i][k], p, nullptr, nullptr, B, cols, ld, 1, 0, scale}); ++k;
     };
-    auto prt = [&](const char* base, const jb::Parts& q, int cols, int ld, float scale = 1.f) {
+    auto prt = [&](const char* base, const jb::Parts& q, int cols, int ld, float scale = 1.f, bool reduced = true) {
       snprintf(nm[i][k], sizeof nm[i][k], "%s%d", base, i);
-      taps.push_back({nm[i][k], q.ptr, nullptr, nullptr, B, cols, ld, q.n, q.stride, scale}); ++k;
+      taps.push_back({nm[i][k], q.ptr, nullptr, nullptr, B, cols, ld, reduced ? 1 : q.n, q.stride, scale}); ++k;
     };
     auto pl = [&](const char* base, const HPlanes& h, int cols, int ld, float scale = 1.f) {
       snprintf(nm[i][k], sizeof nm[i][k], "%s%d", base, i);
@@ -1280,10 +1281,10 @@ long long jb_debug_read(jb_engine* e, const char* name, float* out, long long ca
     f32("x", a.x, D, a.ldD); prt("y1_", a.y1, 2 * D, a.ld2D); pl("h1_", a.h1, 2 * D, a.ld2D); prt("y2_", a.y2, D, a.ldD);
     pl("h2_", a.h2, D, a.ldD); prt("mulv", a.mulv, 2 * L, e->ldmv); f32("z", a.z, L, e->LP); f32("c", a.c, L, e->LP);
     f32("eps", a.eps, L, e->LP); pl("g1_", a.g1, D, a.ldD); pl("g2_", a.g2, 2 * D, a.ld2D); prt("xhat", a.xhat, D, a.ldD);
-    pl("dxhat", a.dxhat, D, a.ldD, ig); prt("dg2_", a.dg2, 2 * D, a.ld2D, ig); pl("dy4_", a.dy4, 2 * D, a.ld2D, ig);
-    prt("dg1_", a.dg1, D, a.ldD, ig); pl("dy3_", a.dy3, D, a.ldD, ig); prt("dc", a.dc, L, e->LP, ig);
-    f32("dmulv", a.dmulv, 2 * L, e->ldmv, ig); prt("dh2_", a.dh2, D, a.ldD, ig); pl("dy2_", a.dy2, D, a.ldD, ig);
-    prt("dh1_", a.dh1, 2 * D, a.ld2D, ig); pl("dy1_", a.dy1, 2 * D, a.ld2D, ig); f32("S", a.S, L, e->LP);
+    pl("dxhat", a.dxhat, D, a.ldD, ig); prt("dg2_", a.dg2, 2 * D, a.ld2D, ig, false); pl("dy4_", a.dy4, 2 * D, a.ld2D, ig);
+    prt("dg1_", a.dg1, D, a.ldD, ig, false); pl("dy3_", a.dy3, D, a.ldD, ig); prt("dc", a.dc, L, e->LP, ig);
+    f32("dmulv", a.dmulv, 2 * L, e->ldmv, ig); prt("dh2_", a.dh2, D, a.ldD, ig, false); pl("dy2_", a.dy2, D, a.ldD, ig);
+    prt("dh1_", a.dh1, 2 * D, a.ld2D, ig, false); pl("dy1_", a.dy1, 2 * D, a.ld2D, ig); f32("S", a.S, L, e->LP);
   }
   taps.push_back({"corr", e->corr, nullptr, nullptr, B, B, B, 1, 0, 1.f});
   taps.push_back({"fblk", e->fblk, nullptr, nullptr, B, B, B, 1, 0, 1.f});

@@ -23,7 +23,17 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = '/root/reference'
+import os
+
+# The reference package is imported from /root/reference when that exists (the build container) and otherwise from
+# oracle/_ref (a byte-for-byte copy of /root/reference/jamie made by __graft_entry__.build(); git-ignored, it only
+# travels to the GPU box so that bench.py --impl reference can time the real reference there).
+_REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+REFERENCE_ROOT = '/root/reference' if os.path.isdir('/root/reference/jamie') else _REF_COPY
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'jamie'))
 
 
 class _Any:
@@ -122,7 +132,7 @@ def install_stubs():
 
 
 def import_reference():
-    """Returns the reference's ``jamie`` package (imported from /root/reference)."""
+    """Returns the reference's ``jamie`` package (imported from /root/reference, or from the oracle/_ref copy)."""
     install_stubs()
     import jamie  # noqa
     assert jamie.__file__.startswith(REFERENCE_ROOT), jamie.__file__

@@ -1,7 +1,10 @@
 """GPU parity tests: the CUDA engine, called through the C ABI, against (a) fixtures recorded from the real reference
-and (b) the numpy oracle on seeded inputs at the headline sizes.  Tolerances: the GEMMs run in TF32 with fp32
-accumulation (operands rounded to nearest by TMA), everything else in fp32; north_star asks for 1e-3 relative on
-per-step losses and gradients with injected eps / dropout masks / batch indices."""
+and (b) the numpy oracle on seeded inputs at the headline sizes.  north_star asks for 1e-3 relative on per-step losses
+and gradients with injected eps / dropout masks / batch indices.  Round 2: every GEMM of the step (forward, dgrad AND
+wgrad) runs the three-pass fp16-split product (hgemm.cuh, fp32-class), everything else is fp32, so the engine agrees
+with the fp32 oracle to ~1e-6 (profiles/parity_r2.md lists the measured per-tensor errors of every shape) and the
+tolerances below are 5x .. 10x TIGHTER than north_star's.  Against the recorded reference fixtures the bound is the
+reference's own fp32 noise (oracle vs reference: up to 2e-4 per tensor, tests/test_oracle_golden.py): 1e-3."""
 import numpy as np
 import pytest
 
@@ -11,9 +14,10 @@ from tests.golden_util import CASES, Golden
 
 pytestmark = pytest.mark.gpu
 
-LOSS_RTOL = 1e-3
-GRAD_RTOL = 2e-3      # per-tensor ||g - g_ref|| / ||g_ref||  (measured: 2e-4 .. 1.2e-3, see profiles/parity_r1.md)
-FWD_RTOL = 1.5e-3
+LOSS_RTOL = 1e-4
+GRAD_RTOL = 2e-4      # per-tensor ||g - g_ref|| / ||g_ref|| vs the oracle (measured <= 3e-6, profiles/parity_r2.md)
+FWD_RTOL = 1e-4       # forward taps vs the oracle (measured <= 6e-7)
+REF_RTOL = 1e-3       # vs values recorded from the reference itself (north_star's tolerance)
 
 
 def _engine(dims, L, B, p, **kw):
@@ -76,21 +80,23 @@ def test_reference_fixture_replay(name):
         ls = eng.read_losses(s + 1)[s]
         np.testing.assert_allclose(eng.debug_read('corr', (B, B)), G[f's{s}/corr'], rtol=1e-6, atol=1e-7)
         for i in range(2):
-            assert U.rel(eng.debug_read(f'z{i}', (B, L)), G[f's{s}/z{i}']) < FWD_RTOL
-            assert U.rel(eng.debug_read(f'c{i}', (B, L)), G[f's{s}/c{i}']) < FWD_RTOL
-            assert U.rel(eng.debug_read(f'xhat{i}', (B, dims[i])), G[f's{s}/xhat{i}']) < 2 * FWD_RTOL
+            assert U.rel(eng.debug_read(f'z{i}', (B, L)), G[f's{s}/z{i}']) < REF_RTOL
+            assert U.rel(eng.debug_read(f'c{i}', (B, L)), G[f's{s}/c{i}']) < REF_RTOL
+            assert U.rel(eng.debug_read(f'xhat{i}', (B, dims[i])), G[f's{s}/xhat{i}']) < REF_RTOL
         if (s + 1) % len_dl == 0:
             for k, nm in enumerate(names):
                 want = G[f'loss_history/{nm}'][s // len_dl] / (lw[k] if lw else 1)
-                assert abs(ls[k] - want) <= LOSS_RTOL * abs(want) + (1e-4 if nm == 'CosSim' else 1e-7), (nm, ls[k], want)
-        _check_grads(eng.spec, eng.get_grads(), G.grads(s), np.abs(G[f's{s}/corr']).sum() > 0, rtol=3e-3)
-        assert abs(ls[5] - float(G[f's{s}/total_norm'])) < 1e-3 * ls[5]
+                # CosSim: the reference's cdist route leaves fp32 cancellation noise ~1e-7 (|z|^2 + |c|^2) per row
+                # (SURVEY.md App. B-16): absolute floor 1e-4 on that term only
+                assert abs(ls[k] - want) <= REF_RTOL * abs(want) + (1e-4 if nm == 'CosSim' else 1e-7), (nm, ls[k], want)
+        _check_grads(eng.spec, eng.get_grads(), G.grads(s), np.abs(G[f's{s}/corr']).sum() > 0, rtol=REF_RTOL)
+        assert abs(ls[5] - float(G[f's{s}/total_norm'])) < REF_RTOL * ls[5]
     bn = eng.get_bn_stats()
     for k, v in G.buffers(f's{G.n_steps - 1}').items():
         if k.endswith('num_batches_tracked'):
             assert int(bn[k]) == int(v)
         else:
-            np.testing.assert_allclose(bn[k], v, rtol=3e-3, atol=3e-4)
+            np.testing.assert_allclose(bn[k], v, rtol=REF_RTOL, atol=1e-4)
     eng.close()
 
 
@@ -146,7 +152,7 @@ def test_step_vs_oracle(dims, L, B, p, prior, use_f):
         assert U.rel(eng.debug_read(key, want.shape), want) < FWD_RTOL, key
     for k in range(4):
         assert abs(ls[k] - float(ols[k])) <= LOSS_RTOL * abs(float(ols[k])) + 1e-6, (k, ls[k], ols[k])
-    assert abs(ls[5] - otot) < 1e-3 * otot
+    assert abs(ls[5] - otot) < LOSS_RTOL * otot
     worst = _check_grads(eng.spec, eng.get_grads(), [ograds[nm] for nm, _ in orc.spec], np.abs(corr).sum() > 0)
     print(f'dims {dims} worst per-tensor grad rel err {worst:.2e}')
     # post-Adam parameters (first step: update = lr * sign(g) up to eps; compare with an absolute tolerance)
