@@ -478,7 +478,7 @@ def main():
         t = torch.tensor([dt], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    assert np.isfinite(out[4])
+    assert np.isfinite(out[4]), f"non-finite loss at the end of the end-to-end leg: {out}"
     e2e_value = BATCH * Ke * world / dt
     h2d = sum(BATCH * d * 4 for d in DIMS) + 2 * BATCH * 4 + 4
     d2h = 8 * 4

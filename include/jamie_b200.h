@@ -139,6 +139,9 @@ int jb_bench_stage(jb_engine* e, int phase, int iters, float* avg_us, double* fl
  * barrier included), *n_launches = jb_num_phases(). Rewinds the plan cursor first (needs >= 2 plan rows) and takes
  * optimizer steps like jb_train_steps. */
 int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_launches, void* stream);
+/* Detail of the last jb_profile_step: out[4 p + k] for phase p, k = 0 total us (as above), 1 longest CTA work,
+ * 2 mean CTA work, 3 barrier tail (end of the grid barrier - end of the last CTA's work). */
+int jb_profile_detail(jb_engine* e, float* out, int cap);
 
 /* Per-step results of the steps run since the last jb_upload_plan, in plan order. Synchronises `stream`.
  * out[s*8 + k]: k=0..3 the reference's `losses` list (KL incl. 0.032*anneal, Rec, 32*CosSim, F; unweighted by

@@ -67,6 +67,7 @@ SIGNATURES = {
     'jb_phase_name': (C.c_char_p, [C.c_int]),
     'jb_bench_stage': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), _P]),
     'jb_profile_step': (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
+    'jb_profile_detail': (C.c_int, [_P, _P, C.c_int]),
     'jb_read_losses': (C.c_int, [_P, _P, C.c_int, _P]),
     'jb_encode': (C.c_int, [_P, C.c_int, _P, _LL, _LL, _P, _LL, C.c_int, _P]),
     'jb_predict': (C.c_int, [_P, C.c_int, C.c_int, _P, _LL, _LL, _P, _LL, C.c_int, _P]),

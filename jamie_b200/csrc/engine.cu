@@ -137,11 +137,11 @@ struct jb_engine {
   ModActs act[2]{};
   float *corr = nullptr, *corr_t = nullptr, *fblk = nullptr, *fblk_t = nullptr;
   float *lat_r = nullptr, *rowpart = nullptr;
+  float *cmax_part = nullptr, *dmax_part = nullptr, *dyn = nullptr;   // dynamic operand scales (stepk.cuh)
   // step tables at batch size step_B
   std::vector<jb::HgProblem> h_probs;
-  jb::HgProblem* d_probs = nullptr;
-  jb::StepCtx h_ctx{};
-  jb::StepCtx* d_ctx = nullptr;
+  jb::StepParams* h_prm = nullptr;   // the step kernel's parameter block (host copy; passed by value at every launch)
+  jb::StepCtx& h_ctx_ref() { return h_prm->cx; }
   int step_B = 0;
   int grid = 148;            // CTAs of k_step: one per SM
   int accumulate = 0, accumulate_dev = 0;
@@ -167,6 +167,8 @@ struct jb_engine {
   int ev_probs_cap = 0;
   cudaStream_t ev_stream[2]{};
   cudaEvent_t ev_done[2]{}, ev_free[2]{};
+  std::vector<float> prof_gemm;     // last jb_profile_step: per GEMM phase 6 role stamps of CTA 0 (us after the phase began)
+  std::vector<float> prof_detail;   // last jb_profile_step: per phase {total, longest CTA work, mean CTA work, barrier tail} us
   long long launches = 0;
 };
 
@@ -273,11 +275,12 @@ void carve(jb_engine* e, Carver& c) {
       a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
-    a.rec_part = c.take<float>((D + jb::SK_CW - 1) / jb::SK_CW);
+    a.rec_part = c.take<float>(D);   // one partial per slab item of the reconstruction phase (at most D items)
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
   e->lat_r = c.take<float>(B * e->LP); e->rowpart = c.take<float>(2 * B * 8);
+  e->cmax_part = c.take<float>(jb::SK_MAX_CTAS); e->dmax_part = c.take<float>(jb::SK_MAX_CTAS); e->dyn = c.take<float>(8);
 }
 
 // ------------------------------------------------------------------------------------------- step tables
@@ -293,6 +296,7 @@ struct StageSpec {   // one problem of a GEMM phase before its split-K factor is
   const float* bias;
   float out_scale;
   int acc_dynamic;
+  int dyn;           // index into StepCtx::dyn of an extra dynamic output factor, or -1
 };
 
 int build_step(jb_engine* e, int B) {
@@ -318,7 +322,8 @@ int build_step(jb_engine* e, int B) {
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     auto fwd = [&](int stage, HPlanes X, int ldx, const Seg& w, const Seg& b, jb::Parts* out, int ldy, int n_out, int n_in) {
-      st[stage].push_back(StageSpec{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode, jb::EPI_BIAS, bias(b), 1.f, 0});
+      st[stage].push_back(StageSpec{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode, jb::EPI_BIAS, bias(b), 1.f, 0,
+                                    stage == 3 ? 0 : -1});   // the c planes carry the dynamic scale s_c
     };
     fwd(0, a.xp, a.ldD, m.W1, m.b1, &a.y1, a.ld2D, 2 * D, D);
     fwd(1, a.h1, a.ld2D, m.W2, m.b2, &a.y2, a.ldD, D, 2 * D);
@@ -328,7 +333,7 @@ int build_step(jb_engine* e, int B) {
     fwd(5, a.g2, a.ld2D, m.W5, m.b5, &a.xhat, a.ldD, D, 2 * D);
     // dgrad dX[B, N_in] = dY W   (A = dY planes K-major, B = W planes MN-major, K = N_out)
     auto dgrad = [&](int stage, HPlanes dY, int lddy, const Seg& s, jb::Parts* out, int lddx, int n_out, int n_in) {
-      st[stage].push_back(StageSpec{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0});
+      st[stage].push_back(StageSpec{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0, -1});
     };
     dgrad(6, a.dxhat, a.ldD, m.W5, &a.dg2, a.ld2D, D, 2 * D);
     dgrad(7, a.dy4, a.ld2D, m.W4, &a.dg1, a.ldD, 2 * D, D);
@@ -337,15 +342,16 @@ int build_step(jb_engine* e, int B) {
     dgrad(10, a.dy2, a.ldD, m.W2, &a.dh1, a.ld2D, D, 2 * D);
   }
   // wgrad dW[N_out, N_in] = dY^T X / gs  (A = dY planes MN-major, B = X planes MN-major, K = batch); largest first
-  auto wgrad = [&](HPlanes dY, int lddy, HPlanes X, int ldx, const Seg& s, int n_out, int n_in) {
+  auto wgrad = [&](HPlanes dY, int lddy, HPlanes X, int ldx, const Seg& s, int n_out, int n_in, int dyn) {
     int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
-    st[11].push_back(StageSpec{dY, lddy, 1, X, ldx, 1, nullptr, G + s.off, s.ld, n_out, n_in, B, bn, wmode, jb::EPI_STORE, nullptr, inv_gs, 1});
+    st[11].push_back(StageSpec{dY, lddy, 1, X, ldx, 1, nullptr, G + s.off, s.ld, n_out, n_in, B, bn, wmode, jb::EPI_STORE, nullptr, inv_gs, 1, dyn});
   };
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D); wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D);
-    wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D); wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D); }
+    // encoder-side gradients carry the dynamic scale s_b of d[mu | logvar] (dyn 1); dW3's B operand is the c planes (dyn 0)
+    wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D, -1); wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D, -1);
+    wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D, 1); wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D, 1); }
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    wgrad(a.dmp, e->ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D); wgrad(a.dy3, a.ldD, a.cp, e->LP, m.W3, D, L); }
+    wgrad(a.dmp, e->ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D, 1); wgrad(a.dy3, a.ldD, a.cp, e->LP, m.W3, D, L, 0); }
   // split-K factor per problem: fill the grid, at least two k-blocks per partial
   size_t parts_bytes = 0;
   std::vector<std::vector<int>> ks(jb::SK_NUM_GEMM);
@@ -370,11 +376,13 @@ int build_step(jb_engine* e, int B) {
   CU(cudaMemset(e->parts_arena, 0, parts_bytes + 256));
   Carver pc(e->parts_arena);
   e->h_probs.clear();
-  jb::StepCtx& cx = e->h_ctx;
+  if (!e->h_prm) e->h_prm = new jb::StepParams();
+  jb::StepCtx& cx = e->h_prm->cx;
   cx = jb::StepCtx{};
   for (int g = 0; g < jb::SK_NUM_GEMM; ++g) {
     const int first = static_cast<int>(e->h_probs.size());
-    if (st[g].size() > static_cast<size_t>(jb::HG_MAX_PROBS)) return fail("too many problems in a GEMM phase");
+    if (st[g].size() > static_cast<size_t>(jb::HG_MAX_PROBS) || e->h_probs.size() + st[g].size() > static_cast<size_t>(jb::SK_MAX_PROBS))
+      return fail("too many problems in a GEMM phase");
     for (size_t q = 0; q < st[g].size(); ++q) {
       const StageSpec& s = st[g][q];
       const int k = ks[g][q];
@@ -391,13 +399,12 @@ int build_step(jb_engine* e, int B) {
       if (rc) return fail("hgemm problem fill failed (%d) for M%d N%d K%d lda%d ldb%d bn%d mode%d", rc, s.M, s.N, s.K, s.lda, s.ldb, s.bn, s.mode);
       if (hp.ksplit != k && s.out != nullptr) s.out->n = hp.ksplit;
       if (s.acc_dynamic) hp.acc_flag = &e->ctl->accum;
+      if (s.dyn >= 0) hp.dyn_scale = e->dyn + s.dyn;
       e->h_probs.push_back(hp);
     }
     cx.gph[g] = jb::hg_phase_finalize(e->h_probs.data(), first, static_cast<int>(st[g].size()));
   }
-  if (e->d_probs) { cudaFree(e->d_probs); e->d_probs = nullptr; }
-  CU(cudaMalloc(&e->d_probs, e->h_probs.size() * sizeof(jb::HgProblem)));
-  CU(cudaMemcpy(e->d_probs, e->h_probs.data(), e->h_probs.size() * sizeof(jb::HgProblem), cudaMemcpyHostToDevice));
+  for (size_t q = 0; q < e->h_probs.size(); ++q) e->h_prm->probs[q] = e->h_probs[q];
   // ---- the rest of the step context
   cx.B = B; cx.L = L; cx.LP = e->LP; cx.ldmv = e->ldmv;
   for (int i = 0; i < 2; ++i) {
@@ -425,13 +432,37 @@ int build_step(jb_engine* e, int B) {
       l.mask = a.inj_mask[k];
       l.dH = bl[k].dH; l.dYh = bl[k].dY.hi; l.dYl = bl[k].dY.lo;
       l.dgamma = G + bl[k].g->off; l.dbeta = G + bl[k].be->off; l.dbias = G + bl[k].b->off;
+      l.gdyn = k < 2 ? e->dyn + 1 : nullptr;   // encoder layers sit downstream of d[mu | logvar]
       l.N = bl[k].N; l.ld = bl[k].ld; l.layer_id = static_cast<unsigned>(bnidx);
     }
+    M.rec_lcw = 0; M.rec_items = 0;   // set below (both modalities share the slab width of a phase)
+  }
+  // slab width per element-wise phase: 16 columns per CTA item unless that leaves most of the grid idle (then 8); halved
+  // further until the backward slab (2 x B x cw floats) fits the operand ring
+  auto slab_lcw = [&](int n0, int n1) {
+    int lcw = 4;
+    if (((n0 + 15) / 16 + (n1 + 15) / 16) * 10 < e->grid * 6) lcw = 3;
+    while (lcw > 0 && static_cast<size_t>(B) * (1u << lcw) * 8 > static_cast<size_t>(jb::HG_RING_BYTES)) --lcw;
+    return lcw;
+  };
+  if (static_cast<size_t>(B) * 8 > static_cast<size_t>(jb::HG_RING_BYTES)) return fail("batch size %d too large for the slab phases", B);
+  for (int k = 0; k < 4; ++k) {
+    const int lcw = slab_lcw(cx.bn[k][0].N, cx.bn[k][1].N);
+    cx.bn[k][0].lcw = cx.bn[k][1].lcw = lcw;
+  }
+  {
+    const int lcw = slab_lcw(e->D[0], e->D[1]);
+    for (int i = 0; i < 2; ++i) { cx.m[i].rec_lcw = lcw; cx.m[i].rec_items = (e->D[i] + (1 << lcw) - 1) >> lcw; }
   }
   cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
   cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
   cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;
   cx.lat_r = e->lat_r; cx.rowpart = e->rowpart;
+  cx.cmax_part = e->cmax_part; cx.dmax_part = e->dmax_part; cx.dyn = e->dyn;
+  {
+    const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    CU(cudaMemcpy(e->dyn, ones, sizeof ones, cudaMemcpyHostToDevice));
+  }
   cx.theta = e->theta; cx.grad = e->grad; cx.adam_m = e->adam_m; cx.adam_v = e->adam_v;
   cx.theta_hi = e->theta_hi; cx.theta_lo = e->theta_lo; cx.n_flat = e->n_flat;
   cx.sigma = T + e->sigma.off; cx.dsigma = G + e->sigma.off; cx.norm_part = e->norm_part;
@@ -444,8 +475,8 @@ int build_step(jb_engine* e, int B) {
   sc.grad_scale = 1.0f / static_cast<float>(e->cfg.world_size > 0 ? e->cfg.world_size : 1);
   sc.B = B; sc.L = L; sc.D[0] = e->D[0]; sc.D[1] = e->D[1];
   cx.gs = e->gs; cx.inv_gs = inv_gs;
-  cx.probs = e->d_probs;
-  CU(cudaMemcpy(e->d_ctx, &cx, sizeof cx, cudaMemcpyHostToDevice));
+  cx.dbg_repeat = 1;
+  if (const char* pv = getenv("JB_DBG_REPEAT")) { if (atoi(pv) >= 1) cx.dbg_repeat = atoi(pv); }
   e->step_B = B;
   return 0;
 }
@@ -464,10 +495,9 @@ int launch_step(jb_engine* e, int lo, int hi, int nsteps, int use_stage, cudaStr
     ++e->launches;
   }
   CU(cudaMemsetAsync(e->bar, 0, sizeof(unsigned int), s));
-  const jb::StepCtx* cxp = e->d_ctx;
   int row_bias = lo > jb::PH_GATHER ? -1 : 0;
   unsigned int* bar = e->bar;
-  void* args[] = {&cxp, &lo, &hi, &nsteps, &bar, &use_stage, &row_bias, &ts};
+  void* args[] = {e->h_prm, &lo, &hi, &nsteps, &bar, &use_stage, &row_bias, &ts};
   CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
   const int fwd = lo == jb::PH_GATHER ? nsteps : 0, upd = hi == jb::PH_COUNT ? nsteps : 0;
   jb::k_ctl_advance<<<1, 1, 0, s>>>(e->ctl, fwd, upd, fwd > 0 ? 1 : 0);
@@ -664,7 +694,6 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMalloc(&e->norm_part, jb::SK_MAX_CTAS * sizeof(double)));
   CU(cudaMalloc(&e->bar, 128));
   CU(cudaMemset(e->bar, 0, 128));
-  CU(cudaMalloc(&e->d_ctx, sizeof(jb::StepCtx)));
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
   if (const char* pv = getenv("JB_WGRAD_MODE")) e->wgrad_mode = strcmp(pv, "single") == 0 ? jb::HG_SINGLE : jb::HG_MEDIUM;
   if (const char* pv = getenv("JB_MAX_KSPLIT")) { if (atoi(pv) >= 1) e->max_ksplit = atoi(pv); }
@@ -710,10 +739,11 @@ void jb_destroy(jb_engine* e) {
   }
   void* ptrs[] = {e->state_slab, e->grad, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
-                  e->arena, e->parts_arena, e->d_probs, e->d_ctx, e->bar, e->d_ts, e->ev_a, e->ev_b, e->ev_in, e->ev_out,
+                  e->arena, e->parts_arena, e->bar, e->d_ts, e->ev_a, e->ev_b, e->ev_in, e->ev_out,
                   e->d_ev_probs};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 2; ++k) if (e->ev_stream[k]) cudaStreamDestroy(e->ev_stream[k]);
+  delete e->h_prm;
   delete e;
 }
 
@@ -1045,7 +1075,7 @@ const char* jb_phase_name(int ph) {
   static const char* names[jb::PH_COUNT] = {
       "gather+corr", "gemm enc1", "bn1", "gemm enc2", "bn2", "gemm heads", "reparam", "combine", "latloss", "gemm dec1", "bn3",
       "gemm dec2", "bn4", "gemm dec3", "rec", "dgrad W5", "bnb4", "dgrad W4", "bnb3", "dgrad W3", "latbc", "latbz",
-      "dgrad heads+final", "bnb2", "dgrad W2", "bnb1", "wgrad x12", "gradnorm", "adam"};
+      "dmulv planes+final", "dgrad heads", "bnb2", "dgrad W2", "bnb1", "wgrad x12", "gradnorm", "adam"};
   return ph >= 0 && ph < jb::PH_COUNT ? names[ph] : "";
 }
 
@@ -1053,25 +1083,26 @@ const char* jb_phase_name(int ph) {
 // launch includes the kernel's setup, so this is an upper bound of the phase's share of a step). flops: GEMM phases only.
 int jb_bench_stage(jb_engine* e, int phase, int iters, float* avg_us, double* flops, void* stream) {
   if (!e || !avg_us || !flops) return fail("null argument");
-  if (phase < 0 || phase >= jb::PH_COUNT || iters <= 0) return fail("bad phase / iters");
+  if (phase < -1 || phase >= jb::PH_COUNT || iters <= 0) return fail("bad phase / iters");   // -1: an empty launch (setup + teardown only)
   if (!e->plan_B) return fail("jb_upload_plan must be called first");
   if (ensure_step(e, e->plan_B)) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   double fl = 0;
   const int gi = jb::gemm_index(phase);
   if (gi >= 0) {
-    const jb::HgPhase& ph = e->h_ctx.gph[gi];
+    const jb::HgPhase& ph = e->h_prm->cx.gph[gi];
     for (int i = ph.first; i < ph.first + ph.count; ++i)
       fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
   }
-  const jb::StepCtx* cxp = e->d_ctx;
-  int lo = phase, hi = phase + 1, one = 1, zero = 0;
+  int lo = phase < 0 ? 0 : phase, hi = phase + 1, one = 1, zero = 0;
   unsigned int* bar = e->bar;
   unsigned long long* ts = nullptr;
-  void* args[] = {&cxp, &lo, &hi, &one, &bar, &zero, &zero, &ts};
+  void* args[] = {e->h_prm, &lo, &hi, &one, &bar, &zero, &zero, &ts};
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i)
+  int nwarm = 3;
+  if (const char* pv = getenv("JB_STAGE_WARM")) nwarm = atoi(pv);   // 0 under ncu: one profiled launch per phase
+  for (int i = 0; i < nwarm; ++i)
     CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
   CU(cudaEventRecord(a, s));
   for (int i = 0; i < iters; ++i)
@@ -1098,7 +1129,10 @@ int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_laun
   if (iters < 1) return fail("the plan needs at least two rows for a profile");
   if (ensure_step(e, e->plan_B)) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t nts = 1 + static_cast<size_t>(iters + 1) * jb::PH_COUNT;
+  const size_t nhead = 1 + static_cast<size_t>(iters + 1) * jb::PH_COUNT;
+  const size_t ndet = static_cast<size_t>(iters + 1) * jb::PH_COUNT * e->grid * 3;
+  const size_t ngem = static_cast<size_t>(iters + 1) * jb::SK_NUM_GEMM * 8;
+  const size_t nts = nhead + ndet + ngem + static_cast<size_t>(iters + 1) * jb::PH_COUNT * 8;
   if (e->d_ts) { cudaFree(e->d_ts); e->d_ts = nullptr; }
   CU(cudaMalloc(&e->d_ts, nts * 8));
   CU(cudaMemsetAsync(e->d_ts, 0, nts * 8, s));
@@ -1113,10 +1147,66 @@ int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_laun
       const size_t k = 1 + static_cast<size_t>(it) * jb::PH_COUNT + p;
       acc[p] += static_cast<double>(ts[k] - ts[k - 1]) * 1e-3;
     }
+  {  // per-CTA detail
+    const int nc = e->grid;
+    auto det = [&](int it, int p, int cta, int k) { return ts[nhead + ((static_cast<size_t>(it) * jb::PH_COUNT + p) * nc + cta) * 3 + k]; };
+    // SM clock rate from CTA 0: cycles per ns over steps 1 .. iters
+    const double cyc = static_cast<double>(det(iters, jb::PH_COUNT - 1, 0, 1) - det(1, 0, 0, 0));
+    const double ns = static_cast<double>(det(iters, jb::PH_COUNT - 1, 0, 2) - ts[1 + jb::PH_COUNT - 1]);
+    const double ghz = ns > 0 ? cyc / ns : 1.9;
+    // GEMM role stamps of CTA 0 (cycles after the phase began): first TMA issued, last TMA issued, first stage landed,
+    // last stage landed, accumulator final, tile stored
+    e->prof_gemm.assign(jb::SK_NUM_GEMM * 7, 0.f);
+    for (int gi = 0; gi < jb::SK_NUM_GEMM; ++gi)
+      for (int it = 1; it <= iters; ++it) {
+        const unsigned long long* d = &ts[nhead + ndet + (static_cast<size_t>(it) * jb::SK_NUM_GEMM + gi) * 8];
+        for (int k = 0; k < 7; ++k)
+          e->prof_gemm[gi * 7 + k] += static_cast<float>(static_cast<double>(static_cast<long long>(d[k] - d[7])) / ghz * 1e-3 / iters);
+      }
+    if (getenv("JB_PROF_ELEM")) {   // element-wise phase stamps of CTA 0 (BatchNorm forward): cycles after the phase began
+      for (int p : {static_cast<int>(jb::PH_BN1), static_cast<int>(jb::PH_BN2), static_cast<int>(jb::PH_BN3), static_cast<int>(jb::PH_BN4)}) {
+        double a[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int it = 1; it <= iters; ++it) {
+          const unsigned long long* d = &ts[nhead + ndet + ngem + (static_cast<size_t>(it) * jb::PH_COUNT + p) * 8];
+          for (int k = 0; k < 7; ++k) a[k] += static_cast<double>(static_cast<long long>(d[k] - d[7])) / ghz * 1e-3 / iters;
+        }
+        fprintf(stderr, "bn fwd phase %d CTA0: enter %.2f | loads+slab %.2f | colsum1 %.2f | var+colsum2+stats %.2f | gamma/beta %.2f | apply %.2f | sync %.2f\n",
+                p, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+      }
+    }
+    e->prof_detail.assign(jb::PH_COUNT * 4, 0.f);
+    for (int p = 0; p < jb::PH_COUNT; ++p) {
+      double wmax = 0, wavg = 0, tail = 0;
+      for (int it = 1; it <= iters; ++it) {
+        double m = 0, a = 0;
+        unsigned long long latest = 0;
+        for (int c = 0; c < nc; ++c) {
+          const double w = static_cast<double>(det(it, p, c, 1) - det(it, p, c, 0)) / ghz * 1e-3;
+          m = w > m ? w : m; a += w;
+          latest = det(it, p, c, 2) > latest ? det(it, p, c, 2) : latest;
+        }
+        wmax += m; wavg += a / nc;
+        const unsigned long long end = ts[1 + static_cast<size_t>(it) * jb::PH_COUNT + p];
+        tail += end > latest ? static_cast<double>(end - latest) * 1e-3 : 0.0;
+      }
+      e->prof_detail[p * 4 + 0] = static_cast<float>(acc[p] / iters);
+      e->prof_detail[p * 4 + 1] = static_cast<float>(wmax / iters);
+      e->prof_detail[p * 4 + 2] = static_cast<float>(wavg / iters);
+      e->prof_detail[p * 4 + 3] = static_cast<float>(tail / iters);
+    }
+  }
   for (int k = 0; k < 8; ++k) e->nbt[k] += iters + 1;
   e->eval_dirty = true;
   *n_launches = jb::PH_COUNT;
   for (int p = 0; p < jb::PH_COUNT && p < cap; ++p) out_us[p] = static_cast<float>(acc[p] / iters);
+  return 0;
+}
+
+int jb_profile_detail(jb_engine* e, float* out, int cap) {
+  if (!e || !out) return fail("null argument");
+  if (e->prof_detail.empty()) return fail("jb_profile_step has not run");
+  for (size_t k = 0; k < e->prof_detail.size() && k < static_cast<size_t>(cap); ++k) out[k] = e->prof_detail[k];
+  for (size_t k = 0; k < e->prof_gemm.size() && e->prof_detail.size() + k < static_cast<size_t>(cap); ++k) out[e->prof_detail.size() + k] = e->prof_gemm[k];
   return 0;
 }
 

@@ -74,6 +74,7 @@ struct alignas(128) HgProblem {
   const int* acc_flag;     // optional device flag: accumulate if *acc_flag != 0 (gradient accumulation over batches)
   float out_scale;         // exact power of two (1 / loss scale for weight gradients)
   float slope;
+  const float* dyn_scale;  // optional device scalar multiplied into out_scale (inverse of a dynamic operand scale)
 };
 
 struct HgPhase {           // one GEMM phase = a table of problems
@@ -96,7 +97,9 @@ struct HgPipe {
   uint32_t par = 0;        // bit i: parity of the number of fills of slot i (per-slot, because the slot count varies)
   int geom = 0;            // slot size of the previous tile; the ring is re-cut (and drained) when it changes
   uint32_t nf0 = 0, nf1 = 0;   // completed uses of accumulator buffer 0 / 1
+  long long* dbg = nullptr;    // profiling: SM clock stamps of this CTA's first tile of the phase (8 slots) or null
 };
+__device__ __forceinline__ void hg_stamp(const HgPipe& pp, int k) { if (pp.dbg != nullptr) pp.dbg[k] = clock64(); }
 
 // fp16 split of one value (producers of GEMM operands call this)
 __device__ __forceinline__ void h_split(float x, __half& hi, __half& lo) {
@@ -188,9 +191,11 @@ __device__ __forceinline__ HgTile hg_decode(const HgProblem* __restrict__ probs,
 
 // ------------------------------------------------------------------------------------------------ TMA producer warp
 __device__ __forceinline__ void hg_produce(const HgProblem* __restrict__ probs, const HgPhase& ph, int cta, int ncta,
-                                           HgCtrl* ctrl, uint8_t* ring, HgPipe& pp) {
+                                        HgCtrl* ctrl, uint8_t* ring, HgPipe& pp_io, const HgTile* first_tile) {
+  HgPipe pp = pp_io;   // the roles are separate functions (own register allocation); the pipeline state travels by value
+  bool first = true;
   for (int t = cta; t < ph.total_tiles; t += ncta) {
-    const HgTile T = hg_decode(probs, ph, t);
+    const HgTile T = (t == cta && first_tile != nullptr) ? *first_tile : hg_decode(probs, ph, t);
     const HgProblem& P = probs[T.p];
     const int a_mn = P.a_mn, b_mn = P.b_mn;
     const CUtensorMap* const tmAh = &P.tmA_hi;
@@ -233,18 +238,21 @@ __device__ __forceinline__ void hg_produce(const HgProblem* __restrict__ probs, 
         }
       }
       __syncwarp();
+      if (first) { if (kb == 0 && lane_id() == 0) hg_stamp(pp, 1); if (kb == T.num_kb - 1) { if (lane_id() == 0) hg_stamp(pp, 2); first = false; } }
       pp.par ^= 1u << pp.s;
       if (++pp.s == T.nstages) pp.s = 0;
     }
   }
+  pp_io = pp;
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer warp
 __device__ __forceinline__ void hg_mma(const HgProblem* __restrict__ probs, const HgPhase& ph, int cta, int ncta,
-                                       HgCtrl* ctrl, uint8_t* ring, uint32_t tmem_d, HgPipe& pp) {
+                                    HgCtrl* ctrl, uint8_t* ring, uint32_t tmem_d, HgPipe& pp_io, const HgTile* first_tile) {
+  HgPipe pp = pp_io;
   const uint32_t ring_u32 = smem_u32(ring);
   for (int t = cta; t < ph.total_tiles; t += ncta) {
-    const HgTile T = hg_decode(probs, ph, t);
+    const HgTile T = (t == cta && first_tile != nullptr) ? *first_tile : hg_decode(probs, ph, t);
     const HgProblem& P = probs[T.p];
     const int a_mn = P.a_mn, b_mn = P.b_mn, mode = P.mode, bn = T.bn;
     const uint32_t idesc = umma_idesc_f16(HG_BM, bn, a_mn, b_mn);
@@ -277,6 +285,7 @@ __device__ __forceinline__ void hg_mma(const HgProblem* __restrict__ probs, cons
       }
       mbar_wait(&ctrl->full[pp.s], (pp.par >> pp.s) & 1u);
       tc_fence_after();
+      if (t == cta && lane_id() == 0) { if (kb == 0) hg_stamp(pp, 3); if (kb == T.num_kb - 1) hg_stamp(pp, 4); }
       if (elect_one()) {
         const uint32_t sa = ring_u32 + pp.s * T.slot_bytes;
         const uint32_t sb = sa + off_b;
@@ -336,65 +345,68 @@ __device__ __forceinline__ void hg_mma(const HgProblem* __restrict__ probs, cons
       if (++pp.s == T.nstages) pp.s = 0;
     }
   }
+  pp_io = pp;
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue warps
 // e = epilogue warp index 0 .. 7: TMEM lane quadrant q = e & 3 (== warp index & 3), column half = e >> 2.
 __device__ __forceinline__ void hg_epilogue(const HgProblem* __restrict__ probs, const HgPhase& ph, int cta, int ncta,
-                                            HgCtrl* ctrl, uint8_t* stage_base, uint32_t tmem_d, HgPipe& pp, int e, int lane) {
+                                         HgCtrl* ctrl, uint8_t* stage_base, uint32_t tmem_d, HgPipe& pp_io, int e, int lane,
+                                         const HgTile* first_tile) {
+  HgPipe pp = pp_io;
   const int q = e & 3, half = e >> 2;
   uint8_t* const stw = stage_base + e * 4096;
   const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
   const int rsub = lane >> 3, ch = lane & 7;   // read-back mapping: 4 rows x 8 float4 per pass
   for (int t = cta; t < ph.total_tiles; t += ncta) {
-    const HgTile T = hg_decode(probs, ph, t);
+    const HgTile T = (t == cta && first_tile != nullptr) ? *first_tile : hg_decode(probs, ph, t);
     const HgProblem& P = probs[T.p];
     const int bn = T.bn, mode = P.mode, pM = P.M, pN = P.N, ldc = P.ldc, epi = P.epi;
     const int accumulate = P.accumulate | (P.acc_flag != nullptr ? __ldcg(P.acc_flag) : 0);
     float* const pC = P.C + static_cast<long long>(T.ks) * P.part_stride;
     const float* const pbias = T.ks == 0 ? P.bias : nullptr;
-    const float slope = P.slope, out_scale = P.out_scale;
+    const float slope = P.slope, out_scale = P.dyn_scale != nullptr ? P.out_scale * __ldcg(P.dyn_scale) : P.out_scale;
     const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
     const int m0 = T.m0, n0 = T.n0;
 
-    // finish one 32-column block held in v (this thread: row q * 32 + lane of the tile): scale, bias, activation, store
+    // finish one 32-column block held in v (this thread: row q * 32 + lane of the tile): the raw accumulators go through
+    // a swizzled 32 x 32 shared-memory block (16-byte unit j of row r at unit j ^ (r & 7): conflict-free both ways); scale,
+    // bias and activation are applied on the way out, four columns per lane, in a ROLLED loop (the step kernel is bound by
+    // instruction fetch: this used to be 32-wide unrolled code in every epilogue variant).
     auto finish = [&](float (&v)[32], int c0) {
       const int nbase = n0 + c0;
       if (nbase >= pN || m0 + q * 32 >= pM) return;   // warp-uniform
-      if (out_scale != 1.f) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= out_scale;
-      }
-      if (epi != EPI_STORE && pbias != nullptr) {
-        const float bl = (nbase + lane < pN) ? __ldg(pbias + nbase + lane) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
-      }
-      if (epi == EPI_BIAS_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = leaky(v[j], slope);
-      }
-      // row-per-lane -> swizzled 32 x 32 block (16-byte unit j of row r at unit j ^ (r & 7): conflict-free both ways)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(stw + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
+      const int n = nbase + ch * 4;
+      float b4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (epi != EPI_STORE && pbias != nullptr) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+        for (int j = 0; j < 4; ++j)
+          if (n + j < pN) b4[j] = __ldg(pbias + n + j);
+      }
+      const bool vec = vec_ok && n + 4 <= pN;
+      float* dst = pC + static_cast<size_t>(m0 + q * 32 + rsub) * ldc + n;
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it, dst += 4 * static_cast<size_t>(ldc)) {
         const int r = it * 4 + rsub;
-        const int grow = m0 + q * 32 + r;
-        const int n = nbase + ch * 4;
-        float4 x = *reinterpret_cast<const float4*>(stw + r * 128 + ((ch ^ (r & 7)) << 4));
-        if (grow < pM && n < pN) {
-          float* dst = pC + static_cast<size_t>(grow) * ldc + n;
-          if (vec_ok && n + 4 <= pN) {
+        const float4 xr = *reinterpret_cast<const float4*>(stw + r * 128 + ((ch ^ (r & 7)) << 4));
+        if (m0 + q * 32 + r < pM && n < pN) {
+          float xs[4] = {xr.x * out_scale + b4[0], xr.y * out_scale + b4[1], xr.z * out_scale + b4[2], xr.w * out_scale + b4[3]};
+          if (epi == EPI_BIAS_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xs[j] = leaky(xs[j], slope);
+          }
+          if (vec) {
             if (accumulate) {
               const float4 o = *reinterpret_cast<const float4*>(dst);
-              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+              xs[0] += o.x; xs[1] += o.y; xs[2] += o.z; xs[3] += o.w;
             }
-            *reinterpret_cast<float4*>(dst) = x;
+            *reinterpret_cast<float4*>(dst) = make_float4(xs[0], xs[1], xs[2], xs[3]);
           } else {
-            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
             for (int j = 0; j < 4; ++j)
               if (n + j < pN) dst[j] = accumulate ? dst[j] + xs[j] : xs[j];
           }
@@ -430,25 +442,28 @@ __device__ __forceinline__ void hg_epilogue(const HgProblem* __restrict__ probs,
         }
       }
       if (mine) {
-        float v[32];
-        tmem_ld_32x32(lane_base + static_cast<uint32_t>(bn + 32 * half), v);   // small0
-        tmem_ld_wait();
-        if (num_chunks > 1) {
-          float w[32];
-          tmem_ld_32x32(lane_base + static_cast<uint32_t>(3 * bn + 32 * half), w);   // small1
+        {
+          float v[32];
+          tmem_ld_32x32(lane_base + static_cast<uint32_t>(bn + 32 * half), v);   // small0
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
-        }
+          for (int j = 0; j < 32; ++j) run[j] += v[j] * HG_LO_INV;
+          if (num_chunks > 1) {
+            tmem_ld_32x32(lane_base + static_cast<uint32_t>(3 * bn + 32 * half), v);   // small1
+            tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = run[j] + v[j] * HG_LO_INV;
+            for (int j = 0; j < 32; ++j) run[j] += v[j] * HG_LO_INV;
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&ctrl->acce[(num_chunks - 1) & 1]);
           if (num_chunks > 1) mbar_arrive(&ctrl->acce[(num_chunks - 2) & 1]);
         }
-        finish(v, 32 * half);
+        if (t == cta && e == 0 && lane == 0) hg_stamp(pp, 5);
+        finish(run, 32 * half);
+        if (t == cta && e == 0 && lane == 0) hg_stamp(pp, 6);
       } else {
         tc_fence_before();
         __syncwarp();
@@ -488,18 +503,20 @@ __device__ __forceinline__ void hg_epilogue(const HgProblem* __restrict__ probs,
       }
     }
   }
+  pp_io = pp;
 }
 
 // One GEMM phase for the calling CTA: every warp calls this; non-role warps return at once.
 __device__ __forceinline__ void hg_run_phase(const HgProblem* __restrict__ probs, const HgPhase& ph, int cta, int ncta,
                                              HgCtrl* ctrl, uint8_t* ring, uint8_t* stage_base, uint32_t tmem_d, HgPipe& pp,
-                                             int warp, int lane) {
+                                             int warp, int lane, const HgTile* first_tile = nullptr) {
   if (warp == HG_WARP_TMA) {
+    if (lane == 0) hg_stamp(pp, 0);
     fence_proxy_async_global();   // operands written by generic stores of earlier phases (any CTA) -> TMA reads
-    hg_produce(probs, ph, cta, ncta, ctrl, ring, pp);
+    hg_produce(probs, ph, cta, ncta, ctrl, ring, pp, first_tile);
   }
-  else if (warp == HG_WARP_MMA) hg_mma(probs, ph, cta, ncta, ctrl, ring, tmem_d, pp);
-  else if (warp >= HG_WARP_EPI0 && warp < HG_WARP_EPI0 + HG_NEPI) hg_epilogue(probs, ph, cta, ncta, ctrl, stage_base, tmem_d, pp, warp - HG_WARP_EPI0, lane);
+  else if (warp == HG_WARP_MMA) hg_mma(probs, ph, cta, ncta, ctrl, ring, tmem_d, pp, first_tile);
+  else if (warp >= HG_WARP_EPI0 && warp < HG_WARP_EPI0 + HG_NEPI) hg_epilogue(probs, ph, cta, ncta, ctrl, stage_base, tmem_d, pp, warp - HG_WARP_EPI0, lane, first_tile);
 }
 
 // ------------------------------------------------------------------------------------------------ stand-alone kernel

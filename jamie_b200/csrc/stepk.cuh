@@ -17,11 +17,13 @@
 //   ENC2     GEMM  y2 = h1 W2^T + b2 (split-K)             BN2  slab -> h2 planes
 //   HEADS    GEMM  [mu | logvar] = h2 Wmv^T + bmv (split-K)
 //   REPARAM  elements: eps (Philox or injected), z         COMBINE rows: sigma-weighted combine over the nonzeros of
-//            the correspondence rows (+ latent loss partials when F is absent)     LATLOSS rows (only with F)
+//            the correspondence rows (+ latent loss partials when F is absent)     LATLOSS rows: planes of c with their
+//            dynamic scale (+ the F loss partials when F is present)
 //   DEC1..3  GEMMs + BN3, BN4 slabs                         REC  slab: reconstruction loss, d xhat planes, bias grad
 //   DG5, DG4, DG3 dgrad GEMMs + BNB4, BNB3 backward slabs   LATBC, LATBZ rows: latent backward (KL with the reference's
 //            logvar quirk, "CosSim", F loss, combine, reparameterisation) -> d[mu | logvar] planes
-//   DGH      dgrad GEMM of the heads; idle CTAs: loss scalars, d sigma, head bias gradients (FINAL)
+//   LATFIN   d[mu | logvar] planes with their dynamic scale; loss scalars, d sigma, head bias gradients
+//   DGH      dgrad GEMM of the heads
 //   BNB2, DG2, BNB1                                         WGRAD all 12 weight gradients (3-pass, 128 x 256 tiles)
 //   NORM     sum g^2 partials                               ADAM  clip + Adam over the flat buffer + fp16 weight planes
 // The backward pass carries the loss scale `gs` (a power of two): d xhat and the latent loss gradients are multiplied by
@@ -32,16 +34,18 @@
 
 namespace jb {
 
+// Loads of data written by OTHER CTAs earlier in the same launch. The grid barrier's gpu-scope acquire fence invalidates
+// the SM's L1 (CCTL.IVALL), so after the barrier plain loads are coherent. The first version used __ldcg here, which
+// compiles to LDG.E.STRONG.GPU: measured 1.65 us for eight independent L2 hits per thread (~234 cycles each: issued one
+// after the other) instead of one latency for all eight.
+template <class T> __device__ __forceinline__ T sk_ld(const T* p) { return *p; }
 constexpr int SK_THREADS = 512;
 constexpr int SK_WARPS = SK_THREADS / 32;
-constexpr int SK_CW = 16;                          // slab: columns per CTA item
-constexpr int SK_SLOTS = SK_THREADS / SK_CW;       // 32 row slots per column
-constexpr int SK_RG = 4;                           // register path: row groups (4 rows each) per thread, B <= 512
 constexpr int SK_MAX_CTAS = 160;
 
 enum StepPhase : int {
   PH_GATHER = 0, PH_ENC1, PH_BN1, PH_ENC2, PH_BN2, PH_HEADS, PH_REPARAM, PH_COMBINE, PH_LATLOSS, PH_DEC1, PH_BN3, PH_DEC2,
-  PH_BN4, PH_DEC3, PH_REC, PH_DG5, PH_BNB4, PH_DG4, PH_BNB3, PH_DG3, PH_LATBC, PH_LATBZ, PH_DGH, PH_BNB2, PH_DG2, PH_BNB1,
+  PH_BN4, PH_DEC3, PH_REC, PH_DG5, PH_BNB4, PH_DG4, PH_BNB3, PH_DG3, PH_LATBC, PH_LATBZ, PH_LATFIN, PH_DGH, PH_BNB2, PH_DG2, PH_BNB1,
   PH_WGRAD, PH_NORM, PH_ADAM, PH_COUNT
 };
 // index of a GEMM phase in StepCtx::gph, or -1
@@ -58,8 +62,8 @@ struct Parts {       // a GEMM output as split-K partial sums: element e of part
   float* ptr; long long stride; int n;
 };
 __device__ __forceinline__ float ld_parts(const Parts& q, long long e) {
-  float s = __ldcg(q.ptr + e);
-  for (int p = 1; p < q.n; ++p) s += __ldcg(q.ptr + p * q.stride + e);
+  float s = sk_ld(q.ptr + e);
+  for (int p = 1; p < q.n; ++p) s += sk_ld(q.ptr + p * q.stride + e);
   return s;
 }
 
@@ -72,7 +76,9 @@ struct BnLayer {     // one BatchNorm(+LeakyReLU+Dropout) layer of one modality,
   Parts dH;                        // gradient wrt the layer output (dgrad result)
   __half *dYh, *dYl;               // gradient wrt the pre-BN output, operand planes
   float *dgamma, *dbeta, *dbias;
+  const float* gdyn;               // extra dynamic factor of the parameter-gradient writes (encoder layers: dyn[1]) or null
   int N, ld;
+  int lcw;                         // log2 of the columns per slab item
   unsigned layer_id;
 };
 
@@ -90,7 +96,8 @@ struct ModCtx {      // per modality
   Parts xhat;                      // reconstruction [B, ldD]
   __half *dxh, *dxl;               // d loss / d xhat planes
   float* db5;                      // bias gradient of the last decoder Linear
-  float* rec_part;                 // [ceil(D / 16)] partial sums of squares
+  float* rec_part;                 // [rec_items] partial sums of squares (one per slab item of the REC phase)
+  int rec_items, rec_lcw;
   float* dbias_heads;              // [2L]
   int D, ldD;
 };
@@ -106,6 +113,10 @@ struct StepCtx {
   int f_present;
   // latent scratch
   float* lat_r; float* rowpart;
+  // dynamic power-of-two operand scales (fp16 range): per-CTA maxima of |c| and |d mulv|, and the published inverse
+  // scales dyn[0] = 1 / s_c (c planes hold s_c c), dyn[1] = 1 / s_b (d mulv planes and everything downstream of them in
+  // the encoder backward hold s_b times the loss-scaled gradient). Both are exactly 1 unless a value leaves fp16's range.
+  float *cmax_part, *dmax_part, *dyn;
   // parameters / optimizer
   float *theta, *grad, *adam_m, *adam_v; __half *theta_hi, *theta_lo;
   long long n_flat;
@@ -115,10 +126,19 @@ struct StepCtx {
   const float* plan_kl; float* out_loss; Ctl* ctl;
   StepConsts sc;
   float gs, inv_gs;                // loss scale of the backward pass and its inverse
+  int dbg_repeat;                  // 1
   // GEMM tables
-  const HgProblem* probs;
   HgPhase gph[SK_NUM_GEMM];
 };
+// The whole description of a step travels as ONE kernel parameter (constant bank: every phase begins by reading its
+// pointers and sizes, and loads from global memory would each cost an L2 round trip after every grid barrier, because
+// the barrier's acquire invalidates L1). The tensor maps inside are used by TMA straight from parameter space.
+constexpr int SK_MAX_PROBS = 36;
+struct StepParams {
+  StepCtx cx;
+  HgProblem probs[SK_MAX_PROBS];
+};
+static_assert(sizeof(StepParams) <= 32000, "kernel parameter space");
 
 struct StepVars {    // per-step scalars (one copy per CTA in shared memory)
   long long row;
@@ -128,23 +148,6 @@ struct StepVars {    // per-step scalars (one copy per CTA in shared memory)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-// column sums of two per-thread partials over the 32 row slots of each of the 16 slab columns (fixed order), broadcast.
-// Thread t owns column t & 15, slot t >> 4. Must be called by all 512 threads.
-__device__ __forceinline__ void sk_colsum2(float& a, float& b, float* sh, int warp, int lane) {
-  a += __shfl_xor_sync(0xffffffffu, a, 16);
-  b += __shfl_xor_sync(0xffffffffu, b, 16);
-  if (lane < 16) { sh[(2 * warp) * 16 + lane] = a; sh[(2 * warp + 1) * 16 + lane] = b; }
-  __syncthreads();
-  if (warp == 0 && lane < 16) {
-    float x = 0.f, y = 0.f;
-#pragma unroll
-    for (int w = 0; w < SK_WARPS; ++w) { x += sh[(2 * w) * 16 + lane]; y += sh[(2 * w + 1) * 16 + lane]; }
-    sh[lane] = x; sh[16 + lane] = y;
-  }
-  __syncthreads();
-  a = sh[lane & 15]; b = sh[16 + (lane & 15)];
-  __syncthreads();
-}
 __device__ __forceinline__ void st_h4(__half* p, float a, float b, float c, float d, bool lo_of = false) { (void)lo_of;
   const __half2 u = __floats2half2_rn(a, b), v = __floats2half2_rn(c, d);
   uint2 w;
@@ -170,376 +173,416 @@ __device__ __forceinline__ float sk_p_entry(const StepCtx& cx, int i0, int i1) {
   if (cx.p_diag) return i0 == i1 ? __ldg(cx.p_diag + i0) : 0.f;
   return 0.f;
 }
-// P / F blocks of the step (jamie/jamie.py:586-604): one CTA per strip of 32 block rows: row sums, then 32 x 32 tiles.
-__device__ void sk_corr_strip(const StepCtx& cx, const StepVars& sv, int strip, float* scratch, float* tiles, int warp, int lane) {
+// P / F blocks of the step (jamie/jamie.py:586-604): one warp per block row: row sums, then the normalised row of corr
+// (coalesced) and the same values into column `a` of the transposed blocks (the entries are recomputed in the second
+// pass instead of being held in registers: rolled loops, small code). fblk / fblk_t only exist with a dense F.
+__device__ __forceinline__ void sk_corr_row(const StepCtx& cx, long long base, int a, int lane) {
   const int B = cx.B;
-  const long long base = sv.row * B;
-  const int a0 = strip * 32;
-  float* rs_p = scratch;        // [32]
-  float* rs_f = scratch + 32;   // [32]
-  for (int rr = warp; rr < 32; rr += SK_WARPS) {
-    const int ra = a0 + rr;
-    float p = 0.f, f = 0.f;
-    if (ra < B) {
-      const int i0 = cx.m[0].idx[base + ra];
-      for (int b = lane; b < B; b += 32) {
-        const int i1 = cx.m[1].idx[base + b];
-        p += sk_p_entry(cx, i0, i1);
-        if (cx.f_dense) f += __ldg(cx.f_dense + static_cast<long long>(i0) * cx.pn1 + i1);
-      }
+  const int i0 = cx.m[0].idx[base + a];
+  const int* __restrict__ idx1 = cx.m[1].idx + base;
+  const float* __restrict__ pd = cx.p_dense != nullptr ? cx.p_dense + static_cast<long long>(i0) * cx.pn1 : nullptr;
+  const float* __restrict__ fd = cx.f_dense != nullptr ? cx.f_dense + static_cast<long long>(i0) * cx.pn1 : nullptr;
+  const float diag = (pd == nullptr && cx.p_diag != nullptr) ? __ldg(cx.p_diag + i0) : 0.f;   // P = diag(m): entry m[i0] where i1 == i0
+  float p = 0.f, f = 0.f;
+#pragma unroll 1
+  for (int b0 = lane; b0 < B; b0 += 128) {     // four entries in flight per lane
+    int i1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) i1[u] = b0 + 32 * u < B ? idx1[b0 + 32 * u] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i1[u] < 0) continue;
+      p += pd != nullptr ? __ldg(pd + i1[u]) : (i1[u] == i0 ? diag : 0.f);
+      if (fd != nullptr) f += __ldg(fd + i1[u]);
     }
-    p = warp_sum(p); f = warp_sum(f);
-    if (lane == 0) { rs_p[rr] = p == 0.f ? 1.f : p; rs_f[rr] = f == 0.f ? 1.f : f; }
   }
-  __syncthreads();
-  float* tc = tiles + warp * (2 * 32 * 33);
-  float* tf = tc + 32 * 33;
-  for (int b0 = warp * 32; b0 < B; b0 += SK_WARPS * 32) {
-    const int bb = b0 + lane;
-    const int i1 = bb < B ? cx.m[1].idx[base + bb] : 0;
-    for (int r = 0; r < 32; ++r) {
-      const int ra = a0 + r;
-      float c = 0.f, f = 0.f;
-      if (ra < B && bb < B) {
-        const int i0 = cx.m[0].idx[base + ra];
-        const float pv = sk_p_entry(cx, i0, i1) / rs_p[r];
-        if (cx.f_dense) f = __ldg(cx.f_dense + static_cast<long long>(i0) * cx.pn1 + i1) / rs_f[r];
-        c = cx.pf_ratio * pv + (1.f - cx.pf_ratio) * f;
-        cx.corr[static_cast<long long>(ra) * B + bb] = c;
-        cx.fblk[static_cast<long long>(ra) * B + bb] = f;
-      }
-      tc[r * 33 + lane] = c;
-      tf[r * 33 + lane] = f;
+  p = warp_sum(p); f = warp_sum(f);
+  const float rp = p == 0.f ? 1.f : p, rf = f == 0.f ? 1.f : f;
+  const float pfr = cx.pf_ratio;
+  float* crow = cx.corr + static_cast<long long>(a) * B;
+  float* frow = cx.fblk + static_cast<long long>(a) * B;
+#pragma unroll 1
+  for (int b0 = lane; b0 < B; b0 += 128) {
+    int i1[4];
+    float pv[4], fv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) i1[u] = b0 + 32 * u < B ? idx1[b0 + 32 * u] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pv[u] = 0.f; fv[u] = 0.f;
+      if (i1[u] < 0) continue;
+      pv[u] = pd != nullptr ? __ldg(pd + i1[u]) : (i1[u] == i0 ? diag : 0.f);
+      if (fd != nullptr) fv[u] = __ldg(fd + i1[u]);
     }
-    __syncwarp();
-    const int ca = a0 + lane;   // transposed: row index = b, column = a
-    for (int r = 0; r < 32; ++r) {
-      const int rb = b0 + r;
-      if (rb < B && ca < B) {
-        cx.corr_t[static_cast<long long>(rb) * B + ca] = tc[lane * 33 + r];
-        cx.fblk_t[static_cast<long long>(rb) * B + ca] = tf[lane * 33 + r];
-      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i1[u] < 0) continue;
+      const int b = b0 + 32 * u;
+      const float fvn = fv[u] / rf;
+      const float c = pfr * (pv[u] / rp) + (1.f - pfr) * fvn;
+      crow[b] = c;
+      cx.corr_t[static_cast<long long>(b) * B + a] = c;
+      if (fd != nullptr) { frow[b] = fvn; cx.fblk_t[static_cast<long long>(b) * B + a] = fvn; }
     }
-    __syncwarp();
   }
-  fence_proxy_async_smem();   // the tile scratch is operand-ring memory: generic writes before the next TMA writes
-  __syncthreads();
 }
 // x_i[b, :] = data_i[idx_i[row][b], :] (jamie/jamie.py:583) + operand planes; one warp per (modality, row)
-__device__ void sk_gather_rows(const StepCtx& cx, const StepVars& sv, int use_stage, int gw, int nw, int lane) {
+__device__ __forceinline__ void sk_gather_row(const StepCtx& cx, const StepVars& sv, int use_stage, int it, int lane) {
   const int B = cx.B;
-  for (int it = gw; it < 2 * B; it += nw) {
-    const int i = it / B, b = it - i * B;
-    const ModCtx& M = cx.m[i];
-    const float* s;
-    if (use_stage) s = M.stage[sv.host_slot != 0 ? 1 : 0] + static_cast<long long>(b) * M.ldD;
-    else s = M.data + static_cast<long long>(M.idx[sv.row * B + b]) * M.ld_data;
-    const long long o = static_cast<long long>(b) * M.ldD;
-    float* d = M.x + o;
-    __half* dh = M.xh + o;
-    __half* dl = M.xl + o;
-    const int D = M.D;
-    int j0 = 0;
-    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
-      const int nv = D >> 2;
-      for (int j = lane; j < nv; j += 32) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(s) + j);
-        reinterpret_cast<float4*>(d)[j] = v;
-        split4_store(dh + 4 * j, dl + 4 * j, v.x, v.y, v.z, v.w);
-      }
-      j0 = nv << 2;
+  const int i = it / B, b = it - i * B;
+  const ModCtx& M = cx.m[i];
+  const float* s;
+  if (use_stage) s = M.stage[sv.host_slot != 0 ? 1 : 0] + static_cast<long long>(b) * M.ldD;
+  else s = M.data + static_cast<long long>(M.idx[sv.row * B + b]) * M.ld_data;
+  const long long o = static_cast<long long>(b) * M.ldD;
+  float* d = M.x + o;
+  __half* dh = M.xh + o;
+  __half* dl = M.xl + o;
+  const int D = M.D;
+  int j0 = 0;
+  if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+    const int nv = D >> 2;
+    for (int j = lane; j < nv; j += 128) {      // four 16-byte loads in flight per lane
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + 32 * u < nv) v[u] = __ldg(reinterpret_cast<const float4*>(s) + j + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + 32 * u < nv) {
+          reinterpret_cast<float4*>(d)[j + 32 * u] = v[u];
+          split4_store(dh + 4 * (j + 32 * u), dl + 4 * (j + 32 * u), v[u].x, v[u].y, v[u].z, v[u].w);
+        }
     }
-    for (int j = j0 + lane; j < D; j += 32) {
-      const float v = __ldg(s + j);
-      d[j] = v;
-      h_split(v, dh[j], dl[j]);
-    }
+    j0 = nv << 2;
+  }
+  for (int j = j0 + lane; j < D; j += 32) {
+    const float v = __ldg(s + j);
+    d[j] = v;
+    h_split(v, dh[j], dl[j]);
   }
 }
 
-// ------------------------------------------------------------------------------------------------ BatchNorm slabs
-// Linear output Y [B, N] -> BatchNorm1d (batch statistics) -> LeakyReLU(0.01) -> Dropout(p)  (jamie/model.py:151-154 and
-// siblings). A CTA item owns 16 feature columns and all B rows: thread t has column t & 15 and row slot t >> 4; rows in
-// groups of 4 (one Philox call = the keep decisions of 4 rows of one column). REG: B <= 512, the column stays in
-// registers between the statistics and the normalisation; otherwise three passes over L2.
-// apply the BatchNorm affine + LeakyReLU + dropout to one element and write its operand planes
-struct BnFwdApply {
-  float mean, invx, g, be, scale, p;
-  uint32_t thresh;
-  bool inject, reduce_y;
-};
-__device__ __forceinline__ void sk_bn_fwd_elem(const BnLayer& L, const BnFwdApply& A, int r, int c, int ld, float y, uint32_t rk) {
-  const long long o = static_cast<long long>(r) * ld + c;
-  if (A.reduce_y) L.Y.ptr[o] = y;   // the backward slab reads one array
-  const float a = A.g * ((y - A.mean) * A.invx) + A.be;
-  float out = a > 0.f ? a : LRELU * a;
-  if (A.p > 0.f) {
-    const bool keep = A.inject ? (L.mask[static_cast<long long>(r) * L.N + c] != 0) : (rk >= A.thresh);
-    out = keep ? out * A.scale : 0.f;
+// ------------------------------------------------------------------------------------------------ column slabs
+// A CTA item owns cw = 2^lcw feature columns (16 at the headline widths, 8 where that would leave half the grid idle)
+// and all B rows, so BatchNorm statistics are CTA-local. Thread t has column t & (cw - 1) and row slot t >> lcw.
+// The slab is staged in shared memory (the GEMM operand ring is idle in these phases) and walked with ROLLED loops:
+// the first version kept the column in registers with everything unrolled, and ncu showed the phases bound by
+// instruction fetch (stall_no_instruction the top reason: a 400 KB kernel whose phase bodies run once per step).
+// Only the global loads are unrolled (8 rows in flight per thread).
+constexpr int SK_UNR = 8;
+
+// sums a, b over all threads of the CTA that share a column (fixed order), broadcast. All 512 threads must call.
+__device__ __noinline__ void sk_colsum2(float& a, float& b, float* sh, int lcw, int warp, int lane) {
+  const int cw = 1 << lcw;
+  for (int o = 16; o >= cw; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
   }
-  h_split(out, L.Hh[o], L.Hl[o]);
+  if (lane < cw) { sh[warp * 32 + lane] = a; sh[512 + warp * 32 + lane] = b; }
+  __syncthreads();
+  if (warp == 0 && lane < cw) {
+    float x = 0.f, y = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) { x += sh[w * 32 + lane]; y += sh[512 + w * 32 + lane]; }
+    sh[1024 + lane] = x; sh[1056 + lane] = y;
+  }
+  __syncthreads();
+  a = sh[1024 + (lane & (cw - 1))]; b = sh[1056 + (lane & (cw - 1))];
+  __syncthreads();
 }
-template <bool REG>
-__device__ void sk_bn_fwd_item(const BnLayer& L, const StepCtx& cx, const StepVars& sv, int cb, float* sh, int tid, int warp, int lane) {
+__device__ __noinline__ uint4 sk_rand4(uint2 key, unsigned layer_id, int col, int rgroup) { return rand4(key, layer_id, col, rgroup); }
+
+// Linear output Y [B, N] -> BatchNorm1d (batch statistics, two-pass variance) -> LeakyReLU(0.01) -> Dropout(p)
+// (jamie/model.py:151-154 and siblings) -> fp16 operand planes of the next GEMM. Also reduces the split-K partials of Y
+// into partial 0 (the backward slab reads one array) and updates the running statistics.
+__device__ __forceinline__ void sk_bn_fwd_item(const BnLayer& Lr, const StepCtx& cx, const StepVars& sv, int cb, float* slab, float* sh,
+                                            int tid, int warp, int lane, long long* stamp = nullptr) {
+  if (stamp != nullptr && tid == 0) stamp[0] = clock64();
   const int B = cx.B;
-  const float p = cx.sc.dropout;
-  const int c = cb * SK_CW + (tid & (SK_CW - 1));
-  const int slot = tid / SK_CW;
-  const bool cok = c < L.N;
-  const int cc = cok ? c : 0;
-  const int ld = L.ld;
-  const int ngroups = (B + 3) >> 2;
-  float v[REG ? 4 * SK_RG : 1];
+  const int lcw = Lr.lcw, cw = 1 << lcw, slots = SK_THREADS >> lcw;
+  const int cl = tid & (cw - 1), slot = tid >> lcw;
+  const int c = (cb << lcw) + cl;
+  const int N = Lr.N, ld = Lr.ld;
+  const bool cok = c < N;
+  float* const Y = Lr.Y.ptr + (cok ? c : 0);
+  const int nparts = Lr.Y.n;
+  const long long pstride = Lr.Y.stride;
   float s = 0.f, dummy = 0.f;
-  if constexpr (REG) {
+  for (int r0 = slot; r0 < B; r0 += SK_UNR * slots) {
+    float v[SK_UNR];
 #pragma unroll
-    for (int t = 0; t < SK_RG; ++t)
+    for (int k = 0; k < SK_UNR; ++k) {
+      const int r = r0 + k * slots;
+      v[k] = (cok && r < B) ? sk_ld(Y + static_cast<long long>(r) * ld) : 0.f;
+    }
+    for (int p = 1; p < nparts; ++p) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = 4 * (slot + SK_SLOTS * t) + k;
-        v[4 * t + k] = (cok && r < B) ? ld_parts(L.Y, static_cast<long long>(r) * ld + cc) : 0.f;
-        s += v[4 * t + k];
+      for (int k = 0; k < SK_UNR; ++k) {
+        const int r = r0 + k * slots;
+        if (cok && r < B) v[k] += sk_ld(Y + p * pstride + static_cast<long long>(r) * ld);
       }
-  } else {
-    for (int r = slot; r < B; r += SK_SLOTS) s += cok ? ld_parts(L.Y, static_cast<long long>(r) * ld + cc) : 0.f;
-  }
-  sk_colsum2(s, dummy, sh, warp, lane);
-  const float mean = s / static_cast<float>(B);
-  float q = 0.f;
-  if constexpr (REG) {
+    }
 #pragma unroll
-    for (int t = 0; t < SK_RG; ++t)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = 4 * (slot + SK_SLOTS * t) + k;
-        const float d = v[4 * t + k] - mean;
-        q += (r < B) ? d * d : 0.f;
+    for (int k = 0; k < SK_UNR; ++k) {
+      const int r = r0 + k * slots;
+      if (r < B) {
+        s += v[k];
+        slab[(r << lcw) + cl] = v[k];
+        if (nparts > 1 && cok) Y[static_cast<long long>(r) * ld] = v[k];
       }
-  } else {
-    for (int r = slot; r < B; r += SK_SLOTS) {
-      const float d = (cok ? ld_parts(L.Y, static_cast<long long>(r) * ld + cc) : mean) - mean;
-      q += d * d;
     }
   }
+  if (stamp != nullptr && tid == 0) stamp[1] = clock64();
+  sk_colsum2(s, dummy, sh, lcw, warp, lane);
+  if (stamp != nullptr && tid == 0) stamp[2] = clock64();
+  const float mean = s / static_cast<float>(B);
+  float q = 0.f;
+#pragma unroll 4
+  for (int r = slot; r < B; r += slots) {
+    const float d = slab[(r << lcw) + cl] - mean;
+    q += d * d;
+  }
   dummy = 0.f;
-  sk_colsum2(q, dummy, sh, warp, lane);
+  sk_colsum2(q, dummy, sh, lcw, warp, lane);
   const float var = q / static_cast<float>(B);
   const float invx = 1.0f / sqrtf(var + BN_EPS);
   if (slot == 0 && cok) {
-    L.mean[c] = mean;
-    L.invstd[c] = invx;
+    Lr.mean[c] = mean;
+    Lr.invstd[c] = invx;
     const float unb = B > 1 ? var * (static_cast<float>(B) / static_cast<float>(B - 1)) : var;
-    L.run_mean[c] = (1.f - BN_MOM) * L.run_mean[c] + BN_MOM * mean;
-    L.run_var[c] = (1.f - BN_MOM) * L.run_var[c] + BN_MOM * unb;
+    Lr.run_mean[c] = (1.f - BN_MOM) * Lr.run_mean[c] + BN_MOM * mean;
+    Lr.run_var[c] = (1.f - BN_MOM) * Lr.run_var[c] + BN_MOM * unb;
   }
-  BnFwdApply A;
-  A.mean = mean; A.invx = invx;
-  A.g = cok ? __ldg(L.gamma + c) : 0.f; A.be = cok ? __ldg(L.beta + c) : 0.f;
-  A.p = p; A.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  A.inject = sv.inject != 0 && L.mask != nullptr;
-  A.thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
-  A.reduce_y = L.Y.n > 1;
-  if constexpr (REG) {
+  if (stamp != nullptr && tid == 0) stamp[3] = clock64();
+  if (!cok) return;   // no block-wide synchronisation below
+  const float p = cx.sc.dropout;
+  const float g = __ldg(Lr.gamma + c), be = __ldg(Lr.beta + c);
+  if (stamp != nullptr && tid == 0) stamp[4] = clock64() + (g == 12345.f ? 1 : 0);
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const bool inject = sv.inject != 0 && Lr.mask != nullptr;
+  const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
+  const unsigned char* const mask = Lr.mask + c;
+  __half* const Hh = Lr.Hh + c;
+  __half* const Hl = Lr.Hl + c;
+  const uint2 key = sv.key;
+  const unsigned lid = Lr.layer_id;
+  const int ngroups = (B + 3) >> 2;
+#pragma unroll 1
+  for (int gq = slot; gq < ngroups; gq += slots) {
+    uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (p > 0.f && !inject) rnd = sk_rand4(key, lid, c, gq);
+    const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
-    for (int t = 0; t < SK_RG; ++t) {
-      const int gq = slot + SK_SLOTS * t;
-      uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (p > 0.f && !A.inject && 4 * gq < B) rnd = rand4(sv.key, L.layer_id, c, gq);
-      const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = gq * 4 + k;
-        if (r < B && cok) sk_bn_fwd_elem(L, A, r, c, ld, v[4 * t + k], rr[k]);
+    for (int k = 0; k < 4; ++k) {
+      const int r = gq * 4 + k;
+      if (r < B) {
+        const float a = g * ((slab[(r << lcw) + cl] - mean) * invx) + be;
+        float out = a > 0.f ? a : LRELU * a;
+        if (p > 0.f) {
+          const bool keep = inject ? (mask[static_cast<long long>(r) * N] != 0) : (rr[k] >= thresh);
+          out = keep ? out * scale : 0.f;
+        }
+        const long long o = static_cast<long long>(r) * ld;
+        h_split(out, Hh[o], Hl[o]);
       }
     }
-  } else {
-    for (int gq = slot; gq < ngroups; gq += SK_SLOTS) {
-      uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (p > 0.f && !A.inject) rnd = rand4(sv.key, L.layer_id, c, gq);
-      const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = gq * 4 + k;
-        if (r < B && cok) sk_bn_fwd_elem(L, A, r, c, ld, ld_parts(L.Y, static_cast<long long>(r) * ld + c), rr[k]);
-      }
-    }
   }
+  if (stamp != nullptr && tid == 0) stamp[5] = clock64();
 }
 
 // Backward of the slab: dH -> dY (through dropout, LeakyReLU, BatchNorm), dgamma, dbeta; the pre-BN bias gradient is
-// identically zero (BN subtracts the batch mean) and is written as 0.
-struct BnBwdApply {
-  float mean, inv, g, be, scale, p;
-  uint32_t thresh;
-  bool inject;
-};
-// da through dropout and LeakyReLU'; x_hat
-__device__ __forceinline__ void sk_bn_bwd_elem(const BnLayer& L, const BnBwdApply& A, int r, int c, bool ok, float y, float d, uint32_t rk,
-                                               float& h_out, float& d_out) {
-  const float h = (y - A.mean) * A.inv;
-  const float a = A.g * h + A.be;
-  if (A.p > 0.f && ok) {
-    const bool keep = A.inject ? (L.mask[static_cast<long long>(r) * L.N + c] != 0) : (rk >= A.thresh);
-    d = keep ? d * A.scale : 0.f;
-  }
-  d = a > 0.f ? d : LRELU * d;
-  h_out = h; d_out = d;
-}
-template <bool REG>
-__device__ void sk_bn_bwd_item(const BnLayer& L, const StepCtx& cx, const StepVars& sv, int cb, float* sh, int tid, int warp, int lane) {
+// identically zero (BN subtracts the batch mean) and is written as 0. slab holds [B][cw] of d a and [B][cw] of x_hat.
+__device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx& cx, const StepVars& sv, int cb, float* slab, float* sh,
+                                            int tid, int warp, int lane) {
   const int B = cx.B;
-  const float p = cx.sc.dropout;
-  const int c = cb * SK_CW + (tid & (SK_CW - 1));
-  const int slot = tid / SK_CW;
-  const bool cok = c < L.N;
+  const int lcw = Lr.lcw, cw = 1 << lcw, slots = SK_THREADS >> lcw;
+  const int cl = tid & (cw - 1), slot = tid >> lcw;
+  const int c = (cb << lcw) + cl;
+  const int N = Lr.N, ld = Lr.ld;
+  const bool cok = c < N;
   const int cc = cok ? c : 0;
-  const int ld = L.ld;
+  float* const xh_slab = slab + (static_cast<long long>(B) << lcw);
+  const float p = cx.sc.dropout;
+  const float mean = sk_ld(Lr.mean + cc), inv = sk_ld(Lr.invstd + cc);
+  const float g = __ldg(Lr.gamma + cc), be = __ldg(Lr.beta + cc);
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const bool inject = sv.inject != 0 && Lr.mask != nullptr;
+  const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
+  const unsigned char* const mask = Lr.mask + cc;
+  const float* const Y = Lr.Y.ptr + cc;
+  const float* const dH = Lr.dH.ptr + cc;
+  const int nparts = Lr.dH.n;
+  const long long pstride = Lr.dH.stride;
+  const uint2 key = sv.key;
+  const unsigned lid = Lr.layer_id;
   const int ngroups = (B + 3) >> 2;
-  BnBwdApply A;
-  A.mean = __ldcg(L.mean + cc); A.inv = __ldcg(L.invstd + cc);
-  A.g = __ldg(L.gamma + cc); A.be = __ldg(L.beta + cc);
-  A.p = p; A.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  A.inject = sv.inject != 0 && L.mask != nullptr;
-  A.thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
-  float yh[REG ? 4 * SK_RG : 1], da[REG ? 4 * SK_RG : 1];
   float s1 = 0.f, s2 = 0.f;
-  if constexpr (REG) {
+  // two row groups (8 rows) per iteration: all loads first
+#pragma unroll 1
+  for (int g0 = slot; g0 < ngroups; g0 += 2 * slots) {
+    float y[8], d[8];
 #pragma unroll
-    for (int t = 0; t < SK_RG; ++t)
+    for (int k = 0; k < 8; ++k) {
+      const int r = (g0 + (k >> 2) * slots) * 4 + (k & 3);
+      const bool ok = cok && r < B;
+      y[k] = ok ? sk_ld(Y + static_cast<long long>(r) * ld) : mean;
+      d[k] = ok ? sk_ld(dH + static_cast<long long>(r) * ld) : 0.f;
+    }
+    for (int q = 1; q < nparts; ++q) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = 4 * (slot + SK_SLOTS * t) + k;
-        const bool ok = cok && r < B;
-        const long long o = static_cast<long long>(r) * ld + cc;
-        yh[4 * t + k] = ok ? __ldcg(L.Y.ptr + o) : A.mean;
-        da[4 * t + k] = ok ? ld_parts(L.dH, o) : 0.f;
-      }
-#pragma unroll
-    for (int t = 0; t < SK_RG; ++t) {
-      const int gq = slot + SK_SLOTS * t;
-      uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (p > 0.f && !A.inject && 4 * gq < B) rnd = rand4(sv.key, L.layer_id, c, gq);
-      const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = gq * 4 + k;
-        float h, dd;
-        sk_bn_bwd_elem(L, A, r, c, cok && r < B, yh[4 * t + k], da[4 * t + k], rr[k], h, dd);
-        yh[4 * t + k] = h; da[4 * t + k] = dd;
-        s1 += dd;
-        s2 += dd * h;
+      for (int k = 0; k < 8; ++k) {
+        const int r = (g0 + (k >> 2) * slots) * 4 + (k & 3);
+        if (cok && r < B) d[k] += sk_ld(dH + q * pstride + static_cast<long long>(r) * ld);
       }
     }
-  } else {
-    for (int gq = slot; gq < ngroups; gq += SK_SLOTS) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gq = g0 + h * slots;
       uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (p > 0.f && !A.inject) rnd = rand4(sv.key, L.layer_id, c, gq);
+      if (p > 0.f && !inject && gq < ngroups) rnd = sk_rand4(key, lid, c, gq);
       const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = gq * 4 + k;
-        const bool ok = cok && r < B;
-        const long long o = static_cast<long long>(r) * ld + cc;
-        float h, dd;
-        sk_bn_bwd_elem(L, A, r, c, ok, ok ? __ldcg(L.Y.ptr + o) : A.mean, ok ? ld_parts(L.dH, o) : 0.f, rr[k], h, dd);
-        s1 += dd;
-        s2 += dd * h;
+        if (r < B) {
+          const float xhat = (y[4 * h + k] - mean) * inv;
+          const float a = g * xhat + be;
+          float dd = d[4 * h + k];
+          if (p > 0.f && cok) {
+            const bool keep = inject ? (mask[static_cast<long long>(r) * N] != 0) : (rr[k] >= thresh);
+            dd = keep ? dd * scale : 0.f;
+          }
+          dd = a > 0.f ? dd : LRELU * dd;
+          s1 += dd;
+          s2 += dd * xhat;
+          slab[(r << lcw) + cl] = dd;
+          xh_slab[(r << lcw) + cl] = xhat;
+        }
       }
     }
   }
-  sk_colsum2(s1, s2, sh, warp, lane);
-  if (slot == 0 && cok) {
-    const float ig = cx.inv_gs;
-    if (sv.accum) { L.dbeta[c] += s1 * ig; L.dgamma[c] += s2 * ig; }
-    else { L.dbeta[c] = s1 * ig; L.dgamma[c] = s2 * ig; L.dbias[c] = 0.f; }
+  sk_colsum2(s1, s2, sh, lcw, warp, lane);
+  if (!cok) return;
+  if (slot == 0) {
+    const float ig = Lr.gdyn != nullptr ? cx.inv_gs * sk_ld(Lr.gdyn) : cx.inv_gs;
+    if (sv.accum) { Lr.dbeta[c] += s1 * ig; Lr.dgamma[c] += s2 * ig; }
+    else { Lr.dbeta[c] = s1 * ig; Lr.dgamma[c] = s2 * ig; Lr.dbias[c] = 0.f; }
   }
   const float fb = static_cast<float>(B);
-  const float k0 = A.inv * A.g / fb;
-  if constexpr (REG) {
-#pragma unroll
-    for (int t = 0; t < SK_RG; ++t)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = 4 * (slot + SK_SLOTS * t) + k;
-        if (r < B && cok) {
-          const long long o = static_cast<long long>(r) * ld + c;
-          h_split(k0 * (fb * da[4 * t + k] - s1 - yh[4 * t + k] * s2), L.dYh[o], L.dYl[o]);
-        }
-      }
-  } else {
-    for (int gq = slot; gq < ngroups; gq += SK_SLOTS) {
-      uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (p > 0.f && !A.inject) rnd = rand4(sv.key, L.layer_id, c, gq);
-      const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = gq * 4 + k;
-        if (r < B && cok) {
-          const long long o = static_cast<long long>(r) * ld + c;
-          float h, dd;
-          sk_bn_bwd_elem(L, A, r, c, true, __ldcg(L.Y.ptr + o), ld_parts(L.dH, o), rr[k], h, dd);
-          h_split(k0 * (fb * dd - s1 - h * s2), L.dYh[o], L.dYl[o]);
-        }
-      }
-    }
+  const float k0 = inv * g / fb;
+  __half* const dYh = Lr.dYh + c;
+  __half* const dYl = Lr.dYl + c;
+#pragma unroll 4
+  for (int r = slot; r < B; r += slots) {
+    const long long o = static_cast<long long>(r) * ld;
+    h_split(k0 * (fb * slab[(r << lcw) + cl] - s1 - xh_slab[(r << lcw) + cl] * s2), dYh[o], dYl[o]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ reconstruction loss
 // d xhat = gs * w_rec * 2 (xhat - x) / (B D); per-item partial of sum (xhat - x)^2; bias gradient of the last decoder
-// Linear = column sums of d xhat / gs   (jamie/jamie.py:637-643).
-template <bool REG>
-__device__ void sk_rec_item(const ModCtx& M, const StepCtx& cx, const StepVars& sv, int cb, float* sh, int tid, int warp, int lane) {
+// Linear = column sums of d xhat / gs   (jamie/jamie.py:637-643). One pass, no staging.
+__device__ __forceinline__ void sk_rec_item(const ModCtx& M, const StepCtx& cx, const StepVars& sv, int cb, int item, float* sh, int tid,
+                                         int warp, int lane) {
   const int B = cx.B;
-  const int c = cb * SK_CW + (tid & (SK_CW - 1));
-  const int slot = tid / SK_CW;
+  const int lcw = M.rec_lcw, cw = 1 << lcw, slots = SK_THREADS >> lcw;
+  const int cl = tid & (cw - 1), slot = tid >> lcw;
+  const int c = (cb << lcw) + cl;
   const bool cok = c < M.D;
   const int cc = cok ? c : 0;
   const int ld = M.ldD;
   const float kk = cx.gs * cx.sc.w[1] * 2.f / (static_cast<float>(B) * static_cast<float>(M.D));
-  const bool reduce = M.xhat.n > 1;
+  const int nparts = M.xhat.n;
+  const long long pstride = M.xhat.stride;
+  float* const XH = M.xhat.ptr + cc;
+  const float* const X = M.x + cc;
+  __half* const dxh = M.dxh + cc;
+  __half* const dxl = M.dxl + cc;
   float sq = 0.f, cs = 0.f;
-  for (int r0 = slot * 4; r0 < B; r0 += SK_SLOTS * 4) {
-    float xh[4], xx[4];
+#pragma unroll 1
+  for (int r0 = slot; r0 < B; r0 += SK_UNR * slots) {
+    float xh[SK_UNR], xx[SK_UNR];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = r0 + k;
+    for (int k = 0; k < SK_UNR; ++k) {
+      const int r = r0 + k * slots;
       const bool ok = cok && r < B;
-      const long long o = static_cast<long long>(r) * ld + cc;
-      xh[k] = ok ? ld_parts(M.xhat, o) : 0.f;
-      xx[k] = ok ? __ldcg(M.x + o) : 0.f;
+      xh[k] = ok ? sk_ld(XH + static_cast<long long>(r) * ld) : 0.f;
+      xx[k] = ok ? sk_ld(X + static_cast<long long>(r) * ld) : 0.f;
+    }
+    for (int q = 1; q < nparts; ++q) {
+#pragma unroll
+      for (int k = 0; k < SK_UNR; ++k) {
+        const int r = r0 + k * slots;
+        if (cok && r < B) xh[k] += sk_ld(XH + q * pstride + static_cast<long long>(r) * ld);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = r0 + k;
-      const float d = xh[k] - xx[k];
-      sq += d * d;
-      const float gx = kk * d;
-      cs += gx;
-      if (r < B && cok) {
-        const long long o = static_cast<long long>(r) * ld + c;
-        if (reduce) M.xhat.ptr[o] = xh[k];
-        h_split(gx, M.dxh[o], M.dxl[o]);
+    for (int k = 0; k < SK_UNR; ++k) {
+      const int r = r0 + k * slots;
+      if (cok && r < B) {
+        const float d = xh[k] - xx[k];
+        sq += d * d;
+        const float gx = kk * d;
+        cs += gx;
+        const long long o = static_cast<long long>(r) * ld;
+        if (nparts > 1) XH[o] = xh[k];
+        h_split(gx, dxh[o], dxl[o]);
       }
     }
   }
-  sk_colsum2(sq, cs, sh, warp, lane);
+  sk_colsum2(sq, cs, sh, lcw, warp, lane);
   if (warp == 0) {
-    if (lane < SK_CW && cok) {
+    if (lane < cw && cok) {
       const float v = cs * cx.inv_gs;
       M.db5[c] = sv.accum ? M.db5[c] + v : v;
     }
-    float t = (lane < SK_CW && cok) ? sq : 0.f;
+    float t = (lane < cw && cok) ? sq : 0.f;
     t = warp_sum(t);
-    if (lane == 0) M.rec_part[cb] = t;
+    if (lane == 0) M.rec_part[item] = t;
   }
-  (void)REG;
+}
+
+// ------------------------------------------------------------------------------------------------ dynamic operand scales
+// fp16 operand planes overflow above 65504. Post-BatchNorm activations and weights are bounded by construction, the
+// backward pass carries the static loss scale, but two tensors are unbounded: the latent c (z = mu + exp(logvar / 2) eps
+// with a large logvar: observed 1e5 within 60 steps of the 1M-cell benchmark) and d[mu | logvar] (the same exp factor).
+// Their producers record the per-CTA maximum magnitude; the phase that writes the planes (after a grid barrier) derives
+// an exact power-of-two scale from the global maximum, identical in every CTA. s = 1 whenever max <= 2^15.
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// every thread passes its running maximum; writes the CTA maximum to part[cta]. All threads of the CTA must call.
+__device__ __forceinline__ void sk_cta_max_store(float v, float* part, int cta, float* sh, int tid, int warp, int lane) {
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) m = fmaxf(m, sh[w]);
+    part[cta] = m;
+  }
+  __syncthreads();
+}
+// (scale, inverse scale) from the per-CTA maxima; warp-cooperative, same result in every warp of every CTA
+__device__ __forceinline__ float2 sk_dyn_scale(const float* part, int ncta, int lane) {
+  float m = 0.f;
+  for (int i = lane; i < ncta; i += 32) m = fmaxf(m, sk_ld(part + i));
+  m = warp_max(m);
+  if (!(m > 32768.f)) return make_float2(1.f, 1.f);
+  int e = 128;
+  if (m < 3.0e38f) frexpf(m, &e);          // m <= 2^e
+  return make_float2(ldexpf(1.f, 15 - e), ldexpf(1.f, e - 15));
 }
 
 // ------------------------------------------------------------------------------------------------ latent stage
 // eps (injected or Philox Box-Muller) and z = mu + (exp(logvar/2) + 1e-7) eps   (jamie/model.py:230-240); also reduces
 // the split-K partials of the heads GEMM into partial 0.
-__device__ void sk_reparam(const StepCtx& cx, const StepVars& sv, int gt, int nt) {
+__device__ __forceinline__ void sk_reparam(const StepCtx& cx, const StepVars& sv, int gt, int nt) {
   const int B = cx.B, L = cx.L;
   for (int t = gt; t < 2 * B * L; t += nt) {
     const int i = t / (B * L), rem = t - i * B * L, b = rem / L, l = rem - b * L;
@@ -563,20 +606,22 @@ __device__ void sk_reparam(const StepCtx& cx, const StepVars& sv, int gt, int nt
 }
 
 // out[l] (per lane, LAT_MAXT strided) = sum_b M[row, b] * V[b, l], skipping zero entries; also returns the row sum.
+// 128 entries of the row per iteration (four loads in flight per lane), then a ballot loop over the nonzeros.
 __device__ __forceinline__ float sk_row_times(const float* __restrict__ Mrow, const float* __restrict__ V, int B, int LP, int L, int lane,
                                               float (&acc)[LAT_MAXT]) {
 #pragma unroll
   for (int t = 0; t < LAT_MAXT; ++t) acc[t] = 0.f;
   float rs = 0.f;
-  for (int sup = 0; sup < B; sup += 512) {
-    float m[16];
+#pragma unroll 1
+  for (int sup = 0; sup < B; sup += 128) {
+    float m[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const int b = sup + 32 * i + lane;
-      m[i] = b < B ? __ldcg(Mrow + b) : 0.f;
+      m[i] = b < B ? sk_ld(Mrow + b) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 4; ++i) {
       unsigned nz = __ballot_sync(0xffffffffu, m[i] != 0.f);
       while (nz) {
         const int src = __ffs(nz) - 1;
@@ -587,7 +632,7 @@ __device__ __forceinline__ float sk_row_times(const float* __restrict__ Mrow, co
 #pragma unroll
         for (int t = 0; t < LAT_MAXT; ++t) {
           const int l = lane + 32 * t;
-          if (l < L) acc[t] += mv * __ldcg(v + l);
+          if (l < L) acc[t] += mv * sk_ld(v + l);
         }
       }
     }
@@ -597,13 +642,14 @@ __device__ __forceinline__ float sk_row_times(const float* __restrict__ Mrow, co
 
 // combine (jamie/model.py:245-259): c_i = (s_i z_i + s_j C_i z_j) / (s_i + s_j rowsum(C_i)), C_0 = corr, C_1 = corr^T.
 // Without F the latent loss partials need nothing of another row and are emitted here (fuse_loss).
-__device__ void sk_combine(const StepCtx& cx, int gw, int nw, int lane) {
+__device__ __forceinline__ void sk_combine(const StepCtx& cx, int gw, int nw, int lane, int cta, float* sh, int tid, int warp) {
   const int B = cx.B, L = cx.L, LP = cx.LP;
   const int fuse_loss = cx.f_present ? 0 : 1;
+  float cmax = 0.f;
   for (int w = gw; w < 2 * B; w += nw) {
     const int i = w / B, row = w - i * B, j = 1 - i;
     const ModCtx& M = cx.m[i];
-    const float si = __ldcg(cx.sigma + i), sj = __ldcg(cx.sigma + j);
+    const float si = sk_ld(cx.sigma + i), sj = sk_ld(cx.sigma + j);
     const float* Ci = (i == 0 ? cx.corr : cx.corr_t) + static_cast<long long>(row) * B;
     float acc[LAT_MAXT];
     const float rs = sk_row_times(Ci, cx.m[j].z, B, LP, L, lane, acc);
@@ -616,12 +662,12 @@ __device__ void sk_combine(const StepCtx& cx, int gw, int nw, int lane) {
       if (l < L) {
         const long long o = static_cast<long long>(row) * LP + l;
         M.S[o] = acc[t];
-        const float zv = __ldcg(M.z + o);
+        const float zv = sk_ld(M.z + o);
         const float cv = (si * zv + sj * acc[t]) / den;
         M.c[o] = cv;
-        h_split(cv, M.ch[o], M.cl[o]);
+        cmax = fmaxf(cmax, fabsf(cv));
         if (fuse_loss) {
-          const float mu = __ldcg(M.mulv.ptr + static_cast<long long>(row) * cx.ldmv + l);
+          const float mu = sk_ld(M.mulv.ptr + static_cast<long long>(row) * cx.ldmv + l);
           smu += mu * mu;
           const float d = zv - cv;
           scs += d * d;
@@ -637,14 +683,27 @@ __device__ void sk_combine(const StepCtx& cx, int gw, int nw, int lane) {
       }
     }
   }
+  sk_cta_max_store(cmax, cx.cmax_part, cta, sh, tid, warp, lane);
 }
 // Row partial sums (rowpart[i][row][k]): 0: sum mu^2  1: sum (z - c)^2  2: sum r^2 (i = 0)  3: sum g z  4: sum g c  5: sum g S
 // F residual r = c0 - F c1 (jamie/jamie.py:663-665).
-__device__ void sk_latloss(const StepCtx& cx, int gw, int nw, int lane) {
+// Also writes the operand planes of c with the dynamic scale s_c (always; the loss part only when F is present).
+__device__ __forceinline__ void sk_latloss(const StepCtx& cx, int gw, int nw, int lane, int ncta) {
   const int B = cx.B, L = cx.L, LP = cx.LP;
+  const float2 sc = sk_dyn_scale(cx.cmax_part, ncta, lane);
+  if (gw == 0 && lane == 0) cx.dyn[0] = sc.y;
   for (int w = gw; w < 2 * B; w += nw) {
     const int i = w / B, row = w - i * B;
     const ModCtx& M = cx.m[i];
+#pragma unroll
+    for (int t = 0; t < LAT_MAXT; ++t) {
+      const int l = lane + 32 * t;
+      if (l < L) {
+        const long long o = static_cast<long long>(row) * LP + l;
+        h_split(sk_ld(M.c + o) * sc.x, M.ch[o], M.cl[o]);
+      }
+    }
+    if (!cx.f_present) continue;
     float acc[LAT_MAXT];
     if (i == 0) sk_row_times(cx.fblk + static_cast<long long>(row) * B, cx.m[1].c, B, LP, L, lane, acc);
     else {
@@ -657,12 +716,12 @@ __device__ void sk_latloss(const StepCtx& cx, int gw, int nw, int lane) {
       const int l = lane + 32 * t;
       if (l < L) {
         const long long o = static_cast<long long>(row) * LP + l;
-        const float mu = __ldcg(M.mulv.ptr + static_cast<long long>(row) * cx.ldmv + l);
+        const float mu = sk_ld(M.mulv.ptr + static_cast<long long>(row) * cx.ldmv + l);
         smu += mu * mu;
-        const float d = __ldcg(M.z + o) - __ldcg(M.c + o);
+        const float d = sk_ld(M.z + o) - sk_ld(M.c + o);
         scs += d * d;
         if (i == 0) {
-          const float r = __ldcg(M.c + o) - acc[t];
+          const float r = sk_ld(M.c + o) - acc[t];
           cx.lat_r[o] = r;
           sr += r * r;
         }
@@ -676,7 +735,7 @@ __device__ void sk_latloss(const StepCtx& cx, int gw, int nw, int lane) {
   }
 }
 // g_i = d(loss)/dc_i / den_i with d/dc_i = decoder dgrad - k_cos (z_i - c_i) + F term (everything times the loss scale).
-__device__ void sk_latbc(const StepCtx& cx, int gw, int nw, int lane) {
+__device__ __forceinline__ void sk_latbc(const StepCtx& cx, int gw, int nw, int lane) {
   const int B = cx.B, L = cx.L, LP = cx.LP;
   const float k_cos = cx.gs * cx.sc.w[2] * 32.f * 2.f / (static_cast<float>(B) * static_cast<float>(L));
   const float k_f = cx.gs * cx.sc.w[3] * 2.f / (static_cast<float>(B) * static_cast<float>(L));
@@ -689,21 +748,21 @@ __device__ void sk_latbc(const StepCtx& cx, int gw, int nw, int lane) {
 #pragma unroll
       for (int t = 0; t < LAT_MAXT; ++t) acc[t] = 0.f;
     }
-    const float den = __ldcg(M.den + row);
+    const float den = sk_ld(M.den + row);
     float p3 = 0.f, p4 = 0.f, p5 = 0.f;
 #pragma unroll
     for (int t = 0; t < LAT_MAXT; ++t) {
       const int l = lane + 32 * t;
       if (l < L) {
         const long long o = static_cast<long long>(row) * LP + l;
-        const float z = __ldcg(M.z + o), c = __ldcg(M.c + o);
+        const float z = sk_ld(M.z + o), c = sk_ld(M.c + o);
         const float dcd = ld_parts(M.dc, o);
         if (M.dc.n > 1) M.dc.ptr[o] = dcd;
         float dc = dcd - k_cos * (z - c);
-        dc += i == 0 ? k_f * __ldcg(cx.lat_r + o) : -k_f * acc[t];
+        dc += i == 0 ? k_f * sk_ld(cx.lat_r + o) : -k_f * acc[t];
         const float g = dc / den;
         M.g[o] = g;
-        p3 += g * z; p4 += g * c; p5 += g * __ldcg(M.S + o);
+        p3 += g * z; p4 += g * c; p5 += g * sk_ld(M.S + o);
       }
     }
     p3 = warp_sum(p3); p4 = warp_sum(p4); p5 = warp_sum(p5);
@@ -716,15 +775,16 @@ __device__ void sk_latbc(const StepCtx& cx, int gw, int nw, int lane) {
 // dz_i = k_cos (z_i - c_i) + s_i g_i + s_i C_i g_j ; then through the reparameterisation and the KL term
 // (jamie/jamie.py:619-632 with the reference's logvar quirk: only rows 0 and 1 of modality 1's logvar get KL
 // gradient, each scaled by the broadcast over the batch).
-__device__ void sk_latbz(const StepCtx& cx, const StepVars& sv, int gw, int nw, int lane) {
+__device__ __forceinline__ void sk_latbz(const StepCtx& cx, const StepVars& sv, int gw, int nw, int lane, int cta, float* sh, int tid, int warp) {
   const int B = cx.B, L = cx.L, LP = cx.LP;
+  float dmax = 0.f;
   const float k_cos = cx.gs * cx.sc.w[2] * 32.f * 2.f / (static_cast<float>(B) * static_cast<float>(L));
   const float kkl = cx.gs * sv.kl_coef;
   const float fbl = static_cast<float>(B) * static_cast<float>(L);
   for (int w = gw; w < 2 * B; w += nw) {
     const int i = w / B, row = w - i * B, j = 1 - i;
     const ModCtx& M = cx.m[i];
-    const float si = __ldcg(cx.sigma + i);
+    const float si = sk_ld(cx.sigma + i);
     const float* Ci = (i == 0 ? cx.corr : cx.corr_t) + static_cast<long long>(row) * B;
     float acc[LAT_MAXT];
     sk_row_times(Ci, cx.m[j].g, B, LP, L, lane, acc);
@@ -734,32 +794,52 @@ __device__ void sk_latbz(const StepCtx& cx, const StepVars& sv, int gw, int nw, 
       if (l < L) {
         const long long o = static_cast<long long>(row) * LP + l;
         const long long om = static_cast<long long>(row) * cx.ldmv;
-        const float mu = __ldcg(M.mulv.ptr + om + l), lv = __ldcg(M.mulv.ptr + om + L + l);
-        const float dz = k_cos * (__ldcg(M.z + o) - __ldcg(M.c + o)) + si * __ldcg(M.g + o) + si * acc[t];
+        const float mu = sk_ld(M.mulv.ptr + om + l), lv = sk_ld(M.mulv.ptr + om + L + l);
+        const float dz = k_cos * (sk_ld(M.z + o) - sk_ld(M.c + o)) + si * sk_ld(M.g + o) + si * acc[t];
         const float dmu = dz + kkl * mu / fbl;
-        float dlv = dz * __ldcg(M.eps + o) * 0.5f * expf(lv * 0.5f);
+        float dlv = dz * sk_ld(M.eps + o) * 0.5f * expf(lv * 0.5f);
         if (i == 1 && row < 2) dlv += kkl * -0.5f * (1.f - expf(lv)) / static_cast<float>(L);
         M.dmulv[om + l] = dmu;
         M.dmulv[om + L + l] = dlv;
-        h_split(dmu, M.dmh[om + l], M.dml[om + l]);
-        h_split(dlv, M.dmh[om + L + l], M.dml[om + L + l]);
+        dmax = fmaxf(dmax, fmaxf(fabsf(dmu), fabsf(dlv)));
       }
     }
   }
+  sk_cta_max_store(dmax, cx.dmax_part, cta, sh, tid, warp, lane);
+}
+// operand planes of d[mu | logvar] with the dynamic scale s_b (the encoder backward carries it from here on)
+__device__ __forceinline__ void sk_dmulv_planes(const StepCtx& cx, int gt, int nt, int lane, int ncta) {
+  const int B = cx.B, L2 = 2 * cx.L;
+  const float2 sb = sk_dyn_scale(cx.dmax_part, ncta, lane);
+  if (gt == 0) cx.dyn[1] = sb.y;
+  for (int t = gt; t < 2 * B * L2; t += nt) {
+    const int i = t / (B * L2), rem = t - i * B * L2, b = rem / L2, l = rem - b * L2;
+    const ModCtx& M = cx.m[i];
+    const long long o = static_cast<long long>(b) * cx.ldmv + l;
+    h_split(sk_ld(M.dmulv + o) * sb.x, M.dmh[o], M.dml[o]);
+  }
 }
 // FINAL, CTA item 0: loss scalars and d sigma (fixed-order sums); items 1 ..: head bias gradients (16 of the 4L columns).
-__device__ void sk_final_item(const StepCtx& cx, const StepVars& sv, int item, float* sh, int tid, int warp, int lane) {
+__device__ __forceinline__ void sk_final_item(const StepCtx& cx, const StepVars& sv, int item, float* sh, int tid, int warp, int lane) {
   const int B = cx.B, L = cx.L;
-  if (item > 0) {
-    const int col = (item - 1) * SK_CW + (tid & (SK_CW - 1));
-    const int slot = tid / SK_CW;
+  if (item > 0) {   // head bias gradients: column sums of d[mu | logvar] (16 columns per item)
+    const int col = (item - 1) * 16 + (tid & 15);
+    const int slot = tid >> 4;
     const bool cok = col < 4 * L;
     const int i = cok ? col / (2 * L) : 0, cidx = cok ? col - i * 2 * L : 0;
     const float* src = cx.m[i].dmulv + cidx;
     float s = 0.f, dummy = 0.f;
-    if (cok)
-      for (int r = slot; r < B; r += SK_SLOTS) s += __ldcg(src + static_cast<long long>(r) * cx.ldmv);
-    sk_colsum2(s, dummy, sh, warp, lane);
+    for (int r0 = slot; r0 < B; r0 += SK_UNR * 32) {
+      float v[SK_UNR];
+#pragma unroll
+      for (int k = 0; k < SK_UNR; ++k) {
+        const int r = r0 + k * 32;
+        v[k] = (cok && r < B) ? sk_ld(src + static_cast<long long>(r) * cx.ldmv) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < SK_UNR; ++k) s += v[k];
+    }
+    sk_colsum2(s, dummy, sh, 4, warp, lane);
     if (slot == 0 && cok) {
       float* dst = cx.m[i].dbias_heads + cidx;
       const float v = s * cx.inv_gs;
@@ -769,20 +849,33 @@ __device__ void sk_final_item(const StepCtx& cx, const StepVars& sv, int item, f
   }
   float* tot = sh + 64;    // [14]: [i * 7 + k], k = 0..5 the rowpart sums, k = 6: sum_r (g.c)[r] * rowsum_i[r]
   float* aux = sh + 80;    // [0,1]: sum_l (1 + lv - exp lv) of logvar rows 0 / 1 (modality 1); [2,3]: sum (xhat - x)^2
-  if (warp < 14) {
-    const int i = warp / 7, k = warp % 7;
-    float s = 0.f;
-    for (int r = lane; r < B; r += 32) {
-      const float* rp = cx.rowpart + (static_cast<long long>(i) * B + r) * 8;
-      s += k < 6 ? __ldcg(rp + k) : __ldcg(rp + 4) * __ldcg(cx.m[i].rs + r);
+  float* wpart = sh + 96;  // [SK_WARPS][16] per-warp partial sums
+  {
+    // every thread takes rows tid, tid + 512, ... of both modalities: the 8 row partials are two 16-byte loads
+    float acc[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) acc[k] = 0.f;
+    for (int r = tid; r < B; r += SK_THREADS) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4* rp = reinterpret_cast<const float4*>(cx.rowpart + (static_cast<long long>(i) * B + r) * 8);
+        const float4 u = sk_ld(rp), v = sk_ld(rp + 1);
+        const float rs = sk_ld(cx.m[i].rs + r);
+        acc[i * 7 + 0] += u.x; acc[i * 7 + 1] += u.y; acc[i * 7 + 2] += u.z; acc[i * 7 + 3] += u.w;
+        acc[i * 7 + 4] += v.x; acc[i * 7 + 5] += v.y; acc[i * 7 + 6] += v.x * rs;
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) tot[warp] = s;
-  } else if (warp == 14) {
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const float t = warp_sum(acc[k]);
+      if (lane == 0) wpart[warp * 16 + k] = t;
+    }
+  }
+  if (warp == 14) {
     for (int i = 0; i < 2; ++i) {
       float t1 = 0.f;
       for (int l = lane; l < L; l += 32) {
-        const float lv = __ldcg(cx.m[1].mulv.ptr + static_cast<long long>(i) * cx.ldmv + L + l);
+        const float lv = sk_ld(cx.m[1].mulv.ptr + static_cast<long long>(i) * cx.ldmv + L + l);
         t1 += 1.f + lv - expf(lv);
       }
       t1 = warp_sum(t1);
@@ -791,11 +884,18 @@ __device__ void sk_final_item(const StepCtx& cx, const StepVars& sv, int item, f
   } else if (warp == 15) {
     for (int i = 0; i < 2; ++i) {
       float sacc = 0.f;
-      const int nb = (cx.m[i].D + SK_CW - 1) / SK_CW;
-      for (int b = lane; b < nb; b += 32) sacc += __ldcg(cx.m[i].rec_part + b);
+      const int nb = cx.m[i].rec_items;
+      for (int b = lane; b < nb; b += 32) sacc += sk_ld(cx.m[i].rec_part + b);
       sacc = warp_sum(sacc);
       if (lane == 0) aux[2 + i] = sacc;
     }
+  }
+  __syncthreads();
+  if (tid < 14) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) t += wpart[w * 16 + tid];
+    tot[tid] = t;
   }
   __syncthreads();
   if (tid == 0) {
@@ -824,13 +924,19 @@ __device__ void sk_final_item(const StepCtx& cx, const StepVars& sv, int item, f
 }
 
 // ------------------------------------------------------------------------------------------------ clip + Adam
-__device__ void sk_norm(const StepCtx& cx, int cta, int ncta, double* shd, int tid) {
+__device__ __forceinline__ void sk_norm(const StepCtx& cx, int cta, int ncta, double* shd, int tid) {
   const long long n4 = cx.n_flat / 4;
   double s = 0.0;
   const float4* g4 = reinterpret_cast<const float4*>(cx.grad);
-  for (long long i = static_cast<long long>(cta) * SK_THREADS + tid; i < n4; i += static_cast<long long>(ncta) * SK_THREADS) {
-    const float4 v = __ldcg(g4 + i);
-    s += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z + static_cast<double>(v.w) * v.w;
+  const long long stride = static_cast<long long>(ncta) * SK_THREADS;
+  for (long long i0 = static_cast<long long>(cta) * SK_THREADS + tid; i0 < n4; i0 += 4 * stride) {   // 4 loads in flight
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = i0 + u * stride < n4 ? sk_ld(g4 + i0 + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      s += static_cast<double>(v[u].x) * v[u].x + static_cast<double>(v[u].y) * v[u].y + static_cast<double>(v[u].z) * v[u].z +
+           static_cast<double>(v[u].w) * v[u].w;
   }
   shd[tid] = s;
   __syncthreads();
@@ -843,9 +949,9 @@ __device__ void sk_norm(const StepCtx& cx, int cta, int ncta, double* shd, int t
 }
 // every CTA re-reduces the partials in the same order (identical clip coefficient everywhere), then
 // g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
-__device__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid) {
+__device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid) {
   double s = 0.0;
-  for (int i = tid; i < ncta; i += SK_THREADS) s += __ldcg(cx.norm_part + i);
+  for (int i = tid; i < ncta; i += SK_THREADS) s += sk_ld(cx.norm_part + i);
   shd[tid] = s;
   __syncthreads();
   for (int o = SK_THREADS / 2; o > 0; o >>= 1) {
@@ -864,22 +970,34 @@ __device__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta
   const float4* g4 = reinterpret_cast<const float4*>(cx.grad);
   float4* m4 = reinterpret_cast<float4*>(cx.adam_m);
   float4* v4 = reinterpret_cast<float4*>(cx.adam_v);
-  for (long long i = static_cast<long long>(cta) * SK_THREADS + tid; i < n4; i += static_cast<long long>(ncta) * SK_THREADS) {
-    const float4 gg = __ldcg(g4 + i);
-    float4 mm = m4[i], vv = v4[i], tt = t4[i];
-    const float gx[4] = {gg.x * coef, gg.y * coef, gg.z * coef, gg.w * coef};
-    float* mp = reinterpret_cast<float*>(&mm);
-    float* vp = reinterpret_cast<float*>(&vv);
-    float* tp = reinterpret_cast<float*>(&tt);
+  const long long stride = static_cast<long long>(ncta) * SK_THREADS;
+#pragma unroll 1
+  for (long long i0 = static_cast<long long>(cta) * SK_THREADS + tid; i0 < n4; i0 += 2 * stride) {   // 8 loads in flight
+    float4 gg[2], mm[2], vv[2], tt[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mp[k] = mp[k] + (gx[k] - mp[k]) * (1.f - b1);
-      vp[k] = vp[k] * b2 + gx[k] * gx[k] * (1.f - b2);
-      const float denom = sqrtf(vp[k]) * ibc2 + eps;
-      tp[k] = tp[k] - step * (mp[k] / denom);
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) { gg[u] = sk_ld(g4 + i); mm[u] = m4[i]; vv[u] = v4[i]; tt[u] = t4[i]; }
     }
-    m4[i] = mm; v4[i] = vv; t4[i] = tt;
-    split4_store(cx.theta_hi + 4 * i, cx.theta_lo + 4 * i, tt.x, tt.y, tt.z, tt.w);   // next step's GEMM operand planes
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        const float gx[4] = {gg[u].x * coef, gg[u].y * coef, gg[u].z * coef, gg[u].w * coef};
+        float* mp = reinterpret_cast<float*>(&mm[u]);
+        float* vp = reinterpret_cast<float*>(&vv[u]);
+        float* tp = reinterpret_cast<float*>(&tt[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mp[k] = mp[k] + (gx[k] - mp[k]) * (1.f - b1);
+          vp[k] = vp[k] * b2 + gx[k] * gx[k] * (1.f - b2);
+          const float denom = sqrtf(vp[k]) * ibc2 + eps;
+          tp[k] = tp[k] - step * (mp[k] / denom);
+        }
+        m4[i] = mm[u]; v4[i] = vv[u]; t4[i] = tt[u];
+        split4_store(cx.theta_hi + 4 * i, cx.theta_lo + 4 * i, tt[u].x, tt[u].y, tt[u].z, tt[u].w);   // next step's GEMM operand planes
+      }
+    }
   }
 }
 
@@ -902,14 +1020,16 @@ __global__ void k_ctl_advance(Ctl* ctl, int d_cursor, int d_adam, int clear_inje
 // uses optimizer step counts ctl->adam_t + 1 ...; the host advances ctl with k_ctl_advance after the launch.
 // use_stage: the batch rows were copied into ModCtx::stage[ctl->host_slot] (host-batch step). row_bias: -1 for an
 // update-only launch (the cursor was already advanced by the backward launch). ts (optional): CTA 0 records the global
-// timer at kernel start (ts[0]) and at the end of every phase (ts[1 + step * PH_COUNT + phase]).
-__global__ void __launch_bounds__(SK_THREADS, 1) k_step(const StepCtx* __restrict__ cxp, int ph_lo, int ph_hi, int nsteps,
+// timer at kernel start (ts[0]) and at the end of every phase (ts[1 + step * PH_COUNT + phase]); behind those, every CTA
+// records {SM clock at phase begin, SM clock at the end of its work, global time at the end of its work} per phase.
+__global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ StepParams prm, int ph_lo, int ph_hi, int nsteps,
                                                          unsigned int* bar, int use_stage, int row_bias,
                                                          unsigned long long* ts) {
   extern __shared__ uint8_t sk_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~uintptr_t(1023));
   HgCtrl* ctrl = reinterpret_cast<HgCtrl*>(smem);
-  StepVars* svp = reinterpret_cast<StepVars*>(smem + 512);
+  StepVars* svp = reinterpret_cast<StepVars*>(smem + 896);
+  HgTile* first_tiles = reinterpret_cast<HgTile*>(smem + 256);   // [SK_NUM_GEMM] this CTA's first work item of every GEMM phase
   uint8_t* ring = smem + HG_CTRL_BYTES;
   uint8_t* stage = ring + HG_RING_BYTES;
   float* sh = reinterpret_cast<float*>(stage);            // reduction scratch of the element-wise phases (GEMM idle)
@@ -917,18 +1037,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const StepCtx* __restric
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int gw = cta * SK_WARPS + warp, nw = ncta * SK_WARPS;
-  const StepCtx& cx = *cxp;
+  const StepCtx& cx = prm.cx;
+  static_assert(sizeof(HgCtrl) <= 256 && sizeof(HgTile) * SK_NUM_GEMM <= 640 && sizeof(StepVars) <= 128, "control block layout");
+  if (warp == 2 && lane < SK_NUM_GEMM && cta < cx.gph[lane].total_tiles) first_tiles[lane] = hg_decode(prm.probs, cx.gph[lane], cta);
   const uint32_t tmem_d = hg_setup(ctrl, warp, lane);
   HgPipe pp;
   unsigned int target = 0;
   const int B = cx.B;
-  const bool reg = B <= 4 * SK_SLOTS * SK_RG;
   // control block: read once (nothing in this launch writes it)
   const long long cursor0 = cx.ctl->cursor, adam0 = cx.ctl->adam_t;
   const unsigned long long stream0 = cx.ctl->stream_id, seed = cx.ctl->seed;
   const int inject = cx.ctl->inject, accum = cx.ctl->accum, host_slot = cx.ctl->host_slot;
 
   if (ts != nullptr && cta == 0 && tid == 0) ts[0] = globaltimer_ns();
+  long long clk_begin = clock64();
   for (int s = 0; s < nsteps; ++s) {
     if (tid == 0) {
       StepVars v;
@@ -950,77 +1072,110 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const StepCtx* __restric
     const StepVars& sv = *svp;
 
     for (int ph = ph_lo; ph < ph_hi; ++ph) {
-      if (ph == PH_LATLOSS && !cx.f_present) {
-        if (ts != nullptr && cta == 0 && tid == 0) ts[1 + s * PH_COUNT + ph] = globaltimer_ns();
-        continue;
-      }
       const int gi = gemm_index(ph);
       if (gi >= 0) {
-        hg_run_phase(cx.probs, cx.gph[gi], cta, ncta, ctrl, ring, stage, tmem_d, pp, warp, lane);
-        if (ph == PH_DGH) {
-          // FINAL on the CTAs from the top down (idle in this phase at the headline shapes), after their own tiles
-          const int nitems = 1 + (4 * cx.L + SK_CW - 1) / SK_CW;
-          bool any = false;
-          for (int it = 0; it < nitems; ++it) any = any || (ncta - 1 - (it % ncta)) == cta;
-          if (any) {
-            __syncthreads();
-            for (int it = 0; it < nitems; ++it)
-              if ((ncta - 1 - (it % ncta)) == cta) sk_final_item(cx, sv, it, sh, tid, warp, lane);
-          }
+        if (ts != nullptr && cta == 0) {   // role stamps of CTA 0's first tile (profiling)
+          pp.dbg = reinterpret_cast<long long*>(ts + 1 + static_cast<long long>(nsteps) * PH_COUNT * (1 + 3 * ncta)) +
+                   (static_cast<long long>(s) * SK_NUM_GEMM + gi) * 8;
+          if (tid == 0) pp.dbg[7] = clk_begin;
         }
+        hg_run_phase(prm.probs, cx.gph[gi], cta, ncta, ctrl, ring, stage, tmem_d, pp, warp, lane, first_tiles + gi);
       } else {
+       for (int rep = 0; rep < cx.dbg_repeat; ++rep) {   // timing experiments only (JB_DBG_REPEAT): repeats the phase's work
         switch (ph) {
           case PH_GATHER: {
-            const int nstrips = (B + 31) / 32;
-            for (int it = 0; it < nstrips; ++it)
-              if ((ncta - 1 - (it % ncta)) == cta) sk_corr_strip(cx, sv, it, sh, reinterpret_cast<float*>(ring), warp, lane);
-            sk_gather_rows(cx, sv, use_stage, gw, nw, lane);
+            // warp items: B rows of the P / F blocks (from the top of the grid down), then 2 B batch rows
+            const long long base = sv.row * B;
+            for (int it = nw - 1 - gw; it < 3 * B; it += nw) {
+              if (it < B) sk_corr_row(cx, base, it, lane);
+              else sk_gather_row(cx, sv, use_stage, it - B, lane);
+            }
             break;
           }
           case PH_BN1: case PH_BN2: case PH_BN3: case PH_BN4: {
             const int which = ph == PH_BN1 ? 0 : (ph == PH_BN2 ? 1 : (ph == PH_BN3 ? 2 : 3));
-            const int nb0 = (cx.bn[which][0].N + SK_CW - 1) / SK_CW, nb1 = (cx.bn[which][1].N + SK_CW - 1) / SK_CW;
+            const int lcw = cx.bn[which][0].lcw;
+            const int nb0 = (cx.bn[which][0].N + (1 << lcw) - 1) >> lcw, nb1 = (cx.bn[which][1].N + (1 << lcw) - 1) >> lcw;
             for (int it = cta; it < nb0 + nb1; it += ncta) {
               const int i = it >= nb0 ? 1 : 0;
-              if (reg) sk_bn_fwd_item<true>(cx.bn[which][i], cx, sv, it - (i ? nb0 : 0), sh, tid, warp, lane);
-              else sk_bn_fwd_item<false>(cx.bn[which][i], cx, sv, it - (i ? nb0 : 0), sh, tid, warp, lane);
+              long long* est = nullptr;
+              if (ts != nullptr && cta == 0 && it == cta) {
+                est = reinterpret_cast<long long*>(ts + 1 + static_cast<long long>(nsteps) * PH_COUNT * (1 + 3 * ncta) + static_cast<long long>(nsteps) * SK_NUM_GEMM * 8) +
+                      (static_cast<long long>(s) * PH_COUNT + ph) * 8;
+                if (tid == 0) est[7] = clk_begin;
+              }
+              sk_bn_fwd_item(cx.bn[which][i], cx, sv, it - (i ? nb0 : 0), reinterpret_cast<float*>(ring), sh, tid, warp, lane, est);
+              __syncthreads();
+              if (est != nullptr && tid == 0) est[6] = clock64();
             }
+            fence_proxy_async_smem();   // the slab is operand-ring memory: generic writes before the next TMA writes
             break;
           }
           case PH_BNB1: case PH_BNB2: case PH_BNB3: case PH_BNB4: {
             const int which = ph == PH_BNB1 ? 0 : (ph == PH_BNB2 ? 1 : (ph == PH_BNB3 ? 2 : 3));
-            const int nb0 = (cx.bn[which][0].N + SK_CW - 1) / SK_CW, nb1 = (cx.bn[which][1].N + SK_CW - 1) / SK_CW;
+            const int lcw = cx.bn[which][0].lcw;
+            const int nb0 = (cx.bn[which][0].N + (1 << lcw) - 1) >> lcw, nb1 = (cx.bn[which][1].N + (1 << lcw) - 1) >> lcw;
             for (int it = cta; it < nb0 + nb1; it += ncta) {
               const int i = it >= nb0 ? 1 : 0;
-              if (reg) sk_bn_bwd_item<true>(cx.bn[which][i], cx, sv, it - (i ? nb0 : 0), sh, tid, warp, lane);
-              else sk_bn_bwd_item<false>(cx.bn[which][i], cx, sv, it - (i ? nb0 : 0), sh, tid, warp, lane);
+              sk_bn_bwd_item(cx.bn[which][i], cx, sv, it - (i ? nb0 : 0), reinterpret_cast<float*>(ring), sh, tid, warp, lane);
+              __syncthreads();
             }
+            fence_proxy_async_smem();
             break;
           }
           case PH_REC: {
-            const int nb0 = (cx.m[0].D + SK_CW - 1) / SK_CW, nb1 = (cx.m[1].D + SK_CW - 1) / SK_CW;
+            const int lcw = cx.m[0].rec_lcw;
+            const int nb0 = (cx.m[0].D + (1 << lcw) - 1) >> lcw, nb1 = (cx.m[1].D + (1 << lcw) - 1) >> lcw;
             for (int it = cta; it < nb0 + nb1; it += ncta) {
               const int i = it >= nb0 ? 1 : 0;
-              sk_rec_item<true>(cx.m[i], cx, sv, it - (i ? nb0 : 0), sh, tid, warp, lane);
+              sk_rec_item(cx.m[i], cx, sv, it - (i ? nb0 : 0), it - (i ? nb0 : 0), sh, tid, warp, lane);
             }
             break;
           }
           case PH_REPARAM: sk_reparam(cx, sv, cta * SK_THREADS + tid, ncta * SK_THREADS); break;
-          case PH_COMBINE: sk_combine(cx, gw, nw, lane); break;
-          case PH_LATLOSS: sk_latloss(cx, gw, nw, lane); break;
+          case PH_COMBINE: sk_combine(cx, gw, nw, lane, cta, sh, tid, warp); break;
+          case PH_LATLOSS: sk_latloss(cx, gw, nw, lane, ncta); break;
           case PH_LATBC: sk_latbc(cx, gw, nw, lane); break;
-          case PH_LATBZ: sk_latbz(cx, sv, gw, nw, lane); break;
+          case PH_LATBZ: sk_latbz(cx, sv, gw, nw, lane, cta, sh, tid, warp); break;
+          case PH_LATFIN: {
+            // operand planes of d[mu | logvar]; then FINAL (loss scalars, d sigma, head bias gradients) on the CTAs from
+            // the top down
+            sk_dmulv_planes(cx, cta * SK_THREADS + tid, ncta * SK_THREADS, lane, ncta);
+            const int nitems = 1 + (4 * cx.L + 15) / 16;
+            for (int it = 0; it < nitems; ++it)
+              if ((ncta - 1 - (it % ncta)) == cta) sk_final_item(cx, sv, it, sh, tid, warp, lane);
+            break;
+          }
           case PH_NORM: sk_norm(cx, cta, ncta, shd, tid); break;
           case PH_ADAM: sk_adam(cx, sv, cta, ncta, shd, tid); break;
           default: break;
         }
+       }
       }
       const bool last = (ph == ph_hi - 1) && (s == nsteps - 1);
-      if (!last) {
+      if (ts != nullptr) {   // per-CTA detail: SM clock at the end of this CTA's work, global time at that moment
+        __syncthreads();
+        if (tid == 0) {
+          unsigned long long* d = ts + 1 + static_cast<long long>(nsteps) * PH_COUNT + ((static_cast<long long>(s) * PH_COUNT + ph) * ncta + cta) * 3;
+          d[0] = static_cast<unsigned long long>(clk_begin);
+          d[1] = static_cast<unsigned long long>(clock64());
+          d[2] = globaltimer_ns();
+        }
+      }
+      // no barrier between ADAM and the next step's GATHER: the gather / correspondence-block build reads nothing that
+      // the optimizer writes and writes nothing that the optimizer reads, so it overlaps Adam's tail; the barrier after
+      // GATHER orders both before ENC1
+      const bool fused_next = ph == PH_ADAM && ph_lo == PH_GATHER && s + 1 < nsteps;
+      if (!last && !fused_next) {
         target += static_cast<unsigned int>(ncta);
         grid_barrier(bar, target);
+      } else if (fused_next) {
+        __syncthreads();   // the next step's StepVars overwrite this step's
       }
-      if (ts != nullptr && cta == 0 && tid == 0) ts[1 + s * PH_COUNT + ph] = globaltimer_ns();
+      if (ts != nullptr) {
+        if (cta == 0 && tid == 0) ts[1 + s * PH_COUNT + ph] = globaltimer_ns();
+        clk_begin = clock64();
+      }
     }
   }
   hg_teardown(tmem_d, warp);

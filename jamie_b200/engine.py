@@ -236,6 +236,14 @@ class Engine:
         _lib.check(self.lib.jb_profile_step(self.h, int(iters), _ptr(out), 64, C.byref(n), C.c_void_p(stream)))
         return out[:n.value].copy()
 
+    def profile_detail(self):
+        """[phases, 4] of the last profile_step: total, longest CTA work, mean CTA work, barrier tail (us)."""
+        n = int(self.lib.jb_num_phases())
+        out = np.zeros(4 * n + 12 * 7, np.float32)
+        _lib.check(self.lib.jb_profile_detail(self.h, _ptr(out), out.size))
+        self.gemm_stamps = out[4 * n:].reshape(12, 7).copy()   # CTA 0 role stamps of the 12 GEMM phases (us)
+        return out[:4 * n].reshape(n, 4)
+
     def set_grad_accumulate(self, flag):
         _lib.check(self.lib.jb_set_grad_accumulate(self.h, int(bool(flag))))
 

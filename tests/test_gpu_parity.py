@@ -165,6 +165,51 @@ def test_step_vs_oracle(dims, L, B, p, prior, use_f):
     eng.close()
 
 
+def test_large_logvar_dynamic_operand_scale():
+    """fp16 operand planes overflow at 65504; the latent c and d[mu | logvar] are unbounded (z = mu + exp(logvar / 2) eps:
+    the 1M-cell benchmark reached |z| = 1e5 within 60 steps). The step kernel rescales those two operands by an exact,
+    dynamically chosen power of two (stepk.cuh: sk_dyn_scale); here a logvar bias of 24 drives |z| past 1e5 and the
+    step must still agree with the fp32 oracle."""
+    dims, L, B, p = [96, 64], 8, 64, 0.3
+    n = 2 * B
+    rng = np.random.default_rng(15)
+    data = U.synth_pair(n, dims, seed=31)
+    params = U.torch_like_init(dims, L, seed=32)
+    spec = O.param_spec(dims, L)
+    names = [nm for nm, _ in spec]
+    params[names.index('fc_vars.1.bias')][:] = 24.0
+    eng = _engine(dims, L, B, p)
+    eng.set_params(params)
+    for i in range(2):
+        eng.set_dataset(i, data[i])
+    m = (rng.random(n) < 0.5).astype(np.float32)
+    eng.set_prior_diag(m)
+    eng.set_f_dense(None)
+    orc = O.OracleModel(dims, L, dropout=p, params=params)
+    i0 = rng.choice(n, B, replace=False)
+    i1 = np.concatenate([i0[:B // 2], rng.choice(n, B - B // 2, replace=False)])
+    eng.upload_plan(i0[None], i1[None], np.array([0.5]))
+    eps, masks = U.draw_randomness(B, dims, L, p, seed=33)
+    eng.inject(eps, masks)
+    eng.train_steps(1)
+    ls = eng.read_losses(1)[0]
+    x = [data[0][i0], data[1][i1]]
+    P = np.diag(m)
+    Pb = O.corr_block(P, i0, i1)
+    Fb = np.zeros_like(Pb)
+    ols, ograds, otot, fw = orc.train_step(x, Pb.astype(np.float32), Fb, eps, masks, 0.5, None)
+    assert np.abs(fw['c'][1]).max() > 65504.0          # the case really leaves fp16's range
+    taps = U.oracle_taps(fw, orc)
+    for key, want in taps.items():
+        assert U.rel(eng.debug_read(key, want.shape), want) < 1e-3, key
+    assert np.all(np.isfinite(ls[:6]))
+    for k in range(4):
+        assert abs(ls[k] - float(ols[k])) <= 1e-3 * abs(float(ols[k])) + 1e-6, (k, ls[k], ols[k])
+    assert abs(ls[5] - otot) < 1e-3 * otot
+    _check_grads(eng.spec, eng.get_grads(), [ograds[nm] for nm, _ in orc.spec], True, rtol=1e-3)
+    eng.close()
+
+
 def test_philox_statistics_and_determinism():
     dims, L, B, p = [256, 128], 16, 256, 0.6
     n = 1024
