@@ -296,40 +296,42 @@ __device__ __noinline__ uint4 sk_rand4(uint2 key, unsigned layer_id, int col, in
 // Linear output Y [B, N] -> BatchNorm1d (batch statistics, two-pass variance) -> LeakyReLU(0.01) -> Dropout(p)
 // (jamie/model.py:151-154 and siblings) -> fp16 operand planes of the next GEMM. Also reduces the split-K partials of Y
 // into partial 0 (the backward slab reads one array) and updates the running statistics.
+// Code-size rules of the slab phases (the step kernel is bound by INSTRUCTION FETCH: a phase body runs once per step, its
+// code comes from L2 at ~234 cycles per 128-byte line): 32-bit element offsets, clamped indices instead of per-load
+// branches, rolled loops everywhere except the 8 independent loads of a round.
 __device__ __forceinline__ void sk_bn_fwd_item(const BnLayer& Lr, const StepCtx& cx, const StepVars& sv, int cb, float* slab, float* sh,
                                             int tid, int warp, int lane, long long* stamp = nullptr) {
   if (stamp != nullptr && tid == 0) stamp[0] = clock64();
   const int B = cx.B;
   const int lcw = Lr.lcw, cw = 1 << lcw, slots = SK_THREADS >> lcw;
   const int cl = tid & (cw - 1), slot = tid >> lcw;
-  const int c = (cb << lcw) + cl;
   const int N = Lr.N, ld = Lr.ld;
+  const int c = (cb << lcw) + cl;
   const bool cok = c < N;
-  float* const Y = Lr.Y.ptr + (cok ? c : 0);
+  const int cc = cok ? c : N - 1;
+  float* const Y = Lr.Y.ptr + cc;
   const int nparts = Lr.Y.n;
   const long long pstride = Lr.Y.stride;
+  float* const sl = slab + cl;
   float s = 0.f, dummy = 0.f;
+#pragma unroll 1
   for (int r0 = slot; r0 < B; r0 += SK_UNR * slots) {
     float v[SK_UNR];
 #pragma unroll
-    for (int k = 0; k < SK_UNR; ++k) {
-      const int r = r0 + k * slots;
-      v[k] = (cok && r < B) ? sk_ld(Y + static_cast<long long>(r) * ld) : 0.f;
-    }
+    for (int k = 0; k < SK_UNR; ++k) v[k] = sk_ld(Y + min(r0 + k * slots, B - 1) * ld);
+#pragma unroll 1
     for (int p = 1; p < nparts; ++p) {
+      const float* Yp = Y + p * pstride;
 #pragma unroll
-      for (int k = 0; k < SK_UNR; ++k) {
-        const int r = r0 + k * slots;
-        if (cok && r < B) v[k] += sk_ld(Y + p * pstride + static_cast<long long>(r) * ld);
-      }
+      for (int k = 0; k < SK_UNR; ++k) v[k] += sk_ld(Yp + min(r0 + k * slots, B - 1) * ld);
     }
 #pragma unroll
     for (int k = 0; k < SK_UNR; ++k) {
       const int r = r0 + k * slots;
       if (r < B) {
         s += v[k];
-        slab[(r << lcw) + cl] = v[k];
-        if (nparts > 1 && cok) Y[static_cast<long long>(r) * ld] = v[k];
+        sl[r << lcw] = v[k];
+        if (nparts > 1 && cok) Y[r * ld] = v[k];
       }
     }
   }
@@ -340,7 +342,7 @@ __device__ __forceinline__ void sk_bn_fwd_item(const BnLayer& Lr, const StepCtx&
   float q = 0.f;
 #pragma unroll 4
   for (int r = slot; r < B; r += slots) {
-    const float d = slab[(r << lcw) + cl] - mean;
+    const float d = sl[r << lcw] - mean;
     q += d * d;
   }
   dummy = 0.f;
@@ -361,6 +363,7 @@ __device__ __forceinline__ void sk_bn_fwd_item(const BnLayer& Lr, const StepCtx&
   if (stamp != nullptr && tid == 0) stamp[4] = clock64() + (g == 12345.f ? 1 : 0);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const bool inject = sv.inject != 0 && Lr.mask != nullptr;
+  const bool draw = p > 0.f && !inject;
   const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
   const unsigned char* const mask = Lr.mask + c;
   __half* const Hh = Lr.Hh + c;
@@ -371,20 +374,19 @@ __device__ __forceinline__ void sk_bn_fwd_item(const BnLayer& Lr, const StepCtx&
 #pragma unroll 1
   for (int gq = slot; gq < ngroups; gq += slots) {
     uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    if (p > 0.f && !inject) rnd = sk_rand4(key, lid, c, gq);
+    if (draw) rnd = sk_rand4(key, lid, c, gq);
     const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int r = gq * 4 + k;
       if (r < B) {
-        const float a = g * ((slab[(r << lcw) + cl] - mean) * invx) + be;
+        const float a = g * ((sl[r << lcw] - mean) * invx) + be;
         float out = a > 0.f ? a : LRELU * a;
         if (p > 0.f) {
-          const bool keep = inject ? (mask[static_cast<long long>(r) * N] != 0) : (rr[k] >= thresh);
+          const bool keep = inject ? (mask[r * N] != 0) : (rr[k] >= thresh);
           out = keep ? out * scale : 0.f;
         }
-        const long long o = static_cast<long long>(r) * ld;
-        h_split(out, Hh[o], Hl[o]);
+        h_split(out, Hh[r * ld], Hl[r * ld]);
       }
     }
   }
@@ -398,16 +400,18 @@ __device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx&
   const int B = cx.B;
   const int lcw = Lr.lcw, cw = 1 << lcw, slots = SK_THREADS >> lcw;
   const int cl = tid & (cw - 1), slot = tid >> lcw;
-  const int c = (cb << lcw) + cl;
   const int N = Lr.N, ld = Lr.ld;
+  const int c = (cb << lcw) + cl;
   const bool cok = c < N;
-  const int cc = cok ? c : 0;
-  float* const xh_slab = slab + (static_cast<long long>(B) << lcw);
+  const int cc = cok ? c : N - 1;
+  float* const sl = slab + cl;
+  float* const xl = sl + (B << lcw);
   const float p = cx.sc.dropout;
   const float mean = sk_ld(Lr.mean + cc), inv = sk_ld(Lr.invstd + cc);
   const float g = __ldg(Lr.gamma + cc), be = __ldg(Lr.beta + cc);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const bool inject = sv.inject != 0 && Lr.mask != nullptr;
+  const bool draw = p > 0.f && !inject;
   const uint32_t thresh = p > 0.f ? static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f)) : 0u;
   const unsigned char* const mask = Lr.mask + cc;
   const float* const Y = Lr.Y.ptr + cc;
@@ -424,23 +428,21 @@ __device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx&
     float y[8], d[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int r = (g0 + (k >> 2) * slots) * 4 + (k & 3);
-      const bool ok = cok && r < B;
-      y[k] = ok ? sk_ld(Y + static_cast<long long>(r) * ld) : mean;
-      d[k] = ok ? sk_ld(dH + static_cast<long long>(r) * ld) : 0.f;
+      const int o = min((g0 + (k >> 2) * slots) * 4 + (k & 3), B - 1) * ld;
+      y[k] = sk_ld(Y + o);
+      d[k] = sk_ld(dH + o);
     }
+#pragma unroll 1
     for (int q = 1; q < nparts; ++q) {
+      const float* dHq = dH + q * pstride;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = (g0 + (k >> 2) * slots) * 4 + (k & 3);
-        if (cok && r < B) d[k] += sk_ld(dH + q * pstride + static_cast<long long>(r) * ld);
-      }
+      for (int k = 0; k < 8; ++k) d[k] += sk_ld(dHq + min((g0 + (k >> 2) * slots) * 4 + (k & 3), B - 1) * ld);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int gq = g0 + h * slots;
       uint4 rnd = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      if (p > 0.f && !inject && gq < ngroups) rnd = sk_rand4(key, lid, c, gq);
+      if (draw && gq < ngroups) rnd = sk_rand4(key, lid, c, gq);
       const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -448,16 +450,16 @@ __device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx&
         if (r < B) {
           const float xhat = (y[4 * h + k] - mean) * inv;
           const float a = g * xhat + be;
-          float dd = d[4 * h + k];
-          if (p > 0.f && cok) {
-            const bool keep = inject ? (mask[static_cast<long long>(r) * N] != 0) : (rr[k] >= thresh);
+          float dd = cok ? d[4 * h + k] : 0.f;
+          if (p > 0.f) {
+            const bool keep = inject ? (mask[r * N] != 0) : (rr[k] >= thresh);
             dd = keep ? dd * scale : 0.f;
           }
           dd = a > 0.f ? dd : LRELU * dd;
           s1 += dd;
           s2 += dd * xhat;
-          slab[(r << lcw) + cl] = dd;
-          xh_slab[(r << lcw) + cl] = xhat;
+          sl[r << lcw] = dd;
+          xl[r << lcw] = xhat;
         }
       }
     }
@@ -474,10 +476,8 @@ __device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx&
   __half* const dYh = Lr.dYh + c;
   __half* const dYl = Lr.dYl + c;
 #pragma unroll 4
-  for (int r = slot; r < B; r += slots) {
-    const long long o = static_cast<long long>(r) * ld;
-    h_split(k0 * (fb * slab[(r << lcw) + cl] - s1 - xh_slab[(r << lcw) + cl] * s2), dYh[o], dYl[o]);
-  }
+  for (int r = slot; r < B; r += slots)
+    h_split(k0 * (fb * sl[r << lcw] - s1 - xl[r << lcw] * s2), dYh[r * ld], dYl[r * ld]);
 }
 
 // ------------------------------------------------------------------------------------------------ reconstruction loss
@@ -490,7 +490,7 @@ __device__ __forceinline__ void sk_rec_item(const ModCtx& M, const StepCtx& cx, 
   const int cl = tid & (cw - 1), slot = tid >> lcw;
   const int c = (cb << lcw) + cl;
   const bool cok = c < M.D;
-  const int cc = cok ? c : 0;
+  const int cc = cok ? c : M.D - 1;
   const int ld = M.ldD;
   const float kk = cx.gs * cx.sc.w[1] * 2.f / (static_cast<float>(B) * static_cast<float>(M.D));
   const int nparts = M.xhat.n;
@@ -505,17 +505,15 @@ __device__ __forceinline__ void sk_rec_item(const ModCtx& M, const StepCtx& cx, 
     float xh[SK_UNR], xx[SK_UNR];
 #pragma unroll
     for (int k = 0; k < SK_UNR; ++k) {
-      const int r = r0 + k * slots;
-      const bool ok = cok && r < B;
-      xh[k] = ok ? sk_ld(XH + static_cast<long long>(r) * ld) : 0.f;
-      xx[k] = ok ? sk_ld(X + static_cast<long long>(r) * ld) : 0.f;
+      const int o = min(r0 + k * slots, B - 1) * ld;
+      xh[k] = sk_ld(XH + o);
+      xx[k] = sk_ld(X + o);
     }
+#pragma unroll 1
     for (int q = 1; q < nparts; ++q) {
+      const float* XHq = XH + q * pstride;
 #pragma unroll
-      for (int k = 0; k < SK_UNR; ++k) {
-        const int r = r0 + k * slots;
-        if (cok && r < B) xh[k] += sk_ld(XH + q * pstride + static_cast<long long>(r) * ld);
-      }
+      for (int k = 0; k < SK_UNR; ++k) xh[k] += sk_ld(XHq + min(r0 + k * slots, B - 1) * ld);
     }
 #pragma unroll
     for (int k = 0; k < SK_UNR; ++k) {
@@ -525,9 +523,8 @@ __device__ __forceinline__ void sk_rec_item(const ModCtx& M, const StepCtx& cx, 
         sq += d * d;
         const float gx = kk * d;
         cs += gx;
-        const long long o = static_cast<long long>(r) * ld;
-        if (nparts > 1) XH[o] = xh[k];
-        h_split(gx, dxh[o], dxl[o]);
+        if (nparts > 1) XH[r * ld] = xh[k];
+        h_split(gx, dxh[r * ld], dxl[r * ld]);
       }
     }
   }
