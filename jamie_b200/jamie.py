@@ -532,12 +532,12 @@ class JAMIE(UnionCom):
 
     # ------------------------------------------------------------------------------------------------ metrics
     def test_closer(self, integrated_data, distance_metric=None):
-        """FOSCTTM (jamie/jamie.py:892-913)"""
-        from .evaluation import foscttm
-        return foscttm(integrated_data[0], integrated_data[1])
+        """Test fraction of samples closer than the true match (jamie/jamie.py:892-913; prints ``foscttm: ...``)"""
+        from .evaluation import test_closer
+        return test_closer(integrated_data, distance_metric=distance_metric)
 
     def test_LabelTA(self, integrated_data, datatype, k=None, return_k=False):
-        """Label transfer accuracy (jamie/jamie.py:943-961)"""
+        """Label transfer accuracy, k defaulting to 20% of the average class size (jamie/jamie.py:943-961)"""
         from .evaluation import label_transfer_accuracy
         return label_transfer_accuracy(integrated_data, datatype, k=k, return_k=return_k)
 

@@ -104,15 +104,50 @@ def test_constructor_surface_and_validation():
 
 
 def test_metrics():
-    from jamie_b200.evaluation import foscttm, imputation_correlation, label_transfer_accuracy
+    """The metrics against the reference's own formulas (jamie/evaluation.py:65-85, 114-132; jamie/jamie.py:943-961)
+    restated with the sklearn calls the reference makes."""
+    import contextlib
+    import io
+    from sklearn.metrics import pairwise_distances
+    from sklearn.neighbors import KNeighborsClassifier
+    from jamie_b200 import evaluation as E
     rng = np.random.default_rng(0)
-    a = rng.normal(size=(50, 4))
-    assert foscttm(a, a) == 0.0
-    assert 0.3 < foscttm(a, rng.normal(size=(50, 4))) < 0.7
-    y = (a[:, 0] > 0).astype(int)
-    assert label_transfer_accuracy([a, a + 0.01 * rng.normal(size=a.shape)], [y, y], k=1) > 0.95
-    r = imputation_correlation(a * 2 + 1, a)
+    a = rng.normal(size=(60, 4))
+    b = a + 0.4 * rng.normal(size=a.shape)
+
+    def ref_foscttm(x):
+        d = pairwise_distances(np.concatenate(x, axis=0), metric='euclidean')
+        size = x[0].shape[0]
+        cnt = 0
+        for i in range(size):
+            loc = d[i][size:]
+            cnt += np.sum(loc < loc[i])
+            loc = d[size + i][:size]
+            cnt += np.sum(loc < loc[i])
+        return cnt / (2 * size ** 2)
+
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        got = E.test_closer([a, b])
+    assert buf.getvalue().startswith('foscttm: ')              # the reference prints this line
+    assert got == pytest.approx(ref_foscttm([a, b]), abs=1e-12)
+    assert E.test_closer([a, a], verbose=False) == 0.0
+    assert E.test_closer([a, b], distance_metric=lambda x: pairwise_distances(x, metric='euclidean'), verbose=False) == got
+    # label transfer: unequal set sizes and label sets, default k = int(.2 * min(len) / n_classes(concat))
+    y0 = rng.integers(0, 3, size=60)
+    emb1 = rng.normal(size=(45, 4))
+    y1 = rng.integers(1, 4, size=45)
+    emb0 = a + np.eye(4)[y0 % 4] * 2
+    for k in (None, 1, 5):
+        kk = int(.2 * 45 / 4) if k is None else k
+        knn = KNeighborsClassifier(n_neighbors=kk).fit(emb1, y1)
+        want = float(np.mean(knn.predict(emb0) == y0))
+        acc, k_used = E.label_transfer_accuracy([emb0, emb1], [y0, y1], k=k, return_k=True)
+        assert k_used == kk and acc == pytest.approx(want, abs=1e-12)
+    assert E.test_LabelTA([emb0, emb1], [y0, y1], verbose=False) == E.label_transfer_accuracy([emb0, emb1], [y0, y1], k=5)
+    r = E.imputation_correlation(a * 2 + 1, a)
     np.testing.assert_allclose(r, 1.0)
+    assert E.mean_feature_r(np.c_[a, a[:, :1]], np.c_[a, np.ones((60, 1))]) == pytest.approx(1.0)
 
 
 def test_kl_anneal_and_chunk_bound():
