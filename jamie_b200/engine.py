@@ -55,6 +55,9 @@ class Engine:
 
     def close(self):
         if getattr(self, 'h', None):
+            from . import utilities
+            if utilities._GPU_PROJECTOR is self:
+                utilities.set_gpu_projector(None)
             self.lib.jb_destroy(self.h)
             self.h = None
 
@@ -235,6 +238,35 @@ class Engine:
         n = C.c_int()
         _lib.check(self.lib.jb_profile_step(self.h, int(iters), _ptr(out), 64, C.byref(n), C.c_void_p(stream)))
         return out[:n.value].copy()
+
+    def pca_project(self, X, components, mean, m, sdev, stream=0):
+        """((X - mean) @ components.T - m) / sdev on the GPU (jb_pca_project: error-compensated split GEMM, fp32-class):
+        the PCA projection + scalar standardisation of ``preclass.transform`` (jamie/utilities.py:660-670). Host arrays
+        in, host fp32 array out."""
+        X = np.ascontiguousarray(X, np.float32)
+        comp = np.ascontiguousarray(components, np.float32)
+        mu = np.ascontiguousarray(mean, np.float32)
+        n, d = X.shape
+        k = comp.shape[0]
+        assert comp.shape[1] == d and mu.shape[0] == d
+        out = np.empty((n, k), np.float32)
+        _lib.check(self.lib.jb_pca_project(self.h, _ptr(X), n, d, _ptr(comp), _ptr(mu), k, float(m), float(sdev), _ptr(out), 0,
+                                           C.c_void_p(stream)))
+        return out
+
+    def pca_inverse(self, Z, components, mean, m, sdev, stream=0):
+        """(Z * sdev + m) @ components + mean on the GPU (jb_pca_inverse): ``preclass.inverse_transform``
+        (jamie/utilities.py:672-678)."""
+        Z = np.ascontiguousarray(Z, np.float32)
+        comp = np.ascontiguousarray(components, np.float32)
+        mu = np.ascontiguousarray(mean, np.float32)
+        n, k = Z.shape
+        d = comp.shape[1]
+        assert comp.shape[0] == k and mu.shape[0] == d
+        out = np.empty((n, d), np.float32)
+        _lib.check(self.lib.jb_pca_inverse(self.h, _ptr(Z), n, k, _ptr(comp), _ptr(mu), d, float(m), float(sdev), _ptr(out), 0,
+                                           C.c_void_p(stream)))
+        return out
 
     def profile_detail(self):
         """[phases, 4] of the last profile_step: total, longest CTA work, mean CTA work, barrier tail (us)."""

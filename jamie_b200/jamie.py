@@ -286,8 +286,9 @@ class JAMIE(UnionCom):
         rank, world = _dist_info()
         timer = time_logger()
 
-        # ---- preprocessing (jamie/jamie.py:433-469): PCA fit on the host, standardise, keep the inverse
-        pca_list, pca_inv_list = [], []
+        # ---- preprocessing (jamie/jamie.py:433-469): the PCA is FIT on the host (sklearn, as in the reference); the
+        # projection + standardisation of the whole dataset runs on the GPU once the engine exists (below)
+        pca_list, pca_inv_list, cols = [], [], []
         dims_req = self.pca_dim if self.pca_dim is not None else [None] * self.dataset_num
         for dim, data in zip(dims_req, self.dataset):
             if dim is not None:
@@ -299,12 +300,13 @@ class JAMIE(UnionCom):
                 pca = make_pca(dim)
                 sample = pca.fit_transform(data)
                 pre = preclass(sample, pca=pca)
+                cols.append(int(sample.shape[1]))
             else:
                 pre = preclass(data, axis=0)
+                cols.append(int(np.shape(data)[1]))
             pca_list.append(pre.transform)
             pca_inv_list.append(pre.inverse_transform)
-        self.dataset = [f(x) for f, x in zip(pca_list, self.dataset)]
-        self.col = [x.shape[1] for x in self.dataset]
+        self.col = cols
 
         # ---- model + optimizer state (jamie/jamie.py:471-481)
         self.model = self.model_class(self.col, self.output_dim, preprocessing=pca_list,
@@ -345,8 +347,10 @@ class JAMIE(UnionCom):
                              loss_weights=self.loss_weights, pf_ratio=self.PF_Ratio,
                              seed=(self.manual_seed or 0) * 1000003 + rank, device=dev, world_size=world)
         eng = self.engine
-        self.model.attach_engine(eng)
+        self.model.attach_engine(eng)      # also routes preclass PCA projections through the engine (jb_pca_project)
         self.model.push_to_engine()
+        # ingest: PCA projection + standardisation of every cell (jamie/jamie.py:458-459)
+        self.dataset = [f(x) for f, x in zip(pca_list, self.dataset)]
         stream = self._stream()
         for i in range(2):
             eng.set_dataset(i, np.asarray(self.dataset[i][lo[i]:hi[i]], np.float32), stream)

@@ -58,6 +58,8 @@ class edModelVar(nn.Module):
 
     def attach_engine(self, engine):
         object.__setattr__(self, '_engine', engine)
+        from .utilities import set_gpu_projector
+        set_gpu_projector(engine)   # preclass PCA projections of this process now run on the engine's GPU
 
     def engine(self):
         return self.__dict__.get('_engine', None)

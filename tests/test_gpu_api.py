@@ -50,6 +50,36 @@ def test_fit_transform_end_to_end(capsys):
     assert np.nanmean(imputation_correlation(pred1, data[1])) > 0.7
 
 
+def test_ingest_pca_projection_runs_on_the_engine():
+    """``preclass.transform`` / ``inverse_transform`` (jamie/utilities.py:660-678) reach jb_pca_project /
+    jb_pca_inverse from the product path (ingest in fit_transform, modal_predict in both directions) and agree with the
+    reference's float64 host arithmetic to fp32 rounding."""
+    from jamie import JAMIE
+    from jamie_b200 import utilities as Ut
+    data, _ = _mmdma_like(n=200, dims=(150, 90), seed=3)
+    jm = JAMIE(output_dim=8, batch_size=64, pca_dim=[24, 20], epoch_DNN=20, min_epochs=5, use_f_tilde=False)
+    jm.fit_transform(dataset=data)
+    eng = jm.engine
+    assert Ut._GPU_PROJECTOR is eng
+    l0 = eng.launch_count()
+    gpu_pre = [jm.model.preprocessing[i](data[i]) for i in range(2)]
+    assert eng.launch_count() > l0                                   # kernels of this engine did the projection
+    imp_gpu = jm.modal_predict(data[0], 0)
+    Ut.set_gpu_projector(None)                                       # the reference's host path (sklearn, float64)
+    try:
+        host_pre = [jm.model.preprocessing[i](data[i]) for i in range(2)]
+        for i in range(2):
+            assert gpu_pre[i].shape == host_pre[i].shape and gpu_pre[i].dtype == np.float64
+            assert np.abs(gpu_pre[i] - host_pre[i]).max() < 2e-5 * max(1.0, np.abs(host_pre[i]).max())
+            np.testing.assert_allclose(jm.dataset[i], host_pre[i], atol=2e-5 * max(1.0, np.abs(host_pre[i]).max()))
+        imp_host = jm.modal_predict(data[0], 0)                      # host pre-processing and inverse, same GPU network
+    finally:
+        Ut.set_gpu_projector(eng)
+    assert U.rel(imp_gpu, imp_host) < 1e-4
+    jm.engine.close()
+    assert Ut._GPU_PROJECTOR is None
+
+
 def test_save_load_roundtrip(tmp_path):
     from jamie import JAMIE
     data, _ = _mmdma_like(n=120, dims=(60, 40), seed=1)

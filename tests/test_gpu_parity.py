@@ -210,6 +210,122 @@ def test_large_logvar_dynamic_operand_scale():
     eng.close()
 
 
+def _post_adam_check(spec, got, want, corr_nonzero=True):
+    noise = U.PRE_BN_BIAS | (set() if corr_nonzero else {'sigma'})
+    for (nm, _), g, w in zip(spec, got, want):
+        if nm in noise:
+            continue
+        bad = np.abs(g - w) > 2e-4
+        assert bad.mean() < 2e-3, (nm, bad.mean())     # sign flips of near-zero gradients only (first Adam step = lr * sign)
+
+
+def test_data_parallel_step_equals_averaged_gradient_update():
+    """R ranks == one update with the gradient averaged over the ranks, per-rank BatchNorm statistics.
+    Two engines (world_size = 2) play the two ranks on one GPU: each runs jb_step_backward on its own shard / batch /
+    randomness, the flat gradient buffers are summed in place (what the NCCL all-reduce does), each runs
+    jb_step_update (which scales by 1 / world_size, clips the AVERAGED gradient's norm and applies Adam). Both ranks must
+    end with bit-identical parameters, equal to the oracle's clip + Adam on the averaged oracle gradients."""
+    import torch
+    dims, L, B, p, R = [96, 64], 8, 64, 0.3, 2
+    n = R * 2 * B
+    rng = np.random.default_rng(40)
+    data = U.synth_pair(n, dims, seed=41)
+    params = U.torch_like_init(dims, L, seed=42)
+    m = (rng.random(n) < 0.5).astype(np.float32)
+    orc = O.OracleModel(dims, L, dropout=p, params=params)
+    engines, ograds, olosses = [], [], []
+    for r in range(R):
+        lo, hi = r * n // R, (r + 1) * n // R
+        eng = _engine(dims, L, B, p, world_size=R)
+        eng.set_params(params)
+        for i in range(2):
+            eng.set_dataset(i, data[i][lo:hi])
+        eng.set_prior_diag(m[lo:hi])
+        eng.set_f_dense(None)
+        i0 = rng.choice(hi - lo, B, replace=False)
+        i1 = np.concatenate([i0[:B // 2], rng.choice(hi - lo, B - B // 2, replace=False)])
+        eng.upload_plan(i0[None], i1[None], np.array([0.4]))
+        eps, masks = U.draw_randomness(B, dims, L, p, seed=50 + r)
+        eng.inject(eps, masks)
+        eng.step_backward()
+        engines.append(eng)
+        x = [data[0][lo:hi][i0], data[1][lo:hi][i1]]
+        Pb = O.corr_block(np.diag(m[lo:hi]), i0, i1).astype(np.float32)
+        fw = orc.forward_train(x, Pb, eps, masks, update_buffers=False)
+        olosses.append(orc.losses(fw, np.zeros_like(Pb), 0.4))
+        ograds.append(orc.backward(fw, np.zeros_like(Pb), 0.4, [1, 1, 1, 1]))
+    gts = [e.grad_tensor() for e in engines]
+    torch.cuda.synchronize()
+    total = gts[0] + gts[1]
+    for g in gts:
+        g.copy_(total)                                  # all-reduce (SUM) of the flat gradient buffer + loss tail
+    torch.cuda.synchronize()
+    for e in engines:
+        e.step_update()
+    avg = {k: ((ograds[0][k].astype(np.float64) + ograds[1][k]) / R).astype(np.float32) for k in ograds[0]}
+    onorm = orc.clip_adam(avg)
+    got = [e.get_params() for e in engines]
+    for a, b in zip(got[0], got[1]):
+        np.testing.assert_array_equal(a, b)            # every rank applies the same update
+    _check_grads(engines[0].spec, [g / R for g in engines[0].get_grads()], [avg[nm] for nm, _ in orc.spec], True)
+    for e in engines:
+        ls = e.read_losses(1)[0]
+        assert abs(ls[5] - onorm) < LOSS_RTOL * onorm  # clip norm of the averaged gradient
+    for r in range(R):
+        ls = engines[r].read_losses(1)[0]
+        for k in range(4):
+            assert abs(ls[k] - float(olosses[r][k])) <= LOSS_RTOL * abs(float(olosses[r][k])) + 1e-6
+    _post_adam_check(orc.spec, got[0], orc.param_list())
+    for e in engines:
+        e.close()
+
+
+def test_batch_step_false_accumulates_over_the_epoch():
+    """``batch_step=False`` (jamie/jamie.py:744-749): gradients of every batch of the epoch accumulate, ONE clip + Adam
+    step per epoch, Adam's step count advances once per epoch (not once per backward pass)."""
+    dims, L, B, p, nb = [80, 48], 8, 32, 0.25, 3
+    n = 4 * B
+    rng = np.random.default_rng(60)
+    data = U.synth_pair(n, dims, seed=61)
+    params = U.torch_like_init(dims, L, seed=62)
+    m = np.ones(n, np.float32)
+    eng = _engine(dims, L, B, p)
+    eng.set_params(params)
+    for i in range(2):
+        eng.set_dataset(i, data[i])
+    eng.set_prior_diag(m)
+    eng.set_f_dense(None)
+    orc = O.OracleModel(dims, L, dropout=p, params=params)
+    idx = np.stack([rng.choice(n, B, replace=False) for _ in range(2 * nb)])
+    eng.upload_plan(idx, idx, np.full(2 * nb, 0.3))
+    for epoch in range(2):
+        acc = None
+        for b in range(nb):
+            s = epoch * nb + b
+            eps, masks = U.draw_randomness(B, dims, L, p, seed=70 + s)
+            eng.set_grad_accumulate(b != 0)
+            eng.inject(eps, masks)
+            eng.step_backward()
+            x = [data[0][idx[s]], data[1][idx[s]]]
+            Pb = np.eye(B, dtype=np.float32)
+            fw = orc.forward_train(x, Pb, eps, masks)
+            orc.losses(fw, np.zeros_like(Pb), 0.3)
+            g = orc.backward(fw, np.zeros_like(Pb), 0.3, [1, 1, 1, 1])
+            acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+        _check_grads(eng.spec, eng.get_grads(), [acc[nm] for nm, _ in orc.spec], True)
+        eng.step_update()
+        onorm = orc.clip_adam(acc)
+        assert eng.get_adam_state()[2] == epoch + 1 == orc.adam_t
+        assert abs(eng.read_losses(2 * nb)[epoch * nb + nb - 1][5] - onorm) < LOSS_RTOL * onorm
+    # second epoch's update is not a sign step any more: compare the parameters directly
+    for (nm, _), got, want in zip(orc.spec, eng.get_params(), orc.param_list()):
+        if nm in U.PRE_BN_BIAS:
+            continue
+        assert np.abs(got - want).max() < 3e-4, nm
+        assert U.rel(got - np.asarray(params[[k for k, _ in orc.spec].index(nm)]), want - np.asarray(params[[k for k, _ in orc.spec].index(nm)])) < 0.05, nm
+    eng.close()
+
+
 def test_philox_statistics_and_determinism():
     dims, L, B, p = [256, 128], 16, 256, 0.6
     n = 1024
