@@ -7,9 +7,9 @@ model forward, the four losses, backward, clip, Adam) is one CUDA-graph launch p
 numpy batch sampler (same draws, same order as the reference, so a seeded run visits the same cells), the epoch
 bookkeeping, early stopping and printing.
 
-Out of scope ("next" rows): estimating F with ``Prime_Dual`` / ``compute_distances``
-(jamie/jamie.py:224-414, 839-890) and the tsne projection branch.  ``use_f_tilde=True`` without a supplied
-``match_result`` therefore falls back to F = 0 with a RuntimeWarning.
+F estimation (``compute_distances`` + ``Prime_Dual``, jamie/jamie.py:224-414, 839-890) lives in ``correspondence.py``: the
+distances on the host with the reference's own sklearn / scipy calls, the primal-dual iteration on the GPU.  Out of scope:
+the tsne projection branch, ``corr_method='jamie'`` (marked WIP in the reference), ``model_pca='umap'``.
 """
 import os
 import time as _time
@@ -252,19 +252,20 @@ class JAMIE(UnionCom):
         for i in range(self.dataset_num):
             self.row.append(np.shape(self.dataset[i])[0])
             self.col.append(np.shape(self.dataset[i])[1])
+        # Distances (jamie/jamie.py:160-166): needed only to estimate F
+        need_dist = self.match_result is None and self.use_f_tilde
+        self.compute_distances(save_dist=need_dist)
         time.log('Distance')
 
-        # Correspondence between samples: supplied, or zeros (use_f_tilde=False, jamie/jamie.py:172-173).
-        # The reference's per-pair linear_sum_assignment (jamie/jamie.py:177-181) only feeds the tsne branch: skipped.
+        # Correspondence between samples: supplied, zeros (use_f_tilde=False, jamie/jamie.py:172-173) or estimated with
+        # Prime_Dual on the GPU. The reference's per-pair linear_sum_assignment (jamie/jamie.py:177-181) only feeds the
+        # tsne branch: skipped.
         if not self.use_f_tilde:
             self.match_result = None
             self._F_dense = None
-        elif self.match_result is None:
-            warnings.warn(
-                'Estimating F (Prime_Dual on geodesic distances) is outside this build; continuing with F = 0 as if '
-                'use_f_tilde=False. Pass match_result=[F] to supply a correspondence estimate.', RuntimeWarning)
-            self._F_dense = None
         else:
+            if self.match_result is None:
+                self.match_result = self.match()
             self._F_dense = np.asarray(self.match_result[0], np.float32)
         time.log('Correspondence')
 
@@ -276,6 +277,45 @@ class JAMIE(UnionCom):
         time.aggregate()
         print()
         return integrated_data
+
+    # ------------------------------------------------------------------------------------------------ F estimation
+    def compute_distances(self, save_dist=True):
+        """Helper function to compute distances for each dataset (jamie/jamie.py:839-890)"""
+        from .correspondence import distance_function
+        if save_dist:
+            self.dist = []
+        print('Shape of Raw data')
+        for i in range(self.dataset_num):
+            print('Dataset {}:'.format(i), np.shape(self.dataset[i]))
+            self.distance_function = distance_function(self.distance_mode, self.kmax)
+            if save_dist:
+                self.dist.append(self.distance_function(self.dataset[i]))
+
+    def match(self):
+        """Find correspondence between multi-omics datasets (jamie/jamie.py:224-250)"""
+        print('Device:', self.device)
+        cor_pairs = []
+        for i in range(self.dataset_num):
+            for j in range(i + 1, self.dataset_num):
+                print('-' * 33)
+                print(f'Find correspondence between Dataset {i + 1} and Dataset {j + 1}')
+                if self.corr_method == 'unioncom':
+                    F = self.Prime_Dual([self.dist[i], self.dist[j]], dx=self.col[i], dy=self.col[j])
+                elif self.corr_method == 'jamie':
+                    raise NotImplementedError("corr_method='jamie' is marked WIP / unreliable in the reference "
+                                              '(jamie/jamie.py:241-246) and is not built')
+                else:
+                    raise Exception(f'corr_method {self.corr_method!r} does not exist')
+                cor_pairs.append(F)
+        print('Finished Matching!')
+        return cor_pairs
+
+    def Prime_Dual(self, dist, dx=None, dy=None, verbose=True):
+        """Prime dual combined with Adam algorithm to find the local optimal solution (jamie/jamie.py:314-414)"""
+        from .correspondence import prime_dual
+        dev = self._cuda_index()
+        return prime_dual(dist[0], dist[1], dx, dy, epoch_pd=self.epoch_pd, epsilon=self.epsilon, rho=self.rho,
+                          delay=self.delay, log_pd=self.log_pd, verbose=verbose, device=f'cuda:{dev}')
 
     # ------------------------------------------------------------------------------------------------ train
     def project_jamie(self, W=None):

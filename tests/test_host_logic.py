@@ -150,6 +150,28 @@ def test_metrics():
     assert E.mean_feature_r(np.c_[a, a[:, :1]], np.c_[a, np.ones((60, 1))]) == pytest.approx(1.0)
 
 
+def test_geodesic_distances_properties():
+    """unioncom's geodesic_distances as restated in jamie_b200/correspondence.py (third-party, parity unpinned): a
+    connected kNN graph gives a symmetric metric with zero diagonal that dominates the euclidean distance; unreachable
+    pairs are set to twice the largest finite distance."""
+    from sklearn.metrics import pairwise_distances
+    from jamie_b200.correspondence import distance_function, geodesic_distances
+    rng = np.random.default_rng(3)
+    t = np.sort(rng.random(80))
+    X = np.stack([np.cos(3 * t), np.sin(3 * t)], 1) + 0.01 * rng.normal(size=(80, 2))
+    d = geodesic_distances(X, 40)
+    assert d.shape == (80, 80) and np.allclose(d, d.T) and np.all(np.diag(d) == 0) and np.all(np.isfinite(d))
+    assert np.all(d >= pairwise_distances(X) - 1e-9)                 # paths are at least as long as the chord
+    assert d[0, -1] > 1.3 * np.linalg.norm(X[0] - X[-1])             # along the arc, not across it
+    far = np.concatenate([X[:6], X[:6] + 1000.0])                    # two clusters no kNN graph up to kmax connects
+    d2 = geodesic_distances(far, 2)
+    finite = d2[:6, :6].max()
+    assert np.allclose(d2[:6, 6:], 2 * max(finite, d2[6:, 6:].max()))
+    np.testing.assert_allclose(distance_function('cosine', 40)(X), pairwise_distances(X, metric='cosine'))
+    sp = distance_function('spearman', 40)(rng.normal(size=(5, 30)))
+    assert sp.shape == (5, 5) and np.allclose(np.diag(sp), 0)
+
+
 def test_kl_anneal_and_chunk_bound():
     # anneal midpoint and shape (jamie/jamie.py:630-631)
     assert abs(O.kl_anneal(250, 500, 10000) - 0.5) < 1e-12
