@@ -38,10 +38,32 @@ def _dist_info():
     return 0, 1
 
 
+def shard_rows_apply(fn, data):
+    """Row-sharded inference ("inference shards trivially by rows"): under torch.distributed every rank calls
+    this with the SAME ``data``; rank r runs ``fn`` on rows [n r / R, n (r + 1) / R) only and one all-gather hands every
+    rank the full [n, d_out] result. No collective on the data path itself. One process: ``fn(data)``."""
+    rank, world = _dist_info()
+    if world == 1:
+        return fn(data)
+    import torch.distributed as dist
+    n = len(data)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    part = np.ascontiguousarray(fn(data[lo:hi]))
+    rows_max = -(-n // world)
+    dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    buf = torch.zeros((rows_max,) + part.shape[1:], dtype=torch.from_numpy(part).dtype, device=dev)
+    buf[:hi - lo] = torch.from_numpy(part).to(dev)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    pieces = [out[r][:(n * (r + 1)) // world - (n * r) // world].cpu().numpy() for r in range(world)]
+    return np.concatenate(pieces, axis=0)
+
+
 class PriorSpec:
     """Correspondence prior in the most compact form that reproduces the reference's dense-matrix semantics."""
 
-    def __init__(self, P, rows):
+    def __init__(self, P, rows, method=None):
+        # method: force the sampling method (data-parallel shards take the method of the GLOBAL prior)
         self.rows = rows
         self.diag = None      # 1-D mask m: P = diag(m)
         self.dense = None     # 2-D ndarray
@@ -76,6 +98,10 @@ class PriorSpec:
         else:
             self.sampling_method = 'zeros'
             self.dense = None
+        if method is not None and method != self.sampling_method:
+            # a shard of a partially matched prior can be fully matched or empty: keep the global method where the shard
+            # supports it ('hybrid' needs two positive entries, checked below), never a stricter one
+            self.sampling_method = method if not (method == 'diag' and (self.diag is None or not np.all(self.diag == 1))) else self.sampling_method
         self.corr_samples = None
         if self.sampling_method == 'hybrid':
             # torch.argwhere(P > 0), of which the reference only ever reads rows 0 and 1 (jamie/jamie.py:525-526, 566)
@@ -85,7 +111,12 @@ class PriorSpec:
             else:
                 self.corr_samples = np.argwhere(self.dense > 0)[:2]
             if len(self.corr_samples) < 2:
-                raise IndexError('hybrid sampling needs at least two positive entries in P')
+                if method is not None:      # a shard without two matched pairs samples uniformly
+                    warnings.warn('this rank\'s shard of P has fewer than two positive entries: sampling uniformly')
+                    self.sampling_method = 'zeros'
+                    self.corr_samples = None
+                else:
+                    raise IndexError('hybrid sampling needs at least two positive entries in P')
 
     def upload(self, engine):
         if self.dense is not None:
@@ -369,15 +400,23 @@ class JAMIE(UnionCom):
             prior = prior_full
             F_local = self._F_dense
         else:
+            # rank r keeps the diagonal block P[lo_r:hi_r, lo_r:hi_r] (and the same block of F): correspondences between
+            # cells of different ranks are not used by the data-parallel step (north_star: "each rank holding its P
+            # sub-block for its batches")
+            gm = prior_full.sampling_method
             if prior_full.diag is not None:
-                prior = PriorSpec(prior_full.diag[lo[0]:hi[0]], [hi[0] - lo[0], hi[1] - lo[1]])
+                prior = PriorSpec(prior_full.diag[lo[0]:hi[0]], [hi[0] - lo[0], hi[1] - lo[1]], method=gm)
             elif prior_full.dense is not None:
-                prior = PriorSpec(prior_full.dense[lo[0]:hi[0], lo[1]:hi[1]], [hi[0] - lo[0], hi[1] - lo[1]])
+                prior = PriorSpec(prior_full.dense[lo[0]:hi[0], lo[1]:hi[1]], [hi[0] - lo[0], hi[1] - lo[1]], method=gm)
             else:
-                prior = PriorSpec(np.zeros((hi[0] - lo[0], hi[1] - lo[1]), np.float32), [hi[0] - lo[0], hi[1] - lo[1]])
+                prior = PriorSpec(np.zeros((hi[0] - lo[0], hi[1] - lo[1]), np.float32), [hi[0] - lo[0], hi[1] - lo[1]], method=gm)
             F_local = None if self._F_dense is None else self._F_dense[lo[0]:hi[0], lo[1]:hi[1]]
         local_rows = [hi[i] - lo[i] for i in range(2)]
         self.F = F_local
+        if world > 1 and min(local_rows) < self.batch_size and not (min(self.col) < self.batch_size):
+            raise ValueError(f'data-parallel training over {world} ranks needs at least batch_size = {self.batch_size} cells per '
+                             f'rank (sampling without replacement); this rank holds {min(local_rows)}. Lower batch_size or '
+                             f'the number of ranks.')
 
         dev = self._cuda_index()
         torch.cuda.set_device(dev)
@@ -515,7 +554,9 @@ class JAMIE(UnionCom):
         if world > 1:
             self._average_bn_stats()
         self.model.pull_from_engine()
-        integrated_data = [eng.encode(i, np.asarray(self.dataset[i], np.float32), stream) for i in range(2)]
+        # every rank encodes its own row range of each modality; one all-gather assembles the embeddings
+        integrated_data = [shard_rows_apply(lambda x, i=i: eng.encode(i, np.asarray(x, np.float32), stream), self.dataset[i])
+                           for i in range(2)]
         timer.log('Output')
         print("Finished Mapping!")
         if self.debug:
@@ -555,24 +596,27 @@ class JAMIE(UnionCom):
         assert self.model is not None, 'Model must be trained before modal prediction.'
         eng = self._ensure_engine()
         to_modality = (modality + 1) % self.dataset_num
-        if not pre_transformed:
-            data = self.model.preprocessing[modality](data)
-        decoded = eng.predict(modality, to_modality, np.asarray(data, np.float32), self._stream())
-        return np.array(self.model.preprocessing_inverse[to_modality](decoded))
+
+        def run(rows):
+            if not pre_transformed:
+                rows = self.model.preprocessing[modality](rows)
+            decoded = eng.predict(modality, to_modality, np.asarray(rows, np.float32), self._stream())
+            return np.array(self.model.preprocessing_inverse[to_modality](decoded))
+        return shard_rows_apply(run, data)     # data-parallel: each rank imputes its own rows (pre- and post-processing too)
 
     def transform(self, dataset, corr=None, pre_transformed=False):
         """Transform data using an already trained model"""
-        eng = self._ensure_engine()
-        if not pre_transformed:
-            dataset = [self.model.preprocessing[i](dataset[i]) for i in range(len(dataset))]
-        return [eng.encode(i, np.asarray(d, np.float32), self._stream()) for i, d in enumerate(dataset)]
+        return [self.transform_one(d, i, pre_transformed=pre_transformed) for i, d in enumerate(dataset)]
 
     def transform_one(self, data, i, pre_transformed=False):
         """Transform data using an already trained model"""
         eng = self._ensure_engine()
-        if not pre_transformed:
-            data = self.model.preprocessing[i](data)
-        return eng.encode(i, np.asarray(data, np.float32), self._stream())
+
+        def run(rows):
+            if not pre_transformed:
+                rows = self.model.preprocessing[i](rows)
+            return eng.encode(i, np.asarray(rows, np.float32), self._stream())
+        return shard_rows_apply(run, data)
 
     # ------------------------------------------------------------------------------------------------ metrics
     def test_closer(self, integrated_data, distance_metric=None):

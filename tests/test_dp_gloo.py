@@ -23,6 +23,13 @@ def _worker(rank, world, port, q):
     g = torch.full((16,), float(rank + 1))
     dist.all_reduce(g)
     len_dataloader = int(max(rows) / (128 * world))
+    # row-sharded inference through the API helper (JAMIE.modal_predict / transform_one / the final encode): every rank
+    # passes the same rows, computes only its own range and receives the full result
+    from jamie_b200.jamie import shard_rows_apply
+    full = np.arange(7 * 3, dtype=np.float32).reshape(7, 3)      # 7 rows over 2 ranks: ranges of 3 and 4 rows
+    seen = []
+    got = shard_rows_apply(lambda x: (seen.append(len(x)), x * 2 + rank * 0)[1], full)
+    assert seen == [3 if rank == 0 else 4] and np.array_equal(got, full * 2)
     q.put((rank, lo, hi, prior.sampling_method, prior.corr_samples.tolist(), g.tolist(), len_dataloader))
     dist.destroy_process_group()
 
