@@ -143,7 +143,9 @@ struct jb_engine {
   jb::StepParams* h_prm = nullptr;   // the step kernel's parameter block (host copy; passed by value at every launch)
   jb::StepCtx& h_ctx_ref() { return h_prm->cx; }
   int step_B = 0;
-  int grid = 148;            // CTAs of k_step: one per SM
+  int grid = 132;            // CTAs of k_step: HG_CLUSTER x the co-resident clusters (33 x 4 on B200; set in jb_create)
+  int fuse_enabled = 1;      // JB_FUSE=0: BatchNorm / reconstruction / reparameterisation as separate phases (the B > 512 path)
+  int fused = 0;             // the current step tables use the cluster-fused tails
   int accumulate = 0, accumulate_dev = 0;
   int wgrad_mode = jb::HG_MEDIUM;
   int wgrad_bn = 256;
@@ -297,6 +299,7 @@ struct StageSpec {   // one problem of a GEMM phase before its split-K factor is
   float out_scale;
   int acc_dynamic;
   int dyn;           // index into StepCtx::dyn of an extra dynamic output factor, or -1
+  int fuse = 0, fuse_arg = 0;
 };
 
 int build_step(jb_engine* e, int B) {
@@ -318,12 +321,31 @@ int build_step(jb_engine* e, int B) {
   const int fmode = e->precision_fast ? jb::HG_SINGLE : jb::HG_PRECISE;
   const int wmode = e->precision_fast ? jb::HG_SINGLE : e->wgrad_mode;
   std::vector<std::vector<StageSpec>> st(jb::SK_NUM_GEMM);
+  // Cluster-fused tails need all rows of a column block in one cluster: B <= HG_CLUSTER M tiles.
+  const bool fused = e->fuse_enabled && B <= jb::HG_CLUSTER * jb::HG_BM;
+  e->fused = fused ? 1 : 0;
+  const int nclusters = e->grid / jb::HG_CLUSTER;
+  // N tile of the forward / dgrad stages: 64 columns, or 32 when the 64-wide column blocks of both modalities would leave
+  // half of the clusters idle (fused) / for narrow outputs
   auto fbn = [&](int N) { return N <= 32 ? 32 : 64; };
+  auto fbn2 = [&](int N0, int N1) {
+    if (!fused) return 64;
+    const int blocks64 = (N0 + 63) / 64 + (N1 + 63) / 64;
+    return 2 * blocks64 <= nclusters ? 32 : 64;
+  };
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     auto fwd = [&](int stage, HPlanes X, int ldx, const Seg& w, const Seg& b, jb::Parts* out, int ldy, int n_out, int n_in) {
-      st[stage].push_back(StageSpec{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode, jb::EPI_BIAS, bias(b), 1.f, 0,
-                                    stage == 3 ? 0 : -1});   // the c planes carry the dynamic scale s_c
+      StageSpec sp{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode, jb::EPI_BIAS, bias(b), 1.f, 0,
+                   stage == 3 ? 0 : -1};   // the c planes carry the dynamic scale s_c
+      if (fused) {
+        static const int bn_layer[6] = {0, 1, -1, 2, 3, -1};
+        if (bn_layer[stage] >= 0) { sp.fuse = jb::FUSE_BN_FWD; sp.fuse_arg = bn_layer[stage] * 2 + i; }
+        else if (stage == 5) { sp.fuse = jb::FUSE_REC; sp.fuse_arg = i; }
+        else if (stage == 2 && 2 * L <= 64) { sp.fuse = jb::FUSE_HEADS; sp.fuse_arg = i; }
+        if (stage != 2 && n_out > 32) sp.bn = stage == 0 || stage == 4 ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
+      }
+      st[stage].push_back(sp);
     };
     fwd(0, a.xp, a.ldD, m.W1, m.b1, &a.y1, a.ld2D, 2 * D, D);
     fwd(1, a.h1, a.ld2D, m.W2, m.b2, &a.y2, a.ldD, D, 2 * D);
@@ -333,7 +355,13 @@ int build_step(jb_engine* e, int B) {
     fwd(5, a.g2, a.ld2D, m.W5, m.b5, &a.xhat, a.ldD, D, 2 * D);
     // dgrad dX[B, N_in] = dY W   (A = dY planes K-major, B = W planes MN-major, K = N_out)
     auto dgrad = [&](int stage, HPlanes dY, int lddy, const Seg& s, jb::Parts* out, int lddx, int n_out, int n_in) {
-      st[stage].push_back(StageSpec{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0, -1});
+      StageSpec sp{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0, -1};
+      if (fused && stage != 8) {   // the dgrad result feeds a BatchNorm backward: stage 6 -> dec2, 7 -> dec1, 9 -> enc2, 10 -> enc1
+        const int k = stage == 6 ? 3 : (stage == 7 ? 2 : (stage == 9 ? 1 : 0));
+        sp.fuse = jb::FUSE_BN_BWD; sp.fuse_arg = k * 2 + i;
+        if (n_in > 32) sp.bn = (k == 0 || k == 3) ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
+      }
+      st[stage].push_back(sp);
     };
     dgrad(6, a.dxhat, a.ldD, m.W5, &a.dg2, a.ld2D, D, 2 * D);
     dgrad(7, a.dy4, a.ld2D, m.W4, &a.dg1, a.ldD, 2 * D, D);
@@ -342,16 +370,19 @@ int build_step(jb_engine* e, int B) {
     dgrad(10, a.dy2, a.ldD, m.W2, &a.dh1, a.ld2D, D, 2 * D);
   }
   // wgrad dW[N_out, N_in] = dY^T X / gs  (A = dY planes MN-major, B = X planes MN-major, K = batch); largest first
-  auto wgrad = [&](HPlanes dY, int lddy, HPlanes X, int ldx, const Seg& s, int n_out, int n_in, int dyn) {
-    int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
-    st[11].push_back(StageSpec{dY, lddy, 1, X, ldx, 1, nullptr, G + s.off, s.ld, n_out, n_in, B, bn, wmode, jb::EPI_STORE, nullptr, inv_gs, 1, dyn});
+  // The two small weight gradients do not wait for the WGRAD phase: d W3 = d y3^T c runs beside the DG3 GEMM (8 + 8 work
+  // items at the headline shape) and d Wmv = d[mu|logvar]^T h2 beside DGH, on CTAs those phases leave idle; WGRAD is then
+  // exactly one work item per CTA (128 items of 128 x 256 on 132 CTAs).
+  auto wgrad = [&](HPlanes dY, int lddy, HPlanes X, int ldx, const Seg& s, int n_out, int n_in, int dyn, int stage = 11) {
+    int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 && stage == 11 ? 256 : 128));
+    st[stage].push_back(StageSpec{dY, lddy, 1, X, ldx, 1, nullptr, G + s.off, s.ld, n_out, n_in, B, bn, wmode, jb::EPI_STORE, nullptr, inv_gs, 1, dyn});
   };
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     // encoder-side gradients carry the dynamic scale s_b of d[mu | logvar] (dyn 1); dW3's B operand is the c planes (dyn 0)
     wgrad(a.dxhat, a.ldD, a.g2, a.ld2D, m.W5, D, 2 * D, -1); wgrad(a.dy4, a.ld2D, a.g1, a.ldD, m.W4, 2 * D, D, -1);
     wgrad(a.dy2, a.ldD, a.h1, a.ld2D, m.W2, D, 2 * D, 1); wgrad(a.dy1, a.ld2D, a.xp, a.ldD, m.W1, 2 * D, D, 1); }
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
-    wgrad(a.dmp, e->ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D, 1); wgrad(a.dy3, a.ldD, a.cp, e->LP, m.W3, D, L, 0); }
+    wgrad(a.dmp, e->ldmv, a.h2, a.ldD, m.Wmv, 2 * L, D, 1, 9); wgrad(a.dy3, a.ldD, a.cp, e->LP, m.W3, D, L, 0, 8); }
   // split-K factor per problem: fill the grid, at least two k-blocks per partial
   size_t parts_bytes = 0;
   std::vector<std::vector<int>> ks(jb::SK_NUM_GEMM);
@@ -362,7 +393,7 @@ int build_step(jb_engine* e, int B) {
       int k = 1;
       if (s.out != nullptr) {
         const int kb = (s.K + jb::HG_BK - 1) / jb::HG_BK;
-        k = e->grid / (tiles > 0 ? tiles : 1);
+        k = s.fuse ? 1 : e->grid / (tiles > 0 ? tiles : 1);
         if (k > kb / 2) k = kb / 2;
         if (k > e->max_ksplit) k = e->max_ksplit;
         if (k < 1) k = 1;
@@ -400,6 +431,8 @@ int build_step(jb_engine* e, int B) {
       if (hp.ksplit != k && s.out != nullptr) s.out->n = hp.ksplit;
       if (s.acc_dynamic) hp.acc_flag = &e->ctl->accum;
       if (s.dyn >= 0) hp.dyn_scale = e->dyn + s.dyn;
+      hp.fuse = s.fuse; hp.fuse_arg = s.fuse_arg;
+      if (s.fuse && hp.tiles_m > jb::HG_CLUSTER) return fail("fused stage with %d M tiles", hp.tiles_m);
       e->h_probs.push_back(hp);
     }
     cx.gph[g] = jb::hg_phase_finalize(e->h_probs.data(), first, static_cast<int>(st[g].size()));
@@ -454,6 +487,16 @@ int build_step(jb_engine* e, int B) {
     const int lcw = slab_lcw(e->D[0], e->D[1]);
     for (int i = 0; i < 2; ++i) { cx.m[i].rec_lcw = lcw; cx.m[i].rec_items = (e->D[i] + (1 << lcw) - 1) >> lcw; }
   }
+  cx.phase_mask = ~0ull;
+  if (fused) {
+    for (int ph : {jb::PH_BN1, jb::PH_BN2, jb::PH_BN3, jb::PH_BN4, jb::PH_BNB1, jb::PH_BNB2, jb::PH_BNB3, jb::PH_BNB4, jb::PH_REC})
+      cx.phase_mask &= ~(1ull << ph);
+    if (2 * L <= 64) cx.phase_mask &= ~(1ull << jb::PH_REPARAM);
+    for (int i = 0; i < 2; ++i) {   // one squared-error partial per (column block, cluster rank) of the last decoder GEMM
+      const jb::HgProblem& hp = e->h_probs[cx.gph[5].first + i];
+      cx.m[i].rec_items = hp.tiles_n * jb::HG_CLUSTER;
+    }
+  }
   cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
   cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
   cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;
@@ -487,6 +530,18 @@ int ensure_step(jb_engine* e, int B) {
   return build_step(e, B);
 }
 
+// k_step always runs as thread-block clusters of HG_CLUSTER CTAs (cooperative: all CTAs co-resident; the grid barrier spins).
+int launch_kstep_raw(jb_engine* e, void** args, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(e->grid); cfg.blockDim = dim3(jb::SK_THREADS); cfg.dynamicSmemBytes = jb::HG_SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = jb::HG_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  CU(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(jb::k_step), args));
+  return 0;
+}
+
 // One launch of the step kernel: phases [lo, hi) of nsteps consecutive steps, then the control-block update.
 int launch_step(jb_engine* e, int lo, int hi, int nsteps, int use_stage, cudaStream_t s, unsigned long long* ts = nullptr) {
   if (e->accumulate != e->accumulate_dev) {
@@ -498,7 +553,7 @@ int launch_step(jb_engine* e, int lo, int hi, int nsteps, int use_stage, cudaStr
   int row_bias = lo > jb::PH_GATHER ? -1 : 0;
   unsigned int* bar = e->bar;
   void* args[] = {e->h_prm, &lo, &hi, &nsteps, &bar, &use_stage, &row_bias, &ts};
-  CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
+  if (launch_kstep_raw(e, args, s)) return 1;
   const int fwd = lo == jb::PH_GATHER ? nsteps : 0, upd = hi == jb::PH_COUNT ? nsteps : 0;
   jb::k_ctl_advance<<<1, 1, 0, s>>>(e->ctl, fwd, upd, fwd > 0 ? 1 : 0);
   CU(cudaGetLastError());
@@ -700,12 +755,21 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(jb::k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::HG_SMEM_BYTES));
   e->num_sms = prop.multiProcessorCount;
-  {  // the step kernel is cooperative: one CTA per SM must be co-resident
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb::k_step, jb::SK_THREADS, jb::HG_SMEM_BYTES));
-    if (per_sm < 1) { jb_destroy(e); return fail("the step kernel does not fit on an SM (shared memory / registers)"); }
-    e->grid = e->num_sms < jb::SK_MAX_CTAS ? e->num_sms : jb::SK_MAX_CTAS;
-    if (const char* pv = getenv("JB_STEP_CTAS")) { if (atoi(pv) >= 1 && atoi(pv) <= e->grid) e->grid = atoi(pv); }
+  {  // the step kernel is cooperative and runs as clusters of HG_CLUSTER CTAs, one CTA per SM: every cluster must be
+     // co-resident (33 clusters = 132 CTAs on a 148-SM B200: GPCs with 18 SMs seat four clusters of four)
+    CU(cudaFuncSetAttribute(jb::k_step, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(jb::HG_CLUSTER * 64); lc.blockDim = dim3(jb::SK_THREADS); lc.dynamicSmemBytes = jb::HG_SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = jb::HG_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    int nclusters = 0;
+    CU(cudaOccupancyMaxActiveClusters(&nclusters, jb::k_step, &lc));
+    if (nclusters < 1) { jb_destroy(e); return fail("the step kernel does not fit on the device (shared memory / registers / clusters)"); }
+    e->grid = nclusters * jb::HG_CLUSTER;
+    if (e->grid > jb::SK_MAX_CTAS) e->grid = (jb::SK_MAX_CTAS / jb::HG_CLUSTER) * jb::HG_CLUSTER;
+    if (const char* pv = getenv("JB_STEP_CTAS")) { const int v = atoi(pv) / jb::HG_CLUSTER * jb::HG_CLUSTER; if (v >= jb::HG_CLUSTER && v <= e->grid) e->grid = v; }
+    if (const char* pv = getenv("JB_FUSE")) e->fuse_enabled = atoi(pv) != 0;
   }
   // rows per pass of the folded chain: one 128-row M tile per SM, so every GEMM of the chain is a whole number of waves
   // (measured on B200, 1M rows 512 -> 512: 8192 rows 59.1, 9472 rows 66.7, 18944 rows 69.0 M rows/s)
@@ -1103,10 +1167,10 @@ int jb_bench_stage(jb_engine* e, int phase, int iters, float* avg_us, double* fl
   int nwarm = 3;
   if (const char* pv = getenv("JB_STAGE_WARM")) nwarm = atoi(pv);   // 0 under ncu: one profiled launch per phase
   for (int i = 0; i < nwarm; ++i)
-    CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
+    if (launch_kstep_raw(e, args, s)) return 1;
   CU(cudaEventRecord(a, s));
   for (int i = 0; i < iters; ++i)
-    CU(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(jb::k_step), dim3(e->grid), dim3(jb::SK_THREADS), args, jb::HG_SMEM_BYTES, s));
+    if (launch_kstep_raw(e, args, s)) return 1;
   CU(cudaEventRecord(b, s));
   CU(cudaEventSynchronize(b));
   float ms = 0;
@@ -1164,13 +1228,13 @@ int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_laun
           e->prof_gemm[gi * 7 + k] += static_cast<float>(static_cast<double>(static_cast<long long>(d[k] - d[7])) / ghz * 1e-3 / iters);
       }
     if (getenv("JB_PROF_ELEM")) {   // element-wise phase stamps of CTA 0 (BatchNorm forward): cycles after the phase began
-      for (int p : {static_cast<int>(jb::PH_BN1), static_cast<int>(jb::PH_BN2), static_cast<int>(jb::PH_BN3), static_cast<int>(jb::PH_BN4)}) {
+      for (int p : {static_cast<int>(jb::PH_ENC1), static_cast<int>(jb::PH_ENC2), static_cast<int>(jb::PH_DEC1), static_cast<int>(jb::PH_DEC2), static_cast<int>(jb::PH_BN1), static_cast<int>(jb::PH_BN2)}) {
         double a[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int it = 1; it <= iters; ++it) {
           const unsigned long long* d = &ts[nhead + ndet + ngem + (static_cast<size_t>(it) * jb::PH_COUNT + p) * 8];
           for (int k = 0; k < 7; ++k) a[k] += static_cast<double>(static_cast<long long>(d[k] - d[7])) / ghz * 1e-3 / iters;
         }
-        fprintf(stderr, "bn fwd phase %d CTA0: enter %.2f | loads+slab %.2f | colsum1 %.2f | var+colsum2+stats %.2f | gamma/beta %.2f | apply %.2f | sync %.2f\n",
+        fprintf(stderr, "bn fwd (tail / slab) phase %d CTA0, us after the phase began: enter %.2f | pass 1 + sum %.2f | pass 2 + sum %.2f | cluster sync %.2f | merge + stats %.2f | apply %.2f | %.2f\n",
                 p, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
       }
     }

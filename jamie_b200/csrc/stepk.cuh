@@ -127,6 +127,7 @@ struct StepCtx {
   StepConsts sc;
   float gs, inv_gs;                // loss scale of the backward pass and its inverse
   int dbg_repeat;                  // 1
+  unsigned long long phase_mask;   // bit ph set: the phase runs (fused layers drop the BatchNorm / REC / REPARAM phases)
   // GEMM tables
   HgPhase gph[SK_NUM_GEMM];
 };
@@ -478,6 +479,382 @@ __device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx&
 #pragma unroll 4
   for (int r = slot; r < B; r += slots)
     h_split(k0 * (fb * sl[r << lcw] - s1 - xl[r << lcw] * s2), dYh[r * ld], dYl[r * ld]);
+}
+
+// ------------------------------------------------------------------------------------------------ cluster-fused tails
+// With B <= 4 x 128 rows the step kernel runs as clusters of HG_CLUSTER = 4 CTAs: the four CTAs of a cluster compute the
+// four M tiles of one column block of a layer (hgemm.cuh: HgProblem::fuse), so the whole batch of every feature column
+// sits in one cluster and the BatchNorm batch statistics are a cluster-local reduction through distributed shared memory.
+// The element-wise work that used to be separate slab phases (each a grid barrier plus an L2 round trip of the layer
+// output) becomes the tail of the GEMM work item: all 16 warps read the tile from the staging blocks.
+//
+// Code-size rule (measured, round 2): a phase body runs once per step, so its instructions come from L2 at ~20 cycles
+// per instruction (no overlap: ~10 ns per STATIC instruction); the first version of these tails (8 columns per thread,
+// everything unrolled: ~1300 instructions each) cost 25 us per work item cold and 10 us warm. Hence ROLLED loops over
+// the rows, tile values re-read from shared memory instead of living in registers, and the dropout keep bits are
+// produced by the six warps without a GEMM role while the main loop runs (sk_side_mask).
+//   thread mapping: warp = octet of rows (16 octets = 128 rows); lane = pair of adjacent columns (bn = 64), or
+//   lane & 15 = pair and lane >> 4 = half of the octet (bn = 32). Pairs: 8-byte shared loads, float2 / half2 stores.
+// Scratch (operand ring, idle while the tail runs; float offsets): red [16 warps][32 pairs] float4, xbuf [32] float4
+// (read by the peers), then a [128][64] tile buffer (y / x prefetch, x_hat).
+enum StepFuse : int { FUSE_NONE = 0, FUSE_BN_FWD = 1, FUSE_BN_BWD = 2, FUSE_REC = 3, FUSE_HEADS = 4 };
+constexpr int SKT_RED = 0, SKT_XBUF = 16 * 32 * 4, SKT_TILE = SKT_XBUF + 32 * 4;
+
+struct TailArgs {
+  uint8_t* stage; float* scr; const uint8_t* keep; int m0, n0, bn, tid, warp, lane; uint32_t rank;
+  long long* stamp;   // profiling: SM clock stamps of thread 0 (8 slots) or null
+};
+__device__ __forceinline__ void tail_stamp(const TailArgs& ta, int k) { if (ta.stamp != nullptr && ta.tid == 0) ta.stamp[k] = clock64(); }
+struct TailGeo {
+  int pr, cl, r0, nk, fold;
+  uint32_t sbase;   // byte offset of (row 0, column cl) in the staging blocks, without the row swizzle
+  int u;            // 16-byte unit of the column pair inside its 128-byte row
+};
+__device__ __forceinline__ TailGeo tail_geo(int bn, int warp, int lane) {
+  TailGeo g;
+  g.fold = bn > 32 ? 0 : 1;
+  g.pr = g.fold ? (lane & 15) : lane;
+  g.cl = 2 * g.pr;
+  g.nk = g.fold ? 4 : 8;
+  g.r0 = warp * 8 + (g.fold ? (lane >> 4) * 4 : 0);
+  g.sbase = static_cast<uint32_t>((g.cl >> 5) * 16384 + (g.cl & 3) * 4);
+  g.u = (g.cl & 31) >> 2;
+  return g;
+}
+// elements (r, cl), (r, cl + 1) of the staged tile (hgemm.cuh: hg_stage_ptr)
+__device__ __forceinline__ float2* tail_stg(const TailArgs& ta, const TailGeo& g, int r) {
+  return reinterpret_cast<float2*>(ta.stage + g.sbase + r * 128 + ((g.u ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ int tile_rows(int B, int rank) { const int n = B - rank * HG_BM; return n < 0 ? 0 : (n > HG_BM ? HG_BM : n); }
+// v = per-thread partial sums {a of column 0, a of column 1, b of column 0, b of column 1}: summed over all rows of the
+// tile (the two halves of an octet, then the 16 warps in a fixed order) and broadcast. All 512 threads must call.
+__device__ __noinline__ float4 tail_sum4(float4 v, float* scr, int pr, int warp, int fold) {
+  if (fold) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, 16); v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+  }
+  float4* red = reinterpret_cast<float4*>(scr + SKT_RED);
+  red[warp * 32 + pr] = v;
+  __syncthreads();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int w = 0; w < SK_WARPS; ++w) { const float4 x = red[w * 32 + pr]; t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w; }
+  __syncthreads();
+  return t;
+}
+// 8 x 16 random bits for rows 8 oc8 .. 8 oc8 + 7 of column c (dropout of the fused layers; oc8 counts octets of the batch)
+__device__ __forceinline__ uint4 sk_rand8(uint2 key, unsigned layer_id, int col, int oc8) {
+  return philox4x32(make_uint4(static_cast<uint32_t>(oc8), static_cast<uint32_t>(col), layer_id + 64u, 0x4A4Du), key);
+}
+// Dropout keep bits of a fused BatchNorm tile: keep[oc * 64 + col] bit k = row 8 oc + k of the tile is kept. Written by
+// the warps without a GEMM role (side = 0 .. HG_NSIDE - 1) while the roles run; forward and backward regenerate the
+// same bits (Philox keyed by step, layer, column, octet) or pack the injected mask.
+__device__ __forceinline__ void sk_side_mask(const StepCtx& cx, const StepVars& sv, const BnLayer& Lr, const HgTile& T, uint8_t* keep, int side, int lane) {
+  const float pdrop = cx.sc.dropout;
+  const bool inject = sv.inject != 0 && Lr.mask != nullptr;
+  const uint32_t thresh = pdrop > 0.f ? static_cast<uint32_t>(fminf(pdrop * 65536.0f + 0.5f, 65535.0f)) : 0u;
+  const int lbn = T.bn > 32 ? 6 : 5;
+  const int N = Lr.N;
+#pragma unroll 1
+  for (int it = side * 32 + lane; it < (16 << lbn); it += HG_NSIDE * 32) {
+    const int oc = it >> lbn, cl = it & (T.bn - 1);
+    const int c = T.n0 + cl;
+    uint32_t bits = 0xffu;
+    if (pdrop > 0.f && c < N) {
+      bits = 0u;
+      if (inject) {
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+          const int row = T.m0 + oc * 8 + k;
+          if (row < cx.B && Lr.mask[static_cast<long long>(row) * N + c] != 0) bits |= 1u << k;
+        }
+      } else {
+        const uint4 r = sk_rand8(sv.key, Lr.layer_id, c, (T.m0 >> 3) + oc);
+        bits |= ((r.x & 0xffffu) >= thresh ? 1u : 0u) | ((r.x >> 16) >= thresh ? 2u : 0u);
+        bits |= ((r.y & 0xffffu) >= thresh ? 4u : 0u) | ((r.y >> 16) >= thresh ? 8u : 0u);
+        bits |= ((r.z & 0xffffu) >= thresh ? 16u : 0u) | ((r.z >> 16) >= thresh ? 32u : 0u);
+        bits |= ((r.w & 0xffffu) >= thresh ? 64u : 0u) | ((r.w >> 16) >= thresh ? 128u : 0u);
+      }
+    }
+    keep[oc * 64 + cl] = static_cast<uint8_t>(bits);
+  }
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) { return ld_shared_cluster_f4(addr); }
+__device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hi);
+  lo = __floats2half2_rn((a - f.x) * HG_LO_SCALE, (b - f.y) * HG_LO_SCALE);
+}
+
+// Linear output tile -> BatchNorm1d (batch statistics over the cluster: per-CTA mean / M2, merged with Chan's formula in
+// rank order) -> LeakyReLU(0.01) -> Dropout(p) -> fp16 operand planes of the next GEMM; stores the pre-BN output y for
+// the backward pass; rank 0 updates the running statistics   (jamie/model.py:151-154 and siblings)
+__device__ __forceinline__ void sk_tail_bn_fwd(const StepCtx& cx, const StepVars& sv, const BnLayer& Lr, const float* __restrict__ biasp, const TailArgs& ta) {
+  const int B = cx.B, N = Lr.N, ld = Lr.ld;
+  const TailGeo g = tail_geo(ta.bn, ta.warp, ta.lane);
+  const int c = ta.n0 + g.cl;
+  const bool cok = c < N, cok1 = c + 1 < N;
+  const int c0 = cok ? c : N - 1, c1 = cok1 ? c + 1 : N - 1;
+  const float bias0 = __ldg(biasp + c0), bias1 = __ldg(biasp + c1);
+  const float ga0 = __ldg(Lr.gamma + c0), ga1 = __ldg(Lr.gamma + c1), be0 = __ldg(Lr.beta + c0), be1 = __ldg(Lr.beta + c1);
+  const int nc = tile_rows(B, static_cast<int>(ta.rank));
+  int nv = nc - g.r0; nv = nv < 0 ? 0 : (nv > g.nk ? g.nk : nv);   // valid rows of this thread
+  tail_stamp(ta, 0);
+  // pass 1: column sums (rows beyond the batch hold exact zeros: TMA zero-fills them)
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int k = 0; k < g.nk; ++k) { const float2 f = *tail_stg(ta, g, g.r0 + k); s.x += f.x; s.y += f.y; }
+  s = tail_sum4(s, ta.scr, g.pr, ta.warp, g.fold);
+  tail_stamp(ta, 1);
+  const float fnc = static_cast<float>(nc > 0 ? nc : 1);
+  const float mc0 = nc > 0 ? s.x / fnc + bias0 : 0.f, mc1 = nc > 0 ? s.y / fnc + bias1 : 0.f;
+  // pass 2: M2 about the CTA mean
+  s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int k = 0; k < nv; ++k) {
+    const float2 f = *tail_stg(ta, g, g.r0 + k);
+    const float d0 = f.x + bias0 - mc0, d1 = f.y + bias1 - mc1;
+    s.x += d0 * d0; s.y += d1 * d1;
+  }
+  s = tail_sum4(s, ta.scr, g.pr, ta.warp, g.fold);
+  float4* xb = reinterpret_cast<float4*>(ta.scr + SKT_XBUF);
+  tail_stamp(ta, 2);
+  if (ta.warp == 0) xb[g.pr] = make_float4(mc0, mc1, s.x, s.y);
+  cluster_sync_all();
+  tail_stamp(ta, 3);
+  float mean0 = 0.f, mean1 = 0.f, m20 = 0.f, m21 = 0.f;
+  {
+    const uint32_t xa = smem_u32(xb + g.pr);
+    float4 pv[HG_CLUSTER];
+#pragma unroll
+    for (int r = 0; r < HG_CLUSTER; ++r) pv[r] = ld_dsmem_f4(mapa_shared(xa, static_cast<uint32_t>(r)));
+    float nacc = 0.f;
+#pragma unroll
+    for (int r = 0; r < HG_CLUSTER; ++r) {
+      const float nr = static_cast<float>(tile_rows(B, r));
+      if (nr > 0.f) {
+        const float ntot = nacc + nr, wr = nr / ntot, wc = nacc * nr / ntot;
+        const float d0 = pv[r].x - mean0, d1 = pv[r].y - mean1;
+        mean0 += d0 * wr; mean1 += d1 * wr;
+        m20 += pv[r].z + d0 * d0 * wc; m21 += pv[r].w + d1 * d1 * wc;
+        nacc = ntot;
+      }
+    }
+  }
+  const float fB = static_cast<float>(B);
+  const float var0 = m20 / fB, var1 = m21 / fB;
+  const float inv0 = 1.0f / sqrtf(var0 + BN_EPS), inv1 = 1.0f / sqrtf(var1 + BN_EPS);
+  if (ta.rank == 0 && ta.warp == 0 && ta.lane == g.pr) {
+    const float ub = B > 1 ? fB / static_cast<float>(B - 1) : 1.f;
+    if (cok) {
+      Lr.mean[c] = mean0; Lr.invstd[c] = inv0;
+      Lr.run_mean[c] = (1.f - BN_MOM) * Lr.run_mean[c] + BN_MOM * mean0;
+      Lr.run_var[c] = (1.f - BN_MOM) * Lr.run_var[c] + BN_MOM * var0 * ub;
+    }
+    if (cok1) {
+      Lr.mean[c + 1] = mean1; Lr.invstd[c + 1] = inv1;
+      Lr.run_mean[c + 1] = (1.f - BN_MOM) * Lr.run_mean[c + 1] + BN_MOM * mean1;
+      Lr.run_var[c + 1] = (1.f - BN_MOM) * Lr.run_var[c + 1] + BN_MOM * var1 * ub;
+    }
+  }
+  tail_stamp(ta, 4);
+  if (!cok) return;   // no block-wide synchronisation below
+  const float pdrop = cx.sc.dropout;
+  const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
+  const uint32_t kb = *reinterpret_cast<const uint16_t*>(ta.keep + ta.warp * 64 + g.cl) >> (g.r0 & 7);   // bits k (column 0), 8 + k (column 1)
+  int o = (ta.m0 + g.r0) * ld + c;
+#pragma unroll 2
+  for (int k = 0; k < nv; ++k, o += ld) {
+    const float2 f = *tail_stg(ta, g, g.r0 + k);
+    const float v0 = f.x + bias0, v1 = cok1 ? f.y + bias1 : 0.f;
+    const float a0 = ga0 * ((v0 - mean0) * inv0) + be0, a1 = ga1 * ((v1 - mean1) * inv1) + be1;
+    float o0 = a0 > 0.f ? a0 : LRELU * a0, o1 = a1 > 0.f ? a1 : LRELU * a1;
+    o0 = ((kb >> k) & 1u) ? o0 * scale : 0.f;
+    o1 = (((kb >> (8 + k)) & 1u) && cok1) ? o1 * scale : 0.f;
+    __half2 hi, lo;
+    split2(o0, o1, hi, lo);
+    *reinterpret_cast<float2*>(Lr.Y.ptr + o) = make_float2(v0, v1);
+    *reinterpret_cast<__half2*>(Lr.Hh + o) = hi;
+    *reinterpret_cast<__half2*>(Lr.Hl + o) = lo;
+  }
+  tail_stamp(ta, 5);
+}
+
+// dgrad tile dH -> through Dropout, LeakyReLU and BatchNorm (batch sums over the cluster) -> dY planes; rank 0 writes
+// d gamma, d beta (the pre-BN bias gradient is identically zero)
+__device__ __forceinline__ void sk_tail_bn_bwd(const StepCtx& cx, const StepVars& sv, const BnLayer& Lr, const TailArgs& ta) {
+  const int B = cx.B, N = Lr.N, ld = Lr.ld;
+  const TailGeo g = tail_geo(ta.bn, ta.warp, ta.lane);
+  const int c = ta.n0 + g.cl;
+  const bool cok = c < N, cok1 = c + 1 < N;
+  const int c0 = cok ? c : N - 1, c1 = cok1 ? c + 1 : N - 1;
+  const int nc = tile_rows(B, static_cast<int>(ta.rank));
+  int nv = nc - g.r0; nv = nv < 0 ? 0 : (nv > g.nk ? g.nk : nv);
+  float2* const xt = reinterpret_cast<float2*>(ta.scr + SKT_TILE + g.cl);   // [r * 32]: y, then x_hat
+  // prefetch this thread's y values (all loads in flight together; row indices clamped instead of branches)
+  {
+    const float* const Y = Lr.Y.ptr + (cok ? c : 0);
+    const int rl = nc > 0 ? ta.m0 + nc - 1 : B - 1;   // last valid row (a CTA without rows reads row B - 1 and ignores it)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int row = ta.m0 + g.r0 + k;
+      const float2 y = sk_ld(reinterpret_cast<const float2*>(Y + (row < rl ? row : rl) * ld));
+      if (k < g.nk) xt[(g.r0 + k) * 32] = y;
+    }
+  }
+  const float mean0 = sk_ld(Lr.mean + c0), mean1 = sk_ld(Lr.mean + c1), inv0 = sk_ld(Lr.invstd + c0), inv1 = sk_ld(Lr.invstd + c1);
+  const float ga0 = __ldg(Lr.gamma + c0), ga1 = __ldg(Lr.gamma + c1), be0 = __ldg(Lr.beta + c0), be1 = __ldg(Lr.beta + c1);
+  const float pdrop = cx.sc.dropout;
+  const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
+  const uint32_t kb = *reinterpret_cast<const uint16_t*>(ta.keep + ta.warp * 64 + g.cl) >> (g.r0 & 7);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int k = 0; k < nv; ++k) {
+    float2* const sp = tail_stg(ta, g, g.r0 + k);
+    const float2 y = xt[(g.r0 + k) * 32];
+    float2 d = *sp;
+    const float x0 = (y.x - mean0) * inv0, x1 = cok1 ? (y.y - mean1) * inv1 : 0.f;
+    const float a0 = ga0 * x0 + be0, a1 = ga1 * x1 + be1;
+    d.x = (((kb >> k) & 1u) && cok) ? d.x * scale : 0.f;
+    d.y = (((kb >> (8 + k)) & 1u) && cok1) ? d.y * scale : 0.f;
+    d.x = a0 > 0.f ? d.x : LRELU * d.x;
+    d.y = a1 > 0.f ? d.y : LRELU * d.y;
+    s.x += d.x; s.y += d.y; s.z += d.x * x0; s.w += d.y * x1;
+    *sp = d;
+    xt[(g.r0 + k) * 32] = make_float2(x0, x1);
+  }
+  s = tail_sum4(s, ta.scr, g.pr, ta.warp, g.fold);
+  float4* xb = reinterpret_cast<float4*>(ta.scr + SKT_XBUF);
+  if (ta.warp == 0) xb[g.pr] = s;
+  cluster_sync_all();
+  {
+    const uint32_t xa = smem_u32(xb + g.pr);
+    float4 pv[HG_CLUSTER];
+#pragma unroll
+    for (int r = 0; r < HG_CLUSTER; ++r) pv[r] = ld_dsmem_f4(mapa_shared(xa, static_cast<uint32_t>(r)));
+    s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < HG_CLUSTER; ++r)
+      if (tile_rows(B, r) > 0) { s.x += pv[r].x; s.y += pv[r].y; s.z += pv[r].z; s.w += pv[r].w; }
+  }
+  if (!cok) return;
+  if (ta.rank == 0 && ta.warp == 0 && ta.lane == g.pr) {
+    const float ig = Lr.gdyn != nullptr ? cx.inv_gs * sk_ld(Lr.gdyn) : cx.inv_gs;
+    if (sv.accum) {
+      Lr.dbeta[c] += s.x * ig; Lr.dgamma[c] += s.z * ig;
+      if (cok1) { Lr.dbeta[c + 1] += s.y * ig; Lr.dgamma[c + 1] += s.w * ig; }
+    } else {
+      Lr.dbeta[c] = s.x * ig; Lr.dgamma[c] = s.z * ig; Lr.dbias[c] = 0.f;
+      if (cok1) { Lr.dbeta[c + 1] = s.y * ig; Lr.dgamma[c + 1] = s.w * ig; Lr.dbias[c + 1] = 0.f; }
+    }
+  }
+  const float fb = static_cast<float>(B);
+  const float k00 = inv0 * ga0 / fb, k01 = inv1 * ga1 / fb;
+  int o = (ta.m0 + g.r0) * ld + c;
+#pragma unroll 2
+  for (int k = 0; k < nv; ++k, o += ld) {
+    const float2 d = *tail_stg(ta, g, g.r0 + k);
+    const float2 x = xt[(g.r0 + k) * 32];
+    __half2 hi, lo;
+    split2(k00 * (fb * d.x - s.x - x.x * s.z), cok1 ? k01 * (fb * d.y - s.y - x.y * s.w) : 0.f, hi, lo);
+    *reinterpret_cast<__half2*>(Lr.dYh + o) = hi;
+    *reinterpret_cast<__half2*>(Lr.dYl + o) = lo;
+  }
+}
+
+// last decoder Linear: xhat tile -> reconstruction loss partial, d xhat planes, bias gradient (column sums over the
+// cluster)   (jamie/jamie.py:637-643)
+__device__ __forceinline__ void sk_tail_rec(const StepCtx& cx, const StepVars& sv, const ModCtx& M, const float* __restrict__ biasp, const TailArgs& ta) {
+  const int B = cx.B, N = M.D, ld = M.ldD;
+  const TailGeo g = tail_geo(ta.bn, ta.warp, ta.lane);
+  const int c = ta.n0 + g.cl;
+  const bool cok = c < N, cok1 = c + 1 < N;
+  const int c0 = cok ? c : N - 1, c1 = cok1 ? c + 1 : N - 1;
+  const int nc = tile_rows(B, static_cast<int>(ta.rank));
+  int nv = nc - g.r0; nv = nv < 0 ? 0 : (nv > g.nk ? g.nk : nv);
+  if (!cok) nv = 0;
+  float2 xv[8];
+  {
+    const float* const X = M.x + (cok ? c : 0);
+    const int rl = nc > 0 ? ta.m0 + nc - 1 : B - 1;   // last valid row (a CTA without rows reads row B - 1 and ignores it)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int row = ta.m0 + g.r0 + k;
+      xv[k] = sk_ld(reinterpret_cast<const float2*>(X + (row < rl ? row : rl) * ld));
+    }
+  }
+  float2* const xt = reinterpret_cast<float2*>(ta.scr + SKT_TILE + g.cl);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < g.nk) xt[(g.r0 + k) * 32] = xv[k];
+  const float kk = cx.gs * cx.sc.w[1] * 2.f / (static_cast<float>(B) * static_cast<float>(N));
+  const float bias0 = __ldg(biasp + c0), bias1 = __ldg(biasp + c1);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);   // column sums of d xhat (x, y), squared error (z)
+  int o = (ta.m0 + g.r0) * ld + c;
+#pragma unroll 2
+  for (int k = 0; k < nv; ++k, o += ld) {
+    const float2 f = *tail_stg(ta, g, g.r0 + k);
+    const float2 x = xt[(g.r0 + k) * 32];
+    const float h0 = f.x + bias0, h1 = cok1 ? f.y + bias1 : 0.f;
+    const float d0 = h0 - x.x, d1 = cok1 ? h1 - x.y : 0.f;
+    s.z += d0 * d0 + d1 * d1;
+    const float g0 = kk * d0, g1 = kk * d1;
+    s.x += g0; s.y += g1;
+    __half2 hi, lo;
+    split2(g0, g1, hi, lo);
+    *reinterpret_cast<float2*>(M.xhat.ptr + o) = make_float2(h0, h1);
+    *reinterpret_cast<__half2*>(M.dxh + o) = hi;
+    *reinterpret_cast<__half2*>(M.dxl + o) = lo;
+  }
+  s = tail_sum4(s, ta.scr, g.pr, ta.warp, g.fold);
+  float4* xb = reinterpret_cast<float4*>(ta.scr + SKT_XBUF);
+  if (ta.warp == 0) xb[g.pr] = s;
+  cluster_sync_all();   // (also a CTA barrier)
+  if (ta.warp == 1) {   // CTA partial of the squared error: the column pairs of the tile in a fixed order
+    float t = (ta.bn > 32 || ta.lane < 16) ? xb[ta.lane].z : 0.f;
+    t = warp_sum(t);
+    if (ta.lane == 0) M.rec_part[(ta.n0 / ta.bn) * HG_CLUSTER + static_cast<int>(ta.rank)] = t;
+  }
+  if (ta.rank == 0 && ta.warp == 0 && ta.lane == g.pr && cok) {
+    const uint32_t xa = smem_u32(xb + g.pr);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < HG_CLUSTER; ++r) {
+      const float4 pv = ld_dsmem_f4(mapa_shared(xa, static_cast<uint32_t>(r)));
+      if (tile_rows(B, r) > 0) { s0 += pv.x; s1 += pv.y; }
+    }
+    const float v0 = s0 * cx.inv_gs, v1 = s1 * cx.inv_gs;
+    M.db5[c] = sv.accum ? M.db5[c] + v0 : v0;
+    if (cok1) M.db5[c + 1] = sv.accum ? M.db5[c + 1] + v1 : v1;
+  }
+}
+
+// heads tile [mu | logvar] (2 L <= 64 columns) -> eps (injected or Philox Box-Muller), z = mu + (exp(logvar/2) + 1e-7) eps
+// (jamie/model.py:230-240)
+__device__ __forceinline__ void sk_tail_heads(const StepCtx& cx, const StepVars& sv, const ModCtx& M, int mod, const float* __restrict__ bias, const TailArgs& ta) {
+  const int B = cx.B, L = cx.L;
+#pragma unroll 1
+  for (int idx = ta.tid; idx < HG_BM * L; idx += SK_THREADS) {
+    const int r = idx / L, l = idx - r * L;
+    const int b = ta.m0 + r;
+    if (b >= B) break;
+    const float mu = reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, l & ~3))[l & 3] + __ldg(bias + l);
+    const float lv = reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, (L + l) & ~3))[(L + l) & 3] + __ldg(bias + L + l);
+    float e;
+    if (sv.inject) {
+      e = M.inj_eps[static_cast<long long>(b) * cx.LP + l];
+    } else {
+      const uint4 rn = philox4x32(make_uint4(static_cast<uint32_t>(b), static_cast<uint32_t>(l), 0xE950u + mod, 0x4A4Du), sv.key);
+      const float u1 = (static_cast<float>(rn.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float u2 = (static_cast<float>(rn.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      e = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    }
+    const long long om = static_cast<long long>(b) * cx.ldmv;
+    M.mulv.ptr[om + l] = mu;
+    M.mulv.ptr[om + L + l] = lv;
+    M.eps[static_cast<long long>(b) * cx.LP + l] = e;
+    M.z[static_cast<long long>(b) * cx.LP + l] = mu + (expf(lv * 0.5f) + 1e-7f) * e;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ reconstruction loss
@@ -1069,6 +1446,15 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
     const StepVars& sv = *svp;
 
     for (int ph = ph_lo; ph < ph_hi; ++ph) {
+      if (!((cx.phase_mask >> ph) & 1ull)) {   // phase folded into a fused GEMM tail: no work, no barrier
+        if (ts != nullptr && tid == 0) {
+          unsigned long long* d = ts + 1 + static_cast<long long>(nsteps) * PH_COUNT + ((static_cast<long long>(s) * PH_COUNT + ph) * ncta + cta) * 3;
+          d[0] = d[1] = static_cast<unsigned long long>(clk_begin);
+          d[2] = globaltimer_ns();
+          if (cta == 0) ts[1 + s * PH_COUNT + ph] = d[2];
+        }
+        continue;
+      }
       const int gi = gemm_index(ph);
       if (gi >= 0) {
         if (ts != nullptr && cta == 0) {   // role stamps of CTA 0's first tile (profiling)
@@ -1076,7 +1462,34 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
                    (static_cast<long long>(s) * SK_NUM_GEMM + gi) * 8;
           if (tid == 0) pp.dbg[7] = clk_begin;
         }
-        hg_run_phase(prm.probs, cx.gph[gi], cta, ncta, ctrl, ring, stage, tmem_d, pp, warp, lane, first_tiles + gi);
+        const HgPhase& gphase = cx.gph[gi];
+        hg_run_phase(prm.probs, gphase, cta, ncta, ctrl, ring, stage, tmem_d, pp, warp, lane, first_tiles + gi,
+                     [&](const HgTile& T, const HgProblem& P, bool more) {
+          TailArgs ta;
+          ta.stage = stage; ta.scr = reinterpret_cast<float*>(ring); ta.keep = smem + 1024; ta.m0 = T.m0; ta.n0 = T.n0; ta.bn = T.bn;
+          ta.tid = tid; ta.warp = warp; ta.lane = lane; ta.rank = static_cast<uint32_t>(cta & (HG_CLUSTER - 1));
+          ta.stamp = nullptr;
+          if (ts != nullptr && cta == 0) {
+            ta.stamp = reinterpret_cast<long long*>(ts + 1 + static_cast<long long>(nsteps) * PH_COUNT * (1 + 3 * ncta) + static_cast<long long>(nsteps) * SK_NUM_GEMM * 8) +
+                       (static_cast<long long>(s) * PH_COUNT + ph) * 8;
+            if (tid == 0) ta.stamp[7] = clk_begin;
+          }
+          const int arg = P.fuse_arg;
+          for (int rep = 0; rep < cx.dbg_repeat; ++rep)
+          switch (P.fuse) {
+            case FUSE_BN_FWD: sk_tail_bn_fwd(cx, sv, cx.bn[arg >> 1][arg & 1], P.bias, ta); break;
+            case FUSE_BN_BWD: sk_tail_bn_bwd(cx, sv, cx.bn[arg >> 1][arg & 1], ta); break;
+            case FUSE_REC: sk_tail_rec(cx, sv, cx.m[arg], P.bias, ta); break;
+            case FUSE_HEADS: sk_tail_heads(cx, sv, cx.m[arg], arg, P.bias, ta); break;
+            default: break;
+          }
+          fence_proxy_async_smem();   // the scratch is operand-ring memory: generic accesses before the next TMA writes
+          if (more) cluster_sync_all();   // the peers have read this CTA's exchange buffer; staging blocks reusable
+        },
+                     [&](const HgTile& T, const HgProblem& P, int side) {
+          if (P.fuse == FUSE_BN_FWD || P.fuse == FUSE_BN_BWD)
+            sk_side_mask(cx, sv, cx.bn[P.fuse_arg >> 1][P.fuse_arg & 1], T, smem + 1024, side, lane);
+        });
       } else {
        for (int rep = 0; rep < cx.dbg_repeat; ++rep) {   // timing experiments only (JB_DBG_REPEAT): repeats the phase's work
         switch (ph) {
