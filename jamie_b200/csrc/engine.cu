@@ -79,7 +79,7 @@ struct ModActs {  // activations and gradients of one modality (device pointers;
   HPlanes dxhat, dy4, dy3, dmp, dy2, dy1;                // backward GEMM operands
   float* dmulv;
   float *z, *c, *S, *g, *eps, *inj_eps, *den, *rs;
-  float *bn_mean[4], *bn_inv[4];  // enc1, enc2, dec1, dec2
+  float *bn_mean[4], *bn_inv[4], *bn_var[4];  // enc1, enc2, dec1, dec2
   unsigned char* inj_mask[4];
   float* rec_part;
   // GEMM outputs (fp32, split-K partial sums; carved per table build)
@@ -146,6 +146,7 @@ struct jb_engine {
   int grid = 132;            // CTAs of k_step: HG_CLUSTER x the co-resident clusters (33 x 4 on B200; set in jb_create)
   int fuse_enabled = 1;      // JB_FUSE=0: BatchNorm / reconstruction / reparameterisation as separate phases (the B > 512 path)
   int fused = 0;             // the current step tables use the cluster-fused tails
+  int merge_latent = 1;      // JB_MERGE_LATENT=0: LATLOSS / LATFIN as separate phases even without F
   int accumulate = 0, accumulate_dev = 0;
   int wgrad_mode = jb::HG_MEDIUM;
   int wgrad_bn = 256;
@@ -274,7 +275,7 @@ void carve(jb_engine* e, Carver& c) {
     a.den = c.take<float>(B); a.rs = c.take<float>(B);
     const int w[4] = {2 * D, D, D, 2 * D};
     for (int k = 0; k < 4; ++k) {
-      a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]);
+      a.bn_mean[k] = c.take<float>(w[k]); a.bn_inv[k] = c.take<float>(w[k]); a.bn_var[k] = c.take<float>(w[k]);
       a.inj_mask[k] = c.take<unsigned char>(B * w[k]);
     }
     a.rec_part = c.take<float>(D);   // one partial per slab item of the reconstruction phase (at most D items)
@@ -460,7 +461,7 @@ int build_step(jb_engine* e, int B) {
       const int bnidx = k < 2 ? (2 * i + k) : (4 + 2 * i + (k - 2));
       l.Y = bl[k].Y; l.Hh = bl[k].H.hi; l.Hl = bl[k].H.lo;
       l.gamma = T + bl[k].g->off; l.beta = T + bl[k].be->off;
-      l.mean = a.bn_mean[k]; l.invstd = a.bn_inv[k];
+      l.mean = a.bn_mean[k]; l.invstd = a.bn_inv[k]; l.var = a.bn_var[k];
       l.run_mean = e->bn_run + e->bn_off[bnidx]; l.run_var = l.run_mean + e->bn_w[bnidx];
       l.mask = a.inj_mask[k];
       l.dH = bl[k].dH; l.dYh = bl[k].dY.hi; l.dYl = bl[k].dY.lo;
@@ -491,12 +492,14 @@ int build_step(jb_engine* e, int B) {
   if (fused) {
     for (int ph : {jb::PH_BN1, jb::PH_BN2, jb::PH_BN3, jb::PH_BN4, jb::PH_BNB1, jb::PH_BNB2, jb::PH_BNB3, jb::PH_BNB4, jb::PH_REC})
       cx.phase_mask &= ~(1ull << ph);
-    if (2 * L <= 64) cx.phase_mask &= ~(1ull << jb::PH_REPARAM);
+    if (2 * L <= 64) { cx.phase_mask &= ~(1ull << jb::PH_REPARAM); cx.eps_early = 1; }
     for (int i = 0; i < 2; ++i) {   // one squared-error partial per (column block, cluster rank) of the last decoder GEMM
       const jb::HgProblem& hp = e->h_probs[cx.gph[5].first + i];
       cx.m[i].rec_items = hp.tiles_n * jb::HG_CLUSTER;
     }
   }
+  cx.merge_latent = (e->f_dense == nullptr && e->merge_latent) ? 1 : 0;
+  if (cx.merge_latent) cx.phase_mask &= ~((1ull << jb::PH_LATLOSS) | (1ull << jb::PH_LATFIN));
   cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
   cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
   cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;
@@ -518,6 +521,8 @@ int build_step(jb_engine* e, int B) {
   sc.grad_scale = 1.0f / static_cast<float>(e->cfg.world_size > 0 ? e->cfg.world_size : 1);
   sc.B = B; sc.L = L; sc.D[0] = e->D[0]; sc.D[1] = e->D[1];
   cx.gs = e->gs; cx.inv_gs = inv_gs;
+  cx.prefetch_state = 0;   // measured: WGRAD +9.4 us (the prefetch competes with the operand loads), ADAM only -3.5 us
+  if (const char* pv = getenv("JB_PREFETCH_STATE")) cx.prefetch_state = atoi(pv) != 0;
   cx.dbg_repeat = 1;
   if (const char* pv = getenv("JB_DBG_REPEAT")) { if (atoi(pv) >= 1) cx.dbg_repeat = atoi(pv); }
   e->step_B = B;
@@ -770,6 +775,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
     if (e->grid > jb::SK_MAX_CTAS) e->grid = (jb::SK_MAX_CTAS / jb::HG_CLUSTER) * jb::HG_CLUSTER;
     if (const char* pv = getenv("JB_STEP_CTAS")) { const int v = atoi(pv) / jb::HG_CLUSTER * jb::HG_CLUSTER; if (v >= jb::HG_CLUSTER && v <= e->grid) e->grid = v; }
     if (const char* pv = getenv("JB_FUSE")) e->fuse_enabled = atoi(pv) != 0;
+    if (const char* pv = getenv("JB_MERGE_LATENT")) e->merge_latent = atoi(pv) != 0;
   }
   // rows per pass of the folded chain: one 128-row M tile per SM, so every GEMM of the chain is a whole number of waves
   // (measured on B200, 1M rows 512 -> 512: 8192 rows 59.1, 9472 rows 66.7, 18944 rows 69.0 M rows/s)

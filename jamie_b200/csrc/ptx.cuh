@@ -130,6 +130,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // (TMA loads issued afterwards by this thread), all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// ---------------------------------------------------------------- L2 prefetch
+// Bulk prefetch of `bytes` (a multiple of 16, 16-byte aligned) of global memory into L2: one instruction, no destination.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes) : "memory");
+}
+// TMA prefetch of one tensor-map box into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
+
 // ---------------------------------------------------------------- grid-wide barrier (persistent kernels, all CTAs co-resident)
 // One monotonically increasing counter in global memory (never reset inside a launch; the host zeroes it before the
 // launch): every CTA adds 1 per barrier and waits until the count reaches `target` = barriers so far * CTAs.

@@ -71,7 +71,7 @@ struct BnLayer {     // one BatchNorm(+LeakyReLU+Dropout) layer of one modality,
   Parts Y;                         // pre-BN Linear output (reduced in place into partial 0 by the forward slab)
   __half *Hh, *Hl;                 // post-dropout activation, operand planes
   const float *gamma, *beta;
-  float *mean, *invstd, *run_mean, *run_var;
+  float *mean, *invstd, *var, *run_mean, *run_var;   // var: biased batch variance (fused path)
   const unsigned char* mask;       // injected keep mask [B, N] or null
   Parts dH;                        // gradient wrt the layer output (dgrad result)
   __half *dYh, *dYl;               // gradient wrt the pre-BN output, operand planes
@@ -127,6 +127,9 @@ struct StepCtx {
   StepConsts sc;
   float gs, inv_gs;                // loss scale of the backward pass and its inverse
   int dbg_repeat;                  // 1
+  int merge_latent;                // no F: LATLOSS / LATFIN folded into COMBINE / LATBZ / the DEC1 and DGH phases (optimistic operand scales)
+  int eps_early;                   // the reparameterisation noise is drawn during ENC1 (heads tail fused)
+  int prefetch_state;              // JB_PREFETCH_STATE=1 (default 0, measured slower): L2 prefetch of theta, m, v during WGRAD
   unsigned long long phase_mask;   // bit ph set: the phase runs (fused layers drop the BatchNorm / REC / REPARAM phases)
   // GEMM tables
   HgPhase gph[SK_NUM_GEMM];
@@ -225,6 +228,44 @@ __device__ __forceinline__ void sk_corr_row(const StepCtx& cx, long long base, i
       cx.corr_t[static_cast<long long>(b) * B + a] = c;
       if (fd != nullptr) { frow[b] = fvn; cx.fblk_t[static_cast<long long>(b) * B + a] = fvn; }
     }
+  }
+}
+// P = diag(m), no F (the identity / partially matched priors of every large run): corr[a][b] = pf m[i0[a]] [i1[b] == i0[a]] /
+// rowsum_a with rowsum_a = m[i0[a]] * #{b': i1[b'] == i0[a]} (1 if that is 0). A matching pair (a, b) shares the cell id,
+// so the row sum of a is also known from b's side: one warp writes row a of corr (it = a) or row b of corr^T (it = B + b),
+// both coalesced; the general path above scatters the transposed entries 4 bytes at a time (measured: GATHER 20 us).
+__device__ __forceinline__ void sk_corr_row_diag(const StepCtx& cx, long long base, int it, int lane) {
+  const int B = cx.B;
+  const bool tr = it >= B;
+  const int a = tr ? it - B : it;
+  const int* __restrict__ idx_self = cx.m[tr ? 1 : 0].idx + base;    // the cell of this row
+  const int* __restrict__ idx_other = cx.m[tr ? 0 : 1].idx + base;   // the cells along the row
+  const int* __restrict__ idx1 = cx.m[1].idx + base;
+  const int cell = idx_self[a];
+  const float diag = __ldg(cx.p_diag + cell);
+  int cnt = 0;
+#pragma unroll 1
+  for (int b0 = lane; b0 < B; b0 += 128) {
+    int v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = b0 + 32 * u < B ? idx1[b0 + 32 * u] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cnt += v[u] == cell ? 1 : 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  float p = 0.f;
+  for (int k = 0; k < cnt; ++k) p += diag;   // the same additions as the general path's row sum (cnt is 0 or 1 in practice)
+  const float rp = p == 0.f ? 1.f : p;
+  const float val = cx.pf_ratio * (diag / rp) + (1.f - cx.pf_ratio) * 0.f;
+  float* row = (tr ? cx.corr_t : cx.corr) + static_cast<long long>(a) * B;
+#pragma unroll 1
+  for (int b0 = lane; b0 < B; b0 += 128) {
+    int v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = b0 + 32 * u < B ? idx_other[b0 + 32 * u] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (b0 + 32 * u < B) row[b0 + 32 * u] = v[u] == cell ? val : 0.f;
   }
 }
 // x_i[b, :] = data_i[idx_i[row][b], :] (jamie/jamie.py:583) + operand planes; one warp per (modality, row)
@@ -600,77 +641,70 @@ __device__ __forceinline__ void sk_tail_bn_fwd(const StepCtx& cx, const StepVars
   const int nc = tile_rows(B, static_cast<int>(ta.rank));
   int nv = nc - g.r0; nv = nv < 0 ? 0 : (nv > g.nk ? g.nk : nv);   // valid rows of this thread
   tail_stamp(ta, 0);
-  // pass 1: column sums (rows beyond the batch hold exact zeros: TMA zero-fills them)
+  // one pass: sums of (x - p) and (x - p)^2 with the pivot p = row 0 of the tile (shifted-data variance: the cancellation
+  // in S2 - S1^2 / n is governed by (mean - p)^2 / var = O(1), not by mean^2 / var)
+  const float2 pv0 = *tail_stg(ta, g, 0);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-  for (int k = 0; k < g.nk; ++k) { const float2 f = *tail_stg(ta, g, g.r0 + k); s.x += f.x; s.y += f.y; }
-  s = tail_sum4(s, ta.scr, g.pr, ta.warp, g.fold);
-  tail_stamp(ta, 1);
-  const float fnc = static_cast<float>(nc > 0 ? nc : 1);
-  const float mc0 = nc > 0 ? s.x / fnc + bias0 : 0.f, mc1 = nc > 0 ? s.y / fnc + bias1 : 0.f;
-  // pass 2: M2 about the CTA mean
-  s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
   for (int k = 0; k < nv; ++k) {
     const float2 f = *tail_stg(ta, g, g.r0 + k);
-    const float d0 = f.x + bias0 - mc0, d1 = f.y + bias1 - mc1;
-    s.x += d0 * d0; s.y += d1 * d1;
+    const float d0 = f.x - pv0.x, d1 = f.y - pv0.y;
+    s.x += d0; s.y += d1; s.z += d0 * d0; s.w += d1 * d1;
   }
   s = tail_sum4(s, ta.scr, g.pr, ta.warp, g.fold);
+  tail_stamp(ta, 1);
+  const float rnc = nc > 0 ? 1.f / static_cast<float>(nc) : 0.f;
+  const float mc0 = nc > 0 ? pv0.x + bias0 + s.x * rnc : 0.f, mc1 = nc > 0 ? pv0.y + bias1 + s.y * rnc : 0.f;
+  s.x = fmaxf(s.z - s.x * s.x * rnc, 0.f);   // M2 about the CTA mean
+  s.y = fmaxf(s.w - s.y * s.y * rnc, 0.f);
   float4* xb = reinterpret_cast<float4*>(ta.scr + SKT_XBUF);
   tail_stamp(ta, 2);
   if (ta.warp == 0) xb[g.pr] = make_float4(mc0, mc1, s.x, s.y);
   cluster_sync_all();
   tail_stamp(ta, 3);
+  // batch mean = sum n_r mean_r / B; M2 = sum [M2_r + n_r (mean_r - mean)^2]   (the ranks in a fixed order)
+  const float rB = 1.f / static_cast<float>(B);
   float mean0 = 0.f, mean1 = 0.f, m20 = 0.f, m21 = 0.f;
   {
     const uint32_t xa = smem_u32(xb + g.pr);
     float4 pv[HG_CLUSTER];
 #pragma unroll
     for (int r = 0; r < HG_CLUSTER; ++r) pv[r] = ld_dsmem_f4(mapa_shared(xa, static_cast<uint32_t>(r)));
-    float nacc = 0.f;
 #pragma unroll
     for (int r = 0; r < HG_CLUSTER; ++r) {
       const float nr = static_cast<float>(tile_rows(B, r));
-      if (nr > 0.f) {
-        const float ntot = nacc + nr, wr = nr / ntot, wc = nacc * nr / ntot;
-        const float d0 = pv[r].x - mean0, d1 = pv[r].y - mean1;
-        mean0 += d0 * wr; mean1 += d1 * wr;
-        m20 += pv[r].z + d0 * d0 * wc; m21 += pv[r].w + d1 * d1 * wc;
-        nacc = ntot;
-      }
+      mean0 += nr * pv[r].x; mean1 += nr * pv[r].y;
+    }
+    mean0 *= rB; mean1 *= rB;
+#pragma unroll
+    for (int r = 0; r < HG_CLUSTER; ++r) {
+      const float nr = static_cast<float>(tile_rows(B, r));
+      const float d0 = pv[r].x - mean0, d1 = pv[r].y - mean1;
+      if (nr > 0.f) { m20 += pv[r].z + nr * d0 * d0; m21 += pv[r].w + nr * d1 * d1; }
     }
   }
-  const float fB = static_cast<float>(B);
-  const float var0 = m20 / fB, var1 = m21 / fB;
-  const float inv0 = 1.0f / sqrtf(var0 + BN_EPS), inv1 = 1.0f / sqrtf(var1 + BN_EPS);
-  if (ta.rank == 0 && ta.warp == 0 && ta.lane == g.pr) {
-    const float ub = B > 1 ? fB / static_cast<float>(B - 1) : 1.f;
-    if (cok) {
-      Lr.mean[c] = mean0; Lr.invstd[c] = inv0;
-      Lr.run_mean[c] = (1.f - BN_MOM) * Lr.run_mean[c] + BN_MOM * mean0;
-      Lr.run_var[c] = (1.f - BN_MOM) * Lr.run_var[c] + BN_MOM * var0 * ub;
-    }
-    if (cok1) {
-      Lr.mean[c + 1] = mean1; Lr.invstd[c + 1] = inv1;
-      Lr.run_mean[c + 1] = (1.f - BN_MOM) * Lr.run_mean[c + 1] + BN_MOM * mean1;
-      Lr.run_var[c + 1] = (1.f - BN_MOM) * Lr.run_var[c + 1] + BN_MOM * var1 * ub;
-    }
+  const float var0 = m20 * rB, var1 = m21 * rB;
+  const float inv0 = rsqrtf(var0 + BN_EPS), inv1 = rsqrtf(var1 + BN_EPS);
+  if (ta.rank == 0 && ta.warp == 0 && ta.lane == g.pr) {   // the running statistics follow in the WGRAD phase (sk_running_stats)
+    if (cok) { Lr.mean[c] = mean0; Lr.invstd[c] = inv0; Lr.var[c] = var0; }
+    if (cok1) { Lr.mean[c + 1] = mean1; Lr.invstd[c + 1] = inv1; Lr.var[c + 1] = var1; }
   }
   tail_stamp(ta, 4);
   if (!cok) return;   // no block-wide synchronisation below
   const float pdrop = cx.sc.dropout;
   const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
   const uint32_t kb = *reinterpret_cast<const uint16_t*>(ta.keep + ta.warp * 64 + g.cl) >> (g.r0 & 7);   // bits k (column 0), 8 + k (column 1)
+  // a = gamma (v - mean) inv + beta as one FMA per element; a column beyond N gets a = 0
+  const float sc0 = ga0 * inv0, sc1 = cok1 ? ga1 * inv1 : 0.f;
+  const float sh0 = be0 - mean0 * sc0, sh1 = cok1 ? be1 - mean1 * sc1 : 0.f;
   int o = (ta.m0 + g.r0) * ld + c;
 #pragma unroll 2
   for (int k = 0; k < nv; ++k, o += ld) {
     const float2 f = *tail_stg(ta, g, g.r0 + k);
-    const float v0 = f.x + bias0, v1 = cok1 ? f.y + bias1 : 0.f;
-    const float a0 = ga0 * ((v0 - mean0) * inv0) + be0, a1 = ga1 * ((v1 - mean1) * inv1) + be1;
-    float o0 = a0 > 0.f ? a0 : LRELU * a0, o1 = a1 > 0.f ? a1 : LRELU * a1;
-    o0 = ((kb >> k) & 1u) ? o0 * scale : 0.f;
-    o1 = (((kb >> (8 + k)) & 1u) && cok1) ? o1 * scale : 0.f;
+    const float v0 = f.x + bias0, v1 = f.y + bias1;
+    const float a0 = v0 * sc0 + sh0, a1 = v1 * sc1 + sh1;
+    const float o0 = fmaxf(a0, LRELU * a0) * (((kb >> k) & 1u) ? scale : 0.f);          // LeakyReLU: max(a, 0.01 a)
+    const float o1 = fmaxf(a1, LRELU * a1) * (((kb >> (8 + k)) & 1u) ? scale : 0.f);
     __half2 hi, lo;
     split2(o0, o1, hi, lo);
     *reinterpret_cast<float2*>(Lr.Y.ptr + o) = make_float2(v0, v1);
@@ -706,19 +740,19 @@ __device__ __forceinline__ void sk_tail_bn_bwd(const StepCtx& cx, const StepVars
   const float ga0 = __ldg(Lr.gamma + c0), ga1 = __ldg(Lr.gamma + c1), be0 = __ldg(Lr.beta + c0), be1 = __ldg(Lr.beta + c1);
   const float pdrop = cx.sc.dropout;
   const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
-  const uint32_t kb = *reinterpret_cast<const uint16_t*>(ta.keep + ta.warp * 64 + g.cl) >> (g.r0 & 7);
+  uint32_t kb = *reinterpret_cast<const uint16_t*>(ta.keep + ta.warp * 64 + g.cl) >> (g.r0 & 7);
+  if (!cok) kb = 0u;
+  if (!cok1) kb &= 0xffu;   // a column beyond N: d = 0 (its y is finite: the forward tail wrote the padding)
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
   for (int k = 0; k < nv; ++k) {
     float2* const sp = tail_stg(ta, g, g.r0 + k);
     const float2 y = xt[(g.r0 + k) * 32];
     float2 d = *sp;
-    const float x0 = (y.x - mean0) * inv0, x1 = cok1 ? (y.y - mean1) * inv1 : 0.f;
+    const float x0 = (y.x - mean0) * inv0, x1 = (y.y - mean1) * inv1;
     const float a0 = ga0 * x0 + be0, a1 = ga1 * x1 + be1;
-    d.x = (((kb >> k) & 1u) && cok) ? d.x * scale : 0.f;
-    d.y = (((kb >> (8 + k)) & 1u) && cok1) ? d.y * scale : 0.f;
-    d.x = a0 > 0.f ? d.x : LRELU * d.x;
-    d.y = a1 > 0.f ? d.y : LRELU * d.y;
+    d.x *= (((kb >> k) & 1u) ? scale : 0.f) * (a0 > 0.f ? 1.f : LRELU);
+    d.y *= (((kb >> (8 + k)) & 1u) ? scale : 0.f) * (a1 > 0.f ? 1.f : LRELU);
     s.x += d.x; s.y += d.y; s.z += d.x * x0; s.w += d.y * x1;
     *sp = d;
     xt[(g.r0 + k) * 32] = make_float2(x0, x1);
@@ -748,15 +782,18 @@ __device__ __forceinline__ void sk_tail_bn_bwd(const StepCtx& cx, const StepVars
       if (cok1) { Lr.dbeta[c + 1] = s.y * ig; Lr.dgamma[c + 1] = s.w * ig; Lr.dbias[c + 1] = 0.f; }
     }
   }
-  const float fb = static_cast<float>(B);
-  const float k00 = inv0 * ga0 / fb, k01 = inv1 * ga1 / fb;
+  // dy = (gamma inv / B) (B d - s1 - x_hat s2) = A d - (K s1) - x_hat (K s2),  K = gamma inv / B
+  const float rB = 1.f / static_cast<float>(B);
+  const float A0 = inv0 * ga0, A1 = cok1 ? inv1 * ga1 : 0.f;
+  const float K0 = A0 * rB, K1 = A1 * rB;
+  const float b0 = K0 * s.x, b1 = K1 * s.y, e0 = K0 * s.z, e1 = K1 * s.w;
   int o = (ta.m0 + g.r0) * ld + c;
 #pragma unroll 2
   for (int k = 0; k < nv; ++k, o += ld) {
     const float2 d = *tail_stg(ta, g, g.r0 + k);
     const float2 x = xt[(g.r0 + k) * 32];
     __half2 hi, lo;
-    split2(k00 * (fb * d.x - s.x - x.x * s.z), cok1 ? k01 * (fb * d.y - s.y - x.y * s.w) : 0.f, hi, lo);
+    split2(A0 * d.x - b0 - x.x * e0, A1 * d.y - b1 - x.y * e1, hi, lo);
     *reinterpret_cast<__half2*>(Lr.dYh + o) = hi;
     *reinterpret_cast<__half2*>(Lr.dYl + o) = lo;
   }
@@ -795,7 +832,7 @@ __device__ __forceinline__ void sk_tail_rec(const StepCtx& cx, const StepVars& s
   for (int k = 0; k < nv; ++k, o += ld) {
     const float2 f = *tail_stg(ta, g, g.r0 + k);
     const float2 x = xt[(g.r0 + k) * 32];
-    const float h0 = f.x + bias0, h1 = cok1 ? f.y + bias1 : 0.f;
+    const float h0 = f.x + bias0, h1 = f.y + bias1;
     const float d0 = h0 - x.x, d1 = cok1 ? h1 - x.y : 0.f;
     s.z += d0 * d0 + d1 * d1;
     const float g0 = kk * d0, g1 = kk * d1;
@@ -829,8 +866,27 @@ __device__ __forceinline__ void sk_tail_rec(const StepCtx& cx, const StepVars& s
   }
 }
 
-// heads tile [mu | logvar] (2 L <= 64 columns) -> eps (injected or Philox Box-Muller), z = mu + (exp(logvar/2) + 1e-7) eps
-// (jamie/model.py:230-240)
+// eps of both modalities for this step (injected or Philox Box-Muller, jamie/model.py:230-240): drawn by the warps without
+// a GEMM role at the start of ENC1, off the critical path (the heads tail of 8 CTAs used to spend 7 us on it)
+__device__ __forceinline__ void sk_draw_eps(const StepCtx& cx, const StepVars& sv, int gt, int nt) {
+  const int B = cx.B, L = cx.L;
+#pragma unroll 1
+  for (int t = gt; t < 2 * B * L; t += nt) {
+    const int i = t / (B * L), rem = t - i * B * L, b = rem / L, l = rem - b * L;
+    const ModCtx& M = cx.m[i];
+    float e;
+    if (sv.inject) {
+      e = M.inj_eps[static_cast<long long>(b) * cx.LP + l];
+    } else {
+      const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(b), static_cast<uint32_t>(l), 0xE950u + i, 0x4A4Du), sv.key);
+      const float u1 = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float u2 = (static_cast<float>(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      e = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    }
+    M.eps[static_cast<long long>(b) * cx.LP + l] = e;
+  }
+}
+// heads tile [mu | logvar] (2 L <= 64 columns) -> z = mu + (exp(logvar/2) + 1e-7) eps   (jamie/model.py:230-240)
 __device__ __forceinline__ void sk_tail_heads(const StepCtx& cx, const StepVars& sv, const ModCtx& M, int mod, const float* __restrict__ bias, const TailArgs& ta) {
   const int B = cx.B, L = cx.L;
 #pragma unroll 1
@@ -838,21 +894,12 @@ __device__ __forceinline__ void sk_tail_heads(const StepCtx& cx, const StepVars&
     const int r = idx / L, l = idx - r * L;
     const int b = ta.m0 + r;
     if (b >= B) break;
+    const float e = sk_ld(M.eps + static_cast<long long>(b) * cx.LP + l);
     const float mu = reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, l & ~3))[l & 3] + __ldg(bias + l);
     const float lv = reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, (L + l) & ~3))[(L + l) & 3] + __ldg(bias + L + l);
-    float e;
-    if (sv.inject) {
-      e = M.inj_eps[static_cast<long long>(b) * cx.LP + l];
-    } else {
-      const uint4 rn = philox4x32(make_uint4(static_cast<uint32_t>(b), static_cast<uint32_t>(l), 0xE950u + mod, 0x4A4Du), sv.key);
-      const float u1 = (static_cast<float>(rn.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-      const float u2 = (static_cast<float>(rn.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-      e = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
-    }
     const long long om = static_cast<long long>(b) * cx.ldmv;
     M.mulv.ptr[om + l] = mu;
     M.mulv.ptr[om + L + l] = lv;
-    M.eps[static_cast<long long>(b) * cx.LP + l] = e;
     M.z[static_cast<long long>(b) * cx.LP + l] = mu + (expf(lv * 0.5f) + 1e-7f) * e;
   }
 }
@@ -944,8 +991,12 @@ __device__ __forceinline__ void sk_cta_max_store(float v, float* part, int cta, 
 }
 // (scale, inverse scale) from the per-CTA maxima; warp-cooperative, same result in every warp of every CTA
 __device__ __forceinline__ float2 sk_dyn_scale(const float* part, int ncta, int lane) {
+  float v[SK_MAX_CTAS / 32];
+#pragma unroll
+  for (int u = 0; u < SK_MAX_CTAS / 32; ++u) v[u] = sk_ld(part + min(lane + 32 * u, ncta - 1));   // all loads in flight together
   float m = 0.f;
-  for (int i = lane; i < ncta; i += 32) m = fmaxf(m, sk_ld(part + i));
+#pragma unroll
+  for (int u = 0; u < SK_MAX_CTAS / 32; ++u) m = fmaxf(m, v[u]);
   m = warp_max(m);
   if (!(m > 32768.f)) return make_float2(1.f, 1.f);
   int e = 128;
@@ -1040,6 +1091,7 @@ __device__ __forceinline__ void sk_combine(const StepCtx& cx, int gw, int nw, in
         const float cv = (si * zv + sj * acc[t]) / den;
         M.c[o] = cv;
         cmax = fmaxf(cmax, fabsf(cv));
+        if (cx.merge_latent) h_split(cv, M.ch[o], M.cl[o]);   // scale 1; DEC1 re-scales if the global maximum leaves fp16's range
         if (fuse_loss) {
           const float mu = sk_ld(M.mulv.ptr + static_cast<long long>(row) * cx.ldmv + l);
           smu += mu * mu;
@@ -1108,6 +1160,48 @@ __device__ __forceinline__ void sk_latloss(const StepCtx& cx, int gw, int nw, in
     }
   }
 }
+// slow path of the optimistic operand scales: re-write the planes of c (d[mu|logvar]) with the scale derived from the
+// per-CTA maxima; every CTA takes the same decision (same data). Returns true if the planes were rewritten.
+__device__ __forceinline__ bool sk_rescale_c(const StepCtx& cx, int gt, int nt, int lane, int ncta, int* flag, int tid) {
+  if (tid < 32) {
+    const float2 sc = sk_dyn_scale(cx.cmax_part, ncta, lane);
+    if (lane == 0) { flag[0] = sc.x != 1.f ? 1 : 0; reinterpret_cast<float*>(flag)[1] = sc.x; reinterpret_cast<float*>(flag)[2] = sc.y; }
+  }
+  __syncthreads();
+  const bool need = flag[0] != 0;
+  const float sx = reinterpret_cast<const float*>(flag)[1], sy = reinterpret_cast<const float*>(flag)[2];
+  __syncthreads();
+  if (gt == 0) cx.dyn[0] = need ? sy : 1.f;
+  if (!need) return false;
+  const int B = cx.B, L = cx.L;
+#pragma unroll 1
+  for (int t = gt; t < 2 * B * L; t += nt) {
+    const int i = t / (B * L), rem = t - i * B * L, b = rem / L, l = rem - b * L;
+    const long long o = static_cast<long long>(b) * cx.LP + l;
+    h_split(sk_ld(cx.m[i].c + o) * sx, cx.m[i].ch[o], cx.m[i].cl[o]);
+  }
+  return true;
+}
+__device__ __forceinline__ bool sk_rescale_dmulv(const StepCtx& cx, int gt, int nt, int lane, int ncta, int* flag, int tid) {
+  if (tid < 32) {
+    const float2 sc = sk_dyn_scale(cx.dmax_part, ncta, lane);
+    if (lane == 0) { flag[0] = sc.x != 1.f ? 1 : 0; reinterpret_cast<float*>(flag)[1] = sc.x; reinterpret_cast<float*>(flag)[2] = sc.y; }
+  }
+  __syncthreads();
+  const bool need = flag[0] != 0;
+  const float sx = reinterpret_cast<const float*>(flag)[1], sy = reinterpret_cast<const float*>(flag)[2];
+  __syncthreads();
+  if (gt == 0) cx.dyn[1] = need ? sy : 1.f;
+  if (!need) return false;
+  const int B = cx.B, L2 = 2 * cx.L;
+#pragma unroll 1
+  for (int t = gt; t < 2 * B * L2; t += nt) {
+    const int i = t / (B * L2), rem = t - i * B * L2, b = rem / L2, l = rem - b * L2;
+    const long long o = static_cast<long long>(b) * cx.ldmv + l;
+    h_split(sk_ld(cx.m[i].dmulv + o) * sx, cx.m[i].dmh[o], cx.m[i].dml[o]);
+  }
+  return true;
+}
 // g_i = d(loss)/dc_i / den_i with d/dc_i = decoder dgrad - k_cos (z_i - c_i) + F term (everything times the loss scale).
 __device__ __forceinline__ void sk_latbc(const StepCtx& cx, int gw, int nw, int lane) {
   const int B = cx.B, L = cx.L, LP = cx.LP;
@@ -1175,6 +1269,7 @@ __device__ __forceinline__ void sk_latbz(const StepCtx& cx, const StepVars& sv, 
         if (i == 1 && row < 2) dlv += kkl * -0.5f * (1.f - expf(lv)) / static_cast<float>(L);
         M.dmulv[om + l] = dmu;
         M.dmulv[om + L + l] = dlv;
+        if (cx.merge_latent) { h_split(dmu, M.dmh[om + l], M.dml[om + l]); h_split(dlv, M.dmh[om + L + l], M.dml[om + L + l]); }
         dmax = fmaxf(dmax, fmaxf(fabsf(dmu), fabsf(dlv)));
       }
     }
@@ -1345,13 +1440,17 @@ __device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, i
   float4* m4 = reinterpret_cast<float4*>(cx.adam_m);
   float4* v4 = reinterpret_cast<float4*>(cx.adam_v);
   const long long stride = static_cast<long long>(ncta) * SK_THREADS;
+  // The sweep: 8 independent 16-byte loads per thread before the first use. Measured alternatives (B200): 16 loads in
+  // flight (U = 4) spills inside the 128-register budget and takes 45.8 us instead of 31; theta / m / v prefetched into L2
+  // during WGRAD (JB_PREFETCH_STATE=1) brings the phase to 27.6 us but costs WGRAD 9.4 us: the phase moves 121 MB at
+  // 3.9 TB/s = 60 % of the measured copy bandwidth with nine interleaved streams.
 #pragma unroll 1
   for (long long i0 = static_cast<long long>(cta) * SK_THREADS + tid; i0 < n4; i0 += 2 * stride) {   // 8 loads in flight
     float4 gg[2], mm[2], vv[2], tt[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < n4) { gg[u] = sk_ld(g4 + i); mm[u] = m4[i]; vv[u] = v4[i]; tt[u] = t4[i]; }
+      const long long i = i0 + u * stride < n4 ? i0 + u * stride : n4 - 1;   // clamped, not predicated: every register is defined
+      gg[u] = sk_ld(g4 + i); mm[u] = m4[i]; vv[u] = v4[i]; tt[u] = t4[i];
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -1372,6 +1471,39 @@ __device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, i
         split4_store(cx.theta_hi + 4 * i, cx.theta_lo + 4 * i, tt[u].x, tt[u].y, tt[u].z, tt[u].w);   // next step's GEMM operand planes
       }
     }
+  }
+}
+
+// running_mean / running_var of the eight BatchNorm layers from the batch statistics the fused forward tails stored
+// (jamie/model.py BatchNorm1d, momentum 0.1, unbiased variance). Runs on warps without a GEMM role at the start of WGRAD,
+// i.e. once per forward pass and off the critical path (in the tail it was four serialised L2 round trips: 2.4 us).
+__device__ __forceinline__ void sk_running_stats(const StepCtx& cx, int gt, int nt) {
+  const float fB = static_cast<float>(cx.B);
+  const float ub = cx.B > 1 ? fB / static_cast<float>(cx.B - 1) : 1.f;
+#pragma unroll 1
+  for (int ki = 0; ki < 8; ++ki) {
+    const BnLayer& Lr = cx.bn[ki >> 1][ki & 1];
+#pragma unroll 1
+    for (int c = gt; c < Lr.N; c += nt) {
+      const float m = sk_ld(Lr.mean + c), v = sk_ld(Lr.var + c);
+      Lr.run_mean[c] = (1.f - BN_MOM) * Lr.run_mean[c] + BN_MOM * m;
+      Lr.run_var[c] = (1.f - BN_MOM) * Lr.run_var[c] + BN_MOM * v * ub;
+    }
+  }
+}
+
+// theta, m, v (52 MB at the headline shape) are pulled into L2 while the WGRAD GEMMs run, by the warps without a GEMM
+// role: the ADAM phase that follows (after NORM) then reads L2 instead of HBM. 16 KB per instruction.
+__device__ __forceinline__ void sk_prefetch_state(const StepCtx& cx, int gt, int nt) {
+  const long long bytes = cx.n_flat * 4;
+  const long long nchunk = (bytes + 16383) >> 14;
+#pragma unroll 1
+  for (long long i = gt; i < 3 * nchunk; i += nt) {
+    const int which = static_cast<int>(i / nchunk);
+    const long long off = (i - which * nchunk) << 14;
+    const char* base = reinterpret_cast<const char*>(which == 0 ? cx.theta : (which == 1 ? cx.adam_m : cx.adam_v));
+    const long long left = bytes - off;
+    prefetch_l2_bulk(base + off, static_cast<uint32_t>(left < 16384 ? left : 16384));
   }
 }
 
@@ -1419,15 +1551,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
   unsigned int target = 0;
   const int B = cx.B;
   // control block: read once (nothing in this launch writes it)
-  const long long cursor0 = cx.ctl->cursor, adam0 = cx.ctl->adam_t;
-  const unsigned long long stream0 = cx.ctl->stream_id, seed = cx.ctl->seed;
-  const int inject = cx.ctl->inject, accum = cx.ctl->accum, host_slot = cx.ctl->host_slot;
+  // (the control block is read by thread 0 at every step start, not held in registers: everything that lives across the
+  // phase loop costs registers in every phase body, and the Adam sweep spills first)
 
   if (ts != nullptr && cta == 0 && tid == 0) ts[0] = globaltimer_ns();
   long long clk_begin = clock64();
   for (int s = 0; s < nsteps; ++s) {
     if (tid == 0) {
       StepVars v;
+      const long long cursor0 = cx.ctl->cursor, adam0 = cx.ctl->adam_t;
+      const unsigned long long stream0 = cx.ctl->stream_id, seed = cx.ctl->seed;
+      const int inject = cx.ctl->inject, accum = cx.ctl->accum, host_slot = cx.ctl->host_slot;
       v.row = cursor0 + s + row_bias;
       const long long t = adam0 + s + 1;
       v.kl_base = cx.plan_kl[v.row];
@@ -1463,6 +1597,23 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
           if (tid == 0) pp.dbg[7] = clk_begin;
         }
         const HgPhase& gphase = cx.gph[gi];
+        if (ph == PH_WGRAD && warp >= HG_WARP_EPI0 + HG_NEPI) {
+          if (cx.prefetch_state && ph_hi > PH_ADAM) sk_prefetch_state(cx, cta * 128 + (tid - 32 * (HG_WARP_EPI0 + HG_NEPI)), ncta * 128);
+          if (!((cx.phase_mask >> PH_BN1) & 1ull)) sk_running_stats(cx, cta * 128 + (tid - 32 * (HG_WARP_EPI0 + HG_NEPI)), ncta * 128);
+        }
+        if (ph == PH_ENC1 && cx.eps_early && warp >= HG_WARP_EPI0 + HG_NEPI)
+          sk_draw_eps(cx, sv, cta * 128 + (tid - 32 * (HG_WARP_EPI0 + HG_NEPI)), ncta * 128);
+        if (cx.merge_latent && (ph == PH_DEC1 || ph == PH_DGH)) {
+          // optimistic operand scales: COMBINE / LATBZ wrote the planes of c / d[mu|logvar] with scale 1; if a value left
+          // fp16's range every CTA sees the same maxima, rewrites the planes with the exact power-of-two scale and meets
+          // at an extra grid barrier
+          const bool redo = ph == PH_DEC1 ? sk_rescale_c(cx, cta * SK_THREADS + tid, ncta * SK_THREADS, lane, ncta, reinterpret_cast<int*>(sh), tid)
+                                          : sk_rescale_dmulv(cx, cta * SK_THREADS + tid, ncta * SK_THREADS, lane, ncta, reinterpret_cast<int*>(sh), tid);
+          if (redo) {
+            target += static_cast<unsigned int>(ncta);
+            grid_barrier(bar, target);
+          }
+        }
         hg_run_phase(prm.probs, gphase, cta, ncta, ctrl, ring, stage, tmem_d, pp, warp, lane, first_tiles + gi,
                      [&](const HgTile& T, const HgProblem& P, bool more) {
           TailArgs ta;
@@ -1490,15 +1641,27 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
           if (P.fuse == FUSE_BN_FWD || P.fuse == FUSE_BN_BWD)
             sk_side_mask(cx, sv, cx.bn[P.fuse_arg >> 1][P.fuse_arg & 1], T, smem + 1024, side, lane);
         });
+        if (ph == PH_DGH && cx.merge_latent) {   // loss scalars, d sigma, head bias gradients: CTAs from the top down (idle in this phase at the headline shape)
+          const int nitems = 1 + (4 * cx.L + 15) / 16;
+          for (int it = 0; it < nitems; ++it)
+            if ((ncta - 1 - (it % ncta)) == cta) { __syncthreads(); sk_final_item(cx, sv, it, sh, tid, warp, lane); }
+        }
       } else {
        for (int rep = 0; rep < cx.dbg_repeat; ++rep) {   // timing experiments only (JB_DBG_REPEAT): repeats the phase's work
         switch (ph) {
           case PH_GATHER: {
             // warp items: B rows of the P / F blocks (from the top of the grid down), then 2 B batch rows
             const long long base = sv.row * B;
-            for (int it = nw - 1 - gw; it < 3 * B; it += nw) {
-              if (it < B) sk_corr_row(cx, base, it, lane);
-              else sk_gather_row(cx, sv, use_stage, it - B, lane);
+            if (cx.p_diag != nullptr && cx.p_dense == nullptr && cx.f_dense == nullptr) {   // 2 B rows of corr / corr^T, then 2 B batch rows
+              for (int it = nw - 1 - gw; it < 4 * B; it += nw) {
+                if (it < 2 * B) sk_corr_row_diag(cx, base, it, lane);
+                else sk_gather_row(cx, sv, use_stage, it - 2 * B, lane);
+              }
+            } else {
+              for (int it = nw - 1 - gw; it < 3 * B; it += nw) {
+                if (it < B) sk_corr_row(cx, base, it, lane);
+                else sk_gather_row(cx, sv, use_stage, it - B, lane);
+              }
             }
             break;
           }
