@@ -128,6 +128,8 @@ struct jb_engine {
   int plan_cap = 0, plan_steps = 0, plan_B = 0;
   jb::Ctl* ctl = nullptr;
   double* norm_part = nullptr;
+  float *norm_tile = nullptr, *norm_small = nullptr;   // fused clip norm (stepk.cuh)
+  int norm_fuse = 1;                                   // JB_NORM_FUSE=0: always sweep the gradient buffer
   unsigned int* bar = nullptr;          // grid barrier counter of k_step
   unsigned long long* d_ts = nullptr;   // phase timestamps (profiling)
   // workspaces
@@ -344,7 +346,8 @@ int build_step(jb_engine* e, int B) {
         if (bn_layer[stage] >= 0) { sp.fuse = jb::FUSE_BN_FWD; sp.fuse_arg = bn_layer[stage] * 2 + i; }
         else if (stage == 5) { sp.fuse = jb::FUSE_REC; sp.fuse_arg = i; }
         else if (stage == 2 && 2 * L <= 64) { sp.fuse = jb::FUSE_HEADS; sp.fuse_arg = i; }
-        if (stage != 2 && n_out > 32) sp.bn = stage == 0 || stage == 4 ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
+        // narrow column blocks only pay where the main loop is long (K >= 256); short-K stages keep 64
+        if (stage != 2 && n_out > 32 && n_in >= 256) sp.bn = stage == 0 || stage == 4 ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
       }
       st[stage].push_back(sp);
     };
@@ -360,7 +363,7 @@ int build_step(jb_engine* e, int B) {
       if (fused && stage != 8) {   // the dgrad result feeds a BatchNorm backward: stage 6 -> dec2, 7 -> dec1, 9 -> enc2, 10 -> enc1
         const int k = stage == 6 ? 3 : (stage == 7 ? 2 : (stage == 9 ? 1 : 0));
         sp.fuse = jb::FUSE_BN_BWD; sp.fuse_arg = k * 2 + i;
-        if (n_in > 32) sp.bn = (k == 0 || k == 3) ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
+        if (n_in > 32 && n_out >= 256) sp.bn = (k == 0 || k == 3) ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
       }
       st[stage].push_back(sp);
     };
@@ -375,7 +378,7 @@ int build_step(jb_engine* e, int B) {
   // items at the headline shape) and d Wmv = d[mu|logvar]^T h2 beside DGH, on CTAs those phases leave idle; WGRAD is then
   // exactly one work item per CTA (128 items of 128 x 256 on 132 CTAs).
   auto wgrad = [&](HPlanes dY, int lddy, HPlanes X, int ldx, const Seg& s, int n_out, int n_in, int dyn, int stage = 11) {
-    int bn = n_in <= 32 ? 32 : (n_in <= 64 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 && stage == 11 ? 256 : 128));
+    int bn = n_in <= 32 ? 32 : (n_in <= 64 || stage != 11 ? 64 : (n_in >= 256 && e->wgrad_bn >= 256 ? 256 : 128));
     st[stage].push_back(StageSpec{dY, lddy, 1, X, ldx, 1, nullptr, G + s.off, s.ld, n_out, n_in, B, bn, wmode, jb::EPI_STORE, nullptr, inv_gs, 1, dyn});
   };
   for (int i = 0; i < 2; ++i) { ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
@@ -411,6 +414,7 @@ int build_step(jb_engine* e, int B) {
   if (!e->h_prm) e->h_prm = new jb::StepParams();
   jb::StepCtx& cx = e->h_prm->cx;
   cx = jb::StepCtx{};
+  int n_norm_tile = 0;
   for (int g = 0; g < jb::SK_NUM_GEMM; ++g) {
     const int first = static_cast<int>(e->h_probs.size());
     if (st[g].size() > static_cast<size_t>(jb::HG_MAX_PROBS) || e->h_probs.size() + st[g].size() > static_cast<size_t>(jb::SK_MAX_PROBS))
@@ -433,6 +437,10 @@ int build_step(jb_engine* e, int B) {
       if (s.acc_dynamic) hp.acc_flag = &e->ctl->accum;
       if (s.dyn >= 0) hp.dyn_scale = e->dyn + s.dyn;
       hp.fuse = s.fuse; hp.fuse_arg = s.fuse_arg;
+      if (s.out == nullptr) {   // weight gradient: per-warp sums of squares of what the epilogue stored
+        hp.norm_out = e->norm_tile + n_norm_tile;
+        n_norm_tile += hp.tiles_m * hp.tiles_n * jb::HG_NEPI;
+      }
       if (s.fuse && hp.tiles_m > jb::HG_CLUSTER) return fail("fused stage with %d M tiles", hp.tiles_m);
       e->h_probs.push_back(hp);
     }
@@ -497,6 +505,18 @@ int build_step(jb_engine* e, int B) {
       const jb::HgProblem& hp = e->h_probs[cx.gph[5].first + i];
       cx.m[i].rec_items = hp.tiles_n * jb::HG_CLUSTER;
     }
+  }
+  cx.norm_tile = e->norm_tile; cx.norm_small = e->norm_small; cx.n_norm_tile = n_norm_tile;
+  cx.norm_fuse = e->norm_fuse && n_norm_tile <= 8192 ? 1 : 0;
+  {
+    int nr = 0;
+    auto rng = [&](const Seg& sg) { cx.norm_rng[nr][0] = static_cast<int>(sg.off); cx.norm_rng[nr][1] = sg.cols; ++nr; };
+    rng(e->sigma);
+    for (int i = 0; i < 2; ++i) {
+      const ModSegs& m = e->ms[i];
+      for (const Seg* sg : {&m.b1, &m.g1, &m.be1, &m.b2, &m.g2, &m.be2, &m.bmv, &m.b3, &m.g3, &m.be3, &m.b4, &m.g4, &m.be4, &m.b5}) rng(*sg);
+    }
+    cx.n_norm_rng = nr;
   }
   cx.merge_latent = (e->f_dense == nullptr && e->merge_latent) ? 1 : 0;
   if (cx.merge_latent) cx.phase_mask &= ~((1ull << jb::PH_LATLOSS) | (1ull << jb::PH_LATFIN));
@@ -752,6 +772,11 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   c0.seed = cfg->seed;
   CU(cudaMemcpy(e->ctl, &c0, sizeof c0, cudaMemcpyHostToDevice));
   CU(cudaMalloc(&e->norm_part, jb::SK_MAX_CTAS * sizeof(double)));
+  CU(cudaMalloc(&e->norm_tile, 8192 * sizeof(float)));
+  CU(cudaMalloc(&e->norm_small, jb::SK_MAX_CTAS * 4 * sizeof(float)));
+  CU(cudaMemset(e->norm_tile, 0, 8192 * sizeof(float)));
+  CU(cudaMemset(e->norm_small, 0, jb::SK_MAX_CTAS * 4 * sizeof(float)));
+  if (const char* pv = getenv("JB_NORM_FUSE")) e->norm_fuse = atoi(pv) != 0;
   CU(cudaMalloc(&e->bar, 128));
   CU(cudaMemset(e->bar, 0, 128));
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
@@ -1242,6 +1267,18 @@ int jb_profile_step(jb_engine* e, int iters, float* out_us, int cap, int* n_laun
         }
         fprintf(stderr, "bn fwd (tail / slab) phase %d CTA0, us after the phase began: enter %.2f | pass 1 + sum %.2f | pass 2 + sum %.2f | cluster sync %.2f | merge + stats %.2f | apply %.2f | %.2f\n",
                 p, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+      }
+    }
+    if (const char* pv = getenv("JB_PROF_CTA_PHASE")) {   // per-CTA work of one phase (us, averaged over the steps)
+      const int p = atoi(pv);
+      if (p >= 0 && p < jb::PH_COUNT) {
+        fprintf(stderr, "phase %d work per CTA (us):", p);
+        for (int c = 0; c < nc; ++c) {
+          double w = 0;
+          for (int it = 1; it <= iters; ++it) w += static_cast<double>(det(it, p, c, 1) - det(it, p, c, 0)) / ghz * 1e-3;
+          fprintf(stderr, "%s%.1f", c % 16 == 0 ? "\n  " : " ", w / iters);
+        }
+        fprintf(stderr, "\n");
       }
     }
     e->prof_detail.assign(jb::PH_COUNT * 4, 0.f);

@@ -81,6 +81,8 @@ struct alignas(128) HgProblem {
   // block (CTA rank in the cluster = M tile). The accumulators are not stored: they are left in the staging blocks for
   // the caller's tail (BatchNorm statistics over the cluster, activation, dropout, loss ...). Requires tiles_m <=
   // HG_CLUSTER, bn <= 64, ksplit = 1.
+  float* norm_out;         // optional (weight gradients): sum of squares of the values this work item stored, one partial per
+                           // epilogue warp at norm_out[item * HG_NEPI + e] (the clip norm without a sweep over the gradient buffer)
   int fuse;                // 0 = plain epilogue; otherwise the kind of tail (StepFuse)
   int fuse_arg;            // which layer / modality the tail works on
 };
@@ -168,6 +170,7 @@ __device__ __forceinline__ void hg_teardown(uint32_t tmem_d, int warp) {
 // geometry of one work item, derived identically by every role
 struct HgTile {
   int p, m0, n0, ks, kb_begin, num_kb, bn, b_bytes, slot_bytes, nstages, planes;
+  int lt;                  // index of the work item inside its problem
   int null;                // fused problems: this CTA's M tile lies beyond M (no GEMM work, the CTA still joins the tail)
 };
 __device__ __forceinline__ HgTile hg_decode(const HgProblem* __restrict__ probs, const HgPhase& ph, int t) {
@@ -177,6 +180,7 @@ __device__ __forceinline__ HgTile hg_decode(const HgProblem* __restrict__ probs,
   const HgProblem& P = probs[ph.first + p];
   T.p = ph.first + p;
   const int local = t - ph.base[p];
+  T.lt = local;
   const int ksplit = P.ksplit;
   T.ks = local % ksplit;
   const int tt = local / ksplit;
@@ -378,6 +382,7 @@ __device__ __forceinline__ void hg_epilogue_tile(const HgProblem& P, const HgTil
   const float slope = P.slope, out_scale = P.dyn_scale != nullptr ? P.out_scale * __ldcg(P.dyn_scale) : P.out_scale;
   const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(pC) & 15) == 0;
   const int m0 = T.m0, n0 = T.n0;
+  float nsq = 0.f;         // sum of squares of the values this thread stored (HgProblem::norm_out)
 
   // finish one 32-column block held in v (this thread: row q * 32 + lane of the tile): the raw accumulators go through
   // the warp's staging block; scale, bias and activation are applied on the way out, four columns per lane, in a ROLLED
@@ -422,10 +427,11 @@ __device__ __forceinline__ void hg_epilogue_tile(const HgProblem& P, const HgTil
             xs[0] += o.x; xs[1] += o.y; xs[2] += o.z; xs[3] += o.w;
           }
           *reinterpret_cast<float4*>(dst) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+          nsq += xs[0] * xs[0] + xs[1] * xs[1] + xs[2] * xs[2] + xs[3] * xs[3];
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n + j < pN) dst[j] = accumulate ? dst[j] + xs[j] : xs[j];
+            if (n + j < pN) { const float w = accumulate ? dst[j] + xs[j] : xs[j]; dst[j] = w; nsq += w * w; }
         }
       }
     }
@@ -518,6 +524,11 @@ __device__ __forceinline__ void hg_epilogue_tile(const HgProblem& P, const HgTil
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctrl->acce[0]);
     }
+  }
+  if (P.norm_out != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, o);
+    if (lane == 0) P.norm_out[T.lt * HG_NEPI + e] = nsq;
   }
   pp_io = pp;
 }

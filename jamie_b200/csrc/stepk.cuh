@@ -122,6 +122,13 @@ struct StepCtx {
   long long n_flat;
   const float* sigma; float* dsigma;
   double* norm_part;               // [SK_MAX_CTAS]
+  // clip norm without the NORM sweep (launches that contain every weight-gradient GEMM and ADAM): the weight-gradient
+  // epilogues leave per-warp sums of squares in norm_tile [n_norm_tile]; the gradients of the small tensors (biases,
+  // BatchNorm affine, sigma: norm_rng (offset, length) pairs) are summed by warps without a GEMM role during WGRAD into
+  // norm_small [4 ncta]
+  float *norm_tile, *norm_small;
+  int n_norm_tile, n_norm_rng, norm_fuse;
+  int norm_rng[32][2];
   // plan / control / outputs
   const float* plan_kl; float* out_loss; Ctl* ctl;
   StepConsts sc;
@@ -1418,9 +1425,14 @@ __device__ __forceinline__ void sk_norm(const StepCtx& cx, int cta, int ncta, do
 }
 // every CTA re-reduces the partials in the same order (identical clip coefficient everywhere), then
 // g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
-__device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid) {
+__device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid, bool fused_norm) {
   double s = 0.0;
-  for (int i = tid; i < ncta; i += SK_THREADS) s += sk_ld(cx.norm_part + i);
+  if (fused_norm) {
+    for (int i = tid; i < cx.n_norm_tile; i += SK_THREADS) s += static_cast<double>(sk_ld(cx.norm_tile + i));
+    for (int i = tid; i < 4 * ncta; i += SK_THREADS) s += static_cast<double>(sk_ld(cx.norm_small + i));
+  } else {
+    for (int i = tid; i < ncta; i += SK_THREADS) s += sk_ld(cx.norm_part + i);
+  }
   shd[tid] = s;
   __syncthreads();
   for (int o = SK_THREADS / 2; o > 0; o >>= 1) {
@@ -1472,6 +1484,27 @@ __device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, i
       }
     }
   }
+}
+
+// sum of squares of the gradients of the small tensors (everything that is not a weight matrix): 128 threads per CTA
+// (the four warps without a role during WGRAD), one partial per warp
+__device__ __forceinline__ void sk_norm_small(const StepCtx& cx, int cta, int ncta, int w4, int lane) {
+  const int gt = (cta * 4 + w4) * 32 + lane, nt = ncta * 128;
+  float s = 0.f;
+  int base = 0;
+#pragma unroll 1
+  for (int r = 0; r < cx.n_norm_rng; ++r) {
+    const int len = cx.norm_rng[r][1];
+    const float* g = cx.grad + cx.norm_rng[r][0];
+    // element e of the concatenated ranges belongs to thread e mod nt
+    int first = gt - (base % nt);
+    if (first < 0) first += nt;
+#pragma unroll 1
+    for (int i = first; i < len; i += nt) { const float v = sk_ld(g + i); s += v * v; }
+    base += len;
+  }
+  s = warp_sum(s);
+  if (lane == 0) cx.norm_small[cta * 4 + w4] = s;
 }
 
 // running_mean / running_var of the eight BatchNorm layers from the batch statistics the fused forward tails stored
@@ -1550,7 +1583,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
   HgPipe pp;
   unsigned int target = 0;
   const int B = cx.B;
-  // control block: read once (nothing in this launch writes it)
+  const bool norm_fused = cx.norm_fuse != 0 && ph_lo <= PH_DG3 && ph_hi > PH_ADAM;   // every weight-gradient epilogue of the step is in this launch
   // (the control block is read by thread 0 at every step start, not held in registers: everything that lives across the
   // phase loop costs registers in every phase body, and the Adam sweep spills first)
 
@@ -1580,7 +1613,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
     const StepVars& sv = *svp;
 
     for (int ph = ph_lo; ph < ph_hi; ++ph) {
-      if (!((cx.phase_mask >> ph) & 1ull)) {   // phase folded into a fused GEMM tail: no work, no barrier
+      if (!((cx.phase_mask >> ph) & 1ull) || (ph == PH_NORM && norm_fused)) {   // phase folded away: no work, no barrier
         if (ts != nullptr && tid == 0) {
           unsigned long long* d = ts + 1 + static_cast<long long>(nsteps) * PH_COUNT + ((static_cast<long long>(s) * PH_COUNT + ph) * ncta + cta) * 3;
           d[0] = d[1] = static_cast<unsigned long long>(clk_begin);
@@ -1600,6 +1633,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
         if (ph == PH_WGRAD && warp >= HG_WARP_EPI0 + HG_NEPI) {
           if (cx.prefetch_state && ph_hi > PH_ADAM) sk_prefetch_state(cx, cta * 128 + (tid - 32 * (HG_WARP_EPI0 + HG_NEPI)), ncta * 128);
           if (!((cx.phase_mask >> PH_BN1) & 1ull)) sk_running_stats(cx, cta * 128 + (tid - 32 * (HG_WARP_EPI0 + HG_NEPI)), ncta * 128);
+          if (norm_fused) sk_norm_small(cx, cta, ncta, warp - (HG_WARP_EPI0 + HG_NEPI), lane);
         }
         if (ph == PH_ENC1 && cx.eps_early && warp >= HG_WARP_EPI0 + HG_NEPI)
           sk_draw_eps(cx, sv, cta * 128 + (tid - 32 * (HG_WARP_EPI0 + HG_NEPI)), ncta * 128);
@@ -1641,9 +1675,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
           if (P.fuse == FUSE_BN_FWD || P.fuse == FUSE_BN_BWD)
             sk_side_mask(cx, sv, cx.bn[P.fuse_arg >> 1][P.fuse_arg & 1], T, smem + 1024, side, lane);
         });
-        if (ph == PH_DGH && cx.merge_latent) {   // loss scalars, d sigma, head bias gradients: CTAs from the top down (idle in this phase at the headline shape)
+        if (cx.merge_latent && (ph == PH_DGH || ph == PH_DG2)) {
+          // head bias gradients (DGH) and loss scalars + d sigma (DG2): CTAs from the top down, which have no GEMM work in
+          // these phases at the headline shape (80 resp. 128 work items on 132 CTAs)
           const int nitems = 1 + (4 * cx.L + 15) / 16;
-          for (int it = 0; it < nitems; ++it)
+          for (int it = ph == PH_DG2 ? 0 : 1; it < (ph == PH_DG2 ? 1 : nitems); ++it)
             if ((ncta - 1 - (it % ncta)) == cta) { __syncthreads(); sk_final_item(cx, sv, it, sh, tid, warp, lane); }
         }
       } else {
@@ -1720,7 +1756,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
             break;
           }
           case PH_NORM: sk_norm(cx, cta, ncta, shd, tid); break;
-          case PH_ADAM: sk_adam(cx, sv, cta, ncta, shd, tid); break;
+          case PH_ADAM: sk_adam(cx, sv, cta, ncta, shd, tid, norm_fused); break;
           default: break;
         }
        }
