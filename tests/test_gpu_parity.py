@@ -401,8 +401,12 @@ def test_split_step_equals_fused_step():
             eng.train_steps(4)
         res.append((eng.read_losses(4).copy(), eng.get_params(as_list=False)))
         eng.close()
-    np.testing.assert_array_equal(res[0][0], res[1][0])
-    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][0][:, :5], res[1][0][:, :5])     # the losses are bit-identical
+    # The clip norm is summed differently: a launch that holds the whole step takes per-work-item partial sums from the
+    # weight-gradient epilogues, the split path (whose gradient buffer may have been all-reduced in between) sweeps the
+    # buffer. Same value to ~1e-7 relative, so the clip coefficient and the parameters agree to the last bit or two.
+    np.testing.assert_allclose(res[0][0][:, 5], res[1][0][:, 5], rtol=1e-6)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=0, atol=1e-6)
 
 
 def test_hostbatch_async_equals_sync_and_resident():
