@@ -360,7 +360,9 @@ int build_step(jb_engine* e, int B) {
     // dgrad dX[B, N_in] = dY W   (A = dY planes K-major, B = W planes MN-major, K = N_out)
     auto dgrad = [&](int stage, HPlanes dY, int lddy, const Seg& s, jb::Parts* out, int lddx, int n_out, int n_in) {
       StageSpec sp{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0, -1};
-      if (fused && stage != 8) {   // the dgrad result feeds a BatchNorm backward: stage 6 -> dec2, 7 -> dec1, 9 -> enc2, 10 -> enc1
+      if (fused && stage == 8) {   // d c: the LATBC phase becomes the tail (no F, one column block)
+        if (e->f_dense == nullptr && e->merge_latent && L <= 64) { sp.fuse = jb::FUSE_LATBC; sp.fuse_arg = i; }
+      } else if (fused) {   // the dgrad result feeds a BatchNorm backward: stage 6 -> dec2, 7 -> dec1, 9 -> enc2, 10 -> enc1
         const int k = stage == 6 ? 3 : (stage == 7 ? 2 : (stage == 9 ? 1 : 0));
         sp.fuse = jb::FUSE_BN_BWD; sp.fuse_arg = k * 2 + i;
         if (n_in > 32 && n_out >= 256) sp.bn = (k == 0 || k == 3) ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
@@ -520,6 +522,7 @@ int build_step(jb_engine* e, int B) {
   }
   cx.merge_latent = (e->f_dense == nullptr && e->merge_latent) ? 1 : 0;
   if (cx.merge_latent) cx.phase_mask &= ~((1ull << jb::PH_LATLOSS) | (1ull << jb::PH_LATFIN));
+  if (e->h_probs[cx.gph[8].first].fuse == jb::FUSE_LATBC) cx.phase_mask &= ~(1ull << jb::PH_LATBC);
   cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
   cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
   cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;

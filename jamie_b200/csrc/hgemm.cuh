@@ -212,7 +212,7 @@ __device__ __forceinline__ HgTile hg_decode(const HgProblem* __restrict__ probs,
 // The three roles below process ONE work item; hg_run_phase walks the items of the calling CTA (every role walks the
 // same sequence, so the pipeline counters in HgPipe agree without communication).
 __device__ __forceinline__ void hg_produce_tile(const HgProblem& P, const HgTile& T, HgCtrl* ctrl, uint8_t* ring, HgPipe& pp_io,
-                                             bool stamp) {
+                                             bool stamp) {   // stamp: the CTA's first work item of the phase
   HgPipe pp = pp_io;   // the roles are separate functions (own register allocation); the pipeline state travels by value
   const int a_mn = P.a_mn, b_mn = P.b_mn;
   const CUtensorMap* const tmAh = &P.tmA_hi;
@@ -222,7 +222,10 @@ __device__ __forceinline__ void hg_produce_tile(const HgProblem& P, const HgTile
   const bool two = T.planes == 2;
   const int off_b = two ? 2 * HG_A_BYTES : HG_A_BYTES;
   if (T.slot_bytes != pp.geom) {
-    for (int i = 0; i < HG_MAX_STAGES; ++i) mbar_wait(&ctrl->empty[i], ((pp.par >> i) & 1u) ^ 1u);   // ring drained
+    // the ring is re-cut: every slot of the old geometry must have been released. At the first work item of a phase that
+    // is known (the previous phase ended with its accumulators complete, then a grid barrier); the eight waits cost 0.7 us
+    if (!stamp)
+      for (int i = 0; i < HG_MAX_STAGES; ++i) mbar_wait(&ctrl->empty[i], ((pp.par >> i) & 1u) ^ 1u);
     pp.s = 0;
     pp.geom = T.slot_bytes;
   }

@@ -545,7 +545,7 @@ __device__ __forceinline__ void sk_bn_bwd_item(const BnLayer& Lr, const StepCtx&
 //   lane & 15 = pair and lane >> 4 = half of the octet (bn = 32). Pairs: 8-byte shared loads, float2 / half2 stores.
 // Scratch (operand ring, idle while the tail runs; float offsets): red [16 warps][32 pairs] float4, xbuf [32] float4
 // (read by the peers), then a [128][64] tile buffer (y / x prefetch, x_hat).
-enum StepFuse : int { FUSE_NONE = 0, FUSE_BN_FWD = 1, FUSE_BN_BWD = 2, FUSE_REC = 3, FUSE_HEADS = 4 };
+enum StepFuse : int { FUSE_NONE = 0, FUSE_BN_FWD = 1, FUSE_BN_BWD = 2, FUSE_REC = 3, FUSE_HEADS = 4, FUSE_LATBC = 5 };
 constexpr int SKT_RED = 0, SKT_XBUF = 16 * 32 * 4, SKT_TILE = SKT_XBUF + 32 * 4;
 
 struct TailArgs {
@@ -1399,6 +1399,49 @@ __device__ __forceinline__ void sk_final_item(const StepCtx& cx, const StepVars&
   __syncthreads();
 }
 
+__device__ __forceinline__ void ld8(const float* p, float (&x)[8]) {
+  const float4 a = sk_ld(reinterpret_cast<const float4*>(p)), b = sk_ld(reinterpret_cast<const float4*>(p + 4));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
+// decoder dgrad tile d c (L <= 64 columns, no F) -> g = d(loss)/dc / den and the row partials of d sigma: the LATBC phase as
+// the tail of the DG3 work item. Thread = (row, group of 8 latent columns): every load of a thread is independent (the
+// first version walked 8 rows per warp one after the other: 8 L2 round trips, 19 us for the phase).
+__device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M, int mod, const TailArgs& ta) {
+  const int B = cx.B, L = cx.L, LP = cx.LP;
+  const float k_cos = cx.gs * cx.sc.w[2] * 32.f * 2.f / (static_cast<float>(B) * static_cast<float>(L));
+  const float k_f = mod == 0 ? cx.gs * cx.sc.w[3] * 2.f / (static_cast<float>(B) * static_cast<float>(L)) : 0.f;
+  const int r = ta.tid >> 2, q = ta.tid & 3, row = ta.m0 + r;
+  const bool rok = row < B;
+  const int rr = rok ? row : B - 1;
+  const float rden = 1.f / sk_ld(M.den + rr);
+  float p3 = 0.f, p4 = 0.f, p5 = 0.f;
+#pragma unroll 1
+  for (int l0 = q * 8; l0 < LP; l0 += 32) {
+    const long long o = static_cast<long long>(rr) * LP + l0;
+    float z[8], c[8], S[8], lr[8], g[8];
+    ld8(M.z + o, z); ld8(M.c + o, c); ld8(M.S + o, S); ld8(cx.lat_r + o, lr);
+    const float4 d0 = *hg_stage_ptr(ta.stage, r, l0), d1 = *hg_stage_ptr(ta.stage, r, l0 + 4);
+    const float dcd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = l0 + j < L;
+      g[j] = ok ? (dcd[j] - k_cos * (z[j] - c[j]) + k_f * lr[j]) * rden : 0.f;
+      p3 += g[j] * z[j]; p4 += g[j] * c[j]; p5 += g[j] * S[j];
+    }
+    if (rok) { st8(M.g + o, g); st8(M.dc.ptr + o, dcd); }
+  }
+  p3 += __shfl_xor_sync(0xffffffffu, p3, 1); p4 += __shfl_xor_sync(0xffffffffu, p4, 1); p5 += __shfl_xor_sync(0xffffffffu, p5, 1);
+  p3 += __shfl_xor_sync(0xffffffffu, p3, 2); p4 += __shfl_xor_sync(0xffffffffu, p4, 2); p5 += __shfl_xor_sync(0xffffffffu, p5, 2);
+  if (q == 0 && rok) {
+    float* rp = cx.rowpart + (static_cast<long long>(mod) * B + row) * 8;
+    rp[3] = p3; rp[4] = p4; rp[5] = p5;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ clip + Adam
 __device__ __forceinline__ void sk_norm(const StepCtx& cx, int cta, int ncta, double* shd, int tid) {
   const long long n4 = cx.n_flat / 4;
@@ -1666,6 +1709,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
             case FUSE_BN_BWD: sk_tail_bn_bwd(cx, sv, cx.bn[arg >> 1][arg & 1], ta); break;
             case FUSE_REC: sk_tail_rec(cx, sv, cx.m[arg], P.bias, ta); break;
             case FUSE_HEADS: sk_tail_heads(cx, sv, cx.m[arg], arg, P.bias, ta); break;
+            case FUSE_LATBC: sk_tail_latbc(cx, cx.m[arg], arg, ta); break;
             default: break;
           }
           fence_proxy_async_smem();   // the scratch is operand-ring memory: generic accesses before the next TMA writes
@@ -1675,6 +1719,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
           if (P.fuse == FUSE_BN_FWD || P.fuse == FUSE_BN_BWD)
             sk_side_mask(cx, sv, cx.bn[P.fuse_arg >> 1][P.fuse_arg & 1], T, smem + 1024, side, lane);
         });
+        if (warp == HG_WARP_TMA && lane == 0) {
+          // the tensor maps of this CTA's first work item of the NEXT GEMM phase (a TMA issue stalls on a cold descriptor:
+          // four of them cost ~1.6 us at the head of every GEMM phase)
+          const int gn = gi + 1 == SK_NUM_GEMM ? 0 : gi + 1;
+          if (cta < cx.gph[gn].total_tiles && !first_tiles[gn].null) {
+            const HgProblem& Pn = prm.probs[first_tiles[gn].p];
+            tma_prefetch_desc(&Pn.tmA_hi); tma_prefetch_desc(&Pn.tmB_hi);
+            if (Pn.mode != HG_SINGLE) { tma_prefetch_desc(&Pn.tmA_lo); tma_prefetch_desc(&Pn.tmB_lo); }
+          }
+        }
         if (cx.merge_latent && (ph == PH_DGH || ph == PH_DG2)) {
           // head bias gradients (DGH) and loss scalars + d sigma (DG2): CTAs from the top down, which have no GEMM work in
           // these phases at the headline shape (80 resp. 128 work items on 132 CTAs)
