@@ -544,6 +544,8 @@ int build_step(jb_engine* e, int B) {
   sc.grad_scale = 1.0f / static_cast<float>(e->cfg.world_size > 0 ? e->cfg.world_size : 1);
   sc.B = B; sc.L = L; sc.D[0] = e->D[0]; sc.D[1] = e->D[1];
   cx.gs = e->gs; cx.inv_gs = inv_gs;
+  cx.adam_stream = 1;
+  if (const char* pv = getenv("JB_ADAM_STREAM")) cx.adam_stream = atoi(pv);
   cx.prefetch_state = 0;   // measured: WGRAD +9.4 us (the prefetch competes with the operand loads), ADAM only -3.5 us
   if (const char* pv = getenv("JB_PREFETCH_STATE")) cx.prefetch_state = atoi(pv) != 0;
   cx.dbg_repeat = 1;

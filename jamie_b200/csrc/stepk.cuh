@@ -136,6 +136,7 @@ struct StepCtx {
   int dbg_repeat;                  // 1
   int merge_latent;                // no F: LATLOSS / LATFIN folded into COMBINE / LATBZ / the DEC1 and DGH phases (optimistic operand scales)
   int eps_early;                   // the reparameterisation noise is drawn during ENC1 (heads tail fused)
+  int adam_stream;                 // JB_ADAM_STREAM=0: plain-load Adam sweep
   int prefetch_state;              // JB_PREFETCH_STATE=1 (default 0, measured slower): L2 prefetch of theta, m, v during WGRAD
   unsigned long long phase_mask;   // bit ph set: the phase runs (fused layers drop the BatchNorm / REC / REPARAM phases)
   // GEMM tables
@@ -1466,9 +1467,109 @@ __device__ __forceinline__ void sk_norm(const StepCtx& cx, int cta, int ncta, do
   if (tid == 0) cx.norm_part[cta] = shd[0];
   __syncthreads();
 }
+// The Adam sweep as a TMA-staged stream (round 2): with plain loads the phase holds 8 x 16 bytes per thread in flight (64 KB
+// per SM; 16 loads per thread spill inside the 128-register budget) and ran at 3.9 TB/s. Here one thread moves 8 KB
+// chunks of g, m, v, theta into the (idle) operand ring with 1-D bulk copies, ADAM_STAGES - 2 chunks ahead; all threads
+// update one float4 of each array in shared memory; m, v, theta and the fp16 planes go back with bulk stores.
+constexpr int ADAM_CHUNK = 2048;                 // floats per array per stage
+constexpr int ADAM_STAGE_BYTES = 4 * ADAM_CHUNK * 4;
+constexpr int ADAM_STAGES = HG_RING_BYTES / ADAM_STAGE_BYTES;   // 6
+__device__ __forceinline__ void sk_adam_stream(const StepCtx& cx, uint8_t* ring, uint64_t* bars, int cta, int ncta, int tid,
+                                               float coef, float b1, float b2, float eps, float step, float ibc2) {
+  const long long nchunk = (cx.n_flat + ADAM_CHUNK - 1) / ADAM_CHUNK;
+  const int mine = cta < nchunk ? static_cast<int>((nchunk - cta + ncta - 1) / ncta) : 0;   // chunks cta, cta + ncta, ...
+  // bars[0 .. STAGES) are initialised once per launch (k_step prologue); bars[STAGES] holds their parity bits between
+  // uses (an initialised mbarrier must not be initialised again)
+  uint32_t par = *reinterpret_cast<volatile uint32_t*>(&bars[ADAM_STAGES]);
+  const uint64_t pol = l2_policy_evict_first();
+  __syncthreads();
+  auto issue = [&](int k) {   // thread 0: loads of this CTA's k-th chunk
+    const long long c = cta + static_cast<long long>(k) * ncta;
+    const long long e0 = c * ADAM_CHUNK;
+    const long long left = cx.n_flat - e0;
+    const uint32_t bytes = static_cast<uint32_t>((left < ADAM_CHUNK ? left : ADAM_CHUNK) * 4);
+    uint8_t* st = ring + (k % ADAM_STAGES) * ADAM_STAGE_BYTES;
+    uint64_t* bar = &bars[k % ADAM_STAGES];
+    mbar_arrive_expect_tx(bar, 4 * bytes);
+    if (cx.adam_stream == 2) {
+      bulk_load_hint(st, cx.grad + e0, bytes, bar, pol);
+      bulk_load_hint(st + ADAM_CHUNK * 4, cx.adam_m + e0, bytes, bar, pol);
+      bulk_load_hint(st + 2 * ADAM_CHUNK * 4, cx.adam_v + e0, bytes, bar, pol);
+      bulk_load_hint(st + 3 * ADAM_CHUNK * 4, cx.theta + e0, bytes, bar, pol);
+    } else {
+      bulk_load(st, cx.grad + e0, bytes, bar);
+      bulk_load(st + ADAM_CHUNK * 4, cx.adam_m + e0, bytes, bar);
+      bulk_load(st + 2 * ADAM_CHUNK * 4, cx.adam_v + e0, bytes, bar);
+      bulk_load(st + 3 * ADAM_CHUNK * 4, cx.theta + e0, bytes, bar);
+    }
+  };
+  if (tid == 0)
+    for (int k = 0; k < ADAM_STAGES - 2 && k < mine; ++k) issue(k);
+#pragma unroll 1
+  for (int k = 0; k < mine; ++k) {
+    if (tid == 0) {
+      bulk_wait_read_1();   // the stores of chunk k - 2 have read their stage: it is the one chunk k + STAGES - 2 lands in
+      if (k + ADAM_STAGES - 2 < mine) issue(k + ADAM_STAGES - 2);
+    }
+    uint8_t* st = ring + (k % ADAM_STAGES) * ADAM_STAGE_BYTES;
+    mbar_wait(&bars[k % ADAM_STAGES], (par >> (k % ADAM_STAGES)) & 1u);
+    par ^= 1u << (k % ADAM_STAGES);
+    const long long c = cta + static_cast<long long>(k) * ncta;
+    const long long e0 = c * ADAM_CHUNK;
+    const long long left = cx.n_flat - e0;
+    const int n = static_cast<int>(left < ADAM_CHUNK ? left : ADAM_CHUNK);
+    float4* sg = reinterpret_cast<float4*>(st);
+    float4* sm = sg + ADAM_CHUNK / 4;
+    float4* sv4 = sm + ADAM_CHUNK / 4;
+    float4* stt = sv4 + ADAM_CHUNK / 4;
+    const bool act = tid * 4 < n;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = g4, v4 = g4, t4 = g4;
+    if (act) { g4 = sg[tid]; m4 = sm[tid]; v4 = sv4[tid]; t4 = stt[tid]; }
+    __syncthreads();   // the planes below overwrite the g part of the stage, which other threads read above
+    if (act) {
+      const float gx[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+      float* mp = reinterpret_cast<float*>(&m4);
+      float* vp = reinterpret_cast<float*>(&v4);
+      float* tp = reinterpret_cast<float*>(&t4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mp[j] = mp[j] + (gx[j] - mp[j]) * (1.f - b1);
+        vp[j] = vp[j] * b2 + gx[j] * gx[j] * (1.f - b2);
+        const float denom = sqrtf(vp[j]) * ibc2 + eps;
+        tp[j] = tp[j] - step * (mp[j] / denom);
+      }
+      sm[tid] = m4; sv4[tid] = v4; stt[tid] = t4;
+      // the planes of theta replace g in the stage: hi in its first half, lo in the second
+      split4_store(reinterpret_cast<__half*>(st) + 4 * tid, reinterpret_cast<__half*>(st + ADAM_CHUNK * 2) + 4 * tid, t4.x, t4.y, t4.z, t4.w);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(n) * 4;
+      if (cx.adam_stream == 2) {
+        bulk_store_hint(cx.adam_m + e0, st + ADAM_CHUNK * 4, bytes, pol);
+        bulk_store_hint(cx.adam_v + e0, st + 2 * ADAM_CHUNK * 4, bytes, pol);
+        bulk_store_hint(cx.theta + e0, st + 3 * ADAM_CHUNK * 4, bytes, pol);
+      } else {
+        bulk_store(cx.adam_m + e0, st + ADAM_CHUNK * 4, bytes);
+        bulk_store(cx.adam_v + e0, st + 2 * ADAM_CHUNK * 4, bytes);
+        bulk_store(cx.theta + e0, st + 3 * ADAM_CHUNK * 4, bytes);
+      }
+      bulk_store(cx.theta_hi + e0, st, bytes / 2);
+      bulk_store(cx.theta_lo + e0, st + ADAM_CHUNK * 2, bytes / 2);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) {
+    tma_store_wait_all();       // every bulk store complete
+    fence_proxy_async_all();    // async-proxy writes -> generic / async reads after the next grid barrier
+    *reinterpret_cast<volatile uint32_t*>(&bars[ADAM_STAGES]) = par;
+  }
+  __syncthreads();
+}
 // every CTA re-reduces the partials in the same order (identical clip coefficient everywhere), then
 // g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
-__device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid, bool fused_norm) {
+__device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid, bool fused_norm, uint8_t* ring, uint64_t* abars) {
   double s = 0.0;
   if (fused_norm) {
     for (int i = tid; i < cx.n_norm_tile; i += SK_THREADS) s += static_cast<double>(sk_ld(cx.norm_tile + i));
@@ -1489,6 +1590,10 @@ __device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, i
   __syncthreads();
   const float b1 = sc.beta1, b2 = sc.beta2, eps = sc.adam_eps;
   const float step = sv.step_size, ibc2 = sv.inv_bc2_sqrt;
+  if (cx.adam_stream) {
+    sk_adam_stream(cx, ring, abars, cta, ncta, tid, coef, b1, b2, eps, step, ibc2);
+    return;
+  }
   const long long n4 = cx.n_flat / 4;
   float4* t4 = reinterpret_cast<float4*>(cx.theta);
   const float4* g4 = reinterpret_cast<const float4*>(cx.grad);
@@ -1620,9 +1725,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int gw = cta * SK_WARPS + warp, nw = ncta * SK_WARPS;
   const StepCtx& cx = prm.cx;
-  static_assert(sizeof(HgCtrl) <= 256 && sizeof(HgTile) * SK_NUM_GEMM <= 640 && sizeof(StepVars) <= 128, "control block layout");
+  static_assert(sizeof(HgCtrl) <= 192 && (ADAM_STAGES + 1) * 8 <= 64 && sizeof(HgTile) * SK_NUM_GEMM <= 640 && sizeof(StepVars) <= 128, "control block layout");
   if (warp == 2 && lane < SK_NUM_GEMM && cta < cx.gph[lane].total_tiles) first_tiles[lane] = hg_decode(prm.probs, cx.gph[lane], cta);
-  const uint32_t tmem_d = hg_setup(ctrl, warp, lane);
+  if (tid == 0) {   // barriers of the Adam stream (sk_adam_stream) + their parity word
+    uint64_t* abars = reinterpret_cast<uint64_t*>(smem + 192);
+    for (int s = 0; s < ADAM_STAGES; ++s) mbar_init(&abars[s], 1);
+    abars[ADAM_STAGES] = 0;
+  }
+  const uint32_t tmem_d = hg_setup(ctrl, warp, lane);   // (fences the barrier initialisation, __syncthreads)
   HgPipe pp;
   unsigned int target = 0;
   const int B = cx.B;
@@ -1810,7 +1920,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
             break;
           }
           case PH_NORM: sk_norm(cx, cta, ncta, shd, tid); break;
-          case PH_ADAM: sk_adam(cx, sv, cta, ncta, shd, tid, norm_fused); break;
+          case PH_ADAM: sk_adam(cx, sv, cta, ncta, shd, tid, norm_fused, ring, reinterpret_cast<uint64_t*>(smem + 192)); break;
           default: break;
         }
        }
