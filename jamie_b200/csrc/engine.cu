@@ -107,6 +107,8 @@ struct jb_engine {
   std::vector<PackMap> packmap;
   long long n_packed = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
+  __half* theta_eval_h = nullptr;   // fp16 copy of the folded inference weights (operands of the fp16 layers of the chain)
+  bool eval_f16 = true;             // JB_EVAL_F16=0: the whole chain in TF32 with fp32 activations
   __half *theta_hi = nullptr, *theta_lo = nullptr;   // fp16 operand planes of theta (same element offsets)
   float* state_slab = nullptr;   // one allocation: theta | adam_m | adam_v | theta_hi, theta_lo
   size_t slab_bytes = 0;
@@ -130,6 +132,7 @@ struct jb_engine {
   double* norm_part = nullptr;
   float *norm_tile = nullptr, *norm_small = nullptr;   // fused clip norm (stepk.cuh)
   int norm_fuse = 1;                                   // JB_NORM_FUSE=0: always sweep the gradient buffer
+  int norm_tile_cap = 0;
   unsigned int* bar = nullptr;          // grid barrier counter of k_step
   unsigned long long* d_ts = nullptr;   // phase timestamps (profiling)
   // workspaces
@@ -439,8 +442,8 @@ int build_step(jb_engine* e, int B) {
       if (s.acc_dynamic) hp.acc_flag = &e->ctl->accum;
       if (s.dyn >= 0) hp.dyn_scale = e->dyn + s.dyn;
       hp.fuse = s.fuse; hp.fuse_arg = s.fuse_arg;
-      if (s.out == nullptr) {   // weight gradient: per-warp sums of squares of what the epilogue stored
-        hp.norm_out = e->norm_tile + n_norm_tile;
+      if (s.out == nullptr) {   // weight gradient: per-warp sums of squares of what the epilogue stored (offset now, base below)
+        hp.norm_out = reinterpret_cast<float*>(static_cast<uintptr_t>(n_norm_tile) * 4 + 4);   // +4: distinguishes offset 0 from "none"
         n_norm_tile += hp.tiles_m * hp.tiles_n * jb::HG_NEPI;
       }
       if (s.fuse && hp.tiles_m > jb::HG_CLUSTER) return fail("fused stage with %d M tiles", hp.tiles_m);
@@ -448,6 +451,15 @@ int build_step(jb_engine* e, int B) {
     }
     cx.gph[g] = jb::hg_phase_finalize(e->h_probs.data(), first, static_cast<int>(st[g].size()));
   }
+  if (n_norm_tile > e->norm_tile_cap) {
+    if (e->norm_tile) cudaFree(e->norm_tile);
+    e->norm_tile = nullptr; e->norm_tile_cap = 0;
+    CU(cudaMalloc(&e->norm_tile, static_cast<size_t>(n_norm_tile) * 4));
+    e->norm_tile_cap = n_norm_tile;
+  }
+  if (n_norm_tile > 0) CU(cudaMemset(e->norm_tile, 0, static_cast<size_t>(n_norm_tile) * 4));
+  for (jb::HgProblem& hp : e->h_probs)
+    if (hp.norm_out != nullptr) hp.norm_out = e->norm_tile + (reinterpret_cast<uintptr_t>(hp.norm_out) - 4) / 4;
   for (size_t q = 0; q < e->h_probs.size(); ++q) e->h_prm->probs[q] = e->h_probs[q];
   // ---- the rest of the step context
   cx.B = B; cx.L = L; cx.LP = e->LP; cx.ldmv = e->ldmv;
@@ -509,7 +521,7 @@ int build_step(jb_engine* e, int B) {
     }
   }
   cx.norm_tile = e->norm_tile; cx.norm_small = e->norm_small; cx.n_norm_tile = n_norm_tile;
-  cx.norm_fuse = e->norm_fuse && n_norm_tile <= 8192 ? 1 : 0;
+  cx.norm_fuse = e->norm_fuse ? 1 : 0;
   {
     int nr = 0;
     auto rng = [&](const Seg& sg) { cx.norm_rng[nr][0] = static_cast<int>(sg.off); cx.norm_rng[nr][1] = sg.cols; ++nr; };
@@ -612,6 +624,7 @@ int prepare_eval(jb_engine* e, cudaStream_t s) {
       ++e->launches;
     }
   }
+  if (e->eval_f16) { jb::k_to_half<<<296, 256, 0, s>>>(e->theta_eval, e->theta_eval_h, e->n_flat); ++e->launches; }
   CU(cudaGetLastError());
   e->eval_dirty = false;
   return 0;
@@ -626,6 +639,44 @@ int run_chain(jb_engine* e, int from, int to, const float* in, int ld_in, int ro
   ModSegs& mf = e->ms[from];
   const int Df = e->D[from];
   std::vector<GemmProblem> tab;
+  if (e->eval_persist && e->eval_f16) {
+    // fp16 chain: the wide layers exchange fp16 activations and read fp16 weights (half the operand bytes); the first
+    // layer of each half reads fp32 (the caller's rows, the fp32 embedding) as TF32; embeddings and outputs stay fp32
+    const __half* Th = e->theta_eval_h;
+    __half* hA = reinterpret_cast<__half*>(bufA);
+    __half* hB = reinterpret_cast<__half*>(bufB);
+    auto addc = [&](const void* A, int lda, const Seg& Wt, const Seg& bt, void* C, int ldc, int N, int K, int epi, int f16_ops, int out_f16) {
+      GemmProblem g;
+      int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N >= e->eval_bn256_min ? 256 : 128));
+      if (out_f16 && bn < 64) bn = 64;
+      const void* Bw = f16_ops ? static_cast<const void*>(Th + Wt.off) : static_cast<const void*>(T + Wt.off);
+      int rc = jb::gemm_chain_problem_fill(&g, A, lda, Bw, Wt.ld, C, ldc, rows, N, K, bn, epi, T + bt.off, jb::LRELU, f16_ops, out_f16);
+      if (rc) return fail("eval tensor map encode failed (%d)", rc);
+      jb::gemm_table_finalize(&g, 1);
+      tab.push_back(g);
+      return 0;
+    };
+    const int h2f = r8(2 * Df), hf = r8(Df);
+    if (addc(in, ld_in, mf.W1, mf.b1, hA, h2f, 2 * Df, Df, jb::EPI_BIAS_LRELU, 0, 1)) return 1;
+    if (addc(hA, h2f, mf.W2, mf.b2, hB, hf, Df, 2 * Df, jb::EPI_BIAS_LRELU, 1, 1)) return 1;
+    if (to < 0) {
+      if (addc(hB, hf, mf.Wmv, mf.bmv, out, ld_out, L, Df, jb::EPI_BIAS, 1, 0)) return 1;
+    } else {
+      ModSegs& mt = e->ms[to];
+      const int Dt = e->D[to];
+      const int h2t = r8(2 * Dt), ht = r8(Dt);
+      if (addc(hB, hf, mf.Wmv, mf.bmv, bufA, e->LP, L, Df, jb::EPI_BIAS, 1, 0)) return 1;
+      if (addc(bufA, e->LP, mt.W3, mt.b3, hB, ht, Dt, L, jb::EPI_BIAS_LRELU, 0, 1)) return 1;
+      if (addc(hB, ht, mt.W4, mt.b4, hA, h2t, 2 * Dt, Dt, jb::EPI_BIAS_LRELU, 1, 1)) return 1;
+      if (addc(hA, h2t, mt.W5, mt.b5, out, ld_out, Dt, 2 * Dt, jb::EPI_BIAS, 1, 0)) return 1;
+    }
+    CU(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, s));
+    for (size_t k = 0; k < tab.size(); ++k) {
+      CU(jb::gemm_launch_persistent(d_tab + k, tab[k], e->num_sms, s, k > 0));
+      ++e->launches;
+    }
+    return 0;
+  }
   auto add = [&](const float* A, int lda, const Seg& Wt, const Seg& bt, int n_rows_w, float* C, int ldc, int N, int K, int epi) {
     GemmProblem g;
     (void)n_rows_w;
@@ -777,9 +828,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   c0.seed = cfg->seed;
   CU(cudaMemcpy(e->ctl, &c0, sizeof c0, cudaMemcpyHostToDevice));
   CU(cudaMalloc(&e->norm_part, jb::SK_MAX_CTAS * sizeof(double)));
-  CU(cudaMalloc(&e->norm_tile, 8192 * sizeof(float)));
+  e->norm_tile = nullptr; e->norm_tile_cap = 0;   // sized by build_step (one partial per epilogue warp and weight-gradient work item)
   CU(cudaMalloc(&e->norm_small, jb::SK_MAX_CTAS * 4 * sizeof(float)));
-  CU(cudaMemset(e->norm_tile, 0, 8192 * sizeof(float)));
   CU(cudaMemset(e->norm_small, 0, jb::SK_MAX_CTAS * 4 * sizeof(float)));
   if (const char* pv = getenv("JB_NORM_FUSE")) e->norm_fuse = atoi(pv) != 0;
   CU(cudaMalloc(&e->bar, 128));
@@ -813,6 +863,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   if (const char* pv = getenv("JB_EVAL_CHUNK")) { if (atoi(pv) >= 128) e->eval_chunk = atoi(pv); }
   if (const char* pv = getenv("JB_EVAL_BN256_MIN")) e->eval_bn256_min = atoi(pv);
   if (const char* pv = getenv("JB_EVAL_PERSIST")) e->eval_persist = atoi(pv) != 0;
+  if (const char* pv = getenv("JB_EVAL_F16")) e->eval_f16 = atoi(pv) != 0;
+  CU(cudaMalloc(&e->theta_eval_h, static_cast<size_t>(e->n_flat + 32) * 2));
   // eval workspaces: two slots of chunk activations
   {
     const int Dm = e->D[0] > e->D[1] ? e->D[0] : e->D[1];
@@ -840,7 +892,7 @@ void jb_destroy(jb_engine* e) {
   void* ptrs[] = {e->state_slab, e->grad, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
                   e->arena, e->parts_arena, e->bar, e->d_ts, e->ev_a, e->ev_b, e->ev_in, e->ev_out,
-                  e->d_ev_probs};
+                  e->d_ev_probs, e->theta_eval_h, e->norm_tile, e->norm_small};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 2; ++k) if (e->ev_stream[k]) cudaStreamDestroy(e->ev_stream[k]);
   delete e->h_prm;

@@ -1,6 +1,10 @@
-// Persistent single-pass TF32 GEMM for the inference chain (modal_predict / transform): C = act(A * B^T + bias) with
-// A [M, K] and B [N, K] both K-major fp32 (TFLOAT32 tensor maps: TMA rounds to nearest on load), M in the tens of
-// thousands (a chunk of cells), N and K the layer widths.
+// Persistent single-pass GEMM for the inference chain (modal_predict / transform): C = act(A * B^T + bias) with
+// A [M, K] and B [N, K] both K-major, M in the tens of thousands (a chunk of cells), N and K the layer widths.
+// Operands: fp32 read as TF32 (TFLOAT32 tensor maps: TMA rounds to nearest on load) or fp16 (kind::f16: the same 128-byte
+// k-block rows hold 64 elements instead of 32, so a layer moves half the operand bytes through L2 -> shared memory, the
+// measured bound of the TF32 chain). Output: fp32, or fp16 when the next layer takes fp16 operands: the wide layers of
+// the chain exchange fp16 activations (11-bit significand, like the TF32 rounding they replace), the first layer reads
+// the caller's fp32 rows as TF32 and the last one writes fp32.
 //
 // One CTA per SM walks the output tiles (tile = blockIdx.x, += gridDim.x; the N tiles of one M tile are adjacent, so
 // neighbouring SMs share the A rows in L2). The operand ring, the barriers and the TMEM allocation live for the whole
@@ -11,6 +15,7 @@
 // epilogue from every tile but the last.
 #pragma once
 #include "gemm_tf32.cuh"
+#include "hgemm.cuh"   // umma_f16, umma_idesc_f16, make_tmap_f16
 
 namespace jb {
 
@@ -39,7 +44,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
   const int pM = P.M, pN = P.N, epi = P.epi;
   const float* const pbias = P.bias;
   const float slope = P.slope;
-  const int num_kb = (P.K + GEMM_BK - 1) / GEMM_BK;
+  const int f16 = P.f16_ops, out_f16 = P.out_f16;
+  const int bk = f16 ? 2 * GEMM_BK : GEMM_BK;   // elements per k-block (128 bytes per row either way)
+  const int num_kb = (P.K + bk - 1) / bk;
   const int b_bytes = bn * GEMM_BK * 4;
   const int kb_bytes = GEMM_A_STAGE_BYTES + b_bytes;
   int nstages = GEMM_TILE_SMEM / kb_bytes;
@@ -84,8 +91,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
           uint64_t* bar = &ctrl->full[s];
           mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kb_bytes));
           uint8_t* sa = tiles + s * kb_bytes;
-          tma_load_2d(sa, tmA, bar, kb * GEMM_BK, m0);                        // box {32 k, 128 rows}
-          tma_load_2d(sa + GEMM_A_STAGE_BYTES, tmB, bar, kb * GEMM_BK, n0);   // box {32 k, bn rows}
+          tma_load_2d(sa, tmA, bar, kb * bk, m0);                        // box {128 bytes of k, 128 rows}
+          tma_load_2d(sa + GEMM_A_STAGE_BYTES, tmB, bar, kb * bk, n0);   // box {128 bytes of k, bn rows}
         }
         __syncwarp();
         if (++s == nstages) { s = 0; ph ^= 1; }
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer: accumulator buffer j & 1 for the CTA's j-th tile
-    const uint32_t idesc = umma_idesc_tf32(GEMM_BM, bn, 0, 0);
+    const uint32_t idesc = f16 ? umma_idesc_f16(GEMM_BM, bn, 0, 0) : umma_idesc_tf32(GEMM_BM, bn, 0, 0);
     const uint64_t d_hi = umma_smem_desc(0u, 16u, 1024u, 2u);   // K-major, SWIZZLE_128B
     const uint32_t tiles_u32 = smem_u32(tiles);
     int s = 0;
@@ -112,8 +119,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
           const uint64_t da0 = d_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
           const uint64_t db0 = d_hi | static_cast<uint64_t>(((sa + GEMM_A_STAGE_BYTES) >> 4) & 0x3FFFu);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
-            umma_tf32(acc, da0 + 2u * k, db0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {   // four instructions of 32 bytes of K each
+            if (f16) umma_f16(acc, da0 + 2u * k, db0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_tf32(acc, da0 + 2u * k, db0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&ctrl->empty[s]);                              // frees the ring slot when these MMAs have read it
           if (kb == num_kb - 1) umma_commit(&ctrl->acc_full[buf]);   // ... and hands the accumulator to the epilogue
         }
@@ -136,6 +145,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
       mbar_wait(&ctrl->acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * bn);
+      if (out_f16) {
+        // fp16 output: 64 columns per store (32 rows x 128 bytes in the same swizzle)
+        for (int c0 = 0; c0 < bn; c0 += 64) {
+          const int nbase = n0 + c0;
+          float v[64];
+          tmem_ld_32x32(lane_base + static_cast<uint32_t>(c0), *reinterpret_cast<float(*)[32]>(&v[0]));
+          tmem_ld_32x32(lane_base + static_cast<uint32_t>(c0 + 32), *reinterpret_cast<float(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          if (c0 + 64 >= bn) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->acc_empty[buf]);
+          }
+          if (nbase >= pN || m0 + q * 32 >= pM) continue;
+          if (epi != EPI_STORE) {
+            const float bl0 = (nbase + lane < pN) ? __ldg(pbias + nbase + lane) : 0.f;
+            const float bl1 = (nbase + 32 + lane < pN) ? __ldg(pbias + nbase + 32 + lane) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x0 = v[i] + __shfl_sync(0xffffffffu, bl0, i), x1 = v[32 + i] + __shfl_sync(0xffffffffu, bl1, i);
+              if (epi == EPI_BIAS_LRELU) { x0 = leaky(x0, slope); x1 = leaky(x1, slope); }
+              v[i] = x0; v[32 + i] = x1;
+            }
+          }
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {   // 16-byte unit i = columns 8 i .. 8 i + 7
+            const __half2 h0 = __floats2half2_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+            const __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(stw + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                           *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmC, stw, nbase, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
       for (int c0 = 0; c0 < bn; c0 += 32) {
         const int nbase = n0 + c0;
         float v[32];
@@ -180,6 +232,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_persistent_kernel(c
 inline int gemm_problem_set_store_map(GemmProblem* g) {
   PFN_tmapEncodeTiled fn = tmap_encode_fn();
   if (!fn) return -1;
+  if (g->out_f16) {   // C [M, N] fp16, pitch ldc halves: 64 x 32 boxes in the 128-byte swizzle
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->N), static_cast<cuuint64_t>(g->M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(g->ldc) * sizeof(__half)};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&g->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g->C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+  }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->N), static_cast<cuuint64_t>(g->M)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(g->ldc) * sizeof(float)};
   cuuint32_t box[2] = {32, 32};
@@ -189,12 +250,37 @@ inline int gemm_problem_set_store_map(GemmProblem* g) {
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// A problem of the inference chain: K-major operands, fp32-as-TF32 or fp16 (A, B: [rows, K] with pitches in elements of
+// their type); C fp32 or fp16 (ldc in elements of its type).
+inline int gemm_chain_problem_fill(GemmProblem* g, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                                   int bn, int epi, const float* bias, float slope, int f16_ops, int out_f16) {
+  int rc;
+  if (!f16_ops) {
+    if ((rc = gemm_problem_fill(g, static_cast<const float*>(A), lda, 0, static_cast<const float*>(B), ldb, 0, static_cast<float*>(C), ldc, M, N, K, bn,
+                                epi, bias, slope, 0)))
+      return rc;
+  } else {
+    *g = GemmProblem{};
+    if ((rc = make_tmap_f16(&g->tmA, static_cast<const __half*>(A), K, M, lda, 64, GEMM_BM))) return rc;
+    if ((rc = make_tmap_f16(&g->tmB, static_cast<const __half*>(B), K, N, ldb, 64, bn))) return rc;
+    g->C = static_cast<float*>(C); g->bias = bias;
+    g->M = M; g->N = N; g->K = K; g->ldc = ldc;
+    g->bn = bn; g->epi = epi;
+    g->tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    g->tiles_n = (N + bn - 1) / bn;
+    g->slope = slope;
+  }
+  g->f16_ops = f16_ops; g->out_f16 = out_f16;
+  return gemm_problem_set_store_map(g);
+}
+
 // One problem (filled by gemm_problem_fill with K-major operands, no split, + gemm_problem_set_store_map), one CTA per
 // SM at most.
 inline cudaError_t gemm_launch_persistent(const GemmProblem* dev_prob, const GemmProblem& host_prob, int sms, cudaStream_t st,
                                           bool use_pdl) {
   if (host_prob.a_mn || host_prob.b_mn || host_prob.split || host_prob.accumulate || host_prob.bn > 256) return cudaErrorInvalidValue;
-  if ((host_prob.ldc & 3) != 0 || (reinterpret_cast<uintptr_t>(host_prob.C) & 15) != 0) return cudaErrorInvalidValue;   // TMA store
+  if ((host_prob.ldc & (host_prob.out_f16 ? 7 : 3)) != 0 || (reinterpret_cast<uintptr_t>(host_prob.C) & 15) != 0) return cudaErrorInvalidValue;   // TMA store
+  if (host_prob.out_f16 && (host_prob.bn & 63) != 0) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);

@@ -84,6 +84,9 @@ struct alignas(128) GemmProblem {
   int accumulate;  // C += result (one CTA owns the tile: no atomics)
   float slope;
   int split;       // 1: error-compensated 3xTF32 on pre-split hi/lo planes, see the header comment
+  // persistent inference GEMM only (gemm_persistent.cuh):
+  int f16_ops;     // A and B are fp16 tensors (kind::f16, 64 elements per k-block) instead of fp32 read as TF32
+  int out_f16;     // C is an fp16 tensor (the next layer's operand): 64 x 32 output boxes
 };
 
 // First CTA of every problem of a launch, passed BY VALUE (constant bank): the CTA -> problem lookup costs no dependent

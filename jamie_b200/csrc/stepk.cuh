@@ -1179,7 +1179,9 @@ __device__ __forceinline__ bool sk_rescale_c(const StepCtx& cx, int gt, int nt, 
   const bool need = flag[0] != 0;
   const float sx = reinterpret_cast<const float*>(flag)[1], sy = reinterpret_cast<const float*>(flag)[2];
   __syncthreads();
-  if (gt == 0) cx.dyn[0] = need ? sy : 1.f;
+  // every CTA publishes the (identical) inverse scale before its own epilogues read it: no barrier separates this from the
+  // GEMM below in the fast path, so a single writer would race with the other CTAs' readers
+  if (tid == 0) cx.dyn[0] = need ? sy : 1.f;
   if (!need) return false;
   const int B = cx.B, L = cx.L;
 #pragma unroll 1
@@ -1199,7 +1201,7 @@ __device__ __forceinline__ bool sk_rescale_dmulv(const StepCtx& cx, int gt, int 
   const bool need = flag[0] != 0;
   const float sx = reinterpret_cast<const float*>(flag)[1], sy = reinterpret_cast<const float*>(flag)[2];
   __syncthreads();
-  if (gt == 0) cx.dyn[1] = need ? sy : 1.f;
+  if (tid == 0) cx.dyn[1] = need ? sy : 1.f;
   if (!need) return false;
   const int B = cx.B, L2 = 2 * cx.L;
 #pragma unroll 1
@@ -1692,6 +1694,11 @@ __device__ __forceinline__ void sk_prefetch_state(const StepCtx& cx, int gt, int
 __global__ void k_hsplit_flat(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
     h_split(src[i], hi[i], lo[i]);
+}
+// fp32 -> fp16 over a flat buffer (the folded inference weights)
+__global__ void k_to_half(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
 }
 __global__ void k_set_accum(Ctl* ctl, int v) { ctl->accum = v; }
 // after a launch of k_step: advance the plan cursor / optimizer step count / Philox stream, clear the injection flag
