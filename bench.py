@@ -381,7 +381,11 @@ def main():
     eng.set_f_dense(None)
     idx0, idx1 = make_plan(n, W + K, rng, cs)
     eng.upload_plan(idx0, idx1, np.full(W + K, 0.5), stream)
-    gt = eng.grad_tensor() if world > 1 else None
+    gx = None
+    if world > 1:
+        from jamie_b200.dp import GradExchange
+        gx = GradExchange(eng)
+        eng.upload_plan(idx0, idx1, np.full(W + K, 0.5), stream)   # (the step tables were rebuilt around the exchange buffer)
     if args.predict_only:
         p = predict_leg(eng, torch, peaks, stream)
         emit({k: p[k] for k in ('value', 'ms', 'e2e', 'gpu_launches')})
@@ -394,7 +398,7 @@ def main():
         else:
             for _ in range(k):                  # backward | one all-reduce of the flat gradient buffer | update
                 eng.step_backward(stream)
-                dist.all_reduce(gt)
+                gx.all_reduce()
                 eng.step_update(stream)
 
     def sync_all():
@@ -460,7 +464,7 @@ def main():
                     pending -= 1
             else:
                 eng.step_backward_hostbatch(b[0].data_ptr(), b[1].data_ptr(), i0e[s], i1e[s], 0.5, stream)
-                dist.all_reduce(gt)
+                gx.all_reduce()
                 eng.step_update(stream)
                 out = eng.read_losses(2, stream)[s & 1]
         while pending:
@@ -521,7 +525,7 @@ def main():
             'metric': 'train cells/sec (fwd+bwd+Adam)', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
             'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f16x2 (fp16 hi/lo split operands, fp32 accumulate: fp32-class products)', 'data': 'synthetic',
-            'config': workload_config(world),
+            'config': dict(workload_config(world), **({'exchange': gx.mode + ' all-reduce of the flat gradient buffer (jamie_b200/dp.py)'} if gx is not None else {})),
             'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': Ke, 'note': 'per step: host gather of the batch rows into pinned memory, H2D of rows + cell ids, '
                                          'step kernel, D2H of the 8 loss scalars; jb_hostbatch_submit / jb_hostbatch_wait keep '

@@ -97,6 +97,10 @@ int jb_train_steps(jb_engine* e, int nsteps, void* stream);
 int jb_step_backward(jb_engine* e, void* stream);
 int jb_step_update(jb_engine* e, void* stream);
 int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats);
+/* Make the engine write its gradients into a caller-owned device buffer of at least the jb_grad_buffer size (16-byte
+ * aligned), e.g. one allocated in NVLink symmetric / multicast memory so that the exchange can be a multimem all-reduce
+ * instead of an NCCL call. dev_ptr = NULL returns to the engine's own buffer. The caller keeps the buffer alive. */
+int jb_set_grad_buffer(jb_engine* e, float* dev_ptr, long long n_floats);
 /* batch_step=False (jamie/jamie.py:744-749): accumulate gradients over several jb_step_backward calls, one
  * jb_step_update per epoch. accumulate != 0 makes the following backward passes add into the gradient buffer instead of
  * overwriting it (a device-side flag: no rebuild, no synchronisation). The optimizer step count (Adam bias correction)

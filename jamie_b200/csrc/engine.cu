@@ -107,6 +107,7 @@ struct jb_engine {
   std::vector<PackMap> packmap;
   long long n_packed = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
+  float* grad_own = nullptr;        // the engine's own gradient buffer while a caller-owned one is in use (jb_set_grad_buffer)
   __half* theta_eval_h = nullptr;   // fp16 copy of the folded inference weights (operands of the fp16 layers of the chain)
   bool eval_f16 = true;             // JB_EVAL_F16=0: the whole chain in TF32 with fp32 activations
   __half *theta_hi = nullptr, *theta_lo = nullptr;   // fp16 operand planes of theta (same element offsets)
@@ -133,7 +134,8 @@ struct jb_engine {
   float *norm_tile = nullptr, *norm_small = nullptr;   // fused clip norm (stepk.cuh)
   int norm_fuse = 1;                                   // JB_NORM_FUSE=0: always sweep the gradient buffer
   int norm_tile_cap = 0;
-  unsigned int* bar = nullptr;          // grid barrier counter of k_step
+  unsigned int* bar = nullptr;          // grid barrier counters of k_step: [0] and [32], used by alternate launches
+  int bar_parity = 0;
   unsigned long long* d_ts = nullptr;   // phase timestamps (profiling)
   // workspaces
   char* arena = nullptr;
@@ -591,15 +593,16 @@ int launch_step(jb_engine* e, int lo, int hi, int nsteps, int use_stage, cudaStr
     e->accumulate_dev = e->accumulate;
     ++e->launches;
   }
-  CU(cudaMemsetAsync(e->bar, 0, sizeof(unsigned int), s));
   int row_bias = lo > jb::PH_GATHER ? -1 : 0;
-  unsigned int* bar = e->bar;
-  void* args[] = {e->h_prm, &lo, &hi, &nsteps, &bar, &use_stage, &row_bias, &ts};
-  if (launch_kstep_raw(e, args, s)) return 1;
   const int fwd = lo == jb::PH_GATHER ? nsteps : 0, upd = hi == jb::PH_COUNT ? nsteps : 0;
-  jb::k_ctl_advance<<<1, 1, 0, s>>>(e->ctl, fwd, upd, fwd > 0 ? 1 : 0);
+  int3 adv = make_int3(fwd, upd, fwd > 0 ? 1 : 0);
+  unsigned int* bar = e->bar + (e->bar_parity ? 32 : 0);   // this launch's counter; the kernel zeroes the other one
+  unsigned int* bar_next = e->bar + (e->bar_parity ? 0 : 32);
+  e->bar_parity ^= 1;
+  void* args[] = {e->h_prm, &lo, &hi, &nsteps, &bar, &use_stage, &row_bias, &ts, &adv, &bar_next};
+  if (launch_kstep_raw(e, args, s)) return 1;
   CU(cudaGetLastError());
-  e->launches += 2;
+  e->launches += 1;
   return 0;
 }
 
@@ -832,8 +835,8 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMalloc(&e->norm_small, jb::SK_MAX_CTAS * 4 * sizeof(float)));
   CU(cudaMemset(e->norm_small, 0, jb::SK_MAX_CTAS * 4 * sizeof(float)));
   if (const char* pv = getenv("JB_NORM_FUSE")) e->norm_fuse = atoi(pv) != 0;
-  CU(cudaMalloc(&e->bar, 128));
-  CU(cudaMemset(e->bar, 0, 128));
+  CU(cudaMalloc(&e->bar, 512));
+  CU(cudaMemset(e->bar, 0, 512));
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
   if (const char* pv = getenv("JB_WGRAD_MODE")) e->wgrad_mode = strcmp(pv, "single") == 0 ? jb::HG_SINGLE : jb::HG_MEDIUM;
   if (const char* pv = getenv("JB_MAX_KSPLIT")) { if (atoi(pv) >= 1) e->max_ksplit = atoi(pv); }
@@ -889,7 +892,7 @@ void jb_destroy(jb_engine* e) {
     if (e->ev_slot_free[k]) cudaEventDestroy(e->ev_slot_free[k]);
     if (e->ev_loss[k]) cudaEventDestroy(e->ev_loss[k]);
   }
-  void* ptrs[] = {e->state_slab, e->grad, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
+  void* ptrs[] = {e->state_slab, e->grad_own ? e->grad_own : e->grad, e->theta_eval, e->bn_run, e->data[0], e->data[1], e->p_diag,
                   e->p_dense, e->f_dense, e->plan_idx[0], e->plan_idx[1], e->plan_kl, e->out_loss, e->ctl, e->norm_part,
                   e->arena, e->parts_arena, e->bar, e->d_ts, e->ev_a, e->ev_b, e->ev_in, e->ev_out,
                   e->d_ev_probs, e->theta_eval_h, e->norm_tile, e->norm_small};
@@ -1118,6 +1121,21 @@ int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats) {
   *n_floats = e->n_flat + 8;  // flat gradients + the loss scalars appended by the loss phase
   return 0;
 }
+int jb_set_grad_buffer(jb_engine* e, float* dev_ptr, long long n_floats) {
+  if (!e) return fail("null argument");
+  CU(cudaDeviceSynchronize());
+  if (dev_ptr == nullptr) {
+    if (e->grad_own) e->grad = e->grad_own;
+  } else {
+    if (n_floats < e->n_flat + 8) return fail("gradient buffer too small (%lld floats, need %lld)", n_floats, e->n_flat + 8);
+    if (reinterpret_cast<uintptr_t>(dev_ptr) & 15) return fail("gradient buffer must be 16-byte aligned");
+    if (!e->grad_own) e->grad_own = e->grad;
+    CU(cudaMemset(dev_ptr, 0, static_cast<size_t>(e->n_flat + 8) * 4));   // the padding stays zero forever
+    e->grad = dev_ptr;
+  }
+  e->step_B = 0;   // the step tables hold the address
+  return 0;
+}
 int jb_set_grad_accumulate(jb_engine* e, int accumulate) {
   if (!e) return fail("null argument");
   e->accumulate = accumulate ? 1 : 0;   // reaches the device control block with the next launch (no re-build, no sync)
@@ -1247,9 +1265,11 @@ int jb_bench_stage(jb_engine* e, int phase, int iters, float* avg_us, double* fl
       fl += 2.0 * e->h_probs[i].M * e->h_probs[i].N * e->h_probs[i].K;
   }
   int lo = phase < 0 ? 0 : phase, hi = phase + 1, one = 1, zero = 0;
-  unsigned int* bar = e->bar;
+  unsigned int* bar = e->bar + 64;     // (a single phase: no grid barrier)
   unsigned long long* ts = nullptr;
-  void* args[] = {e->h_prm, &lo, &hi, &one, &bar, &zero, &zero, &ts};
+  int3 adv0 = make_int3(0, 0, 0);
+  unsigned int* bar_next = e->bar + 96;
+  void* args[] = {e->h_prm, &lo, &hi, &one, &bar, &zero, &zero, &ts, &adv0, &bar_next};
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
   int nwarm = 3;

@@ -1716,9 +1716,13 @@ __global__ void k_ctl_advance(Ctl* ctl, int d_cursor, int d_adam, int clear_inje
 // update-only launch (the cursor was already advanced by the backward launch). ts (optional): CTA 0 records the global
 // timer at kernel start (ts[0]) and at the end of every phase (ts[1 + step * PH_COUNT + phase]); behind those, every CTA
 // records {SM clock at phase begin, SM clock at the end of its work, global time at the end of its work} per phase.
+// The launch is self-contained (no memset / control kernels around it, which cost a stream operation each in the split
+// data-parallel and host-batch paths): `bar` points at the barrier counter of this launch, bar_next at the one of the
+// next launch, which is zeroed here; when the last phase is done CTA 0 advances the control block by adv = {plan rows, optimizer
+// steps, clear the injection flag} (every CTA read it before its first grid barrier).
 __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ StepParams prm, int ph_lo, int ph_hi, int nsteps,
                                                          unsigned int* bar, int use_stage, int row_bias,
-                                                         unsigned long long* ts) {
+                                                         unsigned long long* ts, int3 adv, unsigned int* bar_next) {
   extern __shared__ uint8_t sk_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~uintptr_t(1023));
   HgCtrl* ctrl = reinterpret_cast<HgCtrl*>(smem);
@@ -1742,18 +1746,21 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
   const uint32_t tmem_d = hg_setup(ctrl, warp, lane);   // (fences the barrier initialisation, __syncthreads)
   HgPipe pp;
   unsigned int target = 0;
+  if (cta == 0 && tid == 0) *bar_next = 0u;
   const int B = cx.B;
   const bool norm_fused = cx.norm_fuse != 0 && ph_lo <= PH_DG3 && ph_hi > PH_ADAM;   // every weight-gradient epilogue of the step is in this launch
-  // (the control block is read by thread 0 at every step start, not held in registers: everything that lives across the
-  // phase loop costs registers in every phase body, and the Adam sweep spills first)
+  // the counters CTA 0 advances at the end are read once, before this CTA's first grid barrier (used by thread 0 only)
+  long long ctl_cursor0 = 0, ctl_adam0 = 0;
+  unsigned long long ctl_stream0 = 0;
+  if (tid == 0) { ctl_cursor0 = cx.ctl->cursor; ctl_adam0 = cx.ctl->adam_t; ctl_stream0 = cx.ctl->stream_id; }
 
   if (ts != nullptr && cta == 0 && tid == 0) ts[0] = globaltimer_ns();
   long long clk_begin = clock64();
   for (int s = 0; s < nsteps; ++s) {
     if (tid == 0) {
       StepVars v;
-      const long long cursor0 = cx.ctl->cursor, adam0 = cx.ctl->adam_t;
-      const unsigned long long stream0 = cx.ctl->stream_id, seed = cx.ctl->seed;
+      const long long cursor0 = ctl_cursor0, adam0 = ctl_adam0;
+      const unsigned long long stream0 = ctl_stream0, seed = cx.ctl->seed;
       const int inject = cx.ctl->inject, accum = cx.ctl->accum, host_slot = cx.ctl->host_slot;
       v.row = cursor0 + s + row_bias;
       const long long t = adam0 + s + 1;
@@ -1957,6 +1964,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
         clk_begin = clock64();
       }
     }
+  }
+  if (cta == 0 && tid == 0 && (adv.x | adv.y | adv.z) != 0) {
+    Ctl* c = cx.ctl;
+    c->cursor = ctl_cursor0 + adv.x;
+    c->stream_id = ctl_stream0 + static_cast<unsigned long long>(adv.x);
+    c->adam_t = ctl_adam0 + adv.y;
+    if (adv.z) c->inject = 0;
   }
   hg_teardown(tmem_d, warp);
 }

@@ -286,6 +286,15 @@ class Engine:
         _lib.check(self.lib.jb_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def set_grad_buffer(self, tensor):
+        """Gradients go into a caller-owned CUDA float32 tensor (e.g. NVLink symmetric memory); None restores the engine's own."""
+        if tensor is None:
+            _lib.check(self.lib.jb_set_grad_buffer(self.h, None, 0))
+            self._ext_grad = None
+        else:
+            _lib.check(self.lib.jb_set_grad_buffer(self.h, C.c_void_p(tensor.data_ptr()), C.c_longlong(tensor.numel())))
+            self._ext_grad = tensor   # keep it alive
+
     def grad_tensor(self):
         """The gradient buffer as a torch CUDA tensor view (no copy) -- what torch.distributed all-reduces."""
         import torch

@@ -439,7 +439,8 @@ class JAMIE(UnionCom):
             eng.set_grad_accumulate(False)
         if world > 1:
             import torch.distributed as dist
-            gt = eng.grad_tensor()
+            from .dp import GradExchange
+            gx = GradExchange(eng)   # NVLS multimem / peer-memory all-reduce on an NVSwitch box, else NCCL (gloo on CPU tests)
         self.model.train()
         # O(batch) sampler for large datasets; seeded from numpy's global generator, so np.random.seed(...) in the caller
         # still makes a run reproducible
@@ -495,7 +496,7 @@ class JAMIE(UnionCom):
                     last_of_epoch = (s_ + 1) % len_dataloader == 0
                     if self.batch_step or last_of_epoch:
                         if world > 1:
-                            dist.all_reduce(gt)
+                            gx.all_reduce()
                         eng.step_update(stream)
             # The steps above are only enqueued: the next chunk's plan is sampled on the host while the GPU runs them.
             # Its size uses the largest streak this chunk can end with, so it never crosses an early-stop decision.
