@@ -581,7 +581,10 @@ int launch_kstep_raw(jb_engine* e, void** args, cudaStream_t s) {
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = jb::HG_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = 2;
+  // JB_COOP=0 (profilers that cannot replay a cooperative cluster launch): a plain cluster launch; the grid still fits the
+  // device in one wave, which is all the software grid barrier needs when nothing else runs on the GPU
+  static const bool coop = !(getenv("JB_COOP") && atoi(getenv("JB_COOP")) == 0);
+  cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
   CU(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(jb::k_step), args));
   return 0;
 }
