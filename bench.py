@@ -512,7 +512,9 @@ def main():
                      'unit': 'TFLOP/s', 'frac': ALG_FLOPS_PER_STEP / (gus * 1e-6) / 1e12 / peaks['bf16_tflops_sustained'],
                      'gemm_phases_us': round(gus, 2), 'flops_per_step': ALG_FLOPS_PER_STEP,
                      'note': 'all 12 GEMM phases of a step together: algorithmic FLOPs (one fp32-class product per MAC; the '
-                             'kernel issues three fp16 tensor-core passes per product) over their in-kernel time'}
+                             'kernel issues three fp16 tensor-core passes per product) over their in-kernel time. Since the '
+                             'cluster fusion these phases also contain the BatchNorm / dropout / loss tails and their grid '
+                             'barriers (the separate element-wise phases are gone), so this is a lower bound of the GEMM rate'}
         fit = None
         if world == 1 and not args.no_fit:
             eng.close()
