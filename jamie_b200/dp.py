@@ -38,6 +38,9 @@ class GradExchange:
             self.buf = eng.grad_tensor()
 
     def _setup_symm(self, want):
+        # measured on B200: multimem 360 us/step vs two-shot 381 at 8 ranks, but 466 vs NCCL's 366 at 2 ranks
+        if want == 'auto' and self.dist.get_world_size(self.group) < 4:
+            raise RuntimeError('NCCL is faster below 4 ranks')
         import torch.distributed._symmetric_memory as symm_mem
         torch = self.torch
         _, n = self.eng.grad_buffer()
@@ -49,9 +52,6 @@ class GradExchange:
         self.eng.set_grad_buffer(buf)
         self.buf = buf
         self.handle = hdl
-        # measured on B200: multimem 360 us/step vs two-shot 381 at 8 ranks, but 466 vs NCCL's 366 at 2 ranks
-        if want == 'auto' and self.dist.get_world_size(self.group) < 4:
-            raise RuntimeError('NCCL is faster below 4 ranks')
         modes = ['multimem', 'two_shot'] if want == 'auto' else [want]
         err = None
         for m in modes:
