@@ -154,6 +154,7 @@ struct jb_engine {
   int fuse_enabled = 1;      // JB_FUSE=0: BatchNorm / reconstruction / reparameterisation as separate phases (the B > 512 path)
   int fused = 0;             // the current step tables use the cluster-fused tails
   int merge_latent = 1;      // JB_MERGE_LATENT=0: LATLOSS / LATFIN as separate phases even without F
+  int fuse_ks = 1;           // JB_FUSE_KS=0: HEADS / DG3 as one CTA per M tile instead of K split over the cluster
   int accumulate = 0, accumulate_dev = 0;
   int wgrad_mode = jb::HG_MEDIUM;
   int wgrad_bn = 256;
@@ -307,7 +308,7 @@ struct StageSpec {   // one problem of a GEMM phase before its split-K factor is
   float out_scale;
   int acc_dynamic;
   int dyn;           // index into StepCtx::dyn of an extra dynamic output factor, or -1
-  int fuse = 0, fuse_arg = 0;
+  int fuse = 0, fuse_arg = 0, fuse_ks = 0;
 };
 
 int build_step(jb_engine* e, int B) {
@@ -350,7 +351,7 @@ int build_step(jb_engine* e, int B) {
         static const int bn_layer[6] = {0, 1, -1, 2, 3, -1};
         if (bn_layer[stage] >= 0) { sp.fuse = jb::FUSE_BN_FWD; sp.fuse_arg = bn_layer[stage] * 2 + i; }
         else if (stage == 5) { sp.fuse = jb::FUSE_REC; sp.fuse_arg = i; }
-        else if (stage == 2 && 2 * L <= 64) { sp.fuse = jb::FUSE_HEADS; sp.fuse_arg = i; }
+        else if (stage == 2 && 2 * L <= 64) { sp.fuse = jb::FUSE_HEADS; sp.fuse_arg = i; sp.fuse_ks = e->fuse_ks && n_in >= 8 * jb::HG_BK; }
         // narrow column blocks only pay where the main loop is long (K >= 256); short-K stages keep 64
         if (stage != 2 && n_out > 32 && n_in >= 256) sp.bn = stage == 0 || stage == 4 ? fbn2(2 * e->D[0], 2 * e->D[1]) : fbn2(e->D[0], e->D[1]);
       }
@@ -366,7 +367,7 @@ int build_step(jb_engine* e, int B) {
     auto dgrad = [&](int stage, HPlanes dY, int lddy, const Seg& s, jb::Parts* out, int lddx, int n_out, int n_in) {
       StageSpec sp{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0, -1};
       if (fused && stage == 8) {   // d c: the LATBC phase becomes the tail (no F, one column block)
-        if (e->f_dense == nullptr && e->merge_latent && L <= 64) { sp.fuse = jb::FUSE_LATBC; sp.fuse_arg = i; }
+        if (e->f_dense == nullptr && e->merge_latent && L <= 64) { sp.fuse = jb::FUSE_LATBC; sp.fuse_arg = i; sp.fuse_ks = e->fuse_ks && n_out >= 8 * jb::HG_BK; }
       } else if (fused) {   // the dgrad result feeds a BatchNorm backward: stage 6 -> dec2, 7 -> dec1, 9 -> enc2, 10 -> enc1
         const int k = stage == 6 ? 3 : (stage == 7 ? 2 : (stage == 9 ? 1 : 0));
         sp.fuse = jb::FUSE_BN_BWD; sp.fuse_arg = k * 2 + i;
@@ -404,7 +405,7 @@ int build_step(jb_engine* e, int B) {
       int k = 1;
       if (s.out != nullptr) {
         const int kb = (s.K + jb::HG_BK - 1) / jb::HG_BK;
-        k = s.fuse ? 1 : e->grid / (tiles > 0 ? tiles : 1);
+        k = s.fuse ? (s.fuse_ks ? jb::HG_CLUSTER : 1) : e->grid / (tiles > 0 ? tiles : 1);
         if (k > kb / 2) k = kb / 2;
         if (k > e->max_ksplit) k = e->max_ksplit;
         if (k < 1) k = 1;
@@ -441,9 +442,11 @@ int build_step(jb_engine* e, int B) {
                                    pstride, 0, s.out_scale, jb::LRELU);
       if (rc) return fail("hgemm problem fill failed (%d) for M%d N%d K%d lda%d ldb%d bn%d mode%d", rc, s.M, s.N, s.K, s.lda, s.ldb, s.bn, s.mode);
       if (hp.ksplit != k && s.out != nullptr) s.out->n = hp.ksplit;
+      if (s.fuse && s.out != nullptr) s.out->n = 1;   // fused tails store the finished tensor (K parts are summed over DSMEM)
+      if (s.fuse_ks && hp.ksplit != jb::HG_CLUSTER) return fail("cluster K split needs %d parts, got %d", jb::HG_CLUSTER, hp.ksplit);
       if (s.acc_dynamic) hp.acc_flag = &e->ctl->accum;
       if (s.dyn >= 0) hp.dyn_scale = e->dyn + s.dyn;
-      hp.fuse = s.fuse; hp.fuse_arg = s.fuse_arg;
+      hp.fuse = s.fuse; hp.fuse_arg = s.fuse_arg; hp.fuse_ks = s.fuse_ks;
       if (s.out == nullptr) {   // weight gradient: per-warp sums of squares of what the epilogue stored (offset now, base below)
         hp.norm_out = reinterpret_cast<float*>(static_cast<uintptr_t>(n_norm_tile) * 4 + 4);   // +4: distinguishes offset 0 from "none"
         n_norm_tile += hp.tiles_m * hp.tiles_n * jb::HG_NEPI;
@@ -862,6 +865,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
     if (const char* pv = getenv("JB_STEP_CTAS")) { const int v = atoi(pv) / jb::HG_CLUSTER * jb::HG_CLUSTER; if (v >= jb::HG_CLUSTER && v <= e->grid) e->grid = v; }
     if (const char* pv = getenv("JB_FUSE")) e->fuse_enabled = atoi(pv) != 0;
     if (const char* pv = getenv("JB_MERGE_LATENT")) e->merge_latent = atoi(pv) != 0;
+    if (const char* pv = getenv("JB_FUSE_KS")) e->fuse_ks = atoi(pv) != 0;
   }
   // rows per pass of the folded chain: one 128-row M tile per SM, so every GEMM of the chain is a whole number of waves
   // (measured on B200, 1M rows 512 -> 512: 8192 rows 59.1, 9472 rows 66.7, 18944 rows 69.0 M rows/s)

@@ -85,6 +85,9 @@ struct alignas(128) HgProblem {
                            // epilogue warp at norm_out[item * HG_NEPI + e] (the clip norm without a sweep over the gradient buffer)
   int fuse;                // 0 = plain epilogue; otherwise the kind of tail (StepFuse)
   int fuse_arg;            // which layer / modality the tail works on
+  int fuse_ks;             // fused problem with ONE column block whose K range is split over the HG_CLUSTER ranks instead
+                           // (ksplit = HG_CLUSTER; work items M tile major, rank = K part): the tail sums the four staged
+                           // partial tiles through distributed shared memory. For GEMMs with a handful of M tiles.
 };
 
 struct HgPhase {           // one GEMM phase = a table of problems
@@ -186,7 +189,7 @@ __device__ __forceinline__ HgTile hg_decode(const HgProblem* __restrict__ probs,
   const int tt = local / ksplit;
   const int tiles_n = P.tiles_n;
   T.bn = P.bn;
-  if (P.fuse) {
+  if (P.fuse && !P.fuse_ks) {
     T.m0 = (tt % HG_CLUSTER) * HG_BM;
     T.n0 = (tt / HG_CLUSTER) * T.bn;
   } else {
@@ -649,7 +652,7 @@ inline HgPhase hg_phase_finalize(HgProblem* all, int first, int count) {
   for (int i = 0; i < count; ++i) {
     all[first + i].tile_base = base;
     ph.base[i] = base;
-    base += all[first + i].fuse ? HG_CLUSTER * all[first + i].tiles_n : all[first + i].tiles_m * all[first + i].tiles_n * all[first + i].ksplit;
+    base += (all[first + i].fuse && !all[first + i].fuse_ks) ? HG_CLUSTER * all[first + i].tiles_n : all[first + i].tiles_m * all[first + i].tiles_n * all[first + i].ksplit;
   }
   ph.total_tiles = base;
   return ph;

@@ -895,16 +895,30 @@ __device__ __forceinline__ void sk_draw_eps(const StepCtx& cx, const StepVars& s
   }
 }
 // heads tile [mu | logvar] (2 L <= 64 columns) -> z = mu + (exp(logvar/2) + 1e-7) eps   (jamie/model.py:230-240)
-__device__ __forceinline__ void sk_tail_heads(const StepCtx& cx, const StepVars& sv, const ModCtx& M, int mod, const float* __restrict__ bias, const TailArgs& ta) {
+// element (r, c) of the staged tile of cluster rank rk (distributed shared memory)
+__device__ __forceinline__ float tail_stage_remote(const TailArgs& ta, int r, int c, uint32_t rk) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(mapa_shared(smem_u32(reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, c & ~3)) + (c & 3)), rk)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sk_tail_heads(const StepCtx& cx, const StepVars& sv, const ModCtx& M, int mod, const float* __restrict__ bias, const TailArgs& ta, int ks) {
   const int B = cx.B, L = cx.L;
+  if (ks) cluster_sync_all();   // K split over the cluster: the four partial tiles are staged; this CTA finishes rows [32 rank, +32)
+  const int r_lo = ks ? 32 * static_cast<int>(ta.rank) : 0, n_r = ks ? 32 : HG_BM;
 #pragma unroll 1
-  for (int idx = ta.tid; idx < HG_BM * L; idx += SK_THREADS) {
-    const int r = idx / L, l = idx - r * L;
+  for (int idx = ta.tid; idx < n_r * L; idx += SK_THREADS) {
+    const int r = r_lo + idx / L, l = idx % L;
     const int b = ta.m0 + r;
     if (b >= B) break;
     const float e = sk_ld(M.eps + static_cast<long long>(b) * cx.LP + l);
-    const float mu = reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, l & ~3))[l & 3] + __ldg(bias + l);
-    const float lv = reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, (L + l) & ~3))[(L + l) & 3] + __ldg(bias + L + l);
+    float mu = __ldg(bias + l), lv = __ldg(bias + L + l);
+    if (ks) {
+#pragma unroll
+      for (uint32_t rk = 0; rk < HG_CLUSTER; ++rk) { mu += tail_stage_remote(ta, r, l, rk); lv += tail_stage_remote(ta, r, L + l, rk); }
+    } else {
+      mu += reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, l & ~3))[l & 3];
+      lv += reinterpret_cast<const float*>(hg_stage_ptr(ta.stage, r, (L + l) & ~3))[(L + l) & 3];
+    }
     const long long om = static_cast<long long>(b) * cx.ldmv;
     M.mulv.ptr[om + l] = mu;
     M.mulv.ptr[om + L + l] = lv;
@@ -1413,12 +1427,13 @@ __device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
 // decoder dgrad tile d c (L <= 64 columns, no F) -> g = d(loss)/dc / den and the row partials of d sigma: the LATBC phase as
 // the tail of the DG3 work item. Thread = (row, group of 8 latent columns): every load of a thread is independent (the
 // first version walked 8 rows per warp one after the other: 8 L2 round trips, 19 us for the phase).
-__device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M, int mod, const TailArgs& ta) {
+__device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M, int mod, const TailArgs& ta, int ks) {
+  if (ks) cluster_sync_all();   // K split over the cluster: sum the four staged partial tiles; this CTA finishes rows [32 rank, +32)
   const int B = cx.B, L = cx.L, LP = cx.LP;
   const float k_cos = cx.gs * cx.sc.w[2] * 32.f * 2.f / (static_cast<float>(B) * static_cast<float>(L));
   const float k_f = mod == 0 ? cx.gs * cx.sc.w[3] * 2.f / (static_cast<float>(B) * static_cast<float>(L)) : 0.f;
-  const int r = ta.tid >> 2, q = ta.tid & 3, row = ta.m0 + r;
-  const bool rok = row < B;
+  const int r = (ks ? 32 * static_cast<int>(ta.rank) : 0) + (ta.tid >> 2), q = ta.tid & 3, row = ta.m0 + r;
+  const bool rok = row < B && (!ks || ta.tid < 128);
   const int rr = rok ? row : B - 1;
   const float rden = 1.f / sk_ld(M.den + rr);
   float p3 = 0.f, p4 = 0.f, p5 = 0.f;
@@ -1427,7 +1442,19 @@ __device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M
     const long long o = static_cast<long long>(rr) * LP + l0;
     float z[8], c[8], S[8], lr[8], g[8];
     ld8(M.z + o, z); ld8(M.c + o, c); ld8(M.S + o, S); ld8(cx.lat_r + o, lr);
-    const float4 d0 = *hg_stage_ptr(ta.stage, r, l0), d1 = *hg_stage_ptr(ta.stage, r, l0 + 4);
+    float4 d0, d1;
+    if (ks) {
+      d0 = make_float4(0.f, 0.f, 0.f, 0.f); d1 = d0;
+      const int rs = ta.tid < 128 ? r : 0;
+#pragma unroll
+      for (uint32_t rk = 0; rk < HG_CLUSTER; ++rk) {
+        const float4 a = ld_shared_cluster_f4(mapa_shared(smem_u32(hg_stage_ptr(ta.stage, rs, l0)), rk));
+        const float4 b = ld_shared_cluster_f4(mapa_shared(smem_u32(hg_stage_ptr(ta.stage, rs, l0 + 4)), rk));
+        d0.x += a.x; d0.y += a.y; d0.z += a.z; d0.w += a.w; d1.x += b.x; d1.y += b.y; d1.z += b.z; d1.w += b.w;
+      }
+    } else {
+      d0 = *hg_stage_ptr(ta.stage, r, l0); d1 = *hg_stage_ptr(ta.stage, r, l0 + 4);
+    }
     const float dcd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1832,8 +1859,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
             case FUSE_BN_FWD: sk_tail_bn_fwd(cx, sv, cx.bn[arg >> 1][arg & 1], P.bias, ta); break;
             case FUSE_BN_BWD: sk_tail_bn_bwd(cx, sv, cx.bn[arg >> 1][arg & 1], ta); break;
             case FUSE_REC: sk_tail_rec(cx, sv, cx.m[arg], P.bias, ta); break;
-            case FUSE_HEADS: sk_tail_heads(cx, sv, cx.m[arg], arg, P.bias, ta); break;
-            case FUSE_LATBC: sk_tail_latbc(cx, cx.m[arg], arg, ta); break;
+            case FUSE_HEADS: sk_tail_heads(cx, sv, cx.m[arg], arg, P.bias, ta, P.fuse_ks); break;
+            case FUSE_LATBC: sk_tail_latbc(cx, cx.m[arg], arg, ta, P.fuse_ks); break;
             default: break;
           }
           fence_proxy_async_smem();   // the scratch is operand-ring memory: generic accesses before the next TMA writes
