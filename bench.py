@@ -393,8 +393,9 @@ def main():
         return
 
     def run_steps(k):
-        if world == 1:
-            eng.train_steps(k, stream)          # ONE launch of the persistent step kernel for k optimizer steps
+        if world == 1 or gx.mode == 'kernel':
+            eng.train_steps(k, stream)          # ONE launch of the persistent step kernel for k optimizer steps (N > 1: the
+                                                # kernel exchanges the gradients over peer memory itself)
         else:
             for _ in range(k):                  # backward | one all-reduce of the flat gradient buffer | update
                 eng.step_backward(stream)

@@ -101,6 +101,17 @@ int jb_grad_buffer(jb_engine* e, float** dev_ptr, long long* n_floats);
  * aligned), e.g. one allocated in NVLink symmetric / multicast memory so that the exchange can be a multimem all-reduce
  * instead of an NCCL call. dev_ptr = NULL returns to the engine's own buffer. The caller keeps the buffer alive. */
 int jb_set_grad_buffer(jb_engine* e, float* dev_ptr, long long n_floats);
+/* In-kernel gradient exchange over peer memory (NVLink / NVSwitch): grad_ptrs[q] = rank q's gradient buffer (each rank
+ * passed its own to jb_set_grad_buffer; all of them mapped into this process, e.g. NVLink symmetric memory), flag_ptrs[q]
+ * = rank q's zero-initialised scratch block of at least jb_exchange_scratch_bytes(). With an exchange configured the
+ * step kernel sums the gradients across the ranks itself (reduce-scatter + all-gather + clip-norm partials inside the
+ * persistent kernel, between WGRAD and ADAM): jb_train_steps(n) is ONE launch for n data-parallel optimizer steps and the
+ * caller must not all-reduce jb_grad_buffer. All ranks must run the same number of steps in lockstep. world <= 1 or
+ * NULL pointers turn it off. grad_multicast = the NVSwitch multicast address bound to all ranks' gradient buffers, or
+ * NULL: with it the sum is taken inside the switch (multimem.ld_reduce) and broadcast with multimem.st. */
+int jb_set_exchange(jb_engine* e, int rank, int world, float* const* grad_ptrs, unsigned int* const* flag_ptrs,
+                    float* grad_multicast);
+long long jb_exchange_scratch_bytes(void);
 /* batch_step=False (jamie/jamie.py:744-749): accumulate gradients over several jb_step_backward calls, one
  * jb_step_update per epoch. accumulate != 0 makes the following backward passes add into the gradient buffer instead of
  * overwriting it (a device-side flag: no rebuild, no synchronisation). The optimizer step count (Adam bias correction)

@@ -107,6 +107,7 @@ struct jb_engine {
   std::vector<PackMap> packmap;
   long long n_packed = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr, *theta_eval = nullptr;
+  float* xg[8]{}; unsigned int* xf[8]{}; float* xmc = nullptr; int xrank = 0, xworld = 0; long long x_adam0 = 0;   // in-kernel exchange (jb_set_exchange)
   float* grad_own = nullptr;        // the engine's own gradient buffer while a caller-owned one is in use (jb_set_grad_buffer)
   __half* theta_eval_h = nullptr;   // fp16 copy of the folded inference weights (operands of the fp16 layers of the chain)
   bool eval_f16 = true;             // JB_EVAL_F16=0: the whole chain in TF32 with fp32 activations
@@ -561,6 +562,9 @@ int build_step(jb_engine* e, int B) {
   sc.grad_scale = 1.0f / static_cast<float>(e->cfg.world_size > 0 ? e->cfg.world_size : 1);
   sc.B = B; sc.L = L; sc.D[0] = e->D[0]; sc.D[1] = e->D[1];
   cx.gs = e->gs; cx.inv_gs = inv_gs;
+  for (int q = 0; q < 8; ++q) { cx.xg[q] = e->xg[q]; cx.xf[q] = e->xf[q]; }
+  cx.xrank = e->xrank; cx.xworld = e->xworld; cx.xmc = e->xworld > 1 ? e->xmc : nullptr; cx.x_adam0 = e->x_adam0;
+  cx.xdbg = getenv("JB_XCHG_DBG") ? atoi(getenv("JB_XCHG_DBG")) : 0;
   cx.adam_stream = 1;
   if (const char* pv = getenv("JB_ADAM_STREAM")) cx.adam_stream = atoi(pv);
   cx.prefetch_state = 0;   // measured: WGRAD +9.4 us (the prefetch competes with the operand loads), ADAM only -3.5 us
@@ -953,6 +957,7 @@ int jb_set_adam_state(jb_engine* e, const float* m, const float* v, long long n,
   if (copy_packed(e, e->adam_m, const_cast<float*>(m), true) || copy_packed(e, e->adam_v, const_cast<float*>(v), true)) return 1;
   jb::Ctl c;
   CU(cudaMemcpy(&c, e->ctl, sizeof c, cudaMemcpyDeviceToHost));
+  if (e->xworld > 1) { e->x_adam0 += t - c.adam_t; e->step_B = 0; }   // exchange epochs keep counting from where they were
   c.adam_t = t;
   CU(cudaMemcpy(e->ctl, &c, sizeof c, cudaMemcpyHostToDevice));
   return 0;
@@ -1141,6 +1146,27 @@ int jb_set_grad_buffer(jb_engine* e, float* dev_ptr, long long n_floats) {
     e->grad = dev_ptr;
   }
   e->step_B = 0;   // the step tables hold the address
+  return 0;
+}
+long long jb_exchange_scratch_bytes(void) { return 256 + 8LL * jb::SK_MAX_CTAS * 8; }
+int jb_set_exchange(jb_engine* e, int rank, int world, float* const* grad_ptrs, unsigned int* const* flag_ptrs, float* grad_multicast) {
+  if (!e) return fail("null argument");
+  CU(cudaDeviceSynchronize());
+  e->xworld = 0; e->xmc = nullptr;
+  if (world > 1 && grad_ptrs && flag_ptrs) {
+    if (world > 8 || rank < 0 || rank >= world) return fail("exchange over %d ranks (rank %d): at most 8 ranks of one box", world, rank);
+    if (world != e->cfg.world_size) return fail("exchange world %d != jb_config.world_size %d", world, e->cfg.world_size);
+    if (grad_ptrs[rank] != e->grad) return fail("grad_ptrs[rank] must be the buffer given to jb_set_grad_buffer");
+    for (int q = 0; q < world; ++q) {
+      if (!grad_ptrs[q] || !flag_ptrs[q]) return fail("null peer pointer for rank %d", q);
+      e->xg[q] = grad_ptrs[q]; e->xf[q] = flag_ptrs[q];
+    }
+    e->xrank = rank; e->xworld = world; e->xmc = grad_multicast;
+    jb::Ctl c;   // exchange epochs count from the optimizer step at which the (zeroed) scratch blocks were handed over
+    CU(cudaMemcpy(&c, e->ctl, sizeof c, cudaMemcpyDeviceToHost));
+    e->x_adam0 = c.adam_t;
+  }
+  e->step_B = 0;
   return 0;
 }
 int jb_set_grad_accumulate(jb_engine* e, int accumulate) {

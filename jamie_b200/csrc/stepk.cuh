@@ -136,6 +136,10 @@ struct StepCtx {
   int dbg_repeat;                  // 1
   int merge_latent;                // no F: LATLOSS / LATFIN folded into COMBINE / LATBZ / the DEC1 and DGH phases (optimistic operand scales)
   int eps_early;                   // the reparameterisation noise is drawn during ENC1 (heads tail fused)
+  // in-kernel data-parallel exchange (sk_exchange); xworld <= 1: off
+  float* xg[8]; unsigned int* xf[8]; int xrank, xworld, xdbg;   // xdbg: timing experiments (JB_XCHG_DBG bit 0: no sweep, bit 1: no cross-GPU barriers)
+  long long x_adam0;               // optimizer step count when the exchange was configured (epoch 0 of the flags)
+  float* xmc;                      // NVSwitch multicast address of the gradient buffers (NULL: peer loads / stores)
   int adam_stream;                 // JB_ADAM_STREAM=0: plain-load Adam sweep
   int prefetch_state;              // JB_PREFETCH_STATE=1 (default 0, measured slower): L2 prefetch of theta, m, v during WGRAD
   unsigned long long phase_mask;   // bit ph set: the phase runs (fused layers drop the BatchNorm / REC / REPARAM phases)
@@ -1472,6 +1476,151 @@ __device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M
   }
 }
 
+// ------------------------------------------------------------------------------------------------ in-kernel gradient exchange
+// Data-parallel training without leaving the step kernel (one all-reduce of the flat gradient buffer per
+// step). Every rank's gradient buffer lives in NVLink symmetric memory and is mapped into every peer (xg[q]); xf[q] is
+// rank q's flag / partial block: [0, R) = "gradients ready" epochs (slot = source rank), [16] = "delivered" arrival counter,
+// doubles from byte 256: [src rank][SK_MAX_CTAS] partial sums of squares of the reduced slices.
+//   1. (after the WGRAD grid barrier) tell every peer "my gradients of this step are complete"; wait for all peers
+//   2. reduce-scatter + all-gather in one sweep: this rank owns 1/R of the buffer; each CTA sums its part of the slice over
+//      the ranks in rank order (peer loads over NVLink), writes the sum into EVERY rank's buffer (peer stores), and
+//      leaves the sum of squares of what it reduced in every rank's partial block: the clip norm of the summed gradient
+//      needs no sweep and no further collective
+//   3. grid barrier (all of this rank's remote writes are issued and fenced), tell every peer "my slice is delivered";
+//      wait for all peers. ADAM then reads the local buffer.
+// Spins are bounded (a protocol error traps instead of hanging the box).
+__device__ __forceinline__ void xchg_signal(const StepCtx& cx, int slot0, unsigned int epoch, int tid) {
+  if (tid < cx.xworld) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(cx.xf[tid] + slot0 + cx.xrank), "r"(epoch) : "memory");
+  }
+}
+__device__ __forceinline__ void xchg_wait(const StepCtx& cx, int slot0, unsigned int epoch, int tid) {
+  if (tid < cx.xworld) {
+    const unsigned int* f = cx.xf[cx.xrank] + slot0 + tid;
+    unsigned int v, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (++spins > (1u << 26)) __trap();
+    } while (static_cast<int>(v - epoch) < 0);
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// sum of [a, b) (float4 units) over the ranks, in rank order, written to every rank; returns this thread's sum of squares.
+// MAXR loads per element are always issued (ranks beyond the world re-read the local buffer and are not added): no
+// predicated loads into the register array.
+template <int MAXR>
+__device__ __forceinline__ double xchg_sweep(const StepCtx& cx, long long a, long long b, int tid) {
+  constexpr int U = 8 / MAXR;   // elements per thread per round: U x MAXR = 8 loads of 16 bytes in flight (an NVLink round
+                                // trip is 3 - 5 us: with one element per round the sweep was 60 us at two ranks)
+  const int R = cx.xworld;
+  float sq = 0.f;   // at most a few dozen squares per thread: fp32 here, double from the CTA reduction on (FP64 is slow on B200)
+#pragma unroll 1
+  for (long long i0 = a + tid; i0 < b; i0 += U * SK_THREADS) {
+    float4 v[U][MAXR];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * SK_THREADS < b ? i0 + u * SK_THREADS : b - 1;   // clamped, not predicated
+#pragma unroll
+      for (int q = 0; q < MAXR; ++q) v[u][q] = ld_sys_f4(reinterpret_cast<const float4*>(cx.xg[q < R ? q : cx.xrank]) + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * SK_THREADS;
+      if (i < b) {
+        float4 s = v[u][0];
+#pragma unroll
+        for (int q = 1; q < MAXR; ++q)
+          if (q < R) { s.x += v[u][q].x; s.y += v[u][q].y; s.z += v[u][q].z; s.w += v[u][q].w; }
+        if (i * 4 < cx.n_flat) sq += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+#pragma unroll
+        for (int q = 0; q < MAXR; ++q)
+          if (q < R) reinterpret_cast<float4*>(cx.xg[q])[i] = s;
+      }
+    }
+  }
+  return static_cast<double>(sq);
+}
+// the same sweep through the switch (NVLS): multimem.ld_reduce returns the sum over all ranks' copies of the address in ONE
+// load (reduced inside the NVSwitch), multimem.st writes every rank's copy in ONE store: 1/R of the instructions and of
+// the bytes through this GPU's links. Every rank receives the same bits; the order of the in-switch sum is the switch's.
+__device__ __forceinline__ double xchg_sweep_mc(const StepCtx& cx, long long a, long long b, int tid) {
+  constexpr int U = 8;
+  float sq = 0.f;
+  float4* const mc = reinterpret_cast<float4*>(cx.xmc);
+#pragma unroll 1
+  for (long long i0 = a + tid; i0 < b; i0 += U * SK_THREADS) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * SK_THREADS < b ? i0 + u * SK_THREADS : b - 1;   // clamped, not predicated
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * SK_THREADS;
+      if (i < b) {
+        const float4 s = v[u];
+        if (i * 4 < cx.n_flat) sq += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+      }
+    }
+  }
+  return static_cast<double>(sq);
+}
+__device__ __forceinline__ void sk_exchange(const StepCtx& cx, unsigned int epoch, int cta, int ncta, int tid, double* shd) {
+  const int R = cx.xworld, me = cx.xrank;
+  if (!(cx.xdbg & 2)) {
+    if (cta == 0) xchg_signal(cx, 0, epoch, tid);
+    xchg_wait(cx, 0, epoch, tid);
+  }
+  const long long n4 = (cx.n_flat + 8) / 4;                       // gradients + the 8 loss scalars behind them
+  const long long lo = n4 * me / R, hi = n4 * (me + 1) / R;       // this rank's slice
+  const long long per = (hi - lo + ncta - 1) / ncta;
+  const long long a = lo + per * cta, b = a + per < hi ? a + per : hi;
+  double sq = 0.0;
+  if (cx.xdbg & 1) sq = 1.0;
+  else if (cx.xmc != nullptr) sq = xchg_sweep_mc(cx, a, b, tid);
+  else if (R <= 2) sq = xchg_sweep<2>(cx, a, b, tid);
+  else if (R <= 4) sq = xchg_sweep<4>(cx, a, b, tid);
+  else sq = xchg_sweep<8>(cx, a, b, tid);
+  shd[tid] = sq;
+  __syncthreads();   // (also: every thread's peer stores of the sweep are ordered before the fence below)
+  for (int o = SK_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) shd[tid] += shd[tid + o];
+    __syncthreads();
+  }
+  // "delivered": every CTA of every rank counts itself in at every rank (one remote atomic per destination) once its part
+  // of the slice and its norm partial are written and fenced; a CTA goes on to ADAM when its own rank's counter shows all
+  // R x ncta arrivals of this epoch. No grid barrier and no single signalling CTA on the way (the phase's own grid barrier
+  // is skipped as well): the counter orders the local CTAs among themselves too.
+  if (tid < R) {
+    reinterpret_cast<double*>(reinterpret_cast<char*>(cx.xf[tid]) + 256)[me * SK_MAX_CTAS + cta] = shd[0];
+    __threadfence_system();
+    if (!(cx.xdbg & 2) || tid == me)
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(cx.xf[tid] + 16) : "memory");
+  }
+  if (tid == 0) {
+    const unsigned int want = epoch * static_cast<unsigned int>(((cx.xdbg & 2) ? 1 : R) * ncta);
+    const unsigned int* f = cx.xf[me] + 16;
+    unsigned int v, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (++spins > (1u << 26)) __trap();
+    } while (static_cast<int>(v - want) < 0);
+    __threadfence_system();
+  }
+  __syncthreads();
+  fence_proxy_async_global();   // the reduced gradients (peer stores) -> the Adam stream's bulk loads
+}
+
 // ------------------------------------------------------------------------------------------------ clip + Adam
 __device__ __forceinline__ void sk_norm(const StepCtx& cx, int cta, int ncta, double* shd, int tid) {
   const long long n4 = cx.n_flat / 4;
@@ -1600,7 +1749,11 @@ __device__ __forceinline__ void sk_adam_stream(const StepCtx& cx, uint8_t* ring,
 // g *= grad_scale * clip;  m, v, theta updated with torch.optim.Adam's formulas (jamie/jamie.py:739-741).
 __device__ __forceinline__ void sk_adam(const StepCtx& cx, const StepVars& sv, int cta, int ncta, double* shd, int tid, bool fused_norm, uint8_t* ring, uint64_t* abars) {
   double s = 0.0;
-  if (fused_norm) {
+  if (cx.xworld > 1) {   // partial sums of squares of the reduced slices, delivered by every rank (sk_exchange)
+    const double* xp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(cx.xf[cx.xrank]) + 256);
+    for (int i = tid; i < cx.xworld * SK_MAX_CTAS; i += SK_THREADS)
+      if (i % SK_MAX_CTAS < ncta) s += sk_ld(xp + i);
+  } else if (fused_norm) {
     for (int i = tid; i < cx.n_norm_tile; i += SK_THREADS) s += static_cast<double>(sk_ld(cx.norm_tile + i));
     for (int i = tid; i < 4 * ncta; i += SK_THREADS) s += static_cast<double>(sk_ld(cx.norm_small + i));
   } else {
@@ -1775,11 +1928,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
   unsigned int target = 0;
   if (cta == 0 && tid == 0) *bar_next = 0u;
   const int B = cx.B;
-  const bool norm_fused = cx.norm_fuse != 0 && ph_lo <= PH_DG3 && ph_hi > PH_ADAM;   // every weight-gradient epilogue of the step is in this launch
+  const bool norm_fused = cx.norm_fuse != 0 && ph_lo <= PH_DG3 && ph_hi > PH_ADAM && cx.xworld <= 1;   // every weight-gradient epilogue of the step is in this launch
   // the counters CTA 0 advances at the end are read once, before this CTA's first grid barrier (used by thread 0 only)
   long long ctl_cursor0 = 0, ctl_adam0 = 0;
   unsigned long long ctl_stream0 = 0;
   if (tid == 0) { ctl_cursor0 = cx.ctl->cursor; ctl_adam0 = cx.ctl->adam_t; ctl_stream0 = cx.ctl->stream_id; }
+  const long long ctl_xepoch = cx.xworld > 1 ? cx.ctl->adam_t - cx.x_adam0 : 0;   // exchange epochs = optimizer steps: the same on every rank
 
   if (ts != nullptr && cta == 0 && tid == 0) ts[0] = globaltimer_ns();
   long long clk_begin = clock64();
@@ -1960,7 +2114,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
               if ((ncta - 1 - (it % ncta)) == cta) sk_final_item(cx, sv, it, sh, tid, warp, lane);
             break;
           }
-          case PH_NORM: sk_norm(cx, cta, ncta, shd, tid); break;
+          case PH_NORM:
+            if (cx.xworld > 1) sk_exchange(cx, static_cast<unsigned int>(ctl_xepoch + s + 1), cta, ncta, tid, shd);
+            else sk_norm(cx, cta, ncta, shd, tid);
+            break;
           case PH_ADAM: sk_adam(cx, sv, cta, ncta, shd, tid, norm_fused, ring, reinterpret_cast<uint64_t*>(smem + 192)); break;
           default: break;
         }
@@ -1980,7 +2137,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_step(const __grid_constant__ 
       // the optimizer writes and writes nothing that the optimizer reads, so it overlaps Adam's tail; the barrier after
       // GATHER orders both before ENC1
       const bool fused_next = ph == PH_ADAM && ph_lo == PH_GATHER && s + 1 < nsteps;
-      if (!last && !fused_next) {
+      const bool xchg_done = ph == PH_NORM && cx.xworld > 1;   // sk_exchange ends with its own (cross-GPU) barrier
+      if (!last && !fused_next && !xchg_done) {
         target += static_cast<unsigned int>(ncta);
         grid_barrier(bar, target);
       } else if (fused_next) {

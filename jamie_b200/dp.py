@@ -7,8 +7,14 @@ the buffer with multimem.ld_reduce and broadcasts it with multimem.st), which mo
 exposes that as ``torch.ops.symm_mem.multimem_all_reduce_`` on buffers allocated in NVLink symmetric memory, so the
 engine is pointed at such a buffer (``jb_set_grad_buffer``) and writes its gradients there in the first place.
 
-Order of preference at 4 or more ranks: multimem (NVSwitch multicast) -> two-shot over peer memory -> NCCL; below that
-NCCL (measured faster at two ranks). ``JB_DP_ALLREDUCE`` forces one.
+Round 2, second half: the exchange moved INTO the step kernel (``mode == 'kernel'``, jb_set_exchange): every rank's
+gradient buffer and a small scratch block live in symmetric memory mapped into all peers; between its WGRAD and ADAM phases
+the persistent kernel signals its peers, reduces its 1/R slice with peer loads, writes the sum into every rank's buffer
+with peer stores, and delivers the clip-norm partials the same way. A data-parallel run is then ONE launch for any number
+of optimizer steps, like the single-GPU run, and ``all_reduce()`` is a no-op.
+
+Order of preference: kernel (peer memory) -> multimem / two-shot all-reduce (4+ ranks) -> NCCL. ``JB_DP_ALLREDUCE``
+forces one of ``kernel | multimem | two_shot | nccl``.
 """
 import os
 
@@ -24,7 +30,7 @@ class GradExchange:
         self.buf = None
         want = os.environ.get('JB_DP_ALLREDUCE', 'auto')
         backend = dist.get_backend(self.group)
-        if backend == 'nccl' and want in ('auto', 'multimem', 'two_shot'):
+        if backend == 'nccl' and want in ('auto', 'kernel', 'multimem', 'two_shot'):
             try:
                 self._setup_symm(want)
             except Exception as ex:   # no multicast / symmetric memory on this box: NCCL
@@ -32,17 +38,40 @@ class GradExchange:
                     raise
                 self.why = f'{type(ex).__name__}: {ex}'
                 self.buf = None
+                eng.set_exchange(0, 1, None, None)
                 eng.set_grad_buffer(None)
                 self.mode = 'nccl'
         if self.buf is None:
             self.buf = eng.grad_tensor()
 
     def _setup_symm(self, want):
-        # measured on B200: multimem 360 us/step vs two-shot 381 at 8 ranks, but 466 vs NCCL's 366 at 2 ranks
-        if want == 'auto' and self.dist.get_world_size(self.group) < 4:
-            raise RuntimeError('NCCL is faster below 4 ranks')
         import torch.distributed._symmetric_memory as symm_mem
         torch = self.torch
+        world, rank = self.dist.get_world_size(self.group), self.dist.get_rank(self.group)
+        if want in ('auto', 'kernel') and world <= 8:
+            _, n = self.eng.grad_buffer()
+            n_alloc = (n + 1023) // 1024 * 1024
+            dev = torch.device('cuda', self.eng.device)
+            buf = symm_mem.empty(n_alloc, dtype=torch.float32, device=dev)
+            scratch = symm_mem.empty((self.eng.exchange_scratch_bytes() + 1023) // 1024 * 256, dtype=torch.int32, device=dev)
+            buf.zero_(); scratch.zero_()
+            hb = symm_mem.rendezvous(buf, self.group)
+            hs = symm_mem.rendezvous(scratch, self.group)
+            torch.cuda.synchronize()
+            self.dist.barrier(self.group)
+            self.eng.set_grad_buffer(buf)
+            # in-switch reduction (NVLS multicast) where the box has it: JB_XCHG_MC = 0 | 1 | auto (auto: 4 or more ranks)
+            mc_want = os.environ.get('JB_XCHG_MC', 'auto')
+            mc = int(getattr(hb, 'multicast_ptr', 0) or 0)
+            use_mc = mc != 0 and (mc_want == '1' or (mc_want == 'auto' and world >= 4))
+            self.eng.set_exchange(rank, world, list(hb.buffer_ptrs), list(hs.buffer_ptrs), mc if use_mc else 0)
+            self.buf, self.scratch, self.handle, self.handle_s = buf, scratch, hb, hs
+            self.mode = 'kernel'
+            self.multicast = use_mc
+            return
+        # measured on B200: multimem 360 us/step vs two-shot 381 at 8 ranks, but 466 vs NCCL's 366 at 2 ranks
+        if want == 'auto' and world < 4:
+            raise RuntimeError('NCCL is faster below 4 ranks')
         _, n = self.eng.grad_buffer()
         n_alloc = (n + 1023) // 1024 * 1024
         buf = symm_mem.empty(n_alloc, dtype=torch.float32, device=torch.device('cuda', self.eng.device))
@@ -65,7 +94,10 @@ class GradExchange:
         raise err
 
     def all_reduce(self):
-        """Sum of the gradient buffer over the ranks, in place, on torch's current stream."""
+        """Sum of the gradient buffer over the ranks, in place, on torch's current stream (no-op when the step kernel
+        exchanges the gradients itself)."""
+        if self.mode == 'kernel':
+            return
         if self.mode == 'multimem':
             self.torch.ops.symm_mem.multimem_all_reduce_(self.buf, 'sum', self.group_name)
         elif self.mode == 'two_shot':

@@ -295,6 +295,19 @@ class Engine:
             _lib.check(self.lib.jb_set_grad_buffer(self.h, C.c_void_p(tensor.data_ptr()), C.c_longlong(tensor.numel())))
             self._ext_grad = tensor   # keep it alive
 
+    def set_exchange(self, rank, world, grad_ptrs, flag_ptrs, multicast_ptr=0):
+        """In-kernel gradient exchange over peer memory: device pointers of every rank's gradient buffer / scratch block
+        (multicast_ptr: the NVSwitch multicast address of the gradient buffers, 0 = peer loads / stores)."""
+        if not grad_ptrs:
+            _lib.check(self.lib.jb_set_exchange(self.h, 0, 1, None, None, None))
+            return
+        ga = (C.c_void_p * world)(*[int(p) for p in grad_ptrs])
+        fa = (C.c_void_p * world)(*[int(p) for p in flag_ptrs])
+        _lib.check(self.lib.jb_set_exchange(self.h, int(rank), int(world), ga, fa, C.c_void_p(int(multicast_ptr) or None)))
+
+    def exchange_scratch_bytes(self):
+        return int(self.lib.jb_exchange_scratch_bytes())
+
     def grad_tensor(self):
         """The gradient buffer as a torch CUDA tensor view (no copy) -- what torch.distributed all-reduces."""
         import torch

@@ -486,8 +486,8 @@ class JAMIE(UnionCom):
             t1 = _time.perf_counter()
             eng.upload_plan(idx0, idx1, anneal, stream)
             nsteps = n_ep * len_dataloader
-            if world == 1 and self.batch_step:
-                eng.train_steps(nsteps, stream)
+            if (world == 1 or gx.mode == 'kernel') and self.batch_step:
+                eng.train_steps(nsteps, stream)          # (data-parallel: the step kernel exchanges the gradients itself)
             else:
                 for s_ in range(nsteps):
                     if not self.batch_step:

@@ -1,0 +1,88 @@
+"""Data-parallel check on R GPUs (torchrun): the in-kernel peer-memory exchange (JB_DP_ALLREDUCE=kernel) against the NCCL
+split path (backward | all-reduce | update) on the same shards, seeds and plan: parameters after K steps must agree to
+fp32 rounding of the summation order, and be bit-identical across the ranks of one run.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 tools/dp_check.py"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch
+import torch.distributed as dist
+from jamie_b200.engine import Engine
+from jamie_b200.dp import GradExchange
+from tests import parity_util as U
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+dims, L, B, p, n, K = [512, 512], 32, 512, 0.6, 4096, int(sys.argv[1]) if len(sys.argv) > 1 else 6
+params = U.torch_like_init(dims, L, seed=2)
+data = U.synth_pair(n, dims, seed=10 + rank)
+rng = np.random.default_rng(100 + rank)
+idx = np.stack([rng.choice(n, B, replace=False) for _ in range(K)])
+out = {}
+MODES = os.environ.get('JB_DP_MODES', 'nccl,kernel,kernel_mc').split(',')
+for mode in MODES:
+    os.environ['JB_DP_ALLREDUCE'] = mode.split('_')[0]
+    os.environ['JB_XCHG_MC'] = '1' if mode == 'kernel_mc' else '0'
+    eng = Engine(dims, L, B, p, seed=7 + rank, device=local, world_size=world)
+    eng.set_params(params)
+    for i in range(2):
+        eng.set_dataset(i, data[i])
+    eng.set_prior_diag(np.ones(n, np.float32)); eng.set_f_dense(None)
+    gx = GradExchange(eng)
+    assert gx.mode == mode.split('_')[0], (gx.mode, getattr(gx, 'why', ''))
+    if mode == 'kernel_mc' and not gx.multicast:
+        if rank == 0:
+            print('no multicast address on this box: kernel_mc skipped')
+        eng.close(); del gx
+        continue
+    eng.upload_plan(idx, idx, np.full(K, 0.3))
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def run():
+        if mode != 'nccl':
+            eng.train_steps(K)
+        else:
+            for _ in range(K):
+                eng.step_backward(); gx.all_reduce(); eng.step_update()
+    run()
+    torch.cuda.synchronize()
+    res = (eng.get_params(as_list=False), eng.read_losses(K).copy())
+    eng.upload_plan(idx, idx, np.full(K, 0.3))   # timed: the same K steps once more (warm)
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    run()
+    e1.record(); torch.cuda.synchronize()
+    out[mode] = res + (e0.elapsed_time(e1) * 1e3 / K,)
+    if mode != 'nccl' and K >= 18 and os.environ.get('JB_DP_PROFILE'):
+        us = eng.profile_step(16)
+        if rank == 0:
+            print(f'{mode}: in-kernel phase timeline with the exchange (gradnorm = the exchange):')
+            print('  ' + '  '.join(f'{nm} {u:.1f}' for nm, u in zip(eng.phase_names(), us) if u > 1.0) + f'  | sum {us.sum():.1f}')
+    eng.close(); del gx
+    dist.barrier()
+if rank == 0:
+    print(f'world {world}, K = {K}: ' + ', '.join(f'{m} {out[m][2]:.1f} us/step' for m in out))
+if os.environ.get('JB_XCHG_DBG') or 'nccl' not in out or 'kernel' not in out:   # timing experiments: no numerical claims
+    dist.destroy_process_group()
+    sys.exit(0)
+if 'kernel_mc' in out:   # the in-switch sum has its own order: close to the peer-load sum, identical across the ranks
+    pm = out['kernel_mc'][0]
+    t = torch.from_numpy(pm).cuda(); tmin = t.clone(); tmax = t.clone()
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    same_mc = bool((tmin == tmax).all().item())
+    dmc = float(np.abs(pm - out['kernel'][0]).max())
+    if rank == 0:
+        print(f'multicast sweep: parameters identical across ranks: {same_mc}; max |kernel_mc - kernel| = {dmc:.2e}')
+    assert same_mc and dmc < 2e-6
+pk, pn = out['kernel'][0], out['nccl'][0]
+t = torch.from_numpy(pk).cuda(); tmin = t.clone(); tmax = t.clone()
+dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+same = bool((tmin == tmax).all().item())
+diff = float(np.abs(pk - pn).max()); moved = float(np.abs(pk - np.concatenate([np.asarray(x, np.float32).ravel() for x in params])).max())
+gn_k, gn_n = out['kernel'][1][:, 5], out['nccl'][1][:, 5]
+if rank == 0:
+    print(f'parameters identical across ranks: {same}; max |kernel - nccl| = {diff:.2e} (parameters moved by up to {moved:.2e}); '
+          f'clip norm rel diff {float(np.abs(gn_k - gn_n).max() / np.abs(gn_n).max()):.1e}')
+assert same and diff < 2e-6 and moved > 1e-4
+dist.destroy_process_group()
