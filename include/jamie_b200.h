@@ -112,6 +112,9 @@ int jb_set_grad_buffer(jb_engine* e, float* dev_ptr, long long n_floats);
 int jb_set_exchange(jb_engine* e, int rank, int world, float* const* grad_ptrs, unsigned int* const* flag_ptrs,
                     float* grad_multicast);
 long long jb_exchange_scratch_bytes(void);
+/* dist_method of sim_diff_func (jamie/jamie.py:484-502): 0 = 'euclidean' (the default: the "CosSim" loss is the row-wise
+ * squared distance |z_i - c_i|^2), 1 = 'cosine' ((1 - cos(z_i, c_i))^2). Takes effect with the next step. */
+int jb_set_dist_method(jb_engine* e, int method);
 /* batch_step=False (jamie/jamie.py:744-749): accumulate gradients over several jb_step_backward calls, one
  * jb_step_update per epoch. accumulate != 0 makes the following backward passes add into the gradient buffer instead of
  * overwriting it (a device-side flag: no rebuild, no synchronisation). The optimizer step count (Adam bias correction)

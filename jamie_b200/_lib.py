@@ -62,6 +62,7 @@ SIGNATURES = {
     'jb_set_exchange': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P]),
     'jb_exchange_scratch_bytes': (_LL, []),
     'jb_set_grad_accumulate': (C.c_int, [_P, C.c_int]),
+    'jb_set_dist_method': (C.c_int, [_P, C.c_int]),
     'jb_train_step_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P, _P]),
     'jb_step_backward_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),
     'jb_hostbatch_submit': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),

@@ -144,7 +144,8 @@ struct jb_engine {
   char* parts_arena = nullptr;          // GEMM outputs with their split-K partials (depends on the batch size)
   ModActs act[2]{};
   float *corr = nullptr, *corr_t = nullptr, *fblk = nullptr, *fblk_t = nullptr;
-  float *lat_r = nullptr, *rowpart = nullptr;
+  float *lat_r = nullptr, *rowpart = nullptr, *lat_coef = nullptr;
+  int cosine = 0;                   // jb_set_dist_method
   float *cmax_part = nullptr, *dmax_part = nullptr, *dyn = nullptr;   // dynamic operand scales (stepk.cuh)
   // step tables at batch size step_B
   std::vector<jb::HgProblem> h_probs;
@@ -291,7 +292,7 @@ void carve(jb_engine* e, Carver& c) {
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
-  e->lat_r = c.take<float>(B * e->LP); e->rowpart = c.take<float>(2 * B * 8);
+  e->lat_r = c.take<float>(B * e->LP); e->rowpart = c.take<float>(2 * B * 8); e->lat_coef = c.take<float>(2 * B * 4);
   e->cmax_part = c.take<float>(jb::SK_MAX_CTAS); e->dmax_part = c.take<float>(jb::SK_MAX_CTAS); e->dyn = c.take<float>(8);
 }
 
@@ -544,7 +545,7 @@ int build_step(jb_engine* e, int B) {
   cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
   cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
   cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;
-  cx.lat_r = e->lat_r; cx.rowpart = e->rowpart;
+  cx.lat_r = e->lat_r; cx.rowpart = e->rowpart; cx.lat_coef = e->lat_coef; cx.cosine = e->cosine;
   cx.cmax_part = e->cmax_part; cx.dmax_part = e->dmax_part; cx.dyn = e->dyn;
   {
     const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
@@ -1167,6 +1168,14 @@ int jb_set_exchange(jb_engine* e, int rank, int world, float* const* grad_ptrs, 
     e->x_adam0 = c.adam_t;
   }
   e->step_B = 0;
+  return 0;
+}
+int jb_set_dist_method(jb_engine* e, int method) {
+  if (!e) return fail("null argument");
+  if (method != 0 && method != 1) return fail("dist_method %d: 0 = euclidean, 1 = cosine", method);
+  CU(cudaDeviceSynchronize());
+  e->cosine = method;
+  e->step_B = 0;   // the step context holds the flag
   return 0;
 }
 int jb_set_grad_accumulate(jb_engine* e, int accumulate) {

@@ -113,6 +113,8 @@ struct StepCtx {
   int f_present;
   // latent scratch
   float* lat_r; float* rowpart;
+  int cosine;                      // dist_method == 'cosine' (jamie/jamie.py:485-494); 0: euclidean
+  float* lat_coef;                 // cosine: per row [i][row] {a_zz, a_x, a_cc, -}: d loss / dz = a_zz z + a_x c, d loss / dc = a_x z + a_cc c
   // dynamic power-of-two operand scales (fp16 range): per-CTA maxima of |c| and |d mulv|, and the published inverse
   // scales dyn[0] = 1 / s_c (c planes hold s_c c), dyn[1] = 1 / s_b (d mulv planes and everything downstream of them in
   // the encoder backward hold s_b times the loss-scaled gradient). Both are exactly 1 unless a value leaves fp16's range.
@@ -1091,6 +1093,19 @@ __device__ __forceinline__ float sk_row_times(const float* __restrict__ Mrow, co
   return rs;
 }
 
+// dist_method == 'cosine' (jamie/jamie.py:485-494, 655-657): the row's loss term is (1 - cos(z, c))^2 instead of |z - c|^2.
+// From the row sums z.c, z.z, c.c: returns the loss term; lane 0 leaves the coefficients of its gradient,
+//   d/dz = k d (cos z / |z|^2 - c / (|z| |c|)),  d/dc = k d (cos c / |c|^2 - z / (|z| |c|)),  d = 1 - cos, k = the weight k_cos
+__device__ __forceinline__ float sk_cos_row(const StepCtx& cx, int i, int row, float szc, float szz, float scc, int lane) {
+  const float nz = sqrtf(szz), nc = sqrtf(scc);
+  const float cosv = szc / (nz * nc), d = 1.f - cosv;
+  if (lane == 0) {
+    const float k = cx.gs * cx.sc.w[2] * 32.f * 2.f / (static_cast<float>(cx.B) * static_cast<float>(cx.L));
+    const float kd = k * d;
+    reinterpret_cast<float4*>(cx.lat_coef)[static_cast<long long>(i) * cx.B + row] = make_float4(kd * cosv / szz, -kd / (nz * nc), kd * cosv / scc, 0.f);
+  }
+  return d * d;
+}
 // combine (jamie/model.py:245-259): c_i = (s_i z_i + s_j C_i z_j) / (s_i + s_j rowsum(C_i)), C_0 = corr, C_1 = corr^T.
 // Without F the latent loss partials need nothing of another row and are emitted here (fuse_loss).
 __device__ __forceinline__ void sk_combine(const StepCtx& cx, int gw, int nw, int lane, int cta, float* sh, int tid, int warp) {
@@ -1106,7 +1121,7 @@ __device__ __forceinline__ void sk_combine(const StepCtx& cx, int gw, int nw, in
     const float rs = sk_row_times(Ci, cx.m[j].z, B, LP, L, lane, acc);
     const float den = si + sj * rs;
     if (lane == 0) { M.den[row] = den; M.rs[row] = rs; }
-    float smu = 0.f, scs = 0.f, sr = 0.f;
+    float smu = 0.f, scs = 0.f, sr = 0.f, szc = 0.f, szz = 0.f, scc = 0.f;
 #pragma unroll
     for (int t = 0; t < LAT_MAXT; ++t) {
       const int l = lane + 32 * t;
@@ -1123,12 +1138,14 @@ __device__ __forceinline__ void sk_combine(const StepCtx& cx, int gw, int nw, in
           smu += mu * mu;
           const float d = zv - cv;
           scs += d * d;
+          if (cx.cosine) { szc += zv * cv; szz += zv * zv; scc += cv * cv; }
           if (i == 0) { cx.lat_r[o] = cv; sr += cv * cv; }
         }
       }
     }
     if (fuse_loss) {
       smu = warp_sum(smu); scs = warp_sum(scs); sr = warp_sum(sr);
+      if (cx.cosine) scs = sk_cos_row(cx, i, row, warp_sum(szc), warp_sum(szz), warp_sum(scc), lane);
       if (lane == 0) {
         float* rp = cx.rowpart + (static_cast<long long>(i) * B + row) * 8;
         rp[0] = smu; rp[1] = scs; rp[2] = sr;
@@ -1162,7 +1179,7 @@ __device__ __forceinline__ void sk_latloss(const StepCtx& cx, int gw, int nw, in
 #pragma unroll
       for (int t = 0; t < LAT_MAXT; ++t) acc[t] = 0.f;
     }
-    float smu = 0.f, scs = 0.f, sr = 0.f;
+    float smu = 0.f, scs = 0.f, sr = 0.f, szc = 0.f, szz = 0.f, scc = 0.f;
 #pragma unroll
     for (int t = 0; t < LAT_MAXT; ++t) {
       const int l = lane + 32 * t;
@@ -1170,16 +1187,19 @@ __device__ __forceinline__ void sk_latloss(const StepCtx& cx, int gw, int nw, in
         const long long o = static_cast<long long>(row) * LP + l;
         const float mu = sk_ld(M.mulv.ptr + static_cast<long long>(row) * cx.ldmv + l);
         smu += mu * mu;
-        const float d = sk_ld(M.z + o) - sk_ld(M.c + o);
+        const float zv = sk_ld(M.z + o), cv = sk_ld(M.c + o);
+        const float d = zv - cv;
         scs += d * d;
+        if (cx.cosine) { szc += zv * cv; szz += zv * zv; scc += cv * cv; }
         if (i == 0) {
-          const float r = sk_ld(M.c + o) - acc[t];
+          const float r = cv - acc[t];
           cx.lat_r[o] = r;
           sr += r * r;
         }
       }
     }
     smu = warp_sum(smu); scs = warp_sum(scs); sr = warp_sum(sr);
+    if (cx.cosine) scs = sk_cos_row(cx, i, row, warp_sum(szc), warp_sum(szz), warp_sum(scc), lane);
     if (lane == 0) {
       float* rp = cx.rowpart + (static_cast<long long>(i) * B + row) * 8;
       rp[0] = smu; rp[1] = scs; rp[2] = sr;
@@ -1245,6 +1265,8 @@ __device__ __forceinline__ void sk_latbc(const StepCtx& cx, int gw, int nw, int 
       for (int t = 0; t < LAT_MAXT; ++t) acc[t] = 0.f;
     }
     const float den = sk_ld(M.den + row);
+    float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cx.cosine) cf = sk_ld(reinterpret_cast<const float4*>(cx.lat_coef) + static_cast<long long>(i) * B + row);
     float p3 = 0.f, p4 = 0.f, p5 = 0.f;
 #pragma unroll
     for (int t = 0; t < LAT_MAXT; ++t) {
@@ -1254,7 +1276,7 @@ __device__ __forceinline__ void sk_latbc(const StepCtx& cx, int gw, int nw, int 
         const float z = sk_ld(M.z + o), c = sk_ld(M.c + o);
         const float dcd = ld_parts(M.dc, o);
         if (M.dc.n > 1) M.dc.ptr[o] = dcd;
-        float dc = dcd - k_cos * (z - c);
+        float dc = cx.cosine ? dcd + (cf.y * z + cf.z * c) : dcd - k_cos * (z - c);
         dc += i == 0 ? k_f * sk_ld(cx.lat_r + o) : -k_f * acc[t];
         const float g = dc / den;
         M.g[o] = g;
@@ -1284,6 +1306,8 @@ __device__ __forceinline__ void sk_latbz(const StepCtx& cx, const StepVars& sv, 
     const float* Ci = (i == 0 ? cx.corr : cx.corr_t) + static_cast<long long>(row) * B;
     float acc[LAT_MAXT];
     sk_row_times(Ci, cx.m[j].g, B, LP, L, lane, acc);
+    float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cx.cosine) cf = sk_ld(reinterpret_cast<const float4*>(cx.lat_coef) + static_cast<long long>(i) * B + row);
 #pragma unroll
     for (int t = 0; t < LAT_MAXT; ++t) {
       const int l = lane + 32 * t;
@@ -1291,7 +1315,8 @@ __device__ __forceinline__ void sk_latbz(const StepCtx& cx, const StepVars& sv, 
         const long long o = static_cast<long long>(row) * LP + l;
         const long long om = static_cast<long long>(row) * cx.ldmv;
         const float mu = sk_ld(M.mulv.ptr + om + l), lv = sk_ld(M.mulv.ptr + om + L + l);
-        const float dz = k_cos * (sk_ld(M.z + o) - sk_ld(M.c + o)) + si * sk_ld(M.g + o) + si * acc[t];
+        const float zv = sk_ld(M.z + o), cv = sk_ld(M.c + o);
+        const float dz = (cx.cosine ? cf.x * zv + cf.y * cv : k_cos * (zv - cv)) + si * sk_ld(M.g + o) + si * acc[t];
         const float dmu = dz + kkl * mu / fbl;
         float dlv = dz * sk_ld(M.eps + o) * 0.5f * expf(lv * 0.5f);
         if (i == 1 && row < 2) dlv += kkl * -0.5f * (1.f - expf(lv)) / static_cast<float>(L);
@@ -1440,6 +1465,8 @@ __device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M
   const bool rok = row < B && (!ks || ta.tid < 128);
   const int rr = rok ? row : B - 1;
   const float rden = 1.f / sk_ld(M.den + rr);
+  float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cx.cosine) cf = sk_ld(reinterpret_cast<const float4*>(cx.lat_coef) + static_cast<long long>(mod) * B + rr);
   float p3 = 0.f, p4 = 0.f, p5 = 0.f;
 #pragma unroll 1
   for (int l0 = q * 8; l0 < LP; l0 += 32) {
@@ -1463,7 +1490,8 @@ __device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool ok = l0 + j < L;
-      g[j] = ok ? (dcd[j] - k_cos * (z[j] - c[j]) + k_f * lr[j]) * rden : 0.f;
+      const float dd = cx.cosine ? cf.y * z[j] + cf.z * c[j] : -k_cos * (z[j] - c[j]);
+      g[j] = ok ? (dcd[j] + dd + k_f * lr[j]) * rden : 0.f;
       p3 += g[j] * z[j]; p4 += g[j] * c[j]; p5 += g[j] * S[j];
     }
     if (rok) { st8(M.g + o, g); st8(M.dc.ptr + o, dcd); }
@@ -1489,21 +1517,27 @@ __device__ __forceinline__ void sk_tail_latbc(const StepCtx& cx, const ModCtx& M
 //   3. grid barrier (all of this rank's remote writes are issued and fenced), tell every peer "my slice is delivered";
 //      wait for all peers. ADAM then reads the local buffer.
 // Spins are bounded (a protocol error traps instead of hanging the box).
+// One system-scope fence per side of a flag: release = fence + relaxed store / red, acquire = relaxed polls + fence (a
+// .release store / .acquire load per poll would each carry a fence of their own: measured 16 us of fences per exchange).
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void xchg_signal(const StepCtx& cx, int slot0, unsigned int epoch, int tid) {
   if (tid < cx.xworld) {
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(cx.xf[tid] + slot0 + cx.xrank), "r"(epoch) : "memory");
+    fence_sys();
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(cx.xf[tid] + slot0 + cx.xrank), "r"(epoch) : "memory");
   }
 }
 __device__ __forceinline__ void xchg_wait(const StepCtx& cx, int slot0, unsigned int epoch, int tid) {
   if (tid < cx.xworld) {
     const unsigned int* f = cx.xf[cx.xrank] + slot0 + tid;
-    unsigned int v, spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    unsigned int spins = 0;
+    while (static_cast<int>(ld_relaxed_sys_u32(f) - epoch) < 0)
       if (++spins > (1u << 26)) __trap();
-    } while (static_cast<int>(v - epoch) < 0);
-    __threadfence_system();
+    fence_sys();
   }
   __syncthreads();
 }
@@ -1603,19 +1637,17 @@ __device__ __forceinline__ void sk_exchange(const StepCtx& cx, unsigned int epoc
   // is skipped as well): the counter orders the local CTAs among themselves too.
   if (tid < R) {
     reinterpret_cast<double*>(reinterpret_cast<char*>(cx.xf[tid]) + 256)[me * SK_MAX_CTAS + cta] = shd[0];
-    __threadfence_system();
+    fence_sys();
     if (!(cx.xdbg & 2) || tid == me)
-      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(cx.xf[tid] + 16) : "memory");
+      asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(cx.xf[tid] + 16) : "memory");
   }
   if (tid == 0) {
     const unsigned int want = epoch * static_cast<unsigned int>(((cx.xdbg & 2) ? 1 : R) * ncta);
     const unsigned int* f = cx.xf[me] + 16;
-    unsigned int v, spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    unsigned int spins = 0;
+    while (static_cast<int>(ld_relaxed_sys_u32(f) - want) < 0)
       if (++spins > (1u << 26)) __trap();
-    } while (static_cast<int>(v - want) < 0);
-    __threadfence_system();
+    fence_sys();
   }
   __syncthreads();
   fence_proxy_async_global();   // the reduced gradients (peer stores) -> the Adam stream's bulk loads

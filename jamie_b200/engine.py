@@ -276,6 +276,10 @@ class Engine:
         self.gemm_stamps = out[4 * n:].reshape(12, 7).copy()   # CTA 0 role stamps of the 12 GEMM phases (us)
         return out[:4 * n].reshape(n, 4)
 
+    def set_dist_method(self, name):
+        """sim_diff_func branch of the training loss (jamie/jamie.py:484-502): 'euclidean' or 'cosine'."""
+        _lib.check(self.lib.jb_set_dist_method(self.h, {'euclidean': 0, 'cosine': 1}[name]))
+
     def set_grad_accumulate(self, flag):
         _lib.check(self.lib.jb_set_grad_accumulate(self.h, int(bool(flag))))
 

@@ -420,12 +420,15 @@ class JAMIE(UnionCom):
 
         dev = self._cuda_index()
         torch.cuda.set_device(dev)
-        if self.dist_method != 'euclidean':
-            raise NotImplementedError("only dist_method='euclidean' (the reference default) is built")
+        if self.dist_method not in ('euclidean', 'cosine'):
+            # the reference's sim_diff_func (jamie/jamie.py:484-504) has exactly these two branches; anything else leaves
+            # it return None and the first step dies unpacking it
+            raise ValueError(f"dist_method='{self.dist_method}': the training loss knows 'euclidean' and 'cosine'")
         self.engine = Engine(self.col, self.output_dim, self.batch_size, self.model.dropout_p, lr=self.model_lr,
                              loss_weights=self.loss_weights, pf_ratio=self.PF_Ratio,
                              seed=(self.manual_seed or 0) * 1000003 + rank, device=dev, world_size=world)
         eng = self.engine
+        eng.set_dist_method(self.dist_method)
         self.model.attach_engine(eng)      # also routes preclass PCA projections through the engine (jb_pca_project)
         self.model.push_to_engine()
         # ingest: PCA projection + standardisation of every cell (jamie/jamie.py:458-459)

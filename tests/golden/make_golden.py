@@ -49,6 +49,11 @@ CASES = {
     'pca': dict(n=(60, 60), d=(100, 80), P='none', F='zero',
                 kw=dict(output_dim=8, batch_size=32, pca_dim=[16, 12], epoch_DNN=3, min_epochs=2, dropout=0.5,
                         use_f_tilde=False)),
+    # dist_method='cosine' (the other live branch of sim_diff_func, jamie/jamie.py:485-494); a partially matched prior and
+    # F so that c != z and every latent term is exercised
+    'cosine': dict(n=(56, 56), d=(36, 28), P='half', F='dense',
+                   kw=dict(output_dim=8, batch_size=32, pca_dim=None, epoch_DNN=3, min_epochs=1, dropout=0.3,
+                           dist_method='cosine', PF_Ratio=0.6, loss_weights=[1, 1, 4, 2])),
     'multibatch': dict(n=(100, 100), d=(24, 16), P='none', F='zero',
                        kw=dict(output_dim=8, batch_size=32, pca_dim=None, epoch_DNN=2, min_epochs=2, dropout=0.2,
                                use_f_tilde=False)),
@@ -164,8 +169,12 @@ def build_checkpoint():
 
 def main():
     torch.set_num_threads(4)
-    build_checkpoint()
+    only = sys.argv[1:]          # `python make_golden.py cosine` (re)generates the named cases only
+    if not only:
+        build_checkpoint()
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         out = build_case(name, spec)
         path = os.path.join(HERE, f'{name}.npz')
         np.savez_compressed(path, **out)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['diag_drop', 'rep_F', 'hybrid', 'zeros_unequal', 'pca', 'multibatch']
+CASES = ['diag_drop', 'rep_F', 'hybrid', 'zeros_unequal', 'pca', 'multibatch', 'cosine']
 
 
 class Golden:

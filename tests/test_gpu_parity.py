@@ -49,6 +49,7 @@ def test_reference_fixture_replay(name):
     lw = kw.get('loss_weights')
     pf = kw.get('PF_Ratio') or 1
     eng = _engine(dims, L, B, G.meta['dropout'], loss_weights=lw, pf_ratio=pf)
+    eng.set_dist_method(kw.get('dist_method', 'euclidean'))
     eng.set_params(G.init_params())
     eng.set_bn_stats(G.buffers('init'))
     data = [G[f'pre{i}'].astype(np.float32) for i in range(2)]
@@ -110,8 +111,15 @@ SHAPES = [
 ]
 
 
+@pytest.mark.parametrize('dims,L,B,p,prior,use_f', [SHAPES[0], SHAPES[4]])
+def test_step_vs_oracle_cosine(dims, L, B, p, prior, use_f):
+    """dist_method='cosine' (jamie/jamie.py:485-494): the headline shape on the merged-latent path (no F) and the odd
+    shape on the LATLOSS / LATBC path (dense F)."""
+    test_step_vs_oracle(dims, L, B, p, prior, use_f, dist_method='cosine')
+
+
 @pytest.mark.parametrize('dims,L,B,p,prior,use_f', SHAPES)
-def test_step_vs_oracle(dims, L, B, p, prior, use_f):
+def test_step_vs_oracle(dims, L, B, p, prior, use_f, dist_method='euclidean'):
     n = 2 * B if prior != 'eye_rep' else B
     rng = np.random.default_rng(5)
     data = U.synth_pair(n, dims, seed=1)
@@ -119,6 +127,7 @@ def test_step_vs_oracle(dims, L, B, p, prior, use_f):
     lw = [1, 2, 0.5, 3] if use_f else None
     pf = 0.7 if use_f else 1.0
     eng = _engine(dims, L, B, p, loss_weights=lw, pf_ratio=pf)
+    eng.set_dist_method(dist_method)
     eng.set_params(params)
     for i in range(2):
         eng.set_dataset(i, data[i])
@@ -133,7 +142,7 @@ def test_step_vs_oracle(dims, L, B, p, prior, use_f):
     Fm = (rng.random((n, n)) * (rng.random((n, n)) < 0.05)).astype(np.float32) if use_f else None
     eng.set_f_dense(Fm)
     Fd = np.zeros((n, n), np.float32) if Fm is None else Fm
-    orc = O.OracleModel(dims, L, dropout=p, params=params)
+    orc = O.OracleModel(dims, L, dropout=p, params=params, dist_method=dist_method)
     rep = prior == 'eye_rep'
     i0 = rng.choice(n, B, replace=rep)
     i1 = i0.copy() if prior in ('eye', 'eye_rep') else np.concatenate([i0[:B // 2], rng.choice(n, B - B // 2, replace=False)])

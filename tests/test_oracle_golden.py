@@ -27,7 +27,8 @@ def test_replay(name):
     L = kw['output_dim']
     B = G.meta['batch_size']
     rows = G.meta['n']
-    model = O.OracleModel(dims, L, dropout=G.meta['dropout'], params=G.init_params(), buffers=G.buffers('init'))
+    model = O.OracleModel(dims, L, dropout=G.meta['dropout'], params=G.init_params(), buffers=G.buffers('init'),
+                          dist_method=kw.get('dist_method', 'euclidean'))
     assert [n for n, _ in model.spec] == G.param_names
     P = G.P_dense(); Fm = G.F_dense()
     method = O.sampling_method(P)
