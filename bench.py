@@ -452,13 +452,14 @@ def main():
     def e2e_run(first, count):
         """The reference's loop shape (jamie/jamie.py:549-742) with host-resident data: gather the batch rows on the host,
         hand them to the engine, read the step's losses back. N = 1: the engine's asynchronous host-batch API keeps two
-        steps in flight, so the host gather of batch k + 1 overlaps step k; N > 1: backward, all-reduce, update."""
+        steps in flight, so the host gather of batch k + 1 overlaps step k (also at N > 1 when the step kernel carries the
+        gradient exchange); N > 1 with an NCCL / multimem exchange: backward, all-reduce, update."""
         out, pending = None, 0
         for s in range(first, first + count):
             b = hb[s & 1]
             for i in range(2):
                 torch.index_select(host[i], 0, ti[i][s], out=b[i])      # the reference's dataset[i][random_batch[i]]
-            if world == 1:
+            if world == 1 or gx.mode == 'kernel':   # (N > 1: the step kernel exchanges the gradients itself, same pipeline)
                 eng.hostbatch_submit(b[0].data_ptr(), b[1].data_ptr(), i0e[s], i1e[s], 0.5, stream)
                 pending += 1
                 if pending == 2:
@@ -529,7 +530,7 @@ def main():
             'metric': 'train cells/sec (fwd+bwd+Adam)', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
             'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f16x2 (fp16 hi/lo split operands, fp32 accumulate: fp32-class products)', 'data': 'synthetic',
-            'config': dict(workload_config(world), **({'exchange': gx.mode + ' all-reduce of the flat gradient buffer (jamie_b200/dp.py)'} if gx is not None else {})),
+            'config': dict(workload_config(world), **({'exchange': ('in-kernel reduce-scatter + all-gather over NVLink peer memory' + (' (NVLS multimem)' if getattr(gx, 'multicast', False) else '') + ', between WGRAD and ADAM of the persistent step kernel' if gx.mode == 'kernel' else gx.mode + ' all-reduce of the flat gradient buffer') + ' (jamie_b200/dp.py)'} if gx is not None else {})),
             'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': Ke, 'note': 'per step: host gather of the batch rows into pinned memory, H2D of rows + cell ids, '
                                          'step kernel, D2H of the 8 loss scalars; jb_hostbatch_submit / jb_hostbatch_wait keep '

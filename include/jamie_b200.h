@@ -187,6 +187,31 @@ int jb_pca_project(jb_engine* e, const float* X, long long n, long long d, const
 int jb_pca_inverse(jb_engine* e, const float* Z, long long n, int k, const float* comp, const float* mean,
                    long long d, float m, float s, float* out, int on_device, void* stream);
 
+/* PCA fit (jamie/jamie.py:436-452, sklearn PCA(n_components).fit with the covariance_eigh solver): the two O(n d) /
+ * O(n d^2) passes over the [n, d] matrix run on the GPU -- column sums, then the centred Gram matrix
+ * (X - mean)^T (X - mean) as a split (fp32-class) tensor-core GEMM accumulated over row chunks in float64. The caller
+ * divides / all-reduces (rows sharded over ranks: sum colsum and n, then sum the Gram matrices) and solves the d x d
+ * symmetric eigenproblem (host LAPACK: independent of n). X host or device pointer (packed rows); colsum [d], gram [d, d]
+ * host float64. Synchronous. */
+int jb_pca_colsum(jb_engine* e, const float* X, long long n, long long d, double* colsum, int on_device, void* stream);
+int jb_pca_gram(jb_engine* e, const float* X, long long n, long long d, const double* mean, double* gram, int on_device,
+                void* stream);
+
+/* Evaluation metrics of the reference on the GPU (no engine handle needed; host pointers in, synchronous).
+ *   jb_metric_foscttm: test_closer (jamie/evaluation.py:65-85, jamie/jamie.py:892-913) on two [n, L] embeddings with the
+ *     euclidean distance: raw_count_closer = #{j: d(a_i, b_j) < d(a_i, b_i)} + #{j: d(b_i, a_j) < d(b_i, a_i)} summed over
+ *     i; the caller divides by 2 n^2. Distances in float64.
+ *   jb_metric_knn_vote: the kNN classifier of test_LabelTA (jamie/evaluation.py:114-132, jamie/jamie.py:943-961): for
+ *     every query row the majority class (uniform votes; ties to the lowest class index) of its k nearest reference rows
+ *     (euclidean; equal distances by the lowest row index). ref_class: class indices in [0, n_classes).
+ *   jb_metric_feature_pearson: per-feature Pearson r of two [n, d] matrices (jamie/evaluation.py:491-513, sklearn
+ *     r_regression); a constant feature gives nan. */
+int jb_metric_foscttm(const float* emb0, const float* emb1, long long n, int L, int device,
+                      unsigned long long* raw_count_closer);
+int jb_metric_knn_vote(const float* query, long long nq, const float* ref, const int* ref_class, long long nr, int L,
+                       int k, int n_classes, int device, int* pred_class);
+int jb_metric_feature_pearson(const float* x, const float* y, long long n, long long d, int device, double* r);
+
 /* Debug / parity taps: copy a named intermediate of the last step to the host (synchronises).
  * Names: "x0","y1_0","h1_0","y2_0","h2_0","mulv0","z0","c0","xhat0", ... (see csrc/engine.cu: tap table),
  * "corr", "fblk", "grad" (padded flat), "theta". Returns the number of floats written, or -1. */

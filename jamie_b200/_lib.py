@@ -63,6 +63,11 @@ SIGNATURES = {
     'jb_exchange_scratch_bytes': (_LL, []),
     'jb_set_grad_accumulate': (C.c_int, [_P, C.c_int]),
     'jb_set_dist_method': (C.c_int, [_P, C.c_int]),
+    'jb_pca_colsum': (C.c_int, [_P, _P, _LL, _LL, _P, C.c_int, _P]),
+    'jb_pca_gram': (C.c_int, [_P, _P, _LL, _LL, _P, _P, C.c_int, _P]),
+    'jb_metric_foscttm': (C.c_int, [_P, _P, _LL, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]),
+    'jb_metric_knn_vote': (C.c_int, [_P, _LL, _P, _P, _LL, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    'jb_metric_feature_pearson': (C.c_int, [_P, _P, _LL, _LL, C.c_int, _P]),
     'jb_train_step_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P, _P]),
     'jb_step_backward_hostbatch': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),
     'jb_hostbatch_submit': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, _P]),

@@ -32,6 +32,7 @@
 #include "kernels.cuh"
 #include "hgemm.cuh"
 #include "stepk.cuh"
+#include "metrics.cuh"
 
 namespace {
 
@@ -159,6 +160,7 @@ struct jb_engine {
   int fuse_ks = 1;           // JB_FUSE_KS=0: HEADS / DG3 as one CTA per M tile instead of K split over the cluster
   int accumulate = 0, accumulate_dev = 0;
   int wgrad_mode = jb::HG_MEDIUM;
+  int fwd_mode = jb::HG_PRECISE;    // JB_FWD_MODE=medium: forward / dgrad GEMMs without the accumulator drains (exploration)
   int wgrad_bn = 256;
   int max_ksplit = 8;
   float gs = 1.f;
@@ -329,7 +331,7 @@ int build_step(jb_engine* e, int B) {
     if (const char* pv = getenv("JB_LOSS_SCALE_LOG2")) e->gs = ldexpf(1.f, atoi(pv));
   }
   const float inv_gs = 1.f / e->gs;
-  const int fmode = e->precision_fast ? jb::HG_SINGLE : jb::HG_PRECISE;
+  const int fmode = e->precision_fast ? jb::HG_SINGLE : e->fwd_mode;
   const int wmode = e->precision_fast ? jb::HG_SINGLE : e->wgrad_mode;
   std::vector<std::vector<StageSpec>> st(jb::SK_NUM_GEMM);
   // Cluster-fused tails need all rows of a column block in one cluster: B <= HG_CLUSTER M tiles.
@@ -566,6 +568,7 @@ int build_step(jb_engine* e, int B) {
   for (int q = 0; q < 8; ++q) { cx.xg[q] = e->xg[q]; cx.xf[q] = e->xf[q]; }
   cx.xrank = e->xrank; cx.xworld = e->xworld; cx.xmc = e->xworld > 1 ? e->xmc : nullptr; cx.x_adam0 = e->x_adam0;
   cx.xdbg = getenv("JB_XCHG_DBG") ? atoi(getenv("JB_XCHG_DBG")) : 0;
+  cx.xfence = (getenv("JB_XCHG_FENCE") && strcmp(getenv("JB_XCHG_FENCE"), "sys") == 0) ? 1 : 0;
   cx.adam_stream = 1;
   if (const char* pv = getenv("JB_ADAM_STREAM")) cx.adam_stream = atoi(pv);
   cx.prefetch_state = 0;   // measured: WGRAD +9.4 us (the prefetch competes with the operand loads), ADAM only -3.5 us
@@ -790,6 +793,22 @@ int eval_common(jb_engine* e, int from, int to, const float* X, long long n, lon
 }  // namespace
 
 // =============================================================================================== C ABI
+namespace {
+template <class T> struct DevArr {   // scoped device allocation of any type
+  T* p = nullptr;
+  ~DevArr() { if (p) cudaFree(p); }
+  int alloc(size_t n) { CU(cudaMalloc(&p, (n ? n : 1) * sizeof(T))); return 0; }
+  int upload(const T* h, size_t n) { if (alloc(n)) return 1; CU(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice)); return 0; }
+};
+int metric_grid(long long tiles) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long g = static_cast<long long>(sms) * 4;
+  return static_cast<int>(tiles < g ? (tiles > 0 ? tiles : 1) : g);
+}
+}  // namespace
+
 extern "C" {
 
 const char* jb_last_error(void) { return g_err.c_str(); }
@@ -849,6 +868,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMalloc(&e->bar, 512));
   CU(cudaMemset(e->bar, 0, 512));
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
+  if (const char* pv = getenv("JB_FWD_MODE")) e->fwd_mode = strcmp(pv, "medium") == 0 ? jb::HG_MEDIUM : jb::HG_PRECISE;
   if (const char* pv = getenv("JB_WGRAD_MODE")) e->wgrad_mode = strcmp(pv, "single") == 0 ? jb::HG_SINGLE : jb::HG_MEDIUM;
   if (const char* pv = getenv("JB_MAX_KSPLIT")) { if (atoi(pv) >= 1) e->max_ksplit = atoi(pv); }
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));
@@ -1527,6 +1547,83 @@ int jb_pca_project(jb_engine* e, const float* X, long long n, long long d, const
   return 0;
 }
 
+// PCA fit, GPU part (jamie/jamie.py:436-452: sklearn PCA(n_components).fit): column sums and the centred Gram matrix; the
+// d x d symmetric eigenproblem stays with the caller (host LAPACK, independent of n), as does the all-reduce of both
+// results when the rows are sharded over ranks.
+int jb_pca_colsum(jb_engine* e, const float* X, long long n, long long d, double* colsum, int on_device, void* stream) {
+  if (!e || !X || !colsum) return fail("null argument");
+  if (n <= 0 || d <= 0) return fail("bad PCA shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long R = pca_chunk_rows(d);
+  const int slabs = 64;
+  DevBuf x_raw;
+  DevArr<double> part;
+  if (part.alloc(static_cast<size_t>(slabs) * d)) return 1;
+  if (!on_device && x_raw.alloc(static_cast<size_t>(R) * d)) return 1;
+  std::vector<double> h(static_cast<size_t>(slabs) * d);
+  for (long long c = 0; c < d; ++c) colsum[c] = 0.0;
+  for (long long r0 = 0; r0 < n; r0 += R) {
+    const long long rows = n - r0 < R ? n - r0 : R;
+    const float* src = X + r0 * d;
+    if (!on_device) {
+      CU(cudaMemcpyAsync(x_raw.p, src, static_cast<size_t>(rows) * d * 4, cudaMemcpyHostToDevice, s));
+      src = x_raw.p;
+    }
+    const long long per = (rows + slabs - 1) / slabs;
+    jb::k_col_sums<<<dim3(static_cast<unsigned>((d + 127) / 128), slabs), 128, 0, s>>>(src, rows, d, per, part.p); ++e->launches;
+    CU(cudaMemcpyAsync(h.data(), part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int sl = 0; sl < slabs; ++sl)   // fixed order: deterministic
+      if (sl * per < rows)
+        for (long long c = 0; c < d; ++c) colsum[c] += h[static_cast<size_t>(sl) * d + c];
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int jb_pca_gram(jb_engine* e, const float* X, long long n, long long d, const double* mean, double* gram, int on_device, void* stream) {
+  if (!e || !X || !mean || !gram) return fail("null argument");
+  if (n <= 0 || d <= 0) return fail("bad PCA shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long ldd = r4(static_cast<int>(d));
+  const long long R = pca_chunk_rows(ldd);
+  DevBuf d_mean, x_raw, x_hi, x_lo, g32;
+  DevArr<double> g64;
+  if (d_mean.alloc(d) || x_hi.alloc(static_cast<size_t>(R) * ldd) || x_lo.alloc(static_cast<size_t>(R) * ldd) ||
+      g32.alloc(static_cast<size_t>(d) * ldd) || g64.alloc(static_cast<size_t>(d) * d)) return 1;
+  if (!on_device && x_raw.alloc(static_cast<size_t>(R) * d)) return 1;
+  {
+    std::vector<float> mf(d);
+    for (long long c = 0; c < d; ++c) mf[c] = static_cast<float>(mean[c]);
+    CU(cudaMemcpyAsync(d_mean.p, mf.data(), static_cast<size_t>(d) * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  CU(cudaMemsetAsync(g64.p, 0, static_cast<size_t>(d) * d * sizeof(double), s));
+  for (long long r0 = 0; r0 < n; r0 += R) {
+    const long long rows = n - r0 < R ? n - r0 : R;
+    const float* src = X + r0 * d;
+    if (!on_device) {
+      CU(cudaMemcpyAsync(x_raw.p, src, static_cast<size_t>(rows) * d * 4, cudaMemcpyHostToDevice, s));
+      src = x_raw.p;
+    }
+    jb::k_split_tf32<<<static_cast<unsigned>(rows), 256, 0, s>>>(src, d, rows, static_cast<int>(d), 0, d_mean.p, 1.f, 0.f, x_hi.p, x_lo.p, ldd); ++e->launches;
+    {
+      GemmProblem g;   // G[d, d] = Xc^T Xc over this chunk: both operands are the same [rows][ldd] planes, MN-major (K = rows)
+      int rc = jb::gemm_problem_fill(&g, x_hi.p, static_cast<int>(ldd), 1, x_hi.p, static_cast<int>(ldd), 1, g32.p, static_cast<int>(ldd),
+                                     static_cast<int>(d), static_cast<int>(d), static_cast<int>(rows), 64, jb::EPI_STORE, nullptr, 0.f, 0, 0,
+                                     x_lo.p, x_lo.p);
+      if (rc) return fail("PCA Gram tensor map encode failed (%d)", rc);
+      if (launch_one(e, g, e->d_ev_probs, s)) return 1;
+    }
+    jb::k_acc_f64<<<static_cast<unsigned>(d), 256, 0, s>>>(g32.p, ldd, g64.p, d); ++e->launches;
+    CU(cudaStreamSynchronize(s));  // temporaries and the table slot are reused by the next chunk
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(gram, g64.p, static_cast<size_t>(d) * d * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
 int jb_pca_inverse(jb_engine* e, const float* Z, long long n, int k, const float* comp, const float* mean, long long d,
                    float m, float sdev, float* out, int on_device, void* stream) {
   if (!e || !Z || !comp || !mean || !out) return fail("null argument");
@@ -1564,6 +1661,72 @@ int jb_pca_inverse(jb_engine* e, const float* Z, long long n, int k, const float
     CU(cudaStreamSynchronize(s));
   }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- evaluation metrics (N4)
+
+int jb_metric_foscttm(const float* emb0, const float* emb1, long long n, int L, int device, unsigned long long* raw_count_closer) {
+  if (!emb0 || !emb1 || !raw_count_closer) return fail("null argument");
+  if (n <= 0 || L <= 0) return fail("bad embedding shape");
+  CU(cudaSetDevice(device));
+  DevArr<float> a, b; DevArr<double> diag; DevArr<unsigned long long> cnt;
+  if (a.upload(emb0, static_cast<size_t>(n) * L) || b.upload(emb1, static_cast<size_t>(n) * L) || diag.alloc(n) || cnt.alloc(1)) return 1;
+  CU(cudaMemset(cnt.p, 0, sizeof(unsigned long long)));
+  jb::k_pair_diag<<<static_cast<unsigned>((n + 255) / 256), 256>>>(a.p, b.p, n, L, diag.p);
+  const long long tiles = (n + jb::MT_TILE - 1) / jb::MT_TILE;
+  jb::k_foscttm<<<metric_grid(tiles * tiles), jb::MT_THREADS>>>(a.p, b.p, n, L, diag.p, cnt.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(raw_count_closer, cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int jb_metric_knn_vote(const float* query, long long nq, const float* ref, const int* ref_class, long long nr, int L, int k,
+                       int n_classes, int device, int* pred_class) {
+  if (!query || !ref || !ref_class || !pred_class) return fail("null argument");
+  if (nq <= 0 || nr <= 0 || L <= 0) return fail("bad embedding shape");
+  if (k < 1 || k > nr) return fail("k = %d neighbours of %lld reference rows", k, nr);
+  if (n_classes < 1 || n_classes > 8192) return fail("%d classes (1 .. 8192)", n_classes);
+  for (long long j = 0; j < nr; ++j)
+    if (ref_class[j] < 0 || ref_class[j] >= n_classes) return fail("class index %d of row %lld out of range", ref_class[j], j);
+  CU(cudaSetDevice(device));
+  long long Q = (512LL << 20) / (4 * nr);   // query rows per chunk: a 512 MB distance slab
+  if (Q < 1) Q = 1;
+  if (Q > nq) Q = nq;
+  DevArr<float> q, r, D; DevArr<int> cls, pred;
+  if (q.upload(query, static_cast<size_t>(nq) * L) || r.upload(ref, static_cast<size_t>(nr) * L) || cls.upload(ref_class, nr) ||
+      D.alloc(static_cast<size_t>(Q) * nr) || pred.alloc(nq)) return 1;
+  for (long long q0 = 0; q0 < nq; q0 += Q) {
+    const long long rows = nq - q0 < Q ? nq - q0 : Q;
+    const long long tiles = ((rows + jb::MT_TILE - 1) / jb::MT_TILE) * ((nr + jb::MT_TILE - 1) / jb::MT_TILE);
+    jb::k_dist_rows<<<metric_grid(tiles), jb::MT_THREADS>>>(q.p + q0 * L, rows, r.p, nr, L, D.p);
+    jb::k_knn_vote<<<static_cast<unsigned>(rows), jb::KV_THREADS, static_cast<size_t>(n_classes) * sizeof(int)>>>(D.p, nr, k, cls.p, n_classes, pred.p + q0);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(pred_class, pred.p, static_cast<size_t>(nq) * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int jb_metric_feature_pearson(const float* x, const float* y, long long n, long long d, int device, double* r) {
+  if (!x || !y || !r) return fail("null argument");
+  if (n <= 0 || d <= 0) return fail("bad matrix shape");
+  CU(cudaSetDevice(device));
+  const int slabs = static_cast<int>(n < 64 ? 1 : (n / 64 < 256 ? n / 64 : 256));
+  const long long per = (n + slabs - 1) / slabs;
+  DevArr<float> dx, dy; DevArr<double> part;
+  if (dx.upload(x, static_cast<size_t>(n) * d) || dy.upload(y, static_cast<size_t>(n) * d) || part.alloc(static_cast<size_t>(slabs) * d * 5)) return 1;
+  jb::k_col_moments<<<dim3(static_cast<unsigned>((d + 127) / 128), slabs), 128>>>(dx.p, dy.p, n, d, per, part.p);
+  CU(cudaGetLastError());
+  std::vector<double> h(static_cast<size_t>(slabs) * d * 5);
+  CU(cudaMemcpy(h.data(), part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const double N = static_cast<double>(n);
+  for (long long c = 0; c < d; ++c) {
+    double m[5] = {0, 0, 0, 0, 0};
+    for (int sl = 0; sl < slabs; ++sl)   // fixed order: deterministic
+      for (int q = 0; q < 5; ++q) m[q] += h[(static_cast<size_t>(sl) * d + c) * 5 + q];
+    const double cxy = m[4] - m[0] * m[1] / N, cxx = m[2] - m[0] * m[0] / N, cyy = m[3] - m[1] * m[1] / N;
+    r[c] = cxy / std::sqrt(cxx * cyy);   // constant feature: 0 / 0 = nan, as the host definition gives
+  }
   return 0;
 }
 

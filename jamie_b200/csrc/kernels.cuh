@@ -130,4 +130,20 @@ __global__ void k_standardise(const float* __restrict__ z, long long ldz, long l
   }
 }
 
+// ------------------------------------------------------------------------------------------------ PCA fit (Gram matrix)
+// column sums of a slab of rows in float64: part[slab][c]
+__global__ void k_col_sums(const float* __restrict__ x, long long n, long long d, long long rows_per_slab, double* __restrict__ part) {
+  const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const long long r0 = blockIdx.y * rows_per_slab, r1 = r0 + rows_per_slab < n ? r0 + rows_per_slab : n;
+  double s = 0.0;
+  for (long long r = r0; r < r1; ++r) s += x[r * d + c];
+  part[static_cast<long long>(blockIdx.y) * d + c] = s;
+}
+// G64[r, c] += G32[r, c] (the float64 accumulator over row chunks of the fp32-class chunk products)
+__global__ void k_acc_f64(const float* __restrict__ g32, long long ld32, double* __restrict__ g64, long long d) {
+  const long long r = blockIdx.x;
+  for (long long c = threadIdx.x; c < d; c += blockDim.x) g64[r * d + c] += static_cast<double>(g32[r * ld32 + c]);
+}
+
 }  // namespace jb

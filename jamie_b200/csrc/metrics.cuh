@@ -13,19 +13,17 @@ constexpr int MT_TILE = 64;      // rows of a x rows of b per block
 constexpr int MT_LC = 32;        // latent columns per shared-memory chunk
 constexpr int MT_THREADS = 256;  // 16 x 16 threads, 4 x 4 pairs each
 
-// squared distance of matched pairs: diag[i] = |a_i - b_i|^2 (float64 accumulation of float64 differences)
+// squared distance of matched pairs: diag[i] = |a_i - b_i|^2. The same float64 operations in the same order as a tile
+// element of mt_tile (sequential fma over the latent columns), so that D[i, i] of the tile equals diag[i] bit for bit.
 __global__ void k_pair_diag(const float* __restrict__ a, const float* __restrict__ b, long long n, int L, double* __restrict__ diag) {
-  const long long i = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int l = lane; l < L; l += 32) {
+  for (int l = 0; l < L; ++l) {
     const double d = static_cast<double>(a[i * L + l]) - static_cast<double>(b[i * L + l]);
-    s += d * d;
+    s = fma(d, d, s);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) diag[i] = s;
+  diag[i] = s;
 }
 
 // 64 x 64 tile of D[i, j] = |a_i - b_j|^2 in registers (4 x 4 per thread); `fn(i, j, d)` sees every valid pair
@@ -56,7 +54,7 @@ __device__ __forceinline__ void mt_tile(const float* __restrict__ a, long long n
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const double d = av[u] - bv[v];
-          acc[u][v] += d * d;
+          acc[u][v] = fma(d, d, acc[u][v]);
         }
     }
   }
@@ -151,11 +149,11 @@ __global__ void __launch_bounds__(KV_THREADS) k_knn_vote(const float* __restrict
     const unsigned int bal = __ballot_sync(0xffffffffu, tie);
     if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
     __syncthreads();
-    if (bal != 0u || true) {
+    if (tie) {   // ties in index order: the first s_need of them are among the k nearest
       unsigned int before = s_run;
       for (int w = 0; w < (tid >> 5); ++w) before += wcnt[w];
       before += __popc(bal & ((1u << (tid & 31)) - 1u));
-      if (tie && before < s_need) atomicAdd(&votes[cls[j]], 1);
+      if (before < s_need) atomicAdd(&votes[cls[j]], 1);
     }
     __syncthreads();
     if (tid == 0) {

@@ -268,6 +268,26 @@ class Engine:
                                            C.c_void_p(stream)))
         return out
 
+    def pca_colsum(self, X, stream=0):
+        """Column sums (float64) of a host [n, d] fp32 matrix on the GPU (jb_pca_colsum): first pass of the PCA fit."""
+        X = np.ascontiguousarray(X, np.float32)
+        n, d = X.shape
+        out = np.empty(d, np.float64)
+        _lib.check(self.lib.jb_pca_colsum(self.h, _ptr(X), n, d, out.ctypes.data_as(C.c_void_p), 0, C.c_void_p(stream)))
+        return out
+
+    def pca_gram(self, X, mean, stream=0):
+        """(X - mean)^T (X - mean) as float64 [d, d] (jb_pca_gram: split tensor-core GEMM over row chunks, float64
+        accumulation): second pass of the PCA fit (jamie/jamie.py:436-452)."""
+        X = np.ascontiguousarray(X, np.float32)
+        mean = np.ascontiguousarray(mean, np.float64)
+        n, d = X.shape
+        assert mean.shape[0] == d
+        out = np.empty((d, d), np.float64)
+        _lib.check(self.lib.jb_pca_gram(self.h, _ptr(X), n, d, mean.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 0,
+                                        C.c_void_p(stream)))
+        return out
+
     def profile_detail(self):
         """[phases, 4] of the last profile_step: total, longest CTA work, mean CTA work, barrier tail (us)."""
         n = int(self.lib.jb_num_phases())

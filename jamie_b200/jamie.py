@@ -195,11 +195,15 @@ class JAMIE(UnionCom):
                  in_place=False, loss_weights=None, model_pca='pca', model_class=edModelVar, model_lr=1e-3,
                  dropout=None, pca_dim=2 * [512], batch_step=True, use_f_tilde=True, use_early_stop=True,
                  min_epochs=2500, min_increment=1e-8, max_steps_without_increment=500, debug=False, log_debug=100,
-                 record_loss=True, enable_memory_logging=False, device='cpu', sampler='auto', **kwargs):
+                 record_loss=True, enable_memory_logging=False, device='cpu', sampler='auto', pca_fit='gpu', **kwargs):
         # sampler (not in the reference): 'reference' = the reference's numpy draws call for call; 'fast' = the same
         # distribution from an O(batch) draw; 'auto' = 'reference' up to FAST_SAMPLER_ROWS cells, 'fast' above.
         assert sampler in ('auto', 'reference', 'fast'), f"sampler must be 'auto', 'reference' or 'fast', not {sampler!r}"
         self.sampler = sampler
+        # pca_fit (not in the reference): 'gpu' = column sums + Gram matrix on the GPU, d x d eigensolver on the host (sklearn's
+        # covariance_eigh algorithm, exact PCA); 'sklearn' = the reference's host call PCA(n_components).fit_transform(data).
+        assert pca_fit in ('gpu', 'sklearn'), f"pca_fit must be 'gpu' or 'sklearn', not {pca_fit!r}"
+        self.pca_fit = pca_fit
         self.match_result = match_result
         self.PF_Ratio = PF_Ratio
         self.corr_method = corr_method
@@ -357,10 +361,13 @@ class JAMIE(UnionCom):
         rank, world = _dist_info()
         timer = time_logger()
 
-        # ---- preprocessing (jamie/jamie.py:433-469): the PCA is FIT on the host (sklearn, as in the reference); the
-        # projection + standardisation of the whole dataset runs on the GPU once the engine exists (below)
+        # ---- preprocessing (jamie/jamie.py:433-469). The PCA fit runs its two passes over the [n, d] matrix on the GPU
+        # (column sums + centred Gram matrix, rows sharded over the data-parallel ranks and all-reduced; pca_fit.py) and
+        # only the d x d eigenproblem on the host -- sklearn's covariance_eigh algorithm, returned as a fitted sklearn PCA.
+        # The projection + standardisation of the whole dataset runs on the GPU once the engine exists (below).
         pca_list, pca_inv_list, cols = [], [], []
         dims_req = self.pca_dim if self.pca_dim is not None else [None] * self.dataset_num
+        fit_engine = None
         for dim, data in zip(dims_req, self.dataset):
             if dim is not None:
                 if min(*data.shape) < dim:
@@ -368,8 +375,16 @@ class JAMIE(UnionCom):
                         f'PCA dim must be lower than {min(*data.shape)}, found {dim}, '
                         f'adjusting to compensate.')
                     dim = min(*data.shape)
-                pca = make_pca(dim)
-                sample = pca.fit_transform(data)
+                if self.pca_fit == 'gpu':
+                    from . import pca_fit
+                    if fit_engine is None:   # a minimal handle: the PCA entry points only need its device and GEMM tables
+                        dev0 = self._cuda_index()
+                        torch.cuda.set_device(dev0)
+                        fit_engine = Engine([8, 8], 2, 8, 0.0, device=dev0)
+                    pca, sample = pca_fit.fit_transform(fit_engine, np.asarray(data), dim, rank, world)
+                else:
+                    pca = make_pca(dim)
+                    sample = pca.fit_transform(data)
                 pre = preclass(sample, pca=pca)
                 cols.append(int(sample.shape[1]))
             else:
@@ -377,6 +392,8 @@ class JAMIE(UnionCom):
                 cols.append(int(np.shape(data)[1]))
             pca_list.append(pre.transform)
             pca_inv_list.append(pre.inverse_transform)
+        if fit_engine is not None:
+            fit_engine.close()
         self.col = cols
 
         # ---- model + optimizer state (jamie/jamie.py:471-481)

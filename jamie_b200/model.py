@@ -99,13 +99,22 @@ class edModelVar(nn.Module):
             raise RuntimeError('no CUDA engine attached to this model; use JAMIE.load_model / fit_transform')
 
     def forward(self, *X, corr=None):
-        """Eval-mode forward: (zs, combined, X_hat, mus, logvars) with zs = mus (jamie/model.py:233-234). ``corr``
-        only influences ``combined`` / ``X_hat`` which the reference's callers discard (jamie/jamie.py:798, 828);
-        they are returned for the zero-correspondence case."""
+        """Eval-mode forward: (zs, combined, X_hat, mus, logvars) with zs = mus (jamie/model.py:233-234). The reference's
+        own eval callers discard everything but ``zs`` (jamie/jamie.py:798, 828); ``combined`` / ``X_hat`` are returned for
+        the zero-correspondence case (combined = mus, X_hat = decode(mus)). A non-zero ``corr`` would mix the modalities
+        in ``combine`` (jamie/model.py:245-259), which only the training step of the engine implements: it raises here
+        rather than return tensors that silently ignore it."""
         self._require_eval()
         eng = self.engine()
-        mus = [torch.as_tensor(eng.encode(i, np.asarray(x, np.float32))) for i, x in enumerate(X)]
-        xhat = [torch.as_tensor(eng.predict(i, i, np.asarray(x, np.float32))) for i, x in enumerate(X)]
+
+        def host(x):
+            return (x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)).astype(np.float32)
+
+        if corr is not None and np.any(host(corr) != 0):
+            raise NotImplementedError('edModelVar.forward in eval mode with a non-zero corr: combined / X_hat of the mixed '
+                                      'latents are only computed inside the training step (jb_train_steps)')
+        mus = [torch.as_tensor(eng.encode(i, host(x))) for i, x in enumerate(X)]
+        xhat = [torch.as_tensor(eng.predict(i, i, host(x))) for i, x in enumerate(X)]
         return mus, mus, xhat, mus, None
 
     def impute(self, X, compose):

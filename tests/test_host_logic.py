@@ -104,13 +104,13 @@ def test_constructor_surface_and_validation():
 
 
 def test_metrics():
-    """The metrics against the reference's own formulas (jamie/evaluation.py:65-85, 114-132; jamie/jamie.py:943-961)
-    restated with the sklearn calls the reference makes."""
+    """The metrics oracle (oracle/metrics_oracle.py, the checker of the GPU metrics) against the reference's own formulas
+    (jamie/evaluation.py:65-85, 114-132; jamie/jamie.py:943-961) restated with the sklearn calls the reference makes."""
     import contextlib
     import io
     from sklearn.metrics import pairwise_distances
     from sklearn.neighbors import KNeighborsClassifier
-    from jamie_b200 import evaluation as E
+    from oracle import metrics_oracle as E
     rng = np.random.default_rng(0)
     a = rng.normal(size=(60, 4))
     b = a + 0.4 * rng.normal(size=a.shape)
