@@ -160,7 +160,7 @@ struct jb_engine {
   int fuse_ks = 1;           // JB_FUSE_KS=0: HEADS / DG3 as one CTA per M tile instead of K split over the cluster
   int accumulate = 0, accumulate_dev = 0;
   int wgrad_mode = jb::HG_MEDIUM;
-  int fwd_mode = jb::HG_PRECISE;    // JB_FWD_MODE=medium: forward / dgrad GEMMs without the accumulator drains (exploration)
+  int fwd_mode = -1;                // forward / dgrad GEMM mode: -1 = by K (see build_step), else forced (JB_FWD_MODE=precise | medium)
   int wgrad_bn = 256;
   int max_ksplit = 8;
   float gs = 1.f;
@@ -331,7 +331,15 @@ int build_step(jb_engine* e, int B) {
     if (const char* pv = getenv("JB_LOSS_SCALE_LOG2")) e->gs = ldexpf(1.f, atoi(pv));
   }
   const float inv_gs = 1.f / e->gs;
-  const int fmode = e->precision_fast ? jb::HG_SINGLE : e->fwd_mode;
+  // Forward / dgrad mode by reduction length: the tensor core adds products into its fp32 accumulator with truncation, a
+  // bias that grows with the number of accumulation steps. Up to K = 1024 (64 steps) three undrained passes (HG_MEDIUM)
+  // stay at 7e-6 of the fp32 oracle at the headline shape and save 9 us per step; longer reductions (2000-wide inputs
+  // without PCA: measured 6e-4 undrained) keep the drained HG_PRECISE mode.
+  auto fmode_for = [&](int K) {
+    if (e->precision_fast) return static_cast<int>(jb::HG_SINGLE);
+    if (e->fwd_mode >= 0) return e->fwd_mode;
+    return static_cast<int>(K <= 1024 ? jb::HG_MEDIUM : jb::HG_PRECISE);
+  };
   const int wmode = e->precision_fast ? jb::HG_SINGLE : e->wgrad_mode;
   std::vector<std::vector<StageSpec>> st(jb::SK_NUM_GEMM);
   // Cluster-fused tails need all rows of a column block in one cluster: B <= HG_CLUSTER M tiles.
@@ -349,7 +357,7 @@ int build_step(jb_engine* e, int B) {
   for (int i = 0; i < 2; ++i) {
     ModActs& a = e->act[i]; ModSegs& m = e->ms[i]; const int D = e->D[i];
     auto fwd = [&](int stage, HPlanes X, int ldx, const Seg& w, const Seg& b, jb::Parts* out, int ldy, int n_out, int n_in) {
-      StageSpec sp{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode, jb::EPI_BIAS, bias(b), 1.f, 0,
+      StageSpec sp{X, ldx, 0, W(w), w.ld, 0, out, nullptr, ldy, B, n_out, n_in, fbn(n_out), fmode_for(n_in), jb::EPI_BIAS, bias(b), 1.f, 0,
                    stage == 3 ? 0 : -1};   // the c planes carry the dynamic scale s_c
       if (fused) {
         static const int bn_layer[6] = {0, 1, -1, 2, 3, -1};
@@ -369,7 +377,7 @@ int build_step(jb_engine* e, int B) {
     fwd(5, a.g2, a.ld2D, m.W5, m.b5, &a.xhat, a.ldD, D, 2 * D);
     // dgrad dX[B, N_in] = dY W   (A = dY planes K-major, B = W planes MN-major, K = N_out)
     auto dgrad = [&](int stage, HPlanes dY, int lddy, const Seg& s, jb::Parts* out, int lddx, int n_out, int n_in) {
-      StageSpec sp{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode, jb::EPI_STORE, nullptr, 1.f, 0, -1};
+      StageSpec sp{dY, lddy, 0, W(s), s.ld, 1, out, nullptr, lddx, B, n_in, n_out, fbn(n_in), fmode_for(n_out), jb::EPI_STORE, nullptr, 1.f, 0, -1};
       if (fused && stage == 8) {   // d c: the LATBC phase becomes the tail (no F, one column block)
         if (e->f_dense == nullptr && e->merge_latent && L <= 64) { sp.fuse = jb::FUSE_LATBC; sp.fuse_arg = i; sp.fuse_ks = e->fuse_ks && n_out >= 8 * jb::HG_BK; }
       } else if (fused) {   // the dgrad result feeds a BatchNorm backward: stage 6 -> dec2, 7 -> dec1, 9 -> enc2, 10 -> enc1
@@ -868,7 +876,7 @@ int jb_create(const jb_config* cfg, jb_engine** out) {
   CU(cudaMalloc(&e->bar, 512));
   CU(cudaMemset(e->bar, 0, 512));
   if (const char* pv = getenv("JB_WGRAD_BN")) e->wgrad_bn = atoi(pv);
-  if (const char* pv = getenv("JB_FWD_MODE")) e->fwd_mode = strcmp(pv, "medium") == 0 ? jb::HG_MEDIUM : jb::HG_PRECISE;
+  if (const char* pv = getenv("JB_FWD_MODE")) e->fwd_mode = strcmp(pv, "medium") == 0 ? jb::HG_MEDIUM : (strcmp(pv, "precise") == 0 ? jb::HG_PRECISE : -1);
   if (const char* pv = getenv("JB_WGRAD_MODE")) e->wgrad_mode = strcmp(pv, "single") == 0 ? jb::HG_SINGLE : jb::HG_MEDIUM;
   if (const char* pv = getenv("JB_MAX_KSPLIT")) { if (atoi(pv) >= 1) e->max_ksplit = atoi(pv); }
   CU(cudaFuncSetAttribute(jb::gemm_tf32_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jb::GEMM_SMEM_BYTES));

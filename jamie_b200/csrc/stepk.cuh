@@ -1621,6 +1621,10 @@ __device__ __forceinline__ double xchg_sweep_mc(const StepCtx& cx, long long a, 
   }
   return static_cast<double>(sq);
 }
+// (Measured and removed: the same sweep as TMA bulk copies through the idle operand ring -- R bulk loads per sub-chunk into
+// shared memory, sum, R bulk stores. 39.8 vs 40.5 us per exchange at two ranks, i.e. the sweep is bound by the NVLink
+// stream, not by load issue; and the bulk loads of peer memory returned stale lines in ~1e-3 of the elements, which the
+// .relaxed.sys register loads below cannot.)
 __device__ __forceinline__ void sk_exchange(const StepCtx& cx, unsigned int epoch, int cta, int ncta, int tid, double* shd) {
   const int R = cx.xworld, me = cx.xrank;
   if (!(cx.xdbg & 2)) {

