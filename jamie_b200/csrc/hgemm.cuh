@@ -115,9 +115,25 @@ struct HgPipe {
 __device__ __forceinline__ void hg_stamp(const HgPipe& pp, int k) { if (pp.dbg != nullptr) pp.dbg[k] = clock64(); }
 
 // fp16 split of one value (producers of GEMM operands call this)
+// Conversions SATURATE to +-65504 instead of overflowing to inf (cvt.rn.satfinite: same single instruction). Operand
+// magnitudes are bounded by construction or by the dynamic scales, except in blow-ups (measured on the noise benchmark:
+// one latent row at 1e16 crushes the other rows' planes to zero, a BatchNorm layer sees zero variance and amplifies its
+// gradient 316x past fp16's range): an inf there became NaN in the lo plane and destroyed every parameter, where the fp32
+// reference takes one clipped step and carries on. Saturated values are wrong but finite, and the global-norm clip
+// that such a step always triggers scales them away.
+__device__ __forceinline__ __half h_sat(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return __ushort_as_half(r);
+}
+__device__ __forceinline__ __half2 h2_sat(float a, float b) {   // .x = a, .y = b
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return *reinterpret_cast<__half2*>(&r);
+}
 __device__ __forceinline__ void h_split(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn((x - __half2float(hi)) * HG_LO_SCALE);
+  hi = h_sat(x);
+  lo = h_sat((x - __half2float(hi)) * HG_LO_SCALE);
 }
 __device__ __forceinline__ float h_join(__half hi, __half lo) { return __half2float(hi) + __half2float(lo) * HG_LO_INV; }
 

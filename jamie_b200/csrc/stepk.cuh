@@ -168,17 +168,17 @@ struct StepVars {    // per-step scalars (one copy per CTA in shared memory)
 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ void st_h4(__half* p, float a, float b, float c, float d, bool lo_of = false) { (void)lo_of;
-  const __half2 u = __floats2half2_rn(a, b), v = __floats2half2_rn(c, d);
+  const __half2 u = h2_sat(a, b), v = h2_sat(c, d);
   uint2 w;
   w.x = *reinterpret_cast<const uint32_t*>(&u); w.y = *reinterpret_cast<const uint32_t*>(&v);
   *reinterpret_cast<uint2*>(p) = w;
 }
 // split four values into the hi / lo planes with two 8-byte stores
 __device__ __forceinline__ void split4_store(__half* hi, __half* lo, float a, float b, float c, float d) {
-  const __half ha = __float2half_rn(a), hb = __float2half_rn(b), hc = __float2half_rn(c), hd = __float2half_rn(d);
+  const __half ha = h_sat(a), hb = h_sat(b), hc = h_sat(c), hd = h_sat(d);
   const __half2 h01 = __halves2half2(ha, hb), h23 = __halves2half2(hc, hd);
-  const __half2 l01 = __floats2half2_rn((a - __half2float(ha)) * HG_LO_SCALE, (b - __half2float(hb)) * HG_LO_SCALE);
-  const __half2 l23 = __floats2half2_rn((c - __half2float(hc)) * HG_LO_SCALE, (d - __half2float(hd)) * HG_LO_SCALE);
+  const __half2 l01 = h2_sat((a - __half2float(ha)) * HG_LO_SCALE, (b - __half2float(hb)) * HG_LO_SCALE);
+  const __half2 l23 = h2_sat((c - __half2float(hc)) * HG_LO_SCALE, (d - __half2float(hd)) * HG_LO_SCALE);
   uint2 wh, wl;
   wh.x = *reinterpret_cast<const uint32_t*>(&h01); wh.y = *reinterpret_cast<const uint32_t*>(&h23);
   wl.x = *reinterpret_cast<const uint32_t*>(&l01); wl.y = *reinterpret_cast<const uint32_t*>(&l23);
@@ -637,9 +637,9 @@ __device__ __forceinline__ void sk_side_mask(const StepCtx& cx, const StepVars& 
 }
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) { return ld_shared_cluster_f4(addr); }
 __device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
-  hi = __floats2half2_rn(a, b);
+  hi = h2_sat(a, b);
   const float2 f = __half22float2(hi);
-  lo = __floats2half2_rn((a - f.x) * HG_LO_SCALE, (b - f.y) * HG_LO_SCALE);
+  lo = h2_sat((a - f.x) * HG_LO_SCALE, (b - f.y) * HG_LO_SCALE);
 }
 
 // Linear output tile -> BatchNorm1d (batch statistics over the cluster: per-CTA mean / M2, merged with Chan's formula in
