@@ -396,7 +396,12 @@ class JAMIE(UnionCom):
             fit_engine.close()
         self.col = cols
 
-        # ---- model + optimizer state (jamie/jamie.py:471-481)
+        # ---- model + optimizer state (jamie/jamie.py:471-481). The engine implements exactly edModelVar (the only model the
+        # reference ships): another architecture passed as model_class would be built here and then trained as
+        # something else, so it is rejected instead of silently ignored.
+        if not (isinstance(self.model_class, type) and issubclass(self.model_class, edModelVar)):
+            raise NotImplementedError(f'model_class={self.model_class!r}: the CUDA engine implements jamie.model.edModelVar '
+                                      '(or a subclass that keeps its architecture)')
         self.model = self.model_class(self.col, self.output_dim, preprocessing=pca_list,
                                       preprocessing_inverse=pca_inv_list, dropout=self.dropout)
         # Batch size setup (jamie/jamie.py:510-514); with R data-parallel ranks an epoch is max(row)/(B*R) steps

@@ -15,8 +15,10 @@ The result is returned as a genuine ``sklearn.decomposition.PCA`` object with it
 import numpy as np
 
 
-def _all_reduce_sum(arr, group=None):
-    """Sum a float64 host array over the ranks of an initialised torch.distributed group (no-op otherwise)."""
+def _all_reduce_sum(arr, world, group=None):
+    """Sum a float64 host array over the `world` ranks of an initialised torch.distributed group (no-op for one rank)."""
+    if world <= 1:
+        return arr
     try:
         import torch
         import torch.distributed as dist
@@ -41,10 +43,10 @@ def gram_pca_fit(engine, X, n_components, rank=0, world=1, group=None):
     lo, hi = n * rank // world, n * (rank + 1) // world
     Xs = X[lo:hi]
     colsum = engine.pca_colsum(Xs) if hi > lo else np.zeros(d)
-    colsum = _all_reduce_sum(colsum, group)
+    colsum = _all_reduce_sum(colsum, world, group)
     mean = colsum / n
     gram = engine.pca_gram(Xs, mean) if hi > lo else np.zeros((d, d))
-    gram = _all_reduce_sum(gram, group)
+    gram = _all_reduce_sum(gram, world, group)
     gram = (gram + gram.T) * 0.5                      # the tensor-core product is symmetric only to rounding
     C = gram / max(n - 1, 1)
     evals, evecs = np.linalg.eigh(C)                   # ascending

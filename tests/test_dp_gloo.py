@@ -30,7 +30,30 @@ def _worker(rank, world, port, q):
     seen = []
     got = shard_rows_apply(lambda x: (seen.append(len(x)), x * 2 + rank * 0)[1], full)
     assert seen == [3 if rank == 0 else 4] and np.array_equal(got, full * 2)
-    q.put((rank, lo, hi, prior.sampling_method, prior.corr_samples.tolist(), g.tolist(), len_dataloader))
+    # PCA fit with the rows sharded over the ranks (jamie_b200/pca_fit.py): each rank reduces its own rows (here a numpy
+    # stand-in for jb_pca_colsum / jb_pca_gram), column sums and Gram matrices are all-reduced, every rank solves the same
+    # d x d eigenproblem -> the same components as one rank over all rows, and as sklearn's own fit
+    from jamie_b200 import pca_fit
+
+    class HostPasses:
+        def pca_colsum(self, X):
+            return np.asarray(X, np.float64).sum(0)
+
+        def pca_gram(self, X, mean):
+            Xc = np.asarray(X, np.float64) - mean
+            return Xc.T @ Xc
+
+    rng = np.random.default_rng(3)
+    X = (rng.normal(size=(301, 6)) * np.linspace(3, 0.5, 6)) @ rng.normal(size=(6, 20)) + rng.normal(size=20)
+    X = X.astype(np.float32)
+    comps, mean, ev, tot, n = pca_fit.gram_pca_fit(HostPasses(), X, 4, rank, world)
+    comps1, mean1, ev1, tot1, n1 = pca_fit.gram_pca_fit(HostPasses(), X, 4, 0, 1)
+    from sklearn.decomposition import PCA
+    ref = PCA(n_components=4, svd_solver='full').fit(X.astype(np.float64))
+    pca_ok = (n == n1 == 301 and np.allclose(comps, comps1, atol=1e-10) and np.allclose(ev, ev1, rtol=1e-10)
+              and np.allclose(comps, ref.components_, atol=1e-8) and np.allclose(ev, ref.explained_variance_, rtol=1e-8)
+              and np.allclose(mean, ref.mean_, atol=1e-10))
+    q.put((rank, lo, hi, prior.sampling_method, prior.corr_samples.tolist(), g.tolist(), len_dataloader, bool(pca_ok)))
     dist.destroy_process_group()
 
 
@@ -45,7 +68,8 @@ def test_two_rank_sharding_and_reduce():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, lo0, hi0, m0, c0, g0, l0), (r1, lo1, hi1, m1, c1, g1, l1) = res
+    (r0, lo0, hi0, m0, c0, g0, l0, p0), (r1, lo1, hi1, m1, c1, g1, l1, p1) = res
+    assert p0 and p1                                                          # sharded PCA fit == single-rank fit == sklearn
     assert lo0 == [0, 0] and hi0 == lo1 and hi1 == [1001, 1001]          # contiguous, disjoint, covering
     assert m0 == m1 == 'hybrid'
     assert c0 == [[0, 0], [2, 2]] and c1 == [[0, 0], [2, 2]]                 # shard-local indices (500 is even)

@@ -109,3 +109,30 @@ def test_load_reference_checkpoint():
         got = jm.modal_predict(io[f'data{i}'], i)
         assert U.rel(got, io[f'pred{i}']) < 3e-3
         assert U.rel(jm.transform_one(io[f'data{i}'], i), io[f'tone{i}']) < 3e-3
+
+
+def test_early_stop_fires_at_the_epoch_the_reference_rule_gives():
+    """A run that really stops early (the chunks of epochs the fit loop enqueues never cross the stop decision): with one
+    batch per epoch `best_batch_loss` is the epoch's total loss = the sum of the four `loss_history` entries, so the
+    reference's bookkeeping (jamie/jamie.py:777-792) can be replayed on the recorded history and must stop where the run did."""
+    from jamie import JAMIE
+    data, _ = _mmdma_like(n=100, dims=(60, 40), seed=3)
+    np.random.seed(7)
+    kw = dict(min_epochs=30, min_increment=2e-2, max_steps_without_increment=6, epoch_DNN=3000)
+    jm = JAMIE(output_dim=8, batch_size=128, pca_dim=None, use_f_tilde=False, log_DNN=10 ** 6, **kw)
+    jm.fit_transform(dataset=data)
+    ran = len(jm.loss_history['KL'])
+    assert jm.epochs_run == ran
+    total = np.sum([np.asarray(jm.loss_history[k], np.float64) for k in ('KL', 'Rec', 'CosSim', 'F')], axis=0)
+    best, streak, want = np.inf, 0, kw['epoch_DNN']
+    for epoch in range(len(total)):
+        if epoch > kw['min_epochs']:
+            if best - total[epoch] > kw['min_increment']:
+                best, streak = total[epoch], 0
+            else:
+                streak += 1
+            if streak >= kw['max_steps_without_increment']:
+                want = epoch + 1
+                break
+    assert kw['min_epochs'] + kw['max_steps_without_increment'] < ran < kw['epoch_DNN'], ran     # it did stop early
+    assert ran == want, (ran, want)

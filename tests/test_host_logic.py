@@ -101,6 +101,9 @@ def test_constructor_surface_and_validation():
         JAMIE(distance_mode='nope').fit_transform(dataset=[np.zeros((4, 3)), np.zeros((4, 3))])
     with pytest.raises(AssertionError, match='Model must be trained'):
         JAMIE().modal_predict(np.zeros((2, 2)), 0)
+    # the engine implements edModelVar only: any other model_class is rejected before anything is trained
+    with pytest.raises(NotImplementedError, match='model_class'):
+        JAMIE(model_class=dict, use_f_tilde=False, pca_dim=None).fit_transform(dataset=[np.random.rand(8, 3), np.random.rand(8, 3)])
 
 
 def test_metrics():
