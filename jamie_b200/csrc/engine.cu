@@ -146,6 +146,7 @@ struct jb_engine {
   ModActs act[2]{};
   float *corr = nullptr, *corr_t = nullptr, *fblk = nullptr, *fblk_t = nullptr;
   float *lat_r = nullptr, *rowpart = nullptr, *lat_coef = nullptr;
+  int2* corr_hint = nullptr;
   int cosine = 0;                   // jb_set_dist_method
   float *cmax_part = nullptr, *dmax_part = nullptr, *dyn = nullptr;   // dynamic operand scales (stepk.cuh)
   // step tables at batch size step_B
@@ -294,7 +295,7 @@ void carve(jb_engine* e, Carver& c) {
   }
   e->corr = c.take<float>(B * B); e->corr_t = c.take<float>(B * B);
   e->fblk = c.take<float>(B * B); e->fblk_t = c.take<float>(B * B);
-  e->lat_r = c.take<float>(B * e->LP); e->rowpart = c.take<float>(2 * B * 8); e->lat_coef = c.take<float>(2 * B * 4);
+  e->lat_r = c.take<float>(B * e->LP); e->rowpart = c.take<float>(2 * B * 8); e->lat_coef = c.take<float>(2 * B * 4); e->corr_hint = c.take<int2>(2 * B);
   e->cmax_part = c.take<float>(jb::SK_MAX_CTAS); e->dmax_part = c.take<float>(jb::SK_MAX_CTAS); e->dyn = c.take<float>(8);
 }
 
@@ -555,6 +556,8 @@ int build_step(jb_engine* e, int B) {
   cx.p_diag = e->p_diag; cx.p_dense = e->p_dense; cx.f_dense = e->f_dense; cx.pn1 = e->pn1;
   cx.corr = e->corr; cx.corr_t = e->corr_t; cx.fblk = e->fblk; cx.fblk_t = e->fblk_t;
   cx.pf_ratio = e->cfg.pf_ratio; cx.f_present = e->f_dense != nullptr;
+  // the row shortcut of COMBINE / LATBZ exists where GATHER builds the blocks with sk_corr_row_diag (same condition as there)
+  cx.corr_hint = (e->p_diag != nullptr && e->p_dense == nullptr && e->f_dense == nullptr && !getenv("JB_NO_CORR_HINT")) ? e->corr_hint : nullptr;
   cx.lat_r = e->lat_r; cx.rowpart = e->rowpart; cx.lat_coef = e->lat_coef; cx.cosine = e->cosine;
   cx.cmax_part = e->cmax_part; cx.dmax_part = e->dmax_part; cx.dyn = e->dyn;
   {

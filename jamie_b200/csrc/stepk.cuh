@@ -109,6 +109,7 @@ struct StepCtx {
   // correspondence blocks
   const float *p_diag, *p_dense, *f_dense; long long pn1;
   float *corr, *corr_t, *fblk, *fblk_t;
+  int2* corr_hint;                 // diagonal priors: per row of corr (then corr^T) {number of nonzeros, column of the first}; else null
   float pf_ratio;
   int f_present;
   // latent scratch
@@ -273,15 +274,22 @@ __device__ __forceinline__ void sk_corr_row_diag(const StepCtx& cx, long long ba
   const float rp = p == 0.f ? 1.f : p;
   const float val = cx.pf_ratio * (diag / rp) + (1.f - cx.pf_ratio) * 0.f;
   float* row = (tr ? cx.corr_t : cx.corr) + static_cast<long long>(a) * B;
+  int nn = 0, first = B;   // nonzeros along the row and the column of the first one (the consumers' shortcut, sk_row_times)
 #pragma unroll 1
   for (int b0 = lane; b0 < B; b0 += 128) {
     int v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = b0 + 32 * u < B ? idx_other[b0 + 32 * u] : -1;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (b0 + 32 * u < B) row[b0 + 32 * u] = v[u] == cell ? val : 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const bool hit = v[u] == cell;
+      if (b0 + 32 * u < B) row[b0 + 32 * u] = hit ? val : 0.f;
+      if (hit) { ++nn; first = min(first, b0 + 32 * u); }
+    }
   }
+  nn = __reduce_add_sync(0xffffffffu, nn);
+  first = __reduce_min_sync(0xffffffffu, first);
+  if (lane == 0 && cx.corr_hint != nullptr) cx.corr_hint[it] = val != 0.f ? make_int2(nn, first) : make_int2(0, 0);
 }
 // x_i[b, :] = data_i[idx_i[row][b], :] (jamie/jamie.py:583) + operand planes; one warp per (modality, row)
 __device__ __forceinline__ void sk_gather_row(const StepCtx& cx, const StepVars& sv, int use_stage, int it, int lane) {
@@ -1061,11 +1069,28 @@ __device__ __forceinline__ void sk_reparam(const StepCtx& cx, const StepVars& sv
 
 // out[l] (per lane, LAT_MAXT strided) = sum_b M[row, b] * V[b, l], skipping zero entries; also returns the row sum.
 // 128 entries of the row per iteration (four loads in flight per lane), then a ballot loop over the nonzeros.
+// hint (diagonal priors, written by sk_corr_row_diag): {nonzeros of the row, column of the first}: rows without a nonzero
+// (unmatched cells) and rows with exactly one (every matched cell unless the batch repeats it) skip the scan of the dense
+// row -- four dependent L2 round trips on the critical path of COMBINE and LATBZ. Same arithmetic: 0 + x = x.
 __device__ __forceinline__ float sk_row_times(const float* __restrict__ Mrow, const float* __restrict__ V, int B, int LP, int L, int lane,
-                                              float (&acc)[LAT_MAXT]) {
+                                              float (&acc)[LAT_MAXT], const int2* __restrict__ hint = nullptr) {
 #pragma unroll
   for (int t = 0; t < LAT_MAXT; ++t) acc[t] = 0.f;
   float rs = 0.f;
+  if (hint != nullptr) {
+    const int2 h = sk_ld(hint);
+    if (h.x == 0) return 0.f;
+    if (h.x == 1) {
+      const float mv = sk_ld(Mrow + h.y);
+      const float* v = V + static_cast<long long>(h.y) * LP;
+#pragma unroll
+      for (int t = 0; t < LAT_MAXT; ++t) {
+        const int l = lane + 32 * t;
+        if (l < L) acc[t] += mv * sk_ld(v + l);
+      }
+      return rs + mv;
+    }
+  }
 #pragma unroll 1
   for (int sup = 0; sup < B; sup += 128) {
     float m[4];
@@ -1119,7 +1144,7 @@ __device__ __forceinline__ void sk_combine(const StepCtx& cx, int gw, int nw, in
     const float si = sk_ld(cx.sigma + i), sj = sk_ld(cx.sigma + j);
     const float* Ci = (i == 0 ? cx.corr : cx.corr_t) + static_cast<long long>(row) * B;
     float acc[LAT_MAXT];
-    const float rs = sk_row_times(Ci, cx.m[j].z, B, LP, L, lane, acc);
+    const float rs = sk_row_times(Ci, cx.m[j].z, B, LP, L, lane, acc, cx.corr_hint != nullptr ? cx.corr_hint + w : nullptr);
     const float den = si + sj * rs;
     if (lane == 0) { M.den[row] = den; M.rs[row] = rs; }
     float smu = 0.f, scs = 0.f, sr = 0.f, szc = 0.f, szz = 0.f, scc = 0.f;
@@ -1306,7 +1331,7 @@ __device__ __forceinline__ void sk_latbz(const StepCtx& cx, const StepVars& sv, 
     const float si = sk_ld(cx.sigma + i);
     const float* Ci = (i == 0 ? cx.corr : cx.corr_t) + static_cast<long long>(row) * B;
     float acc[LAT_MAXT];
-    sk_row_times(Ci, cx.m[j].g, B, LP, L, lane, acc);
+    sk_row_times(Ci, cx.m[j].g, B, LP, L, lane, acc, cx.corr_hint != nullptr ? cx.corr_hint + w : nullptr);
     float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cx.cosine) cf = sk_ld(reinterpret_cast<const float4*>(cx.lat_coef) + static_cast<long long>(i) * B + row);
 #pragma unroll
