@@ -433,6 +433,18 @@ class JAMIE(UnionCom):
             else:
                 prior = PriorSpec(np.zeros((hi[0] - lo[0], hi[1] - lo[1]), np.float32), [hi[0] - lo[0], hi[1] - lo[1]], method=gm)
             F_local = None if self._F_dense is None else self._F_dense[lo[0]:hi[0], lo[1]:hi[1]]
+            if rank == 0:   # say so once when a dense P / F has correspondences that the sharding drops
+                for name, M_ in (('P', prior_full.dense), ('F', self._F_dense)):
+                    if M_ is None:
+                        continue
+                    kept = sum(int(np.count_nonzero(M_[(self.row[0] * r_) // world:(self.row[0] * (r_ + 1)) // world,
+                                                      (self.row[1] * r_) // world:(self.row[1] * (r_ + 1)) // world]))
+                               for r_ in range(world))
+                    total_nz = int(np.count_nonzero(M_))
+                    if kept < total_nz:
+                        warnings.warn(f'data-parallel training over {world} ranks uses the diagonal blocks of {name} only: '
+                                      f'{total_nz - kept} of its {total_nz} nonzero correspondences link cells of different '
+                                      'ranks and are ignored')
         local_rows = [hi[i] - lo[i] for i in range(2)]
         self.F = F_local
         if world > 1 and min(local_rows) < self.batch_size and not (min(self.col) < self.batch_size):
