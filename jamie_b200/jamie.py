@@ -324,7 +324,10 @@ class JAMIE(UnionCom):
             print('Dataset {}:'.format(i), np.shape(self.dataset[i]))
             self.distance_function = distance_function(self.distance_mode, self.kmax)
             if save_dist:
-                self.dist.append(self.distance_function(self.dataset[i]))
+                data_i = self.dataset[i]
+                if hasattr(data_i, 'toarray') and not isinstance(data_i, np.ndarray):   # scipy.sparse (AnnData.X)
+                    data_i = data_i.toarray()
+                self.dist.append(self.distance_function(data_i))
 
     def match(self):
         """Find correspondence between multi-omics datasets (jamie/jamie.py:224-250)"""
@@ -368,7 +371,7 @@ class JAMIE(UnionCom):
         pca_list, pca_inv_list, cols = [], [], []
         dims_req = self.pca_dim if self.pca_dim is not None else [None] * self.dataset_num
         fit_engine = None
-        for dim, data in zip(dims_req, self.dataset):
+        for i_mod, (dim, data) in enumerate(zip(dims_req, self.dataset)):
             if dim is not None:
                 if min(*data.shape) < dim:
                     warnings.warn(
@@ -381,13 +384,16 @@ class JAMIE(UnionCom):
                         dev0 = self._cuda_index()
                         torch.cuda.set_device(dev0)
                         fit_engine = Engine([8, 8], 2, 8, 0.0, device=dev0)
-                    pca, sample = pca_fit.fit_transform(fit_engine, np.asarray(data), dim, rank, world)
+                    pca, sample = pca_fit.fit_transform(fit_engine, data if pca_fit.is_sparse(data) else np.asarray(data),
+                                                        dim, rank, world)
                 else:
                     pca = make_pca(dim)
                     sample = pca.fit_transform(data)
                 pre = preclass(sample, pca=pca)
                 cols.append(int(sample.shape[1]))
             else:
+                if hasattr(data, 'toarray') and not isinstance(data, np.ndarray):   # no PCA on a sparse matrix: it is trained on as is
+                    data = self.dataset[i_mod] = data.toarray()
                 pre = preclass(data, axis=0)
                 cols.append(int(np.shape(data)[1]))
             pca_list.append(pre.transform)

@@ -35,17 +35,41 @@ def _all_reduce_sum(arr, world, group=None):
     return t.numpy()
 
 
+BLOCK_ROWS = 16384   # rows densified at a time when the input is a scipy.sparse matrix (AnnData.X)
+
+
+def is_sparse(X):
+    return hasattr(X, 'toarray') and not isinstance(X, np.ndarray)
+
+
+def dense_blocks(X, lo=0, hi=None, rows=BLOCK_ROWS):
+    """float32 row blocks of X[lo:hi]: the whole range at once for an ndarray, BLOCK_ROWS densified rows at a time for a
+    scipy.sparse matrix (column sums, Gram matrices and projections are all additive / independent over row blocks, so a
+    sparse single-cell matrix never has to exist densely on the host)."""
+    hi = X.shape[0] if hi is None else hi
+    if not is_sparse(X):
+        if hi > lo:
+            yield lo, np.ascontiguousarray(X[lo:hi], np.float32)
+        return
+    Xr = X.tocsr() if hasattr(X, 'tocsr') else X
+    for r0 in range(lo, hi, rows):
+        r1 = min(hi, r0 + rows)
+        yield r0, np.ascontiguousarray(Xr[r0:r1].toarray(), np.float32)
+
+
 def gram_pca_fit(engine, X, n_components, rank=0, world=1, group=None):
-    """Fit on the rows ``X[rank::...]`` shard of this rank (contiguous split), reduce over ranks; returns
+    """Fit on the rows of this rank's contiguous shard of X (ndarray or scipy.sparse), reduce over ranks; returns
     (components [k, d], mean [d], explained_variance [k], total_variance, n_samples), float64."""
-    X = np.ascontiguousarray(X, np.float32)
     n, d = X.shape
     lo, hi = n * rank // world, n * (rank + 1) // world
-    Xs = X[lo:hi]
-    colsum = engine.pca_colsum(Xs) if hi > lo else np.zeros(d)
+    colsum = np.zeros(d)
+    for _, blk in dense_blocks(X, lo, hi):
+        colsum += engine.pca_colsum(blk)
     colsum = _all_reduce_sum(colsum, world, group)
     mean = colsum / n
-    gram = engine.pca_gram(Xs, mean) if hi > lo else np.zeros((d, d))
+    gram = np.zeros((d, d))
+    for _, blk in dense_blocks(X, lo, hi):
+        gram += engine.pca_gram(blk, mean)
     gram = _all_reduce_sum(gram, world, group)
     gram = (gram + gram.T) * 0.5                      # the tensor-core product is symmetric only to rounding
     C = gram / max(n - 1, 1)
@@ -87,5 +111,7 @@ def fit_transform(engine, X, n_components, rank=0, world=1, group=None):
     """(fitted sklearn PCA, sample = the projected training matrix [n, k] float64): what ``pca.fit_transform(data)`` gives
     the reference (jamie/jamie.py:451); the projection is ``jb_pca_project`` without standardisation."""
     pca = fit_sklearn_pca(engine, X, n_components, rank, world, group)
-    sample = engine.pca_project(np.ascontiguousarray(X, np.float32), pca.components_, pca.mean_, 0.0, 1.0).astype(np.float64)
+    sample = np.empty((X.shape[0], int(n_components)), np.float64)
+    for r0, blk in dense_blocks(X):
+        sample[r0:r0 + blk.shape[0]] = engine.pca_project(blk, pca.components_, pca.mean_, 0.0, 1.0)
     return pca, sample

@@ -109,7 +109,11 @@ class preclass:
         if lin is not None and _GPU_PROJECTOR is not None and getattr(_GPU_PROJECTOR, 'h', None) and np.ndim(X) == 2:
             m, s = self.stats()
             if np.isfinite(s) and s > 0:
-                return _GPU_PROJECTOR.pca_project(X, lin[0], lin[1], m, s).astype(np.float64)   # the reference returns float64
+                from .pca_fit import dense_blocks   # scipy.sparse inputs (AnnData.X) are densified 16 k rows at a time
+                out = np.empty((X.shape[0], lin[0].shape[0]), np.float64)   # the reference returns float64
+                for r0, blk in dense_blocks(X):
+                    out[r0:r0 + blk.shape[0]] = _GPU_PROJECTOR.pca_project(blk, lin[0], lin[1], m, s)
+                return out
         out = X
         if self.pca is not None:
             out = self.pca.transform(out)

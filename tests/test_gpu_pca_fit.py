@@ -81,3 +81,26 @@ def test_fit_transform_uses_the_gpu_pca_fit_and_matches_the_host_fit():
     for i in range(2):
         assert isinstance(pres['gpu'][1][i], PCA)
         np.testing.assert_allclose(pres['gpu'][0][i], pres['sklearn'][0][i], atol=2e-3)
+
+
+def test_sparse_input_matches_dense_through_the_api():
+    """AnnData-style scipy.sparse matrices: PCA fit and projection run block-wise (16 k densified rows at a time) and give
+    what the dense matrices give."""
+    import scipy.sparse as sp
+    from jamie import JAMIE
+    rng = np.random.default_rng(8)
+    data = []
+    for d, seed in ((90, 4), (70, 5)):
+        X = _data(300, d, 24, seed)
+        X[np.abs(X - X.mean(0)) < 0.4 * X.std(0)] = 0.0          # make it sparse-ish (structure survives)
+        data.append(X.astype(np.float32).astype(np.float64))
+    outs = {}
+    for how in ('dense', 'sparse'):
+        np.random.seed(1)
+        jm = JAMIE(output_dim=8, batch_size=64, pca_dim=[20, 16], epoch_DNN=3, min_epochs=1, use_f_tilde=False, manual_seed=5)
+        emb = jm.fit_transform(dataset=[(sp.csr_matrix(d) if how == 'sparse' else d.copy()) for d in data])
+        outs[how] = [np.asarray(jm.dataset[i]) for i in range(2)], emb, jm.modal_predict(sp.csr_matrix(data[0]) if how == 'sparse' else data[0], 0)
+    for i in range(2):
+        np.testing.assert_allclose(outs['sparse'][0][i], outs['dense'][0][i], atol=1e-5)
+        np.testing.assert_allclose(outs['sparse'][1][i], outs['dense'][1][i], atol=1e-4)
+    np.testing.assert_allclose(outs['sparse'][2], outs['dense'][2], atol=1e-3)

@@ -281,3 +281,46 @@ def test_chunked_early_stopping_matches_the_epoch_by_epoch_rule():
                     break
             n = nxt
         assert epoch == want, (trial, epoch, want)
+
+
+def test_pca_fit_accepts_sparse_blocks():
+    """scipy.sparse inputs (AnnData.X) go through the PCA fit and the projection 16 k densified rows at a time: column sums,
+    Gram matrices and projections add up / concatenate over row blocks, so the result equals the dense one (the GPU passes
+    are replaced by numpy stand-ins here; the block logic is what is tested)."""
+    import scipy.sparse as sp
+    from jamie_b200 import pca_fit
+
+    class HostPasses:
+        calls = 0
+
+        def pca_colsum(self, X):
+            HostPasses.calls += 1
+            assert isinstance(X, np.ndarray) and X.dtype == np.float32
+            return X.astype(np.float64).sum(0)
+
+        def pca_gram(self, X, mean):
+            Xc = X.astype(np.float64) - mean
+            return Xc.T @ Xc
+
+        def pca_project(self, X, comp, mean, m, s):
+            return ((X.astype(np.float64) - mean) @ comp.T - m) / s
+
+    rng = np.random.default_rng(1)
+    X = (rng.random((700, 40)) * (rng.random((700, 40)) < 0.2)).astype(np.float32)       # 80 % zeros
+    X[:, :6] += (rng.normal(size=(700, 3)) @ rng.normal(size=(3, 6))).astype(np.float32)
+    old = pca_fit.BLOCK_ROWS
+    try:
+        pca_d, sample_d = pca_fit.fit_transform(HostPasses(), X, 5)
+        n_dense = HostPasses.calls
+        blocks = list(pca_fit.dense_blocks(sp.csr_matrix(X), 100, 650, rows=256))
+        assert [b[0] for b in blocks] == [100, 356, 612] and blocks[-1][1].shape == (38, 40)
+        np.testing.assert_array_equal(np.concatenate([b[1] for b in blocks]), X[100:650])
+        HostPasses.calls = 0
+        pca_fit.dense_blocks.__defaults__ = (0, None, 256)      # small blocks so that several are summed
+        pca_s, sample_s = pca_fit.fit_transform(HostPasses(), sp.csr_matrix(X), 5)
+        assert HostPasses.calls == 3 and n_dense == 1
+    finally:
+        pca_fit.dense_blocks.__defaults__ = (0, None, old)
+    np.testing.assert_allclose(pca_s.components_, pca_d.components_, atol=1e-10)
+    np.testing.assert_allclose(pca_s.explained_variance_, pca_d.explained_variance_, rtol=1e-10)
+    np.testing.assert_allclose(sample_s, sample_d, atol=1e-9)
