@@ -90,3 +90,23 @@ def test_feature_pearson_matches_oracle():
     np.testing.assert_allclose(got[keep], want[keep], rtol=0, atol=1e-9)
     assert E.mean_feature_r(x, y) == pytest.approx(MO.mean_feature_r(x, y), abs=1e-9)
     np.testing.assert_allclose(E.imputation_correlation(x * 2 + 1, x), 1.0, atol=1e-9)
+
+
+def test_gpu_metrics_reproduce_the_reference_values():
+    """the GPU metrics on the embeddings of tests/golden/metrics.npz == what the reference's own functions returned"""
+    import json
+    import os
+    from jamie_b200 import evaluation as E
+    from tests.golden_util import GOLDEN_DIR
+    G = np.load(os.path.join(GOLDEN_DIR, 'metrics.npz'))
+    for c, rec in enumerate(json.loads(str(G['meta']))):
+        e0, e1, y0, y1 = (G[f'c{c}/{k}'] for k in ('e0', 'e1', 'y0', 'y1'))
+        if 'foscttm' in rec:
+            assert E.test_closer([e0, e1], verbose=False) == rec['foscttm']
+        for k in (1, 5, 17):
+            assert E.test_LabelTA([e0, e1], [y0, y1], k=k, verbose=False) == rec[f'lta_k{k}']
+        acc, kdef = E.label_transfer_accuracy([e0, e1], [y0, y1], k=None, return_k=True)
+        assert kdef == rec['k_default'] and acc == rec['lta_default']
+        want = G[f'c{c}/r']
+        keep = np.isfinite(want)
+        np.testing.assert_allclose(E.imputation_correlation(G[f'c{c}/x'], G[f'c{c}/y'])[keep], want[keep], atol=1e-6)

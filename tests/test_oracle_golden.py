@@ -118,3 +118,29 @@ def test_modal_predict_and_preclass(name):
         dec = model.impute(pres[i].transform(G[f'data{i}']).astype(np.float32), i, to)
         got = pres[to].inverse_transform(dec)
         assert rel(got, G[f'pred{i}']) < 2e-5
+
+
+def test_metrics_oracle_against_the_reference_functions():
+    """oracle/metrics_oracle.py against values the unmodified reference's own evaluation functions produced
+    (tests/golden/metrics.npz, written by tests/golden/make_metrics.py: jamie.evaluation.test_closer / test_LabelTA, the
+    JAMIE class methods with their default k, sklearn r_regression per feature)."""
+    import json
+    import os
+    from oracle import metrics_oracle as MO
+    from tests.golden_util import GOLDEN_DIR
+    G = np.load(os.path.join(GOLDEN_DIR, 'metrics.npz'))
+    meta = json.loads(str(G['meta']))
+    for c, rec in enumerate(meta):
+        e0, e1, y0, y1 = (G[f'c{c}/{k}'] for k in ('e0', 'e1', 'y0', 'y1'))
+        if 'foscttm' in rec:
+            assert MO.test_closer([e0, e1], verbose=False) == rec['foscttm'] == rec['foscttm_method']
+        for k in (1, 5, 17):
+            assert MO.test_LabelTA([e0, e1], [y0, y1], k=k, verbose=False) == rec[f'lta_k{k}']
+        acc, kdef = MO.label_transfer_accuracy([e0, e1], [y0, y1], k=None, return_k=True)
+        assert kdef == rec['k_default'] and acc == rec['lta_default']
+        with np.errstate(all='ignore'):
+            r = MO.imputation_correlation(G[f'c{c}/x'], G[f'c{c}/y'])
+        want = G[f'c{c}/r']
+        keep = np.isfinite(want)
+        assert not keep[5] and keep.sum() == 11
+        np.testing.assert_allclose(r[keep], want[keep], atol=1e-6)      # r_regression works in the inputs' float32
